@@ -1,0 +1,528 @@
+// plan_driver.cc -- a plain client of "supersonic/supersonic.h" (see ssplan.h).
+//
+// Nothing in this file knows which implementation it is linked against: the
+// include path decides (the reference tree, or supersonic_b200/host/include).
+//
+// Plan grammar (S-expressions; atoms are bare words, numbers or "quoted"):
+//   operation :=
+//     (scan N)                                   ScanView(tables[N])
+//     (compute EXPR OP)                          Compute
+//     (filter EXPR PROJ OP)                      Filter
+//     (project PROJ OP)                          Project
+//     (group PROJ (aggs AGG...) OP)              GroupAggregate
+//     (scalar_agg (aggs AGG...) OP)              ScalarAggregate
+//     (hash_join INNER|LEFT_OUTER PROJ PROJ MPROJ UNIQUE|NOT_UNIQUE OP OP)
+//     (sort (order (NAME ASC|DESC)...) PROJ OP)  Sort
+//   AGG   := (SUM|MIN|MAX|COUNT|FIRST|LAST in out [TYPE]) | (distinct FN in out)
+//   PROJ  := (all) | (all PREFIX) | (named N...) | (at I...) | (rename (N A)...) | (cat PROJ...)
+//   MPROJ := (multi (SRC PROJ)...)
+//   EXPR  := (col NAME) | (at I) | (i32 V) (i64 V) (u32 V) (u64 V) (f32 V) (f64 V)
+//          | (bool V) (date V) (datetime V) | (null TYPE) | (sequence)
+//          | (OP1 EXPR) | (OP2 EXPR EXPR) | (if EXPR EXPR EXPR) | (nulling_if EXPR EXPR EXPR)
+//          | (cast TYPE EXPR) | (as NAME EXPR) | (case EXPR...) | (in EXPR EXPR...)
+//          | (compound EXPR|(as NAME EXPR)...)
+#include "ssplan.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "supersonic/supersonic.h"
+
+namespace {
+
+using namespace supersonic;  // NOLINT
+
+// ------------------------------------------------------------------ s-expr
+struct Sx {
+  bool atom;
+  std::string text;
+  std::vector<Sx> kids;
+  Sx() : atom(false) {}
+};
+
+struct ParseError {
+  std::string msg;
+};
+
+class SxParser {
+ public:
+  explicit SxParser(const char* s) : p_(s) {}
+  Sx Parse() {
+    Sx r = ParseOne();
+    Skip();
+    if (*p_) throw ParseError{"trailing characters in plan"};
+    return r;
+  }
+
+ private:
+  void Skip() {
+    while (*p_ == ' ' || *p_ == '\n' || *p_ == '\t' || *p_ == '\r') ++p_;
+  }
+  Sx ParseOne() {
+    Skip();
+    Sx r;
+    if (*p_ == '(') {
+      ++p_;
+      for (;;) {
+        Skip();
+        if (!*p_) throw ParseError{"unbalanced '('"};
+        if (*p_ == ')') { ++p_; break; }
+        r.kids.push_back(ParseOne());
+      }
+      return r;
+    }
+    r.atom = true;
+    if (*p_ == '"') {
+      ++p_;
+      while (*p_ && *p_ != '"') r.text.push_back(*p_++);
+      if (*p_ != '"') throw ParseError{"unterminated string"};
+      ++p_;
+      return r;
+    }
+    while (*p_ && *p_ != ' ' && *p_ != '(' && *p_ != ')' && *p_ != '\n' && *p_ != '\t') {
+      r.text.push_back(*p_++);
+    }
+    if (r.text.empty()) throw ParseError{"empty atom"};
+    return r;
+  }
+  const char* p_;
+};
+
+const std::string& Head(const Sx& s) {
+  if (s.atom || s.kids.empty() || !s.kids[0].atom) throw ParseError{"expected (head ...)"};
+  return s.kids[0].text;
+}
+
+const std::string& Atom(const Sx& s) {
+  if (!s.atom) throw ParseError{"expected atom"};
+  return s.text;
+}
+
+void Arity(const Sx& s, size_t n) {
+  if (s.kids.size() != n + 1) {
+    throw ParseError{"wrong number of arguments for '" + Head(s) + "'"};
+  }
+}
+
+DataType ParseType(const std::string& t) {
+  if (t == "INT32") return INT32;
+  if (t == "INT64") return INT64;
+  if (t == "UINT32") return UINT32;
+  if (t == "UINT64") return UINT64;
+  if (t == "FLOAT") return FLOAT;
+  if (t == "DOUBLE") return DOUBLE;
+  if (t == "BOOL") return BOOL;
+  if (t == "DATE") return DATE;
+  if (t == "DATETIME") return DATETIME;
+  throw ParseError{"unknown type '" + t + "'"};
+}
+
+// ------------------------------------------------------------------ builders
+const Expression* BuildExpr(const Sx& s);
+
+typedef const Expression* (*Unary)(const Expression*);
+typedef const Expression* (*Binary)(const Expression*, const Expression*);
+
+Unary FindUnary(const std::string& h) {
+  if (h == "negate") return &Negate;
+  if (h == "not") return &Not;
+  if (h == "is_null") return &IsNull;
+  if (h == "bitwise_not") return &BitwiseNot;
+  if (h == "is_odd") return &IsOdd;
+  if (h == "is_even") return &IsEven;
+  return NULL;
+}
+
+Binary FindBinary(const std::string& h) {
+  if (h == "plus") return &Plus;
+  if (h == "minus") return &Minus;
+  if (h == "multiply") return &Multiply;
+  if (h == "divide_signaling") return &DivideSignaling;
+  if (h == "divide_nulling") return &DivideNulling;
+  if (h == "divide_quiet") return &DivideQuiet;
+  if (h == "cpp_divide_signaling") return &CppDivideSignaling;
+  if (h == "cpp_divide_nulling") return &CppDivideNulling;
+  if (h == "modulus_signaling") return &ModulusSignaling;
+  if (h == "modulus_nulling") return &ModulusNulling;
+  if (h == "equal") return &Equal;
+  if (h == "not_equal") return &NotEqual;
+  if (h == "less") return &Less;
+  if (h == "less_or_equal") return &LessOrEqual;
+  if (h == "greater") return &Greater;
+  if (h == "greater_or_equal") return &GreaterOrEqual;
+  if (h == "and") return &And;
+  if (h == "or") return &Or;
+  if (h == "and_not") return &AndNot;
+  if (h == "xor") return &Xor;
+  if (h == "bitwise_and") return &BitwiseAnd;
+  if (h == "bitwise_or") return &BitwiseOr;
+  if (h == "bitwise_xor") return &BitwiseXor;
+  if (h == "bitwise_and_not") return &BitwiseAndNot;
+  if (h == "shift_left") return &ShiftLeft;
+  if (h == "shift_right") return &ShiftRight;
+  if (h == "if_null") return &IfNull;
+  return NULL;
+}
+
+const Expression* BuildExpr(const Sx& s) {
+  const std::string& h = Head(s);
+  if (h == "col") { Arity(s, 1); return NamedAttribute(Atom(s.kids[1])); }
+  if (h == "at") { Arity(s, 1); return AttributeAt(atoi(Atom(s.kids[1]).c_str())); }
+  if (h == "i32") { Arity(s, 1); return ConstInt32(static_cast<int32>(strtoll(Atom(s.kids[1]).c_str(), NULL, 0))); }
+  if (h == "i64") { Arity(s, 1); return ConstInt64(strtoll(Atom(s.kids[1]).c_str(), NULL, 0)); }
+  if (h == "u32") { Arity(s, 1); return ConstUint32(static_cast<uint32>(strtoull(Atom(s.kids[1]).c_str(), NULL, 0))); }
+  if (h == "u64") { Arity(s, 1); return ConstUint64(strtoull(Atom(s.kids[1]).c_str(), NULL, 0)); }
+  if (h == "f32") { Arity(s, 1); return ConstFloat(strtof(Atom(s.kids[1]).c_str(), NULL)); }
+  if (h == "f64") { Arity(s, 1); return ConstDouble(strtod(Atom(s.kids[1]).c_str(), NULL)); }
+  if (h == "bool") { Arity(s, 1); return ConstBool(Atom(s.kids[1]) == "true" || Atom(s.kids[1]) == "1"); }
+  if (h == "date") { Arity(s, 1); return ConstDate(static_cast<int32>(strtoll(Atom(s.kids[1]).c_str(), NULL, 0))); }
+  if (h == "datetime") { Arity(s, 1); return ConstDateTime(strtoll(Atom(s.kids[1]).c_str(), NULL, 0)); }
+  if (h == "null") { Arity(s, 1); return Null(ParseType(Atom(s.kids[1]))); }
+  if (h == "sequence") { Arity(s, 0); return Sequence(); }
+  if (h == "cast") { Arity(s, 2); return CastTo(ParseType(Atom(s.kids[1])), BuildExpr(s.kids[2])); }
+  if (h == "as") { Arity(s, 2); return Alias(Atom(s.kids[1]), BuildExpr(s.kids[2])); }
+  if (h == "if") {
+    Arity(s, 3);
+    return If(BuildExpr(s.kids[1]), BuildExpr(s.kids[2]), BuildExpr(s.kids[3]));
+  }
+  if (h == "nulling_if") {
+    Arity(s, 3);
+    return NullingIf(BuildExpr(s.kids[1]), BuildExpr(s.kids[2]), BuildExpr(s.kids[3]));
+  }
+  if (h == "case") {
+    std::unique_ptr<ExpressionList> list(new ExpressionList);
+    for (size_t i = 1; i < s.kids.size(); ++i) list->add(BuildExpr(s.kids[i]));
+    return Case(list.release());
+  }
+  if (h == "in") {
+    if (s.kids.size() < 3) throw ParseError{"in needs a needle and a haystack"};
+    const Expression* needle = BuildExpr(s.kids[1]);
+    std::unique_ptr<ExpressionList> list(new ExpressionList);
+    for (size_t i = 2; i < s.kids.size(); ++i) list->add(BuildExpr(s.kids[i]));
+    return In(needle, list.release());
+  }
+  if (h == "compound") {
+    std::unique_ptr<CompoundExpression> c(new CompoundExpression);
+    for (size_t i = 1; i < s.kids.size(); ++i) {
+      const Sx& k = s.kids[i];
+      if (Head(k) == "as") {
+        Arity(k, 2);
+        c->AddAs(Atom(k.kids[1]), BuildExpr(k.kids[2]));
+      } else {
+        c->Add(BuildExpr(k));
+      }
+    }
+    return c.release();
+  }
+  if (Unary u = FindUnary(h)) { Arity(s, 1); return u(BuildExpr(s.kids[1])); }
+  if (Binary b = FindBinary(h)) {
+    Arity(s, 2);
+    const Expression* l = BuildExpr(s.kids[1]);
+    return b(l, BuildExpr(s.kids[2]));
+  }
+  throw ParseError{"unknown expression '" + h + "'"};
+}
+
+const SingleSourceProjector* BuildProjector(const Sx& s) {
+  const std::string& h = Head(s);
+  if (h == "all") {
+    if (s.kids.size() == 1) return ProjectAllAttributes();
+    Arity(s, 1);
+    return ProjectAllAttributes(Atom(s.kids[1]));
+  }
+  if (h == "named" || h == "at" || h == "rename" || h == "cat") {
+    std::unique_ptr<CompoundSingleSourceProjector> c(new CompoundSingleSourceProjector);
+    for (size_t i = 1; i < s.kids.size(); ++i) {
+      const Sx& k = s.kids[i];
+      if (h == "named") {
+        c->add(ProjectNamedAttribute(Atom(k)));
+      } else if (h == "at") {
+        c->add(ProjectAttributeAt(atoi(Atom(k).c_str())));
+      } else if (h == "rename") {
+        if (k.atom || k.kids.size() != 2) throw ParseError{"rename takes (NAME ALIAS) pairs"};
+        c->add(ProjectNamedAttributeAs(Atom(k.kids[0]), Atom(k.kids[1])));
+      } else {
+        c->add(BuildProjector(k));
+      }
+    }
+    return c.release();
+  }
+  throw ParseError{"unknown projector '" + h + "'"};
+}
+
+const MultiSourceProjector* BuildMultiProjector(const Sx& s) {
+  if (Head(s) != "multi") throw ParseError{"expected (multi (SRC PROJ)...)"};
+  std::unique_ptr<CompoundMultiSourceProjector> c(new CompoundMultiSourceProjector);
+  for (size_t i = 1; i < s.kids.size(); ++i) {
+    const Sx& k = s.kids[i];
+    if (k.atom || k.kids.size() != 2) throw ParseError{"multi takes (SRC PROJ) pairs"};
+    c->add(atoi(Atom(k.kids[0]).c_str()), BuildProjector(k.kids[1]));
+  }
+  return c.release();
+}
+
+Aggregation ParseAggregation(const std::string& a) {
+  if (a == "SUM") return SUM;
+  if (a == "MIN") return MIN;
+  if (a == "MAX") return MAX;
+  if (a == "COUNT") return COUNT;
+  if (a == "FIRST") return FIRST;
+  if (a == "LAST") return LAST;
+  throw ParseError{"unknown aggregation '" + a + "'"};
+}
+
+AggregationSpecification* BuildAggs(const Sx& s) {
+  if (Head(s) != "aggs") throw ParseError{"expected (aggs ...)"};
+  std::unique_ptr<AggregationSpecification> spec(new AggregationSpecification);
+  for (size_t i = 1; i < s.kids.size(); ++i) {
+    const Sx& k = s.kids[i];
+    const std::string& h = Head(k);
+    if (h == "distinct") {
+      Arity(k, 3);
+      spec->AddDistinctAggregation(ParseAggregation(Atom(k.kids[1])), Atom(k.kids[2]),
+                                   Atom(k.kids[3]));
+    } else if (k.kids.size() == 4) {
+      spec->AddAggregationWithDefinedOutputType(ParseAggregation(h), Atom(k.kids[1]),
+                                                Atom(k.kids[2]), ParseType(Atom(k.kids[3])));
+    } else {
+      Arity(k, 2);
+      spec->AddAggregation(ParseAggregation(h), Atom(k.kids[1]), Atom(k.kids[2]));
+    }
+  }
+  return spec.release();
+}
+
+struct Inputs {
+  std::vector<View> views;
+};
+
+Operation* BuildOp(const Sx& s, const Inputs& in) {
+  const std::string& h = Head(s);
+  if (h == "scan") {
+    Arity(s, 1);
+    size_t n = static_cast<size_t>(atoi(Atom(s.kids[1]).c_str()));
+    if (n >= in.views.size()) throw ParseError{"scan: no such table"};
+    return ScanView(in.views[n]);
+  }
+  if (h == "compute") {
+    Arity(s, 2);
+    const Expression* e = BuildExpr(s.kids[1]);
+    return Compute(e, BuildOp(s.kids[2], in));
+  }
+  if (h == "filter") {
+    Arity(s, 3);
+    const Expression* e = BuildExpr(s.kids[1]);
+    const SingleSourceProjector* p = BuildProjector(s.kids[2]);
+    return Filter(e, p, BuildOp(s.kids[3], in));
+  }
+  if (h == "project") {
+    Arity(s, 2);
+    const SingleSourceProjector* p = BuildProjector(s.kids[1]);
+    return Project(p, BuildOp(s.kids[2], in));
+  }
+  if (h == "group") {
+    Arity(s, 3);
+    const SingleSourceProjector* p = BuildProjector(s.kids[1]);
+    AggregationSpecification* a = BuildAggs(s.kids[2]);
+    return GroupAggregate(p, a, NULL, BuildOp(s.kids[3], in));
+  }
+  if (h == "scalar_agg") {
+    Arity(s, 2);
+    AggregationSpecification* a = BuildAggs(s.kids[1]);
+    return ScalarAggregate(a, BuildOp(s.kids[2], in));
+  }
+  if (h == "hash_join") {
+    Arity(s, 7);
+    const std::string& jt = Atom(s.kids[1]);
+    JoinType join_type;
+    if (jt == "INNER") join_type = INNER;
+    else if (jt == "LEFT_OUTER") join_type = LEFT_OUTER;
+    else if (jt == "RIGHT_OUTER") join_type = RIGHT_OUTER;
+    else if (jt == "FULL_OUTER") join_type = FULL_OUTER;
+    else throw ParseError{"unknown join type"};
+    const SingleSourceProjector* lk = BuildProjector(s.kids[2]);
+    const SingleSourceProjector* rk = BuildProjector(s.kids[3]);
+    const MultiSourceProjector* rp = BuildMultiProjector(s.kids[4]);
+    const std::string& u = Atom(s.kids[5]);
+    if (u != "UNIQUE" && u != "NOT_UNIQUE") throw ParseError{"unknown key uniqueness"};
+    Operation* l = BuildOp(s.kids[6], in);
+    Operation* r = BuildOp(s.kids[7], in);
+    return new HashJoinOperation(join_type, lk, rk, rp, u == "UNIQUE" ? UNIQUE : NOT_UNIQUE, l, r);
+  }
+  if (h == "sort") {
+    Arity(s, 3);
+    if (Head(s.kids[1]) != "order") throw ParseError{"expected (order ...)"};
+    std::unique_ptr<SortOrder> order(new SortOrder);
+    for (size_t i = 1; i < s.kids[1].kids.size(); ++i) {
+      const Sx& k = s.kids[1].kids[i];
+      if (k.atom || k.kids.size() != 2) throw ParseError{"order takes (NAME ASC|DESC) pairs"};
+      const std::string& d = Atom(k.kids[1]);
+      if (d != "ASC" && d != "DESC") throw ParseError{"order direction must be ASC or DESC"};
+      order->add(ProjectNamedAttribute(Atom(k.kids[0])), d == "ASC" ? ASCENDING : DESCENDING);
+    }
+    const SingleSourceProjector* p = BuildProjector(s.kids[2]);
+    return Sort(order.release(), p, static_cast<size_t>(1) << 40, BuildOp(s.kids[3], in));
+  }
+  throw ParseError{"unknown operation '" + h + "'"};
+}
+
+double WallNow() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+}  // namespace
+
+struct ssplan_result {
+  int code;
+  std::string error;
+  struct Col {
+    std::string name;
+    int dtype;
+    int nullable;
+    size_t width;
+    bool saw_nulls;
+    std::vector<char> data;
+    std::vector<uint8_t> is_null;
+  };
+  std::vector<Col> cols;
+  int64_t rows;
+  double create_s, drain_s;
+  int64_t next_calls;
+  ssplan_result() : code(0), rows(0), create_s(0), drain_s(0), next_calls(0) {}
+};
+
+extern "C" {
+
+int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
+               int64_t next_max_rows, int32_t flags, ssplan_result** out) {
+  ssplan_result* r = new ssplan_result;
+  *out = r;
+  Inputs in;
+  for (int t = 0; t < ntables; ++t) {
+    TupleSchema schema;
+    for (int c = 0; c < tables[t].ncols; ++c) {
+      const ssplan_column& col = tables[t].cols[c];
+      if (!schema.add_attribute(Attribute(col.name, static_cast<DataType>(col.dtype),
+                                          col.nullable ? NULLABLE : NOT_NULLABLE))) {
+        r->code = ERROR_ATTRIBUTE_EXISTS;
+        r->error = "duplicate input column name";
+        return r->code;
+      }
+    }
+    View v(schema);
+    v.set_row_count(tables[t].rows);
+    for (int c = 0; c < tables[t].ncols; ++c) {
+      const ssplan_column& col = tables[t].cols[c];
+      v.mutable_column(c)->Reset(col.data, reinterpret_cast<const bool*>(col.is_null));
+    }
+    in.views.push_back(v);
+  }
+
+  std::unique_ptr<Operation> op;
+  try {
+    Sx sx = SxParser(plan).Parse();
+    op.reset(BuildOp(sx, in));
+  } catch (const ParseError& e) {
+    r->code = ERROR_BAD_PROTO;
+    r->error = "plan parse error: " + e.msg;
+    return r->code;
+  }
+
+  double t0 = WallNow();
+  FailureOrOwned<Cursor> created = op->CreateCursor();
+  r->create_s = WallNow() - t0;
+  if (created.is_failure()) {
+    r->code = created.exception().return_code();
+    r->error = created.exception().message();
+    return r->code;
+  }
+  std::unique_ptr<Cursor> cursor(created.release());
+
+  const TupleSchema& schema = cursor->schema();
+  r->cols.resize(schema.attribute_count());
+  for (int c = 0; c < schema.attribute_count(); ++c) {
+    const Attribute& a = schema.attribute(c);
+    r->cols[c].name = a.name();
+    r->cols[c].dtype = a.type();
+    r->cols[c].nullable = a.is_nullable() ? 1 : 0;
+    r->cols[c].width = GetTypeInfo(a.type()).size();
+    r->cols[c].saw_nulls = false;
+    if (a.type() == STRING || a.type() == BINARY) {
+      r->code = ERROR_NOT_IMPLEMENTED;
+      r->error = "plan driver returns fixed-width columns only";
+      return r->code;
+    }
+  }
+
+  const rowcount_t max_rows =
+      next_max_rows > 0 ? static_cast<rowcount_t>(next_max_rows) : Cursor::kDefaultRowCount;
+  t0 = WallNow();
+  for (;;) {
+    ResultView rv = cursor->Next(max_rows);
+    ++r->next_calls;
+    if (rv.is_failure()) {
+      r->code = rv.exception().return_code();
+      r->error = rv.exception().message();
+      break;
+    }
+    if (!rv.has_data()) {
+      if (rv.is_eos()) break;
+      r->code = WAITING_ON_BARRIER;
+      r->error = "unexpected WAITING_ON_BARRIER";
+      break;
+    }
+    const View& v = rv.view();
+    const size_t n = v.row_count();
+    if (!(flags & SSPLAN_DISCARD)) {
+      for (size_t c = 0; c < r->cols.size(); ++c) {
+        ssplan_result::Col& col = r->cols[c];
+        const char* src = static_cast<const char*>(v.column(c).data().raw());
+        col.data.insert(col.data.end(), src, src + n * col.width);
+        const bool* nulls = v.column(c).is_null();
+        if (nulls != NULL) {
+          if (!col.saw_nulls) {
+            col.is_null.assign(r->rows, 0);
+            col.saw_nulls = true;
+          }
+          const uint8_t* nb = reinterpret_cast<const uint8_t*>(nulls);
+          col.is_null.insert(col.is_null.end(), nb, nb + n);
+        } else if (col.saw_nulls) {
+          col.is_null.insert(col.is_null.end(), n, 0);
+        }
+      }
+    }
+    r->rows += n;
+  }
+  r->drain_s = WallNow() - t0;
+  return r->code;
+}
+
+int ssplan_result_code(const ssplan_result* r) { return r->code; }
+const char* ssplan_result_error(const ssplan_result* r) { return r->error.c_str(); }
+int32_t ssplan_result_ncols(const ssplan_result* r) { return static_cast<int32_t>(r->cols.size()); }
+int64_t ssplan_result_rows(const ssplan_result* r) { return r->rows; }
+const char* ssplan_result_col_name(const ssplan_result* r, int32_t i) { return r->cols[i].name.c_str(); }
+int32_t ssplan_result_col_dtype(const ssplan_result* r, int32_t i) { return r->cols[i].dtype; }
+int32_t ssplan_result_col_nullable(const ssplan_result* r, int32_t i) { return r->cols[i].nullable; }
+const void* ssplan_result_col_data(const ssplan_result* r, int32_t i) { return r->cols[i].data.data(); }
+const uint8_t* ssplan_result_col_is_null(const ssplan_result* r, int32_t i) {
+  return r->cols[i].saw_nulls ? r->cols[i].is_null.data() : NULL;
+}
+double ssplan_result_create_seconds(const ssplan_result* r) { return r->create_s; }
+double ssplan_result_drain_seconds(const ssplan_result* r) { return r->drain_s; }
+int64_t ssplan_result_next_calls(const ssplan_result* r) { return r->next_calls; }
+void ssplan_result_free(ssplan_result* r) { delete r; }
+
+#ifndef SSPLAN_IMPL_NAME
+#define SSPLAN_IMPL_NAME "reference"
+#endif
+const char* ssplan_impl(void) { return SSPLAN_IMPL_NAME; }
+
+}  // extern "C"

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- filter+project (BASELINE config 2) on N B200s, one rank per GPU.
+
+Workload (SURVEY.md section 8d, config C2 variant A): synthetic 8 x INT64 table generated
+in HBM by the counter-based generator (seed 42); the plan is
+    Filter(d < 2^19, project e, Compute({e := a*b + c, d}, ScanView(table)))
+One "step" = one pass of the fused kernel over the rank's whole shard (rows per GPU fixed:
+weak scaling; Compute/Filter rows are independent, so ranks share nothing and no collective
+is on the data path).
+
+Printed JSON (rank 0): value = rows/s over all ranks with inputs resident in HBM;
+roofline = algorithmic bytes (32 B read + 8 B written per kept row) / kernel time against the
+measured HBM peak; e2e = the same plan through the supersonic.h mirror with pinned HOST
+buffers (H2D + kernel + D2H inside the timed region); cpu_baseline = the unmodified
+reference (oracle/_ref) on a bounded sample, single thread (the engine is single-threaded).
+--impl reference times the reference's own CPU path on all host cores instead.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PLAN = ("(filter (less (col d) (i64 524288)) (named e) (compute (compound "
+        "(as e (plus (multiply (col a) (col b)) (col c))) (col d)) (scan 0)))")
+SEED = 42
+K_SEL = 1 << 19
+# column generators: (kind, lo, span) -- a,b in [-2^31,2^31), c in [-2^62,2^62), d in [0,2^20)
+GEN = {"a": (0, -(1 << 31), 1 << 32), "b": (0, -(1 << 31), 1 << 32), "c": (0, -(1 << 62), 1 << 63),
+       "d": (0, 0, 1 << 20), "e": (0, 0, 0), "f": (0, 0, 0), "g": (0, 0, 0), "h": (0, 0, 0)}
+COLS = "abcdefgh"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.lines, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_program(capi, ctx):
+    """Bound DAG of the plan: e = a*b + c ; predicate d < K. Inputs: a, b, c, d."""
+    n = capi.node
+    I64, BOOL = capi.INT64, capi.BOOL
+    nodes = [n(capi.OP_INPUT, I64, [0]), n(capi.OP_INPUT, I64, [1]), n(capi.OP_INPUT, I64, [2]),
+             n(capi.OP_INPUT, I64, [3]), n(capi.OP_MUL, I64, [0, 1]), n(capi.OP_ADD, I64, [4, 2]),
+             n(capi.OP_CONST, I64, [], i64=K_SEL), n(capi.OP_LT, BOOL, [3, 6])]
+    return capi.Program(ctx, nodes, [I64] * 4, [0] * 4, [5], predicate=7)
+
+
+def host_column(capi, name, rows, first_row=0):
+    kind, lo, span = GEN[name]
+    out = np.empty(rows, dtype=np.int64)
+    capi.load().ssb_generate_host(out.ctypes.data, rows, first_row, SEED, COLS.index(name), kind, lo, span)
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from supersonic_b200 import capi, ssplan
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    rows = args.rows
+    prog = build_program(capi, ctx)
+    # --- resident inputs: this rank's row range of the global table
+    first = rank * rows
+    d_cols = {}
+    for name in COLS:
+        d_cols[name] = ctx.malloc(rows * 8 + 256)
+        kind, lo, span = GEN[name]
+        ctx.generate(d_cols[name], rows, first, SEED, COLS.index(name), kind, lo, span)
+    d_out = ctx.malloc(rows * 8 + 256)
+    d_count = ctx.malloc(8)
+    ctx.sync()
+    inputs = [(d_cols[c], None, capi.INT64) for c in "abcd"]
+    outputs = [(d_out, None, capi.INT64)]
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ctx.enable_timing(True)
+    for _ in range(args.warmup):
+        prog.run(inputs, rows, outputs, d_count)
+    ctx.sync()
+    launches0 = ctx.launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    kernel_ms = []
+    ctx.timer_start()
+    for _ in range(args.steps):
+        prog.run(inputs, rows, outputs, d_count)
+        if args.per_kernel_timing:
+            kernel_ms.append(ctx.last_kernel_ms())
+    total_ms = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches() - launches0
+    kept = np.zeros(1, dtype=np.int64)
+    ctx.d2h(kept, d_count)
+    if not args.per_kernel_timing:
+        # average launch duration of the dominant kernel from the event pair around each launch
+        for _ in range(3):
+            prog.run(inputs, rows, outputs, d_count)
+            kernel_ms.append(ctx.last_kernel_ms())
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        k = torch.tensor([float(kept[0])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(k, op=dist.ReduceOp.SUM)
+        kept_total = int(k.item())
+    else:
+        kept_total = int(kept[0])
+    ms_per_step = total_ms / args.steps
+    value = world * rows / (ms_per_step * 1e-3)
+
+    result = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        sel = kept_total / float(world * rows)
+        alg_bytes = rows * (32.0 + 8.0 * sel)
+        k_ms = float(np.mean(kernel_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        result = {
+            "metric": "rows/sec, filter+project (Compute a*b+c, Filter d<K) over 8xINT64 rows resident in HBM",
+            "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "C2 variant A: Filter(d<2^19, project e, Compute(e=a*b+c, d)) over a %d-row "
+                                   "8xINT64 table per GPU (4 columns read, selectivity 0.5)" % rows,
+                       "rows_per_gpu": rows, "selectivity": sel, "l2": "inputs (%.1f GB per step) larger than L2"
+                       % (rows * 32 / 1e9), "parallelism": "row-range shards, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "expr_kernel<256,4>", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_row": 32.0 + 8.0 * sel},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "kept_rows": kept_total,
+        }
+    # ---- end to end through the supersonic.h mirror with pinned host buffers (rank 0 rows only)
+    e2e_rows = min(args.e2e_rows, rows)
+    host = {}
+    for name in "abcd":
+        p = ctx.malloc_host(e2e_rows * 8)
+        arr = np.ctypeslib.as_array((C.c_int64 * e2e_rows).from_address(p))
+        arr[:] = host_column(capi, name, e2e_rows, first)
+        host[name] = (p, arr)
+    plan_lib = ssplan.PlanLib(os.path.join(ROOT, "supersonic_b200", "lib", "libssb200_plan.so"))
+    cols = [ssplan.Column(nm, ssplan.INT64, host[nm][1]) for nm in "abcd"]
+    for c, nm in zip(cols, "abcd"):
+        c.data = host[nm][1]            # keep the pinned buffer (no numpy copy)
+    e2e_s = []
+    e2e_kept = 0
+    for i in range(1 + args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        r = plan_lib.run(PLAN, [cols], next_max_rows=1 << 22, flags=ssplan.SSPLAN_DISCARD)
+        dt = time.perf_counter() - t0
+        if r.code != 0:
+            raise RuntimeError("e2e plan failed: %d %s" % (r.code, r.error))
+        e2e_kept = r.rows
+        if i > 0:
+            e2e_s.append(dt)
+    e2e_t = float(np.mean(e2e_s))
+    if world > 1:
+        t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    if rank == 0:
+        result["e2e"] = {"value": world * e2e_rows / e2e_t, "unit": "rows/s", "rows_per_gpu": e2e_rows,
+                         "h2d_bytes_per_step": int(e2e_rows * 32), "d2h_bytes_per_step": int(e2e_kept * 8),
+                         "api": "supersonic::Filter/Compute/ScanView cursors via the plan driver, pinned host views"}
+        # ---- CPU baseline: the reference itself, one thread, bounded sample
+        result["cpu_baseline"] = cpu_reference_sample(args.cpu_rows, threads=1)
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ref_worker(arg):
+    rows, first = arg
+    from supersonic_b200 import capi, ssplan
+    ref = ssplan.PlanLib(os.path.join(ROOT, "oracle", "_ref", "libssref.so"))
+    cols = [ssplan.Column(nm, ssplan.INT64, host_column(capi, nm, rows, first)) for nm in "abcd"]
+    best = None
+    for _ in range(3):
+        r = ref.run(PLAN, [cols], next_max_rows=1024, flags=ssplan.SSPLAN_DISCARD)
+        if r.code != 0:
+            raise RuntimeError(r.error)
+        best = r.drain_seconds if best is None else min(best, r.drain_seconds)
+    return rows, best, r.rows
+
+
+def cpu_reference_sample(rows, threads):
+    """Times the unmodified reference (oracle/_ref/libssref.so) over `rows` rows per thread."""
+    import multiprocessing as mp
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libssref.so")
+    if not os.path.exists(ref_path):
+        return {"value": None, "unit": "rows/s", "cores": threads, "kind": "reference",
+                "sample": "oracle/_ref/libssref.so missing"}
+    t0 = time.perf_counter()
+    if threads == 1:
+        res = [_ref_worker((rows, 0))]
+        wall = res[0][1]
+    else:
+        with mp.get_context("fork").Pool(threads) as pool:
+            res = pool.map(_ref_worker, [(rows, i * rows) for i in range(threads)])
+        wall = max(r[1] for r in res)
+    total = sum(r[0] for r in res)
+    return {"value": total / wall, "unit": "rows/s", "cores": threads, "kind": "reference",
+            "sample": "%d rows per thread of the same plan, Next(1024) drain, best of 3, wall %.2fs"
+                      % (rows, time.perf_counter() - t0)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    args.cpu_rows = max(1 << 20, min(args.cpu_rows, 400_000_000 // cores))   # bounded memory and time
+    values = []
+    base = None
+    for _ in range(max(1, args.steps)):
+        base = cpu_reference_sample(args.cpu_rows, threads=cores)
+        values.append(base["value"])
+    v = float(np.mean(values))
+    out = {"impl": "reference", "metric": "rows/sec, filter+project (Compute a*b+c, Filter d<K) over 8xINT64 rows",
+           "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": cores * args.cpu_rows / v * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+           "config": {"workload": "C2 variant A plan on the reference's CPU cursors: %d independent single-thread "
+                                  "cursors (the engine is single-threaded), %d rows each" % (cores, args.cpu_rows)},
+           "cpu_baseline": dict(base, value=v),
+           "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (BASELINE C2: 1e9)")
+    ap.add_argument("--e2e-rows", type=int, default=1 << 26)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-rows", type=int, default=20_000_000)
+    ap.add_argument("--per-kernel-timing", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

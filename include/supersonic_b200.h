@@ -1,0 +1,254 @@
+/* supersonic_b200.h -- C ABI of libssb200.so, the B200 (sm_100a) implementation of
+ * Supersonic's vectorised columnar execution hot path.
+ *
+ * The reference (google/supersonic) has no FFI: its seam is the set of C++ factory
+ * functions and virtual interfaces of supersonic.h. This
+ * header is the thin C boundary *underneath* that seam: every entry point names the
+ * reference interface it replaces (file:line under /root/reference/supersonic).
+ * The C++ mirror of supersonic.h that calls it lives in supersonic_b200/host/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types
+ *  - every function returns a supersonic::ReturnCode value (proto/supersonic.proto:40-82):
+ *    0 OK, 102 ERROR_MEMORY_EXCEEDED, 103 ERROR_NOT_IMPLEMENTED, 104 ERROR_EVALUATION_ERROR,
+ *    405 ERROR_INVALID_ARGUMENT_TYPE, 407 ERROR_INVALID_ARGUMENT_VALUE, 100 unknown/CUDA error;
+ *    ssb_last_error(ctx) holds the message of the last failure on that context
+ *  - all device work is ordered on the context's stream; calls that return a count to
+ *    the host synchronise that stream, the others are asynchronous
+ *  - column data live in HBM as SoA: one typed array per column plus an optional
+ *    is_null BITMAP (bit i of 32-bit word i/32 set = row i is NULL). The reference's
+ *    in-memory format is one bool per row (base/infrastructure/bit_pointers.h:528-534);
+ *    ssb_nulls_pack/unpack convert at the boundary only
+ *  - there is no CPU fallback anywhere behind this header
+ */
+#ifndef SUPERSONIC_B200_H_
+#define SUPERSONIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+/* supersonic::DataType numbering (proto/supersonic.proto:15-37). Fixed-width types only. */
+enum {
+  SSB_INT32 = 1, SSB_INT64 = 2, SSB_UINT64 = 3, SSB_DATETIME = 4, SSB_DOUBLE = 5, SSB_BOOL = 6,
+  SSB_UINT32 = 8, SSB_FLOAT = 9, SSB_DATE = 10, SSB_ENUM = 13
+};
+
+enum {
+  SSB_OK = 0, SSB_ERROR_UNKNOWN = 100, SSB_ERROR_MEMORY_EXCEEDED = 102,
+  SSB_ERROR_NOT_IMPLEMENTED = 103, SSB_ERROR_EVALUATION_ERROR = 104,
+  SSB_ERROR_INVALID_ARGUMENT_TYPE = 405, SSB_ERROR_INVALID_ARGUMENT_VALUE = 407
+};
+
+typedef struct ssb_ctx ssb_ctx;
+
+/* A column resident in HBM. `data` must be 16-byte aligned for the TMA path (any
+ * cudaMalloc'ed pointer is); other alignments run on the plain-load path.
+ * Replaces supersonic::Column (base/infrastructure/block.h:55-192). */
+typedef struct {
+  void* data;
+  uint32_t* nulls;   /* bitmap, or NULL = no NULLs in this column */
+  int32_t dtype;     /* SSB_* */
+  int32_t reserved;
+} ssb_column;
+
+/* ------------------------------------------------------------------ context */
+/* One context = one device + one stream + a workspace pool. Plays the role of the
+ * BufferAllocator seam (base/memory/memory.h:100-236) for device memory. */
+int ssb_ctx_create(int device, ssb_ctx** out);
+void ssb_ctx_destroy(ssb_ctx* ctx);
+const char* ssb_last_error(const ssb_ctx* ctx);
+void* ssb_ctx_stream(ssb_ctx* ctx);              /* cudaStream_t */
+int ssb_ctx_sync(ssb_ctx* ctx);
+int ssb_abi_version(void);
+/* Number of kernels launched by this library on the context since creation. */
+int64_t ssb_ctx_launch_count(const ssb_ctx* ctx);
+/* Device time (ms, CUDA events on the context stream) of the most recent ssb_program_run /
+ * ssb_group_update / ssb_join_probe / ssb_sort_permutation call; valid after a sync. */
+int ssb_ctx_last_kernel_ms(ssb_ctx* ctx, float* ms);
+int ssb_ctx_enable_timing(ssb_ctx* ctx, int enable);
+/* A stopwatch on the context stream (CUDA events): start records, stop records, waits and
+ * returns the device time between the two in milliseconds. */
+int ssb_ctx_timer_start(ssb_ctx* ctx);
+int ssb_ctx_timer_stop(ssb_ctx* ctx, float* ms);
+
+int ssb_malloc(ssb_ctx* ctx, size_t bytes, void** out);
+int ssb_free(ssb_ctx* ctx, void* ptr);
+int ssb_malloc_host(ssb_ctx* ctx, size_t bytes, void** out);   /* pinned */
+int ssb_free_host(ssb_ctx* ctx, void* ptr);
+int ssb_memcpy_h2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
+int ssb_memcpy_d2h(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
+int ssb_memset(ssb_ctx* ctx, void* dst, int value, size_t bytes);            /* async */
+/* 1 when `ptr` is device memory, 0 for host memory (pageable or pinned). Lets ScanView accept
+ * views over either (cursor/core/scan_view.h:35 takes any readable pointer). */
+int ssb_pointer_is_device(const void* ptr);
+
+/* bool-per-row (device) <-> bitmap (device). rows may be any value; the bitmap must
+ * hold ceil(rows/32) words. Boundary conversion for bit_pointers.h:528-534. */
+int ssb_nulls_pack(ssb_ctx* ctx, const uint8_t* d_bools, int64_t rows, uint32_t* d_bitmap);
+int ssb_nulls_unpack(ssb_ctx* ctx, const uint32_t* d_bitmap, int64_t rows, uint8_t* d_bools);
+
+/* Counter-based synthetic column generator, identical on host and device:
+ * value(i) = splitmix64(seed ^ (stream * 0x9E3779B97F4A7C15) + i), then
+ * kind 0: INT64 uniform in [lo, lo + span)   (span a power of two, or 0 = full 64 bit)
+ * kind 1: INT64 u mod span + lo
+ * kind 2: DOUBLE (u >> 44) * 2^-10           (exactly summable payload)
+ * kind 3: DOUBLE (u >> 11) * 2^-53           (uniform [0,1)) */
+int ssb_generate(ssb_ctx* ctx, void* d_out, int64_t rows, int64_t first_row, uint64_t seed,
+                 uint64_t stream, int kind, int64_t lo, uint64_t span);
+void ssb_generate_host(void* out, int64_t rows, int64_t first_row, uint64_t seed,
+                       uint64_t stream, int kind, int64_t lo, uint64_t span);
+
+/* ------------------------------------------------------------------ expressions */
+/* Bound (fully typed) expression DAG, children before parents. This is what the
+ * reference's Bound* factories produce as a tree of BoundExpression objects
+ * (expression/templated/abstract_bound_expressions.h:63-230); here the whole tree is
+ * handed over so that one kernel evaluates it. All type promotion has already been
+ * done by the caller (explicit SSB_OP_CAST nodes), exactly as
+ * expression/templated/bound_expression_factory.cc:44-123 inserts casts at bind time. */
+enum {
+  SSB_OP_INPUT = 1,        /* arg[0] = input column index */
+  SSB_OP_CONST = 2,        /* imm; flags & SSB_NODE_NULL = typed NULL constant */
+  SSB_OP_CAST = 3,         /* child type -> out_type (operators.h:50-57, C++ conversion) */
+  SSB_OP_DATE_TO_DATETIME = 4,  /* operators.h:59-61 */
+  SSB_OP_NEGATE = 10,      /* operators.h:63-71 (UINT32/UINT64 -> INT64) */
+  SSB_OP_ADD = 11, SSB_OP_SUB = 12, SSB_OP_MUL = 13,   /* operators.h:73-86 */
+  SSB_OP_DIV = 14,         /* C++ '/' on the (common) operand type, operators.h:88-91 */
+  SSB_OP_MOD = 15,         /* C++ '%'; FLOAT/DOUBLE operands: int64 % int64, operators.h:93-106 */
+  SSB_OP_IS_ODD = 16, SSB_OP_IS_EVEN = 17,             /* operators.h:108-128 */
+  SSB_OP_EQ = 20, SSB_OP_NE = 21, SSB_OP_LT = 22, SSB_OP_LE = 23, SSB_OP_GT = 24,
+  SSB_OP_GE = 25,          /* operators.h:185-294 incl. the mixed signed/unsigned overloads */
+  SSB_OP_AND = 30, SSB_OP_OR = 31, SSB_OP_XOR = 32, SSB_OP_AND_NOT = 33, SSB_OP_NOT = 34,
+                           /* SQL three-valued logic, elementary_bound_expressions.cc:270-506 */
+  SSB_OP_BIT_AND = 40, SSB_OP_BIT_OR = 41, SSB_OP_BIT_XOR = 42, SSB_OP_BIT_AND_NOT = 43,
+  SSB_OP_BIT_NOT = 44, SSB_OP_SHL = 45, SSB_OP_SHR = 46,  /* operators.h:150-183 */
+  SSB_OP_IS_NULL = 50,     /* elementary_bound_expressions.cc:58-100 */
+  SSB_OP_IF_NULL = 51,     /* arg0 unless NULL, else arg1 */
+  SSB_OP_IF = 52,          /* arg0 ? arg1 : arg2; NULL condition selects arg2 */
+  SSB_OP_NULLING_IF = 53   /* as IF, NULL condition gives NULL */
+};
+
+enum {
+  SSB_NODE_NULL = 1,            /* CONST: the constant is NULL */
+  SSB_NODE_ZERO_NULLS = 2,      /* DIV/MOD: divisor == 0 -> result NULL (…Nulling variants) */
+  SSB_NODE_ZERO_FAILS = 4       /* DIV/MOD: divisor == 0 -> ERROR_EVALUATION_ERROR (…Signaling) */
+};
+
+typedef struct {
+  int32_t op;          /* SSB_OP_* */
+  int32_t out_type;    /* SSB_* type of the node's value */
+  int32_t arg[3];      /* child node indices (< own index), -1 = unused */
+  int32_t flags;       /* SSB_NODE_* */
+  union { int64_t i64; uint64_t u64; double f64; float f32; int32_t i32; uint32_t u32; uint8_t b; } imm;
+} ssb_expr_node;
+
+typedef struct ssb_program ssb_program;
+
+/* Compiles an expression DAG into one fused kernel configuration.
+ *   outputs[j]   node whose value becomes output column j (Compute / Project;
+ *                cursor/core/compute.cc:49-56, project.cc:49-59)
+ *   predicate    node index of a BOOL predicate or -1. With a predicate the run is a
+ *                Filter (cursor/core/filter.cc:96-230): rows where the predicate is
+ *                true and not NULL are kept, in input order.
+ * input_nullable[i] != 0 declares that input column i may carry a null bitmap. */
+int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes,
+                       int32_t n_inputs, const int32_t* input_types,
+                       const int32_t* input_nullable,
+                       const int32_t* outputs, int32_t n_outputs, int32_t predicate,
+                       ssb_program** out);
+void ssb_program_destroy(ssb_program* prog);
+int32_t ssb_program_output_type(const ssb_program* prog, int32_t j);
+int32_t ssb_program_output_nullable(const ssb_program* prog, int32_t j);
+/* Bytes of HBM traffic the algorithm needs per input row / per output row (roofline). */
+int32_t ssb_program_bytes_per_input_row(const ssb_program* prog);
+int32_t ssb_program_bytes_per_output_row(const ssb_program* prog);
+
+/* Runs the program over `rows` rows. outputs[j].data must hold `rows` elements (Filter
+ * may keep every row); outputs[j].nulls must be non-NULL (ceil(rows/32)+1 words) when
+ * ssb_program_output_nullable(j). d_out_rows (device int64, may be NULL without a
+ * predicate) receives the number of rows written. Asynchronous. */
+int ssb_program_run(ssb_program* prog, const ssb_column* inputs, int64_t rows,
+                    const ssb_column* outputs, int64_t* d_out_rows);
+/* Same, then waits and returns the count on the host; 104 if a signaling op failed. */
+int ssb_program_run_sync(ssb_program* prog, const ssb_column* inputs, int64_t rows,
+                         const ssb_column* outputs, int64_t* out_rows);
+/* After a sync: 0, or 104 if any ZERO_FAILS node saw a zero divisor since the last check. */
+int ssb_program_check_failure(ssb_program* prog);
+
+/* ------------------------------------------------------------------ group-by */
+/* Replaces GroupAggregateCursor / RowHashSet / Aggregator (cursor/core/aggregate_groups.cc:
+ * 332-433, cursor/infrastructure/row_hash_set.cc:458-518, cursor/core/aggregator.cc:206-221,
+ * column_aggregator.cc:108-226). supersonic::Aggregation numbering (supersonic.proto:91-99). */
+enum { SSB_AGG_SUM = 0, SSB_AGG_MIN = 1, SSB_AGG_MAX = 2, SSB_AGG_COUNT = 3,
+       SSB_AGG_FIRST = 5, SSB_AGG_LAST = 6 };
+
+typedef struct {
+  int32_t fn;          /* SSB_AGG_* */
+  int32_t input;       /* index into the `values` array of ssb_group_update, -1 = COUNT(*) */
+  int32_t in_type;     /* SSB_* of the input column (ignored for COUNT(*)) */
+  int32_t out_type;    /* SSB_* of the result (SUM/MIN/MAX: numeric; COUNT: UINT64 ...) */
+  int32_t in_nullable; /* input column may carry a null bitmap */
+  int32_t reserved;
+} ssb_agg_spec;
+
+typedef struct ssb_group ssb_group;
+
+/* n_keys == 0 gives ScalarAggregate (cursor/core/aggregate_scalar.cc:40-90): one group. */
+int ssb_group_create(ssb_ctx* ctx, int32_t n_keys, const int32_t* key_types,
+                     const int32_t* key_nullable, int32_t n_aggs, const ssb_agg_spec* aggs,
+                     int64_t expected_groups, ssb_group** out);
+void ssb_group_destroy(ssb_group* g);
+/* Accumulates `rows` rows; may be called repeatedly (row order across calls = call order). */
+int ssb_group_update(ssb_group* g, const ssb_column* keys, const ssb_column* values,
+                     int64_t rows);
+/* Compacts the table into dense result columns owned by `g` (valid until destroy or the
+ * next update). Synchronises. A NULL key is a group of its own (row_hash_set.cc:81-90);
+ * an aggregate over only-NULL inputs is NULL (column_aggregator.cc:108-125). */
+int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb_column* agg_out);
+/* Adds the groups of a finalized `src` table (same specification) into `dst`: the merge
+ * step of the row-range sharded aggregate. Both on the same device. */
+int ssb_group_merge(ssb_group* dst, int64_t n_groups, const ssb_column* key_cols,
+                    const ssb_column* agg_cols);
+
+/* ------------------------------------------------------------------ hash join */
+/* Replaces HashIndexOnMaterializedCursor + ResultCursor (cursor/core/hash_join.cc:604-625,
+ * 707-831) and RowHashSet/RowHashMultiSet (row_hash_set.cc:424-608). */
+enum { SSB_JOIN_INNER = 0, SSB_JOIN_LEFT_OUTER = 1 };
+enum { SSB_KEYS_NOT_UNIQUE = 0, SSB_KEYS_UNIQUE = 1 };
+
+typedef struct ssb_join ssb_join;
+
+/* Builds the index over the rhs key columns (rows with a NULL key column never match,
+ * hash_join.cc:67-76,616-617). The key columns must stay valid while the index lives. */
+int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows,
+                   int32_t uniqueness, ssb_join** out);
+void ssb_join_destroy(ssb_join* j);
+/* Probes with the lhs key columns; the result is the list of (lhs row, rhs row) pairs in
+ * lhs order and, per lhs row, rhs insertion order (hash_join.cc:793-831). LEFT_OUTER emits
+ * rhs row -1 for unmatched lhs rows. Pair buffers are owned by `j` (valid until the next
+ * probe). Synchronises to return the count. */
+int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type,
+                   int64_t* n_pairs, const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
+
+/* dst[i] = src[idx[i]]; idx[i] < 0 -> NULL (base/infrastructure/copy_column.cc:112-127,
+ * 200-286). dst.nulls may be NULL when neither src.nulls nor negative indices occur. */
+int ssb_gather(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64_t n,
+               const ssb_column* dst);
+
+/* ------------------------------------------------------------------ sort */
+/* Replaces SortPermutation / SortTypedColumn (cursor/core/sort.cc:150-322,781-805): writes
+ * the permutation that sorts `rows` rows by the key columns (first key most significant;
+ * descending[k] != 0 = DESCENDING; ASCENDING puts NULLs first, DESCENDING last,
+ * sort.cc:174-238). Stable (the reference is not: ties may differ). */
+int ssb_sort_permutation(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys,
+                         const int32_t* descending, int64_t rows, int64_t* d_perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SUPERSONIC_B200_H_ */

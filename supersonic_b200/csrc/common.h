@@ -1,0 +1,75 @@
+// common.h -- context object and helpers shared by the translation units of libssb200.so.
+#ifndef SSB_CSRC_COMMON_H_
+#define SSB_CSRC_COMMON_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/supersonic_b200.h"
+#include "ops.h"
+
+struct ssb_ctx {
+  int device;
+  cudaStream_t stream;
+  int num_sms;
+  size_t smem_optin;          // max dynamic shared memory per block
+  std::string last_error;
+  int64_t launches;
+  bool timing;
+  cudaEvent_t ev0, ev1;
+  cudaEvent_t tm0, tm1;       // user stopwatch
+  bool ev_valid;
+  // reusable device scratch (grown on demand)
+  void* scratch;
+  size_t scratch_bytes;
+  int32_t* d_fail;            // failure flag of signaling ops
+  int64_t* d_count;           // one int64 result slot
+  int64_t* h_count;           // pinned mirror
+  int32_t* h_fail;            // pinned mirror
+};
+
+namespace ssb {
+
+int fail(ssb_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(ssb_ctx* ctx, cudaError_t e, const char* what);
+// Returns the context scratch buffer, at least `bytes` large (contents undefined).
+int scratch(ssb_ctx* ctx, size_t bytes, void** out);
+
+#define SSB_CUDA(ctx, call)                                          \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) return ::ssb::cuda_fail((ctx), e_, #call); \
+  } while (0)
+
+struct TimedRegion {
+  explicit TimedRegion(ssb_ctx* c) : ctx(c) {
+    if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
+  }
+  ~TimedRegion() {
+    if (ctx->timing) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_valid = true; }
+  }
+  ssb_ctx* ctx;
+};
+
+// SSB_* dtype -> physical type, or -1.
+inline int phys_of(int dtype) {
+  switch (dtype) {
+    case SSB_INT32: case SSB_DATE: case SSB_ENUM: return T_I32;
+    case SSB_INT64: case SSB_DATETIME: return T_I64;
+    case SSB_UINT32: return T_U32;
+    case SSB_UINT64: return T_U64;
+    case SSB_FLOAT: return T_F32;
+    case SSB_DOUBLE: return T_F64;
+    case SSB_BOOL: return T_B8;
+    default: return -1;
+  }
+}
+inline int width_of(int dtype) { int p = phys_of(dtype); return p < 0 ? 0 : phys_width(p); }
+
+inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace ssb
+#endif  // SSB_CSRC_COMMON_H_

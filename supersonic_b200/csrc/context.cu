@@ -1,0 +1,263 @@
+// context.cu -- context, device memory, null-vector conversion and the synthetic generator.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "common.h"
+
+namespace ssb {
+
+int fail(ssb_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+int cuda_fail(ssb_ctx* ctx, cudaError_t e, const char* what) {
+  std::string msg = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();
+  return fail(ctx, e == cudaErrorMemoryAllocation ? SSB_ERROR_MEMORY_EXCEEDED : SSB_ERROR_UNKNOWN, msg);
+}
+
+int scratch(ssb_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes) {
+    if (ctx->scratch) {
+      SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      SSB_CUDA(ctx, cudaFree(ctx->scratch));
+      ctx->scratch = nullptr;
+      ctx->scratch_bytes = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    SSB_CUDA(ctx, cudaMalloc(&ctx->scratch, want));
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->scratch;
+  return 0;
+}
+
+// bool per row -> bitmap: each warp packs 32 rows with one ballot.
+__global__ void pack_nulls_kernel(const uint8_t* __restrict__ bools, long long rows,
+                                  uint32_t* __restrict__ bitmap) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long rows_up = (rows + 31) & ~31LL;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows_up; i += stride) {
+    const bool v = i < rows && bools[i] != 0;
+    const uint32_t w = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) bitmap[i >> 5] = w;
+  }
+}
+
+__global__ void unpack_nulls_kernel(const uint32_t* __restrict__ bitmap, long long rows,
+                                    uint8_t* __restrict__ bools) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    bools[i] = (bitmap[i >> 5] >> (i & 31)) & 1u;
+  }
+}
+
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__host__ __device__ inline uint64_t gen_value(uint64_t seed, uint64_t stream, uint64_t row, int kind,
+                                              int64_t lo, uint64_t span) {
+  const uint64_t u = splitmix64((seed ^ (stream * 0x9E3779B97F4A7C15ull)) + row);
+  switch (kind) {
+    case 0: return static_cast<uint64_t>(lo) + (span ? (u & (span - 1)) : u);
+    case 1: return static_cast<uint64_t>(lo) + (u % span);
+    case 2: { double d = static_cast<double>(u >> 44) * (1.0 / 1024.0); uint64_t b; memcpy(&b, &d, 8); return b; }
+    default: { double d = static_cast<double>(u >> 11) * (1.0 / 9007199254740992.0); uint64_t b; memcpy(&b, &d, 8); return b; }
+  }
+}
+
+__global__ void generate_kernel(uint64_t* __restrict__ out, long long rows, long long first_row,
+                                uint64_t seed, uint64_t stream, int kind, int64_t lo, uint64_t span) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    out[i] = gen_value(seed, stream, static_cast<uint64_t>(first_row + i), kind, lo, span);
+  }
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+extern "C" {
+
+int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+
+int ssb_ctx_create(int device, ssb_ctx** out) {
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return SSB_ERROR_UNKNOWN;   // no CUDA device: there is no fallback
+  }
+  ssb_ctx* ctx = new ssb_ctx;
+  ctx->device = device;
+  ctx->launches = 0;
+  ctx->timing = false;
+  ctx->ev_valid = false;
+  ctx->scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return SSB_ERROR_UNKNOWN; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (prop.major < 10) {
+    fprintf(stderr, "libssb200: device %d is sm_%d%d; this library carries sm_100a code only\n",
+            device, prop.major, prop.minor);
+    delete ctx;
+    return SSB_ERROR_NOT_IMPLEMENTED;
+  }
+  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->tm0);
+  cudaEventCreate(&ctx->tm1);
+  cudaMalloc(&ctx->d_fail, sizeof(int32_t));
+  cudaMalloc(&ctx->d_count, sizeof(int64_t));
+  cudaMemset(ctx->d_fail, 0, sizeof(int32_t));
+  cudaMallocHost(&ctx->h_count, sizeof(int64_t));
+  cudaMallocHost(&ctx->h_fail, sizeof(int32_t));
+  if (cudaGetLastError() != cudaSuccess) { delete ctx; return SSB_ERROR_UNKNOWN; }
+  *out = ctx;
+  return 0;
+}
+
+void ssb_ctx_destroy(ssb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  cudaFree(ctx->d_fail);
+  cudaFree(ctx->d_count);
+  cudaFreeHost(ctx->h_count);
+  cudaFreeHost(ctx->h_fail);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->tm0);
+  cudaEventDestroy(ctx->tm1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* ssb_last_error(const ssb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+void* ssb_ctx_stream(ssb_ctx* ctx) { return ctx->stream; }
+int64_t ssb_ctx_launch_count(const ssb_ctx* ctx) { return ctx->launches; }
+
+int ssb_ctx_sync(ssb_ctx* ctx) {
+  SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int ssb_ctx_enable_timing(ssb_ctx* ctx, int enable) {
+  ctx->timing = enable != 0;
+  ctx->ev_valid = false;
+  return 0;
+}
+
+int ssb_ctx_last_kernel_ms(ssb_ctx* ctx, float* ms) {
+  if (!ctx->timing || !ctx->ev_valid) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "no timed region recorded");
+  SSB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  SSB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+int ssb_ctx_timer_start(ssb_ctx* ctx) {
+  SSB_CUDA(ctx, cudaEventRecord(ctx->tm0, ctx->stream));
+  return 0;
+}
+int ssb_ctx_timer_stop(ssb_ctx* ctx, float* ms) {
+  SSB_CUDA(ctx, cudaEventRecord(ctx->tm1, ctx->stream));
+  SSB_CUDA(ctx, cudaEventSynchronize(ctx->tm1));
+  SSB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
+  return 0;
+}
+
+int ssb_malloc(ssb_ctx* ctx, size_t bytes, void** out) {
+  *out = nullptr;
+  SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+  SSB_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+int ssb_free(ssb_ctx* ctx, void* ptr) {
+  if (ptr) SSB_CUDA(ctx, cudaFree(ptr));
+  return 0;
+}
+int ssb_malloc_host(ssb_ctx* ctx, size_t bytes, void** out) {
+  *out = nullptr;
+  SSB_CUDA(ctx, cudaMallocHost(out, bytes ? bytes : 1));
+  return 0;
+}
+int ssb_free_host(ssb_ctx* ctx, void* ptr) {
+  if (ptr) SSB_CUDA(ctx, cudaFreeHost(ptr));
+  return 0;
+}
+int ssb_memcpy_h2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int ssb_memcpy_d2h(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+int ssb_memset(ssb_ctx* ctx, void* dst, int value, size_t bytes) {
+  if (bytes) SSB_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+  return 0;
+}
+
+int ssb_pointer_is_device(const void* ptr) {
+  if (ptr == nullptr) return 0;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return attr.type == cudaMemoryTypeDevice ? 1 : 0;
+}
+
+static unsigned grid_for(ssb_ctx* ctx, int64_t n, int block) {
+  int64_t g = div_up(n, block);
+  const int64_t cap = static_cast<int64_t>(ctx->num_sms) * 8;
+  if (g > cap) g = cap;
+  return static_cast<unsigned>(g < 1 ? 1 : g);
+}
+
+int ssb_nulls_pack(ssb_ctx* ctx, const uint8_t* d_bools, int64_t rows, uint32_t* d_bitmap) {
+  if (rows <= 0) return 0;
+  pack_nulls_kernel<<<grid_for(ctx, rows, 256), 256, 0, ctx->stream>>>(d_bools, rows, d_bitmap);
+  ++ctx->launches;
+  SSB_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int ssb_nulls_unpack(ssb_ctx* ctx, const uint32_t* d_bitmap, int64_t rows, uint8_t* d_bools) {
+  if (rows <= 0) return 0;
+  unpack_nulls_kernel<<<grid_for(ctx, rows, 256), 256, 0, ctx->stream>>>(d_bitmap, rows, d_bools);
+  ++ctx->launches;
+  SSB_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int ssb_generate(ssb_ctx* ctx, void* d_out, int64_t rows, int64_t first_row, uint64_t seed,
+                 uint64_t stream, int kind, int64_t lo, uint64_t span) {
+  if (rows <= 0) return 0;
+  if (kind == 1 && span == 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "kind 1 needs a span");
+  if (kind == 0 && (span & (span - 1))) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "kind 0 needs a power-of-two span");
+  generate_kernel<<<grid_for(ctx, rows, 256), 256, 0, ctx->stream>>>(
+      static_cast<uint64_t*>(d_out), rows, first_row, seed, stream, kind, lo, span);
+  ++ctx->launches;
+  SSB_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+void ssb_generate_host(void* out, int64_t rows, int64_t first_row, uint64_t seed, uint64_t stream,
+                       int kind, int64_t lo, uint64_t span) {
+  uint64_t* o = static_cast<uint64_t*>(out);
+  for (int64_t i = 0; i < rows; ++i) {
+    o[i] = gen_value(seed, stream, static_cast<uint64_t>(first_row + i), kind, lo, span);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,798 @@
+// group.cu -- GroupAggregate / ScalarAggregate on the GPU.
+//
+// Replaces the reference's chain (per 1024-row block, one thread)
+//   RowHashSetImpl::InsertUnique  (cursor/infrastructure/row_hash_set.cc:458-518)
+//   Aggregator::UpdateAggregations -> ColumnAggregatorImpl::UpdateAggregation
+//                                    (cursor/core/aggregator.cc:206-221, column_aggregator.cc:108-226)
+// by an open-addressed hash table in HBM (L2-resident for the headline sizes):
+//   * slot claim by atomicCAS on a 64-bit key word (single-column keys) or on a state word
+//     with the key columns stored beside it (multi-column keys)
+//   * accumulators are 8-byte words per (slot, aggregate) updated with L2 atomics
+//     (atomicAdd on u64 / double, atomicMin/Max, CAS loops for floating MIN/MAX)
+//   * when few groups exist, rows of one warp that hit the same slot are combined with
+//     __match_any_sync + shuffles first, so an atomic is issued per distinct slot per warp
+//   * rows that find no free slot within the probe limit are appended to a deferred list; the
+//     host grows the table (re-inserting the old slots) and replays only those rows, so every
+//     row is accumulated exactly once
+// NULL is a group key of its own (row_hash_set.cc:81-90); an aggregate whose inputs were all
+// NULL is NULL (column_aggregator.cc:108-125); COUNT never is.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "common.h"
+
+namespace ssb {
+
+enum { kMaxKeys = 8, kMaxAggs = 16, kProbeLimit = 96 };
+static constexpr unsigned long long kEmptyKey = ~0ull;
+
+struct AggDev {
+  int32_t fn;            // SSB_AGG_*
+  int32_t in_phys;       // physical type of the input column (-1: COUNT(*))
+  int32_t out_phys;      // physical type of the accumulator / result
+  int32_t in_nullable;
+  const void* in_data;
+  const uint32_t* in_nulls;
+  unsigned long long* acc;   // [capacity + 2]
+  uint32_t* seen;            // [capacity + 2] or NULL (input not nullable and not merging)
+};
+
+struct GroupParams {
+  int32_t n_keys, n_aggs;
+  int32_t packed;            // single key column stored in the slot word
+  int32_t merge;             // inputs are partial aggregates (COUNT adds its input)
+  int32_t warp_combine;      // combine equal slots inside a warp before the atomics
+  int32_t key_phys[kMaxKeys];
+  const void* key_data[kMaxKeys];
+  const uint32_t* key_nulls[kMaxKeys];
+  // table
+  unsigned long long capacity;       // power of two; special slots: capacity (EMPTY key), capacity+1 (NULL key)
+  unsigned long long* slot_key;      // packed: key word; generic: unused
+  uint32_t* slot_state;              // generic: 0 empty, 1 being written, 2 ready; packed: special-slot flags
+  unsigned long long* key_store[kMaxKeys];   // generic: stored key values per column [capacity]
+  uint32_t* key_store_null;          // generic: bit c set = key column c is NULL [capacity]
+  unsigned long long* n_groups;
+  AggDev agg[kMaxAggs];
+  // rows
+  long long rows;
+  const long long* row_index;        // replay of deferred rows, or NULL
+  long long* deferred;
+  unsigned long long* n_deferred;
+};
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+
+__device__ __forceinline__ unsigned long long load_raw(const void* base, int phys, long long i) {
+  switch (phys_width(phys)) {
+    case 8: return static_cast<const unsigned long long*>(base)[i];
+    case 4: return static_cast<const uint32_t*>(base)[i];
+    default: return static_cast<const uint8_t*>(base)[i];
+  }
+}
+__device__ __forceinline__ bool bit_at(const uint32_t* bm, long long i) {
+  return bm != nullptr && ((bm[i >> 5] >> (i & 31)) & 1u);
+}
+
+// value of physical type `from` converted (C++ conversion) into a container of type `to`
+__device__ __forceinline__ unsigned long long convert_value(unsigned long long v, int from, int to) {
+  if (from == to) return v;
+  Insn in;
+  in.kind = K_ALU1; in.mop = M_CAST; in.t = static_cast<uint8_t>(from); in.t2 = static_cast<uint8_t>(to);
+  in.flags = 0; in.rhs_nullable = 0; in.rw = 0; in.a = 0; in.b = 0; in.pad2 = 0;
+  u64 acc[1] = {v}, rhs[1] = {0}, rhs2[1] = {0};
+  uint32_t n = 0, fail = 0;
+  alu<1>(in, acc, n, rhs, 0u, rhs2, 0u, 1u, fail);
+  return acc[0];
+}
+
+// ---- slot lookup ---------------------------------------------------------------------------
+// Returns the slot of the row's key, inserting it if new; -1 when the probe limit is hit.
+__device__ __forceinline__ long long find_slot_packed(const GroupParams& p, long long row) {
+  if (p.n_keys == 0) return 0;
+  if (bit_at(p.key_nulls[0], row)) {
+    if (atomicExch(&p.slot_state[1], 1u) == 0u) atomicAdd(p.n_groups, 1ull);
+    return static_cast<long long>(p.capacity + 1);
+  }
+  const unsigned long long key = load_raw(p.key_data[0], p.key_phys[0], row);
+  if (key == kEmptyKey) {
+    if (atomicExch(&p.slot_state[0], 1u) == 0u) atomicAdd(p.n_groups, 1ull);
+    return static_cast<long long>(p.capacity);
+  }
+  const unsigned long long mask = p.capacity - 1;
+  unsigned long long s = mix64(key) & mask;
+  for (int probe = 0; probe < kProbeLimit; ++probe) {
+    unsigned long long cur = p.slot_key[s];
+    if (cur == key) return static_cast<long long>(s);
+    if (cur == kEmptyKey) {
+      const unsigned long long old = atomicCAS(&p.slot_key[s], kEmptyKey, key);
+      if (old == kEmptyKey) { atomicAdd(p.n_groups, 1ull); return static_cast<long long>(s); }
+      if (old == key) return static_cast<long long>(s);
+    }
+    s = (s + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ long long find_slot_generic(const GroupParams& p, long long row) {
+  unsigned long long kv[kMaxKeys];
+  uint32_t knull = 0;
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (int c = 0; c < p.n_keys; ++c) {
+    const bool isn = bit_at(p.key_nulls[c], row);
+    kv[c] = isn ? 0ull : load_raw(p.key_data[c], p.key_phys[c], row);
+    if (isn) knull |= 1u << c;
+    h = mix64(h ^ (kv[c] + (isn ? 0xdeadbabeull : 0ull))) + c;
+  }
+  const unsigned long long mask = p.capacity - 1;
+  unsigned long long s = h & mask;
+  for (int probe = 0; probe < kProbeLimit; ++probe) {
+    uint32_t st = *reinterpret_cast<volatile uint32_t*>(&p.slot_state[s]);
+    if (st == 0u) {
+      const uint32_t old = atomicCAS(&p.slot_state[s], 0u, 1u);
+      if (old == 0u) {
+        for (int c = 0; c < p.n_keys; ++c) p.key_store[c][s] = kv[c];
+        p.key_store_null[s] = knull;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(&p.slot_state[s]) = 2u;
+        atomicAdd(p.n_groups, 1ull);
+        return static_cast<long long>(s);
+      }
+      st = old;
+    }
+    while (st == 1u) st = *reinterpret_cast<volatile uint32_t*>(&p.slot_state[s]);
+    __threadfence();
+    bool same = *reinterpret_cast<volatile uint32_t*>(&p.key_store_null[s]) == knull;
+    for (int c = 0; same && c < p.n_keys; ++c) {
+      same = *reinterpret_cast<volatile unsigned long long*>(&p.key_store[c][s]) == kv[c];
+    }
+    if (same) return static_cast<long long>(s);
+    s = (s + 1) & mask;
+  }
+  return -1;
+}
+
+// ---- accumulation -------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_max_f64(unsigned long long* addr, double v, bool is_min) {
+  unsigned long long old = *addr;
+  for (;;) {
+    const double cur = __longlong_as_double(static_cast<long long>(old));
+    if (is_min ? !(v < cur) : !(cur < v)) return;
+    const unsigned long long prev = atomicCAS(addr, old, static_cast<unsigned long long>(__double_as_longlong(v)));
+    if (prev == old) return;
+    old = prev;
+  }
+}
+__device__ __forceinline__ void atomic_add_f32(unsigned long long* addr, float v) {
+  atomicAdd(reinterpret_cast<float*>(addr), v);   // low 32 bits of the container (little endian)
+}
+__device__ __forceinline__ void atomic_min_max_f32(unsigned long long* addr, float v, bool is_min) {
+  unsigned int* a = reinterpret_cast<unsigned int*>(addr);
+  unsigned int old = *a;
+  for (;;) {
+    const float cur = __uint_as_float(old);
+    if (is_min ? !(v < cur) : !(cur < v)) return;
+    const unsigned int prev = atomicCAS(a, old, __float_as_uint(v));
+    if (prev == old) return;
+    old = prev;
+  }
+}
+
+// Applies one (already converted) value to the accumulator of `slot`.
+__device__ __forceinline__ void apply(const AggDev& a, long long slot, unsigned long long v, unsigned long long count) {
+  unsigned long long* dst = &a.acc[slot];
+  switch (a.fn) {
+    case SSB_AGG_COUNT: atomicAdd(dst, count); break;
+    case SSB_AGG_SUM:
+      if (a.out_phys == T_F64) atomicAdd(reinterpret_cast<double*>(dst), Codec<double>::dec(v));
+      else if (a.out_phys == T_F32) atomic_add_f32(dst, Codec<float>::dec(v));
+      else atomicAdd(dst, a.out_phys == T_I32 ? static_cast<unsigned long long>(static_cast<long long>(Codec<int32_t>::dec(v))) : v);
+      break;
+    case SSB_AGG_MIN:
+    case SSB_AGG_MAX: {
+      const bool is_min = a.fn == SSB_AGG_MIN;
+      switch (a.out_phys) {
+        case T_F64: atomic_min_max_f64(dst, Codec<double>::dec(v), is_min); break;
+        case T_F32: atomic_min_max_f32(dst, Codec<float>::dec(v), is_min); break;
+        case T_I64: { long long x = Codec<int64_t>::dec(v); if (is_min) atomicMin(reinterpret_cast<long long*>(dst), x); else atomicMax(reinterpret_cast<long long*>(dst), x); } break;
+        case T_I32: { long long x = Codec<int32_t>::dec(v); if (is_min) atomicMin(reinterpret_cast<long long*>(dst), x); else atomicMax(reinterpret_cast<long long*>(dst), x); } break;
+        default: if (is_min) atomicMin(dst, v); else atomicMax(dst, v); break;   // U32 / U64 / B8 containers
+      }
+    } break;
+    default: break;
+  }
+}
+
+// Combines two partial values of one aggregate (warp pre-aggregation).
+__device__ __forceinline__ unsigned long long combine(const AggDev& a, unsigned long long x, unsigned long long y) {
+  switch (a.fn) {
+    case SSB_AGG_SUM:
+      if (a.out_phys == T_F64) return Codec<double>::enc(Codec<double>::dec(x) + Codec<double>::dec(y));
+      if (a.out_phys == T_F32) return Codec<float>::enc(Codec<float>::dec(x) + Codec<float>::dec(y));
+      if (a.out_phys == T_I32) return Codec<int32_t>::enc(Arith<int32_t>::add(Codec<int32_t>::dec(x), Codec<int32_t>::dec(y)));
+      return x + y;
+    case SSB_AGG_MIN:
+    case SSB_AGG_MAX: {
+      const bool is_min = a.fn == SSB_AGG_MIN;
+      bool take_y;
+      switch (a.out_phys) {
+        case T_F64: take_y = is_min ? Codec<double>::dec(y) < Codec<double>::dec(x) : Codec<double>::dec(x) < Codec<double>::dec(y); break;
+        case T_F32: take_y = is_min ? Codec<float>::dec(y) < Codec<float>::dec(x) : Codec<float>::dec(x) < Codec<float>::dec(y); break;
+        case T_I64: take_y = is_min ? Codec<int64_t>::dec(y) < Codec<int64_t>::dec(x) : Codec<int64_t>::dec(x) < Codec<int64_t>::dec(y); break;
+        case T_I32: take_y = is_min ? Codec<int32_t>::dec(y) < Codec<int32_t>::dec(x) : Codec<int32_t>::dec(x) < Codec<int32_t>::dec(y); break;
+        default: take_y = is_min ? y < x : x < y; break;
+      }
+      return take_y ? y : x;
+    }
+    default: return x + y;
+  }
+}
+
+__global__ void __launch_bounds__(256) group_update_kernel(const __grid_constant__ GroupParams p) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long rows_up = (p.rows + 31) & ~31LL;   // whole warps stay converged for the shuffles
+  const int lane = threadIdx.x & 31;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows_up; i += stride) {
+    const bool live = i < p.rows;
+    long long row = 0, slot = -2;
+    if (live) {
+      row = p.row_index ? p.row_index[i] : i;
+      slot = p.packed ? find_slot_packed(p, row) : find_slot_generic(p, row);
+      if (slot < 0) {
+        const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+        p.deferred[d] = row;
+      }
+    }
+    const bool active = live && slot >= 0;
+    if (!p.warp_combine) {
+      if (active) {
+        for (int a = 0; a < p.n_aggs; ++a) {
+          const AggDev& ag = p.agg[a];
+          if (ag.in_phys >= 0 && bit_at(ag.in_nulls, row)) continue;
+          unsigned long long v = 0, cnt = 1;
+          if (ag.in_phys >= 0) {
+            v = load_raw(ag.in_data, ag.in_phys, row);
+            if (ag.fn == SSB_AGG_COUNT) { cnt = p.merge ? v : 1ull; }
+            else v = convert_value(v, ag.in_phys, ag.out_phys);
+          }
+          apply(ag, slot, v, cnt);
+          if (ag.seen != nullptr) ag.seen[slot] = 1u;
+        }
+      }
+      continue;
+    }
+    // few groups: one atomic per distinct slot per warp
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    if (amask == 0u) continue;
+    unsigned peers = 0;
+    if (active) peers = __match_any_sync(amask, slot);
+    const bool leader = active && (__ffs(peers) - 1 == lane);
+    for (int a = 0; a < p.n_aggs; ++a) {
+      const AggDev& ag = p.agg[a];
+      const bool has = active && !(ag.in_phys >= 0 && bit_at(ag.in_nulls, row));
+      unsigned long long v = 0, cnt = has ? 1ull : 0ull;
+      if (has && ag.in_phys >= 0) {
+        v = load_raw(ag.in_data, ag.in_phys, row);
+        if (ag.fn == SSB_AGG_COUNT) { cnt = p.merge ? v : 1ull; }
+        else v = convert_value(v, ag.in_phys, ag.out_phys);
+      }
+      // serial over the distinct slots of this warp; each step is a full-warp reduction
+      unsigned remaining = amask;
+      unsigned long long my_v = v, my_c = cnt;
+      bool my_has = has;
+      while (remaining) {
+        const int l = __ffs(remaining) - 1;
+        const unsigned m = __shfl_sync(0xffffffffu, peers, l);
+        const bool in = active && ((m >> lane) & 1u);
+        unsigned long long rv = v, rc = in ? cnt : 0ull;
+        bool rh = in && has;
+        for (int d = 16; d > 0; d >>= 1) {
+          const unsigned long long ov = __shfl_xor_sync(0xffffffffu, rv, d);
+          const unsigned long long oc = __shfl_xor_sync(0xffffffffu, rc, d);
+          const bool oh = __shfl_xor_sync(0xffffffffu, rh ? 1 : 0, d) != 0;
+          if (oh) { rv = rh ? combine(ag, rv, ov) : ov; rh = true; }
+          rc += oc;
+        }
+        if (lane == l) { my_v = rv; my_c = rc; my_has = rh; }
+        remaining &= ~m;
+      }
+      if (leader && my_has) {
+        apply(ag, slot, my_v, my_c);
+        if (ag.seen != nullptr) ag.seen[slot] = 1u;
+      }
+    }
+  }
+}
+
+// ---- finalize: dense result columns ---------------------------------------------------------
+struct FinalizeParams {
+  GroupParams g;
+  unsigned long long total_slots;      // capacity + 2
+  unsigned long long* block_counts;    // [grid]
+  void* key_out[kMaxKeys];
+  uint32_t* key_out_nulls[kMaxKeys];
+  void* agg_out[kMaxAggs];
+  uint32_t* agg_out_nulls[kMaxAggs];
+};
+
+__device__ __forceinline__ bool slot_used(const GroupParams& p, unsigned long long s) {
+  if (p.n_keys == 0) return s == 0;
+  if (p.packed) {
+    if (s < p.capacity) return p.slot_key[s] != kEmptyKey;
+    return p.slot_state[s - p.capacity] != 0u;
+  }
+  return s < p.capacity && p.slot_state[s] == 2u;
+}
+
+__global__ void __launch_bounds__(256) group_count_kernel(const __grid_constant__ FinalizeParams f) {
+  __shared__ unsigned int warp_sum[8];
+  const unsigned long long per_block = (f.total_slots + gridDim.x - 1) / gridDim.x;
+  const unsigned long long begin = per_block * blockIdx.x;
+  unsigned long long end = begin + per_block;
+  if (end > f.total_slots) end = f.total_slots;
+  unsigned int c = 0;
+  for (unsigned long long s = begin + threadIdx.x; s < end; s += blockDim.x) c += slot_used(f.g, s) ? 1u : 0u;
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += warp_sum[w];
+    f.block_counts[blockIdx.x] = t;
+  }
+}
+
+__device__ __forceinline__ void store_typed(void* base, int phys, unsigned long long pos, unsigned long long v) {
+  switch (phys_width(phys)) {
+    case 8: static_cast<unsigned long long*>(base)[pos] = v; break;
+    case 4: static_cast<uint32_t*>(base)[pos] = static_cast<uint32_t>(v); break;
+    default: static_cast<uint8_t*>(base)[pos] = static_cast<uint8_t>(v); break;
+  }
+}
+
+// One block per slot range; positions inside the block come from a block-wide scan so that
+// the output order is the slot order (deterministic for a given table size).
+__global__ void __launch_bounds__(256) group_emit_kernel(const __grid_constant__ FinalizeParams f) {
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned int warp_off[8];
+  const GroupParams& p = f.g;
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    for (unsigned int i = 0; i < blockIdx.x; ++i) b += f.block_counts[i];
+    s_base = b;
+  }
+  __syncthreads();
+  const unsigned long long per_block = (f.total_slots + gridDim.x - 1) / gridDim.x;
+  const unsigned long long begin = per_block * blockIdx.x;
+  unsigned long long end = begin + per_block;
+  if (end > f.total_slots) end = f.total_slots;
+  unsigned long long running = s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned long long s0 = begin; s0 < end; s0 += blockDim.x) {
+    const unsigned long long s = s0 + threadIdx.x;
+    const bool used = s < end && slot_used(p, s);
+    const unsigned m = __ballot_sync(0xffffffffu, used);
+    if (lane == 0) warp_off[warp] = __popc(m);
+    __syncthreads();
+    unsigned int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) before += warp_off[w]; total += warp_off[w]; }
+    if (used) {
+      const unsigned long long pos = running + before + __popc(m & ((1u << lane) - 1u));
+      // keys
+      for (int c = 0; c < p.n_keys; ++c) {
+        unsigned long long kv = 0;
+        bool kn = false;
+        if (p.packed) {
+          if (s < p.capacity) kv = p.slot_key[s];
+          else if (s == p.capacity) kv = kEmptyKey;
+          else kn = true;
+        } else {
+          kv = p.key_store[c][s];
+          kn = (p.key_store_null[s] >> c) & 1u;
+        }
+        store_typed(f.key_out[c], p.key_phys[c], pos, kv);
+        if (kn && f.key_out_nulls[c] != nullptr) atomicOr(&f.key_out_nulls[c][pos >> 5], 1u << (pos & 31));
+      }
+      for (int a = 0; a < p.n_aggs; ++a) {
+        const AggDev& ag = p.agg[a];
+        store_typed(f.agg_out[a], ag.out_phys, pos, ag.acc[s]);
+        const bool isnull = ag.fn != SSB_AGG_COUNT && ag.seen != nullptr && ag.seen[s] == 0u;
+        if (isnull && f.agg_out_nulls[a] != nullptr) atomicOr(&f.agg_out_nulls[a][pos >> 5], 1u << (pos & 31));
+      }
+    }
+    running += total;
+    __syncthreads();
+  }
+}
+
+// Fills a u64 array with a value (accumulator identities, empty keys).
+__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long n, unsigned long long v) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+struct ssb_group {
+  ssb_ctx* ctx;
+  int n_keys, n_aggs;
+  std::vector<int32_t> key_types, key_nullable;
+  std::vector<ssb_agg_spec> aggs;
+  bool packed;
+  unsigned long long capacity;
+  // table storage
+  unsigned long long* slot_key;
+  uint32_t* slot_state;
+  unsigned long long* key_store[kMaxKeys];
+  uint32_t* key_store_null;
+  unsigned long long* acc[kMaxAggs];
+  uint32_t* seen[kMaxAggs];
+  unsigned long long* counters;   // [0] n_groups, [1] n_deferred
+  unsigned long long* h_counters; // pinned
+  long long* deferred;
+  size_t deferred_cap;
+  long long rows_seen;
+  bool merged_any;
+  // result storage
+  void* key_out[kMaxKeys];
+  uint32_t* key_out_nulls[kMaxKeys];
+  void* agg_out[kMaxAggs];
+  uint32_t* agg_out_nulls[kMaxAggs];
+  unsigned long long* block_counts;
+  long long out_capacity;
+};
+
+namespace ssb {
+
+static unsigned long long identity_of(const ssb_agg_spec& a) {
+  const int phys = phys_of(a.out_type);
+  if (a.fn == SSB_AGG_MIN) {
+    switch (phys) {
+      case T_F64: return Codec<double>::enc(__builtin_huge_val());
+      case T_F32: return Codec<float>::enc(__builtin_huge_valf());
+      case T_I64: case T_I32: return static_cast<unsigned long long>(INT64_MAX);
+      default: return ~0ull;
+    }
+  }
+  if (a.fn == SSB_AGG_MAX) {
+    switch (phys) {
+      case T_F64: return Codec<double>::enc(-__builtin_huge_val());
+      case T_F32: return Codec<float>::enc(-__builtin_huge_valf());
+      case T_I64: case T_I32: return static_cast<unsigned long long>(INT64_MIN);
+      default: return 0ull;
+    }
+  }
+  return 0ull;
+}
+
+static void free_table(ssb_group* g) {
+  cudaFree(g->slot_key); g->slot_key = nullptr;
+  cudaFree(g->slot_state); g->slot_state = nullptr;
+  for (int c = 0; c < kMaxKeys; ++c) { cudaFree(g->key_store[c]); g->key_store[c] = nullptr; }
+  cudaFree(g->key_store_null); g->key_store_null = nullptr;
+  for (int a = 0; a < kMaxAggs; ++a) { cudaFree(g->acc[a]); g->acc[a] = nullptr; cudaFree(g->seen[a]); g->seen[a] = nullptr; }
+}
+
+static unsigned fill_grid(ssb_ctx* ctx, unsigned long long n) {
+  unsigned long long g = (n + 255) / 256;
+  const unsigned long long cap = static_cast<unsigned long long>(ctx->num_sms) * 8;
+  return static_cast<unsigned>(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+static int alloc_table(ssb_group* g, unsigned long long capacity) {
+  ssb_ctx* ctx = g->ctx;
+  g->capacity = capacity;
+  const unsigned long long total = capacity + 2;
+  if (g->packed) {
+    SSB_CUDA(ctx, cudaMalloc(&g->slot_key, total * 8));
+    SSB_CUDA(ctx, cudaMemsetAsync(g->slot_key, 0xff, total * 8, ctx->stream));
+    SSB_CUDA(ctx, cudaMalloc(&g->slot_state, 2 * 4));
+    SSB_CUDA(ctx, cudaMemsetAsync(g->slot_state, 0, 2 * 4, ctx->stream));
+  } else {
+    SSB_CUDA(ctx, cudaMalloc(&g->slot_state, total * 4));
+    SSB_CUDA(ctx, cudaMemsetAsync(g->slot_state, 0, total * 4, ctx->stream));
+    for (int c = 0; c < g->n_keys; ++c) SSB_CUDA(ctx, cudaMalloc(&g->key_store[c], total * 8));
+    SSB_CUDA(ctx, cudaMalloc(&g->key_store_null, total * 4));
+  }
+  for (int a = 0; a < g->n_aggs; ++a) {
+    SSB_CUDA(ctx, cudaMalloc(&g->acc[a], total * 8));
+    const unsigned long long id = identity_of(g->aggs[a]);
+    if (id == 0) {
+      SSB_CUDA(ctx, cudaMemsetAsync(g->acc[a], 0, total * 8, ctx->stream));
+    } else {
+      fill_u64_kernel<<<fill_grid(ctx, total), 256, 0, ctx->stream>>>(g->acc[a], total, id);
+      ++ctx->launches;
+    }
+    // `seen` decides NULL-ness of SUM/MIN/MAX results; kept for every non-COUNT aggregate so
+    // that merging partial tables (whose values may be NULL) needs no re-layout
+    if (g->aggs[a].fn != SSB_AGG_COUNT) {
+      SSB_CUDA(ctx, cudaMalloc(&g->seen[a], total * 4));
+      SSB_CUDA(ctx, cudaMemsetAsync(g->seen[a], 0, total * 4, ctx->stream));
+    }
+  }
+  SSB_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+static void fill_table_params(const ssb_group* g, GroupParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->n_keys = g->n_keys;
+  p->n_aggs = g->n_aggs;
+  p->packed = g->packed ? 1 : 0;
+  for (int c = 0; c < g->n_keys; ++c) {
+    p->key_phys[c] = phys_of(g->key_types[c]);
+    p->key_store[c] = g->key_store[c];
+  }
+  p->capacity = g->capacity;
+  p->slot_key = g->slot_key;
+  p->slot_state = g->slot_state;
+  p->key_store_null = g->key_store_null;
+  p->n_groups = &g->counters[0];
+  p->n_deferred = &g->counters[1];
+  for (int a = 0; a < g->n_aggs; ++a) {
+    p->agg[a].fn = g->aggs[a].fn;
+    p->agg[a].in_phys = g->aggs[a].input < 0 ? -1 : phys_of(g->aggs[a].in_type);
+    p->agg[a].out_phys = phys_of(g->aggs[a].out_type);
+    p->agg[a].in_nullable = g->aggs[a].in_nullable;
+    p->agg[a].acc = g->acc[a];
+    p->agg[a].seen = g->seen[a];
+  }
+}
+
+static int read_counters(ssb_group* g) {
+  ssb_ctx* ctx = g->ctx;
+  SSB_CUDA(ctx, cudaMemcpyAsync(g->h_counters, g->counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static unsigned update_grid(ssb_ctx* ctx, long long rows) {
+  long long g = div_up(rows, 256);
+  const long long cap = static_cast<long long>(ctx->num_sms) * 8;
+  return static_cast<unsigned>(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, int64_t rows, bool merge,
+                bool internal);
+
+// Moves every group of the current table into a table of `new_capacity` slots.
+static int grow_table(ssb_group* g, unsigned long long new_capacity) {
+  ssb_ctx* ctx = g->ctx;
+  int64_t n = 0;
+  std::vector<ssb_column> keys(g->n_keys ? g->n_keys : 1), aggs(g->n_aggs ? g->n_aggs : 1);
+  if (int rc = ssb_group_finalize(g, &n, keys.data(), aggs.data())) return rc;
+  // the dense copy must outlive the rebuild: detach it from the group
+  void* key_out[kMaxKeys]; uint32_t* key_nulls[kMaxKeys]; void* agg_out[kMaxAggs]; uint32_t* agg_nulls[kMaxAggs];
+  for (int c = 0; c < kMaxKeys; ++c) { key_out[c] = g->key_out[c]; key_nulls[c] = g->key_out_nulls[c]; g->key_out[c] = nullptr; g->key_out_nulls[c] = nullptr; }
+  for (int a = 0; a < kMaxAggs; ++a) { agg_out[a] = g->agg_out[a]; agg_nulls[a] = g->agg_out_nulls[a]; g->agg_out[a] = nullptr; g->agg_out_nulls[a] = nullptr; }
+  g->out_capacity = 0;
+  // finalize reports NOT-NULL keys / COUNT columns without bitmap; that is what merge expects
+  free_table(g);
+  int rc = alloc_table(g, new_capacity);
+  if (rc == 0) {
+    cudaMemsetAsync(g->counters, 0, 16, ctx->stream);
+    g->h_counters[0] = g->h_counters[1] = 0;
+    if (n > 0 && g->n_keys > 0) rc = feed(g, keys.data(), aggs.data(), n, true, true);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  for (int c = 0; c < kMaxKeys; ++c) { cudaFree(key_out[c]); cudaFree(key_nulls[c]); }
+  for (int a = 0; a < kMaxAggs; ++a) { cudaFree(agg_out[a]); cudaFree(agg_nulls[a]); }
+  return rc;
+}
+
+// One slice: launch, then grow-and-replay until no row is deferred.
+static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows, bool merge) {
+  ssb_ctx* ctx = g->ctx;
+  long long remaining = rows;
+  long long* replay = nullptr;
+  int rc = 0;
+  for (int round = 0; round < 48 && remaining > 0; ++round) {
+    if (g->deferred_cap < static_cast<size_t>(remaining)) {
+      cudaFree(g->deferred);
+      g->deferred = nullptr;
+      g->deferred_cap = 0;
+      cudaError_t e = cudaMalloc(&g->deferred, static_cast<size_t>(remaining) * 8);
+      if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "deferred row list"); break; }
+      g->deferred_cap = static_cast<size_t>(remaining);
+    }
+    GroupParams p;
+    fill_table_params(g, &p);
+    for (int c = 0; c < g->n_keys; ++c) { p.key_data[c] = keys[c].data; p.key_nulls[c] = keys[c].nulls; }
+    for (int a = 0; a < g->n_aggs; ++a) {
+      if (merge) {
+        p.agg[a].in_phys = phys_of(g->aggs[a].out_type);   // partial results carry the output type
+        p.agg[a].in_data = values[a].data;
+        p.agg[a].in_nulls = values[a].nulls;
+      } else if (g->aggs[a].input >= 0) {
+        p.agg[a].in_data = values[g->aggs[a].input].data;
+        p.agg[a].in_nulls = values[g->aggs[a].input].nulls;
+      }
+    }
+    p.merge = merge ? 1 : 0;
+    p.rows = remaining;
+    p.row_index = replay;
+    p.deferred = g->deferred;
+    // Few groups after the first megarow (or a scalar aggregate): combine inside the warp.
+    p.warp_combine = (g->n_keys == 0 || (g->rows_seen >= (1 << 20) && g->h_counters[0] <= 4096)) ? 1 : 0;
+    cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
+    group_update_kernel<<<update_grid(ctx, remaining), 256, 0, ctx->stream>>>(p);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "group_update_kernel"); break; }
+    if ((rc = read_counters(g))) break;
+    const unsigned long long n_def = g->h_counters[1];
+    if (n_def == 0) { remaining = 0; break; }
+    long long* next = nullptr;
+    e = cudaMalloc(&next, n_def * 8);
+    if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "replay list"); break; }
+    cudaMemcpyAsync(next, g->deferred, n_def * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(replay);
+    replay = next;
+    unsigned long long want = g->capacity * 2;
+    while (want < 4 * (g->h_counters[0] + n_def)) want *= 2;
+    if ((rc = grow_table(g, want))) break;
+    remaining = static_cast<long long>(n_def);
+  }
+  if (rc == 0 && remaining > 0) rc = fail(ctx, SSB_ERROR_UNKNOWN, "group-by table did not converge");
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(replay);
+  return rc;
+}
+
+static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, int64_t rows, bool merge,
+                bool internal) {
+  ssb_ctx* ctx = g->ctx;
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  int n_values = 0;
+  for (int a = 0; a < g->n_aggs; ++a) if (g->aggs[a].input >= n_values) n_values = g->aggs[a].input + 1;
+  if (merge) n_values = g->n_aggs;
+  long long offset = 0;
+  while (offset < rows) {
+    long long n = rows - offset;
+    // The first megarow runs alone so that the group count seen so far can pick the strategy.
+    if (!internal && g->rows_seen < (1 << 20) && n > (1 << 20)) n = 1 << 20;
+    ssb_column k2[kMaxKeys], v2[kMaxAggs];
+    for (int c = 0; c < g->n_keys; ++c) {
+      k2[c] = keys[c];
+      k2[c].data = static_cast<char*>(keys[c].data) + static_cast<size_t>(offset) * width_of(keys[c].dtype);
+      if (keys[c].nulls) k2[c].nulls = keys[c].nulls + offset / 32;   // offset is a multiple of 32
+    }
+    for (int v = 0; v < n_values; ++v) {
+      v2[v] = values[v];
+      v2[v].data = static_cast<char*>(values[v].data) + static_cast<size_t>(offset) * width_of(values[v].dtype);
+      if (values[v].nulls) v2[v].nulls = values[v].nulls + offset / 32;
+    }
+    if (int rc = feed_slice(g, k2, v2, n, merge)) return rc;
+    offset += n;
+    if (!internal) g->rows_seen += n;
+  }
+  return 0;
+}
+
+}  // namespace ssb
+
+extern "C" {
+
+int ssb_group_create(ssb_ctx* ctx, int32_t n_keys, const int32_t* key_types, const int32_t* key_nullable,
+                     int32_t n_aggs, const ssb_agg_spec* aggs, int64_t expected_groups, ssb_group** out) {
+  *out = nullptr;
+  if (n_keys < 0 || n_keys > kMaxKeys) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "too many group-by key columns");
+  if (n_aggs < 0 || n_aggs > kMaxAggs) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "too many aggregates");
+  for (int c = 0; c < n_keys; ++c) {
+    if (phys_of(key_types[c]) < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported group-by key type");
+  }
+  for (int a = 0; a < n_aggs; ++a) {
+    const ssb_agg_spec& s = aggs[a];
+    if (s.fn == SSB_AGG_FIRST || s.fn == SSB_AGG_LAST) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "FIRST/LAST aggregates are not implemented on the GPU yet");
+    if (s.fn != SSB_AGG_SUM && s.fn != SSB_AGG_MIN && s.fn != SSB_AGG_MAX && s.fn != SSB_AGG_COUNT) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "unknown aggregate function");
+    if (phys_of(s.out_type) < 0 || (s.input >= 0 && phys_of(s.in_type) < 0)) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported aggregate type");
+    if (s.fn != SSB_AGG_COUNT && s.input < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "aggregate without input");
+    if (s.fn == SSB_AGG_SUM && phys_of(s.out_type) == T_B8) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "SUM of BOOL");
+    if (s.fn == SSB_AGG_COUNT && phys_width(phys_of(s.out_type)) < 4) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "COUNT needs an integer result");
+  }
+  ssb_group* g = new ssb_group();
+  memset(static_cast<void*>(&g->slot_key), 0, sizeof(ssb_group) - offsetof(ssb_group, slot_key));
+  g->ctx = ctx;
+  g->n_keys = n_keys;
+  g->n_aggs = n_aggs;
+  g->key_types.assign(key_types, key_types + n_keys);
+  g->key_nullable.assign(key_nullable, key_nullable + n_keys);
+  g->aggs.assign(aggs, aggs + n_aggs);
+  g->packed = n_keys <= 1;
+  unsigned long long cap = 1ull << 16;
+  if (n_keys == 0) cap = 2;
+  const unsigned long long want = expected_groups > 0 ? static_cast<unsigned long long>(expected_groups) * 2 : (1ull << 20);
+  while (n_keys > 0 && cap < want) cap *= 2;
+  cudaError_t e = cudaMalloc(&g->counters, 16);
+  if (e == cudaSuccess) e = cudaMallocHost(&g->h_counters, 16);
+  if (e != cudaSuccess) { delete g; return cuda_fail(ctx, e, "group counters"); }
+  cudaMemsetAsync(g->counters, 0, 16, ctx->stream);
+  g->h_counters[0] = g->h_counters[1] = 0;
+  if (int rc = alloc_table(g, cap)) { ssb_group_destroy(g); return rc; }
+  *out = g;
+  return 0;
+}
+
+void ssb_group_destroy(ssb_group* g) {
+  if (!g) return;
+  cudaStreamSynchronize(g->ctx->stream);
+  free_table(g);
+  cudaFree(g->counters);
+  cudaFreeHost(g->h_counters);
+  cudaFree(g->deferred);
+  cudaFree(g->block_counts);
+  for (int c = 0; c < kMaxKeys; ++c) { cudaFree(g->key_out[c]); cudaFree(g->key_out_nulls[c]); }
+  for (int a = 0; a < kMaxAggs; ++a) { cudaFree(g->agg_out[a]); cudaFree(g->agg_out_nulls[a]); }
+  delete g;
+}
+
+int ssb_group_update(ssb_group* g, const ssb_column* keys, const ssb_column* values, int64_t rows) {
+  TimedRegion timed(g->ctx);
+  return feed(g, keys, values, rows, false, false);
+}
+
+int ssb_group_merge(ssb_group* dst, int64_t n_groups, const ssb_column* key_cols, const ssb_column* agg_cols) {
+  dst->merged_any = true;
+  return feed(dst, key_cols, agg_cols, n_groups, true, false);
+}
+
+int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb_column* agg_out) {
+  ssb_ctx* ctx = g->ctx;
+  if (int rc = read_counters(g)) return rc;
+  long long n = g->n_keys == 0 ? 1 : static_cast<long long>(g->h_counters[0]);
+  if (g->n_keys == 0 && g->rows_seen == 0 && !g->merged_any) n = 1;   // ScalarAggregate: exactly one row
+  const long long cap = n > 0 ? n : 1;
+  if (g->out_capacity < cap) {
+    for (int c = 0; c < kMaxKeys; ++c) { cudaFree(g->key_out[c]); cudaFree(g->key_out_nulls[c]); g->key_out[c] = nullptr; g->key_out_nulls[c] = nullptr; }
+    for (int a = 0; a < kMaxAggs; ++a) { cudaFree(g->agg_out[a]); cudaFree(g->agg_out_nulls[a]); g->agg_out[a] = nullptr; g->agg_out_nulls[a] = nullptr; }
+    for (int c = 0; c < g->n_keys; ++c) {
+      SSB_CUDA(ctx, cudaMalloc(&g->key_out[c], static_cast<size_t>(cap) * 8 + 128));
+      SSB_CUDA(ctx, cudaMalloc(&g->key_out_nulls[c], static_cast<size_t>(cap / 32 + 2) * 4 + 128));
+    }
+    for (int a = 0; a < g->n_aggs; ++a) {
+      SSB_CUDA(ctx, cudaMalloc(&g->agg_out[a], static_cast<size_t>(cap) * 8 + 128));
+      SSB_CUDA(ctx, cudaMalloc(&g->agg_out_nulls[a], static_cast<size_t>(cap / 32 + 2) * 4 + 128));
+    }
+    g->out_capacity = cap;
+  }
+  for (int c = 0; c < g->n_keys; ++c) SSB_CUDA(ctx, cudaMemsetAsync(g->key_out_nulls[c], 0, static_cast<size_t>(cap / 32 + 2) * 4, ctx->stream));
+  for (int a = 0; a < g->n_aggs; ++a) SSB_CUDA(ctx, cudaMemsetAsync(g->agg_out_nulls[a], 0, static_cast<size_t>(cap / 32 + 2) * 4, ctx->stream));
+  FinalizeParams f;
+  memset(&f, 0, sizeof(f));
+  fill_table_params(g, &f.g);
+  f.total_slots = g->capacity + 2;
+  unsigned grid = static_cast<unsigned>(ctx->num_sms) * 4;
+  if (grid > f.total_slots / 256 + 1) grid = static_cast<unsigned>(f.total_slots / 256 + 1);
+  if (!g->block_counts) SSB_CUDA(ctx, cudaMalloc(&g->block_counts, static_cast<size_t>(ctx->num_sms) * 4 * 8));
+  f.block_counts = g->block_counts;
+  for (int c = 0; c < g->n_keys; ++c) { f.key_out[c] = g->key_out[c]; f.key_out_nulls[c] = g->key_out_nulls[c]; }
+  for (int a = 0; a < g->n_aggs; ++a) { f.agg_out[a] = g->agg_out[a]; f.agg_out_nulls[a] = g->agg_out_nulls[a]; }
+  group_count_kernel<<<grid, 256, 0, ctx->stream>>>(f);
+  group_emit_kernel<<<grid, 256, 0, ctx->stream>>>(f);
+  ctx->launches += 2;
+  SSB_CUDA(ctx, cudaGetLastError());
+  SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < g->n_keys; ++c) {
+    key_out[c].data = g->key_out[c];
+    key_out[c].nulls = g->key_nullable[c] ? g->key_out_nulls[c] : nullptr;
+    key_out[c].dtype = g->key_types[c];
+    key_out[c].reserved = 0;
+  }
+  for (int a = 0; a < g->n_aggs; ++a) {
+    agg_out[a].data = g->agg_out[a];
+    agg_out[a].nulls = g->aggs[a].fn == SSB_AGG_COUNT ? nullptr : g->agg_out_nulls[a];
+    agg_out[a].dtype = g->aggs[a].out_type;
+    agg_out[a].reserved = 0;
+  }
+  *n_groups = n;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// join.cu -- hash join build and probe on the GPU.
+//
+// Replaces HashIndexOnMaterializedCursor::{MaterializeInputAndBuildIndex, MultiLookup} and
+// ResultCursor (cursor/core/hash_join.cc:604-625,707-831) over RowHashSet / RowHashMultiSet
+// (cursor/infrastructure/row_hash_set.cc:424-608):
+//   build   open-addressed table of {key word, first build row}; a slot is claimed with
+//           atomicCAS on its row field, duplicates of a key keep the smallest row as the head.
+//           NOT_UNIQUE keys: the build rows are additionally grouped per slot with a stable
+//           radix sort of (slot, row), giving per key a contiguous run in insertion order.
+//   probe   pass 1 looks every lhs row up and writes its match count, an exclusive scan turns
+//           counts into output offsets, pass 2 writes the (lhs row, rhs row) pairs. The output
+//           is therefore in lhs order and, per lhs row, in build insertion order, exactly the
+//           order the reference emits (hash_join.cc:793-831).
+// Rows with a NULL in any key column never match (hash_join.cc:67-76,616-617,755-756).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "common.h"
+#include "device_utils.h"
+
+namespace ssb {
+
+enum { kJoinMaxKeys = 8 };
+
+struct JoinKeys {
+  int32_t n_keys;
+  int32_t phys[kJoinMaxKeys];
+  const void* data[kJoinMaxKeys];
+  const uint32_t* nulls[kJoinMaxKeys];
+};
+
+struct JoinTable {
+  unsigned long long capacity;    // power of two
+  long long* slot_row;            // head build row + 1, 0 = empty
+  unsigned long long* slot_key;   // first key column's raw bits of the head row (fast reject)
+  // multiset
+  unsigned long long* run_start;  // [capacity] offset into run_rows
+  unsigned int* run_count;        // [capacity]
+  long long* run_rows;            // build rows grouped by slot, insertion order
+};
+
+__device__ __forceinline__ unsigned long long jmix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ unsigned long long jload(const void* base, int phys, long long i) {
+  switch (phys_width(phys)) {
+    case 8: return static_cast<const unsigned long long*>(base)[i];
+    // INT32 is sign-extended so that integer keys of different widths compare by value
+    case 4: return phys == T_I32 ? static_cast<unsigned long long>(static_cast<long long>(static_cast<const int32_t*>(base)[i]))
+                                 : static_cast<unsigned long long>(static_cast<const uint32_t*>(base)[i]);
+    default: return static_cast<const uint8_t*>(base)[i];
+  }
+}
+__device__ __forceinline__ bool key_has_null(const JoinKeys& k, long long row) {
+  for (int c = 0; c < k.n_keys; ++c) {
+    if (k.nulls[c] != nullptr && ((k.nulls[c][row >> 5] >> (row & 31)) & 1u)) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ unsigned long long key_hash(const JoinKeys& k, long long row, unsigned long long* first) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (int c = 0; c < k.n_keys; ++c) {
+    const unsigned long long v = jload(k.data[c], k.phys[c], row);
+    if (c == 0) *first = v;
+    h = jmix64(h ^ v) + c;
+  }
+  return h;
+}
+__device__ __forceinline__ bool keys_equal(const JoinKeys& a, long long ra, const JoinKeys& b, long long rb) {
+  for (int c = 1; c < a.n_keys; ++c) {   // column 0 was compared through slot_key
+    if (jload(a.data[c], a.phys[c], ra) != jload(b.data[c], b.phys[c], rb)) return false;
+  }
+  return true;
+}
+
+// Finds the slot holding the key of (keys,row); -1 when absent. `build` are the build keys.
+__device__ __forceinline__ long long lookup(const JoinTable& t, const JoinKeys& build, const JoinKeys& keys, long long row) {
+  unsigned long long first = 0;
+  const unsigned long long mask = t.capacity - 1;
+  unsigned long long s = key_hash(keys, row, &first) & mask;
+  for (;;) {
+    const long long head = t.slot_row[s];
+    if (head == 0) return -1;
+    if (t.slot_key[s] == first && keys_equal(keys, row, build, head - 1)) return static_cast<long long>(s);
+    s = (s + 1) & mask;
+  }
+}
+
+// Build: every non-NULL-key row finds or claims the slot of its key. slot_of[row] = slot, or
+// -1 for NULL keys. The head of a slot ends as the smallest row with that key.
+__global__ void __launch_bounds__(256) join_build_kernel(JoinTable t, JoinKeys build, long long rows,
+                                                          long long* __restrict__ slot_of) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const unsigned long long mask = t.capacity - 1;
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
+    if (key_has_null(build, row)) { if (slot_of) slot_of[row] = -1; continue; }
+    unsigned long long first = 0;
+    unsigned long long s = key_hash(build, row, &first) & mask;
+    for (;;) {
+      long long head = *reinterpret_cast<volatile long long*>(&t.slot_row[s]);
+      if (head == 0) {
+        // claim with a negative marker, publish the key word, then publish the row
+        const long long old = static_cast<long long>(atomicCAS(reinterpret_cast<unsigned long long*>(&t.slot_row[s]), 0ull,
+                                                               static_cast<unsigned long long>(-(row + 1))));
+        if (old == 0) {
+          t.slot_key[s] = first;
+          __threadfence();
+          atomicExch(reinterpret_cast<unsigned long long*>(&t.slot_row[s]), static_cast<unsigned long long>(row + 1));
+          if (slot_of) slot_of[row] = static_cast<long long>(s);
+          break;
+        }
+        head = old;
+      }
+      while (head < 0) head = *reinterpret_cast<volatile long long*>(&t.slot_row[s]);   // being published
+      __threadfence();
+      if (*reinterpret_cast<volatile unsigned long long*>(&t.slot_key[s]) == first && keys_equal(build, row, build, head - 1)) {
+        // same key: keep the smallest row as head (insertion order of the reference)
+        atomicMin(reinterpret_cast<long long*>(&t.slot_row[s]), row + 1);
+        if (slot_of) slot_of[row] = static_cast<long long>(s);
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+}
+
+// NOTE on atomicMin above: heads are positive once published, so min keeps the smallest row;
+// a concurrent reader may compare keys against either row of the same key - both are equal.
+
+__global__ void run_bounds_kernel(const unsigned long long* __restrict__ sorted_slots, long long n_valid,
+                                  unsigned long long* __restrict__ run_start, unsigned int* __restrict__ run_count) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_valid; i += stride) {
+    const unsigned long long s = sorted_slots[i];
+    if (i == 0 || sorted_slots[i - 1] != s) run_start[s] = static_cast<unsigned long long>(i);
+    atomicAdd(&run_count[s], 1u);
+  }
+}
+
+__global__ void slot_keys_kernel(const long long* __restrict__ slot_of, long long rows, unsigned long long capacity,
+                                 unsigned long long* __restrict__ keys, long long* __restrict__ vals) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    keys[i] = slot_of[i] < 0 ? capacity : static_cast<unsigned long long>(slot_of[i]);   // NULL keys sort last
+    vals[i] = i;
+  }
+}
+
+// Probe pass 1: match slot and output count per lhs row.
+__global__ void __launch_bounds__(256) join_count_kernel(JoinTable t, JoinKeys build, JoinKeys probe, long long rows,
+                                                          int unique, int left_outer, long long* __restrict__ slot_of,
+                                                          unsigned long long* __restrict__ counts) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
+    long long s = -1;
+    if (!key_has_null(probe, row)) s = lookup(t, build, probe, row);
+    slot_of[row] = s;
+    unsigned long long c = 0;
+    if (s >= 0) c = unique ? 1ull : t.run_count[s];
+    else if (left_outer) c = 1ull;
+    counts[row] = c;
+  }
+}
+
+// Probe pass 2: write the pairs at the scanned offsets.
+__global__ void __launch_bounds__(256) join_emit_kernel(JoinTable t, long long rows, int unique,
+                                                         const long long* __restrict__ slot_of,
+                                                         const unsigned long long* __restrict__ offsets,
+                                                         long long* __restrict__ lhs_out, long long* __restrict__ rhs_out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
+    const long long s = slot_of[row];
+    const unsigned long long off = offsets[row];
+    if (s < 0) {
+      // counts were 0 (INNER) or 1 (LEFT_OUTER); offsets of the next row tell which
+      const unsigned long long next = offsets[row + 1];
+      if (next != off) { lhs_out[off] = row; rhs_out[off] = -1; }
+    } else if (unique) {
+      lhs_out[off] = row;
+      rhs_out[off] = t.slot_row[s] - 1;
+    } else {
+      const unsigned long long start = t.run_start[s];
+      const unsigned int cnt = t.run_count[s];
+      for (unsigned int j = 0; j < cnt; ++j) { lhs_out[off + j] = row; rhs_out[off + j] = t.run_rows[start + j]; }
+    }
+  }
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+struct ssb_join {
+  ssb_ctx* ctx;
+  JoinKeys build_keys;
+  long long build_rows;
+  int uniqueness;
+  JoinTable table;
+  long long* lhs_out;
+  long long* rhs_out;
+};
+
+extern "C" {
+
+void ssb_join_destroy(ssb_join* j) {
+  if (!j) return;
+  cudaStreamSynchronize(j->ctx->stream);
+  cudaFree(j->table.slot_row);
+  cudaFree(j->table.slot_key);
+  cudaFree(j->table.run_start);
+  cudaFree(j->table.run_count);
+  cudaFree(j->table.run_rows);
+  cudaFree(j->lhs_out);
+  cudaFree(j->rhs_out);
+  delete j;
+}
+
+static int fill_keys(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, JoinKeys* out) {
+  if (n_keys < 1 || n_keys > kJoinMaxKeys) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "hash join needs 1..8 key columns");
+  memset(out, 0, sizeof(*out));
+  out->n_keys = n_keys;
+  for (int c = 0; c < n_keys; ++c) {
+    out->phys[c] = phys_of(keys[c].dtype);
+    if (out->phys[c] < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported join key type");
+    out->data[c] = keys[c].data;
+    out->nulls[c] = keys[c].nulls;
+  }
+  return 0;
+}
+
+int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows, int32_t uniqueness,
+                   ssb_join** out) {
+  *out = nullptr;
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  ssb_join* j = new ssb_join();
+  memset(j, 0, sizeof(*j));
+  j->ctx = ctx;
+  if (int rc = fill_keys(ctx, n_keys, keys, &j->build_keys)) { delete j; return rc; }
+  j->build_rows = rows;
+  j->uniqueness = uniqueness;
+  unsigned long long cap = 1024;
+  while (cap < static_cast<unsigned long long>(rows) * 2) cap *= 2;
+  j->table.capacity = cap;
+  TimedRegion timed(ctx);
+  cudaError_t e = cudaMalloc(&j->table.slot_row, cap * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&j->table.slot_key, cap * 8);
+  if (e != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e, "join table"); }
+  cudaMemsetAsync(j->table.slot_row, 0, cap * 8, ctx->stream);
+  long long* slot_of = nullptr;
+  const bool multi = uniqueness != SSB_KEYS_UNIQUE;
+  if (multi && rows > 0) {
+    e = cudaMalloc(&slot_of, static_cast<size_t>(rows) * 8);
+    if (e != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e, "join build scratch"); }
+  }
+  if (rows > 0) {
+    join_build_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, j->build_keys, rows, slot_of);
+    ++ctx->launches;
+  }
+  int rc = 0;
+  if (multi) {
+    e = cudaMalloc(&j->table.run_start, cap * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&j->table.run_count, cap * 4);
+    if (e != cudaSuccess) { cudaFree(slot_of); ssb_join_destroy(j); return cuda_fail(ctx, e, "join runs"); }
+    cudaMemsetAsync(j->table.run_count, 0, cap * 4, ctx->stream);
+    if (rows > 0) {
+      unsigned long long *k0 = nullptr, *k1 = nullptr;
+      long long *v0 = nullptr, *v1 = nullptr;
+      e = cudaMalloc(&k0, static_cast<size_t>(rows) * 8);
+      if (e == cudaSuccess) e = cudaMalloc(&k1, static_cast<size_t>(rows) * 8);
+      if (e == cudaSuccess) e = cudaMalloc(&v0, static_cast<size_t>(rows) * 8);
+      if (e == cudaSuccess) e = cudaMalloc(&v1, static_cast<size_t>(rows) * 8);
+      if (e != cudaSuccess) {
+        cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(slot_of);
+        ssb_join_destroy(j);
+        return cuda_fail(ctx, e, "join sort scratch");
+      }
+      slot_keys_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(slot_of, rows, cap, k0, v0);
+      ++ctx->launches;
+      int bits = 1;
+      while ((1ull << bits) <= cap) ++bits;   // slots < cap, NULL marker == cap
+      bits = (bits + 7) / 8 * 8;
+      rc = radix_sort_pairs(ctx, &k0, &v0, &k1, &v1, static_cast<unsigned long long>(rows), 0, bits);
+      if (rc == 0) {
+        // rows with NULL keys (marker cap) sort last and own no run
+        run_bounds_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(k0, rows, j->table.run_start, j->table.run_count);
+        ++ctx->launches;
+      }
+      j->table.run_rows = v0;
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(k0); cudaFree(k1); cudaFree(v1);
+    }
+  }
+  e = cudaGetLastError();
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(slot_of);
+  if (rc == 0 && e != cudaSuccess) rc = cuda_fail(ctx, e, "join build");
+  if (rc) { ssb_join_destroy(j); return rc; }
+  *out = j;
+  return 0;
+}
+
+int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type, int64_t* n_pairs,
+                   const int64_t** d_lhs_rows, const int64_t** d_rhs_rows) {
+  ssb_ctx* ctx = j->ctx;
+  *n_pairs = 0;
+  *d_lhs_rows = nullptr;
+  *d_rhs_rows = nullptr;
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  if (join_type != SSB_JOIN_INNER && join_type != SSB_JOIN_LEFT_OUTER) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "join type");
+  if (rows == 0) return 0;
+  JoinKeys probe;
+  if (int rc = fill_keys(ctx, j->build_keys.n_keys, keys, &probe)) return rc;
+  for (int c = 0; c < probe.n_keys; ++c) {
+    const int a = probe.phys[c], b = j->build_keys.phys[c];
+    const bool ints = (a == T_I32 || a == T_I64 || a == T_U32 || a == T_U64) && (b == T_I32 || b == T_I64 || b == T_U32 || b == T_U64);
+    if (a != b && !ints) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "probe key types differ from the build keys");
+  }
+  TimedRegion timed(ctx);
+  long long* slot_of = nullptr;
+  unsigned long long* counts = nullptr;
+  unsigned long long* d_total = nullptr;
+  cudaError_t e = cudaMalloc(&slot_of, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&counts, static_cast<size_t>(rows + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_total, 8);
+  if (e != cudaSuccess) { cudaFree(slot_of); cudaFree(counts); cudaFree(d_total); return cuda_fail(ctx, e, "join probe scratch"); }
+  const int unique = j->uniqueness == SSB_KEYS_UNIQUE ? 1 : 0;
+  join_count_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, j->build_keys, probe, rows, unique,
+                                                                       join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, slot_of, counts);
+  ++ctx->launches;
+  cudaMemsetAsync(counts + rows, 0, 8, ctx->stream);
+  int rc = exclusive_scan_u64(ctx, counts, static_cast<unsigned long long>(rows) + 1, d_total);
+  unsigned long long total = 0;
+  if (rc == 0) {
+    cudaMemcpyAsync(ctx->h_count, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    total = static_cast<unsigned long long>(*ctx->h_count);
+    cudaFree(j->lhs_out); cudaFree(j->rhs_out);
+    j->lhs_out = j->rhs_out = nullptr;
+    e = cudaMalloc(&j->lhs_out, (total + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&j->rhs_out, (total + 1) * 8);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "join result");
+  }
+  if (rc == 0 && total > 0) {
+    join_emit_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, rows, unique, slot_of, counts, j->lhs_out, j->rhs_out);
+    ++ctx->launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "join probe");
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(slot_of); cudaFree(counts); cudaFree(d_total);
+  if (rc) return rc;
+  *n_pairs = static_cast<int64_t>(total);
+  *d_lhs_rows = reinterpret_cast<const int64_t*>(j->lhs_out);
+  *d_rhs_rows = reinterpret_cast<const int64_t*>(j->rhs_out);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// program.h -- the compiled form of a bound expression DAG: bytecode for the accumulator
+// machine of expr_kernel.cu plus the shared-memory plan of one CTA.
+#ifndef SSB_CSRC_PROGRAM_H_
+#define SSB_CSRC_PROGRAM_H_
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/supersonic_b200.h"
+#include "ops.h"
+
+namespace ssb {
+
+enum {
+  kThreads = 256,             // threads per CTA
+  kRowsPerThread = 4,         // R
+  kTile = kThreads * kRowsPerThread,   // rows per tile (1024, the reference's block size)
+  kTileWords = kTile / 32,    // null-bitmap words per tile
+  kMaxInsn = 64,
+  kMaxImm = 16,
+  kMaxIn = 12,
+  kMaxOut = 16,
+  kMaxTmp = 10,
+  kMaxStages = 4,
+};
+
+// Kernel parameters (passed by value, lives in the constant bank).
+struct ExprParams {
+  Insn insn[kMaxInsn];
+  uint64_t imm[kMaxImm];
+  int32_t n_insn;
+  // ---- inputs: slot i < n_in is input column i of the current pipeline stage
+  int32_t n_in;
+  const void* in_data[kMaxIn];
+  const uint32_t* in_nulls[kMaxIn];     // NULL = column has no bitmap in this run
+  uint8_t in_width[kMaxIn];
+  uint8_t in_nullable[kMaxIn];          // compiled with null words for this input
+  uint32_t in_off[kMaxIn];              // byte offset of the column tile inside a stage
+  int32_t in_nullw[kMaxIn];             // index of its null-word row inside a stage, -1
+  // ---- temporaries: slot n_in + t
+  int32_t n_tmp;
+  // ---- outputs
+  int32_t n_out;
+  void* out_data[kMaxOut];
+  uint32_t* out_nulls[kMaxOut];
+  uint8_t out_slot[kMaxOut];
+  uint8_t out_width[kMaxOut];
+  uint8_t out_nullable[kMaxOut];
+  // ---- shared memory plan (byte offsets from the 128-byte aligned base)
+  uint32_t off_bar, off_scan, off_nullw, off_data, off_tmp;
+  uint32_t stage_bytes;                 // data bytes of one stage
+  uint32_t stage_nullw;                 // null-word rows per stage (nullable inputs)
+  uint32_t stage_tx_bytes;              // bytes one full-tile TMA fill delivers
+  int32_t stages;
+  // ---- run
+  int64_t rows;
+  int64_t num_tiles;
+  int32_t has_pred;
+  int32_t use_tma;
+  unsigned long long* tile_status;      // decoupled look-back words (Filter)
+  int64_t* d_out_rows;
+  int32_t* d_fail;
+};
+
+struct Program {
+  // compile-time description
+  std::vector<ssb_expr_node> nodes;
+  std::vector<int32_t> input_types;
+  std::vector<int32_t> input_nullable;
+  std::vector<int32_t> outputs;
+  int32_t predicate;
+  // compiled
+  ExprParams params;          // pointers / run fields are filled per run
+  std::vector<int32_t> out_types;
+  std::vector<int32_t> out_nullable;
+  uint32_t smem_bytes;
+  int32_t bytes_in_row, bytes_out_row;
+  bool has_signaling;
+};
+
+// Compiles nodes into prog->params (bytecode + shared-memory plan for `smem_budget` bytes per
+// CTA). Returns 0 or an SSB_ERROR_* with *err set. Pure host code (unit-tested without a GPU).
+int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs,
+                    const int32_t* input_types, const int32_t* input_nullable,
+                    const int32_t* outputs, int32_t n_outputs, int32_t predicate,
+                    uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err);
+
+}  // namespace ssb
+
+struct ssb_program {
+  ssb_ctx* ctx;
+  ssb::Program prog;
+  int max_ctas_per_sm;
+};
+
+#endif  // SSB_CSRC_PROGRAM_H_

@@ -1,0 +1,675 @@
+// expression.cc -- expression factories and binding (type promotion, naming, nullability).
+//
+// Follows the reference's bind-time rules:
+//   common type table        expression/templated/bound_expression_factory.cc:70-90
+//   comparison promotion     expression/core/comparison_bound_expressions.cc:587-636
+//   result names             expression/vector/expression_traits.h:1209-1453
+//   cast rules               expression/templated/cast_bound_expression.cc
+// and is checked against the reference build for every (operator, type pair) in
+// tests/test_binding.py.
+#include <stdio.h>
+
+#include "internal.h"
+
+namespace supersonic {
+
+using internal::ExprNode;
+using internal::NodePtr;
+
+namespace {
+
+Exception* TypeMismatch(const string& msg) { return new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, msg); }
+
+bool IsInteger(DataType t) { return t == INT32 || t == INT64 || t == UINT32 || t == UINT64; }
+bool IsNumeric(DataType t) { return IsInteger(t) || t == FLOAT || t == DOUBLE; }
+
+const string& TypeName(DataType t) { return GetTypeInfo(t).name(); }
+
+std::shared_ptr<ExprNode> NewNode(int op, DataType type, bool nullable, const string& name) {
+  std::shared_ptr<ExprNode> n(new ExprNode);
+  n->op = op;
+  n->type = type;
+  n->nullable = nullable;
+  n->name = name;
+  return n;
+}
+
+bool AllConstNonNull(const vector<NodePtr>& args) {
+  for (size_t i = 0; i < args.size(); ++i) {
+    if (!args[i]->constant || args[i]->nullable) return false;
+  }
+  return !args.empty();
+}
+
+// A node over `args`; sub-trees made only of non-NULL constants take the name the reference
+// gives them after constant folding (basic_bound_expression.cc:57,286-327).
+NodePtr MakeNode(int op, DataType type, bool nullable, const string& name, const vector<NodePtr>& args, int flags = 0) {
+  std::shared_ptr<ExprNode> n = NewNode(op, type, nullable, name);
+  n->args = args;
+  n->flags = flags;
+  bool constant = !args.empty();
+  for (size_t i = 0; i < args.size(); ++i) constant = constant && args[i]->constant;
+  n->constant = constant;
+  if (AllConstNonNull(args) && !nullable) n->name = "CONST_" + TypeName(type);
+  return n;
+}
+
+NodePtr MakeCast(const NodePtr& child, DataType to) {
+  if (child->type == to) return child;
+  const int op = (child->type == DATE && to == DATETIME) ? SSB_OP_DATE_TO_DATETIME : SSB_OP_CAST;
+  return MakeNode(op, to, child->nullable,
+                  "CAST_" + TypeName(child->type) + "_TO_" + TypeName(to) + "(" + child->name + ")",
+                  vector<NodePtr>(1, child));
+}
+
+// bound_expression_factory.cc:70-90
+bool CommonType(DataType a, DataType b, DataType* out) {
+  if (a == b) { *out = a; return true; }
+  struct Rule { DataType x, y, r; };
+  static const Rule rules[] = {
+    {DOUBLE, INT32, DOUBLE}, {DOUBLE, INT64, DOUBLE}, {DOUBLE, UINT32, DOUBLE}, {DOUBLE, UINT64, DOUBLE},
+    {DOUBLE, FLOAT, DOUBLE}, {FLOAT, INT32, FLOAT}, {FLOAT, UINT32, FLOAT}, {FLOAT, UINT64, DOUBLE},
+    {FLOAT, INT64, DOUBLE}, {INT64, INT32, INT64}, {INT64, UINT32, INT64}, {INT64, UINT64, INT64},
+    {UINT64, INT32, INT64}, {UINT64, UINT32, UINT64}, {UINT32, INT32, INT64}, {DATE, DATETIME, DATETIME},
+  };
+  for (size_t i = 0; i < sizeof(rules) / sizeof(rules[0]); ++i) {
+    if ((rules[i].x == a && rules[i].y == b) || (rules[i].x == b && rules[i].y == a)) { *out = rules[i].r; return true; }
+  }
+  return false;
+}
+
+enum Kind {
+  K_PLUS, K_MINUS, K_MULTIPLY, K_DIV_SIGNALING, K_DIV_NULLING, K_DIV_QUIET, K_CPPDIV_SIGNALING,
+  K_CPPDIV_NULLING, K_MOD_SIGNALING, K_MOD_NULLING, K_NEGATE,
+  K_EQUAL, K_NOT_EQUAL, K_LESS, K_LESS_OR_EQUAL, K_GREATER, K_GREATER_OR_EQUAL, K_IS_ODD, K_IS_EVEN,
+  K_AND, K_OR, K_AND_NOT, K_XOR, K_NOT, K_IS_NULL, K_IF_NULL, K_IF, K_NULLING_IF,
+  K_BIT_AND, K_BIT_OR, K_BIT_XOR, K_BIT_AND_NOT, K_BIT_NOT, K_SHL, K_SHR, K_CAST
+};
+
+const char* KindName(Kind k) {
+  switch (k) {
+    case K_PLUS: return "PLUS"; case K_MINUS: return "SUBTRACT"; case K_MULTIPLY: return "MULTIPLY";
+    case K_DIV_SIGNALING: case K_DIV_NULLING: case K_DIV_QUIET: return "DIVIDE";
+    case K_CPPDIV_SIGNALING: case K_CPPDIV_NULLING: return "CPP_DIVIDE";
+    case K_MOD_SIGNALING: case K_MOD_NULLING: return "MODULUS";
+    case K_NEGATE: return "NEGATE"; case K_IS_ODD: return "IS_ODD"; case K_IS_EVEN: return "IS_EVEN";
+    case K_BIT_AND: return "BITWISE_AND"; case K_BIT_OR: return "BITWISE_OR"; case K_BIT_XOR: return "BITWISE_XOR";
+    case K_BIT_AND_NOT: return "BITWISE_ANDNOT"; case K_BIT_NOT: return "BITWISE_NOT";
+    case K_SHL: return "SHIFT_LEFT"; case K_SHR: return "SHIFT_RIGHT";
+    default: return "OPERATION";
+  }
+}
+
+Exception* FactoryMismatch(Kind k) {
+  return TypeMismatch(string("Factory creation of operation ") + KindName(k) + " failed due to type mismatch.");
+}
+
+Exception* WrongType(DataType expected, const NodePtr& got) {
+  return TypeMismatch("Wrong type of argument supplied. Expected: " + TypeName(expected) + "; is: " + got->name +
+                      ": " + TypeName(got->type) + (got->nullable ? "" : " NOT NULL"));
+}
+
+FailureOr<NodePtr> BindArithmetic(Kind k, const NodePtr& a, const NodePtr& b) {
+  const vector<NodePtr> none;
+  DataType common;
+  if (!IsNumeric(a->type) || !IsNumeric(b->type) || !CommonType(a->type, b->type, &common)) THROW(FactoryMismatch(k));
+  int op = 0, flags = 0;
+  const char* sym = "";
+  bool nullable = a->nullable || b->nullable;
+  switch (k) {
+    case K_PLUS: op = SSB_OP_ADD; sym = " + "; break;
+    case K_MINUS: op = SSB_OP_SUB; sym = " - "; break;
+    case K_MULTIPLY: op = SSB_OP_MUL; sym = " * "; break;
+    case K_DIV_SIGNALING: op = SSB_OP_DIV; sym = " /. "; common = DOUBLE; flags = SSB_NODE_ZERO_FAILS; break;
+    case K_DIV_NULLING: op = SSB_OP_DIV; sym = " /. "; common = DOUBLE; flags = SSB_NODE_ZERO_NULLS; nullable = true; break;
+    case K_DIV_QUIET: op = SSB_OP_DIV; sym = " /. "; common = DOUBLE; break;
+    case K_CPPDIV_SIGNALING: op = SSB_OP_DIV; sym = " / "; flags = SSB_NODE_ZERO_FAILS; break;
+    case K_CPPDIV_NULLING: op = SSB_OP_DIV; sym = " / "; flags = SSB_NODE_ZERO_NULLS; nullable = true; break;
+    case K_MOD_SIGNALING: op = SSB_OP_MOD; sym = " % "; flags = SSB_NODE_ZERO_FAILS; break;
+    case K_MOD_NULLING: op = SSB_OP_MOD; sym = " % "; flags = SSB_NODE_ZERO_NULLS; nullable = true; break;
+    default: THROW(FactoryMismatch(k));
+  }
+  if ((k == K_MOD_SIGNALING || k == K_MOD_NULLING) && !IsInteger(common)) THROW(FactoryMismatch(k));
+  const NodePtr l = MakeCast(a, common), r = MakeCast(b, common);
+  vector<NodePtr> args;
+  args.push_back(l);
+  args.push_back(r);
+  return Success(MakeNode(op, common, nullable, "(" + l->name + sym + r->name + ")", args, flags));
+}
+
+// comparison_bound_expressions.cc:587-636 and :832-847 (Greater(a,b) = Less(b,a))
+FailureOr<NodePtr> BindComparison(Kind k, NodePtr a, NodePtr b) {
+  if (k == K_GREATER) { std::swap(a, b); k = K_LESS; }
+  if (k == K_GREATER_OR_EQUAL) { std::swap(a, b); k = K_LESS_OR_EQUAL; }
+  if (a->type != b->type) {
+    if (!IsNumeric(a->type) || !IsNumeric(b->type)) {
+      THROW(TypeMismatch("Cannot compare expressions of different, non-numeric types"));
+    }
+    if (a->type == DOUBLE || b->type == DOUBLE) { a = MakeCast(a, DOUBLE); b = MakeCast(b, DOUBLE); }
+    else if (a->type == FLOAT || b->type == FLOAT) { a = MakeCast(a, FLOAT); b = MakeCast(b, FLOAT); }
+    // two different integer types: compared through the mixed overloads of operators.h:185-294.
+    // EQUAL / NOT_EQUAL put the smaller type on the left, ordering INT32 < UINT32 < INT64 <
+    // UINT64 (comparison_bound_expressions.cc:513-548).
+    else if (k == K_EQUAL || k == K_NOT_EQUAL) {
+      struct Rank { static int of(DataType t) { return t == INT32 ? 0 : t == UINT32 ? 1 : t == INT64 ? 2 : 3; } };
+      if (Rank::of(a->type) > Rank::of(b->type)) std::swap(a, b);
+    }
+  }
+  int op = 0;
+  const char* sym = "";
+  switch (k) {
+    case K_EQUAL: op = SSB_OP_EQ; sym = " == "; break;
+    case K_NOT_EQUAL: op = SSB_OP_NE; sym = " <> "; break;
+    case K_LESS: op = SSB_OP_LT; sym = " < "; break;
+    default: op = SSB_OP_LE; sym = " <= "; break;
+  }
+  vector<NodePtr> args;
+  args.push_back(a);
+  args.push_back(b);
+  return Success(MakeNode(op, BOOL, a->nullable || b->nullable, "(" + a->name + sym + b->name + ")", args));
+}
+
+FailureOr<NodePtr> BindLogic(Kind k, const NodePtr& a, const NodePtr& b) {
+  if (a->type != BOOL) THROW(WrongType(BOOL, a));
+  if (b->type != BOOL) THROW(WrongType(BOOL, b));
+  int op = 0;
+  const char* sym = "";
+  switch (k) {
+    case K_AND: op = SSB_OP_AND; sym = " AND "; break;
+    case K_OR: op = SSB_OP_OR; sym = " OR "; break;
+    case K_AND_NOT: op = SSB_OP_AND_NOT; sym = " !&& "; break;
+    default: op = SSB_OP_XOR; sym = " XOR "; break;
+  }
+  vector<NodePtr> args;
+  args.push_back(a);
+  args.push_back(b);
+  return Success(MakeNode(op, BOOL, a->nullable || b->nullable, "(" + a->name + sym + b->name + ")", args));
+}
+
+FailureOr<NodePtr> BindBitwise(Kind k, const NodePtr& a, const NodePtr& b) {
+  if (!IsInteger(a->type) || !IsInteger(b->type)) THROW(FactoryMismatch(k));
+  vector<NodePtr> args;
+  if (k == K_SHL || k == K_SHR) {   // result type = left type, no promotion
+    args.push_back(a);
+    args.push_back(b);
+    return Success(MakeNode(k == K_SHL ? SSB_OP_SHL : SSB_OP_SHR, a->type, a->nullable || b->nullable,
+                            "(" + a->name + (k == K_SHL ? " << " : " >> ") + b->name + ")", args));
+  }
+  DataType common;
+  if (!CommonType(a->type, b->type, &common)) THROW(FactoryMismatch(k));
+  const NodePtr l = MakeCast(a, common), r = MakeCast(b, common);
+  args.push_back(l);
+  args.push_back(r);
+  int op = 0;
+  string name;
+  switch (k) {
+    case K_BIT_AND: op = SSB_OP_BIT_AND; name = "(" + l->name + " & " + r->name + ")"; break;
+    case K_BIT_OR: op = SSB_OP_BIT_OR; name = "(" + l->name + " | " + r->name + ")"; break;
+    case K_BIT_XOR: op = SSB_OP_BIT_XOR; name = "(" + l->name + " ^ " + r->name + ")"; break;
+    default: op = SSB_OP_BIT_AND_NOT; name = "(~" + l->name + " & " + r->name + ")"; break;
+  }
+  return Success(MakeNode(op, common, l->nullable || r->nullable, name, args));
+}
+
+NodePtr MakeConstBool(bool v) {
+  std::shared_ptr<ExprNode> n = NewNode(SSB_OP_CONST, BOOL, false, "CONST_BOOL");
+  n->constant = true;
+  n->imm.u64 = 0;
+  n->imm.b = v;
+  return n;
+}
+
+FailureOr<NodePtr> BindUnary(Kind k, const NodePtr& a, DataType cast_to) {
+  const vector<NodePtr> args(1, a);
+  switch (k) {
+    case K_NEGATE: {
+      if (!IsNumeric(a->type)) THROW(FactoryMismatch(k));
+      // expression_traits: NEGATE of UINT32 yields INT32, of UINT64 INT64.
+      const DataType out = a->type == UINT32 ? INT32 : (a->type == UINT64 ? INT64 : a->type);
+      if (a->type == UINT32) {
+        // -(int64)arg narrowed to INT32 == two's complement negate of the reinterpreted value
+        const NodePtr as_i32 = MakeNode(SSB_OP_CAST, INT32, a->nullable, a->name, args);
+        return Success(MakeNode(SSB_OP_NEGATE, INT32, a->nullable, "(-" + a->name + ")", vector<NodePtr>(1, as_i32)));
+      }
+      return Success(MakeNode(SSB_OP_NEGATE, out, a->nullable, "(-" + a->name + ")", args));
+    }
+    case K_NOT:
+      if (a->type != BOOL) THROW(WrongType(BOOL, a));
+      return Success(MakeNode(SSB_OP_NOT, BOOL, a->nullable, "(NOT " + a->name + ")", args));
+    case K_IS_NULL:
+      if (!a->nullable) return Success(MakeConstBool(false));
+      if (a->op == SSB_OP_CONST) return Success(MakeConstBool((a->flags & SSB_NODE_NULL) != 0));
+      return Success(MakeNode(SSB_OP_IS_NULL, BOOL, false, "ISNULL(" + a->name + ")", args));
+    case K_BIT_NOT:
+      if (!IsInteger(a->type)) THROW(FactoryMismatch(k));
+      return Success(MakeNode(SSB_OP_BIT_NOT, a->type, a->nullable, "(~" + a->name + ")", args));
+    case K_IS_ODD:
+    case K_IS_EVEN:
+      if (!IsInteger(a->type)) THROW(FactoryMismatch(k));
+      return Success(MakeNode(k == K_IS_ODD ? SSB_OP_IS_ODD : SSB_OP_IS_EVEN, BOOL, a->nullable,
+                              string(k == K_IS_ODD ? "IS_ODD(" : "IS_EVEN(") + a->name + ")", args));
+    case K_CAST: {
+      if (a->type == cast_to) return Success(a);
+      const bool from_fp = a->type == FLOAT || a->type == DOUBLE;
+      bool ok = false;
+      if (IsNumeric(a->type) && IsNumeric(cast_to)) ok = !(from_fp && IsInteger(cast_to));
+      if (a->type == DATE && cast_to == DATETIME) ok = true;
+      if (!ok) {
+        THROW(TypeMismatch("Cannot cast " + TypeName(a->type) + " to " + TypeName(cast_to) + " in CAST_TO_" +
+                           TypeName(cast_to) + "(" + a->name + ")."));
+      }
+      return Success(MakeCast(a, cast_to));
+    }
+    default: THROW(FactoryMismatch(k));
+  }
+}
+
+FailureOr<NodePtr> BindIfNull(const NodePtr& a, const NodePtr& b) {
+  DataType common;
+  if (!CommonType(a->type, b->type, &common)) {
+    THROW(TypeMismatch("Cannot reconcile types: " + TypeName(a->type) + " and " + TypeName(b->type) + "."));
+  }
+  const NodePtr l = MakeCast(a, common), r = MakeCast(b, common);
+  if (!a->nullable) return Success(l);   // nothing to substitute: the (promoted) first argument
+  vector<NodePtr> args;
+  args.push_back(l);
+  args.push_back(r);
+  return Success(MakeNode(SSB_OP_IF_NULL, common, l->nullable && r->nullable,
+                          "IFNULL(" + l->name + ", " + r->name + ")", args));
+}
+
+FailureOr<NodePtr> BindIf(bool nulling, const NodePtr& c, const NodePtr& a, const NodePtr& b) {
+  if (c->type != BOOL) THROW(WrongType(BOOL, c));
+  DataType common;
+  if (!CommonType(a->type, b->type, &common)) {
+    THROW(TypeMismatch("Cannot reconcile types: " + TypeName(a->type) + " and " + TypeName(b->type) + "."));
+  }
+  const NodePtr l = MakeCast(a, common), r = MakeCast(b, common);
+  vector<NodePtr> args;
+  args.push_back(c);
+  args.push_back(l);
+  args.push_back(r);
+  const bool nullable = l->nullable || r->nullable || (nulling && c->nullable);
+  return Success(MakeNode(nulling ? SSB_OP_NULLING_IF : SSB_OP_IF, common, nullable,
+                          "IF " + c->name + " THEN " + l->name + " ELSE " + r->name, args));
+}
+
+FailureOrOwned<BoundExpression> Single(const TupleSchema& input, const NodePtr& node) {
+  TupleSchema rs = TupleSchema::Singleton(node->name, node->type, node->nullable ? NULLABLE : NOT_NULLABLE);
+  return Success(new BoundExpression(input, rs, vector<NodePtr>(1, node)));
+}
+
+FailureOr<NodePtr> BindOne(const Expression* e, const TupleSchema& input, BufferAllocator* allocator,
+                           rowcount_t max_rows, const char* what) {
+  FailureOrOwned<BoundExpression> b = e->DoBind(input, allocator, max_rows);
+  PROPAGATE_ON_FAILURE(b);
+  if (b->column_count() != 1) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "%s: expected an expression with 1 attribute, got %d", what, b->column_count());
+    THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, buf));
+  }
+  NodePtr n = b->node(0);
+  return Success(n);
+}
+
+// The generic operator expression.
+class FnExpression : public Expression {
+ public:
+  FnExpression(Kind kind, const Expression* a, const Expression* b = NULL, const Expression* c = NULL,
+               DataType cast_to = INT32)
+      : kind_(kind), a_(a), b_(b), c_(c), cast_to_(cast_to) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator* allocator,
+                                                 rowcount_t max_rows) const {
+    FailureOr<NodePtr> a = BindOne(a_.get(), input, allocator, max_rows, KindName(kind_));
+    PROPAGATE_ON_FAILURE(a);
+    NodePtr na = a.get(), nb, nc;
+    if (b_) {
+      FailureOr<NodePtr> b = BindOne(b_.get(), input, allocator, max_rows, KindName(kind_));
+      PROPAGATE_ON_FAILURE(b);
+      nb = b.get();
+    }
+    if (c_) {
+      FailureOr<NodePtr> c = BindOne(c_.get(), input, allocator, max_rows, KindName(kind_));
+      PROPAGATE_ON_FAILURE(c);
+      nc = c.get();
+    }
+    FailureOr<NodePtr> r = Apply(na, nb, nc);
+    PROPAGATE_ON_FAILURE(r);
+    return Single(input, r.get());
+  }
+  virtual string ToString(bool verbose) const {
+    string s = string(KindName(kind_)) + "(" + a_->ToString(verbose);
+    if (b_) s += ", " + b_->ToString(verbose);
+    if (c_) s += ", " + c_->ToString(verbose);
+    return s + ")";
+  }
+ private:
+  FailureOr<NodePtr> Apply(const NodePtr& a, const NodePtr& b, const NodePtr& c) const {
+    switch (kind_) {
+      case K_PLUS: case K_MINUS: case K_MULTIPLY: case K_DIV_SIGNALING: case K_DIV_NULLING: case K_DIV_QUIET:
+      case K_CPPDIV_SIGNALING: case K_CPPDIV_NULLING: case K_MOD_SIGNALING: case K_MOD_NULLING:
+        return BindArithmetic(kind_, a, b);
+      case K_EQUAL: case K_NOT_EQUAL: case K_LESS: case K_LESS_OR_EQUAL: case K_GREATER: case K_GREATER_OR_EQUAL:
+        return BindComparison(kind_, a, b);
+      case K_AND: case K_OR: case K_AND_NOT: case K_XOR: return BindLogic(kind_, a, b);
+      case K_BIT_AND: case K_BIT_OR: case K_BIT_XOR: case K_BIT_AND_NOT: case K_SHL: case K_SHR:
+        return BindBitwise(kind_, a, b);
+      case K_IF_NULL: return BindIfNull(a, b);
+      case K_IF: return BindIf(false, a, b, c);
+      case K_NULLING_IF: return BindIf(true, a, b, c);
+      default: return BindUnary(kind_, a, cast_to_);
+    }
+  }
+  Kind kind_;
+  std::unique_ptr<const Expression> a_, b_, c_;
+  DataType cast_to_;
+};
+
+class ConstExpression : public Expression {
+ public:
+  ConstExpression(DataType type, bool is_null) : type_(type), is_null_(is_null) { imm_.u64 = 0; }
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator*, rowcount_t) const {
+    std::shared_ptr<ExprNode> n = NewNode(SSB_OP_CONST, type_, is_null_, is_null_ ? "NULL" : "CONST_" + TypeName(type_));
+    n->constant = true;
+    n->flags = is_null_ ? SSB_NODE_NULL : 0;
+    memcpy(&n->imm, &imm_, sizeof(imm_));
+    return Single(input, n);
+  }
+  virtual string ToString(bool) const { return is_null_ ? "<" + TypeName(type_) + ">NULL" : "CONST_" + TypeName(type_); }
+  union { int64 i64; uint64 u64; double f64; float f32; int32 i32; uint32 u32; bool b; } imm_;
+ private:
+  DataType type_;
+  bool is_null_;
+};
+
+class AttributeExpression : public Expression {
+ public:
+  AttributeExpression(const string& name, int position) : name_(name), position_(position) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator*, rowcount_t) const {
+    int pos = position_;
+    if (pos < 0) {
+      pos = input.LookupAttributePosition(name_);
+      if (pos < 0) {
+        THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "No attribute '" + name_ + "' in the schema: (" +
+                                                         input.GetHumanReadableSpecification() + ")"));
+      }
+    } else if (pos >= input.attribute_count()) {
+      char buf[160];
+      snprintf(buf, sizeof(buf), "Attribute position %d out of range; the schema has %d attributes", pos,
+               input.attribute_count());
+      THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, buf));
+    }
+    return Single(input, internal::MakeInputNode(input, pos));
+  }
+  virtual string ToString(bool) const { return position_ < 0 ? name_ : "AttributeAt"; }
+ private:
+  string name_;
+  int position_;
+};
+
+class AliasExpression : public Expression {
+ public:
+  AliasExpression(const string& name, const Expression* arg) : name_(name), arg_(arg) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator* a, rowcount_t m) const {
+    FailureOr<NodePtr> n = BindOne(arg_.get(), input, a, m, "ALIAS");
+    PROPAGATE_ON_FAILURE(n);
+    std::shared_ptr<ExprNode> copy(new ExprNode(*n.get()));
+    copy->name = name_;
+    return Single(input, copy);
+  }
+  virtual string ToString(bool v) const { return arg_->ToString(v) + " AS " + name_; }
+ private:
+  string name_;
+  std::unique_ptr<const Expression> arg_;
+};
+
+class ProjectionExpression : public Expression {
+ public:
+  explicit ProjectionExpression(const SingleSourceProjector* p) : projector_(p) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator*, rowcount_t) const {
+    FailureOrOwned<const BoundSingleSourceProjector> b = projector_->Bind(input);
+    PROPAGATE_ON_FAILURE(b);
+    vector<NodePtr> nodes;
+    for (int i = 0; i < b->result_schema().attribute_count(); ++i) {
+      std::shared_ptr<ExprNode> n(new ExprNode(*internal::MakeInputNode(input, b->source_attribute_position(i))));
+      n->name = b->result_schema().attribute(i).name();
+      nodes.push_back(n);
+    }
+    return Success(new BoundExpression(input, b->result_schema(), nodes));
+  }
+  virtual string ToString(bool v) const { return projector_->ToString(v); }
+ private:
+  std::unique_ptr<const SingleSourceProjector> projector_;
+};
+
+class NotImplementedExpression : public Expression {
+ public:
+  explicit NotImplementedExpression(const char* what) : what_(what) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema&, BufferAllocator*, rowcount_t) const {
+    THROW(new Exception(ERROR_NOT_IMPLEMENTED, what_ + " is not part of the B200 hot path yet"));
+  }
+  virtual string ToString(bool) const { return what_; }
+ private:
+  string what_;
+};
+
+template <typename T> ConstExpression* NewConst(DataType type) { return new ConstExpression(type, false); }
+
+}  // namespace
+
+namespace internal {
+
+NodePtr MakeInputNode(const TupleSchema& schema, int position) {
+  const Attribute& a = schema.attribute(position);
+  std::shared_ptr<ExprNode> n = NewNode(SSB_OP_INPUT, a.type(), a.is_nullable(), a.name());
+  n->input = position;
+  return n;
+}
+
+NodePtr MakeBinaryLogic(int op, const NodePtr& a, const NodePtr& b) {
+  vector<NodePtr> args;
+  args.push_back(a);
+  args.push_back(b);
+  return MakeNode(op, BOOL, a->nullable || b->nullable, "(" + a->name + " AND " + b->name + ")", args);
+}
+
+namespace {
+NodePtr SubstituteMemo(const NodePtr& node, const vector<NodePtr>& inputs, std::map<const ExprNode*, NodePtr>* memo) {
+  std::map<const ExprNode*, NodePtr>::iterator it = memo->find(node.get());
+  if (it != memo->end()) return it->second;
+  NodePtr result;
+  if (node->op == SSB_OP_INPUT) {
+    result = inputs[node->input];
+  } else if (node->args.empty()) {
+    result = node;
+  } else {
+    std::shared_ptr<ExprNode> copy(new ExprNode(*node));
+    for (size_t i = 0; i < copy->args.size(); ++i) copy->args[i] = SubstituteMemo(node->args[i], inputs, memo);
+    result = copy;
+  }
+  (*memo)[node.get()] = result;
+  return result;
+}
+}  // namespace
+
+NodePtr Substitute(const NodePtr& node, const vector<NodePtr>& inputs) {
+  std::map<const ExprNode*, NodePtr> memo;
+  return SubstituteMemo(node, inputs, &memo);
+}
+
+}  // namespace internal
+
+// ---- BoundExpression
+namespace {
+void CollectInputs(const NodePtr& n, std::map<int, bool>* seen) {
+  if (n->op == SSB_OP_INPUT) (*seen)[n->input] = true;
+  for (size_t i = 0; i < n->args.size(); ++i) CollectInputs(n->args[i], seen);
+}
+}  // namespace
+
+bool BoundExpression::is_constant() const {
+  for (size_t i = 0; i < nodes_.size(); ++i) if (!nodes_[i]->constant) return false;
+  return true;
+}
+void BoundExpression::CollectReferredAttributeNames(vector<string>* names) const {
+  std::map<int, bool> seen;
+  for (size_t i = 0; i < nodes_.size(); ++i) CollectInputs(nodes_[i], &seen);
+  for (std::map<int, bool>::iterator it = seen.begin(); it != seen.end(); ++it) {
+    names->push_back(input_schema_.attribute(it->first).name());
+  }
+}
+
+FailureOrOwned<BoundExpressionTree> Expression::Bind(const TupleSchema& input_schema, BufferAllocator* allocator,
+                                                     rowcount_t max_row_count) const {
+  FailureOrOwned<BoundExpression> b = DoBind(input_schema, allocator, max_row_count);
+  PROPAGATE_ON_FAILURE(b);
+  return Success(new BoundExpressionTree(b.release(), allocator, max_row_count));
+}
+
+string ExpressionList::ToString(bool verbose) const {
+  string s;
+  for (size_t i = 0; i < list_.size(); ++i) { if (i) s += ", "; s += list_[i]->ToString(verbose); }
+  return s;
+}
+
+// ---- CompoundExpression (projecting_bound_expressions.cc:102-279)
+CompoundExpression::~CompoundExpression() {
+  for (size_t i = 0; i < entries_.size(); ++i) delete entries_[i].expression;
+}
+CompoundExpression* CompoundExpression::Add(const Expression* argument) {
+  Entry e;
+  e.expression = argument;
+  entries_.push_back(e);
+  return this;
+}
+CompoundExpression* CompoundExpression::AddAs(const StringPiece& alias, const Expression* argument) {
+  Entry e;
+  e.aliases.push_back(alias.as_string());
+  e.expression = argument;
+  entries_.push_back(e);
+  return this;
+}
+CompoundExpression* CompoundExpression::AddAsMulti(const vector<string>& aliases, const Expression* argument) {
+  Entry e;
+  e.aliases = aliases;
+  e.expression = argument;
+  entries_.push_back(e);
+  return this;
+}
+FailureOrOwned<BoundExpression> CompoundExpression::DoBind(const TupleSchema& input, BufferAllocator* allocator,
+                                                           rowcount_t max_rows) const {
+  TupleSchema rs;
+  vector<NodePtr> nodes;
+  for (size_t i = 0; i < entries_.size(); ++i) {
+    FailureOrOwned<BoundExpression> b = entries_[i].expression->DoBind(input, allocator, max_rows);
+    PROPAGATE_ON_FAILURE(b);
+    if (!entries_[i].aliases.empty() && static_cast<int>(entries_[i].aliases.size()) != b->column_count()) {
+      THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "Alias count differs from the attribute count of the expression"));
+    }
+    for (int c = 0; c < b->column_count(); ++c) {
+      const Attribute& a = b->result_schema().attribute(c);
+      const string name = entries_[i].aliases.empty() ? a.name() : entries_[i].aliases[c];
+      if (!rs.add_attribute(Attribute(name, a.type(), a.nullability()))) {
+        THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + name + "' in result schema"));
+      }
+      NodePtr n = b->node(c);
+      if (n->name != name) {
+        std::shared_ptr<ExprNode> copy(new ExprNode(*n));
+        copy->name = name;
+        n = copy;
+      }
+      nodes.push_back(n);
+    }
+  }
+  return Success(new BoundExpression(input, rs, nodes));
+}
+string CompoundExpression::ToString(bool verbose) const {
+  string s;
+  for (size_t i = 0; i < entries_.size(); ++i) { if (i) s += ", "; s += entries_[i].expression->ToString(verbose); }
+  return s;
+}
+
+// ---- factories
+#define SSB200_CONST(NAME, DT, FIELD, CPP)                       \
+  const Expression* NAME(const CPP& value) {                     \
+    ConstExpression* e = new ConstExpression(DT, false);         \
+    e->imm_.FIELD = value;                                       \
+    return e;                                                    \
+  }
+SSB200_CONST(ConstInt32, INT32, i32, int32)
+SSB200_CONST(ConstInt64, INT64, i64, int64)
+SSB200_CONST(ConstUint32, UINT32, u32, uint32)
+SSB200_CONST(ConstUint64, UINT64, u64, uint64)
+SSB200_CONST(ConstFloat, FLOAT, f32, float)
+SSB200_CONST(ConstDouble, DOUBLE, f64, double)
+SSB200_CONST(ConstBool, BOOL, b, bool)
+SSB200_CONST(ConstDate, DATE, i32, int32)
+SSB200_CONST(ConstDateTime, DATETIME, i64, int64)
+#undef SSB200_CONST
+const Expression* Null(DataType type) { return new ConstExpression(type, true); }
+const Expression* Sequence() { return new NotImplementedExpression("SEQUENCE"); }
+
+const Expression* NamedAttribute(const string& name) { return new AttributeExpression(name, -1); }
+const Expression* AttributeAt(int position) { return new AttributeExpression("", position); }
+const Expression* Alias(const string& new_name, const Expression* argument) { return new AliasExpression(new_name, argument); }
+const Expression* InputAttributeProjection(const SingleSourceProjector* projector) { return new ProjectionExpression(projector); }
+
+#define SSB200_BINARY(NAME, KIND) \
+  const Expression* NAME(const Expression* const a, const Expression* const b) { return new FnExpression(KIND, a, b); }
+SSB200_BINARY(Plus, K_PLUS)
+SSB200_BINARY(Minus, K_MINUS)
+SSB200_BINARY(Multiply, K_MULTIPLY)
+SSB200_BINARY(Divide, K_DIV_SIGNALING)
+SSB200_BINARY(DivideSignaling, K_DIV_SIGNALING)
+SSB200_BINARY(DivideNulling, K_DIV_NULLING)
+SSB200_BINARY(DivideQuiet, K_DIV_QUIET)
+SSB200_BINARY(CppDivide, K_CPPDIV_SIGNALING)
+SSB200_BINARY(CppDivideSignaling, K_CPPDIV_SIGNALING)
+SSB200_BINARY(CppDivideNulling, K_CPPDIV_NULLING)
+SSB200_BINARY(Modulus, K_MOD_SIGNALING)
+SSB200_BINARY(ModulusSignaling, K_MOD_SIGNALING)
+SSB200_BINARY(ModulusNulling, K_MOD_NULLING)
+SSB200_BINARY(Equal, K_EQUAL)
+SSB200_BINARY(NotEqual, K_NOT_EQUAL)
+SSB200_BINARY(Less, K_LESS)
+SSB200_BINARY(LessOrEqual, K_LESS_OR_EQUAL)
+SSB200_BINARY(Greater, K_GREATER)
+SSB200_BINARY(GreaterOrEqual, K_GREATER_OR_EQUAL)
+SSB200_BINARY(And, K_AND)
+SSB200_BINARY(Or, K_OR)
+SSB200_BINARY(AndNot, K_AND_NOT)
+SSB200_BINARY(Xor, K_XOR)
+SSB200_BINARY(IfNull, K_IF_NULL)
+#undef SSB200_BINARY
+const Expression* BitwiseAnd(const Expression* a, const Expression* b) { return new FnExpression(K_BIT_AND, a, b); }
+const Expression* BitwiseOr(const Expression* a, const Expression* b) { return new FnExpression(K_BIT_OR, a, b); }
+const Expression* BitwiseXor(const Expression* a, const Expression* b) { return new FnExpression(K_BIT_XOR, a, b); }
+const Expression* BitwiseAndNot(const Expression* a, const Expression* b) { return new FnExpression(K_BIT_AND_NOT, a, b); }
+const Expression* ShiftLeft(const Expression* a, const Expression* s) { return new FnExpression(K_SHL, a, s); }
+const Expression* ShiftRight(const Expression* a, const Expression* s) { return new FnExpression(K_SHR, a, s); }
+const Expression* Negate(const Expression* const a) { return new FnExpression(K_NEGATE, a); }
+const Expression* IsOdd(const Expression* const a) { return new FnExpression(K_IS_ODD, a); }
+const Expression* IsEven(const Expression* const a) { return new FnExpression(K_IS_EVEN, a); }
+const Expression* Not(const Expression* const e) { return new FnExpression(K_NOT, e); }
+const Expression* IsNull(const Expression* const e) { return new FnExpression(K_IS_NULL, e); }
+const Expression* BitwiseNot(const Expression* a) { return new FnExpression(K_BIT_NOT, a); }
+const Expression* CastTo(DataType to_type, const Expression* const source) {
+  return new FnExpression(K_CAST, source, NULL, NULL, to_type);
+}
+const Expression* If(const Expression* const c, const Expression* const t, const Expression* const o) {
+  return new FnExpression(K_IF, c, t, o);
+}
+const Expression* NullingIf(const Expression* const c, const Expression* const t, const Expression* const o) {
+  return new FnExpression(K_NULLING_IF, c, t, o);
+}
+const Expression* Case(const ExpressionList* const arguments) {
+  delete arguments;
+  return new NotImplementedExpression("CASE");
+}
+const Expression* In(const Expression* const needle, const ExpressionList* haystack) {
+  delete needle;
+  delete haystack;
+  return new NotImplementedExpression("IN");
+}
+
+}  // namespace supersonic

@@ -1,0 +1,716 @@
+// ops.cc -- Operation factories and GPU cursors (see include/supersonic/cursor.h).
+#include <stdio.h>
+
+#include "internal.h"
+
+namespace supersonic {
+
+using namespace internal;   // NOLINT
+
+// ------------------------------------------------------------------ BasicOperation
+BasicOperation::~BasicOperation() {
+  for (size_t i = 0; i < children_.size(); ++i) delete children_[i];
+}
+void BasicOperation::SetBufferAllocator(BufferAllocator* allocator, bool cascade_to_children) {
+  allocator_ = allocator;
+  if (cascade_to_children) {
+    for (size_t i = 0; i < children_.size(); ++i) children_[i]->SetBufferAllocator(allocator, true);
+  }
+}
+void BasicOperation::SetBufferAllocatorWhereUnset(BufferAllocator* allocator, bool cascade_to_children) {
+  if (allocator_ == NULL) allocator_ = allocator;
+  if (cascade_to_children) {
+    for (size_t i = 0; i < children_.size(); ++i) children_[i]->SetBufferAllocatorWhereUnset(allocator, true);
+  }
+}
+void BasicOperation::AppendDebugDescription(string* target) const {
+  target->append(DebugName());
+  target->append("(");
+  for (size_t i = 0; i < children_.size(); ++i) {
+    if (i) target->append(", ");
+    children_[i]->AppendDebugDescription(target);
+  }
+  target->append(")");
+}
+
+namespace {
+
+#define SSB_CALL(session, call, what)                              \
+  do {                                                             \
+    const int rc_ = (call);                                        \
+    if (rc_ != 0) THROW((session)->Error(rc_, what));              \
+  } while (0)
+
+// ------------------------------------------------------------------ host view cursor
+// cursor/infrastructure/view_cursor.cc:47-75: slices an in-memory view, zero copy.
+class ViewCursor : public Cursor {
+ public:
+  explicit ViewCursor(const View& view) : full_(view), out_(view.schema()), offset_(0), interrupted_(false) {}
+  virtual const TupleSchema& schema() const { return full_.schema(); }
+  virtual ResultView Next(rowcount_t max_row_count) {
+    if (interrupted_) return ResultView::Failure(new Exception(INTERRUPTED, "cursor interrupted"));
+    if (offset_ >= full_.row_count()) return ResultView::EOS();
+    rowcount_t n = full_.row_count() - offset_;
+    if (n > max_row_count) n = max_row_count;
+    out_.ResetFromSubRange(full_, offset_, n);
+    offset_ += n;
+    return ResultView::Success(&out_);
+  }
+  virtual void Interrupt() { interrupted_ = true; }
+  virtual void AppendDebugDescription(string* target) const { target->append("ViewCursor"); }
+  virtual CursorId GetCursorId() const { return VIEW; }
+  const View& full_view() const { return full_; }
+ private:
+  View full_, out_;
+  rowcount_t offset_;
+  volatile bool interrupted_;
+};
+
+// ------------------------------------------------------------------ row-wise cursor
+// One fused kernel for a chain of ScanView / Compute / Filter / Project
+// (replaces ComputeCursor::Next, FilterCursor::Next, ProjectCursor::Next).
+class RowwiseCursor : public GpuCursor {
+ public:
+  RowwiseCursor(const RowwisePlan& plan, BufferAllocator* allocator, CursorId id)
+      : GpuCursor(plan.schema, allocator, "RowwiseCursor"), plan_(plan), id_(id) {}
+  virtual CursorId GetCursorId() const { return id_; }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOrOwned<DeviceProgram> created = DeviceProgram::Create(plan_.base_schema, plan_.outputs, plan_.predicate);
+    PROPAGATE_ON_FAILURE(created);
+    std::unique_ptr<DeviceProgram> program(created.release());
+    DeviceTable in;
+    std::unique_ptr<Block> keepalive;
+    int64 rows = 0;
+    vector<ssb_column> ic;
+    if (plan_.source) {
+      DeviceTable whole;
+      PROPAGATE_ON_FAILURE(MaterializeOnDevice(plan_.source.get(), &whole, &keepalive));
+      rows = whole.rows;
+      for (size_t k = 0; k < program->used_inputs().size(); ++k) {
+        in.columns.push_back(whole.columns[program->used_inputs()[k]]);
+      }
+    } else {
+      rows = static_cast<int64>(plan_.base.row_count());
+      PROPAGATE_ON_FAILURE(UploadColumns(plan_.base, program->used_inputs(), 0, plan_.base.row_count(), &in));
+    }
+    for (size_t k = 0; k < in.columns.size(); ++k) ic.push_back(in.columns[k].col);
+    PROPAGATE_ON_FAILURE(result->Allocate(plan_.schema, rows, /* force_nulls = */ true));
+    vector<ssb_column> oc;
+    for (size_t j = 0; j < result->columns.size(); ++j) oc.push_back(result->columns[j].col);
+    FailureOr<Session*> s = Session::Get();
+    PROPAGATE_ON_FAILURE(s);
+    for (size_t j = 0; j < oc.size(); ++j) {
+      SSB_CALL(s.get(), ssb_memset(s.get()->ctx(), oc[j].nulls, 0, static_cast<size_t>((rows + 31) / 32 + 1) * 4), "memset");
+    }
+    FailureOr<int64> n = program->Run(ic, rows, oc);
+    PROPAGATE_ON_FAILURE(n);
+    result->rows = n.get();
+    return Success();
+  }
+ private:
+  RowwisePlan plan_;
+  CursorId id_;
+};
+
+FailureOrOwned<Cursor> CreateRowwiseCursor(const Operation* op, BufferAllocator* allocator, CursorId id) {
+  RowwisePlan plan;
+  PROPAGATE_ON_FAILURE(DescribeAny(op, &plan));
+  return Success(static_cast<Cursor*>(new RowwiseCursor(plan, allocator, id)));
+}
+
+// ------------------------------------------------------------------ ScanView
+class ScanViewOperation : public BasicOperation {
+ public:
+  explicit ScanViewOperation(const View& view) : view_(view) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const { return Success(static_cast<Cursor*>(new ViewCursor(view_))); }
+  virtual bool DescribeRowwise(RowwisePlan* plan, Exception**) const {
+    plan->base = view_;
+    plan->source.reset();
+    plan->base_schema = view_.schema();
+    plan->schema = view_.schema();
+    plan->outputs.clear();
+    for (int i = 0; i < view_.schema().attribute_count(); ++i) plan->outputs.push_back(MakeInputNode(view_.schema(), i));
+    plan->predicate.reset();
+    return true;
+  }
+ protected:
+  virtual string DebugName() const { return "ScanView"; }
+ private:
+  View view_;
+};
+
+// ------------------------------------------------------------------ Compute
+class ComputeOperation : public BasicOperation {
+ public:
+  ComputeOperation(const Expression* computation, Operation* child) : BasicOperation(child), computation_(computation) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const { return CreateRowwiseCursor(this, buffer_allocator(), COMPUTE); }
+  virtual bool DescribeRowwise(RowwisePlan* plan, Exception** error) const {
+    FailureOrVoid d = DescribeAny(child(), plan);
+    if (d.is_failure()) { *error = d.release_exception(); return true; }
+    FailureOrOwned<BoundExpression> bound = computation_->DoBind(plan->schema, buffer_allocator(), Cursor::kDefaultRowCount);
+    if (bound.is_failure()) { *error = bound.release_exception(); return true; }
+    vector<NodePtr> outs;
+    for (int i = 0; i < bound->column_count(); ++i) outs.push_back(Substitute(bound->node(i), plan->outputs));
+    plan->outputs = outs;
+    plan->schema = bound->result_schema();
+    return true;
+  }
+ protected:
+  virtual string DebugName() const { return "Compute"; }
+ private:
+  std::unique_ptr<const Expression> computation_;
+};
+
+// ------------------------------------------------------------------ Filter
+class FilterOperation : public BasicOperation {
+ public:
+  FilterOperation(const Expression* predicate, const SingleSourceProjector* projector, Operation* child)
+      : BasicOperation(child), predicate_(predicate), projector_(projector) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const { return CreateRowwiseCursor(this, buffer_allocator(), FILTER); }
+  virtual bool DescribeRowwise(RowwisePlan* plan, Exception** error) const {
+    FailureOrVoid d = DescribeAny(child(), plan);
+    if (d.is_failure()) { *error = d.release_exception(); return true; }
+    FailureOrOwned<BoundExpression> bound = predicate_->DoBind(plan->schema, buffer_allocator(), Cursor::kDefaultRowCount);
+    if (bound.is_failure()) { *error = bound.release_exception(); return true; }
+    // cursor/core/filter.cc:79-87
+    if (bound->column_count() != 1) {
+      *error = new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "Predicate has to return exactly one column in (" +
+                                                                 bound->result_schema().GetHumanReadableSpecification() + ")");
+      return true;
+    }
+    if (bound->result_schema().attribute(0).type() != BOOL) {
+      *error = new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, "Predicate has to return column of type BOOL in (" +
+                                                                bound->result_schema().GetHumanReadableSpecification() + ")");
+      return true;
+    }
+    FailureOrOwned<const BoundSingleSourceProjector> proj = projector_->Bind(plan->schema);
+    if (proj.is_failure()) { *error = proj.release_exception(); return true; }
+    NodePtr pred = Substitute(bound->node(0), plan->outputs);
+    plan->predicate = plan->predicate ? MakeBinaryLogic(SSB_OP_AND, plan->predicate, pred) : pred;
+    vector<NodePtr> outs;
+    for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+      outs.push_back(plan->outputs[proj->source_attribute_position(i)]);
+    }
+    plan->outputs = outs;
+    plan->schema = proj->result_schema();
+    return true;
+  }
+ protected:
+  virtual string DebugName() const { return "Filter"; }
+ private:
+  std::unique_ptr<const Expression> predicate_;
+  std::unique_ptr<const SingleSourceProjector> projector_;
+};
+
+// ------------------------------------------------------------------ Project
+class ProjectOperation : public BasicOperation {
+ public:
+  ProjectOperation(const SingleSourceProjector* projector, Operation* child) : BasicOperation(child), projector_(projector) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const { return CreateRowwiseCursor(this, buffer_allocator(), PROJECT); }
+  virtual bool DescribeRowwise(RowwisePlan* plan, Exception** error) const {
+    FailureOrVoid d = DescribeAny(child(), plan);
+    if (d.is_failure()) { *error = d.release_exception(); return true; }
+    FailureOrOwned<const BoundSingleSourceProjector> proj = projector_->Bind(plan->schema);
+    if (proj.is_failure()) { *error = proj.release_exception(); return true; }
+    vector<NodePtr> outs;
+    for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+      outs.push_back(plan->outputs[proj->source_attribute_position(i)]);
+    }
+    plan->outputs = outs;
+    plan->schema = proj->result_schema();
+    return true;
+  }
+ protected:
+  virtual string DebugName() const { return "Project"; }
+ private:
+  std::unique_ptr<const SingleSourceProjector> projector_;
+};
+
+// ------------------------------------------------------------------ GroupAggregate
+struct BoundAggregation {
+  ssb_agg_spec spec;
+  int input_position;   // child column, -1 for COUNT(*)
+};
+
+bool IsNumericType(DataType t) { return GetTypeInfo(t).is_numeric(); }
+
+// cursor/core/aggregator.cc:63-152, column_aggregator.cc:520-566: result types and nullability.
+FailureOrVoid BindAggregations(const AggregationSpecification& spec, const TupleSchema& child,
+                               vector<BoundAggregation>* out, TupleSchema* result_schema) {
+  for (int i = 0; i < spec.size(); ++i) {
+    const AggregationSpecification::Element& e = spec.aggregation(i);
+    BoundAggregation b;
+    memset(&b.spec, 0, sizeof(b.spec));
+    const Aggregation fn = e.aggregation_operator();
+    if (e.is_distinct()) THROW(new Exception(ERROR_NOT_IMPLEMENTED, "DISTINCT aggregations are not on the B200 hot path yet"));
+    if (fn == CONCAT) THROW(new Exception(ERROR_NOT_IMPLEMENTED, "CONCAT needs STRING columns (SURVEY 8f)"));
+    b.spec.fn = fn;
+    b.input_position = -1;
+    DataType in_type = INT64;
+    bool in_nullable = false;
+    if (e.input().empty()) {
+      if (fn != COUNT) THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "Only COUNT may have an empty input attribute name"));
+    } else {
+      b.input_position = child.LookupAttributePosition(e.input());
+      if (b.input_position < 0) {
+        THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "No attribute '" + e.input() + "' in the schema: (" +
+                                                         child.GetHumanReadableSpecification() + ")"));
+      }
+      in_type = child.attribute(b.input_position).type();
+      in_nullable = child.attribute(b.input_position).is_nullable();
+    }
+    DataType out_type;
+    Nullability out_null = NULLABLE;
+    if (fn == COUNT) {
+      out_type = e.output_type_specified() ? e.output_type() : UINT64;
+      out_null = NOT_NULLABLE;
+      if (!GetTypeInfo(out_type).is_integer()) {
+        THROW(new Exception(ERROR_INVALID_ARGUMENT_TYPE, "Aggregation not supported. Count can not store result in output column of type " + DataType_Name(out_type) + "."));
+      }
+    } else {
+      out_type = e.output_type_specified() ? e.output_type() : in_type;
+      if (fn == SUM && !IsNumericType(in_type)) {
+        THROW(new Exception(ERROR_INVALID_ARGUMENT_TYPE, "Aggregation not supported. Aggregation function SUM not defined for types " +
+                                                             DataType_Name(in_type) + " and " + DataType_Name(out_type) + "."));
+      }
+      if (out_type != in_type) {
+        if (!(IsNumericType(in_type) && IsNumericType(out_type))) {
+          THROW(new Exception(ERROR_INVALID_ARGUMENT_TYPE,
+                              "Aggregation not supported. Aggregation function " + Aggregation_Name(fn) +
+                                  " not defined for types " + DataType_Name(in_type) + " and " + DataType_Name(out_type) + "."));
+        }
+      }
+      if (in_type == STRING || in_type == BINARY) {
+        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length aggregates are not on the B200 hot path (SURVEY 8f)"));
+      }
+    }
+    b.spec.input = -1;   // filled by the cursor (index into the values array)
+    b.spec.in_type = in_type;
+    b.spec.out_type = out_type;
+    b.spec.in_nullable = in_nullable ? 1 : 0;
+    if (!result_schema->add_attribute(Attribute(e.output(), out_type, out_null))) {
+      THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + e.output() + "' in result schema"));
+    }
+    out->push_back(b);
+  }
+  return Success();
+}
+
+class GroupCursor : public GpuCursor {
+ public:
+  GroupCursor(const TupleSchema& schema, BufferAllocator* allocator, Cursor* child, const vector<int>& keys,
+              const vector<BoundAggregation>& aggs, size_t estimated_groups, bool scalar)
+      : GpuCursor(schema, allocator, scalar ? "ScalarAggregateCursor" : "GroupAggregateCursor"), child_(child),
+        keys_(keys), aggs_(aggs), estimated_groups_(estimated_groups), scalar_(scalar), group_(NULL) {}
+  virtual ~GroupCursor() { if (group_) ssb_group_destroy(group_); }
+  virtual CursorId GetCursorId() const { return scalar_ ? SCALAR_AGGREGATE : GROUP_AGGREGATE; }
+  virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    DeviceTable in;
+    std::unique_ptr<Block> keepalive;
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(child_.get(), &in, &keepalive));
+    vector<int32_t> key_types, key_nullable;
+    vector<ssb_column> key_cols, value_cols;
+    for (size_t k = 0; k < keys_.size(); ++k) {
+      const Attribute& a = child_->schema().attribute(keys_[k]);
+      key_types.push_back(a.type());
+      key_nullable.push_back(a.is_nullable() ? 1 : 0);
+      key_cols.push_back(in.columns[keys_[k]].col);
+    }
+    vector<ssb_agg_spec> specs;
+    for (size_t i = 0; i < aggs_.size(); ++i) {
+      ssb_agg_spec sp = aggs_[i].spec;
+      if (aggs_[i].input_position >= 0) {
+        sp.input = static_cast<int32_t>(value_cols.size());
+        value_cols.push_back(in.columns[aggs_[i].input_position].col);
+      }
+      specs.push_back(sp);
+    }
+    int32_t dummy = 0;
+    ssb_column dummy_col;
+    memset(&dummy_col, 0, sizeof(dummy_col));
+    int64 expected = estimated_groups_ ? static_cast<int64>(estimated_groups_) : 0;
+    SSB_CALL(s, ssb_group_create(s->ctx(), static_cast<int32_t>(keys_.size()), key_types.empty() ? &dummy : key_types.data(),
+                                 key_nullable.empty() ? &dummy : key_nullable.data(), static_cast<int32_t>(specs.size()),
+                                 specs.data(), expected, &group_), "group-by setup");
+    SSB_CALL(s, ssb_group_update(group_, key_cols.empty() ? &dummy_col : key_cols.data(),
+                                 value_cols.empty() ? &dummy_col : value_cols.data(), in.rows), "group-by");
+    int64_t n_groups = 0;
+    vector<ssb_column> kout(keys_.size() ? keys_.size() : 1), aout(specs.size() ? specs.size() : 1);
+    SSB_CALL(s, ssb_group_finalize(group_, &n_groups, kout.data(), aout.data()), "group-by finalize");
+    result->schema = schema();
+    result->columns.clear();
+    for (size_t k = 0; k < keys_.size(); ++k) { DeviceColumnRef c; c.col = kout[k]; result->columns.push_back(c); }
+    for (size_t i = 0; i < specs.size(); ++i) { DeviceColumnRef c; c.col = aout[i]; result->columns.push_back(c); }
+    result->rows = n_groups;
+    return Success();
+  }
+ private:
+  std::unique_ptr<Cursor> child_;
+  vector<int> keys_;
+  vector<BoundAggregation> aggs_;
+  size_t estimated_groups_;
+  bool scalar_;
+  ssb_group* group_;
+};
+
+class GroupAggregateOperation : public BasicOperation {
+ public:
+  GroupAggregateOperation(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
+                          GroupAggregateOptions* options, Operation* child)
+      : BasicOperation(child), group_by_(group_by), aggregation_(aggregation), options_(options) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    FailureOrOwned<Cursor> child_cursor = child()->CreateCursor();
+    PROPAGATE_ON_FAILURE(child_cursor);
+    const TupleSchema& cs = child_cursor->schema();
+    TupleSchema result;
+    vector<int> keys;
+    if (group_by_) {
+      FailureOrOwned<const BoundSingleSourceProjector> proj = group_by_->Bind(cs);
+      PROPAGATE_ON_FAILURE(proj);
+      for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+        keys.push_back(proj->source_attribute_position(i));
+        result.add_attribute(proj->result_schema().attribute(i));
+        const DataType t = proj->result_schema().attribute(i).type();
+        if (t == STRING || t == BINARY) {
+          THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length group keys are not on the B200 hot path (SURVEY 8f)"));
+        }
+      }
+    }
+    vector<BoundAggregation> aggs;
+    PROPAGATE_ON_FAILURE(BindAggregations(*aggregation_, cs, &aggs, &result));
+    const size_t est = options_ ? options_->estimated_result_row_count() : 0;
+    return Success(static_cast<Cursor*>(new GroupCursor(result, buffer_allocator(), child_cursor.release(), keys, aggs,
+                                                        est, group_by_ == NULL)));
+  }
+ protected:
+  virtual string DebugName() const { return group_by_ ? "GroupAggregate" : "ScalarAggregate"; }
+ private:
+  std::unique_ptr<const SingleSourceProjector> group_by_;
+  std::unique_ptr<AggregationSpecification> aggregation_;
+  std::unique_ptr<GroupAggregateOptions> options_;
+};
+
+// ------------------------------------------------------------------ gather helper
+FailureOrVoid GatherColumns(Session* s, const DeviceTable& src, const vector<int>& positions, const int64_t* d_idx,
+                            int64 n, bool force_nulls, DeviceTable* out, size_t first_out) {
+  for (size_t k = 0; k < positions.size(); ++k) {
+    const DeviceColumnRef& from = src.columns[positions[k]];
+    DeviceColumnRef& to = out->columns[first_out + k];
+    if (to.col.nulls == NULL && (from.col.nulls != NULL || force_nulls)) {
+      THROW(new Exception(ERROR_UNKNOWN_ERROR, "internal: gather target lacks a null bitmap"));
+    }
+    ssb_column dst = to.col;
+    if (from.col.nulls == NULL && !force_nulls) dst.nulls = NULL;
+    SSB_CALL(s, ssb_gather(s->ctx(), &from.col, d_idx, n, &dst), "gather");
+  }
+  return Success();
+}
+
+// ------------------------------------------------------------------ HashJoin
+class HashJoinCursor : public GpuCursor {
+ public:
+  HashJoinCursor(const TupleSchema& schema, BufferAllocator* allocator, Cursor* lhs, Cursor* rhs, JoinType join_type,
+                 KeyUniqueness uniqueness, const vector<int>& lhs_keys, const vector<int>& rhs_keys,
+                 const BoundMultiSourceProjector* projector)
+      : GpuCursor(schema, allocator, "HashJoinCursor"), lhs_(lhs), rhs_(rhs), join_type_(join_type),
+        uniqueness_(uniqueness), lhs_keys_(lhs_keys), rhs_keys_(rhs_keys), projector_(projector), join_(NULL) {}
+  virtual ~HashJoinCursor() { if (join_) ssb_join_destroy(join_); }
+  virtual CursorId GetCursorId() const { return HASH_JOIN; }
+  virtual void Interrupt() { GpuCursor::Interrupt(); lhs_->Interrupt(); rhs_->Interrupt(); }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    std::unique_ptr<Block> keep_l, keep_r;
+    // build side first (hash_join.cc:406-420), then the probe side
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(rhs_.get(), &rhs_table_, &keep_r));
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(lhs_.get(), &lhs_table_, &keep_l));
+    vector<ssb_column> rk, lk;
+    for (size_t k = 0; k < rhs_keys_.size(); ++k) rk.push_back(rhs_table_.columns[rhs_keys_[k]].col);
+    for (size_t k = 0; k < lhs_keys_.size(); ++k) lk.push_back(lhs_table_.columns[lhs_keys_[k]].col);
+    SSB_CALL(s, ssb_join_build(s->ctx(), static_cast<int32_t>(rk.size()), rk.data(), rhs_table_.rows,
+                               uniqueness_ == UNIQUE ? SSB_KEYS_UNIQUE : SSB_KEYS_NOT_UNIQUE, &join_), "hash join build");
+    int64_t n_pairs = 0;
+    const int64_t* d_l = NULL;
+    const int64_t* d_r = NULL;
+    SSB_CALL(s, ssb_join_probe(join_, lk.data(), lhs_table_.rows,
+                               join_type_ == LEFT_OUTER ? SSB_JOIN_LEFT_OUTER : SSB_JOIN_INNER, &n_pairs, &d_l, &d_r),
+             "hash join probe");
+    PROPAGATE_ON_FAILURE(result->Allocate(schema(), n_pairs, /* force_nulls = */ true));
+    for (int i = 0; i < projector_->result_schema().attribute_count(); ++i) {
+      const int src = projector_->source_index(i);
+      const vector<int> pos(1, projector_->source_attribute_position(i));
+      const bool outer_side = (src == 1 && join_type_ == LEFT_OUTER);
+      PROPAGATE_ON_FAILURE(GatherColumns(s, src == 0 ? lhs_table_ : rhs_table_, pos, src == 0 ? d_l : d_r, n_pairs,
+                                         outer_side, result, static_cast<size_t>(i)));
+      // columns gathered without nulls: clear the bitmap so the download reads zeros
+      const DeviceColumnRef& from = (src == 0 ? lhs_table_ : rhs_table_).columns[pos[0]];
+      if (from.col.nulls == NULL && !outer_side) {
+        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[i].col.nulls, 0, static_cast<size_t>((n_pairs + 31) / 32 + 1) * 4), "memset");
+      }
+    }
+    result->rows = n_pairs;
+    SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
+    return Success();
+  }
+ private:
+  std::unique_ptr<Cursor> lhs_, rhs_;
+  JoinType join_type_;
+  KeyUniqueness uniqueness_;
+  vector<int> lhs_keys_, rhs_keys_;
+  std::unique_ptr<const BoundMultiSourceProjector> projector_;
+  ssb_join* join_;
+  DeviceTable lhs_table_, rhs_table_;
+};
+
+// ------------------------------------------------------------------ Sort
+class SortCursor : public GpuCursor {
+ public:
+  SortCursor(const TupleSchema& schema, BufferAllocator* allocator, Cursor* child,
+             const vector<std::pair<int, ColumnOrder> >& keys, const vector<int>& projected)
+      : GpuCursor(schema, allocator, "SortCursor"), child_(child), keys_(keys), projected_(projected) {}
+  virtual CursorId GetCursorId() const { return SORT; }
+  virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    DeviceTable in;
+    std::unique_ptr<Block> keepalive;
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(child_.get(), &in, &keepalive));
+    vector<ssb_column> kc;
+    vector<int32_t> desc;
+    for (size_t k = 0; k < keys_.size(); ++k) {
+      kc.push_back(in.columns[keys_[k].first].col);
+      desc.push_back(keys_[k].second == DESCENDING ? 1 : 0);
+    }
+    DeviceBuffer perm;
+    PROPAGATE_ON_FAILURE(perm.Allocate(static_cast<size_t>(in.rows) * 8 + 128));
+    ssb_column dummy_col;
+    memset(&dummy_col, 0, sizeof(dummy_col));
+    int32_t dummy = 0;
+    SSB_CALL(s, ssb_sort_permutation(s->ctx(), static_cast<int32_t>(kc.size()), kc.empty() ? &dummy_col : kc.data(),
+                                     desc.empty() ? &dummy : desc.data(), in.rows, static_cast<int64_t*>(perm.get())),
+             "sort");
+    PROPAGATE_ON_FAILURE(result->Allocate(schema(), in.rows, /* force_nulls = */ true));
+    for (size_t i = 0; i < projected_.size(); ++i) {
+      const vector<int> pos(1, projected_[i]);
+      PROPAGATE_ON_FAILURE(GatherColumns(s, in, pos, static_cast<const int64_t*>(perm.get()), in.rows, false, result, i));
+      if (in.columns[projected_[i]].col.nulls == NULL) {
+        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[i].col.nulls, 0, static_cast<size_t>((in.rows + 31) / 32 + 1) * 4), "memset");
+      }
+    }
+    result->rows = in.rows;
+    SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
+    return Success();
+  }
+ private:
+  std::unique_ptr<Cursor> child_;
+  vector<std::pair<int, ColumnOrder> > keys_;
+  vector<int> projected_;
+};
+
+class SortOperation : public BasicOperation {
+ public:
+  SortOperation(const SortOrder* order, const SingleSourceProjector* projector, Operation* child)
+      : BasicOperation(child), order_(order), projector_(projector) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    FailureOrOwned<Cursor> child_cursor = child()->CreateCursor();
+    PROPAGATE_ON_FAILURE(child_cursor);
+    const TupleSchema& cs = child_cursor->schema();
+    vector<std::pair<int, ColumnOrder> > keys;
+    PROPAGATE_ON_FAILURE(order_->Bind(cs, &keys));
+    vector<int> projected;
+    TupleSchema result;
+    if (projector_) {
+      FailureOrOwned<const BoundSingleSourceProjector> proj = projector_->Bind(cs);
+      PROPAGATE_ON_FAILURE(proj);
+      result = proj->result_schema();
+      for (int i = 0; i < result.attribute_count(); ++i) projected.push_back(proj->source_attribute_position(i));
+    } else {
+      result = cs;
+      for (int i = 0; i < cs.attribute_count(); ++i) projected.push_back(i);
+    }
+    return Success(static_cast<Cursor*>(new SortCursor(result, buffer_allocator(), child_cursor.release(), keys, projected)));
+  }
+ protected:
+  virtual string DebugName() const { return "Sort"; }
+ private:
+  std::unique_ptr<const SortOrder> order_;
+  std::unique_ptr<const SingleSourceProjector> projector_;
+};
+
+}  // namespace
+
+namespace internal {
+
+FailureOrVoid DescribeAny(const Operation* op, RowwisePlan* plan) {
+  Exception* error = NULL;
+  if (op->DescribeRowwise(plan, &error)) {
+    if (error != NULL) return Failure(error);
+    return Success();
+  }
+  FailureOrOwned<Cursor> c = op->CreateCursor();
+  PROPAGATE_ON_FAILURE(c);
+  plan->source.reset(c.release());
+  plan->base_schema = plan->source->schema();
+  plan->base = View(plan->base_schema);
+  plan->schema = plan->base_schema;
+  plan->outputs.clear();
+  for (int i = 0; i < plan->schema.attribute_count(); ++i) plan->outputs.push_back(MakeInputNode(plan->schema, i));
+  plan->predicate.reset();
+  return Success();
+}
+
+}  // namespace internal
+
+// ------------------------------------------------------------------ factories
+Operation* ScanView(const View& view) { return new ScanViewOperation(view); }
+Operation* Compute(const Expression* computation, Operation* child) { return new ComputeOperation(computation, child); }
+Operation* Filter(const Expression* predicate, const SingleSourceProjector* projector, Operation* child) {
+  return new FilterOperation(predicate, projector, child);
+}
+Operation* Project(const SingleSourceProjector* projector, Operation* child) { return new ProjectOperation(projector, child); }
+Operation* GroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
+                          GroupAggregateOptions* options, Operation* child) {
+  return new GroupAggregateOperation(group_by, aggregation, options, child);
+}
+Operation* ScalarAggregate(AggregationSpecification* aggregation, Operation* child) {
+  return new GroupAggregateOperation(NULL, aggregation, NULL, child);
+}
+Operation* Sort(const SortOrder* sort_order, const SingleSourceProjector* result_projector, size_t, Operation* child) {
+  return new SortOperation(sort_order, result_projector, child);
+}
+
+SortOrder::~SortOrder() { for (size_t i = 0; i < keys_.size(); ++i) delete keys_[i].first; }
+FailureOrVoid SortOrder::Bind(const TupleSchema& schema, vector<std::pair<int, ColumnOrder> >* keys) const {
+  for (size_t i = 0; i < keys_.size(); ++i) {
+    FailureOrOwned<const BoundSingleSourceProjector> p = keys_[i].first->Bind(schema);
+    PROPAGATE_ON_FAILURE(p);
+    for (int c = 0; c < p->result_schema().attribute_count(); ++c) {
+      const DataType t = p->result_schema().attribute(c).type();
+      if (t == STRING || t == BINARY) {
+        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length sort keys are not on the B200 hot path (SURVEY 8f)"));
+      }
+      keys->push_back(std::make_pair(p->source_attribute_position(c), keys_[i].second));
+    }
+  }
+  return Success();
+}
+
+// ------------------------------------------------------------------ HashJoinOperation
+HashJoinOperation::HashJoinOperation(JoinType join_type, const SingleSourceProjector* lhs_key_selector,
+                                     const SingleSourceProjector* rhs_key_selector,
+                                     const MultiSourceProjector* result_projector, KeyUniqueness rhs_key_uniqueness,
+                                     Operation* lhs_child, Operation* rhs_child)
+    : BasicOperation(lhs_child, rhs_child), join_type_(join_type), lhs_key_selector_(lhs_key_selector),
+      rhs_key_selector_(rhs_key_selector), result_projector_(result_projector),
+      rhs_key_uniqueness_(rhs_key_uniqueness) {}
+HashJoinOperation::~HashJoinOperation() {}
+
+FailureOrOwned<Cursor> HashJoinOperation::CreateCursor() const {
+  // hash_join.cc:713-726
+  if (join_type_ != INNER && join_type_ != LEFT_OUTER) {
+    THROW(new Exception(ERROR_NOT_IMPLEMENTED, "Join type " + JoinType_Name(join_type_) + " not implemented in hash join"));
+  }
+  FailureOrOwned<Cursor> lhs = child_at(0)->CreateCursor();
+  PROPAGATE_ON_FAILURE(lhs);
+  FailureOrOwned<Cursor> rhs = child_at(1)->CreateCursor();
+  PROPAGATE_ON_FAILURE(rhs);
+  FailureOrOwned<const BoundSingleSourceProjector> lk = lhs_key_selector_->Bind(lhs->schema());
+  PROPAGATE_ON_FAILURE(lk);
+  FailureOrOwned<const BoundSingleSourceProjector> rk = rhs_key_selector_->Bind(rhs->schema());
+  PROPAGATE_ON_FAILURE(rk);
+  {
+    // key types must agree, except that integer keys of different widths / signedness are
+    // compared by value (operators::Equal, row_hash_set.cc key comparators)
+    bool ok = lk->result_schema().attribute_count() == rk->result_schema().attribute_count();
+    for (int i = 0; ok && i < lk->result_schema().attribute_count(); ++i) {
+      const DataType a = lk->result_schema().attribute(i).type(), b = rk->result_schema().attribute(i).type();
+      ok = a == b || (GetTypeInfo(a).is_integer() && GetTypeInfo(b).is_integer());
+    }
+    if (!ok) {
+      THROW(new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, "Hash join key columns differ in number or type: (" +
+                                                             lk->result_schema().GetHumanReadableSpecification() + ") vs (" +
+                                                             rk->result_schema().GetHumanReadableSpecification() + ")"));
+    }
+  }
+  vector<int> lkeys, rkeys;
+  for (int i = 0; i < lk->result_schema().attribute_count(); ++i) {
+    const DataType t = lk->result_schema().attribute(i).type();
+    if (t == STRING || t == BINARY) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length join keys are not on the B200 hot path (SURVEY 8f)"));
+    }
+    lkeys.push_back(lk->source_attribute_position(i));
+    rkeys.push_back(rk->source_attribute_position(i));
+  }
+  // LEFT_OUTER: the rhs columns become nullable in the result (hash_join.h:37-38)
+  TupleSchema rhs_schema;
+  for (int i = 0; i < rhs->schema().attribute_count(); ++i) {
+    const Attribute& a = rhs->schema().attribute(i);
+    rhs_schema.add_attribute(Attribute(a.name(), a.type(), join_type_ == LEFT_OUTER ? NULLABLE : a.nullability()));
+  }
+  vector<const TupleSchema*> sources;
+  sources.push_back(&lhs->schema());
+  sources.push_back(&rhs_schema);
+  FailureOrOwned<const BoundMultiSourceProjector> proj = result_projector_->Bind(sources);
+  PROPAGATE_ON_FAILURE(proj);
+  const TupleSchema result = proj->result_schema();
+  return Success(static_cast<Cursor*>(new HashJoinCursor(result, buffer_allocator(), lhs.release(), rhs.release(), join_type_,
+                                                         rhs_key_uniqueness_, lkeys, rkeys, proj.release())));
+}
+
+// ------------------------------------------------------------------ Table
+Table::Table(const TupleSchema& schema, BufferAllocator* allocator)
+    : block_(new Block(schema, allocator)), view_(schema) {}
+Table::~Table() {}
+bool Table::ReserveRowCapacity(rowcount_t needed) {
+  if (needed <= block_->row_capacity()) return true;
+  rowcount_t cap = block_->row_capacity() ? block_->row_capacity() : 16;
+  while (cap < needed) cap *= 2;
+  const rowcount_t rows = view_.row_count();
+  if (!block_->Reallocate(cap)) return false;
+  view_.ResetFromSubRange(block_->view(), 0, rows);
+  return true;
+}
+rowid_t Table::AddRow() {
+  if (!ReserveRowCapacity(view_.row_count() + 1)) return -1;
+  const rowcount_t r = view_.row_count();
+  view_.ResetFromSubRange(block_->view(), 0, r + 1);
+  return static_cast<rowid_t>(r);
+}
+rowcount_t Table::AppendView(const View& view) {
+  const rowcount_t rows = view_.row_count(), n = view.row_count();
+  if (!ReserveRowCapacity(rows + n)) return 0;
+  for (int c = 0; c < view.column_count(); ++c) {
+    const size_t w = view.column(c).type_info().size();
+    memcpy(static_cast<char*>(block_->mutable_data(c)) + rows * w, view.column(c).data().raw(), n * w);
+    if (bool* hn = block_->mutable_is_null(c)) {
+      if (view.column(c).is_null()) memcpy(hn + rows, view.column(c).is_null(), n);
+      else memset(hn + rows, 0, n);
+    }
+  }
+  view_.ResetFromSubRange(block_->view(), 0, rows + n);
+  return n;
+}
+FailureOrOwned<Cursor> Table::CreateCursor() const { return Success(static_cast<Cursor*>(new ViewCursor(view_))); }
+
+TableRowWriter& TableRowWriter::AddRow() {
+  row_ = table_->AddRow();
+  col_ = 0;
+  if (row_ < 0) ok_ = false;
+  return *this;
+}
+void TableRowWriter::CheckSuccess() const {
+  if (!ok_) { fprintf(stderr, "FATAL: TableRowWriter failed (out of memory)\n"); abort(); }
+}
+
+}  // namespace supersonic

@@ -461,6 +461,8 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
     }
   }
 
+  if (flags & SSPLAN_BIND_ONLY) return r->code;
+
   const rowcount_t max_rows =
       next_max_rows > 0 ? static_cast<rowcount_t>(next_max_rows) : Cursor::kDefaultRowCount;
   t0 = WallNow();

@@ -40,6 +40,7 @@ typedef struct ssplan_result ssplan_result;
 
 enum {
   SSPLAN_DISCARD = 1,        /* drain the cursor but do not materialise rows (timing) */
+  SSPLAN_BIND_ONLY = 2,      /* CreateCursor only: report the result schema, never call Next */
 };
 
 /* Builds and runs `plan` over `tables`. Always sets *out (free it with

@@ -24,6 +24,7 @@ NAME_OF = {INT32: "INT32", INT64: "INT64", UINT32: "UINT32", UINT64: "UINT64", F
 DTYPE_OF_NAME = {v: k for k, v in NAME_OF.items()}
 
 SSPLAN_DISCARD = 1
+SSPLAN_BIND_ONLY = 2
 
 OK = 0
 ERROR_MEMORY_EXCEEDED = 102
@@ -124,7 +125,7 @@ class PlanLib(object):
                 dt = L.ssplan_result_col_dtype(out, i)
                 dtypes.append(dt)
                 nullable.append(bool(L.ssplan_result_col_nullable(out, i)))
-                if code != 0 or (flags & SSPLAN_DISCARD):
+                if code != 0 or (flags & (SSPLAN_DISCARD | SSPLAN_BIND_ONLY)):
                     columns.append(None)
                     nulls.append(None)
                     continue

@@ -1,0 +1,240 @@
+"""Shared test material: known-answer vectors taken from the reference's own tests (cited per
+case) and randomised plan families. `N` marks a NULL cell."""
+import numpy as np
+
+from supersonic_b200 import ssplan as sp
+
+N = None
+
+
+def col(name, dtype, values):
+    """Column from a python list; None entries become NULL."""
+    nulls = [v is None for v in values]
+    data = [0 if v is None else v for v in values]
+    if any(nulls):
+        return sp.Column(name, dtype, data, is_null=nulls)
+    return sp.Column(name, dtype, data)
+
+
+def ncol(name, dtype, values):
+    """As col() but always NULLABLE."""
+    nulls = [v is None for v in values]
+    data = [0 if v is None else v for v in values]
+    return sp.Column(name, dtype, data, is_null=nulls)
+
+
+# (id, plan, tables, expected {name: list}, ordered)
+GOLDEN = [
+    # expression/core/arithmetic_expressions_test.cc:68-99 (Plus INT64)
+    ("plus_int64", "(compute (plus (col a) (col b)) (scan 0))",
+     [[col("a", sp.INT64, [-1, -2, 2, 13]), col("b", sp.INT64, [1, 2, 2, 1])]],
+     {"(a + b)": [0, 0, 4, 14]}, True),
+    # :80-92 nullable rows
+    ("plus_nullable", "(compute (plus (col a) (col b)) (scan 0))",
+     [[ncol("a", sp.INT64, [1, N, 3, N]), ncol("b", sp.INT64, [1, 2, N, N])]],
+     {"(a + b)": [2, N, N, N]}, True),
+    # :94-99 INT64 + INT32 promotes
+    ("plus_promote", "(compute (plus (col a) (col b)) (scan 0))",
+     [[col("a", sp.INT64, [5, -7]), col("b", sp.INT32, [3, 7])]],
+     {"(a + CAST_INT32_TO_INT64(b))": [8, 0]}, True),
+    # :127-144 Minus / Multiply incl. NULL rows
+    ("minus", "(compute (minus (col a) (col b)) (scan 0))",
+     [[ncol("a", sp.INT32, [3, 10, N]), ncol("b", sp.INT32, [1, 20, 4])]],
+     {"(a - b)": [2, -10, N]}, True),
+    ("multiply", "(compute (multiply (col a) (col b)) (scan 0))",
+     [[ncol("a", sp.INT32, [20, N, -3]), ncol("b", sp.INT32, [20, 2, 4])]],
+     {"(a * b)": [400, N, -12]}, True),
+    # :146-218 Divide quiet / nulling
+    ("divide_quiet", "(compute (divide_quiet (col a) (col b)) (scan 0))",
+     [[col("a", sp.DOUBLE, [1.0, 0.0, 6.0]), col("b", sp.DOUBLE, [0.0, 0.0, 4.0])]],
+     {"(a /. b)": [float("inf"), float("nan"), 1.5]}, True),
+    ("divide_nulling", "(compute (divide_nulling (col a) (col b)) (scan 0))",
+     [[col("a", sp.INT32, [1, 0, 6]), col("b", sp.INT32, [0, 0, 4])]],
+     {"(CAST_INT32_TO_DOUBLE(a) /. CAST_INT32_TO_DOUBLE(b))": [N, N, 1.5]}, True),
+    ("cpp_divide_nulling", "(compute (cpp_divide_nulling (col a) (col b)) (scan 0))",
+     [[col("a", sp.INT32, [7, -7, 5]), col("b", sp.INT32, [2, 2, 0])]],
+     {"(a / b)": [3, -3, N]}, True),
+    ("modulus_nulling", "(compute (modulus_nulling (col a) (col b)) (scan 0))",
+     [[col("a", sp.INT32, [7, -7, 5]), col("b", sp.INT32, [3, 3, 0])]],
+     {"(a % b)": [1, -1, N]}, True),
+    # cursor/core/compute_test.cc:51-79
+    ("compute_sum", "(compute (as sum (plus (col col1) (col col3))) (scan 0))",
+     [[ncol("col1", sp.INT64, [12, 13, N]), col("col2", sp.INT64, [1, 2, 3]), ncol("col3", sp.INT64, [5, 6, N])]],
+     {"sum": [17, 19, N]}, True),
+    # elementary_expressions_test.cc: three-valued logic truth tables
+    ("and_3vl", "(compute (and (col a) (col b)) (scan 0))",
+     [[ncol("a", sp.BOOL, [True, True, True, False, False, False, N, N, N]),
+       ncol("b", sp.BOOL, [True, False, N, True, False, N, True, False, N])]],
+     {"(a AND b)": [True, False, N, False, False, False, N, False, N]}, True),
+    ("or_3vl", "(compute (or (col a) (col b)) (scan 0))",
+     [[ncol("a", sp.BOOL, [True, True, True, False, False, False, N, N, N]),
+       ncol("b", sp.BOOL, [True, False, N, True, False, N, True, False, N])]],
+     {"(a OR b)": [True, True, True, True, False, N, True, N, N]}, True),
+    ("not_3vl", "(compute (not (col a)) (scan 0))",
+     [[ncol("a", sp.BOOL, [True, False, N])]], {"(NOT a)": [False, True, N]}, True),
+    ("if_null_cond", "(compute (if (col c) (col a) (col b)) (scan 0))",
+     [[ncol("c", sp.BOOL, [True, False, N]), col("a", sp.INT32, [1, 2, 3]), col("b", sp.INT32, [10, 20, 30])]],
+     {"IF c THEN a ELSE b": [1, 20, 30]}, True),
+    ("ifnull", "(compute (if_null (col a) (col b)) (scan 0))",
+     [[ncol("a", sp.INT32, [1, N, N]), ncol("b", sp.INT32, [5, 6, N])]],
+     {"IFNULL(a, b)": [1, 6, N]}, True),
+    # cursor/core/filter_test.cc:151-329
+    ("filter_some", "(filter (col p) (named v) (scan 0))",
+     [[col("p", sp.BOOL, [True, False, True, False, True]), col("v", sp.INT32, [1, 2, 3, 4, 5])]],
+     {"v": [1, 3, 5]}, True),
+    ("filter_none", "(filter (col p) (named v) (scan 0))",
+     [[col("p", sp.BOOL, [False, False]), col("v", sp.INT32, [1, 2])]], {"v": []}, True),
+    ("filter_null_predicate", "(filter (col p) (all) (scan 0))",
+     [[ncol("p", sp.BOOL, [True, N, False, True]), ncol("v", sp.INT64, [1, 2, 3, N])]],
+     {"p": [True, True], "v": [1, N]}, True),
+    ("filter_projected_away", "(filter (less (col k) (i32 3)) (named v) (scan 0))",
+     [[col("k", sp.INT32, [1, 5, 2, 7]), col("v", sp.DOUBLE, [0.5, 1.5, 2.5, 3.5])]],
+     {"v": [0.5, 2.5]}, True),
+    # cursor/core/aggregate_groups_test.cc:102-218, :272-294, :330-353, :379-428
+    ("group_sum", "(group (named k) (aggs (SUM v sum) (COUNT v cnt) (COUNT \"\" cnt_all)) (scan 0))",
+     [[col("k", sp.INT32, [1, 3, 1, 3, 1]), ncol("v", sp.INT32, [3, -3, 4, -5, N])]],
+     {"k": [1, 3], "sum": [7, -8], "cnt": [2, 2], "cnt_all": [3, 2]}, False),
+    ("group_all_null_sum", "(group (named k) (aggs (SUM v sum) (MIN v mn) (MAX v mx)) (scan 0))",
+     [[col("k", sp.INT32, [1, 1, 2]), ncol("v", sp.INT64, [N, N, 9])]],
+     {"k": [1, 2], "sum": [N, 9], "mn": [N, 9], "mx": [N, 9]}, False),
+    ("group_null_key", "(group (named k) (aggs (SUM v s)) (scan 0))",
+     [[ncol("k", sp.INT32, [1, N, 1, N]), col("v", sp.INT32, [1, 2, 3, 4])]],
+     {"k": [N, 1], "s": [6, 4]}, False),
+    ("group_two_keys", "(group (named a b) (aggs (SUM v s) (MIN v m) (COUNT \"\" c)) (scan 0))",
+     [[col("a", sp.INT32, [1, 1, 2, 1, 2]), col("b", sp.INT64, [7, 8, 7, 7, 7]), col("v", sp.DOUBLE, [1.0, 2.0, 3.0, 4.0, 5.0])]],
+     {"a": [1, 1, 2], "b": [7, 8, 7], "s": [5.0, 2.0, 8.0], "m": [1.0, 2.0, 3.0], "c": [2, 1, 2]}, False),
+    ("group_sum_int32_to_int64", "(group (named k) (aggs (SUM v s INT64)) (scan 0))",
+     [[col("k", sp.INT32, [1, 1]), col("v", sp.INT32, [2000000000, 2000000000])]],
+     {"k": [1], "s": [4000000000]}, False),
+    ("group_empty", "(group (named k) (aggs (SUM v s)) (scan 0))",
+     [[col("k", sp.INT32, []), col("v", sp.INT32, [])]], {"k": [], "s": []}, False),
+    # cursor/core/aggregate_scalar_test.cc:53-90
+    ("scalar_agg", "(scalar_agg (aggs (SUM v s) (COUNT \"\" c) (MAX v m)) (scan 0))",
+     [[col("v", sp.INT64, [5, 7, -2])]], {"s": [10], "c": [3], "m": [7]}, True),
+    ("scalar_agg_empty", "(scalar_agg (aggs (SUM v s) (COUNT \"\" c)) (scan 0))",
+     [[col("v", sp.INT64, [])]], {"s": [N], "c": [0]}, True),
+    # test/guide/primer.cc GroupAggregateTest
+    ("primer_group", "(group (named key) (aggs (SUM data data_sums)) (scan 0))",
+     [[col("key", sp.INT32, [1, 2, 3, 1, 2, 3, 1, 2]), col("data", sp.DOUBLE, [1.5, 3.0, 3.0, 7.6, 5.5, 2.0, 1.6, 9.5])]],
+     {"key": [1, 2, 3], "data_sums": [1.5 + 7.6 + 1.6, 3.0 + 5.5 + 9.5, 3.0 + 2.0]}, False),
+    # cursor/core/hash_join_test.cc:140-238, 240-281, 305-319, 355-382
+    ("join_inner_unique",
+     "(hash_join INNER (named k) (named k2) (multi (0 (all)) (1 (named w))) UNIQUE (scan 0) (scan 1))",
+     [[col("k", sp.INT64, [1, 2, 3, 4, 5]), col("v", sp.INT64, [10, 20, 30, 40, 50])],
+      [col("k2", sp.INT64, [6, 5, 4, 3, 2, 1]), col("w", sp.INT64, [600, 500, 400, 300, 200, 100])]],
+     {"k": [1, 2, 3, 4, 5], "v": [10, 20, 30, 40, 50], "w": [100, 200, 300, 400, 500]}, True),
+    ("join_left_outer",
+     "(hash_join LEFT_OUTER (named k) (named k2) (multi (0 (all)) (1 (named w))) UNIQUE (scan 0) (scan 1))",
+     [[col("k", sp.INT64, [1, 2, 3]), col("v", sp.INT64, [10, 20, 30])],
+      [col("k2", sp.INT64, [3, 1]), col("w", sp.INT64, [300, 100])]],
+     {"k": [1, 2, 3], "v": [10, 20, 30], "w": [100, N, 300]}, True),
+    ("join_duplicates",
+     "(hash_join INNER (named k) (named k2) (multi (0 (named k v)) (1 (named w))) NOT_UNIQUE (scan 0) (scan 1))",
+     [[col("k", sp.INT32, [2, 3, 2]), col("v", sp.INT32, [1, 2, 3])],
+      [col("k2", sp.INT32, [2, 2, 3, 2]), col("w", sp.INT32, [10, 20, 30, 40])]],
+     {"k": [2, 2, 2, 3, 2, 2, 2], "v": [1, 1, 1, 2, 3, 3, 3], "w": [10, 20, 40, 30, 10, 20, 40]}, True),
+    ("join_two_keys",
+     "(hash_join INNER (named a b) (named a2 b2) (multi (0 (named v)) (1 (named w))) UNIQUE (scan 0) (scan 1))",
+     [[col("a", sp.INT32, [1, 1, 2]), col("b", sp.INT64, [1, 2, 1]), col("v", sp.INT32, [10, 20, 30])],
+      [col("a2", sp.INT32, [2, 1]), col("b2", sp.INT64, [1, 2]), col("w", sp.INT32, [7, 8])]],
+     {"v": [20, 30], "w": [8, 7]}, True),
+    ("join_null_keys",
+     "(hash_join LEFT_OUTER (named k) (named k2) (multi (0 (named v)) (1 (named w))) NOT_UNIQUE (scan 0) (scan 1))",
+     [[ncol("k", sp.INT32, [1, N, 2]), col("v", sp.INT32, [10, 20, 30])],
+      [ncol("k2", sp.INT32, [N, 1, N]), col("w", sp.INT32, [7, 8, 9])]],
+     {"v": [10, 20, 30], "w": [8, N, N]}, True),
+    ("join_empty_rhs",
+     "(hash_join INNER (named k) (named k2) (multi (0 (named v)) (1 (named w))) UNIQUE (scan 0) (scan 1))",
+     [[col("k", sp.INT32, [1, 2]), col("v", sp.INT32, [10, 20])], [col("k2", sp.INT32, []), col("w", sp.INT32, [])]],
+     {"v": [], "w": []}, True),
+    # cursor/core/sort_test.cc:121-381
+    ("sort_asc_nulls_first", "(sort (order (k ASC)) (all) (scan 0))",
+     [[ncol("k", sp.INT32, [3, N, 1, 2]), col("v", sp.INT32, [30, 0, 10, 20])]],
+     {"k": [N, 1, 2, 3], "v": [0, 10, 20, 30]}, True),
+    ("sort_desc_nulls_last", "(sort (order (k DESC)) (all) (scan 0))",
+     [[ncol("k", sp.INT32, [3, N, 1, 2]), col("v", sp.INT32, [30, 0, 10, 20])]],
+     {"k": [3, 2, 1, N], "v": [30, 20, 10, 0]}, True),
+    ("sort_two_keys", "(sort (order (a ASC) (b DESC)) (named b a) (scan 0))",
+     [[col("a", sp.INT64, [2, 1, 2, 1]), col("b", sp.DOUBLE, [0.5, -1.0, 7.0, 3.0])]],
+     {"b": [3.0, -1.0, 7.0, 0.5], "a": [1, 1, 2, 2]}, True),
+]
+
+
+def check_result(r, expected, ordered):
+    """Compares a PlanResult with {name: list}; NULL cells compare by is_null only
+    (testing/view_comparator.cc:54-61); unordered results are sorted on all columns first."""
+    assert r.code == 0, (r.code, r.error)
+    assert r.names == list(expected.keys()), (r.names, list(expected.keys()))
+    n = len(next(iter(expected.values()))) if expected else 0
+    assert r.rows == n, (r.rows, n)
+    got_rows, want_rows = [], []
+    for i in range(n):
+        g, w = [], []
+        for j, name in enumerate(r.names):
+            isn = bool(r.nulls[j][i]) if r.nulls[j] is not None else False
+            v = r.columns[j][i].item()
+            g.append(("null",) if isn else ("v", _norm(v)))
+            e = expected[name][i]
+            w.append(("null",) if e is None else ("v", _norm(e)))
+        got_rows.append(tuple(g))
+        want_rows.append(tuple(w))
+    if not ordered:
+        got_rows.sort(key=repr)
+        want_rows.sort(key=repr)
+    assert got_rows == want_rows, (got_rows, want_rows)
+
+
+def _norm(v):
+    if isinstance(v, float):
+        if v != v:
+            return "nan"
+        return float(v)
+    if isinstance(v, bool):
+        return bool(v)
+    return v
+
+
+def same_results(a, b, ordered=True, sort_cols=None):
+    """Bit-exact comparison of two PlanResults (masking data under NULL)."""
+    assert a.code == b.code, (a.code, a.error, b.code, b.error)
+    if a.code != 0:
+        return
+    assert a.names == b.names and a.dtypes == b.dtypes and a.nullable == b.nullable, \
+        (a.names, b.names, a.dtypes, b.dtypes, a.nullable, b.nullable)
+    assert a.rows == b.rows, (a.rows, b.rows)
+    if a.rows == 0:
+        return
+    ca, cb = _masked(a), _masked(b)
+    if not ordered:
+        ca, cb = _sorted(ca, sort_cols), _sorted(cb, sort_cols)
+    for j in range(len(ca)):
+        va, na = ca[j]
+        vb, nb = cb[j]
+        assert np.array_equal(na, nb), "null vectors differ in column %s" % a.names[j]
+        assert np.array_equal(va.view(np.uint8), vb.view(np.uint8)), \
+            "column %s differs: %s vs %s" % (a.names[j], va[:8], vb[:8])
+
+
+def _masked(r):
+    out = []
+    for j in range(len(r.columns)):
+        v = r.columns[j].copy()
+        n = r.nulls[j] if r.nulls[j] is not None else np.zeros(r.rows, dtype=np.bool_)
+        if v.dtype == np.bool_:
+            v = v.astype(np.uint8)
+        v[n] = 0
+        if v.dtype.kind == "f":
+            v = v + 0.0   # canonical zero sign is not touched; NaN payloads are kept bit-exact
+        out.append((v, n))
+    return out
+
+
+def _sorted(cols, sort_cols):
+    keys = []
+    idx = list(range(len(cols))) if sort_cols is None else sort_cols
+    for j in reversed(idx):
+        v, n = cols[j]
+        keys.append(v.view(np.uint64) if v.dtype.itemsize == 8 else v.astype(np.int64))
+        keys.append(n)
+    order = np.lexsort(keys)
+    return [(v[order], n[order]) for v, n in cols]

@@ -1,0 +1,52 @@
+"""The C-ABI library loads and exports every entry point include/supersonic_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import os
+
+import pytest
+
+from supersonic_b200 import capi
+
+
+def test_header_symbols_exported(built):
+    lib = capi.load()
+    names = capi.declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.ssb_abi_version() == 1
+
+
+def test_no_device_fails_loudly(built):
+    """Without a B200 the product must refuse to run; there is no CPU path to fall back to."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.SsbError):
+        capi.Context(0)
+
+
+def test_plan_driver_reports_missing_device(b200):
+    import numpy as np
+    import torch
+    from supersonic_b200 import ssplan as sp
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cols = [sp.Column("a", sp.INT64, np.arange(10))]
+    r = b200.run("(compute (plus (col a) (i64 1)) (scan 0))", [cols])
+    assert r.code != 0 and "no usable B200" in r.error
+
+
+def test_host_generator_matches_definition(built):
+    import ctypes as C
+    import numpy as np
+    lib = capi.load()
+    out = np.zeros(16, dtype=np.uint64)
+    lib.ssb_generate_host(out.ctypes.data, 16, 5, 42, 3, 0, 0, 0)
+
+    def splitmix(x):
+        x = (x + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return x ^ (x >> 31)
+    want = [splitmix(((42 ^ ((3 * 0x9E3779B97F4A7C15) & (2**64 - 1))) + 5 + i) & (2**64 - 1)) for i in range(16)]
+    assert [int(v) for v in out] == want

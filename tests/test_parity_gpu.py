@@ -1,0 +1,257 @@
+"""Parity of the CUDA path with the oracle (the unmodified reference), through the same
+plan text compiled against both supersonic.h implementations. Integer, bool, index and row
+order results must be bit-exact; DOUBLE sums are bit-exact on exactly-summable payloads and
+within 1 ulp per addend otherwise (tolerance stated at the test)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from cases import GOLDEN, check_result, same_results
+from supersonic_b200 import ssplan as sp
+
+pytestmark = pytest.mark.gpu
+
+NP = {sp.INT32: np.int32, sp.INT64: np.int64, sp.UINT32: np.uint32, sp.UINT64: np.uint64,
+      sp.FLOAT: np.float32, sp.DOUBLE: np.float64, sp.BOOL: np.bool_, sp.DATE: np.int32,
+      sp.DATETIME: np.int64}
+TNAME = {sp.INT32: "i32", sp.INT64: "i64", sp.UINT32: "u32", sp.UINT64: "u64", sp.FLOAT: "f32",
+         sp.DOUBLE: "f64", sp.BOOL: "b", sp.DATE: "d", sp.DATETIME: "dt"}
+
+
+def random_column(rng, name, dtype, n, nullable, small=False):
+    if dtype == sp.BOOL:
+        data = rng.integers(0, 2, n).astype(np.bool_)
+    elif dtype in (sp.FLOAT, sp.DOUBLE):
+        data = (rng.integers(-1000, 1000, n) / 8.0).astype(NP[dtype])
+    else:
+        info = np.iinfo(NP[dtype])
+        lo, hi = (max(info.min, -50), min(info.max, 50)) if small else (max(info.min, -2**31), min(info.max, 2**31 - 1))
+        data = rng.integers(lo, hi, n, dtype=np.int64).astype(NP[dtype])
+        # sprinkle zeros and extremes
+        data[rng.integers(0, n, max(1, n // 50))] = 0
+    nulls = (rng.random(n) < 0.1) if nullable else None
+    return sp.Column(name, dtype, data, is_null=nulls)
+
+
+def table(rng, n, small=False):
+    cols = []
+    for dt, nm in TNAME.items():
+        cols.append(random_column(rng, nm, dt, n, False, small))
+        cols.append(random_column(rng, "n" + nm, dt, n, True, small))
+    return cols
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c[0] for c in GOLDEN])
+@pytest.mark.parametrize("next_rows", [0, 1, 3])
+def test_reference_vectors(b200, case, next_rows):
+    _, plan, tables, expected, ordered = case
+    check_result(b200.run(plan, tables, next_max_rows=next_rows), expected, ordered)
+
+
+ARITH = ["plus", "minus", "multiply", "divide_quiet", "divide_nulling", "cpp_divide_nulling", "modulus_nulling"]
+CMP = ["equal", "not_equal", "less", "less_or_equal", "greater", "greater_or_equal"]
+NUMS = ["i32", "i64", "u32", "u64", "f32", "f64"]
+INTS = ["i32", "i64", "u32", "u64"]
+
+
+@pytest.mark.parametrize("n", [1, 31, 1024, 5000, 100003])
+def test_expression_matrix(ref, b200, n):
+    rng = np.random.default_rng(n)
+    cols = table(rng, n, small=True)
+    exprs = []
+    for op in ARITH:
+        for x, y in itertools.product(NUMS, NUMS):
+            if op.startswith("modulus") and ("f" in x or "f" in y):
+                continue
+            exprs.append("(%s (col %s) (col n%s))" % (op, x, y))
+    for op in CMP:
+        for x, y in itertools.product(NUMS + ["b", "d", "dt"], NUMS + ["b", "d", "dt"]):
+            exprs.append("(%s (col n%s) (col %s))" % (op, x, y))
+    for op in ["and", "or", "and_not", "xor"]:
+        exprs.append("(%s (col nb) (less (col ni32) (col i64)))" % op)
+        exprs.append("(%s (col b) (col nb))" % op)
+    for op in ["bitwise_and", "bitwise_or", "bitwise_xor", "bitwise_and_not"]:
+        for x, y in itertools.product(INTS, INTS):
+            exprs.append("(%s (col %s) (col n%s))" % (op, x, y))
+    for x in NUMS:
+        exprs.append("(negate (col n%s))" % x)
+        exprs.append("(is_null (col n%s))" % x)
+        exprs.append("(if_null (col n%s) (col %s))" % (x, x))
+        exprs.append("(if (col nb) (col %s) (col n%s))" % (x, x))
+        exprs.append("(nulling_if (col nb) (col %s) (col n%s))" % (x, x))
+        for t in ["INT64", "DOUBLE", "FLOAT", "UINT64", "INT32", "UINT32"]:
+            exprs.append("(cast %s (col n%s))" % (t, x))
+    for x in INTS:
+        exprs.append("(is_odd (col n%s))" % x)
+        exprs.append("(is_even (col %s))" % x)
+        exprs.append("(bitwise_not (col n%s))" % x)
+        exprs.append("(shift_left (col %s) (i32 3))" % x)
+        exprs.append("(shift_right (col n%s) (i32 2))" % x)
+    exprs += ["(not (col nb))", "(cast DATETIME (col nd))",
+              "(plus (multiply (col i64) (col i32)) (minus (col f64) (col nu32)))",
+              "(if (less (col i32) (i32 0)) (negate (col i32)) (col i32))",
+              "(and (less (col i32) (col i64)) (or (is_null (col nf64)) (greater (col nf64) (f64 1.5))))"]
+    # evaluate in groups through one Compute each (also exercises multi-output programs)
+    bad = []
+    for i in range(0, len(exprs), 6):
+        chunk = exprs[i:i + 6]
+        plan = "(compute (compound %s) (scan 0))" % " ".join("(as c%d %s)" % (k, e) for k, e in enumerate(chunk))
+        a = ref.run(plan, [cols])
+        b = b200.run(plan, [cols])
+        try:
+            same_results(a, b)
+        except AssertionError as err:
+            # narrow down to the single expression
+            for e in chunk:
+                p1 = "(compute (as c %s) (scan 0))" % e
+                try:
+                    same_results(ref.run(p1, [cols]), b200.run(p1, [cols]))
+                except AssertionError as err1:
+                    bad.append((e, str(err1)[:200]))
+            if not bad:
+                bad.append((chunk, str(err)[:200]))
+    assert not bad, bad[:10]
+
+
+def test_signaling_division_fails(ref, b200):
+    cols = [sp.Column("a", sp.INT32, [1, 2, 3]), sp.Column("b", sp.INT32, [1, 0, 3])]
+    for op in ["divide_signaling", "cpp_divide_signaling", "modulus_signaling"]:
+        plan = "(compute (%s (col a) (col b)) (scan 0))" % op
+        a, b = ref.run(plan, [cols]), b200.run(plan, [cols])
+        assert a.code == 104 and b.code == 104, (op, a.code, b.code, b.error)
+    ok = [sp.Column("a", sp.INT32, [1, 2, 3]), sp.Column("b", sp.INT32, [1, 2, 3])]
+    same_results(ref.run("(compute (cpp_divide_signaling (col a) (col b)) (scan 0))", [ok]),
+                 b200.run("(compute (cpp_divide_signaling (col a) (col b)) (scan 0))", [ok]))
+
+
+@pytest.mark.parametrize("n,sel", [(10_000_000, 2**19), (1_000_003, 2**10), (2049, 2**20), (1024, 0)])
+def test_filter_project_c1(ref, b200, n, sel):
+    """BASELINE config 1: Compute(a*b+c) then Filter(d<K) over 4 x INT64, bit-exact, in order."""
+    rng = np.random.default_rng(42)
+    cols = [sp.Column("a", sp.INT64, rng.integers(-2**31, 2**31, n)),
+            sp.Column("b", sp.INT64, rng.integers(-2**31, 2**31, n)),
+            sp.Column("c", sp.INT64, rng.integers(-2**62, 2**62, n)),
+            sp.Column("d", sp.INT64, rng.integers(0, 2**20, n))]
+    plan = ("(filter (less (col d) (i64 %d)) (named e) (compute (compound (as e (plus (multiply "
+            "(col a) (col b)) (col c))) (col d)) (scan 0)))" % sel)
+    same_results(ref.run(plan, [cols], next_max_rows=16384), b200.run(plan, [cols], next_max_rows=16384))
+    plan_b = ("(filter (less (col d) (i64 %d)) (all) (compute (compound (as e (plus (multiply "
+              "(col a) (col b)) (col c))) (col a) (col b) (col c) (col d)) (scan 0)))" % sel)
+    same_results(ref.run(plan_b, [cols], next_max_rows=16384), b200.run(plan_b, [cols], next_max_rows=16384))
+
+
+def test_filter_with_nulls_and_stacked_operators(ref, b200):
+    rng = np.random.default_rng(3)
+    cols = table(rng, 70001)
+    plans = [
+        "(filter (less (col ni32) (col i64)) (named ni64 f64 nb) (scan 0))",
+        "(filter (col nb) (all) (scan 0))",
+        "(project (named x) (filter (greater (col x) (i64 0)) (all) (compute (compound (as x (plus (col i64) (col ni32))) (col b)) (scan 0))))",
+        "(filter (col b) (named y) (compute (as y (multiply (col x) (col x))) (filter (less (col x) (f64 100)) (named x b) (compute (compound (as x (col f64)) (col b)) (scan 0)))))",
+        "(compute (plus (col s) (i64 1)) (group (named b) (aggs (SUM i64 s)) (scan 0)))",
+    ]
+    for plan in plans:
+        same_results(ref.run(plan, [cols]), b200.run(plan, [cols]), ordered="group" not in plan)
+
+
+@pytest.mark.parametrize("n,groups", [(1_000_000, 1000), (2_000_000, 300_000), (100_000, 3), (5000, 5000)])
+def test_group_aggregate(ref, b200, n, groups):
+    """C3 shape: SUM(DOUBLE) + COUNT per INT64 key. The payload k * 2^-10 (k < 2^20) makes every
+    partial sum exactly representable, so the result is bit-exact in any order."""
+    rng = np.random.default_rng(n)
+    cols = [sp.Column("k", sp.INT64, rng.integers(0, groups, n)),
+            sp.Column("v", sp.DOUBLE, rng.integers(0, 2**20, n) / 1024.0),
+            sp.Column("w", sp.INT32, rng.integers(-1000, 1000, n), is_null=rng.random(n) < 0.2),
+            sp.Column("u", sp.UINT64, rng.integers(0, 2**40, n))]
+    plan = ("(group (named k) (aggs (SUM v sum_v) (COUNT \"\" cnt) (MIN w mn) (MAX w mx) (SUM w sw INT64) "
+            "(COUNT w cw) (MAX u mu) (MIN v mv)) (scan 0))")
+    same_results(ref.run(plan, [cols]), b200.run(plan, [cols]), ordered=False, sort_cols=[0])
+
+
+def test_group_multi_key_and_null_keys(ref, b200):
+    rng = np.random.default_rng(11)
+    n = 300_000
+    cols = [sp.Column("a", sp.INT32, rng.integers(0, 50, n), is_null=rng.random(n) < 0.05),
+            sp.Column("b", sp.INT64, rng.integers(-3, 3, n)),
+            sp.Column("c", sp.BOOL, rng.integers(0, 2, n).astype(np.bool_), is_null=rng.random(n) < 0.3),
+            sp.Column("v", sp.INT64, rng.integers(-10**6, 10**6, n))]
+    plan = "(group (named a b c) (aggs (SUM v s) (COUNT \"\" n) (MIN v mn)) (scan 0))"
+    same_results(ref.run(plan, [cols]), b200.run(plan, [cols]), ordered=False, sort_cols=[0, 1, 2])
+    plan1 = "(group (named a) (aggs (SUM v s) (MAX b m)) (scan 0))"
+    same_results(ref.run(plan1, [cols]), b200.run(plan1, [cols]), ordered=False, sort_cols=[0])
+
+
+def test_group_double_sum_tolerance(ref, b200):
+    """Arbitrary doubles: the GPU adds in a different order than the reference's sequential
+    loop (column_aggregator.cc:112-123). Tolerance: |diff| <= n_group * ulp(max partial)."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    cols = [sp.Column("k", sp.INT64, rng.integers(0, 100, n)), sp.Column("v", sp.DOUBLE, rng.random(n))]
+    plan = "(group (named k) (aggs (SUM v s)) (scan 0))"
+    a, b = ref.run(plan, [cols]), b200.run(plan, [cols])
+    oa, ob = np.argsort(a.columns[0]), np.argsort(b.columns[0])
+    assert np.array_equal(a.columns[0][oa], b.columns[0][ob])
+    sa, sb = a.columns[1][oa], b.columns[1][ob]
+    per_group = n / 100
+    assert np.all(np.abs(sa - sb) <= per_group * np.spacing(np.maximum(sa, sb)))
+
+
+@pytest.mark.parametrize("uniq", ["UNIQUE", "NOT_UNIQUE"])
+@pytest.mark.parametrize("jt", ["INNER", "LEFT_OUTER"])
+def test_hash_join(ref, b200, uniq, jt):
+    """C4 shape at test size: probe fk uniform over build keys, order-preserving output."""
+    rng = np.random.default_rng(17)
+    nb, npr = 100_000, 700_001
+    pk = rng.permutation(nb).astype(np.int64) * 3   # gaps: some probes miss
+    if uniq == "NOT_UNIQUE":
+        pk[rng.integers(0, nb, nb // 10)] = pk[rng.integers(0, nb, nb // 10)]
+    build = [sp.Column("pk", sp.INT64, pk), sp.Column("payload", sp.INT64, rng.integers(0, 10**9, nb)),
+             sp.Column("pn", sp.DOUBLE, rng.random(nb), is_null=rng.random(nb) < 0.1)]
+    probe = [sp.Column("fk", sp.INT64, rng.integers(0, nb * 3, npr), is_null=rng.random(npr) < 0.02),
+             sp.Column("lv", sp.INT64, rng.integers(0, 10**9, npr))]
+    plan = ("(hash_join %s (named fk) (named pk) (multi (0 (all)) (1 (named payload pn))) %s (scan 0) (scan 1))"
+            % (jt, uniq))
+    same_results(ref.run(plan, [probe, build], next_max_rows=8192), b200.run(plan, [probe, build], next_max_rows=8192))
+
+
+def test_hash_join_big_fanout(ref, b200):
+    """hash_join_test.cc:321-353: 5 keys x 1100 duplicates, more result rows per key than a block."""
+    lhs = [sp.Column("k", sp.INT32, np.arange(5))]
+    rhs = [sp.Column("k2", sp.INT32, np.tile(np.arange(5), 1100)), sp.Column("w", sp.INT64, np.arange(5500))]
+    plan = "(hash_join INNER (named k) (named k2) (multi (0 (all)) (1 (named w))) NOT_UNIQUE (scan 0) (scan 1))"
+    same_results(ref.run(plan, [lhs, rhs]), b200.run(plan, [lhs, rhs]))
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 250_000])
+def test_sort(ref, b200, n):
+    rng = np.random.default_rng(n)
+    cols = [sp.Column("a", sp.INT64, rng.integers(-50, 50, n), is_null=rng.random(n) < 0.1),
+            sp.Column("b", sp.DOUBLE, rng.integers(-1000, 1000, n) / 4.0),
+            sp.Column("c", sp.INT32, rng.integers(-2**31, 2**31 - 1, n)),
+            sp.Column("id", sp.INT64, np.arange(n))]
+    # a full key (ending in the unique id) makes the order total, so the unstable reference sort
+    # and the stable GPU sort must agree exactly
+    for order in ["(a ASC) (b DESC) (id ASC)", "(c DESC) (id ASC)", "(a DESC) (c ASC) (id DESC)", "(b ASC) (id ASC)"]:
+        plan = "(sort (order %s) (all) (scan 0))" % order
+        same_results(ref.run(plan, [cols]), b200.run(plan, [cols]))
+
+
+def test_q1_shape(ref, b200):
+    """C5 shape: Filter(ship <= D) -> Compute(disc_price, charge) -> GroupAggregate({rf, ls})."""
+    rng = np.random.default_rng(23)
+    n = 600_000
+    cols = [sp.Column("qty", sp.DOUBLE, rng.integers(1, 51, n).astype(np.float64)),
+            sp.Column("price", sp.DOUBLE, rng.integers(100, 10000, n) / 4.0),
+            sp.Column("disc", sp.DOUBLE, rng.integers(0, 5, n) / 16.0),
+            sp.Column("tax", sp.DOUBLE, rng.integers(0, 5, n) / 16.0),
+            sp.Column("rf", sp.INT64, rng.integers(0, 3, n)), sp.Column("ls", sp.INT64, rng.integers(0, 2, n)),
+            sp.Column("ship", sp.INT64, rng.integers(0, 2500, n))]
+    plan = ("(group (named rf ls) (aggs (SUM qty sum_qty) (SUM price sum_price) (SUM disc_price sum_disc_price) "
+            "(SUM charge sum_charge) (SUM disc sum_disc) (COUNT \"\" cnt)) "
+            "(compute (compound (col rf) (col ls) (col qty) (col price) (col disc) "
+            "(as disc_price (multiply (col price) (minus (f64 1) (col disc)))) "
+            "(as charge (multiply (multiply (col price) (minus (f64 1) (col disc))) (plus (f64 1) (col tax))))) "
+            "(filter (less_or_equal (col ship) (i64 2450)) (all) (scan 0))))")
+    # dyadic payloads: products and sums stay exactly representable -> bit-exact in any order
+    same_results(ref.run(plan, [cols]), b200.run(plan, [cols]), ordered=False, sort_cols=[0, 1])

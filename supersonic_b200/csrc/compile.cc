@@ -322,29 +322,10 @@ class Compiler {
       if (info_[predicate].phys != T_B8) return Fail(SSB_ERROR_INVALID_ARGUMENT_TYPE, "predicate must be BOOL");
       CountRef(predicate);
     }
-    // Output columns stay in a slot until the tile is written out, so a node that is both
-    // an output and an operand elsewhere is evaluated once.
+    // The predicate runs first: K_PRED turns the pass bits into in-tile positions, and every
+    // output is then stored already compacted into the tile's output staging buffer.
     p.n_in = n_in_;
     p.n_out = n_out;
-    for (int j = 0; j < n_out; ++j) {
-      const int node = outputs[j];
-      const ssb_expr_node& nd = nodes_[node];
-      int slot;
-      if (nd.op == SSB_OP_INPUT) {
-        slot = nd.arg[0];
-      } else {
-        if (info_[node].slot < 0) {
-          Gen(node);
-          if (info_[node].slot < 0) info_[node].slot = EmitStore(node);
-        }
-        slot = info_[node].slot;
-      }
-      p.out_slot[j] = static_cast<uint8_t>(slot);
-      p.out_width[j] = static_cast<uint8_t>(phys_width(info_[node].phys));
-      p.out_nullable[j] = info_[node].nullable ? 1 : 0;
-      prog_->out_types.push_back(nd.out_type);
-      prog_->out_nullable.push_back(info_[node].nullable ? 1 : 0);
-    }
     if (predicate >= 0) {
       Gen(predicate);
       Insn in;
@@ -353,11 +334,29 @@ class Compiler {
       Emit(in);
       p.has_pred = 1;
     }
+    for (int j = 0; j < n_out; ++j) {
+      const int node = outputs[j];
+      const ssb_expr_node& nd = nodes_[node];
+      Gen(node);
+      Insn in;
+      memset(&in, 0, sizeof(in));
+      in.kind = K_OUT;
+      in.t = static_cast<uint8_t>(info_[node].phys);
+      in.rw = static_cast<uint8_t>(phys_width(info_[node].phys));
+      in.a = static_cast<int16_t>(j);
+      if (info_[node].nullable) in.rhs_nullable = 1;
+      Emit(in);
+      p.out_width[j] = static_cast<uint8_t>(phys_width(info_[node].phys));
+      p.out_nullable[j] = info_[node].nullable ? 1 : 0;
+      prog_->out_types.push_back(nd.out_type);
+      prog_->out_nullable.push_back(info_[node].nullable ? 1 : 0);
+    }
     Insn end;
     memset(&end, 0, sizeof(end));
     end.kind = K_END;
     p.insn[p.n_insn] = end;
     if (code_) return code_;
+    AssignFastCodes();
 
     // ---- shared-memory plan
     p.n_tmp = n_tmp_high_;
@@ -381,28 +380,63 @@ class Compiler {
     prog_->bytes_out_row = 0;
     for (int j = 0; j < n_out; ++j) prog_->bytes_out_row += p.out_width[j];
 
+    // output staging: per column kTile elements (+ kTile null bytes when nullable), 16-byte aligned
+    uint32_t ooff = 0;
+    for (int j = 0; j < n_out; ++j) {
+      p.out_off[j] = ooff;
+      ooff += kTile * p.out_width[j];
+      ooff = (ooff + 15) & ~15u;
+      if (p.out_nullable[j]) { p.out_null_off[j] = ooff; ooff += kTile; } else { p.out_null_off[j] = 0xffffffffu; }
+    }
+    p.out_bytes = (ooff + 127) & ~127u;
     const uint32_t tmp_bytes = static_cast<uint32_t>(p.n_tmp) * kTile * 8;
     const uint32_t tmp_nullw = static_cast<uint32_t>(p.n_tmp);
-    // header: barriers (64 B) + scan scratch (256 B)
+    // header: barriers (64 B) + scan / reduce scratch (512 B)
     p.off_bar = 0;
     p.off_scan = 64;
-    p.off_nullw = 64 + 256 + 64;   // scan scratch: seg_cnt[32], seg_off[32], base (8 B)
+    p.off_nullw = 64 + 512;
     int stages = kMaxStages;
     for (;; --stages) {
       const uint32_t nullw_bytes = (stages * p.stage_nullw + tmp_nullw) * kTileWords * 4;
-      const uint32_t data_off = (p.off_nullw + nullw_bytes + 127) & ~127u;
-      const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + 128;
-      if ((total <= smem_budget && stages >= 2) || stages == 1 ||
-          (stages == 2 && total <= smem_max)) {
+      const uint32_t data_off = (p.off_nullw + nullw_bytes + 1023) & ~1023u;
+      const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + kOutBuffers * p.out_bytes;
+      if ((total <= smem_budget && stages >= 2) || stages == 1 || (stages == 2 && total <= smem_max)) {
         if (total > smem_max) return Fail(SSB_ERROR_NOT_IMPLEMENTED, "expression needs more shared memory than one SM has");
         p.stages = stages;
         p.off_data = data_off;
         p.off_tmp = data_off + stages * p.stage_bytes;
+        p.off_out = p.off_tmp + tmp_bytes;
         prog_->smem_bytes = total;
         break;
       }
     }
     return 0;
+  }
+
+  // Marks the instructions that have a straight-line case in the kernel.
+  void AssignFastCodes() {
+    ExprParams& p = prog_->params;
+    for (int i = 0; i < p.n_insn; ++i) {
+      Insn& in = p.insn[i];
+      in.code = C_GENERIC;
+      if (in.kind != K_ALU2) continue;
+      const bool slot8 = (in.flags & F_RHS_IMM) || in.rw == phys_width(in.t);
+      if (!slot8) continue;
+      if (in.mop == M_AND3 && !(in.flags & F_REV)) { in.code = C_AND3; continue; }
+      if (in.mop == M_OR3) { in.code = C_OR3; continue; }
+      if ((in.mop == M_LT || in.mop == M_EQ) && in.t != in.t2) continue;
+      int base = -1;
+      if (in.t == T_I64) base = C_ADD_I64; else if (in.t == T_F64) base = C_ADD_F64; else if (in.t == T_I32) base = C_ADD_I32;
+      if (base < 0) continue;
+      switch (in.mop) {
+        case M_ADD: in.code = base + 0; break;
+        case M_SUB: in.code = base + 1; break;
+        case M_MUL: in.code = base + 2; break;
+        case M_LT: in.code = base + 3; break;
+        case M_EQ: in.code = base + 4; break;
+        default: break;
+      }
+    }
   }
 
  private:

@@ -64,7 +64,18 @@ enum Kind {
   K_ALU1 = 3,      // acc = mop(acc)
   K_ALU2 = 4,      // acc = mop(acc, rhs)             rhs = slot[a] | imm[a]
   K_ALU3 = 5,      // acc = mop(acc, rhs, rhs2)       rhs2 = slot[b] | imm[b]
-  K_PRED = 6,      // pass = acc && !null
+  K_PRED = 6,      // pass = acc && !null; in-tile compaction offsets are computed here
+  K_OUT = 7,       // output column a = acc, written to the tile's output staging (compacted)
+};
+
+// Fast-path codes: the hot (op, type) pairs get straight-line cases in the kernel; every
+// other instruction runs through the generic alu() below (code C_GENERIC).
+enum Code {
+  C_GENERIC = 0,
+  C_ADD_I64, C_SUB_I64, C_MUL_I64, C_LT_I64, C_EQ_I64,
+  C_ADD_F64, C_SUB_F64, C_MUL_F64, C_LT_F64, C_EQ_F64,
+  C_ADD_I32, C_SUB_I32, C_MUL_I32, C_LT_I32, C_EQ_I32,
+  C_AND3, C_OR3,
 };
 
 struct Insn {
@@ -77,7 +88,8 @@ struct Insn {
   uint8_t rw;      // byte width of the elements of slot a (and b): 1, 4 or 8
   int16_t a;       // slot or immediate index
   int16_t b;
-  int32_t pad2;
+  uint16_t code;   // Code: fast path selector
+  uint16_t pad2;
 };
 
 // ---- container encode / decode ------------------------------------------------------------

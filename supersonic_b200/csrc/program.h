@@ -39,30 +39,34 @@ struct ExprParams {
   uint8_t in_nullable[kMaxIn];          // compiled with null words for this input
   uint32_t in_off[kMaxIn];              // byte offset of the column tile inside a stage
   int32_t in_nullw[kMaxIn];             // index of its null-word row inside a stage, -1
-  // ---- temporaries: slot n_in + t
+  // ---- temporaries: slot n_in + t (one copy; dead once the tile is evaluated)
   int32_t n_tmp;
-  // ---- outputs
+  // ---- outputs: staged (compacted) in shared memory, copied out one tile later
   int32_t n_out;
   void* out_data[kMaxOut];
   uint32_t* out_nulls[kMaxOut];
-  uint8_t out_slot[kMaxOut];
+  uint32_t out_off[kMaxOut];            // byte offset of the column inside an output buffer
+  uint32_t out_null_off[kMaxOut];       // byte offset of its null bytes, or 0xffffffff
   uint8_t out_width[kMaxOut];
   uint8_t out_nullable[kMaxOut];
-  // ---- shared memory plan (byte offsets from the 128-byte aligned base)
-  uint32_t off_bar, off_scan, off_nullw, off_data, off_tmp;
-  uint32_t stage_bytes;                 // data bytes of one stage
+  // ---- shared memory plan (byte offsets from the 1024-byte aligned base)
+  uint32_t off_bar, off_scan, off_nullw, off_data, off_tmp, off_out;
+  uint32_t stage_bytes;                 // data bytes of one input stage
   uint32_t stage_nullw;                 // null-word rows per stage (nullable inputs)
-  uint32_t stage_tx_bytes;              // bytes one full-tile TMA fill delivers
+  uint32_t stage_tx_bytes;              // bytes one full-tile TMA fill delivers (data only)
+  uint32_t out_bytes;                   // bytes of one output buffer
   int32_t stages;
   // ---- run
   int64_t rows;
   int64_t num_tiles;
   int32_t has_pred;
   int32_t use_tma;
-  unsigned long long* tile_status;      // decoupled look-back words (Filter)
+  unsigned long long* tile_status;      // per-tile kept-row counts | valid bit (Filter)
   int64_t* d_out_rows;
   int32_t* d_fail;
 };
+
+enum { kOutBuffers = 2 };              // output staging depth: tile i is copied out while i+1 is evaluated
 
 struct Program {
   // compile-time description

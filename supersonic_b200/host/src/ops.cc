@@ -1,6 +1,8 @@
 // ops.cc -- Operation factories and GPU cursors (see include/supersonic/cursor.h).
 #include <stdio.h>
 
+#include <map>
+
 #include "internal.h"
 
 namespace supersonic {
@@ -76,36 +78,66 @@ class RowwiseCursor : public GpuCursor {
   virtual CursorId GetCursorId() const { return id_; }
  protected:
   virtual FailureOrVoid Run(DeviceTable* result) {
-    FailureOrOwned<DeviceProgram> created = DeviceProgram::Create(plan_.base_schema, plan_.outputs, plan_.predicate);
-    PROPAGATE_ON_FAILURE(created);
-    std::unique_ptr<DeviceProgram> program(created.release());
-    DeviceTable in;
-    std::unique_ptr<Block> keepalive;
-    int64 rows = 0;
-    vector<ssb_column> ic;
-    if (plan_.source) {
-      DeviceTable whole;
-      PROPAGATE_ON_FAILURE(MaterializeOnDevice(plan_.source.get(), &whole, &keepalive));
-      rows = whole.rows;
-      for (size_t k = 0; k < program->used_inputs().size(); ++k) {
-        in.columns.push_back(whole.columns[program->used_inputs()[k]]);
+    // One kernel evaluates the predicate and every output column. Plans too wide for one
+    // CTA's shared memory are split into column groups that share the predicate.
+    const size_t n_out = plan_.outputs.size();
+    for (size_t group = n_out > 0 ? n_out : 1;; group = (group + 1) / 2) {
+      vector<std::unique_ptr<DeviceProgram> > programs;
+      Exception* error = NULL;
+      for (size_t first = 0; first < (n_out > 0 ? n_out : 1) && error == NULL; first += group) {
+        vector<NodePtr> outs;
+        for (size_t j = first; j < n_out && j < first + group; ++j) outs.push_back(plan_.outputs[j]);
+        FailureOrOwned<DeviceProgram> created = DeviceProgram::Create(plan_.base_schema, outs, plan_.predicate);
+        if (created.is_failure()) error = created.release_exception();
+        else programs.push_back(std::unique_ptr<DeviceProgram>(created.release()));
       }
-    } else {
-      rows = static_cast<int64>(plan_.base.row_count());
-      PROPAGATE_ON_FAILURE(UploadColumns(plan_.base, program->used_inputs(), 0, plan_.base.row_count(), &in));
+      if (error == NULL) return RunPrograms(programs, group, result);
+      if (error->return_code() != ERROR_NOT_IMPLEMENTED || group <= 1) return Failure(error);
+      delete error;
     }
-    for (size_t k = 0; k < in.columns.size(); ++k) ic.push_back(in.columns[k].col);
-    PROPAGATE_ON_FAILURE(result->Allocate(plan_.schema, rows, /* force_nulls = */ true));
-    vector<ssb_column> oc;
-    for (size_t j = 0; j < result->columns.size(); ++j) oc.push_back(result->columns[j].col);
+  }
+
+  FailureOrVoid RunPrograms(const vector<std::unique_ptr<DeviceProgram> >& programs, size_t group,
+                            DeviceTable* result) {
     FailureOr<Session*> s = Session::Get();
     PROPAGATE_ON_FAILURE(s);
-    for (size_t j = 0; j < oc.size(); ++j) {
-      SSB_CALL(s.get(), ssb_memset(s.get()->ctx(), oc[j].nulls, 0, static_cast<size_t>((rows + 31) / 32 + 1) * 4), "memset");
+    // the base columns, uploaded (or referenced) once for all programs
+    vector<int> all_cols;
+    for (int c = 0; c < plan_.base_schema.attribute_count(); ++c) all_cols.push_back(c);
+    std::map<int, int> needed;
+    for (size_t g = 0; g < programs.size(); ++g) {
+      for (size_t k = 0; k < programs[g]->used_inputs().size(); ++k) needed[programs[g]->used_inputs()[k]] = 1;
     }
-    FailureOr<int64> n = program->Run(ic, rows, oc);
-    PROPAGATE_ON_FAILURE(n);
-    result->rows = n.get();
+    DeviceTable base;
+    std::unique_ptr<Block> keepalive;
+    int64 rows = 0;
+    std::map<int, DeviceColumnRef> col_of;
+    if (plan_.source) {
+      PROPAGATE_ON_FAILURE(MaterializeOnDevice(plan_.source.get(), &base, &keepalive));
+      rows = base.rows;
+      for (std::map<int, int>::iterator it = needed.begin(); it != needed.end(); ++it) col_of[it->first] = base.columns[it->first];
+    } else {
+      rows = static_cast<int64>(plan_.base.row_count());
+      vector<int> cols;
+      for (std::map<int, int>::iterator it = needed.begin(); it != needed.end(); ++it) cols.push_back(it->first);
+      PROPAGATE_ON_FAILURE(UploadColumns(plan_.base, cols, 0, plan_.base.row_count(), &base));
+      for (size_t k = 0; k < cols.size(); ++k) col_of[cols[k]] = base.columns[k];
+    }
+    PROPAGATE_ON_FAILURE(result->Allocate(plan_.schema, rows, /* force_nulls = */ true));
+    for (size_t j = 0; j < result->columns.size(); ++j) {   // columns the program proves NOT NULL are never written
+      SSB_CALL(s.get(), ssb_memset(s.get()->ctx(), result->columns[j].col.nulls, 0,
+                                   static_cast<size_t>((rows + 31) / 32 + 1) * 4), "memset");
+    }
+    int64 kept = 0;
+    for (size_t g = 0; g < programs.size(); ++g) {
+      vector<ssb_column> ic, oc;
+      for (size_t k = 0; k < programs[g]->used_inputs().size(); ++k) ic.push_back(col_of[programs[g]->used_inputs()[k]].col);
+      for (size_t j = g * group; j < result->columns.size() && j < (g + 1) * group; ++j) oc.push_back(result->columns[j].col);
+      FailureOr<int64> n = programs[g]->Run(ic, rows, oc);
+      PROPAGATE_ON_FAILURE(n);
+      kept = n.get();
+    }
+    result->rows = kept;
     return Success();
   }
  private:

@@ -16,6 +16,7 @@ struct ssb_ctx {
   cudaStream_t stream;
   int num_sms;
   size_t smem_optin;          // max dynamic shared memory per block
+  size_t smem_per_sm, smem_reserved;
   std::string last_error;
   int64_t launches;
   bool timing;

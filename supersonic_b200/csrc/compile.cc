@@ -28,9 +28,9 @@ struct Ref {           // an operand the ALU can read directly
 class Compiler {
  public:
   Compiler(const ssb_expr_node* nodes, int n, int n_in, const int32_t* in_types,
-           const int32_t* in_nullable, Program* prog, std::string* err)
+           const int32_t* in_nullable, int tile, Program* prog, std::string* err)
       : nodes_(nodes), n_(n), n_in_(n_in), in_types_(in_types), in_nullable_(in_nullable),
-        prog_(prog), err_(err), code_(0) {
+        tile_(tile), prog_(prog), err_(err), code_(0) {
     memset(&prog->params, 0, sizeof(prog->params));
     info_.resize(n);
     tmp_used_.assign(kMaxTmp, false);
@@ -356,7 +356,6 @@ class Compiler {
     end.kind = K_END;
     p.insn[p.n_insn] = end;
     if (code_) return code_;
-    AssignFastCodes();
 
     // ---- shared-memory plan
     p.n_tmp = n_tmp_high_;
@@ -368,8 +367,8 @@ class Compiler {
       const int w = width_of(in_types_[i]);
       p.in_width[i] = static_cast<uint8_t>(w);
       p.in_off[i] = off;
-      off += kTile * w;                 // kTile * w is a multiple of 1024: 16-byte aligned
-      tx += kTile * w;
+      off += tile_ * w;                 // tile_ * w is a multiple of 128: 16-byte aligned
+      tx += tile_ * w;
       p.in_nullable[i] = in_nullable_[i] ? 1 : 0;
       p.in_nullw[i] = in_nullable_[i] ? nullw++ : -1;
       prog_->bytes_in_row += w;
@@ -380,16 +379,16 @@ class Compiler {
     prog_->bytes_out_row = 0;
     for (int j = 0; j < n_out; ++j) prog_->bytes_out_row += p.out_width[j];
 
-    // output staging: per column kTile elements (+ kTile null bytes when nullable), 16-byte aligned
+    // output staging: per column tile_ elements (+ tile_ null bytes when nullable), 16-byte aligned
     uint32_t ooff = 0;
     for (int j = 0; j < n_out; ++j) {
       p.out_off[j] = ooff;
-      ooff += kTile * p.out_width[j];
+      ooff += tile_ * p.out_width[j];
       ooff = (ooff + 15) & ~15u;
-      if (p.out_nullable[j]) { p.out_null_off[j] = ooff; ooff += kTile; } else { p.out_null_off[j] = 0xffffffffu; }
+      if (p.out_nullable[j]) { p.out_null_off[j] = ooff; ooff += tile_; } else { p.out_null_off[j] = 0xffffffffu; }
     }
     p.out_bytes = (ooff + 127) & ~127u;
-    const uint32_t tmp_bytes = static_cast<uint32_t>(p.n_tmp) * kTile * 8;
+    const uint32_t tmp_bytes = static_cast<uint32_t>(p.n_tmp) * tile_ * 8;
     const uint32_t tmp_nullw = static_cast<uint32_t>(p.n_tmp);
     // header: barriers (64 B) + scan / reduce scratch (512 B)
     p.off_bar = 0;
@@ -397,12 +396,13 @@ class Compiler {
     p.off_nullw = 64 + 512;
     int stages = kMaxStages;
     for (;; --stages) {
-      const uint32_t nullw_bytes = (stages * p.stage_nullw + tmp_nullw) * kTileWords * 4;
+      const uint32_t nullw_bytes = (stages * p.stage_nullw + tmp_nullw) * (tile_ / 32) * 4;
       const uint32_t data_off = (p.off_nullw + nullw_bytes + 1023) & ~1023u;
       const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + kOutBuffers * p.out_bytes;
       if ((total <= smem_budget && stages >= 2) || stages == 1 || (stages == 2 && total <= smem_max)) {
         if (total > smem_max) return Fail(SSB_ERROR_NOT_IMPLEMENTED, "expression needs more shared memory than one SM has");
         p.stages = stages;
+        p.tile = tile_;
         p.off_data = data_off;
         p.off_tmp = data_off + stages * p.stage_bytes;
         p.off_out = p.off_tmp + tmp_bytes;
@@ -410,33 +410,88 @@ class Compiler {
         break;
       }
     }
+    AssignFastCodes();
     return 0;
   }
 
-  // Marks the instructions that have a straight-line case in the kernel.
+  // Pre-decodes operand addresses and marks the instructions that have a straight-line case
+  // in the kernel. Runs after the shared-memory plan is final.
   void AssignFastCodes() {
     ExprParams& p = prog_->params;
     for (int i = 0; i < p.n_insn; ++i) {
       Insn& in = p.insn[i];
       in.code = C_GENERIC;
-      if (in.kind != K_ALU2) continue;
-      const bool slot8 = (in.flags & F_RHS_IMM) || in.rw == phys_width(in.t);
-      if (!slot8) continue;
-      if (in.mop == M_AND3 && !(in.flags & F_REV)) { in.code = C_AND3; continue; }
-      if (in.mop == M_OR3) { in.code = C_OR3; continue; }
-      if ((in.mop == M_LT || in.mop == M_EQ) && in.t != in.t2) continue;
-      int base = -1;
-      if (in.t == T_I64) base = C_ADD_I64; else if (in.t == T_F64) base = C_ADD_F64; else if (in.t == T_I32) base = C_ADD_I32;
-      if (base < 0) continue;
-      switch (in.mop) {
-        case M_ADD: in.code = base + 0; break;
-        case M_SUB: in.code = base + 1; break;
-        case M_MUL: in.code = base + 2; break;
-        case M_LT: in.code = base + 3; break;
-        case M_EQ: in.code = base + 4; break;
+      in.off_a = SlotOffset(in.a, in.kind != K_OUT && !(in.flags & F_RHS_IMM));
+      in.off_b = SlotOffset(in.b, in.kind == K_ALU3 && !(in.flags & F_RHS2_IMM));
+      const bool imm = (in.flags & F_RHS_IMM) != 0;
+      const bool rhs_clean = imm ? !(in.flags & F_RHS_NULLK) : !(in.rhs_nullable & 1);
+      switch (in.kind) {
+        case K_LOAD:
+          if (!rhs_clean) break;
+          if (imm) in.code = C_LOADK;
+          else if (in.rw == 8) in.code = C_LOAD8;
+          else if (in.rw == 4) in.code = C_LOAD4;
+          break;
+        case K_OUT:
+          if (in.rhs_nullable & 1) break;
+          if (in.rw == 8) in.code = C_OUT8; else if (in.rw == 4) in.code = C_OUT4;
+          break;
+        case K_PRED: in.code = C_PRED; break;
+        case K_ALU2: {
+          if (!rhs_clean) break;
+          if (!imm && in.rw != phys_width(in.t)) break;
+          if ((in.mop == M_LT || in.mop == M_EQ) && in.t != in.t2) break;
+          if (in.mop == M_AND3 && !imm && !(in.flags & F_REV)) { in.code = C_AND3_S; break; }
+          if (in.mop == M_OR3 && !imm) { in.code = C_OR3_S; break; }
+          int base = -1;
+          if (in.t == T_I64) base = C_BIN_I64; else if (in.t == T_F64) base = C_BIN_F64; else if (in.t == T_I32) base = C_BIN_I32;
+          if (base < 0) break;
+          int op = -1;
+          switch (in.mop) {
+            case M_ADD: op = B_ADD; break;
+            case M_SUB: op = B_SUB; break;
+            case M_MUL: op = B_MUL; break;
+            case M_LT: op = B_LT; break;
+            case M_EQ: op = B_EQ; break;
+            default: break;
+          }
+          if (op >= 0) in.code = static_cast<uint16_t>(base + 4 * op + (imm ? 1 : 0));
+        } break;
         default: break;
       }
     }
+    // Peephole: a clean LOAD followed by a fast binary op becomes one two-operand instruction
+    // (the left operand is read from its slot instead of the accumulator).
+    int w = 0;
+    for (int i = 0; i < p.n_insn; ++i) {
+      Insn cur = p.insn[i];
+      if (i + 1 < p.n_insn && (cur.code == C_LOAD8 || cur.code == C_LOAD4)) {
+        Insn& next = p.insn[i + 1];
+        const bool bin = next.code >= C_BIN_BASE && next.code < C_BIN_END && ((next.code - C_BIN_BASE) % 4) < 2;
+        // the accumulator is the LEFT operand unless F_REV; keep the rule simple: fuse only
+        // when the op reads acc on the left
+        if (bin && !(next.flags & F_REV) && phys_width(next.t) == cur.rw) {
+          next.off_b = cur.off_a;
+          next.code = static_cast<uint16_t>(next.code + 2);
+          continue;   // drop the LOAD
+        }
+      }
+      p.insn[w++] = cur;
+    }
+    p.n_insn = w;
+    Insn end;
+    memset(&end, 0, sizeof(end));
+    end.kind = K_END;
+    p.insn[p.n_insn] = end;
+  }
+
+  // Byte offset of a slot's data from the shared-memory base; inputs are stage relative
+  // (bit 31 set: the kernel adds stage * stage_bytes).
+  uint32_t SlotOffset(int slot, bool used) const {
+    const ExprParams& p = prog_->params;
+    if (!used || slot < 0) return 0;
+    if (slot < p.n_in) return (p.off_data + p.in_off[slot]) | 0x80000000u;
+    return p.off_tmp + static_cast<uint32_t>(slot - p.n_in) * tile_ * 8;
   }
 
  private:
@@ -539,6 +594,7 @@ class Compiler {
   int n_, n_in_;
   const int32_t* in_types_;
   const int32_t* in_nullable_;
+  int tile_;
   Program* prog_;
   std::string* err_;
   int code_;
@@ -553,7 +609,7 @@ class Compiler {
 int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs,
                     const int32_t* input_types, const int32_t* input_nullable,
                     const int32_t* outputs, int32_t n_outputs, int32_t predicate,
-                    uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err) {
+                    int32_t tile, uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err) {
   if (n_nodes <= 0 || n_inputs < 0 || n_outputs < 0 || (n_outputs == 0 && predicate < 0)) {
     *err = "empty program";
     return SSB_ERROR_INVALID_ARGUMENT_VALUE;
@@ -570,7 +626,7 @@ int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_input
   prog->out_types.clear();
   prog->out_nullable.clear();
   prog->has_signaling = false;
-  Compiler c(nodes, n_nodes, n_inputs, input_types, input_nullable, prog, err);
+  Compiler c(nodes, n_nodes, n_inputs, input_types, input_nullable, tile, prog, err);
   if (int rc = c.Analyze()) return rc;
   return c.Finish(outputs, n_outputs, predicate, smem_budget, smem_max);
 }

@@ -107,6 +107,8 @@ int ssb_ctx_create(int device, ssb_ctx** out) {
   cudaGetDeviceProperties(&prop, device);
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
+  ctx->smem_reserved = prop.reservedSharedMemPerBlock;
   if (prop.major < 10) {
     fprintf(stderr, "libssb200: device %d is sm_%d%d; this library carries sm_100a code only\n",
             device, prop.major, prop.minor);

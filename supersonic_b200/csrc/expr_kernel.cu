@@ -7,18 +7,24 @@
 //  expression/vector/vector_primitives.h:70-353, base/infrastructure/copy_column.cc:200-286).
 //
 // Shape of the kernel (HBM-bound; no tensor cores because nothing here is a contraction):
-//  * persistent CTAs, tile = 1024 rows; tile t belongs to CTA t % gridDim.x
-//  * input column tiles are staged into shared memory by TMA bulk copies
-//    (cp.async.bulk, one elected thread, mbarrier complete_tx), `stages` tiles in flight
-//    per CTA, so HBM latency is hidden by bytes in flight rather than by occupancy
-//  * the expression program (bytecode in the constant bank) is interpreted warp-uniformly;
-//    each thread owns 4 rows whose values live in registers (the accumulator); shared
-//    memory slots hold operands only
-//  * Filter: warp ballots + one 32-entry scan give in-tile offsets, decoupled look-back over
-//    per-tile status words gives the global offset, so output order = input order with a
-//    single pass over the data
+//  * persistent CTAs; tile t (NT*R rows) belongs to CTA t % gridDim.x, so the CTAs walk the
+//    table in lock-step "waves" of gridDim.x tiles
+//  * input column tiles are staged into shared memory by TMA bulk copies (cp.async.bulk, one
+//    elected thread, mbarrier complete_tx), `stages` tiles in flight per CTA: HBM latency is
+//    hidden by bytes in flight, not by occupancy
+//  * the expression program (bytecode in the constant bank) is interpreted warp-uniformly.
+//    A thread owns R rows whose values live in registers (the accumulator); shared memory
+//    slots hold operands only. Hot (op, type) pairs on NOT NULL operands are pre-decoded
+//    superinstructions (operand address = one add); the rest runs through ops.h's alu()
+//  * Filter: the predicate runs first; warp ballots + a scan over the warps give every kept
+//    row its position inside the tile, outputs are stored already compacted into a staging
+//    buffer, and the tile's kept count is published. One iteration later the CTA reads the
+//    counts of its whole wave with one coalesced load (wave-synchronous prefix: no serial
+//    look-back chain), and copies the staged rows out with fully coalesced stores. Output
+//    order = input order, one pass over the data.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "program.h"
@@ -67,7 +73,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// streaming (evict-first) global accesses: every byte is touched once
+// streaming (evict-first) global stores: every output byte is written once
 __device__ __forceinline__ void st_cs_u64(void* p, uint64_t v) {
   asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -77,38 +83,19 @@ __device__ __forceinline__ void st_cs_u32(void* p, uint32_t v) {
 
 static constexpr unsigned long long kValid = 1ull << 63;
 
-// Straight-line binary step for the hot (op, type) pairs: acc = acc (op) rhs.
-template <int R, typename T, typename F>
-__device__ __forceinline__ void fast_arith(u64 (&acc)[R], const u64 (&rhs)[R], bool rev, F f) {
-#pragma unroll
-  for (int k = 0; k < R; ++k) {
-    const T x = Codec<T>::dec(acc[k]), y = Codec<T>::dec(rhs[k]);
-    acc[k] = Codec<T>::enc(rev ? f(y, x) : f(x, y));
-  }
-}
-template <int R, typename T, typename F>
-__device__ __forceinline__ void fast_cmp(u64 (&acc)[R], const u64 (&rhs)[R], bool rev, bool neg, F f) {
-#pragma unroll
-  for (int k = 0; k < R; ++k) {
-    const T x = Codec<T>::dec(acc[k]), y = Codec<T>::dec(rhs[k]);
-    acc[k] = ((rev ? f(y, x) : f(x, y)) != neg) ? 1u : 0u;
-  }
-}
-
 template <int NT, int R>
-__global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ ExprParams p) {
+__global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprParams p) {
   constexpr int TILE = NT * R;
   constexpr int NW = NT / 32;
-  constexpr int NSEG = NW * R;
-  static_assert(NSEG <= 32, "one warp scans the segment counts");
+  constexpr int WROWS = 32 * R;          // rows owned by one warp: [warp * WROWS, (warp + 1) * WROWS)
   extern __shared__ __align__(1024) unsigned char smem[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row_first = warp * WROWS + lane;   // thread's row k is row_first + 32 * k
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint32_t* seg_cnt = reinterpret_cast<uint32_t*>(smem + p.off_scan);          // [32]
-  uint32_t* seg_off = seg_cnt + 32;                                            // [32]
-  unsigned long long* red = reinterpret_cast<unsigned long long*>(seg_cnt + 64);   // [2 * NW] reduce scratch
-  unsigned long long* s_meta = red + 2 * NW;   // [0..1] tile totals of the two output buffers, [2] base, [3] wave base
+  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(smem + p.off_scan);             // [NW] kept rows per warp
+  unsigned long long* red = reinterpret_cast<unsigned long long*>(warp_cnt + 32);  // [2 * 16] reduce scratch
+  unsigned long long* s_meta = red + 32;   // [0..3] kept rows of the staged tiles, [4] base, [5] wave base
   uint32_t* nullw_base = reinterpret_cast<uint32_t*>(smem + p.off_nullw);
 
   const long long G = gridDim.x;
@@ -121,7 +108,7 @@ __global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ Exp
       for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
       fence_barrier_init();
     }
-    s_meta[3] = 0;
+    s_meta[5] = 0;
   }
   __syncthreads();
 
@@ -161,12 +148,59 @@ __global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ Exp
     for (int s = 0; s < S && s < n_my; ++s) issue(bid + s * G, s);
   }
 
-  const uint32_t all = (1u << R) - 1u;
+  const uint32_t all = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t fail = 0;
 
-  // One extra iteration drains the last deferred tile.
-  for (long long it = 0; it <= n_my; ++it) {
+  // kDefer extra iterations drain the deferred tiles.
+  // Wave-synchronous prefix, done by warp 0 alone and off the critical path: at the top of an
+  // iteration it fetches the kept-row counts the previous wave published (one coalesced read
+  // of gridDim.x words), the L2 round trip overlaps with the evaluation of the current tile,
+  // and the sums are reduced just before the barrier that ends the evaluation.
+  constexpr int kPrefetch = 12;   // status words per lane: covers gridDim.x <= 384
+  for (long long it = 0; it < n_my + kDefer; ++it) {
+    unsigned long long pre[kPrefetch];
+    const bool scan_wave = p.has_pred && it >= kDefer && warp == 0;
+    if (scan_wave) {
+      const long long w0 = (it - kDefer) * G;
+#pragma unroll
+      for (int q = 0; q < kPrefetch; ++q) {
+        const long long j = w0 + lane + q * 32;
+        pre[q] = (j < w0 + G && j < p.num_tiles) ? ld_relaxed(&p.tile_status[j]) : kValid;
+      }
+    }
+    auto finish_wave = [&]() {
+      // base of this CTA's tile of wave it-1 = kept rows of all earlier waves + of the tiles
+      // before it inside the wave
+      const long long w0 = (it - kDefer) * G;
+      const long long my_tile = bid + (it - kDefer) * G;
+      unsigned long long before = 0, sum = 0;
+#pragma unroll
+      for (int q = 0; q < kPrefetch; ++q) {
+        const long long j = w0 + lane + q * 32;
+        unsigned long long v = pre[q];
+        while (!(v & kValid) && !p.debug_nowait) v = ld_relaxed(&p.tile_status[j]);   // a CTA more than one tile behind
+        v &= ~kValid;
+        sum += v;
+        if (j < my_tile) before += v;
+      }
+      for (long long j = w0 + lane + kPrefetch * 32; j < w0 + G && j < p.num_tiles; j += 32) {
+        unsigned long long v;
+        do { v = ld_relaxed(&p.tile_status[j]); } while (!(v & kValid));
+        v &= ~kValid;
+        sum += v;
+        if (j < my_tile) before += v;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, d);
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      }
+      if (lane == 0) {
+        s_meta[4] = s_meta[5] + before;
+        s_meta[5] += sum;
+      }
+    };
     // ======================================================== evaluate tile `it`
     if (it < n_my) {
       const long long tile = bid + it * G;
@@ -203,197 +237,242 @@ __global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ Exp
         const bool have = p.in_nulls[i] != nullptr;
         if (via_tma && have) continue;
         uint32_t* wdst = slot_nullw(i, stage);
-        if (tid < TILE / 32) {
+        for (int wi = tid; wi < TILE / 32; wi += NT) {
           uint32_t wv = 0;
-          if (have && tid * 32 < n) wv = p.in_nulls[i][row0 / 32 + tid];
-          wdst[tid] = wv;
+          if (have && wi * 32 < n) wv = p.in_nulls[i][row0 / 32 + wi];
+          wdst[wi] = wv;
         }
         filled = true;
       }
       if (filled) __syncthreads();
+      // Without a predicate no barrier separates this tile's staging writes from the copy-out
+      // of the tile evaluated two iterations ago (same buffer): add one.
+      if (!p.has_pred) __syncthreads();
 
       uint32_t live = 0;
 #pragma unroll
-      for (int k = 0; k < R; ++k) live |= (k * NT + tid < n ? 1u : 0u) << k;
+      for (int k = 0; k < R; ++k) live |= (row_first + 32 * k < n ? 1u : 0u) << k;
 
       // ---- the accumulator machine
       u64 acc[R];
       uint32_t accn = 0, pass = live;
       int pos[R];
 #pragma unroll
-      for (int k = 0; k < R; ++k) { acc[k] = 0; pos[k] = k * NT + tid; }
-      // Without a predicate no barrier separates this tile's staging writes from the copy-out
-      // of the tile evaluated two iterations ago (same buffer): add one.
-      if (!p.has_pred) __syncthreads();
+      for (int k = 0; k < R; ++k) { acc[k] = 0; pos[k] = row_first + 32 * k; }
+      const uint32_t stage_off = static_cast<uint32_t>(stage) * p.stage_bytes;
+
+#define SSB_BIN4(CODE0, T, EXPR)                                                         \
+  case (CODE0): {                                                                        \
+    const T* ps = reinterpret_cast<const T*>(pa);                                        \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = Codec<T>::dec(acc[k]);                                                 \
+      const T y = ps[row_first + 32 * k];                                                \
+      acc[k] = EXPR;                                                                     \
+    }                                                                                    \
+  } break;                                                                               \
+  case (CODE0) + 1: {                                                                    \
+    const T y = Codec<T>::dec(p.imm[in.a]);                                              \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = Codec<T>::dec(acc[k]);                                                 \
+      acc[k] = EXPR;                                                                     \
+    }                                                                                    \
+  } break;                                                                               \
+  case (CODE0) + 2: {                                                                    \
+    const T* ps = reinterpret_cast<const T*>(pa);                                        \
+    const T* pl = reinterpret_cast<const T*>(pb);                                        \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = pl[row_first + 32 * k];                                                \
+      const T y = ps[row_first + 32 * k];                                                \
+      acc[k] = EXPR;                                                                     \
+    }                                                                                    \
+    accn = 0;                                                                            \
+  } break;                                                                               \
+  case (CODE0) + 3: {                                                                    \
+    const T* pl = reinterpret_cast<const T*>(pb);                                        \
+    const T y = Codec<T>::dec(p.imm[in.a]);                                              \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = pl[row_first + 32 * k];                                                \
+      acc[k] = EXPR;                                                                     \
+    }                                                                                    \
+    accn = 0;                                                                            \
+  } break;
+#define SSB_ENC(T, V) Codec<T>::enc(V)
+#define SSB_CMP(V) (((V) != neg) ? 1u : 0u)
+#define SSB_BIN_TYPE(BASE, T, ADD, SUB, SUBR, MUL)                                       \
+  SSB_BIN4((BASE) + 4 * B_ADD, T, SSB_ENC(T, ADD))                                       \
+  SSB_BIN4((BASE) + 4 * B_SUB, T, SSB_ENC(T, rev ? (SUBR) : (SUB)))                      \
+  SSB_BIN4((BASE) + 4 * B_MUL, T, SSB_ENC(T, MUL))                                       \
+  SSB_BIN4((BASE) + 4 * B_LT, T, SSB_CMP(rev ? y < x : x < y))                           \
+  SSB_BIN4((BASE) + 4 * B_EQ, T, SSB_CMP(x == y))
 
       for (int pc = 0; pc < p.n_insn; ++pc) {
-        const Insn in = p.insn[pc];
-        if (in.kind == K_ALU2 || in.kind == K_LOAD) {
-          // operand fetch
-          u64 rhs[R];
-          uint32_t rn = 0;
-          if (in.flags & F_RHS_IMM) {
-            const u64 c = p.imm[in.a];
-#pragma unroll
-            for (int k = 0; k < R; ++k) rhs[k] = c;
-            rn = (in.flags & F_RHS_NULLK) ? all : 0u;
-          } else {
-            const unsigned char* base = slot_data(in.a, stage);
-            if (in.rw == 8) {
-#pragma unroll
-              for (int k = 0; k < R; ++k) rhs[k] = reinterpret_cast<const u64*>(base)[k * NT + tid];
-            } else if (in.rw == 4) {
-#pragma unroll
-              for (int k = 0; k < R; ++k) rhs[k] = reinterpret_cast<const uint32_t*>(base)[k * NT + tid];
-            } else {
-#pragma unroll
-              for (int k = 0; k < R; ++k) rhs[k] = base[k * NT + tid];
-            }
-            if (in.rhs_nullable & 1) {
-              const uint32_t* w = slot_nullw(in.a, stage);
-              if (w != nullptr) {
-#pragma unroll
-                for (int k = 0; k < R; ++k) rn |= ((w[k * NW + warp] >> lane) & 1u) << k;
-              }
-            }
-          }
-          if (in.kind == K_LOAD) {
-#pragma unroll
-            for (int k = 0; k < R; ++k) acc[k] = rhs[k];
-            accn = rn;
-            continue;
-          }
+        const Insn& in = p.insn[pc];
+        const uint32_t code = in.code;
+        if (code != C_GENERIC) {
+          // pre-decoded fast path: operands cannot be NULL, address = one add
+          const uint32_t oa = in.off_a, ob = in.off_b;
+          const unsigned char* pa = smem + (oa & 0x7fffffffu) + ((oa >> 31) ? stage_off : 0u);
+          const unsigned char* pb = smem + (ob & 0x7fffffffu) + ((ob >> 31) ? stage_off : 0u);
           const bool rev = (in.flags & F_REV) != 0;
           const bool neg = (in.flags & F_NEGATE) != 0;
-          switch (in.code) {
-            case C_ADD_I64: fast_arith<R, int64_t>(acc, rhs, false, [](int64_t x, int64_t y) { return Arith<int64_t>::add(x, y); }); accn |= rn; break;
-            case C_SUB_I64: fast_arith<R, int64_t>(acc, rhs, rev, [](int64_t x, int64_t y) { return Arith<int64_t>::sub(x, y); }); accn |= rn; break;
-            case C_MUL_I64: fast_arith<R, int64_t>(acc, rhs, false, [](int64_t x, int64_t y) { return Arith<int64_t>::mul(x, y); }); accn |= rn; break;
-            case C_LT_I64: fast_cmp<R, int64_t>(acc, rhs, rev, neg, [](int64_t x, int64_t y) { return x < y; }); accn |= rn; break;
-            case C_EQ_I64: fast_cmp<R, int64_t>(acc, rhs, false, neg, [](int64_t x, int64_t y) { return x == y; }); accn |= rn; break;
-            case C_ADD_F64: fast_arith<R, double>(acc, rhs, false, [](double x, double y) { return x + y; }); accn |= rn; break;
-            case C_SUB_F64: fast_arith<R, double>(acc, rhs, rev, [](double x, double y) { return x - y; }); accn |= rn; break;
-            case C_MUL_F64: fast_arith<R, double>(acc, rhs, false, [](double x, double y) { return x * y; }); accn |= rn; break;
-            case C_LT_F64: fast_cmp<R, double>(acc, rhs, rev, neg, [](double x, double y) { return x < y; }); accn |= rn; break;
-            case C_EQ_F64: fast_cmp<R, double>(acc, rhs, false, neg, [](double x, double y) { return x == y; }); accn |= rn; break;
-            case C_ADD_I32: fast_arith<R, int32_t>(acc, rhs, false, [](int32_t x, int32_t y) { return Arith<int32_t>::add(x, y); }); accn |= rn; break;
-            case C_SUB_I32: fast_arith<R, int32_t>(acc, rhs, rev, [](int32_t x, int32_t y) { return Arith<int32_t>::sub(x, y); }); accn |= rn; break;
-            case C_MUL_I32: fast_arith<R, int32_t>(acc, rhs, false, [](int32_t x, int32_t y) { return Arith<int32_t>::mul(x, y); }); accn |= rn; break;
-            case C_LT_I32: fast_cmp<R, int32_t>(acc, rhs, rev, neg, [](int32_t x, int32_t y) { return x < y; }); accn |= rn; break;
-            case C_EQ_I32: fast_cmp<R, int32_t>(acc, rhs, false, neg, [](int32_t x, int32_t y) { return x == y; }); accn |= rn; break;
-            case C_AND3:
-            case C_OR3: {
+          switch (code) {
+            case C_LOAD8: {
+              const u64* ps = reinterpret_cast<const u64*>(pa);
+#pragma unroll
+              for (int k = 0; k < R; ++k) acc[k] = ps[row_first + 32 * k];
+              accn = 0;
+            } break;
+            case C_LOAD4: {
+              const uint32_t* ps = reinterpret_cast<const uint32_t*>(pa);
+#pragma unroll
+              for (int k = 0; k < R; ++k) acc[k] = ps[row_first + 32 * k];
+              accn = 0;
+            } break;
+            case C_LOADK: {
+              const u64 c = p.imm[in.a];
+#pragma unroll
+              for (int k = 0; k < R; ++k) acc[k] = c;
+              accn = 0;
+            } break;
+            SSB_BIN_TYPE(C_BIN_I64, int64_t, Arith<int64_t>::add(x, y), Arith<int64_t>::sub(x, y),
+                         Arith<int64_t>::sub(y, x), Arith<int64_t>::mul(x, y))
+            SSB_BIN_TYPE(C_BIN_F64, double, x + y, x - y, y - x, x * y)
+            SSB_BIN_TYPE(C_BIN_I32, int32_t, Arith<int32_t>::add(x, y), Arith<int32_t>::sub(x, y),
+                         Arith<int32_t>::sub(y, x), Arith<int32_t>::mul(x, y))
+            case C_AND3_S:
+            case C_OR3_S: {
+              // rhs is never NULL here; acc may be
               uint32_t av = 0, bv = 0;
 #pragma unroll
-              for (int k = 0; k < R; ++k) { av |= (acc[k] & 1u) << k; bv |= (rhs[k] & 1u) << k; }
-              const uint32_t at = av & ~accn, af = ~av & ~accn & all, bt = bv & ~rn, bf = ~bv & ~rn & all;
+              for (int k = 0; k < R; ++k) {
+                av |= static_cast<uint32_t>(acc[k] & 1u) << k;
+                bv |= static_cast<uint32_t>(pa[row_first + 32 * k] != 0) << k;
+              }
               uint32_t val, nul;
-              if (in.code == C_OR3) { val = at | bt; nul = (accn | rn) & ~(at | bt); }
-              else { val = at & bt; nul = (accn | rn) & ~(af | bf); }
+              if (code == C_OR3_S) { val = (av & ~accn) | bv; nul = accn & ~bv; }
+              else { val = av & ~accn & bv; nul = accn & bv; }
 #pragma unroll
               for (int k = 0; k < R; ++k) acc[k] = (val >> k) & 1u;
               accn = nul & all;
             } break;
-            default: {
-              u64 rhs2[R];
+            case C_PRED: {
+              uint32_t t = 0;
 #pragma unroll
-              for (int k = 0; k < R; ++k) rhs2[k] = 0;
-              alu<R>(in, acc, accn, rhs, rn, rhs2, 0u, live, fail);
+              for (int k = 0; k < R; ++k) t |= static_cast<uint32_t>(acc[k] & 1u) << k;
+              pass = t & ~accn & live;
+              // in-tile compaction: the warp's rows are contiguous, so positions inside the warp
+              // come from R ballots; one small scan over the warps gives the warp bases
+              uint32_t run = 0;
+#pragma unroll
+              for (int k = 0; k < R; ++k) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (pass >> k) & 1u);
+                pos[k] = static_cast<int>(run + __popc(m & lt));
+                run += __popc(m);
+              }
+              uint32_t* wc = warp_cnt + 16 * (it & 1);   // double buffered: one barrier per tile
+              if (lane == 0) wc[warp] = run;
+              __syncthreads();
+              uint32_t before = 0, total = 0;
+#pragma unroll
+              for (int w = 0; w < NW; ++w) {
+                const uint32_t c = wc[w];
+                if (w < warp) before += c;
+                total += c;
+              }
+#pragma unroll
+              for (int k = 0; k < R; ++k) pos[k] += static_cast<int>(before);
+              if (tid == 0) {
+                s_meta[it % kOutBuffers] = total;
+                st_relaxed(&p.tile_status[tile], kValid | total);   // this tile's share of its wave
+              }
             } break;
+            case C_OUT8: {
+              u64* dst = reinterpret_cast<u64*>(obuf + p.out_off[in.a]);
+#pragma unroll
+              for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = acc[k];
+            } break;
+            case C_OUT4: {
+              uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + p.out_off[in.a]);
+#pragma unroll
+              for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = static_cast<uint32_t>(acc[k]);
+            } break;
+            default: break;
           }
           continue;
         }
+        // ---- generic path: NULL-carrying operands, narrow or mixed types, rare ops.
+        // Works on 4 rows at a time so that its register footprint does not grow with R.
+        auto fetch4 = [&](int c4, int idx, bool is_imm, bool null_const, bool nullable, u64 (&v)[4], uint32_t& nn) {
+          if (is_imm) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = p.imm[idx];
+            nn = null_const ? 15u : 0u;
+            return;
+          }
+          const unsigned char* base = slot_data(idx, stage);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = row_first + 32 * (c4 * 4 + q);
+            v[q] = in.rw == 8 ? reinterpret_cast<const u64*>(base)[r]
+                              : (in.rw == 4 ? static_cast<u64>(reinterpret_cast<const uint32_t*>(base)[r]) : static_cast<u64>(base[r]));
+          }
+          nn = 0;
+          if (nullable) {
+            const uint32_t* w = slot_nullw(idx, stage);
+            if (w != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) nn |= ((w[warp * R + c4 * 4 + q] >> lane) & 1u) << q;
+            }
+          }
+        };
         switch (in.kind) {
+          case K_LOAD:
+          case K_ALU1:
+          case K_ALU2:
+          case K_ALU3: {
+#pragma unroll
+            for (int c4 = 0; c4 < R / 4; ++c4) {
+              u64 a4[4], r1[4], r2[4];
+              uint32_t an = (accn >> (4 * c4)) & 15u, n1 = 0, n2 = 0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { a4[q] = acc[c4 * 4 + q]; r1[q] = 0; r2[q] = 0; }
+              if (in.kind != K_ALU1) fetch4(c4, in.a, in.flags & F_RHS_IMM, in.flags & F_RHS_NULLK, in.rhs_nullable & 1, r1, n1);
+              if (in.kind == K_ALU3) fetch4(c4, in.b, in.flags & F_RHS2_IMM, in.rhs_nullable & 4, in.rhs_nullable & 2, r2, n2);
+              if (in.kind == K_LOAD) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a4[q] = r1[q];
+                an = n1;
+              } else {
+                uint32_t f4 = 0;
+                alu<4>(in, a4, an, r1, n1, r2, n2, (live >> (4 * c4)) & 15u, f4);
+                fail |= f4;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[c4 * 4 + q] = a4[q];
+              accn = (accn & ~(15u << (4 * c4))) | ((an & 15u) << (4 * c4));
+            }
+          } break;
           case K_STORE: {
             unsigned char* base = slot_data(in.a, stage);
             if (in.rw == 8) {
 #pragma unroll
-              for (int k = 0; k < R; ++k) reinterpret_cast<u64*>(base)[k * NT + tid] = acc[k];
+              for (int k = 0; k < R; ++k) reinterpret_cast<u64*>(base)[row_first + 32 * k] = acc[k];
             } else if (in.rw == 4) {
 #pragma unroll
-              for (int k = 0; k < R; ++k) reinterpret_cast<uint32_t*>(base)[k * NT + tid] = static_cast<uint32_t>(acc[k]);
+              for (int k = 0; k < R; ++k) reinterpret_cast<uint32_t*>(base)[row_first + 32 * k] = static_cast<uint32_t>(acc[k]);
             } else {
 #pragma unroll
-              for (int k = 0; k < R; ++k) base[k * NT + tid] = static_cast<unsigned char>(acc[k]);
+              for (int k = 0; k < R; ++k) base[row_first + 32 * k] = static_cast<unsigned char>(acc[k]);
             }
             if (in.rhs_nullable & 1) {
               uint32_t* w = slot_nullw(in.a, stage);
 #pragma unroll
               for (int k = 0; k < R; ++k) {
                 const uint32_t b = __ballot_sync(0xffffffffu, (accn >> k) & 1u);
-                if (lane == 0) w[k * NW + warp] = b;
+                if (lane == 0) w[warp * R + k] = b;
               }
               __syncwarp();   // read back by the lanes of this warp only
             }
-          } break;
-          case K_ALU1: {
-            u64 z[R];
-#pragma unroll
-            for (int k = 0; k < R; ++k) z[k] = 0;
-            alu<R>(in, acc, accn, z, 0u, z, 0u, live, fail);
-          } break;
-          case K_ALU3: {
-            u64 r1[R], r2[R];
-            uint32_t n1 = 0, n2 = 0;
-            // both operands have the element width rw
-            auto fetch = [&](int idx, bool is_imm, bool null_const, bool nullable, u64 (&v)[R], uint32_t& nn) {
-              if (is_imm) {
-#pragma unroll
-                for (int k = 0; k < R; ++k) v[k] = p.imm[idx];
-                nn = null_const ? all : 0u;
-              } else {
-                const unsigned char* base = slot_data(idx, stage);
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                  const int r = k * NT + tid;
-                  v[k] = in.rw == 8 ? reinterpret_cast<const u64*>(base)[r]
-                                    : (in.rw == 4 ? static_cast<u64>(reinterpret_cast<const uint32_t*>(base)[r]) : static_cast<u64>(base[r]));
-                }
-                nn = 0;
-                if (nullable) {
-                  const uint32_t* w = slot_nullw(idx, stage);
-                  if (w != nullptr) {
-#pragma unroll
-                    for (int k = 0; k < R; ++k) nn |= ((w[k * NW + warp] >> lane) & 1u) << k;
-                  }
-                }
-              }
-            };
-            fetch(in.a, in.flags & F_RHS_IMM, in.flags & F_RHS_NULLK, in.rhs_nullable & 1, r1, n1);
-            fetch(in.b, in.flags & F_RHS2_IMM, in.rhs_nullable & 4, in.rhs_nullable & 2, r2, n2);
-            alu<R>(in, acc, accn, r1, n1, r2, n2, live, fail);
-          } break;
-          case K_PRED: {
-            uint32_t t = 0;
-#pragma unroll
-            for (int k = 0; k < R; ++k) t |= static_cast<uint32_t>(acc[k] & 1u) << k;
-            pass = t & ~accn & live;
-            // in-tile compaction: ballots, one 32-entry scan, positions
-            uint32_t mask[R];
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-              mask[k] = __ballot_sync(0xffffffffu, (pass >> k) & 1u);
-              if (lane == 0) seg_cnt[k * NW + warp] = __popc(mask[k]);
-            }
-            __syncthreads();
-            if (warp == 0) {
-              const uint32_t c = lane < NSEG ? seg_cnt[lane] : 0u;
-              uint32_t incl = c;
-#pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += y;
-              }
-              seg_off[lane] = incl - c;
-              const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-              if (lane == 0) {
-                s_meta[it % kOutBuffers] = total;
-                st_relaxed(&p.tile_status[tile], kValid | total);   // this tile's share of its wave
-              }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < R; ++k) pos[k] = static_cast<int>(seg_off[k * NW + warp]) + __popc(mask[k] & lt);
           } break;
           case K_OUT: {
             const int j = in.a;
@@ -417,44 +496,27 @@ __global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ Exp
           default: break;
         }
       }
+#undef SSB_BIN4
+#undef SSB_BIN_TYPE
+#undef SSB_ENC
+#undef SSB_CMP
+      if (scan_wave) finish_wave();
       __syncthreads();   // the stage and the temporaries are free; the staging buffer is complete
       if (tid == 0 && it + S < n_my) issue(tile + S * G, stage);
+    } else {
+      if (scan_wave) finish_wave();
+      __syncthreads();
     }
 
-    // ======================================================== write out tile `it - 1`
-    if (it >= 1) {
-      const long long wave = it - 1;
+    // ======================================================== write out tile `it - kDefer`
+    if (it >= kDefer) {
+      const long long wave = it - kDefer;
       const long long tile = bid + wave * G;
       const unsigned char* obuf = smem + p.off_out + static_cast<int>(wave % kOutBuffers) * p.out_bytes;
       long long total;
       long long base;
       if (p.has_pred) {
-        // Wave-synchronous prefix: every CTA of this wave published its count when it evaluated
-        // the tile (one iteration ago), so this read normally does not spin.
-        const long long w0 = wave * G;
-        unsigned long long before = 0, sum = 0;
-        for (long long j = w0 + tid; j < w0 + G && j < p.num_tiles; j += NT) {
-          unsigned long long v;
-          do { v = ld_relaxed(&p.tile_status[j]); } while (!(v & kValid));
-          v &= ~kValid;
-          sum += v;
-          if (j < tile) before += v;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          before += __shfl_xor_sync(0xffffffffu, before, d);
-          sum += __shfl_xor_sync(0xffffffffu, sum, d);
-        }
-        if (lane == 0) { red[warp] = before; red[NW + warp] = sum; }
-        __syncthreads();
-        if (tid == 0) {
-          unsigned long long b = 0, s = 0;
-          for (int w = 0; w < NW; ++w) { b += red[w]; s += red[NW + w]; }
-          s_meta[2] = s_meta[3] + b;
-          s_meta[3] += s;
-        }
-        __syncthreads();
-        base = static_cast<long long>(s_meta[2]);
+        base = static_cast<long long>(s_meta[4]);
         total = static_cast<long long>(s_meta[wave % kOutBuffers]);
         if (tile == p.num_tiles - 1 && tid == 0 && p.d_out_rows != nullptr) *p.d_out_rows = base + total;
       } else {
@@ -482,15 +544,14 @@ __global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ Exp
             const bool bit = g >= base && g < end && nb[g - base] != 0;
             const uint32_t word = __ballot_sync(0xffffffffu, bit);
             if (lane == 0 && word != 0u) {
-              const long long w0 = g;   // g is a multiple of 32 for lane 0
-              if (w0 >= base && w0 + 32 <= end) p.out_nulls[j][w0 >> 5] = word;
-              else atomicOr(&p.out_nulls[j][w0 >> 5], word);
+              if (g >= base && g + 32 <= end) p.out_nulls[j][g >> 5] = word;
+              else atomicOr(&p.out_nulls[j][g >> 5], word);
             }
           }
         }
       }
-      // No barrier needed here: the next write into this staging buffer happens two
-      // evaluations later, behind at least one __syncthreads of the next iteration.
+      // No barrier needed here: the next write into this staging buffer happens two evaluations
+      // later, behind at least one __syncthreads of the next iteration.
     }
   }
   if (!p.has_pred && p.d_out_rows != nullptr && blockIdx.x == 0 && tid == 0) *p.d_out_rows = p.rows;
@@ -498,11 +559,30 @@ __global__ void __launch_bounds__(NT, 2) expr_kernel(const __grid_constant__ Exp
 }
 
 // ------------------------------------------------------------------ host side
+// Kernel variants: threads per CTA x rows per thread. More rows per thread amortise the
+// interpreter's dispatch; the tile (and with it the shared-memory stage) grows with both.
+struct Variant {
+  int threads, rows_per_thread;
+  void (*kernel)(const ExprParams);
+};
+static const Variant kVariants[] = {
+    {256, 4, expr_kernel<256, 4>},
+    {128, 8, expr_kernel<128, 8>},
+    {256, 8, expr_kernel<256, 8>},
+    {128, 16, expr_kernel<128, 16>},
+    {64, 16, expr_kernel<64, 16>},
+    {128, 4, expr_kernel<128, 4>},
+    {64, 8, expr_kernel<64, 8>},
+};
+static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+static const int kDefaultVariant = 1;
+
 static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t rows,
                           const ssb_column* outputs, int64_t* d_out_rows) {
   ssb_ctx* ctx = sp->ctx;
   Program& prog = sp->prog;
   ExprParams p = prog.params;
+  const Variant& var = kVariants[prog.variant];
   if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
   if (rows == 0) {
     if (d_out_rows) SSB_CUDA(ctx, cudaMemsetAsync(d_out_rows, 0, sizeof(int64_t), ctx->stream));
@@ -529,10 +609,11 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
     }
   }
   p.rows = rows;
-  p.num_tiles = div_up(rows, kTile);
+  p.num_tiles = div_up(rows, p.tile);
   p.use_tma = aligned ? 1 : 0;
   p.d_out_rows = d_out_rows;
   p.d_fail = prog.has_signaling ? ctx->d_fail : nullptr;
+  p.debug_nowait = getenv("SSB200_DEBUG_NOWAIT") ? 1 : 0;   // experiment only: breaks output positions
   if (p.has_pred) {
     void* st = nullptr;
     if (int rc = scratch(ctx, static_cast<size_t>(p.num_tiles) * 8, &st)) return rc;
@@ -542,7 +623,7 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
   long long grid = static_cast<long long>(ctx->num_sms) * sp->max_ctas_per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
   TimedRegion timed(ctx);
-  expr_kernel<kThreads, kRowsPerThread><<<static_cast<unsigned>(grid), kThreads, prog.smem_bytes, ctx->stream>>>(p);
+  var.kernel<<<static_cast<unsigned>(grid), var.threads, prog.smem_bytes, ctx->stream>>>(p);
   ++ctx->launches;
   SSB_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -559,21 +640,40 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
                        const int32_t* input_nullable, const int32_t* outputs,
                        int32_t n_outputs, int32_t predicate, ssb_program** out) {
   *out = nullptr;
-  ssb_program* sp = new ssb_program;
-  sp->ctx = ctx;
+  int variant = kDefaultVariant;
+  if (const char* env = getenv("SSB200_EXPR_VARIANT")) {
+    const int v = atoi(env);
+    if (v >= 0 && v < kNumVariants) variant = v;
+  }
+  // Two resident CTAs per SM is the design point; wide plans fall back to fewer stages, then
+  // to the smallest tile.
+  int ctas = 2;
+  if (const char* env = getenv("SSB200_EXPR_CTAS")) { const int c = atoi(env); if (c >= 1 && c <= 8) ctas = c; }
+  const uint32_t budget = static_cast<uint32_t>((ctx->smem_per_sm - ctas * ctx->smem_reserved) / ctas);
+  ssb_program* sp = nullptr;
   std::string err;
-  // Aim for two resident CTAs per SM (look-back latency of one hides behind the other).
-  const uint32_t budget = static_cast<uint32_t>(ctx->smem_optin / 2 > 2048 ? ctx->smem_optin / 2 - 1024 : ctx->smem_optin);
-  int rc = compile_program(nodes, n_nodes, n_inputs, input_types, input_nullable, outputs, n_outputs,
-                           predicate, budget, static_cast<uint32_t>(ctx->smem_optin), &sp->prog, &err);
-  if (rc) { delete sp; return fail(ctx, rc, err); }
-  cudaError_t e = cudaFuncSetAttribute(expr_kernel<kThreads, kRowsPerThread>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+  int rc = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    sp = new ssb_program;
+    sp->ctx = ctx;
+    const Variant& var = kVariants[variant];
+    rc = compile_program(nodes, n_nodes, n_inputs, input_types, input_nullable, outputs, n_outputs, predicate,
+                         var.threads * var.rows_per_thread, budget, static_cast<uint32_t>(ctx->smem_optin),
+                         &sp->prog, &err);
+    sp->prog.variant = variant;
+    if (rc == 0) break;
+    delete sp;
+    sp = nullptr;
+    if (rc != SSB_ERROR_NOT_IMPLEMENTED || variant == 0) break;
+    variant = 0;   // smallest tile: least shared memory per column
+  }
+  if (rc) return fail(ctx, rc, err);
+  const Variant& var = kVariants[sp->prog.variant];
+  cudaError_t e = cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(ctx->smem_optin));
   if (e != cudaSuccess) { delete sp; return cuda_fail(ctx, e, "cudaFuncSetAttribute(expr_kernel)"); }
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expr_kernel<kThreads, kRowsPerThread>, kThreads,
-                                                    sp->prog.smem_bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.kernel, var.threads, sp->prog.smem_bytes);
   if (e != cudaSuccess || occ < 1) { delete sp; return cuda_fail(ctx, e, "occupancy(expr_kernel)"); }
   sp->max_ctas_per_sm = occ;
   *out = sp;

@@ -83,7 +83,7 @@ __device__ __forceinline__ unsigned long long convert_value(unsigned long long v
   if (from == to) return v;
   Insn in;
   in.kind = K_ALU1; in.mop = M_CAST; in.t = static_cast<uint8_t>(from); in.t2 = static_cast<uint8_t>(to);
-  in.flags = 0; in.rhs_nullable = 0; in.rw = 0; in.a = 0; in.b = 0; in.code = 0; in.pad2 = 0;
+  in.flags = 0; in.rhs_nullable = 0; in.rw = 0; in.a = 0; in.b = 0; in.code = 0; in.pad2 = 0; in.off_a = 0; in.off_b = 0;
   u64 acc[1] = {v}, rhs[1] = {0}, rhs2[1] = {0};
   uint32_t n = 0, fail = 0;
   alu<1>(in, acc, n, rhs, 0u, rhs2, 0u, 1u, fail);

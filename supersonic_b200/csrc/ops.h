@@ -68,15 +68,26 @@ enum Kind {
   K_OUT = 7,       // output column a = acc, written to the tile's output staging (compacted)
 };
 
-// Fast-path codes: the hot (op, type) pairs get straight-line cases in the kernel; every
-// other instruction runs through the generic alu() below (code C_GENERIC).
+// Fast-path codes. Instructions whose operands cannot be NULL and whose type is one of the
+// hot ones get a pre-decoded, straight-line case in the kernel (operand address = one add);
+// everything else runs through the generic path (C_GENERIC) and alu() below.
 enum Code {
   C_GENERIC = 0,
-  C_ADD_I64, C_SUB_I64, C_MUL_I64, C_LT_I64, C_EQ_I64,
-  C_ADD_F64, C_SUB_F64, C_MUL_F64, C_LT_F64, C_EQ_F64,
-  C_ADD_I32, C_SUB_I32, C_MUL_I32, C_LT_I32, C_EQ_I32,
-  C_AND3, C_OR3,
+  C_LOAD8, C_LOAD4, C_LOADK,           // acc = slot / immediate, no NULLs
+  C_OUT8, C_OUT4,                      // staged output, column not nullable
+  C_PRED,
+  C_AND3_S, C_OR3_S,
+  // Binary ops: 4 consecutive codes per (type, op):
+  //   +0 acc (op) slot   +1 acc (op) imm   +2 slot (op) slot   +3 slot (op) imm
+  // (the last two are a LOAD fused into the operation by the compiler's peephole)
+  C_BIN_BASE,
+  C_BIN_I64 = C_BIN_BASE,              // ADD SUB MUL LT EQ
+  C_BIN_F64 = C_BIN_I64 + 20,
+  C_BIN_I32 = C_BIN_F64 + 20,
+  C_BIN_END = C_BIN_I32 + 20,
 };
+enum { B_ADD = 0, B_SUB = 1, B_MUL = 2, B_LT = 3, B_EQ = 4 };
+
 
 struct Insn {
   uint8_t kind;
@@ -90,6 +101,8 @@ struct Insn {
   int16_t b;
   uint16_t code;   // Code: fast path selector
   uint16_t pad2;
+  uint32_t off_a;  // byte offset of slot a from the shared-memory base (stage 0 for inputs)
+  uint32_t off_b;  // same for slot b; bit 31 of either: add the current stage's offset
 };
 
 // ---- container encode / decode ------------------------------------------------------------

@@ -14,10 +14,7 @@
 namespace ssb {
 
 enum {
-  kThreads = 256,             // threads per CTA
-  kRowsPerThread = 4,         // R
-  kTile = kThreads * kRowsPerThread,   // rows per tile (1024, the reference's block size)
-  kTileWords = kTile / 32,    // null-bitmap words per tile
+  kMaxTile = 4096,            // rows per tile of the largest kernel variant
   kMaxInsn = 64,
   kMaxImm = 16,
   kMaxIn = 12,
@@ -56,17 +53,19 @@ struct ExprParams {
   uint32_t stage_tx_bytes;              // bytes one full-tile TMA fill delivers (data only)
   uint32_t out_bytes;                   // bytes of one output buffer
   int32_t stages;
+  int32_t tile;                         // rows per tile (threads * rows per thread of the variant)
   // ---- run
   int64_t rows;
   int64_t num_tiles;
   int32_t has_pred;
   int32_t use_tma;
+  int32_t debug_nowait;
   unsigned long long* tile_status;      // per-tile kept-row counts | valid bit (Filter)
   int64_t* d_out_rows;
   int32_t* d_fail;
 };
 
-enum { kOutBuffers = 2 };              // output staging depth: tile i is copied out while i+1 is evaluated
+enum { kDefer = 1, kOutBuffers = kDefer + 1 };   // tile i is copied out while tile i + kDefer is evaluated
 
 struct Program {
   // compile-time description
@@ -80,6 +79,7 @@ struct Program {
   std::vector<int32_t> out_types;
   std::vector<int32_t> out_nullable;
   uint32_t smem_bytes;
+  int32_t variant;            // kernel variant (threads x rows per thread)
   int32_t bytes_in_row, bytes_out_row;
   bool has_signaling;
 };
@@ -89,7 +89,7 @@ struct Program {
 int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs,
                     const int32_t* input_types, const int32_t* input_nullable,
                     const int32_t* outputs, int32_t n_outputs, int32_t predicate,
-                    uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err);
+                    int32_t tile, uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err);
 
 }  // namespace ssb
 

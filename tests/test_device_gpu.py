@@ -1,0 +1,203 @@
+"""Device-resident checks through the C ABI at sizes closer to BASELINE.json: the table is
+generated in HBM by the counter-based generator, the host regenerates the same rows chunk by
+chunk (ssb_generate_host is bit-identical) and verifies the kernels' outputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from supersonic_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+GEN = {"a": (0, -(1 << 31), 1 << 32), "b": (0, -(1 << 31), 1 << 32), "c": (0, -(1 << 62), 1 << 63), "d": (0, 0, 1 << 20)}
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def host_col(name, rows, first=0):
+    kind, lo, span = GEN[name]
+    out = np.empty(rows, dtype=np.int64)
+    capi.load().ssb_generate_host(out.ctypes.data, rows, first, 42, "abcd".index(name), kind, lo, span)
+    return out
+
+
+def test_generator_device_equals_host(ctx):
+    rows = 1_000_003
+    for name in "abcd":
+        kind, lo, span = GEN[name]
+        p = ctx.malloc(rows * 8)
+        ctx.generate(p, rows, 77, 42, "abcd".index(name), kind, lo, span)
+        got = np.empty(rows, dtype=np.int64)
+        ctx.d2h(got, p)
+        want = np.empty(rows, dtype=np.int64)
+        ctx.lib.ssb_generate_host(want.ctypes.data, rows, 77, 42, "abcd".index(name), kind, lo, span)
+        assert np.array_equal(got, want)
+        ctx.free(p)
+
+
+def c2_program(ctx, k):
+    n, I64, B = capi.node, capi.INT64, capi.BOOL
+    nodes = [n(capi.OP_INPUT, I64, [0]), n(capi.OP_INPUT, I64, [1]), n(capi.OP_INPUT, I64, [2]), n(capi.OP_INPUT, I64, [3]),
+             n(capi.OP_MUL, I64, [0, 1]), n(capi.OP_ADD, I64, [4, 2]), n(capi.OP_CONST, I64, [], i64=k), n(capi.OP_LT, B, [3, 6])]
+    return capi.Program(ctx, nodes, [I64] * 4, [0] * 4, [5], predicate=7)
+
+
+@pytest.mark.parametrize("rows,k", [(60_000_000, 1 << 19), (10_000_001, 1 << 12), (5_000_000, 1 << 20), (4097, 0)])
+def test_c2_device_resident_bit_exact(ctx, rows, k):
+    """BASELINE config 2 shape (scaled): every kept row, in order, equals the host recomputation."""
+    d = {}
+    for name in "abcd":
+        kind, lo, span = GEN[name]
+        d[name] = ctx.malloc(rows * 8 + 256)
+        ctx.generate(d[name], rows, 0, 42, "abcd".index(name), kind, lo, span)
+    out = ctx.malloc(rows * 8 + 256)
+    prog = c2_program(ctx, k)
+    kept = prog.run_sync([(d[c], None, capi.INT64) for c in "abcd"], rows, [(out, None, capi.INT64)])
+    got = np.empty(kept, dtype=np.int64)
+    if kept:
+        ctx.d2h(got, out)
+    # host recomputation in chunks (the 1B-row table does not fit host RAM of every box)
+    pos = 0
+    step = 8_000_000
+    for first in range(0, rows, step):
+        m = min(step, rows - first)
+        a, b, c_, dd = (host_col(x, m, first) for x in "abcd")
+        e = (a * b + c_)[dd < k]
+        assert np.array_equal(got[pos:pos + len(e)], e), "mismatch in chunk starting at row %d" % first
+        pos += len(e)
+    assert pos == kept
+    prog.close()
+    for p in list(d.values()) + [out]:
+        ctx.free(p)
+
+
+def test_filter_is_idempotent_and_order_preserving(ctx):
+    rows = 20_000_000
+    dcol = ctx.malloc(rows * 8 + 256)
+    seq = ctx.malloc(rows * 8 + 256)
+    ctx.generate(dcol, rows, 0, 42, 3, 0, 0, 1 << 20)
+    ctx.h2d(seq, np.arange(rows, dtype=np.int64))
+    n, I64, B = capi.node, capi.INT64, capi.BOOL
+    nodes = [n(capi.OP_INPUT, I64, [0]), n(capi.OP_INPUT, I64, [1]), n(capi.OP_CONST, I64, [], i64=1 << 18), n(capi.OP_LT, B, [0, 2])]
+    prog = capi.Program(ctx, nodes, [I64, I64], [0, 0], [0, 1], predicate=3)
+    o1, o2 = ctx.malloc(rows * 8 + 256), ctx.malloc(rows * 8 + 256)
+    k1 = prog.run_sync([(dcol, None, I64), (seq, None, I64)], rows, [(o1, None, I64), (o2, None, I64)])
+    ids = np.empty(k1, dtype=np.int64)
+    ctx.d2h(ids, o2)
+    assert np.all(np.diff(ids) > 0)                       # input order kept
+    p1, p2 = ctx.malloc(k1 * 8 + 256), ctx.malloc(k1 * 8 + 256)
+    k2 = prog.run_sync([(o1, None, I64), (o2, None, I64)], k1, [(p1, None, I64), (p2, None, I64)])
+    assert k2 == k1                                        # filtering the result again keeps everything
+    ids2 = np.empty(k2, dtype=np.int64)
+    ctx.d2h(ids2, p2)
+    assert np.array_equal(ids, ids2)
+    prog.close()
+    for p in [dcol, seq, o1, o2, p1, p2]:
+        ctx.free(p)
+
+
+def _cols(items):
+    arr = (capi.Column * max(1, len(items)))()
+    for i, (d, n, t) in enumerate(items):
+        arr[i].data, arr[i].nulls, arr[i].dtype = d, n, t
+    return arr
+
+
+def _group(ctx, specs_def, expected):
+    specs = (capi.AggSpec * len(specs_def))()
+    for i, (fn, inp, it, ot) in enumerate(specs_def):
+        specs[i].fn, specs[i].input, specs[i].in_type, specs[i].out_type = fn, inp, it, ot
+    g = C.c_void_p()
+    kt, kn = (C.c_int32 * 1)(capi.INT64), (C.c_int32 * 1)(0)
+    ctx.check(ctx.lib.ssb_group_create(ctx.h, 1, kt, kn, len(specs_def), specs, expected, C.byref(g)))
+    return g
+
+
+def _finalize(ctx, g, n_aggs, dtypes):
+    n = C.c_int64()
+    ko, ao = _cols([(0, None, 0)]), _cols([(0, None, 0)] * n_aggs)
+    ctx.check(ctx.lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+    keys = np.empty(n.value, dtype=np.int64)
+    ctx.d2h(keys, ko[0].data)
+    outs = []
+    for i, dt in enumerate(dtypes):
+        a = np.empty(n.value, dtype=dt)
+        ctx.d2h(a, ao[i].data)
+        outs.append(a)
+    order = np.argsort(keys)
+    return keys[order], [a[order] for a in outs], (ko, ao, n.value)
+
+
+@pytest.mark.parametrize("groups", [7, 5000, 1_000_000])
+def test_group_chunked_updates_and_merge_equal_single_pass(ctx, groups):
+    """C3 shape: aggregating two halves separately and merging the partial tables
+    (ssb_group_merge: the multi-GPU exchange step) equals one pass, equals the host."""
+    rows = 6_000_000
+    k = ctx.malloc(rows * 8 + 256)
+    v = ctx.malloc(rows * 8 + 256)
+    ctx.generate(k, rows, 0, 42, 0, 1, 0, groups)
+    ctx.generate(v, rows, 0, 42, 1, 2, 0, 0)
+    spec = [(capi.AGG_SUM, 0, capi.DOUBLE, capi.DOUBLE), (capi.AGG_COUNT, -1, capi.INT64, capi.UINT64),
+            (capi.AGG_MAX, 0, capi.DOUBLE, capi.DOUBLE)]
+    dts = [np.float64, np.uint64, np.float64]
+    # one pass
+    g = _group(ctx, spec, 0)
+    ctx.check(ctx.lib.ssb_group_update(g, _cols([(k, None, capi.INT64)]), _cols([(v, None, capi.DOUBLE)]), rows))
+    k1, a1, _ = _finalize(ctx, g, 3, dts)
+    # two chunked updates into one table
+    g2 = _group(ctx, spec, 16)
+    half = (rows // 2 // 32) * 32
+    ctx.check(ctx.lib.ssb_group_update(g2, _cols([(k, None, capi.INT64)]), _cols([(v, None, capi.DOUBLE)]), half))
+    ctx.check(ctx.lib.ssb_group_update(g2, _cols([(k + half * 8, None, capi.INT64)]), _cols([(v + half * 8, None, capi.DOUBLE)]), rows - half))
+    k2, a2, _ = _finalize(ctx, g2, 3, dts)
+    # two tables merged
+    ga, gb = _group(ctx, spec, 0), _group(ctx, spec, 0)
+    ctx.check(ctx.lib.ssb_group_update(ga, _cols([(k, None, capi.INT64)]), _cols([(v, None, capi.DOUBLE)]), half))
+    ctx.check(ctx.lib.ssb_group_update(gb, _cols([(k + half * 8, None, capi.INT64)]), _cols([(v + half * 8, None, capi.DOUBLE)]), rows - half))
+    _, _, (kob, aob, nb) = _finalize(ctx, gb, 3, dts)
+    ctx.check(ctx.lib.ssb_group_merge(ga, nb, kob, aob))
+    k3, a3, _ = _finalize(ctx, ga, 3, dts)
+    # host
+    hk = np.empty(rows, dtype=np.int64)
+    hv = np.empty(rows, dtype=np.float64)
+    ctx.lib.ssb_generate_host(hk.ctypes.data, rows, 0, 42, 0, 1, 0, groups)
+    ctx.lib.ssb_generate_host(hv.ctypes.data, rows, 0, 42, 1, 2, 0, 0)
+    uk, inv = np.unique(hk, return_inverse=True)
+    hs = np.bincount(inv, weights=hv, minlength=len(uk))      # exactly summable payload: order-free
+    hc = np.bincount(inv, minlength=len(uk)).astype(np.uint64)
+    hm = np.full(len(uk), -np.inf)
+    np.maximum.at(hm, inv, hv)
+    for kk, aa in [(k1, a1), (k2, a2), (k3, a3)]:
+        assert np.array_equal(kk, uk)
+        assert np.array_equal(aa[0], hs) and np.array_equal(aa[1], hc) and np.array_equal(aa[2], hm)
+    for h in [g, g2, ga, gb]:
+        ctx.lib.ssb_group_destroy(h)
+    ctx.free(k)
+    ctx.free(v)
+
+
+def test_sort_permutation_is_sorted_and_a_permutation(ctx):
+    rows = 3_000_000
+    k = ctx.malloc(rows * 8 + 256)
+    ctx.generate(k, rows, 0, 42, 9, 0, -(1 << 40), 1 << 41)
+    perm = ctx.malloc(rows * 8 + 256)
+    for desc in (0, 1):
+        ctx.check(ctx.lib.ssb_sort_permutation(ctx.h, 1, _cols([(k, None, capi.INT64)]), (C.c_int32 * 1)(desc), rows, perm))
+        p = np.empty(rows, dtype=np.int64)
+        ctx.d2h(p, perm)
+        hk = np.empty(rows, dtype=np.int64)
+        ctx.lib.ssb_generate_host(hk.ctypes.data, rows, 0, 42, 9, 0, -(1 << 40), 1 << 41)
+        assert np.array_equal(np.sort(p), np.arange(rows))
+        s = hk[p]
+        assert np.all(np.diff(s) >= 0) if not desc else np.all(np.diff(s) <= 0)
+        # stable: equal keys keep ascending row ids
+        eq = np.diff(s) == 0
+        assert np.all(np.diff(p)[eq] > 0)
+    ctx.free(k)
+    ctx.free(perm)

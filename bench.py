@@ -47,6 +47,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def measured_traffic(rows):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum at the row count it was taken on), scaled to this
+    run's row count; None when no capture is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return float(t["dram_bytes"]) * rows / float(t["rows"])
+    except Exception:
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -197,8 +208,8 @@ def run_b200(args):
                        "rows_per_gpu": rows, "selectivity": sel, "l2": "inputs (%.1f GB per step) larger than L2"
                        % (rows * 32 / 1e9), "parallelism": "row-range shards, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "expr_kernel<256,4>", "kernel_ms": k_ms,
+                         "frac": achieved / peak, "traffic": measured_traffic(rows), "peak_source": peak_src,
+                         "kernel": "expr_kernel<96,8> (768-row tiles, 3 CTAs/SM)", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_row": 32.0 + 8.0 * sel},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -394,11 +394,15 @@ class Compiler {
     p.off_bar = 0;
     p.off_scan = 64;
     p.off_nullw = 64 + 512;
+    // Filter defers the copy-out by two tiles (the wave's counts are then always published);
+    // without a predicate the output position is known at once and one tile of slack suffices.
+    const uint32_t defer = p.has_pred ? kMaxDefer : 1;
+    p.defer = static_cast<int32_t>(defer);
     int stages = kMaxStages;
     for (;; --stages) {
       const uint32_t nullw_bytes = (stages * p.stage_nullw + tmp_nullw) * (tile_ / 32) * 4;
       const uint32_t data_off = (p.off_nullw + nullw_bytes + 1023) & ~1023u;
-      const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + kOutBuffers * p.out_bytes;
+      const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + (defer + 1) * p.out_bytes;
       if ((total <= smem_budget && stages >= 2) || stages == 1 || (stages == 2 && total <= smem_max)) {
         if (total > smem_max) return Fail(SSB_ERROR_NOT_IMPLEMENTED, "expression needs more shared memory than one SM has");
         p.stages = stages;

@@ -83,19 +83,28 @@ __device__ __forceinline__ void st_cs_u32(void* p, uint32_t v) {
 
 static constexpr unsigned long long kValid = 1ull << 63;
 
+// Consumer-only barrier (named barrier 1): the producer warp does not take part.
+template <int NT>
+__device__ __forceinline__ void bar_consumers() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
+// NT consumer threads evaluate the program; one extra producer warp issues the TMA fills, so
+// that no consumer warp carries the descriptor loop on its critical path.
 template <int NT, int R>
-__global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprParams p) {
+__global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ ExprParams p) {
   constexpr int TILE = NT * R;
   constexpr int NW = NT / 32;
   constexpr int WROWS = 32 * R;          // rows owned by one warp: [warp * WROWS, (warp + 1) * WROWS)
   extern __shared__ __align__(1024) unsigned char smem[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == NW;
   const int row_first = warp * WROWS + lane;   // thread's row k is row_first + 32 * k
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(smem + p.off_scan);             // [NW] kept rows per warp
   unsigned long long* red = reinterpret_cast<unsigned long long*>(warp_cnt + 32);  // [2 * 16] reduce scratch
-  unsigned long long* s_meta = red + 32;   // [0..3] kept rows of the staged tiles, [4] base, [5] wave base
+  unsigned long long* s_meta = red + 32;   // [0..3] kept rows of the staged tiles, [4..5] base (double buffered), [6] wave base
   uint32_t* nullw_base = reinterpret_cast<uint32_t*>(smem + p.off_nullw);
 
   const long long G = gridDim.x;
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
       for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
       fence_barrier_init();
     }
-    s_meta[5] = 0;
+    s_meta[6] = 0;
   }
   __syncthreads();
 
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
     }
   };
 
-  if (tid == 0) {
+  if (producer && lane == 0) {
     for (int s = 0; s < S && s < n_my; ++s) issue(bid + s * G, s);
   }
 
@@ -152,41 +161,43 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t fail = 0;
 
-  // kDefer extra iterations drain the deferred tiles.
-  // Wave-synchronous prefix, done by warp 0 alone and off the critical path: at the top of an
-  // iteration it fetches the kept-row counts the previous wave published (one coalesced read
-  // of gridDim.x words), the L2 round trip overlaps with the evaluation of the current tile,
-  // and the sums are reduced just before the barrier that ends the evaluation.
-  constexpr int kPrefetch = 12;   // status words per lane: covers gridDim.x <= 384
-  for (long long it = 0; it < n_my + kDefer; ++it) {
+  // kdefer_ extra iterations drain the deferred tiles.
+  // Wave-synchronous prefix, shared by all consumer threads: at the top of an iteration every
+  // thread fetches a few of the kept-row counts the wave of kdefer_ tiles ago published (together
+  // one coalesced read of gridDim.x words); the L2 round trip overlaps with the evaluation of the
+  // current tile; the partial sums are combined across the warps through the barrier that ends
+  // the evaluation anyway.
+  const int kdefer_ = p.defer;
+  const int n_obuf = kdefer_ + 1;
+  constexpr int kPrefetch = 6;    // status words per thread: covers gridDim.x <= 6 * NT
+  unsigned long long wave_base = 0;   // kept rows of all earlier waves (every thread keeps a copy)
+  for (long long it = 0; it < n_my + kdefer_; ++it) {
     unsigned long long pre[kPrefetch];
-    const bool scan_wave = p.has_pred && it >= kDefer && warp == 0;
+    const bool scan_wave = p.has_pred && it >= kdefer_ && !producer;
     if (scan_wave) {
-      const long long w0 = (it - kDefer) * G;
+      const long long w0 = (it - kdefer_) * G;
 #pragma unroll
       for (int q = 0; q < kPrefetch; ++q) {
-        const long long j = w0 + lane + q * 32;
+        const long long j = w0 + tid + q * NT;
         pre[q] = (j < w0 + G && j < p.num_tiles) ? ld_relaxed(&p.tile_status[j]) : kValid;
       }
     }
     auto finish_wave = [&]() {
-      // base of this CTA's tile of wave it-1 = kept rows of all earlier waves + of the tiles
-      // before it inside the wave
-      const long long w0 = (it - kDefer) * G;
-      const long long my_tile = bid + (it - kDefer) * G;
+      const long long w0 = (it - kdefer_) * G;
+      const long long my_tile = bid + (it - kdefer_) * G;
       unsigned long long before = 0, sum = 0;
 #pragma unroll
       for (int q = 0; q < kPrefetch; ++q) {
-        const long long j = w0 + lane + q * 32;
+        const long long j = w0 + tid + q * NT;
         unsigned long long v = pre[q];
-        while (!(v & kValid) && !p.debug_nowait) v = ld_relaxed(&p.tile_status[j]);   // a CTA more than one tile behind
+        while (!(v & kValid) && !p.debug_nowait) v = ld_relaxed(&p.tile_status[j]);   // a CTA behind
         v &= ~kValid;
         sum += v;
         if (j < my_tile) before += v;
       }
-      for (long long j = w0 + lane + kPrefetch * 32; j < w0 + G && j < p.num_tiles; j += 32) {
-        unsigned long long v;
-        do { v = ld_relaxed(&p.tile_status[j]); } while (!(v & kValid));
+      for (long long j = w0 + tid + kPrefetch * NT; j < w0 + G && j < p.num_tiles; j += NT) {
+        unsigned long long v = ld_relaxed(&p.tile_status[j]);
+        while (!(v & kValid) && !p.debug_nowait) v = ld_relaxed(&p.tile_status[j]);
         v &= ~kValid;
         sum += v;
         if (j < my_tile) before += v;
@@ -197,10 +208,17 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
         sum += __shfl_xor_sync(0xffffffffu, sum, d);
       }
       if (lane == 0) {
-        s_meta[4] = s_meta[5] + before;
-        s_meta[5] += sum;
+        red[(it & 1) * 16 + warp * 2] = before;
+        red[(it & 1) * 16 + warp * 2 + 1] = sum;
       }
     };
+    if (producer) {
+      // ---- producer warp: wave prefix (then refill the stage
+      // the consumers just released
+      __syncthreads();
+      if (lane == 0 && it < n_my && it + S < n_my) issue(bid + (it + S) * G, static_cast<int>(it % S));
+      continue;
+    }
     // ======================================================== evaluate tile `it`
     if (it < n_my) {
       const long long tile = bid + it * G;
@@ -209,7 +227,7 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
       const long long row0 = tile * TILE;
       const int n = static_cast<int>(p.rows - row0 < TILE ? p.rows - row0 : TILE);
       const bool via_tma = p.use_tma && n == TILE;
-      unsigned char* obuf = smem + p.off_out + static_cast<int>(it % kOutBuffers) * p.out_bytes;
+      unsigned char* obuf = smem + p.off_out + static_cast<int>(it % n_obuf) * p.out_bytes;
 
       if (via_tma) {
         mbar_wait(&bars[stage], parity);
@@ -227,7 +245,7 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
             for (int r = tid; r < n; r += NT) dst[r] = src[r];
           }
         }
-        __syncthreads();
+        bar_consumers<NT>();
       }
       // Null words of inputs declared nullable: TMA delivered them when the column has a
       // bitmap; otherwise (no bitmap in this run, or the plain-load path) fill them here.
@@ -244,10 +262,10 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
         }
         filled = true;
       }
-      if (filled) __syncthreads();
+      if (filled) bar_consumers<NT>();
       // Without a predicate no barrier separates this tile's staging writes from the copy-out
       // of the tile evaluated two iterations ago (same buffer): add one.
-      if (!p.has_pred) __syncthreads();
+      if (!p.has_pred) bar_consumers<NT>();
 
       uint32_t live = 0;
 #pragma unroll
@@ -371,7 +389,7 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
               }
               uint32_t* wc = warp_cnt + 16 * (it & 1);   // double buffered: one barrier per tile
               if (lane == 0) wc[warp] = run;
-              __syncthreads();
+              bar_consumers<NT>();
               uint32_t before = 0, total = 0;
 #pragma unroll
               for (int w = 0; w < NW; ++w) {
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
 #pragma unroll
               for (int k = 0; k < R; ++k) pos[k] += static_cast<int>(before);
               if (tid == 0) {
-                s_meta[it % kOutBuffers] = total;
+                s_meta[it % n_obuf] = total;
                 st_relaxed(&p.tile_status[tile], kValid | total);   // this tile's share of its wave
               }
             } break;
@@ -501,23 +519,29 @@ __global__ void __launch_bounds__(NT) expr_kernel(const __grid_constant__ ExprPa
 #undef SSB_ENC
 #undef SSB_CMP
       if (scan_wave) finish_wave();
-      __syncthreads();   // the stage and the temporaries are free; the staging buffer is complete
-      if (tid == 0 && it + S < n_my) issue(tile + S * G, stage);
+      __syncthreads();   // all threads: the stage and the temporaries are free; the wave base is published
     } else {
       if (scan_wave) finish_wave();
       __syncthreads();
     }
 
-    // ======================================================== write out tile `it - kDefer`
-    if (it >= kDefer) {
-      const long long wave = it - kDefer;
+    // ======================================================== write out tile `it - kdefer_`
+    if (it >= kdefer_) {
+      const long long wave = it - kdefer_;
       const long long tile = bid + wave * G;
-      const unsigned char* obuf = smem + p.off_out + static_cast<int>(wave % kOutBuffers) * p.out_bytes;
+      const unsigned char* obuf = smem + p.off_out + static_cast<int>(wave % n_obuf) * p.out_bytes;
       long long total;
       long long base;
       if (p.has_pred) {
-        base = static_cast<long long>(s_meta[4]);
-        total = static_cast<long long>(s_meta[wave % kOutBuffers]);
+        unsigned long long before = 0, sum = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          before += red[(it & 1) * 16 + w * 2];
+          sum += red[(it & 1) * 16 + w * 2 + 1];
+        }
+        base = static_cast<long long>(wave_base + before);
+        wave_base += sum;
+        total = static_cast<long long>(s_meta[wave % n_obuf]);
         if (tile == p.num_tiles - 1 && tid == 0 && p.d_out_rows != nullptr) *p.d_out_rows = base + total;
       } else {
         base = tile * static_cast<long long>(TILE);
@@ -573,9 +597,11 @@ static const Variant kVariants[] = {
     {64, 16, expr_kernel<64, 16>},
     {128, 4, expr_kernel<128, 4>},
     {64, 8, expr_kernel<64, 8>},
+    {96, 8, expr_kernel<96, 8>},
+    {96, 4, expr_kernel<96, 4>},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-static const int kDefaultVariant = 1;
+static const int kDefaultVariant = 7;   // 96 consumer threads x 8 rows = 768-row tiles, three CTAs per SM
 
 static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t rows,
                           const ssb_column* outputs, int64_t* d_out_rows) {
@@ -623,7 +649,7 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
   long long grid = static_cast<long long>(ctx->num_sms) * sp->max_ctas_per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
   TimedRegion timed(ctx);
-  var.kernel<<<static_cast<unsigned>(grid), var.threads, prog.smem_bytes, ctx->stream>>>(p);
+  var.kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);
   ++ctx->launches;
   SSB_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -647,7 +673,7 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
   }
   // Two resident CTAs per SM is the design point; wide plans fall back to fewer stages, then
   // to the smallest tile.
-  int ctas = 2;
+  int ctas = 3;   // design point: three resident CTAs per SM (measured best, profiles/r1_summary.md)
   if (const char* env = getenv("SSB200_EXPR_CTAS")) { const int c = atoi(env); if (c >= 1 && c <= 8) ctas = c; }
   const uint32_t budget = static_cast<uint32_t>((ctx->smem_per_sm - ctas * ctx->smem_reserved) / ctas);
   ssb_program* sp = nullptr;
@@ -673,7 +699,7 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
                                        static_cast<int>(ctx->smem_optin));
   if (e != cudaSuccess) { delete sp; return cuda_fail(ctx, e, "cudaFuncSetAttribute(expr_kernel)"); }
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.kernel, var.threads, sp->prog.smem_bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.kernel, var.threads + 32, sp->prog.smem_bytes);
   if (e != cudaSuccess || occ < 1) { delete sp; return cuda_fail(ctx, e, "occupancy(expr_kernel)"); }
   sp->max_ctas_per_sm = occ;
   *out = sp;

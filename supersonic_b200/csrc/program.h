@@ -54,6 +54,7 @@ struct ExprParams {
   uint32_t out_bytes;                   // bytes of one output buffer
   int32_t stages;
   int32_t tile;                         // rows per tile (threads * rows per thread of the variant)
+  int32_t defer;                        // copy-out lags evaluation by this many tiles (out buffers = defer + 1)
   // ---- run
   int64_t rows;
   int64_t num_tiles;
@@ -65,7 +66,7 @@ struct ExprParams {
   int32_t* d_fail;
 };
 
-enum { kDefer = 1, kOutBuffers = kDefer + 1 };   // tile i is copied out while tile i + kDefer is evaluated
+enum { kMaxDefer = 2 };   // Filter: tile i is copied out while tile i + defer is evaluated
 
 struct Program {
   // compile-time description

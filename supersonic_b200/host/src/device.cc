@@ -1,6 +1,7 @@
 // device.cc -- bridge between the supersonic.h mirror and the C ABI of libssb200.so.
 #include <stdio.h>
 
+#include <map>
 #include <mutex>
 
 #include "internal.h"
@@ -23,12 +24,26 @@ FailureOr<Session*> Session::Get() {
       THROW(new Exception(ERROR_GENERAL_IO_ERROR,
                           "supersonic-b200: no usable B200 (sm_100a) device; this implementation has no CPU path"));
     }
-    session = new Session(ctx);
+    session = new Session(ctx, device);
   }
   return Success(session);
 }
 
-Exception* Session::Error(int code, const char* what) const {
+FailureOr<ssb_ctx*> Session::lane(int i) {
+  if (lanes_[i] == NULL) {
+    ssb_ctx* c = NULL;
+    if (ssb_ctx_create(device_, &c) != 0 || c == NULL) {
+      THROW(new Exception(ERROR_GENERAL_IO_ERROR, "supersonic-b200: cannot create a copy/compute lane context"));
+    }
+    lanes_[i] = c;
+  }
+  ssb_ctx* c = lanes_[i];
+  return Success(c);
+}
+
+Exception* Session::Error(int code, const char* what) const { return ErrorOn(ctx_, code, what); }
+
+Exception* Session::ErrorOn(ssb_ctx* ctx, int code, const char* what) {
   ReturnCode rc = ERROR_UNKNOWN_ERROR;
   switch (code) {
     case SSB_ERROR_MEMORY_EXCEEDED: rc = ERROR_MEMORY_EXCEEDED; break;
@@ -38,7 +53,7 @@ Exception* Session::Error(int code, const char* what) const {
     case SSB_ERROR_INVALID_ARGUMENT_VALUE: rc = ERROR_INVALID_ARGUMENT_VALUE; break;
     default: break;
   }
-  return new Exception(rc, string(what) + ": " + ssb_last_error(ctx_));
+  return new Exception(rc, string(what) + ": " + ssb_last_error(ctx));
 }
 
 #define SSB_CALL(session, call, what)                              \
@@ -48,20 +63,72 @@ Exception* Session::Error(int code, const char* what) const {
   } while (0)
 
 // ------------------------------------------------------------------ device memory
-FailureOrVoid DeviceBuffer::Allocate(size_t bytes) {
-  Free();
+namespace {
+struct PoolState {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks[2];
+};
+PoolState* pool_state() {
+  static PoolState* p = new PoolState;
+  return p;
+}
+}  // namespace
+
+FailureOr<void*> MemoryPool::Acquire(Kind kind, size_t bytes, size_t* granted) {
+  const size_t granule = 1u << 20;
+  const size_t want = ((bytes ? bytes : 1) + granule - 1) / granule * granule;
+  PoolState* ps = pool_state();
+  {
+    std::lock_guard<std::mutex> lock(ps->mu);
+    std::multimap<size_t, void*>::iterator it = ps->free_blocks[kind].lower_bound(want);
+    if (it != ps->free_blocks[kind].end() && it->first <= want * 2 + granule) {
+      void* p = it->second;
+      *granted = it->first;
+      ps->free_blocks[kind].erase(it);
+      return Success(p);
+    }
+  }
   FailureOr<Session*> s = Session::Get();
   PROPAGATE_ON_FAILURE(s);
-  SSB_CALL(s.get(), ssb_malloc(s.get()->ctx(), bytes, &ptr_), "device allocation");
+  void* p = NULL;
+  int rc = kind == DEVICE ? ssb_malloc(s.get()->ctx(), want, &p) : ssb_malloc_host(s.get()->ctx(), want, &p);
+  if (rc != 0) {
+    // give cached blocks back to the driver and retry once
+    {
+      std::lock_guard<std::mutex> lock(ps->mu);
+      for (std::multimap<size_t, void*>::iterator it = ps->free_blocks[kind].begin(); it != ps->free_blocks[kind].end(); ++it) {
+        if (kind == DEVICE) ssb_free(s.get()->ctx(), it->second); else ssb_free_host(s.get()->ctx(), it->second);
+      }
+      ps->free_blocks[kind].clear();
+    }
+    rc = kind == DEVICE ? ssb_malloc(s.get()->ctx(), want, &p) : ssb_malloc_host(s.get()->ctx(), want, &p);
+    if (rc != 0) THROW(s.get()->Error(rc, kind == DEVICE ? "device allocation" : "pinned allocation"));
+  }
+  *granted = want;
+  return Success(p);
+}
+
+void MemoryPool::Release(Kind kind, void* ptr, size_t granted) {
+  if (ptr == NULL) return;
+  PoolState* ps = pool_state();
+  std::lock_guard<std::mutex> lock(ps->mu);
+  ps->free_blocks[kind].insert(std::make_pair(granted, ptr));
+}
+
+FailureOrVoid DeviceBuffer::Allocate(size_t bytes) {
+  Free();
+  FailureOr<void*> p = MemoryPool::Acquire(MemoryPool::DEVICE, bytes, &granted_);
+  PROPAGATE_ON_FAILURE(p);
+  ptr_ = p.get();
   bytes_ = bytes;
   return Success();
 }
 void DeviceBuffer::Free() {
   if (ptr_ != NULL) {
-    FailureOr<Session*> s = Session::Get();
-    if (s.is_success()) ssb_free(s.get()->ctx(), ptr_);
+    MemoryPool::Release(MemoryPool::DEVICE, ptr_, granted_);
     ptr_ = NULL;
     bytes_ = 0;
+    granted_ = 0;
   }
 }
 
@@ -203,6 +270,16 @@ struct Lowering {
   }
 };
 }  // namespace
+
+void LowerProgram(const vector<NodePtr>& outputs, const NodePtr& predicate, vector<ssb_expr_node>* nodes,
+                  vector<int>* used, vector<int32_t>* outs, int* pred) {
+  Lowering low;
+  outs->clear();
+  for (size_t j = 0; j < outputs.size(); ++j) outs->push_back(low.Lower(outputs[j]));
+  *pred = predicate ? low.Lower(predicate) : -1;
+  *nodes = low.nodes;
+  *used = low.used;
+}
 
 DeviceProgram::~DeviceProgram() { if (prog_) ssb_program_destroy(prog_); }
 

@@ -38,16 +38,37 @@ class Session {
  public:
   static FailureOr<Session*> Get();
   ssb_ctx* ctx() const { return ctx_; }
+  // Additional contexts (own stream each) on the same device, for copy/compute overlap.
+  FailureOr<ssb_ctx*> lane(int i);
+  int device() const { return device_; }
   Exception* Error(int code, const char* what) const;
+  static Exception* ErrorOn(ssb_ctx* ctx, int code, const char* what);
  private:
-  explicit Session(ssb_ctx* c) : ctx_(c) {}
+  Session(ssb_ctx* c, int device) : ctx_(c), device_(device) { lanes_[0] = lanes_[1] = NULL; }
   ssb_ctx* ctx_;
+  int device_;
+  ssb_ctx* lanes_[2];
+};
+
+// Lowers bound expression nodes to the C ABI's node array. `used` lists the referenced input
+// columns in program order; `outs` / `pred` index into `nodes`.
+void LowerProgram(const vector<NodePtr>& outputs, const NodePtr& predicate, vector<ssb_expr_node>* nodes,
+                  vector<int>* used, vector<int32_t>* outs, int* pred);
+
+// Caching allocator for device and pinned host memory: cudaMalloc / cudaMallocHost cost
+// milliseconds, cursors are created per query. Blocks are rounded up to 1 MiB granules and
+// returned to a free list instead of the driver (all users synchronise before releasing).
+class MemoryPool {
+ public:
+  enum Kind { DEVICE = 0, PINNED = 1 };
+  static FailureOr<void*> Acquire(Kind kind, size_t bytes, size_t* granted);
+  static void Release(Kind kind, void* ptr, size_t granted);
 };
 
 // Device memory owned through the session.
 class DeviceBuffer {
  public:
-  DeviceBuffer() : ptr_(NULL), bytes_(0) {}
+  DeviceBuffer() : ptr_(NULL), bytes_(0), granted_(0) {}
   ~DeviceBuffer() { Free(); }
   FailureOrVoid Allocate(size_t bytes);
   void Free();
@@ -58,6 +79,7 @@ class DeviceBuffer {
   void operator=(const DeviceBuffer&);
   void* ptr_;
   size_t bytes_;
+  size_t granted_;
 };
 
 // A set of equally long device columns: either borrowed (device pointers handed in through

@@ -74,8 +74,66 @@ class ViewCursor : public Cursor {
 class RowwiseCursor : public GpuCursor {
  public:
   RowwiseCursor(const RowwisePlan& plan, BufferAllocator* allocator, CursorId id)
-      : GpuCursor(plan.schema, allocator, "RowwiseCursor"), plan_(plan), id_(id) {}
+      : GpuCursor(plan.schema, allocator, "RowwiseCursor"), plan_(plan), id_(id), mode_(UNDECIDED),
+        out_view_(plan.schema), next_first_(0), active_(-1), served_(0) {
+    lanes_[0].Reset();
+    lanes_[1].Reset();
+  }
+  virtual ~RowwiseCursor() {
+    for (int i = 0; i < 2; ++i) lanes_[i].Free();
+  }
   virtual CursorId GetCursorId() const { return id_; }
+
+  // Host-resident inputs are streamed: the view is cut into chunks that alternate between two
+  // contexts (streams), so that the H2D copy of chunk i+1, the kernel of chunk i and the D2H
+  // copy of chunk i-1 overlap. Device-resident inputs and parents that are GPU cursors use
+  // Produce() instead (whole shard, no host round trip).
+  virtual ResultView Next(rowcount_t max_row_count) {
+    if (mode_ == UNDECIDED) {
+      FailureOrVoid d = DecideMode();
+      if (d.is_failure()) return ResultView::Failure(d.release_exception());
+    }
+    if (mode_ == WHOLE) return GpuCursor::Next(max_row_count);
+    if (interrupted()) return ResultView::Failure(new Exception(INTERRUPTED, "cursor interrupted"));
+    for (;;) {
+      if (active_ >= 0 && served_ < static_cast<rowcount_t>(lanes_[active_].kept)) {
+        Lane& l = lanes_[active_];
+        rowcount_t n = static_cast<rowcount_t>(l.kept) - served_;
+        if (n > max_row_count) n = max_row_count;
+        for (int j = 0; j < out_view_.column_count(); ++j) {
+          const size_t w = out_view_.column(j).type_info().size();
+          const bool nullable = out_view_.schema().attribute(j).is_nullable();
+          out_view_.mutable_column(j)->Reset(static_cast<char*>(l.h_out[j]) + served_ * w,
+                                             nullable ? static_cast<bool*>(l.h_out_nulls[j]) + served_ : NULL);
+        }
+        out_view_.set_row_count(n);
+        served_ += n;
+        return ResultView::Success(&out_view_);
+      }
+      // the active lane is drained: give it the next chunk and switch to the other lane
+      if (active_ >= 0) {
+        lanes_[active_].busy = false;
+        FailureOrVoid l = LaunchNext(active_);
+        if (l.is_failure()) return ResultView::Failure(l.release_exception());
+        active_ ^= 1;
+      } else {
+        FailureOrVoid l0 = LaunchNext(0);
+        if (l0.is_failure()) return ResultView::Failure(l0.release_exception());
+        FailureOrVoid l1 = LaunchNext(1);
+        if (l1.is_failure()) return ResultView::Failure(l1.release_exception());
+        active_ = 0;
+      }
+      Lane& l = lanes_[active_];
+      if (!l.busy) return ResultView::EOS();
+      const int rc = ssb_ctx_sync(l.ctx);
+      if (rc != 0) return ResultView::Failure(Session::ErrorOn(l.ctx, rc, "row-wise pipeline"));
+      const int frc = ssb_program_check_failure(l.program);
+      if (frc != 0) return ResultView::Failure(Session::ErrorOn(l.ctx, frc, "expression evaluation"));
+      l.kept = *l.h_count;
+      served_ = 0;
+    }
+  }
+
  protected:
   virtual FailureOrVoid Run(DeviceTable* result) {
     // One kernel evaluates the predicate and every output column. Plans too wide for one
@@ -141,8 +199,174 @@ class RowwiseCursor : public GpuCursor {
     return Success();
   }
  private:
+  enum Mode { UNDECIDED, WHOLE, STREAM };
+  struct Lane {
+    ssb_ctx* ctx;
+    ssb_program* program;
+    vector<void*> d_in, d_in_nulls, d_out, d_out_nulls, h_out, h_out_nulls;
+    vector<std::pair<int, std::pair<void*, size_t> > > owned;   // (kind, (ptr, granted)) from the MemoryPool
+    void* d_bools;
+    int64_t* d_count;
+    int64_t* h_count;
+    int64 kept;
+    bool busy;
+    void Reset() { ctx = NULL; program = NULL; d_bools = NULL; d_count = NULL; h_count = NULL; kept = 0; busy = false; }
+    void Free() {
+      if (ctx == NULL) return;
+      ssb_ctx_sync(ctx);
+      if (program) ssb_program_destroy(program);
+      for (size_t i = 0; i < owned.size(); ++i) {
+        MemoryPool::Release(static_cast<MemoryPool::Kind>(owned[i].first), owned[i].second.first, owned[i].second.second);
+      }
+      owned.clear();
+      d_in.clear(); d_in_nulls.clear(); d_out.clear(); d_out_nulls.clear(); h_out.clear(); h_out_nulls.clear();
+      Reset();
+    }
+  };
+
+#define LANE_CALL(lane, call, what)                                              \
+  do {                                                                           \
+    const int rc_ = (call);                                                      \
+    if (rc_ != 0) THROW(Session::ErrorOn((lane).ctx, rc_, what));                \
+  } while (0)
+
+  static FailureOr<void*> Pooled(Lane* l, MemoryPool::Kind kind, size_t bytes) {
+    size_t granted = 0;
+    FailureOr<void*> p = MemoryPool::Acquire(kind, bytes, &granted);
+    PROPAGATE_ON_FAILURE(p);
+    l->owned.push_back(std::make_pair(static_cast<int>(kind), std::make_pair(p.get(), granted)));
+    return p;
+  }
+#define POOLED(var, lane, kind, bytes)                                \
+  void* var = NULL;                                                   \
+  {                                                                   \
+    FailureOr<void*> r_ = Pooled(&(lane), MemoryPool::kind, (bytes)); \
+    PROPAGATE_ON_FAILURE(r_);                                         \
+    var = r_.get();                                                   \
+  }
+
+  FailureOrVoid DecideMode() {
+    mode_ = WHOLE;
+    if (plan_.source) return Success();
+    const rowcount_t rows = plan_.base.row_count();
+    rowcount_t chunk = 4u << 20;
+    if (const char* env = getenv("SSB200_CHUNK_ROWS")) chunk = static_cast<rowcount_t>(atoll(env));
+    chunk = (chunk / 1024) * 1024;
+    if (chunk < 1024 || rows <= chunk) return Success();
+    vector<int32_t> outs;
+    int pred = -1;
+    LowerProgram(plan_.outputs, plan_.predicate, &nodes_, &used_, &outs, &pred);
+    for (size_t k = 0; k < used_.size(); ++k) {
+      if (IsDevicePointer(plan_.base.column(used_[k]).data().raw())) return Success();
+    }
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    vector<int32_t> types, nullable;
+    for (size_t k = 0; k < used_.size(); ++k) {
+      types.push_back(plan_.base_schema.attribute(used_[k]).type());
+      nullable.push_back(plan_.base_schema.attribute(used_[k]).is_nullable() ? 1 : 0);
+    }
+    int32_t dummy = 0;
+    for (int i = 0; i < 2; ++i) {
+      Lane& l = lanes_[i];
+      FailureOr<ssb_ctx*> c = sr.get()->lane(i);
+      PROPAGATE_ON_FAILURE(c);
+      l.ctx = c.get();
+      const int rc = ssb_program_create(l.ctx, nodes_.data(), static_cast<int32_t>(nodes_.size()),
+                                        static_cast<int32_t>(used_.size()), types.empty() ? &dummy : types.data(),
+                                        nullable.empty() ? &dummy : nullable.data(), outs.empty() ? &dummy : outs.data(),
+                                        static_cast<int32_t>(outs.size()), pred, &l.program);
+      if (rc == SSB_ERROR_NOT_IMPLEMENTED) { l.program = NULL; return Success(); }   // too wide: whole-shard path splits it
+      LANE_CALL(l, rc, "expression compilation");
+      for (size_t k = 0; k < used_.size(); ++k) {
+        POOLED(d, l, DEVICE, chunk * plan_.base.column(used_[k]).type_info().size() + 256);
+        POOLED(dn, l, DEVICE, chunk / 8 + 256);
+        l.d_in.push_back(d);
+        l.d_in_nulls.push_back(dn);
+      }
+      for (int j = 0; j < plan_.schema.attribute_count(); ++j) {
+        const size_t w = GetTypeInfo(plan_.schema.attribute(j).type()).size();
+        POOLED(d, l, DEVICE, chunk * w + 256);
+        POOLED(dn, l, DEVICE, chunk / 8 + 256);
+        POOLED(h, l, PINNED, chunk * w + 256);
+        POOLED(hn, l, PINNED, chunk + 256);
+        memset(hn, 0, chunk + 256);
+        l.d_out.push_back(d); l.d_out_nulls.push_back(dn); l.h_out.push_back(h); l.h_out_nulls.push_back(hn);
+      }
+      POOLED(db, l, DEVICE, chunk + 256);
+      l.d_bools = db;
+      POOLED(dc, l, DEVICE, 64);
+      POOLED(hc, l, PINNED, 64);
+      l.d_count = static_cast<int64_t*>(dc);
+      l.h_count = static_cast<int64_t*>(hc);
+    }
+    chunk_ = chunk;
+    mode_ = STREAM;
+    return Success();
+  }
+
+  // Queues H2D + kernel + D2H of the next chunk on the lane's stream (asynchronous).
+  FailureOrVoid LaunchNext(int lane) {
+    Lane& l = lanes_[lane];
+    const rowcount_t total = plan_.base.row_count();
+    if (next_first_ >= total) return Success();
+    const rowcount_t first = next_first_;
+    const rowcount_t rows = total - first < chunk_ ? total - first : chunk_;
+    next_first_ += rows;
+    vector<ssb_column> ic(used_.size()), oc(l.d_out.size());
+    for (size_t k = 0; k < used_.size(); ++k) {
+      const Column& src = plan_.base.column(used_[k]);
+      const size_t w = src.type_info().size();
+      LANE_CALL(l, ssb_memcpy_h2d(l.ctx, l.d_in[k], static_cast<const char*>(src.data().raw()) + first * w, rows * w), "upload");
+      ic[k].data = l.d_in[k];
+      ic[k].dtype = src.attribute().type();
+      ic[k].reserved = 0;
+      ic[k].nulls = NULL;
+      if (src.is_null() != NULL) {
+        LANE_CALL(l, ssb_memcpy_h2d(l.ctx, l.d_bools, src.is_null() + first, rows), "upload nulls");
+        LANE_CALL(l, ssb_nulls_pack(l.ctx, static_cast<const uint8_t*>(l.d_bools), static_cast<int64_t>(rows),
+                                    static_cast<uint32_t*>(l.d_in_nulls[k])), "null pack");
+        ic[k].nulls = static_cast<uint32_t*>(l.d_in_nulls[k]);
+      }
+    }
+    for (size_t j = 0; j < oc.size(); ++j) {
+      oc[j].data = l.d_out[j];
+      oc[j].nulls = static_cast<uint32_t*>(l.d_out_nulls[j]);
+      oc[j].dtype = plan_.schema.attribute(static_cast<int>(j)).type();
+      oc[j].reserved = 0;
+    }
+    ssb_column dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    LANE_CALL(l, ssb_program_run(l.program, ic.empty() ? &dummy : ic.data(), static_cast<int64_t>(rows),
+                                 oc.empty() ? &dummy : oc.data(), l.d_count), "expression evaluation");
+    LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_count, l.d_count, sizeof(int64_t)), "download");
+    for (size_t j = 0; j < oc.size(); ++j) {
+      const size_t w = GetTypeInfo(plan_.schema.attribute(static_cast<int>(j)).type()).size();
+      // the kept-row count is not known on the host yet: copy the chunk's capacity
+      LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_out[j], l.d_out[j], rows * w), "download");
+      if (plan_.schema.attribute(static_cast<int>(j)).is_nullable() &&
+          ssb_program_output_nullable(l.program, static_cast<int32_t>(j))) {
+        LANE_CALL(l, ssb_nulls_unpack(l.ctx, static_cast<const uint32_t*>(l.d_out_nulls[j]), static_cast<int64_t>(rows),
+                                      static_cast<uint8_t*>(l.d_bools)), "null unpack");
+        LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_out_nulls[j], l.d_bools, rows), "download nulls");
+      }
+    }
+    l.busy = true;
+    return Success();
+  }
+#undef LANE_CALL
+#undef POOLED
+
   RowwisePlan plan_;
   CursorId id_;
+  Mode mode_;
+  View out_view_;
+  vector<ssb_expr_node> nodes_;
+  vector<int> used_;
+  Lane lanes_[2];
+  rowcount_t chunk_, next_first_;
+  int active_;
+  rowcount_t served_;
 };
 
 FailureOrOwned<Cursor> CreateRowwiseCursor(const Operation* op, BufferAllocator* allocator, CursorId id) {

@@ -113,6 +113,80 @@ def build_program(capi, ctx):
     return capi.Program(ctx, nodes, [I64] * 4, [0] * 4, [5], predicate=7)
 
 
+class _DevArray(object):
+    """Zero-copy view of device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
+    """BASELINE config 3 shape, sharded by row range: GroupAggregate(k; SUM(v), COUNT(*)) with
+    k = u mod 1e6 (INT64), v = (u >> 44) * 2^-10 (exactly summable DOUBLE). Every rank aggregates
+    its shard (ssb_group_update), the dense partial tables are all-gathered over NCCL and merged
+    (ssb_group_merge). Returns rows/s over all ranks (host clock around device syncs)."""
+    lib = ctx.lib
+    first = rank * rows
+    k = ctx.malloc(rows * 8 + 256)
+    v = ctx.malloc(rows * 8 + 256)
+    ctx.generate(k, rows, first, SEED, 20, 1, 0, 1000000)
+    ctx.generate(v, rows, first, SEED, 21, 2, 0, 0)
+    specs = (capi.AggSpec * 2)()
+    specs[0].fn, specs[0].input, specs[0].in_type, specs[0].out_type = capi.AGG_SUM, 0, capi.DOUBLE, capi.DOUBLE
+    specs[1].fn, specs[1].input, specs[1].in_type, specs[1].out_type = capi.AGG_COUNT, -1, capi.INT64, capi.UINT64
+    kt, kn = (C.c_int32 * 1)(capi.INT64), (C.c_int32 * 1)(0)
+
+    def cols(items):
+        arr = (capi.Column * max(1, len(items)))()
+        for i, (d, n_, t) in enumerate(items):
+            arr[i].data, arr[i].nulls, arr[i].dtype = d, n_, t
+        return arr
+
+    times, groups = [], 0
+    for it in range(3):
+        g = C.c_void_p()
+        ctx.check(lib.ssb_group_create(ctx.h, 1, kt, kn, 2, specs, 1000000, C.byref(g)))
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.check(lib.ssb_group_update(g, cols([(k, None, capi.INT64)]), cols([(v, None, capi.DOUBLE)]), rows))
+        n = C.c_int64()
+        ko, ao = cols([(0, None, 0)]), cols([(0, None, 0), (0, None, 0)])
+        ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+        if world > 1:
+            from supersonic_b200.distributed import allgather_ragged
+            tk = torch.as_tensor(_DevArray(ko[0].data, n.value, "<i8"), device="cuda")
+            ts = torch.as_tensor(_DevArray(ao[0].data, n.value, "<f8"), device="cuda")
+            tc = torch.as_tensor(_DevArray(ao[1].data, n.value, "<i8"), device="cuda")
+            gk, gs, gc = allgather_ragged(tk), allgather_ragged(ts), allgather_ragged(tc)
+            torch.cuda.synchronize()
+            for r in range(world):
+                if r == rank:
+                    continue
+                ctx.check(lib.ssb_group_merge(g, gk[r].numel(), cols([(gk[r].data_ptr(), None, capi.INT64)]),
+                                              cols([(gs[r].data_ptr(), None, capi.DOUBLE), (gc[r].data_ptr(), None, capi.UINT64)])))
+            ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+            torch.cuda.synchronize()
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt)
+        groups = n.value
+        lib.ssb_group_destroy(g)
+    ctx.free(k)
+    ctx.free(v)
+    best = min(times[1:]) if len(times) > 1 else times[0]
+    return {"metric": "rows/sec, GroupAggregate(k; SUM(v DOUBLE), COUNT(*)), 1M INT64 keys (BASELINE config 3 shape)",
+            "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(groups),
+            "seconds": best, "exchange": "all-gather of dense partial tables + ssb_group_merge" if world > 1 else "none",
+            "algorithmic_gbs_per_gpu": rows * 16 / best / 1e9}
+
+
 def host_column(capi, name, rows, first_row=0):
     kind, lo, span = GEN[name]
     out = np.empty(rows, dtype=np.int64)
@@ -215,7 +289,14 @@ def run_b200(args):
             "clocks": clocks,
             "kept_rows": kept_total,
         }
-    # ---- end to end through the supersonic.h mirror with pinned host buffers (rank 0 rows only)
+    # ---- sharded aggregate (config 3 shape): frees the filter columns first
+    for name in COLS:
+        ctx.free(d_cols[name])
+    ctx.free(d_out)
+    aux_group = group_by_aux(capi, ctx, rank, world, min(rows, args.group_rows), dist, torch)
+    if rank == 0:
+        result["aux"] = {"group_by": aux_group}
+    # ---- end to end through the supersonic.h mirror with pinned host buffers
     e2e_rows = min(args.e2e_rows, rows)
     host = {}
     for name in "abcd":
@@ -324,6 +405,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=1 << 26)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-rows", type=int, default=20_000_000)
+    ap.add_argument("--group-rows", type=int, default=1_000_000_000, help="rows per GPU of the aux group-by")
     ap.add_argument("--per-kernel-timing", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

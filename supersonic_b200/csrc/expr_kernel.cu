@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   // the evaluation anyway.
   const int kdefer_ = p.defer;
   const int n_obuf = kdefer_ + 1;
-  constexpr int kPrefetch = 6;    // status words per thread: covers gridDim.x <= 6 * NT
+  constexpr int kPrefetch = (768 + NT - 1) / NT;   // status words per thread: covers gridDim.x <= 768
   unsigned long long wave_base = 0;   // kept rows of all earlier waves (every thread keeps a copy)
   for (long long it = 0; it < n_my + kdefer_; ++it) {
     unsigned long long pre[kPrefetch];
@@ -673,7 +673,9 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
   }
   // Two resident CTAs per SM is the design point; wide plans fall back to fewer stages, then
   // to the smallest tile.
-  int ctas = 3;   // design point: three resident CTAs per SM (measured best, profiles/r1_summary.md)
+  // Resident CTAs per SM (measured, profiles/r1_summary.md): Filter is insensitive between 3 and
+  // 4 and prefers deeper staging; predicate-free programs gain 24 % from the fourth CTA.
+  int ctas = predicate >= 0 ? 3 : 4;
   if (const char* env = getenv("SSB200_EXPR_CTAS")) { const int c = atoi(env); if (c >= 1 && c <= 8) ctas = c; }
   const uint32_t budget = static_cast<uint32_t>((ctx->smem_per_sm - ctas * ctx->smem_reserved) / ctas);
   ssb_program* sp = nullptr;

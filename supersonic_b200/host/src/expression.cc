@@ -442,6 +442,114 @@ class ProjectionExpression : public Expression {
   std::unique_ptr<const SingleSourceProjector> projector_;
 };
 
+FailureOrVoid BindList(const ExpressionList& list, const TupleSchema& input, BufferAllocator* a, rowcount_t m,
+                       const char* what, vector<NodePtr>* out) {
+  for (int i = 0; i < list.size(); ++i) {
+    FailureOr<NodePtr> n = BindOne(list.get(i), input, a, m, what);
+    PROPAGATE_ON_FAILURE(n);
+    out->push_back(n.get());
+  }
+  return Success();
+}
+
+std::shared_ptr<ExprNode> Renamed(const NodePtr& n, const string& name, bool nullable) {
+  std::shared_ptr<ExprNode> copy(new ExprNode(*n));
+  copy->name = name;
+  copy->nullable = nullable;
+  return copy;
+}
+
+// CASE arg0 WHEN arg2 THEN arg3 WHEN arg4 THEN arg5 [...] ELSE arg1
+// (elementary_expressions.h:91-93, elementary_bound_expressions.cc:541-1050). Lowered to a
+// chain of IFs over equality tests: a NULL switch or WHEN value never matches.
+class CaseExpression : public Expression {
+ public:
+  explicit CaseExpression(const ExpressionList* args) : args_(args) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator* a, rowcount_t m) const {
+    if (args_->size() < 4 || args_->size() % 2 != 0) {
+      char buf[160];
+      snprintf(buf, sizeof(buf), "Bind failed: CASE needs %s (%d provided).",
+               args_->size() < 4 ? "at least 4 arguments" : "an even number of arguments", args_->size());
+      THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, buf));
+    }
+    vector<NodePtr> n;
+    PROPAGATE_ON_FAILURE(BindList(*args_, input, a, m, "CASE", &n));
+    DataType when_type = n[0]->type, then_type = n[1]->type;
+    for (size_t i = 2; i < n.size(); i += 2) {
+      if (!CommonType(when_type, n[i]->type, &when_type) || !CommonType(then_type, n[i + 1]->type, &then_type)) {
+        THROW(TypeMismatch("Cannot reconcile types in CASE"));
+      }
+    }
+    vector<NodePtr> c(n.size());
+    c[0] = MakeCast(n[0], when_type);
+    c[1] = MakeCast(n[1], then_type);
+    for (size_t i = 2; i < n.size(); i += 2) { c[i] = MakeCast(n[i], when_type); c[i + 1] = MakeCast(n[i + 1], then_type); }
+    NodePtr result = c[1];
+    for (size_t i = n.size() - 2; i >= 2; i -= 2) {
+      FailureOr<NodePtr> eq = BindComparison(K_EQUAL, c[0], c[i]);
+      PROPAGATE_ON_FAILURE(eq);
+      vector<NodePtr> args;
+      args.push_back(eq.get());
+      args.push_back(c[i + 1]);
+      args.push_back(result);
+      result = MakeNode(SSB_OP_IF, then_type, c[i + 1]->nullable || result->nullable, "CASE", args);
+    }
+    string name = "CASE(";
+    for (size_t i = 0; i < c.size(); ++i) { if (i) name += ", "; name += c[i]->name; }
+    name += ")";
+    return Single(input, Renamed(result, name, result->nullable));
+  }
+  virtual string ToString(bool v) const { return "CASE(" + args_->ToString(v) + ")"; }
+ private:
+  std::unique_ptr<const ExpressionList> args_;
+};
+
+// needle IN (haystack...) with SQL semantics (comparison_expressions.h:76-88): TRUE when equal
+// to an element, NULL when no match and the needle or an element is NULL, else FALSE -- exactly
+// a three-valued OR over equality tests, which is how it is lowered.
+class InExpression : public Expression {
+ public:
+  InExpression(const Expression* needle, const ExpressionList* haystack) : needle_(needle), haystack_(haystack) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator* a, rowcount_t m) const {
+    FailureOr<NodePtr> nb = BindOne(needle_.get(), input, a, m, "IN");
+    PROPAGATE_ON_FAILURE(nb);
+    vector<NodePtr> h;
+    PROPAGATE_ON_FAILURE(BindList(*haystack_, input, a, m, "IN", &h));
+    if (h.empty()) THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "IN needs a non-empty list"));
+    DataType t = nb.get()->type;
+    for (size_t i = 0; i < h.size(); ++i) {
+      if (!CommonType(t, h[i]->type, &t)) {
+        THROW(TypeMismatch("Cannot reconcile types: " + TypeName(t) + " and " + TypeName(h[i]->type) + "."));
+      }
+    }
+    const NodePtr needle = MakeCast(nb.get(), t);
+    NodePtr result;
+    string list;
+    bool nullable = needle->nullable;
+    for (size_t i = 0; i < h.size(); ++i) {
+      const NodePtr e = MakeCast(h[i], t);
+      if (i) list += ", ";
+      list += e->name;
+      nullable = nullable || e->nullable;
+      FailureOr<NodePtr> eq = BindComparison(K_EQUAL, needle, e);
+      PROPAGATE_ON_FAILURE(eq);
+      if (!result) {
+        result = eq.get();
+      } else {
+        vector<NodePtr> args;
+        args.push_back(result);
+        args.push_back(eq.get());
+        result = MakeNode(SSB_OP_OR, BOOL, result->nullable || eq.get()->nullable, "IN", args);
+      }
+    }
+    return Single(input, Renamed(result, needle->name + " IN (" + list + ")", nullable));
+  }
+  virtual string ToString(bool v) const { return needle_->ToString(v) + " IN (" + haystack_->ToString(v) + ")"; }
+ private:
+  std::unique_ptr<const Expression> needle_;
+  std::unique_ptr<const ExpressionList> haystack_;
+};
+
 class NotImplementedExpression : public Expression {
  public:
   explicit NotImplementedExpression(const char* what) : what_(what) {}
@@ -662,14 +770,9 @@ const Expression* If(const Expression* const c, const Expression* const t, const
 const Expression* NullingIf(const Expression* const c, const Expression* const t, const Expression* const o) {
   return new FnExpression(K_NULLING_IF, c, t, o);
 }
-const Expression* Case(const ExpressionList* const arguments) {
-  delete arguments;
-  return new NotImplementedExpression("CASE");
-}
+const Expression* Case(const ExpressionList* const arguments) { return new CaseExpression(arguments); }
 const Expression* In(const Expression* const needle, const ExpressionList* haystack) {
-  delete needle;
-  delete haystack;
-  return new NotImplementedExpression("IN");
+  return new InExpression(needle, haystack);
 }
 
 }  // namespace supersonic

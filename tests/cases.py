@@ -78,6 +78,20 @@ GOLDEN = [
     ("ifnull", "(compute (if_null (col a) (col b)) (scan 0))",
      [[ncol("a", sp.INT32, [1, N, N]), ncol("b", sp.INT32, [5, 6, N])]],
      {"IFNULL(a, b)": [1, 6, N]}, True),
+    # expression/core/case_expression_test.cc and comparison IN (comparison_expressions.h:76-88)
+    ("case_switch", "(compute (case (col s) (col a) (i32 1) (col b) (i32 2) (i64 7)) (scan 0))",
+     [[ncol("s", sp.INT32, [1, 2, 3, N, 5]), col("a", sp.INT64, [10, 20, 30, 40, 50]), ncol("b", sp.INT64, [100, N, 300, 400, 500])]],
+     {"CASE(s, a, CONST_INT32, b, CONST_INT32, CONST_INT64)": [100, 7, 30, 40, 50]}, True),
+    ("case_null_else", "(compute (case (col s) (null INT64) (col w) (col a)) (scan 0))",
+     [[ncol("s", sp.INT32, [1, 2, 3, N, 5]), col("a", sp.INT64, [10, 20, 30, 40, 50]), ncol("w", sp.INT32, [1, N, 3, 4, 9])]],
+     {"CASE(s, NULL, w, a)": [10, N, 30, N, N]}, True),
+    ("in_consts", "(compute (in (col s) (i32 1) (i32 5)) (scan 0))",
+     [[ncol("s", sp.INT32, [1, 2, 3, N, 5])]], {"s IN (CONST_INT32, CONST_INT32)": [True, False, False, N, True]}, True),
+    ("in_null_element", "(compute (in (col s) (i32 1) (null INT32)) (scan 0))",
+     [[ncol("s", sp.INT32, [1, 2, 3, N, 5])]], {"s IN (CONST_INT32, NULL)": [True, N, N, N, N]}, True),
+    ("in_columns", "(compute (in (col s) (col w) (i32 2)) (scan 0))",
+     [[ncol("s", sp.INT32, [1, 2, 3, N, 5]), ncol("w", sp.INT32, [1, N, 3, 4, 9])]],
+     {"s IN (w, CONST_INT32)": [True, True, True, N, False]}, True),
     # cursor/core/filter_test.cc:151-329
     ("filter_some", "(filter (col p) (named v) (scan 0))",
      [[col("p", sp.BOOL, [True, False, True, False, True]), col("v", sp.INT32, [1, 2, 3, 4, 5])]],

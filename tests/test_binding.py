@@ -71,6 +71,21 @@ def test_constants_aliases_compounds(ref, b200):
     ])
 
 
+def test_case_and_in_binding(ref, b200):
+    exprs = []
+    for sw, w in [("i32", "i32"), ("ni32", "i64"), ("i64", "u32"), ("f64", "i32"), ("b", "b"), ("i32", "b"), ("d", "d")]:
+        for e, t in [("i64", "ni64"), ("f64", "i32"), ("i32", "i32"), ("b", "nb"), ("i32", "b")]:
+            exprs.append("(case (col %s) (col %s) (col %s) (col %s))" % (sw, e, w, t))
+            exprs.append("(case (col %s) (col %s) (col %s) (col %s) (col n%s) (col %s))" % (sw, e, w, t, w, e))
+    exprs += ["(case (col i32))", "(case (col i32) (col i64) (col i32))", "(case (col i32) (null INT64) (col ni32) (col i64))",
+              "(case (col i32) (col i64) (i32 1) (col ni64) (i32 2) (i64 7))"]
+    for n, h in itertools.product(["i32", "ni32", "i64", "u64", "f32", "f64", "b", "d"], ["i32", "ni64", "u32", "f64", "nb", "dt"]):
+        exprs.append("(in (col %s) (col %s))" % (n, h))
+        exprs.append("(in (col %s) (col %s) (col %s))" % (n, h, n))
+    exprs += ["(in (col i32) (i32 1) (null INT32))", "(in (col f64) (i32 1) (f64 2.5))", "(in (col i64) (i32 10) (i64 50) (col ni64))"]
+    _check(ref, b200, exprs)
+
+
 def test_operation_schemas(ref, b200):
     """Result schemas of the operators themselves (filter.cc:79-87, aggregator.cc:63-152,
     hash_join.h:37-38, sort.h)."""

@@ -88,6 +88,10 @@ def test_expression_matrix(ref, b200, n):
         exprs.append("(bitwise_not (col n%s))" % x)
         exprs.append("(shift_left (col %s) (i32 3))" % x)
         exprs.append("(shift_right (col n%s) (i32 2))" % x)
+    exprs += ["(case (col ni32) (col f64) (i32 1) (col ni64) (i32 3) (col i64))",
+              "(case (col i64) (null INT64) (col ni32) (col i64) (col u32) (col ni64))",
+              "(in (col ni32) (col i32) (i32 2) (col ni64))", "(in (col f64) (col ni32) (f64 1.5))",
+              "(in (col i32) (i32 1) (null INT32))"]
     exprs += ["(not (col nb))", "(cast DATETIME (col nd))",
               "(plus (multiply (col i64) (col i32)) (minus (col f64) (col nu32)))",
               "(if (less (col i32) (i32 0)) (negate (col i32)) (col i32))",

@@ -401,12 +401,16 @@ class Compiler {
     int stages = kMaxStages;
     for (;; --stages) {
       const uint32_t nullw_bytes = (stages * p.stage_nullw + tmp_nullw) * (tile_ / 32) * 4;
-      const uint32_t data_off = (p.off_nullw + nullw_bytes + 1023) & ~1023u;
+      // per-stage table of pre-resolved instructions (16 bytes each, + terminator)
+      const uint32_t itab_off = (p.off_nullw + nullw_bytes + 15) & ~15u;
+      const uint32_t itab_bytes = static_cast<uint32_t>(stages) * (p.n_insn + 1) * 16;
+      const uint32_t data_off = (itab_off + itab_bytes + 1023) & ~1023u;
       const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + (defer + 1) * p.out_bytes;
       if ((total <= smem_budget && stages >= 2) || stages == 1 || (stages == 2 && total <= smem_max)) {
         if (total > smem_max) return Fail(SSB_ERROR_NOT_IMPLEMENTED, "expression needs more shared memory than one SM has");
         p.stages = stages;
         p.tile = tile_;
+        p.off_itab = itab_off;
         p.off_data = data_off;
         p.off_tmp = data_off + stages * p.stage_bytes;
         p.off_out = p.off_tmp + tmp_bytes;
@@ -451,11 +455,12 @@ class Compiler {
           if (in.t == T_I64) base = C_BIN_I64; else if (in.t == T_F64) base = C_BIN_F64; else if (in.t == T_I32) base = C_BIN_I32;
           if (base < 0) break;
           int op = -1;
+          const bool rev = (in.flags & F_REV) != 0;
           switch (in.mop) {
             case M_ADD: op = B_ADD; break;
-            case M_SUB: op = B_SUB; break;
+            case M_SUB: op = rev ? B_SUBR : B_SUB; break;
             case M_MUL: op = B_MUL; break;
-            case M_LT: op = B_LT; break;
+            case M_LT: op = rev ? B_GT : B_LT; break;
             case M_EQ: op = B_EQ; break;
             default: break;
           }
@@ -472,9 +477,8 @@ class Compiler {
       if (i + 1 < p.n_insn && (cur.code == C_LOAD8 || cur.code == C_LOAD4)) {
         Insn& next = p.insn[i + 1];
         const bool bin = next.code >= C_BIN_BASE && next.code < C_BIN_END && ((next.code - C_BIN_BASE) % 4) < 2;
-        // the accumulator is the LEFT operand unless F_REV; keep the rule simple: fuse only
-        // when the op reads acc on the left
-        if (bin && !(next.flags & F_REV) && phys_width(next.t) == cur.rw) {
+        // operand order (F_REV) is part of the fast code, so the fused form needs no care
+        if (bin && phys_width(next.t) == cur.rw) {
           next.off_b = cur.off_a;
           next.code = static_cast<uint16_t>(next.code + 2);
           continue;   // drop the LOAD

@@ -91,6 +91,21 @@ __device__ __forceinline__ void bar_consumers() {
 
 // NT consumer threads evaluate the program; one extra producer warp issues the TMA fills, so
 // that no consumer warp carries the descriptor loop on its critical path.
+//
+// Instruction budget. The kernel is bound by instruction issue, not by bytes (ncu: 12 resident
+// warps, "wait" stalls), so everything that runs once per tile is kept off the constant bank
+// and off 64-bit arithmetic: the program is expanded once per CTA into a shared-memory table of
+// pre-resolved entries (one LDS.128 per instruction, the next one prefetched while the current
+// one runs), tile / stage / buffer indices are running 32-bit counters, and the wave scan uses
+// loop-invariant lane masks and REDUX.
+struct __align__(16) TabEntry {
+  uint32_t code_flags;   // Code | flags << 16
+  uint32_t x;            // address of slot a | low half of the immediate | output offset
+  uint32_t y;            // address of slot b (left operand of fused forms)
+  uint32_t z;            // high half of the immediate | index a
+};
+static constexpr uint32_t kCodeEnd = 0xffffu;
+
 template <int NT, int R>
 __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ ExprParams p) {
   constexpr int TILE = NT * R;
@@ -102,22 +117,47 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   const bool producer = warp == NW;
   const int row_first = warp * WROWS + lane;   // thread's row k is row_first + 32 * k
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(smem + p.off_scan);             // [NW] kept rows per warp
-  unsigned long long* red = reinterpret_cast<unsigned long long*>(warp_cnt + 32);  // [2 * 16] reduce scratch
-  unsigned long long* s_meta = red + 32;   // [0..3] kept rows of the staged tiles, [4..5] base (double buffered), [6] wave base
+  uint32_t* warp_cnt = reinterpret_cast<uint32_t*>(smem + p.off_scan);   // [2][16] kept rows per warp
+  uint2* red = reinterpret_cast<uint2*>(warp_cnt + 32);                  // [2][16] {before, sum} per warp
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(red + 32);              // [0..3] kept rows of the staged tiles
   uint32_t* nullw_base = reinterpret_cast<uint32_t*>(smem + p.off_nullw);
+  TabEntry* itab = reinterpret_cast<TabEntry*>(smem + p.off_itab);       // [stages][n_insn + 1]
 
-  const long long G = gridDim.x;
-  const long long bid = blockIdx.x;
-  const long long n_my = (p.num_tiles - bid + G - 1) / G;
+  const int G = static_cast<int>(gridDim.x);
+  const int bid = static_cast<int>(blockIdx.x);
+  const int num_tiles = static_cast<int>(p.num_tiles);
+  const int n_my = (num_tiles - bid + G - 1) / G;
   const int S = p.stages;
+  const int n_tab = p.n_insn + 1;
 
-  if (tid == 0) {
-    if (p.use_tma) {
-      for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
-      fence_barrier_init();
+  if (tid == 0 && p.use_tma) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  // Expand the program: one entry per (stage, instruction) with absolute shared-memory offsets.
+  for (int e = tid; e < S * n_tab; e += NT + 32) {
+    const int s = e / n_tab, pc = e - s * n_tab;
+    TabEntry t;
+    if (pc == p.n_insn) {
+      t.code_flags = kCodeEnd; t.x = t.y = t.z = 0;
+    } else {
+      const Insn& in = p.insn[pc];
+      const uint32_t so = static_cast<uint32_t>(s) * p.stage_bytes;
+      t.code_flags = static_cast<uint32_t>(in.code) | (static_cast<uint32_t>(in.flags) << 16);
+      t.x = (in.off_a & 0x7fffffffu) + ((in.off_a >> 31) ? so : 0u);
+      t.y = (in.off_b & 0x7fffffffu) + ((in.off_b >> 31) ? so : 0u);
+      t.z = static_cast<uint32_t>(static_cast<int32_t>(in.a));
+      const uint32_t c = in.code;
+      const bool bin_imm = c >= C_BIN_BASE && c < C_BIN_END && ((c - C_BIN_BASE) & 1u);
+      if (c == C_LOADK || bin_imm) {
+        const u64 v = p.imm[in.a];
+        t.x = static_cast<uint32_t>(v);
+        t.z = static_cast<uint32_t>(v >> 32);
+      } else if (c == C_OUT8 || c == C_OUT4) {
+        t.x = p.out_off[in.a];
+      }
     }
-    s_meta[6] = 0;
+    itab[e] = t;
   }
   __syncthreads();
 
@@ -134,8 +174,8 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   };
 
   // Issues the TMA fill of `stage` with tile `tile` (full tiles only).
-  auto issue = [&](long long tile, int stage) {
-    const long long row0 = tile * TILE;
+  auto issue = [&](int tile, int stage) {
+    const long long row0 = static_cast<long long>(tile) * TILE;
     if (!p.use_tma || p.rows - row0 < TILE) return;
     uint32_t bytes = p.stage_tx_bytes;
     for (int i = 0; i < p.n_in; ++i) {
@@ -153,81 +193,89 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     }
   };
 
-  if (producer && lane == 0) {
-    for (int s = 0; s < S && s < n_my; ++s) issue(bid + s * G, s);
+  const int kdefer_ = p.defer;
+  const int n_obuf = kdefer_ + 1;
+
+  if (producer) {
+    // ---- producer warp: keeps `S` tiles in flight; refills a stage as soon as the consumers
+    // release it (the __syncthreads that ends every iteration).
+    if (lane == 0) {
+      for (int s = 0; s < S && s < n_my; ++s) issue(bid + s * G, s);
+    }
+    int stage = 0;
+    for (int it = 0; it < n_my + kdefer_; ++it) {
+      __syncthreads();
+      if (lane == 0 && it + S < n_my) issue(bid + (it + S) * G, stage);
+      if (++stage == S) stage = 0;
+    }
+    return;
   }
 
   const uint32_t all = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t fail = 0;
 
-  // kdefer_ extra iterations drain the deferred tiles.
   // Wave-synchronous prefix, shared by all consumer threads: at the top of an iteration every
   // thread fetches a few of the kept-row counts the wave of kdefer_ tiles ago published (together
   // one coalesced read of gridDim.x words); the L2 round trip overlaps with the evaluation of the
   // current tile; the partial sums are combined across the warps through the barrier that ends
-  // the evaluation anyway.
-  const int kdefer_ = p.defer;
-  const int n_obuf = kdefer_ + 1;
+  // the evaluation anyway. Which of a thread's words exist (full wave / last wave) and which
+  // precede this CTA's tile never changes: three lane masks computed once.
   constexpr int kPrefetch = (768 + NT - 1) / NT;   // status words per thread: covers gridDim.x <= 768
-  unsigned long long wave_base = 0;   // kept rows of all earlier waves (every thread keeps a copy)
-  for (long long it = 0; it < n_my + kdefer_; ++it) {
-    unsigned long long pre[kPrefetch];
-    const bool scan_wave = p.has_pred && it >= kdefer_ && !producer;
-    if (scan_wave) {
-      const long long w0 = (it - kdefer_) * G;
+  const int n_waves = (num_tiles + G - 1) / G;
+  const int last_count = num_tiles - (n_waves - 1) * G;   // tiles in the last wave
+  uint32_t full_mask = 0, last_mask = 0, before_mask = 0;
 #pragma unroll
-      for (int q = 0; q < kPrefetch; ++q) {
-        const long long j = w0 + tid + q * NT;
-        pre[q] = (j < w0 + G && j < p.num_tiles) ? ld_relaxed(&p.tile_status[j]) : kValid;
-      }
+  for (int q = 0; q < kPrefetch; ++q) {
+    const int j = tid + q * NT;
+    full_mask |= (j < G ? 1u : 0u) << q;
+    last_mask |= (j < last_count ? 1u : 0u) << q;
+    before_mask |= (j < bid ? 1u : 0u) << q;
+  }
+  const unsigned long long* wave_ptr = p.tile_status + tid;   // status words of the wave scanned next
+  long long wave_base = 0;   // kept rows of all earlier waves (every thread keeps a copy)
+
+  int stage = 0;             // it % S
+  uint32_t parity = 0;       // (it / S) & 1
+  int ob = 0;                // it % n_obuf: staging buffer written by this iteration
+  for (int it = 0; it < n_my + kdefer_; ++it) {
+    unsigned long long pre[kPrefetch];
+    const bool scan_wave = p.has_pred && it >= kdefer_;
+    const unsigned long long* wp = wave_ptr;
+    if (scan_wave) {
+      const uint32_t m = (it - kdefer_ == n_waves - 1) ? last_mask : full_mask;
+#pragma unroll
+      for (int q = 0; q < kPrefetch; ++q) pre[q] = ((m >> q) & 1u) ? ld_relaxed(wp + q * NT) : kValid;
+      wave_ptr += G;
     }
     auto finish_wave = [&]() {
-      const long long w0 = (it - kdefer_) * G;
-      const long long my_tile = bid + (it - kdefer_) * G;
-      unsigned long long before = 0, sum = 0;
+      unsigned long long andv = kValid;
+#pragma unroll
+      for (int q = 0; q < kPrefetch; ++q) andv &= pre[q];
+      if (!(andv & kValid) && !p.debug_nowait) {   // a CTA of the wave is behind: wait for it
+#pragma unroll
+        for (int q = 0; q < kPrefetch; ++q) {
+          while (!(pre[q] & kValid)) pre[q] = ld_relaxed(wp + q * NT);
+        }
+      }
+      uint32_t before = 0, sum = 0;
 #pragma unroll
       for (int q = 0; q < kPrefetch; ++q) {
-        const long long j = w0 + tid + q * NT;
-        unsigned long long v = pre[q];
-        while (!(v & kValid) && !p.debug_nowait) v = ld_relaxed(&p.tile_status[j]);   // a CTA behind
-        v &= ~kValid;
-        sum += v;
-        if (j < my_tile) before += v;
+        const uint32_t c = static_cast<uint32_t>(pre[q]);
+        sum += c;
+        before += ((before_mask >> q) & 1u) ? c : 0u;
       }
-      for (long long j = w0 + tid + kPrefetch * NT; j < w0 + G && j < p.num_tiles; j += NT) {
-        unsigned long long v = ld_relaxed(&p.tile_status[j]);
-        while (!(v & kValid) && !p.debug_nowait) v = ld_relaxed(&p.tile_status[j]);
-        v &= ~kValid;
-        sum += v;
-        if (j < my_tile) before += v;
-      }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        before += __shfl_xor_sync(0xffffffffu, before, d);
-        sum += __shfl_xor_sync(0xffffffffu, sum, d);
-      }
-      if (lane == 0) {
-        red[(it & 1) * 16 + warp * 2] = before;
-        red[(it & 1) * 16 + warp * 2 + 1] = sum;
-      }
+      before = __reduce_add_sync(0xffffffffu, before);
+      sum = __reduce_add_sync(0xffffffffu, sum);
+      if (lane == 0) red[(it & 1) * 16 + warp] = make_uint2(before, sum);
     };
-    if (producer) {
-      // ---- producer warp: wave prefix (then refill the stage
-      // the consumers just released
-      __syncthreads();
-      if (lane == 0 && it < n_my && it + S < n_my) issue(bid + (it + S) * G, static_cast<int>(it % S));
-      continue;
-    }
     // ======================================================== evaluate tile `it`
     if (it < n_my) {
-      const long long tile = bid + it * G;
-      const int stage = static_cast<int>(it % S);
-      const uint32_t parity = static_cast<uint32_t>((it / S) & 1);
-      const long long row0 = tile * TILE;
+      const int tile = bid + it * G;
+      const long long row0 = static_cast<long long>(tile) * TILE;
       const int n = static_cast<int>(p.rows - row0 < TILE ? p.rows - row0 : TILE);
       const bool via_tma = p.use_tma && n == TILE;
-      unsigned char* obuf = smem + p.off_out + static_cast<int>(it % n_obuf) * p.out_bytes;
+      unsigned char* obuf = smem + p.off_out + ob * p.out_bytes;
 
       if (via_tma) {
         mbar_wait(&bars[stage], parity);
@@ -249,27 +297,30 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       }
       // Null words of inputs declared nullable: TMA delivered them when the column has a
       // bitmap; otherwise (no bitmap in this run, or the plain-load path) fill them here.
-      bool filled = false;
-      for (int i = 0; i < p.n_in; ++i) {
-        if (p.in_nullw[i] < 0) continue;
-        const bool have = p.in_nulls[i] != nullptr;
-        if (via_tma && have) continue;
-        uint32_t* wdst = slot_nullw(i, stage);
-        for (int wi = tid; wi < TILE / 32; wi += NT) {
-          uint32_t wv = 0;
-          if (have && wi * 32 < n) wv = p.in_nulls[i][row0 / 32 + wi];
-          wdst[wi] = wv;
+      if (via_tma ? p.fill_nullw_tma : p.fill_nullw_plain) {
+        for (int i = 0; i < p.n_in; ++i) {
+          if (p.in_nullw[i] < 0) continue;
+          const bool have = p.in_nulls[i] != nullptr;
+          if (via_tma && have) continue;
+          uint32_t* wdst = slot_nullw(i, stage);
+          for (int wi = tid; wi < TILE / 32; wi += NT) {
+            uint32_t wv = 0;
+            if (have && wi * 32 < n) wv = p.in_nulls[i][row0 / 32 + wi];
+            wdst[wi] = wv;
+          }
         }
-        filled = true;
+        bar_consumers<NT>();
       }
-      if (filled) bar_consumers<NT>();
       // Without a predicate no barrier separates this tile's staging writes from the copy-out
       // of the tile evaluated two iterations ago (same buffer): add one.
       if (!p.has_pred) bar_consumers<NT>();
 
-      uint32_t live = 0;
+      uint32_t live = all;
+      if (n != TILE) {
+        live = 0;
 #pragma unroll
-      for (int k = 0; k < R; ++k) live |= (row_first + 32 * k < n ? 1u : 0u) << k;
+        for (int k = 0; k < R; ++k) live |= (row_first + 32 * k < n ? 1u : 0u) << k;
+      }
 
       // ---- the accumulator machine
       u64 acc[R];
@@ -277,8 +328,8 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       int pos[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) { acc[k] = 0; pos[k] = row_first + 32 * k; }
-      const uint32_t stage_off = static_cast<uint32_t>(stage) * p.stage_bytes;
 
+      // +0 acc (op) slot, +1 acc (op) imm, +2 slot (op) slot, +3 slot (op) imm; EXPR sees x, y
 #define SSB_BIN4(CODE0, T, EXPR)                                                         \
   case (CODE0): {                                                                        \
     const T* ps = reinterpret_cast<const T*>(pa);                                        \
@@ -289,7 +340,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     }                                                                                    \
   } break;                                                                               \
   case (CODE0) + 1: {                                                                    \
-    const T y = Codec<T>::dec(p.imm[in.a]);                                              \
+    const T y = Codec<T>::dec(immv);                                                     \
     _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
       const T x = Codec<T>::dec(acc[k]);                                                 \
       acc[k] = EXPR;                                                                     \
@@ -307,7 +358,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   } break;                                                                               \
   case (CODE0) + 3: {                                                                    \
     const T* pl = reinterpret_cast<const T*>(pb);                                        \
-    const T y = Codec<T>::dec(p.imm[in.a]);                                              \
+    const T y = Codec<T>::dec(immv);                                                     \
     _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
       const T x = pl[row_first + 32 * k];                                                \
       acc[k] = EXPR;                                                                     \
@@ -315,24 +366,29 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     accn = 0;                                                                            \
   } break;
 #define SSB_ENC(T, V) Codec<T>::enc(V)
-#define SSB_CMP(V) (((V) != neg) ? 1u : 0u)
+#define SSB_CMP(V) (((V) ? 1u : 0u) ^ negb)
 #define SSB_BIN_TYPE(BASE, T, ADD, SUB, SUBR, MUL)                                       \
   SSB_BIN4((BASE) + 4 * B_ADD, T, SSB_ENC(T, ADD))                                       \
-  SSB_BIN4((BASE) + 4 * B_SUB, T, SSB_ENC(T, rev ? (SUBR) : (SUB)))                      \
+  SSB_BIN4((BASE) + 4 * B_SUB, T, SSB_ENC(T, SUB))                                       \
+  SSB_BIN4((BASE) + 4 * B_SUBR, T, SSB_ENC(T, SUBR))                                     \
   SSB_BIN4((BASE) + 4 * B_MUL, T, SSB_ENC(T, MUL))                                       \
-  SSB_BIN4((BASE) + 4 * B_LT, T, SSB_CMP(rev ? y < x : x < y))                           \
+  SSB_BIN4((BASE) + 4 * B_LT, T, SSB_CMP(x < y))                                         \
+  SSB_BIN4((BASE) + 4 * B_GT, T, SSB_CMP(y < x))                                         \
   SSB_BIN4((BASE) + 4 * B_EQ, T, SSB_CMP(x == y))
 
-      for (int pc = 0; pc < p.n_insn; ++pc) {
-        const Insn& in = p.insn[pc];
-        const uint32_t code = in.code;
+      const TabEntry* tab = itab + stage * n_tab;
+      TabEntry next = tab[0];
+      for (int pc = 0;; ++pc) {
+        const TabEntry cur = next;
+        const uint32_t code = cur.code_flags & 0xffffu;
+        if (code == kCodeEnd) break;
+        next = tab[pc + 1];   // in flight while this instruction runs
         if (code != C_GENERIC) {
-          // pre-decoded fast path: operands cannot be NULL, address = one add
-          const uint32_t oa = in.off_a, ob = in.off_b;
-          const unsigned char* pa = smem + (oa & 0x7fffffffu) + ((oa >> 31) ? stage_off : 0u);
-          const unsigned char* pb = smem + (ob & 0x7fffffffu) + ((ob >> 31) ? stage_off : 0u);
-          const bool rev = (in.flags & F_REV) != 0;
-          const bool neg = (in.flags & F_NEGATE) != 0;
+          // pre-decoded fast path: operands cannot be NULL, addresses are resolved
+          const unsigned char* pa = smem + cur.x;
+          const unsigned char* pb = smem + cur.y;
+          const u64 immv = static_cast<u64>(cur.x) | (static_cast<u64>(cur.z) << 32);
+          const uint32_t negb = (cur.code_flags >> 16) & F_NEGATE ? 1u : 0u;
           switch (code) {
             case C_LOAD8: {
               const u64* ps = reinterpret_cast<const u64*>(pa);
@@ -347,9 +403,8 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
               accn = 0;
             } break;
             case C_LOADK: {
-              const u64 c = p.imm[in.a];
 #pragma unroll
-              for (int k = 0; k < R; ++k) acc[k] = c;
+              for (int k = 0; k < R; ++k) acc[k] = immv;
               accn = 0;
             } break;
             SSB_BIN_TYPE(C_BIN_I64, int64_t, Arith<int64_t>::add(x, y), Arith<int64_t>::sub(x, y),
@@ -400,17 +455,17 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
 #pragma unroll
               for (int k = 0; k < R; ++k) pos[k] += static_cast<int>(before);
               if (tid == 0) {
-                s_meta[it % n_obuf] = total;
+                s_meta[ob] = total;
                 st_relaxed(&p.tile_status[tile], kValid | total);   // this tile's share of its wave
               }
             } break;
             case C_OUT8: {
-              u64* dst = reinterpret_cast<u64*>(obuf + p.out_off[in.a]);
+              u64* dst = reinterpret_cast<u64*>(obuf + cur.x);
 #pragma unroll
               for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = acc[k];
             } break;
             case C_OUT4: {
-              uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + p.out_off[in.a]);
+              uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + cur.x);
 #pragma unroll
               for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = static_cast<uint32_t>(acc[k]);
             } break;
@@ -420,6 +475,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
         }
         // ---- generic path: NULL-carrying operands, narrow or mixed types, rare ops.
         // Works on 4 rows at a time so that its register footprint does not grow with R.
+        const Insn& in = p.insn[pc];
         auto fetch4 = [&](int c4, int idx, bool is_imm, bool null_const, bool nullable, u64 (&v)[4], uint32_t& nn) {
           if (is_imm) {
 #pragma unroll
@@ -518,45 +574,55 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
 #undef SSB_BIN_TYPE
 #undef SSB_ENC
 #undef SSB_CMP
-      if (scan_wave) finish_wave();
-      __syncthreads();   // all threads: the stage and the temporaries are free; the wave base is published
-    } else {
-      if (scan_wave) finish_wave();
-      __syncthreads();
     }
+    if (scan_wave) finish_wave();
+    __syncthreads();   // all threads: the stage and the temporaries are free; the wave sums are published
 
     // ======================================================== write out tile `it - kdefer_`
     if (it >= kdefer_) {
-      const long long wave = it - kdefer_;
-      const long long tile = bid + wave * G;
-      const unsigned char* obuf = smem + p.off_out + static_cast<int>(wave % n_obuf) * p.out_bytes;
-      long long total;
+      const int ob_out = (ob + 1 == n_obuf) ? 0 : ob + 1;   // (it - kdefer_) % n_obuf
+      const int tile = bid + (it - kdefer_) * G;
+      const unsigned char* obuf = smem + p.off_out + ob_out * p.out_bytes;
+      int total;
       long long base;
       if (p.has_pred) {
-        unsigned long long before = 0, sum = 0;
+        uint32_t before = 0, sum = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-          before += red[(it & 1) * 16 + w * 2];
-          sum += red[(it & 1) * 16 + w * 2 + 1];
+          const uint2 v = red[(it & 1) * 16 + w];
+          before += v.x;
+          sum += v.y;
         }
-        base = static_cast<long long>(wave_base + before);
+        base = wave_base + before;
         wave_base += sum;
-        total = static_cast<long long>(s_meta[wave % n_obuf]);
-        if (tile == p.num_tiles - 1 && tid == 0 && p.d_out_rows != nullptr) *p.d_out_rows = base + total;
+        total = static_cast<int>(s_meta[ob_out]);
+        if (tile == num_tiles - 1 && tid == 0 && p.d_out_rows != nullptr) *p.d_out_rows = base + total;
       } else {
-        base = tile * static_cast<long long>(TILE);
-        total = p.rows - base < TILE ? p.rows - base : TILE;
+        base = static_cast<long long>(tile) * TILE;
+        total = static_cast<int>(p.rows - base < TILE ? p.rows - base : TILE);
       }
       for (int j = 0; j < p.n_out; ++j) {
         const unsigned char* src = obuf + p.out_off[j];
-        unsigned char* dst = static_cast<unsigned char*>(p.out_data[j]);
         const int w = p.out_width[j];
         if (w == 8) {
-          for (int i = tid; i < total; i += NT) st_cs_u64(dst + (base + i) * 8, reinterpret_cast<const u64*>(src)[i]);
+          u64* d = static_cast<u64*>(p.out_data[j]) + base;
+          const u64* s = reinterpret_cast<const u64*>(src);
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            const int i = tid + k * NT;
+            if (i < total) st_cs_u64(d + i, s[i]);
+          }
         } else if (w == 4) {
-          for (int i = tid; i < total; i += NT) st_cs_u32(dst + (base + i) * 4, reinterpret_cast<const uint32_t*>(src)[i]);
+          uint32_t* d = static_cast<uint32_t*>(p.out_data[j]) + base;
+          const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            const int i = tid + k * NT;
+            if (i < total) st_cs_u32(d + i, s[i]);
+          }
         } else {
-          for (int i = tid; i < total; i += NT) dst[base + i] = src[i];
+          unsigned char* d = static_cast<unsigned char*>(p.out_data[j]) + base;
+          for (int i = tid; i < total; i += NT) d[i] = src[i];
         }
         if (p.out_null_off[j] != 0xffffffffu && p.out_nulls[j] != nullptr) {
           // output bitmap words: interior words belong to this tile alone, the first and last may
@@ -577,10 +643,13 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       // No barrier needed here: the next write into this staging buffer happens two evaluations
       // later, behind at least one __syncthreads of the next iteration.
     }
+    if (++stage == S) { stage = 0; parity ^= 1u; }
+    if (++ob == n_obuf) ob = 0;
   }
   if (!p.has_pred && p.d_out_rows != nullptr && blockIdx.x == 0 && tid == 0) *p.d_out_rows = p.rows;
   if (fail && p.d_fail != nullptr) atomicOr(p.d_fail, 1);
 }
+
 
 // ------------------------------------------------------------------ host side
 // Kernel variants: threads per CTA x rows per thread. More rows per thread amortise the
@@ -634,8 +703,15 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
       SSB_CUDA(ctx, cudaMemsetAsync(p.out_nulls[j], 0, static_cast<size_t>(div_up(rows, 32) + 1) * 4, ctx->stream));
     }
   }
+  p.fill_nullw_tma = p.fill_nullw_plain = 0;
+  for (int i = 0; i < p.n_in; ++i) {
+    if (p.in_nullw[i] < 0) continue;
+    p.fill_nullw_plain = 1;
+    if (p.in_nulls[i] == nullptr) p.fill_nullw_tma = 1;
+  }
   p.rows = rows;
   p.num_tiles = div_up(rows, p.tile);
+  if (p.num_tiles > 0x7fff0000LL) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "more than 2^31 tiles in one launch");
   p.use_tma = aligned ? 1 : 0;
   p.d_out_rows = d_out_rows;
   p.d_fail = prog.has_signaling ? ctx->d_fail : nullptr;
@@ -647,6 +723,7 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
     SSB_CUDA(ctx, cudaMemsetAsync(st, 0, static_cast<size_t>(p.num_tiles) * 8, ctx->stream));
   }
   long long grid = static_cast<long long>(ctx->num_sms) * sp->max_ctas_per_sm;
+  if (p.has_pred && grid > 768) grid = 768;   // the wave scan reads at most 768 status words
   if (grid > p.num_tiles) grid = p.num_tiles;
   TimedRegion timed(ctx);
   var.kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);

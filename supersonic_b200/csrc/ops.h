@@ -81,12 +81,13 @@ enum Code {
   //   +0 acc (op) slot   +1 acc (op) imm   +2 slot (op) slot   +3 slot (op) imm
   // (the last two are a LOAD fused into the operation by the compiler's peephole)
   C_BIN_BASE,
-  C_BIN_I64 = C_BIN_BASE,              // ADD SUB MUL LT EQ
-  C_BIN_F64 = C_BIN_I64 + 20,
-  C_BIN_I32 = C_BIN_F64 + 20,
-  C_BIN_END = C_BIN_I32 + 20,
+  C_BIN_I64 = C_BIN_BASE,              // ADD SUB SUBR MUL LT GT EQ
+  C_BIN_F64 = C_BIN_I64 + 28,
+  C_BIN_I32 = C_BIN_F64 + 28,
+  C_BIN_END = C_BIN_I32 + 28,
 };
-enum { B_ADD = 0, B_SUB = 1, B_MUL = 2, B_LT = 3, B_EQ = 4 };
+// SUBR / GT are SUB / LT with the operands swapped (F_REV resolved at compile time).
+enum { B_ADD = 0, B_SUB = 1, B_SUBR = 2, B_MUL = 3, B_LT = 4, B_GT = 5, B_EQ = 6 };
 
 
 struct Insn {

@@ -47,7 +47,7 @@ struct ExprParams {
   uint8_t out_width[kMaxOut];
   uint8_t out_nullable[kMaxOut];
   // ---- shared memory plan (byte offsets from the 1024-byte aligned base)
-  uint32_t off_bar, off_scan, off_nullw, off_data, off_tmp, off_out;
+  uint32_t off_bar, off_scan, off_nullw, off_itab, off_data, off_tmp, off_out;
   uint32_t stage_bytes;                 // data bytes of one input stage
   uint32_t stage_nullw;                 // null-word rows per stage (nullable inputs)
   uint32_t stage_tx_bytes;              // bytes one full-tile TMA fill delivers (data only)
@@ -61,6 +61,7 @@ struct ExprParams {
   int32_t has_pred;
   int32_t use_tma;
   int32_t debug_nowait;
+  int32_t fill_nullw_tma, fill_nullw_plain;   // some null words are not delivered by TMA / any nullable input
   unsigned long long* tile_status;      // per-tile kept-row counts | valid bit (Filter)
   int64_t* d_out_rows;
   int32_t* d_fail;

@@ -487,6 +487,41 @@ class Compiler {
       p.insn[w++] = cur;
     }
     p.n_insn = w;
+    // Peephole 2: MUL then ADD of a clean slot -> one multiply-add; a fast compare directly
+    // followed by K_PRED -> the compare feeds the compaction itself (no 0/1 materialisation).
+    w = 0;
+    for (int i = 0; i < p.n_insn; ++i) {
+      Insn cur = p.insn[i];
+      if (i + 1 < p.n_insn && cur.code >= C_BIN_BASE && cur.code < C_BIN_END) {
+        const Insn& next = p.insn[i + 1];
+        const int rel = cur.code - C_BIN_BASE;
+        const int type_base = rel / 28, op = (rel % 28) / 4, form = rel % 4;
+        const bool next_add_slot = next.code >= C_BIN_BASE && next.code < C_BIN_END &&
+                                   (next.code - C_BIN_BASE) / 28 == type_base &&
+                                   ((next.code - C_BIN_BASE) % 28) == 4 * B_ADD + 0;
+        if (op == B_MUL && (form == 0 || form == 2) && next_add_slot) {
+          // x = slot a (multiplier), y = slot b of the ADD, z = left slot of the fused MUL
+          const uint32_t left = cur.off_b;
+          cur.off_b = next.off_a;
+          cur.code = static_cast<uint16_t>(C_MAD_I64 + 2 * type_base + (form == 2 ? 1 : 0));
+          cur.pad2 = 0;
+          mad_left_[w] = left;
+          p.insn[w++] = cur;
+          ++i;
+          continue;
+        }
+        if ((op == B_LT || op == B_GT || op == B_EQ) && next.code == C_PRED) {
+          cur.flags |= F_THEN_PRED;
+          p.insn[w++] = cur;
+          ++i;
+          continue;
+        }
+      }
+      mad_left_[w] = 0;
+      p.insn[w++] = cur;
+    }
+    p.n_insn = w;
+    for (int i = 0; i < p.n_insn; ++i) p.insn_c[i] = mad_left_[i];
     Insn end;
     memset(&end, 0, sizeof(end));
     end.kind = K_END;
@@ -503,6 +538,7 @@ class Compiler {
   }
 
  private:
+  uint32_t mad_left_[kMaxInsn + 1];
   struct Info {
     int phys;
     bool nullable;

@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       t.y = (in.off_b & 0x7fffffffu) + ((in.off_b >> 31) ? so : 0u);
       t.z = static_cast<uint32_t>(static_cast<int32_t>(in.a));
       const uint32_t c = in.code;
+      if (c >= C_MAD_I64 && c < C_MAD_END) {
+        const uint32_t oc = p.insn_c[pc];
+        t.z = (oc & 0x7fffffffu) + ((oc >> 31) ? so : 0u);
+      }
       const bool bin_imm = c >= C_BIN_BASE && c < C_BIN_END && ((c - C_BIN_BASE) & 1u);
       if (c == C_LOADK || bin_imm) {
         const u64 v = p.imm[in.a];
@@ -245,7 +249,10 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     if (scan_wave) {
       const uint32_t m = (it - kdefer_ == n_waves - 1) ? last_mask : full_mask;
 #pragma unroll
-      for (int q = 0; q < kPrefetch; ++q) pre[q] = ((m >> q) & 1u) ? ld_relaxed(wp + q * NT) : kValid;
+      for (int q = 0; q < kPrefetch; ++q) {
+        pre[q] = kValid;
+        if (q * NT < G && ((m >> q) & 1u)) pre[q] = ld_relaxed(wp + q * NT);   // first test is CTA-uniform
+      }
       wave_ptr += G;
     }
     auto finish_wave = [&]() {
@@ -365,16 +372,79 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     }                                                                                    \
     accn = 0;                                                                            \
   } break;
+      // comparisons collect one bit per row; materialised as 0/1, or fed to the compaction
+#define SSB_CMP4(CODE0, T, COND)                                                         \
+  case (CODE0): {                                                                        \
+    const T* ps = reinterpret_cast<const T*>(pa);                                        \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = Codec<T>::dec(acc[k]);                                                 \
+      const T y = ps[row_first + 32 * k];                                                \
+      bits |= ((COND) ? 1u : 0u) << k;                                                   \
+    }                                                                                    \
+    post = 1;                                                                            \
+  } break;                                                                               \
+  case (CODE0) + 1: {                                                                    \
+    const T y = Codec<T>::dec(immv);                                                     \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = Codec<T>::dec(acc[k]);                                                 \
+      bits |= ((COND) ? 1u : 0u) << k;                                                   \
+    }                                                                                    \
+    post = 1;                                                                            \
+  } break;                                                                               \
+  case (CODE0) + 2: {                                                                    \
+    const T* ps = reinterpret_cast<const T*>(pa);                                        \
+    const T* pl = reinterpret_cast<const T*>(pb);                                        \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = pl[row_first + 32 * k];                                                \
+      const T y = ps[row_first + 32 * k];                                                \
+      bits |= ((COND) ? 1u : 0u) << k;                                                   \
+    }                                                                                    \
+    accn = 0;                                                                            \
+    post = 1;                                                                            \
+  } break;                                                                               \
+  case (CODE0) + 3: {                                                                    \
+    const T* pl = reinterpret_cast<const T*>(pb);                                        \
+    const T y = Codec<T>::dec(immv);                                                     \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = pl[row_first + 32 * k];                                                \
+      bits |= ((COND) ? 1u : 0u) << k;                                                   \
+    }                                                                                    \
+    accn = 0;                                                                            \
+    post = 1;                                                                            \
+  } break;
+      // multiply-add: +0 acc * slot a + slot b, +1 slot c * slot a + slot b
+#define SSB_MAD2(CODE0, T, EXPR)                                                         \
+  case (CODE0): {                                                                        \
+    const T* ps = reinterpret_cast<const T*>(pa);                                        \
+    const T* pz = reinterpret_cast<const T*>(pb);                                        \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = Codec<T>::dec(acc[k]);                                                 \
+      const T y = ps[row_first + 32 * k];                                                \
+      const T z = pz[row_first + 32 * k];                                                \
+      acc[k] = Codec<T>::enc(EXPR);                                                      \
+    }                                                                                    \
+  } break;                                                                               \
+  case (CODE0) + 1: {                                                                    \
+    const T* ps = reinterpret_cast<const T*>(pa);                                        \
+    const T* pz = reinterpret_cast<const T*>(pb);                                        \
+    const T* pl = reinterpret_cast<const T*>(smem + cur.z);                              \
+    _Pragma("unroll") for (int k = 0; k < R; ++k) {                                      \
+      const T x = pl[row_first + 32 * k];                                                \
+      const T y = ps[row_first + 32 * k];                                                \
+      const T z = pz[row_first + 32 * k];                                                \
+      acc[k] = Codec<T>::enc(EXPR);                                                      \
+    }                                                                                    \
+    accn = 0;                                                                            \
+  } break;
 #define SSB_ENC(T, V) Codec<T>::enc(V)
-#define SSB_CMP(V) (((V) ? 1u : 0u) ^ negb)
 #define SSB_BIN_TYPE(BASE, T, ADD, SUB, SUBR, MUL)                                       \
   SSB_BIN4((BASE) + 4 * B_ADD, T, SSB_ENC(T, ADD))                                       \
   SSB_BIN4((BASE) + 4 * B_SUB, T, SSB_ENC(T, SUB))                                       \
   SSB_BIN4((BASE) + 4 * B_SUBR, T, SSB_ENC(T, SUBR))                                     \
   SSB_BIN4((BASE) + 4 * B_MUL, T, SSB_ENC(T, MUL))                                       \
-  SSB_BIN4((BASE) + 4 * B_LT, T, SSB_CMP(x < y))                                         \
-  SSB_BIN4((BASE) + 4 * B_GT, T, SSB_CMP(y < x))                                         \
-  SSB_BIN4((BASE) + 4 * B_EQ, T, SSB_CMP(x == y))
+  SSB_CMP4((BASE) + 4 * B_LT, T, x < y)                                                  \
+  SSB_CMP4((BASE) + 4 * B_GT, T, y < x)                                                  \
+  SSB_CMP4((BASE) + 4 * B_EQ, T, x == y)
 
       const TabEntry* tab = itab + stage * n_tab;
       TabEntry next = tab[0];
@@ -388,7 +458,8 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
           const unsigned char* pa = smem + cur.x;
           const unsigned char* pb = smem + cur.y;
           const u64 immv = static_cast<u64>(cur.x) | (static_cast<u64>(cur.z) << 32);
-          const uint32_t negb = (cur.code_flags >> 16) & F_NEGATE ? 1u : 0u;
+          uint32_t bits = 0;
+          int post = 0;   // 1: comparison mask in `bits`; 2: K_PRED on the accumulator
           switch (code) {
             case C_LOAD8: {
               const u64* ps = reinterpret_cast<const u64*>(pa);
@@ -412,6 +483,9 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
             SSB_BIN_TYPE(C_BIN_F64, double, x + y, x - y, y - x, x * y)
             SSB_BIN_TYPE(C_BIN_I32, int32_t, Arith<int32_t>::add(x, y), Arith<int32_t>::sub(x, y),
                          Arith<int32_t>::sub(y, x), Arith<int32_t>::mul(x, y))
+            SSB_MAD2(C_MAD_I64, int64_t, Arith<int64_t>::add(Arith<int64_t>::mul(x, y), z))
+            SSB_MAD2(C_MAD_F64, double, __dadd_rn(__dmul_rn(x, y), z))   // two roundings, as the separate ops
+            SSB_MAD2(C_MAD_I32, int32_t, Arith<int32_t>::add(Arith<int32_t>::mul(x, y), z))
             case C_AND3_S:
             case C_OR3_S: {
               // rhs is never NULL here; acc may be
@@ -429,10 +503,33 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
               accn = nul & all;
             } break;
             case C_PRED: {
-              uint32_t t = 0;
 #pragma unroll
-              for (int k = 0; k < R; ++k) t |= static_cast<uint32_t>(acc[k] & 1u) << k;
-              pass = t & ~accn & live;
+              for (int k = 0; k < R; ++k) bits |= static_cast<uint32_t>(acc[k] & 1u) << k;
+              post = 2;
+            } break;
+            case C_OUT8: {
+              u64* dst = reinterpret_cast<u64*>(obuf + cur.x);
+#pragma unroll
+              for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = acc[k];
+            } break;
+            case C_OUT4: {
+              uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + cur.x);
+#pragma unroll
+              for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = static_cast<uint32_t>(acc[k]);
+            } break;
+            default: break;
+          }
+          if (post) {
+            if (post == 1) {
+              if ((cur.code_flags >> 16) & F_NEGATE) bits ^= all;
+              if (!((cur.code_flags >> 16) & F_THEN_PRED)) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) acc[k] = (bits >> k) & 1u;
+                continue;
+              }
+            }
+            {
+              pass = bits & ~accn & live;
               // in-tile compaction: the warp's rows are contiguous, so positions inside the warp
               // come from R ballots; one small scan over the warps gives the warp bases
               uint32_t run = 0;
@@ -458,18 +555,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
                 s_meta[ob] = total;
                 st_relaxed(&p.tile_status[tile], kValid | total);   // this tile's share of its wave
               }
-            } break;
-            case C_OUT8: {
-              u64* dst = reinterpret_cast<u64*>(obuf + cur.x);
-#pragma unroll
-              for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = acc[k];
-            } break;
-            case C_OUT4: {
-              uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + cur.x);
-#pragma unroll
-              for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = static_cast<uint32_t>(acc[k]);
-            } break;
-            default: break;
+            }
           }
           continue;
         }
@@ -571,9 +657,10 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
         }
       }
 #undef SSB_BIN4
+#undef SSB_CMP4
+#undef SSB_MAD2
 #undef SSB_BIN_TYPE
 #undef SSB_ENC
-#undef SSB_CMP
     }
     if (scan_wave) finish_wave();
     __syncthreads();   // all threads: the stage and the temporaries are free; the wave sums are published
@@ -607,18 +694,36 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
         if (w == 8) {
           u64* d = static_cast<u64*>(p.out_data[j]) + base;
           const u64* s = reinterpret_cast<const u64*>(src);
+          if (total == TILE) {   // all loads first, then all stores
+            u64 v[R];
 #pragma unroll
-          for (int k = 0; k < R; ++k) {
-            const int i = tid + k * NT;
-            if (i < total) st_cs_u64(d + i, s[i]);
+            for (int k = 0; k < R; ++k) v[k] = s[tid + k * NT];
+#pragma unroll
+            for (int k = 0; k < R; ++k) st_cs_u64(d + tid + k * NT, v[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              if (k * NT >= total) break;   // CTA-uniform
+              const int i = tid + k * NT;
+              if (i < total) st_cs_u64(d + i, s[i]);
+            }
           }
         } else if (w == 4) {
           uint32_t* d = static_cast<uint32_t*>(p.out_data[j]) + base;
           const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+          if (total == TILE) {
+            uint32_t v[R];
 #pragma unroll
-          for (int k = 0; k < R; ++k) {
-            const int i = tid + k * NT;
-            if (i < total) st_cs_u32(d + i, s[i]);
+            for (int k = 0; k < R; ++k) v[k] = s[tid + k * NT];
+#pragma unroll
+            for (int k = 0; k < R; ++k) st_cs_u32(d + tid + k * NT, v[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              if (k * NT >= total) break;   // CTA-uniform
+              const int i = tid + k * NT;
+              if (i < total) st_cs_u32(d + i, s[i]);
+            }
           }
         } else {
           unsigned char* d = static_cast<unsigned char*>(p.out_data[j]) + base;

@@ -54,6 +54,7 @@ enum {
   F_RHS_IMM = 32,     // rhs is imm[a] (with F_RHS_NULLK: a NULL constant)
   F_RHS_NULLK = 64,
   F_RHS2_IMM = 128,   // M_SEL: rhs2 is imm[b]
+  F_THEN_PRED = 256,  // fast compare directly followed by K_PRED: the row mask feeds the compaction
 };
 
 // Instruction kinds.
@@ -85,6 +86,10 @@ enum Code {
   C_BIN_F64 = C_BIN_I64 + 28,
   C_BIN_I32 = C_BIN_F64 + 28,
   C_BIN_END = C_BIN_I32 + 28,
+  // Multiply-add (a * b + c, each step rounded / wrapped like the separate ops):
+  //   +0 acc * slot a + slot b     +1 slot c * slot a + slot b
+  C_MAD_I64 = C_BIN_END, C_MAD_F64 = C_MAD_I64 + 2, C_MAD_I32 = C_MAD_F64 + 2,
+  C_MAD_END = C_MAD_I32 + 2,
 };
 // SUBR / GT are SUB / LT with the operands swapped (F_REV resolved at compile time).
 enum { B_ADD = 0, B_SUB = 1, B_SUBR = 2, B_MUL = 3, B_LT = 4, B_GT = 5, B_EQ = 6 };

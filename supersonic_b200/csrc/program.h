@@ -27,6 +27,7 @@ enum {
 struct ExprParams {
   Insn insn[kMaxInsn];
   uint64_t imm[kMaxImm];
+  uint32_t insn_c[kMaxInsn];            // third operand offset of multiply-add instructions (encoded like Insn::off_a)
   int32_t n_insn;
   // ---- inputs: slot i < n_in is input column i of the current pipeline stage
   int32_t n_in;

@@ -92,6 +92,11 @@ def test_expression_matrix(ref, b200, n):
               "(case (col i64) (null INT64) (col ni32) (col i64) (col u32) (col ni64))",
               "(in (col ni32) (col i32) (i32 2) (col ni64))", "(in (col f64) (col ni32) (f64 1.5))",
               "(in (col i32) (i32 1) (null INT32))"]
+    # multiply-add superinstruction: two roundings for DOUBLE (no FMA contraction), wrap for ints
+    exprs += ["(plus (multiply (col f64) (col f64)) (col f64))", "(plus (multiply (col i64) (col i64)) (col i64))",
+              "(plus (multiply (col i32) (col i32)) (col i32))", "(plus (col f64) (multiply (col f64) (f64 1.1)))",
+              "(plus (multiply (plus (col f64) (f64 0.3)) (col f64)) (col f64))",
+              "(minus (i64 5) (col i64))", "(greater (col i64) (i64 3))", "(less_or_equal (i32 7) (col i32))"]
     exprs += ["(not (col nb))", "(cast DATETIME (col nd))",
               "(plus (multiply (col i64) (col i32)) (minus (col f64) (col nu32)))",
               "(if (less (col i32) (i32 0)) (negate (col i32)) (col i32))",
@@ -143,6 +148,29 @@ def test_filter_project_c1(ref, b200, n, sel):
     plan_b = ("(filter (less (col d) (i64 %d)) (all) (compute (compound (as e (plus (multiply "
               "(col a) (col b)) (col c))) (col a) (col b) (col c) (col d)) (scan 0)))" % sel)
     same_results(ref.run(plan_b, [cols], next_max_rows=16384), b200.run(plan_b, [cols], next_max_rows=16384))
+
+
+@pytest.mark.parametrize("n", [777, 100_000])
+def test_filter_comparison_predicates(ref, b200, n):
+    """Every fast comparison form feeding the compaction directly (compare fused with the
+    predicate step), next to predicates that go through a materialised BOOL."""
+    rng = np.random.default_rng(n)
+    cols = table(rng, n, small=True)
+    preds = ["(less (col i64) (i64 2))", "(greater_or_equal (col i64) (col i64))", "(greater (col i32) (i32 0))",
+             "(less_or_equal (col f64) (f64 0.5))", "(equal (col i32) (i32 1))", "(not_equal (col i64) (i64 0))",
+             "(less (plus (col i64) (i64 1)) (col i64))", "(greater (multiply (col f64) (f64 2.0)) (col f64))",
+             "(less (col ni64) (i64 2))", "(and (less (col i32) (i32 3)) (greater (col f64) (f64 -1.0)))",
+             "(less (i64 1) (col i64))", "(col b)", "(less (col i32) (col i64))"]
+    for pr in preds:
+        plan = ("(project (named e i32 nf64) (filter %s (all) (compute (compound (col i64) (col i32) (col f64) "
+                "(col ni64) (col nf64) (col b) (as e (plus (multiply (col i64) (col i64)) (col i64)))) (scan 0))))" % pr)
+        a = ref.run(plan, [cols])
+        b = b200.run(plan, [cols])
+        assert a.code == 0, (pr, a.error)
+        try:
+            same_results(a, b)
+        except AssertionError as e:
+            raise AssertionError("%s: %s" % (pr, e))
 
 
 def test_filter_with_nulls_and_stacked_operators(ref, b200):

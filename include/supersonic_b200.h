@@ -83,6 +83,7 @@ int ssb_malloc_host(ssb_ctx* ctx, size_t bytes, void** out);   /* pinned */
 int ssb_free_host(ssb_ctx* ctx, void* ptr);
 int ssb_memcpy_h2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
 int ssb_memcpy_d2h(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
+int ssb_memcpy_d2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
 int ssb_memset(ssb_ctx* ctx, void* dst, int value, size_t bytes);            /* async */
 /* 1 when `ptr` is device memory, 0 for host memory (pageable or pinned). Lets ScanView accept
  * views over either (cursor/core/scan_view.h:35 takes any readable pointer). */
@@ -234,6 +235,15 @@ void ssb_join_destroy(ssb_join* j);
  * probe). Synchronises to return the count. */
 int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type,
                    int64_t* n_pairs, const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
+
+/* Stable hash partition of rows for the multi-GPU join redistribution (the reference
+ * has no counterpart: cursor/core/hash_join.cc runs on one thread). part(row) = high bits of
+ * the join key hash scaled to [0, n_parts); integer keys of different widths hash alike, so the
+ * two sides of a join agree. Rows with a NULL key column never match (hash_join.cc:67-76) and
+ * are assigned to `null_part`. d_perm[rows] receives the row ids grouped by part, ascending
+ * inside each part; h_counts[n_parts] (HOST memory) the rows per part. Synchronises. */
+int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows,
+                       int32_t n_parts, int32_t null_part, int64_t* d_perm, int64_t* h_counts);
 
 /* dst[i] = src[idx[i]]; idx[i] < 0 -> NULL (base/infrastructure/copy_column.cc:112-127,
  * 200-286). dst.nulls may be NULL when neither src.nulls nor negative indices occur. */

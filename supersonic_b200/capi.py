@@ -79,6 +79,7 @@ def load():
         "ssb_free_host": (C.c_int, [P, P]),
         "ssb_memcpy_h2d": (C.c_int, [P, P, P, C.c_size_t]),
         "ssb_memcpy_d2h": (C.c_int, [P, P, P, C.c_size_t]),
+        "ssb_memcpy_d2d": (C.c_int, [P, P, P, C.c_size_t]),
         "ssb_memset": (C.c_int, [P, P, C.c_int, C.c_size_t]),
         "ssb_pointer_is_device": (C.c_int, [P]),
         "ssb_nulls_pack": (C.c_int, [P, P, I64, P]),
@@ -104,6 +105,7 @@ def load():
         "ssb_join_build": (C.c_int, [P, I32, C.POINTER(Column), I64, I32, C.POINTER(P)]),
         "ssb_join_destroy": (None, [P]),
         "ssb_join_probe": (C.c_int, [P, C.POINTER(Column), I64, I32, C.POINTER(I64), C.POINTER(P), C.POINTER(P)]),
+        "ssb_partition_rows": (C.c_int, [P, I32, C.POINTER(Column), I64, I32, I32, P, C.POINTER(I64)]),
         "ssb_gather": (C.c_int, [P, C.POINTER(Column), P, I64, C.POINTER(Column)]),
         "ssb_sort_permutation": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I32), I64, P]),
     }

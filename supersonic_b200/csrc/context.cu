@@ -207,6 +207,10 @@ int ssb_memcpy_d2h(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
+int ssb_memcpy_d2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
 int ssb_memset(ssb_ctx* ctx, void* dst, int value, size_t bytes) {
   if (bytes) SSB_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
   return 0;

@@ -189,6 +189,33 @@ __global__ void __launch_bounds__(256) join_emit_kernel(JoinTable t, long long r
   }
 }
 
+
+// Part id per row for the multi-GPU redistribution: the high bits of the key hash scaled to
+// [0, n_parts) (the table slot uses the low bits, so parts and slots stay independent); rows
+// with a NULL key column never match and stay on `null_part`. Also counts the rows per part.
+__global__ void __launch_bounds__(256) part_id_kernel(JoinKeys keys, long long rows, unsigned int n_parts,
+                                                       unsigned int null_part, unsigned long long* __restrict__ part_of,
+                                                       long long* __restrict__ row_of,
+                                                       unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
+    unsigned int part = null_part;
+    if (!key_has_null(keys, row)) {
+      unsigned long long first = 0;
+      const unsigned long long h = key_hash(keys, row, &first);
+      part = static_cast<unsigned int>(((h >> 32) * n_parts) >> 32);
+    }
+    part_of[row] = part;
+    row_of[row] = row;
+    atomicAdd(&cnt[part], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts && cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(cnt[threadIdx.x]));
+}
+
 }  // namespace ssb
 
 using namespace ssb;
@@ -355,6 +382,50 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
   *n_pairs = static_cast<int64_t>(total);
   *d_lhs_rows = reinterpret_cast<const int64_t*>(j->lhs_out);
   *d_rhs_rows = reinterpret_cast<const int64_t*>(j->rhs_out);
+  return 0;
+}
+
+int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows, int32_t n_parts,
+                       int32_t null_part, int64_t* d_perm, int64_t* h_counts) {
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  if (n_parts < 1 || n_parts > 256 || null_part < 0 || null_part >= n_parts) {
+    return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "partition: 1..256 parts, null_part inside");
+  }
+  for (int p = 0; p < n_parts; ++p) h_counts[p] = 0;
+  if (rows == 0) return 0;
+  JoinKeys jk;
+  if (int rc = fill_keys(ctx, n_keys, keys, &jk)) return rc;
+  TimedRegion timed(ctx);
+  unsigned long long *k0 = nullptr, *k1 = nullptr, *d_counts = nullptr;
+  long long* v0 = nullptr;
+  cudaError_t e = cudaMalloc(&k0, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&k1, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&v0, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_counts, 256 * 8);
+  if (e != cudaSuccess) { cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(d_counts); return cuda_fail(ctx, e, "partition scratch"); }
+  cudaMemsetAsync(d_counts, 0, 256 * 8, ctx->stream);
+  part_id_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(jk, rows, static_cast<unsigned>(n_parts),
+                                                                    static_cast<unsigned>(null_part), k0, v0, d_counts);
+  ++ctx->launches;
+  // one stable 8-bit pass groups the row ids by part; the sorted ids land in the buffer that
+  // holds them after the last pass (d_perm or v0)
+  long long* va = v0;
+  long long* vb = reinterpret_cast<long long*>(d_perm);
+  int rc = radix_sort_pairs(ctx, &k0, &va, &k1, &vb, static_cast<unsigned long long>(rows), 0, 8);
+  if (rc == 0 && va != reinterpret_cast<long long*>(d_perm)) {
+    cudaMemcpyAsync(d_perm, va, static_cast<size_t>(rows) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+  }
+  unsigned long long h[256];
+  if (rc == 0) {
+    e = cudaMemcpyAsync(h, d_counts, static_cast<size_t>(n_parts) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "partition");
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(d_counts);
+  if (rc) return rc;
+  for (int p = 0; p < n_parts; ++p) h_counts[p] = static_cast<int64_t>(h[p]);
   return 0;
 }
 

@@ -101,49 +101,134 @@ int exclusive_scan_u64(ssb_ctx* ctx, unsigned long long* d_data, unsigned long l
 }
 
 // ------------------------------------------------------------------ radix sort of pairs
+// One-sweep LSD radix sort (8 bits per pass) of (u64 key, i64 value) pairs.
+//   1. radix_diff_kernel     OR of key ^ key[0]: digits whose bits never vary are skipped
+//   2. radix_hist_kernel     one read of the keys gives the digit histograms of ALL passes
+//   3. radix_base_kernel     exclusive scan of each 256-bin histogram = global digit bases
+//   4. radix_onesweep_kernel one launch per pass: a CTA takes the next 4096-pair tile (atomic
+//      ticket, so a tile never waits for one that has not started), ranks its keys stably with
+//      warp match + per-warp digit counters, publishes the tile's digit counts and resolves the
+//      counts of all earlier tiles by decoupled look-back (one thread per digit; flag and value
+//      share one 64-bit word, so no fence is needed), stages the tile sorted by digit in shared
+//      memory and writes it out in coalesced runs. Keys and values are read once and written
+//      once per pass (32 B per pair).
 enum { kSortThreads = 256, kSortItemsPerThread = 16, kSortTile = kSortThreads * kSortItemsPerThread,
-       kRadixBits = 8, kRadix = 1 << kRadixBits };
+       kRadixBits = 8, kRadix = 1 << kRadixBits, kMaxPasses = 8 };
 
-// Block digit histogram; hist is digit-major: hist[d * nblocks + block].
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const unsigned long long* __restrict__ keys,
-                                                                   unsigned long long n, int shift,
-                                                                   unsigned long long* __restrict__ hist,
-                                                                   unsigned int nblocks) {
-  __shared__ unsigned int cnt[kRadix];
-  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) cnt[d] = 0;
-  __syncthreads();
-  const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kSortTile;
-  for (int k = 0; k < kSortItemsPerThread; ++k) {
-    const unsigned long long i = base + k * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & (kRadix - 1)], 1u);
-  }
-  __syncthreads();
-  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) hist[static_cast<unsigned long long>(d) * nblocks + blockIdx.x] = cnt[d];
+static constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Stable scatter. Warp w of the block owns the items [w*512, (w+1)*512) of the tile and walks
-// them 32 at a time, so ranks follow the input order.
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
+struct PassList {
+  int n;
+  int shift[kMaxPasses];
+};
+
+__global__ void __launch_bounds__(256) radix_diff_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                          unsigned long long* __restrict__ out_mask) {
+  const unsigned long long k0 = keys[0];
+  unsigned long long m = 0;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const unsigned long long a = keys[i], b = keys[i + stride], c = keys[i + 2 * stride], d = keys[i + 3 * stride];
+    m |= (a ^ k0) | (b ^ k0) | (c ^ k0) | (d ^ k0);
+  }
+  for (; i < n; i += stride) m |= keys[i] ^ k0;
+  for (int d = 16; d > 0; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(out_mask, m);
+}
+
+// ghist[p * 256 + digit] += number of keys with that digit in pass p.
+__global__ void __launch_bounds__(256) radix_hist_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                                          const PassList pl, unsigned long long* __restrict__ ghist) {
+  __shared__ unsigned int h[kMaxPasses * kRadix];
+  for (int j = threadIdx.x; j < pl.n * kRadix; j += blockDim.x) h[j] = 0;
+  __syncthreads();
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    unsigned long long k[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) k[q] = keys[i + q * stride];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      for (int p = 0; p < pl.n; ++p) atomicAdd(&h[p * kRadix + ((k[q] >> pl.shift[p]) & (kRadix - 1))], 1u);
+    }
+  }
+  for (; i < n; i += stride) {
+    const unsigned long long k = keys[i];
+    for (int p = 0; p < pl.n; ++p) atomicAdd(&h[p * kRadix + ((k >> pl.shift[p]) & (kRadix - 1))], 1u);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < pl.n * kRadix; j += blockDim.x) {
+    if (h[j]) atomicAdd(&ghist[j], static_cast<unsigned long long>(h[j]));
+  }
+}
+
+// One CTA of 256 threads per pass: in-place exclusive scan of the pass's 256 bins.
+__global__ void __launch_bounds__(kRadix) radix_base_kernel(unsigned long long* __restrict__ ghist) {
+  __shared__ unsigned long long wsum[kRadix / 32];
+  unsigned long long* h = ghist + static_cast<size_t>(blockIdx.x) * kRadix;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long v = h[threadIdx.x];
+  unsigned long long incl = v;
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  unsigned long long before = 0;
+  for (int w = 0; w < warp; ++w) before += wsum[w];
+  h[threadIdx.x] = before + incl - v;
+}
+
+// aux layout: [0] ticket (u32 in a u64 word), [1 .. 1 + tiles*256) status words of the pass.
+__global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
     const unsigned long long* __restrict__ keys_in, const long long* __restrict__ vals_in,
     unsigned long long* __restrict__ keys_out, long long* __restrict__ vals_out, unsigned long long n, int shift,
-    const unsigned long long* __restrict__ hist_scanned, unsigned int nblocks) {
+    const unsigned long long* __restrict__ gbase, unsigned long long* __restrict__ aux) {
   constexpr int NW = kSortThreads / 32;
   constexpr int PER_WARP = kSortTile / NW;
-  __shared__ unsigned int wcnt[NW][kRadix];     // per-warp digit counts, then exclusive bases
-  __shared__ unsigned long long gbase[kRadix];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int d = threadIdx.x; d < kRadix * NW; d += kSortThreads) (&wcnt[0][0])[d] = 0;
+  constexpr int ROUNDS = PER_WARP / 32;
+  __shared__ unsigned long long stage[kSortTile];        // 32 KB: the tile ordered by digit (keys, then values)
+  __shared__ unsigned long long gadj[kRadix];            // global position of local position 0 of a digit run
+  __shared__ unsigned int lstart[kRadix];                // first local position of a digit
+  __shared__ unsigned short wcnt[NW][kRadix];            // per-warp digit counts, then exclusive bases
+  __shared__ unsigned char dig[kSortTile];               // digit of the staged element
+  __shared__ unsigned int wsum[NW];
+  __shared__ unsigned int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(aux), 1u);
+  for (int d = tid; d < kRadix * NW; d += kSortThreads) (&wcnt[0][0])[d] = 0;
   __syncthreads();
-  const unsigned long long tile0 = static_cast<unsigned long long>(blockIdx.x) * kSortTile + static_cast<unsigned long long>(warp) * PER_WARP;
-  unsigned long long k[PER_WARP / 32];
-  unsigned short rank[PER_WARP / 32];
+  const unsigned long long tile = s_tile;
+  unsigned long long* status = aux + 1;
+  const unsigned long long tile0 = tile * kSortTile;
+  const unsigned long long warp0 = tile0 + static_cast<unsigned long long>(warp) * PER_WARP + lane;
+  const unsigned long long left = n - tile0;
+  const int cnt_tile = left < static_cast<unsigned long long>(kSortTile) ? static_cast<int>(left) : kSortTile;
+
+  unsigned long long k[ROUNDS];
+  unsigned short pos[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const unsigned long long i = warp0 + r * 32;
+    k[r] = i < n ? keys_in[i] : ~0ull;
+  }
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-  for (int r = 0; r < PER_WARP / 32; ++r) {
-    const unsigned long long i = tile0 + r * 32 + lane;
-    const bool live = i < n;
-    k[r] = live ? keys_in[i] : ~0ull;
-    const unsigned d = live ? static_cast<unsigned>((k[r] >> shift) & (kRadix - 1)) : kRadix;   // dead lanes: no digit
+  for (int r = 0; r < ROUNDS; ++r) {
+    const bool live = warp0 + r * 32 < n;
+    const unsigned d = static_cast<unsigned>((k[r] >> shift) & (kRadix - 1));
     const unsigned active = __ballot_sync(0xffffffffu, live);
     unsigned peers = 0;
     if (live) peers = __match_any_sync(active, d);
@@ -151,54 +236,128 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
     if (live) before = wcnt[warp][d];
     __syncwarp();
     if (live) {
-      rank[r] = static_cast<unsigned short>(before + __popc(peers & lt));
-      if ((__ffs(peers) - 1) == lane) wcnt[warp][d] = before + __popc(peers);
+      pos[r] = static_cast<unsigned short>(before + __popc(peers & lt));
+      if ((__ffs(peers) - 1) == lane) wcnt[warp][d] = static_cast<unsigned short>(before + __popc(peers));
     }
     __syncwarp();
   }
   __syncthreads();
-  // exclusive scan over the warps for every digit + global base of (digit, block)
-  for (int d = threadIdx.x; d < kRadix; d += kSortThreads) {
-    unsigned int run = 0;
-    for (int w = 0; w < NW; ++w) { const unsigned int c = wcnt[w][d]; wcnt[w][d] = run; run += c; }
-    gbase[d] = hist_scanned[static_cast<unsigned long long>(d) * nblocks + blockIdx.x];
+  // thread d owns digit d: scan over the warps, publish the tile's count, scan over the digits
+  unsigned int total = 0;
+  {
+    const int d = tid;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { const unsigned int c = wcnt[w][d]; wcnt[w][d] = static_cast<unsigned short>(total); total += c; }
+    st_relaxed_u64(&status[tile * kRadix + d], (tile == 0 ? kFlagPrefix : kFlagAgg) | total);
+    unsigned int incl = total;
+    for (int s = 1; s < 32; s <<= 1) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned int before = 0;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    lstart[d] = before + incl - total;
   }
   __syncthreads();
+  // stage the keys ordered by digit
 #pragma unroll
-  for (int r = 0; r < PER_WARP / 32; ++r) {
-    const unsigned long long i = tile0 + r * 32 + lane;
-    if (i < n) {
+  for (int r = 0; r < ROUNDS; ++r) {
+    if (warp0 + r * 32 < n) {
       const unsigned d = static_cast<unsigned>((k[r] >> shift) & (kRadix - 1));
-      const unsigned long long pos = gbase[d] + wcnt[warp][d] + rank[r];
-      keys_out[pos] = k[r];
-      vals_out[pos] = vals_in[i];
+      const unsigned int q = lstart[d] + wcnt[warp][d] + pos[r];
+      pos[r] = static_cast<unsigned short>(q);
+      stage[q] = k[r];
+      dig[q] = static_cast<unsigned char>(d);
     }
   }
+  // the values travel in a second round through the same staging buffer; fetch them now so
+  // that their latency overlaps the look-back
+  long long v[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const unsigned long long i = warp0 + r * 32;
+    v[r] = i < n ? vals_in[i] : 0;
+  }
+  {
+    const int d = tid;
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      unsigned long long t = tile - 1;
+      for (;;) {
+        const unsigned long long w = ld_relaxed_u64(&status[t * kRadix + d]);
+        const unsigned long long f = w & kFlagMask;
+        if (f == 0) continue;                  // tile t has a ticket, so it is running: wait
+        excl += w & ~kFlagMask;
+        if (f == kFlagPrefix) break;
+        --t;                                   // tile 0 always publishes a prefix
+      }
+      st_relaxed_u64(&status[tile * kRadix + d], kFlagPrefix | (excl + total));
+    }
+    gadj[d] = gbase[d] + excl - lstart[d];
+  }
+  __syncthreads();
+  for (int i = tid; i < cnt_tile; i += kSortThreads) keys_out[gadj[dig[i]] + i] = stage[i];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    if (warp0 + r * 32 < n) stage[pos[r]] = static_cast<unsigned long long>(v[r]);
+  }
+  __syncthreads();
+  for (int i = tid; i < cnt_tile; i += kSortThreads) vals_out[gadj[dig[i]] + i] = static_cast<long long>(stage[i]);
 }
 
 // Sorts (keys, vals) by bits [begin_bit, end_bit) of keys; stable. The result ends in
-// (*keys, *vals); tmp buffers are swapped in and out as needed.
+// (*keys, *vals); tmp buffers are swapped in and out as needed. One host synchronisation
+// (the varying-bits mask decides which passes run at all).
 int radix_sort_pairs(ssb_ctx* ctx, unsigned long long** keys, long long** vals, unsigned long long** keys_tmp,
                      long long** vals_tmp, unsigned long long n, int begin_bit, int end_bit) {
-  if (n <= 1) return 0;
-  const unsigned int nblocks = static_cast<unsigned int>((n + kSortTile - 1) / kSortTile);
-  unsigned long long* hist = nullptr;
-  SSB_CUDA(ctx, cudaMalloc(&hist, static_cast<size_t>(nblocks) * kRadix * 8));
+  if (n <= 1 || end_bit <= begin_bit) return 0;
+  const unsigned long long tiles = (n + kSortTile - 1) / kSortTile;
+  // aux: [mask][ghist 8 x 256][ticket][status tiles x 256]
+  const size_t hist_words = static_cast<size_t>(kMaxPasses) * kRadix;
+  const size_t aux_words = 1 + hist_words + 1 + static_cast<size_t>(tiles) * kRadix;
+  unsigned long long* aux = nullptr;
+  SSB_CUDA(ctx, cudaMalloc(&aux, aux_words * 8));
+  unsigned long long* d_mask = aux;
+  unsigned long long* ghist = aux + 1;
+  unsigned long long* pass_aux = aux + 1 + hist_words;
   int rc = 0;
-  for (int shift = begin_bit; shift < end_bit && rc == 0; shift += kRadixBits) {
-    radix_hist_kernel<<<nblocks, kSortThreads, 0, ctx->stream>>>(*keys, n, shift, hist, nblocks);
+  cudaError_t e = cudaMemsetAsync(aux, 0, (1 + hist_words) * 8, ctx->stream);
+  const unsigned grid = grid_1d(ctx, static_cast<long long>((n + 3) / 4), 256);
+  if (e == cudaSuccess) {
+    radix_diff_kernel<<<grid, 256, 0, ctx->stream>>>(*keys, n, d_mask);
     ++ctx->launches;
-    rc = exclusive_scan_u64(ctx, hist, static_cast<unsigned long long>(nblocks) * kRadix, nullptr);
-    if (rc) break;
-    radix_scatter_kernel<<<nblocks, kSortThreads, 0, ctx->stream>>>(*keys, *vals, *keys_tmp, *vals_tmp, n, shift, hist, nblocks);
+    e = cudaMemcpyAsync(ctx->h_count, d_mask, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(aux); return cuda_fail(ctx, e, "radix sort setup"); }
+  const unsigned long long varying = static_cast<unsigned long long>(*ctx->h_count);
+  PassList pl;
+  pl.n = 0;
+  for (int shift = begin_bit; shift < end_bit && pl.n < kMaxPasses; shift += kRadixBits) {
+    if ((varying >> shift) & (kRadix - 1)) pl.shift[pl.n++] = shift;
+  }
+  if (pl.n > 0) {
+    radix_hist_kernel<<<grid, 256, 0, ctx->stream>>>(*keys, n, pl, ghist);
     ++ctx->launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "radix sort"); break; }
-    std::swap(*keys, *keys_tmp);
-    std::swap(*vals, *vals_tmp);
+    radix_base_kernel<<<pl.n, kRadix, 0, ctx->stream>>>(ghist);
+    ++ctx->launches;
+    for (int p = 0; p < pl.n; ++p) {
+      e = cudaMemsetAsync(pass_aux, 0, (1 + static_cast<size_t>(tiles) * kRadix) * 8, ctx->stream);
+      if (e != cudaSuccess) break;
+      radix_onesweep_kernel<<<static_cast<unsigned>(tiles), kSortThreads, 0, ctx->stream>>>(
+          *keys, *vals, *keys_tmp, *vals_tmp, n, pl.shift[p], ghist + static_cast<size_t>(p) * kRadix, pass_aux);
+      ++ctx->launches;
+      std::swap(*keys, *keys_tmp);
+      std::swap(*vals, *vals_tmp);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "radix sort");
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(hist);
+  cudaFree(aux);
   return rc;
 }
 

@@ -104,3 +104,201 @@ class ShardedGroupAggregate(object):
             nulls.append(None)
         ctx.lib.ssb_group_destroy(g)
         return keys, outs, nulls
+
+
+# ---------------------------------------------------------------------------------------------
+# Hash join over row-range shards (BASELINE config 4)
+# ---------------------------------------------------------------------------------------------
+INNER, LEFT_OUTER = 0, 1
+NOT_UNIQUE, UNIQUE = 0, 1
+
+
+def _torch_dtype(dtype):
+    """torch container of an SSB_* column type (unsigned columns travel as their signed bit image)."""
+    import torch
+    from supersonic_b200 import capi
+    return {capi.INT64: torch.int64, capi.DATETIME: torch.int64, capi.UINT64: torch.int64,
+            capi.DOUBLE: torch.float64, capi.INT32: torch.int32, capi.DATE: torch.int32,
+            capi.ENUM: torch.int32, capi.UINT32: torch.int32, capi.FLOAT: torch.float32,
+            capi.BOOL: torch.uint8}[dtype]
+
+
+class CudaJoinKernels(object):
+    """The four data-path steps of the sharded join, each one C-ABI call into libssb200.so on
+    the device pointers of torch tensors (torch: allocation and collectives only). The torch
+    work of the join is issued on the context's own stream (`stream`), so kernels and
+    collectives stay ordered without host synchronisation."""
+
+    def __init__(self, ctx):
+        import torch
+        from supersonic_b200 import capi
+        self.torch, self.capi, self.ctx = torch, capi, ctx
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.ExternalStream(ctx.lib.ssb_ctx_stream(ctx.h), device=self.device)
+
+    def _cols(self, cols):
+        arr = (self.capi.Column * max(1, len(cols)))()
+        for i, (t, dtype) in enumerate(cols):
+            arr[i].data, arr[i].nulls, arr[i].dtype = t.data_ptr(), None, dtype
+        return arr
+
+    def empty(self, n, dtype):
+        return self.torch.empty(max(int(n), 0), dtype=_torch_dtype(dtype), device=self.device)
+
+    def partition(self, keys, n_parts, null_part):
+        """Stable hash partition: (row ids grouped by part, rows per part)."""
+        rows = keys[0][0].numel()
+        perm = self.empty(rows, self.capi.INT64)
+        counts = (C.c_int64 * n_parts)()
+        self.ctx.check(self.ctx.lib.ssb_partition_rows(self.ctx.h, len(keys), self._cols(keys), rows, n_parts,
+                                                       null_part, perm.data_ptr(), counts))
+        return perm, [int(c) for c in counts]
+
+    def gather(self, col, idx, want_valid=False):
+        """out[i] = col[idx[i]]; with want_valid also an is_null byte per row: 1 where idx[i] < 0."""
+        t, dtype = col
+        n = idx.numel()
+        out = self.empty(n, dtype)
+        dst = self._cols([(out, dtype)])
+        bitmap = None
+        if want_valid:
+            bitmap = self.torch.zeros((n + 31) // 32 + 1, dtype=self.torch.int32, device=self.device)
+            dst[0].nulls = bitmap.data_ptr()
+        if n:
+            self.ctx.check(self.ctx.lib.ssb_gather(self.ctx.h, self._cols([col]), idx.data_ptr(), n, dst))
+        if not want_valid:
+            return out
+        is_null = self.torch.zeros(n, dtype=self.torch.uint8, device=self.device)
+        if n:
+            self.ctx.check(self.ctx.lib.ssb_nulls_unpack(self.ctx.h, bitmap.data_ptr(), n, is_null.data_ptr()))
+        return out, is_null
+
+    def join(self, build_keys, probe_keys, join_type, uniqueness):
+        """(lhs row, rhs row) pairs of the local join in lhs order (rhs -1: unmatched, LEFT_OUTER)."""
+        lib, ctx, torch = self.ctx.lib, self.ctx, self.torch
+        h = C.c_void_p()
+        ctx.check(lib.ssb_join_build(ctx.h, len(build_keys), self._cols(build_keys), build_keys[0][0].numel(),
+                                     uniqueness, C.byref(h)))
+        try:
+            n = C.c_int64()
+            pl, pr = C.c_void_p(), C.c_void_p()
+            ctx.check(lib.ssb_join_probe(h, self._cols(probe_keys), probe_keys[0][0].numel(), join_type,
+                                         C.byref(n), C.byref(pl), C.byref(pr)))
+            li, ri = self.empty(n.value, self.capi.INT64), self.empty(n.value, self.capi.INT64)
+            if n.value:
+                ctx.check(lib.ssb_memcpy_d2d(ctx.h, li.data_ptr(), pl, n.value * 8))
+                ctx.check(lib.ssb_memcpy_d2d(ctx.h, ri.data_ptr(), pr, n.value * 8))
+                ctx.sync()   # the pair buffers die with the join handle
+        finally:
+            lib.ssb_join_destroy(h)
+        return li, ri
+
+    def scope(self):
+        """Context manager: torch work issued inside runs on the library's stream."""
+        return self.torch.cuda.stream(self.stream)
+
+    def finish(self):
+        self.ctx.sync()
+
+    def order_by(self, key):
+        """Stable ascending order of an INT64 column."""
+        n = key.numel()
+        perm = self.empty(n, self.capi.INT64)
+        if n:
+            desc = (C.c_int32 * 1)(0)
+            self.ctx.check(self.ctx.lib.ssb_sort_permutation(self.ctx.h, 1, self._cols([(key, self.capi.INT64)]), desc,
+                                                             n, perm.data_ptr()))
+        return perm
+
+
+def _exchange(tensor, send_counts, recv_counts, group=None):
+    """all-to-all of one column: rank r receives, in rank order, the slice every rank cut for r."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty(int(sum(recv_counts)), dtype=tensor.dtype, device=tensor.device)
+    dist.all_to_all_single(out, tensor.contiguous(), [int(c) for c in recv_counts], [int(c) for c in send_counts],
+                           group=group)
+    return out
+
+
+def _exchange_counts(send_counts, device, group=None):
+    import torch
+    import torch.distributed as dist
+    s = torch.tensor(send_counts, dtype=torch.int64, device=device)
+    r = torch.empty_like(s)
+    dist.all_to_all_single(r, s, group=group)
+    return [int(x) for x in r.tolist()]
+
+
+class ShardedHashJoin(object):
+    """HashJoin(INNER | LEFT_OUTER, UNIQUE | NOT_UNIQUE) over tables sharded by row range.
+
+    Both sides are redistributed by key hash with one all-to-all each (NCCL over NVLink for CUDA
+    tensors): the build side with its payload columns, the probe side as keys + origin row id
+    only. Every rank joins what it received (ssb_join_build / ssb_join_probe), gathers the rhs
+    payload of its pairs and returns them to the rank owning the lhs row with a third
+    all-to-all; the owner restores lhs order with a stable sort on the origin row id. A build
+    row list received in rank order is in global insertion order and all pairs of one lhs row
+    come from one rank, so the concatenation of the per-rank results in rank order is exactly
+    the reference's output order (cursor/core/hash_join.cc:793-831).
+    NOT NULL columns only in this round (a NULL key never matches: hash_join.cc:67-76)."""
+
+    def __init__(self, kernels, group=None):
+        self.k, self.group = kernels, group
+
+    def run(self, lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type=INNER, uniqueness=UNIQUE):
+        """Columns are (tensor, SSB dtype) pairs of this rank's shards. Returns
+        (lhs_rows, lhs payload columns, rhs payload columns, rhs_is_null or None): the join
+        result for this rank's lhs shard in lhs order; lhs_rows are shard-local row ids."""
+        with self.k.scope():
+            out = self._run(lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type, uniqueness)
+        self.k.finish()
+        return out
+
+    def _run(self, lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type, uniqueness):
+        import torch.distributed as dist
+        k, g = self.k, self.group
+        world, rank = dist.get_world_size(g), dist.get_rank(g)
+        device = lhs_keys[0][0].device
+        I64 = 2
+        # ---- build side: keys + payload to the rank that owns the key's hash range
+        perm_b, cnt_b = k.partition(rhs_keys, world, rank)
+        rcv_b = _exchange_counts(cnt_b, device, g)
+        b_keys = [(_exchange(k.gather(c, perm_b), cnt_b, rcv_b, g), c[1]) for c in rhs_keys]
+        b_cols = [(_exchange(k.gather(c, perm_b), cnt_b, rcv_b, g), c[1]) for c in rhs_cols]
+        # ---- probe side: keys + origin row id
+        perm_p, cnt_p = k.partition(lhs_keys, world, rank)
+        rcv_p = _exchange_counts(cnt_p, device, g)
+        p_keys = [(_exchange(k.gather(c, perm_p), cnt_p, rcv_p, g), c[1]) for c in lhs_keys]
+        p_origin = _exchange(perm_p, cnt_p, rcv_p, g)
+        # ---- local join; pairs come in received-lhs order = (source rank, origin row)
+        li, ri = k.join(b_keys, p_keys, join_type, uniqueness)
+        bounds = [0]
+        for c in rcv_p:
+            bounds.append(bounds[-1] + c)
+        import torch
+        edges = torch.searchsorted(li, torch.tensor(bounds, dtype=torch.int64, device=device)).tolist() \
+            if li.numel() else [0] * (world + 1)
+        back = [int(edges[s + 1] - edges[s]) for s in range(world)]
+        rcv_back = _exchange_counts(back, device, g)
+        origin = _exchange(k.gather((p_origin, I64), li), back, rcv_back, g)
+        outer = join_type == LEFT_OUTER
+        r_cols, r_null = [], None
+        for j, c in enumerate(b_cols):
+            if outer and j == 0:
+                vals, is_null = k.gather(c, ri, want_valid=True)
+                r_null = _exchange(is_null, back, rcv_back, g)
+            else:
+                vals = k.gather(c, ri)
+            r_cols.append((_exchange(vals, back, rcv_back, g), c[1]))
+        if outer and not b_cols:
+            _, is_null = k.gather(b_keys[0], ri, want_valid=True)
+            r_null = _exchange(is_null, back, rcv_back, g)
+        # ---- owner: stable order by origin row
+        order = k.order_by(origin)
+        lhs_rows = k.gather((origin, I64), order)
+        out_l = [(k.gather(c, lhs_rows), c[1]) for c in lhs_cols]
+        out_r = [(k.gather(c, order), c[1]) for c in r_cols]
+        if r_null is not None:
+            r_null = k.gather((r_null, 6), order)
+        return lhs_rows, out_l, out_r, r_null

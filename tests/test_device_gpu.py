@@ -201,3 +201,58 @@ def test_sort_permutation_is_sorted_and_a_permutation(ctx):
         assert np.all(np.diff(p)[eq] > 0)
     ctx.free(k)
     ctx.free(perm)
+
+
+@pytest.mark.parametrize("rows,lo,span", [(1, 0, 16), (2, 0, 0), (4095, 0, 1 << 8), (4096, -5, 8), (4097, 0, 0),
+                                          (1_000_001, 0, 1 << 20), (5_000_000, 0, 0), (20_000_000, -(1 << 62), 1 << 63)])
+def test_sort_shapes_match_numpy_stable_argsort(ctx, rows, lo, span):
+    """The one-sweep radix sort against numpy's stable argsort: partial tiles, keys whose high
+    digits never vary (skipped passes), full 64-bit keys, duplicates (stability)."""
+    k = ctx.malloc(rows * 8 + 256)
+    perm = ctx.malloc(rows * 8 + 256)
+    ctx.generate(k, rows, 0, 42, 11, 0, lo, span)
+    hk = np.empty(rows, dtype=np.int64)
+    ctx.lib.ssb_generate_host(hk.ctypes.data, rows, 0, 42, 11, 0, lo, span)
+    ctx.check(ctx.lib.ssb_sort_permutation(ctx.h, 1, _cols([(k, None, capi.INT64)]), (C.c_int32 * 1)(0), rows, perm))
+    p = np.empty(rows, dtype=np.int64)
+    ctx.d2h(p, perm)
+    assert np.array_equal(p, np.argsort(hk, kind="stable"))
+    ctx.free(k)
+    ctx.free(perm)
+
+
+@pytest.mark.parametrize("rows,parts", [(1, 2), (1000, 1), (100_003, 2), (3_000_000, 8), (1_000_000, 200)])
+def test_partition_rows_is_stable_and_sides_agree(ctx, rows, parts):
+    """ssb_partition_rows: a permutation grouped by part with ascending row ids inside each
+    part, counts that add up, and the same key lands in the same part whatever its row,
+    column width (INT32 vs INT64) or side of the join."""
+    k = ctx.malloc(rows * 8 + 256)
+    ctx.generate(k, rows, 0, 42, 12, 1, -500, 1000 if rows > 1000 else 7)
+    hk = np.empty(rows, dtype=np.int64)
+    ctx.lib.ssb_generate_host(hk.ctypes.data, rows, 0, 42, 12, 1, -500, 1000 if rows > 1000 else 7)
+    k32 = ctx.malloc(rows * 4 + 256)
+    ctx.h2d(k32, hk.astype(np.int32))
+    perm = ctx.malloc(rows * 8 + 256)
+    got = []
+    for ptr, dt in [(k, capi.INT64), (k32, capi.INT32)]:
+        counts = (C.c_int64 * parts)()
+        ctx.check(ctx.lib.ssb_partition_rows(ctx.h, 1, _cols([(ptr, None, dt)]), rows, parts, 0, perm, counts))
+        p = np.empty(rows, dtype=np.int64)
+        ctx.d2h(p, perm)
+        cnt = np.array(list(counts))
+        assert cnt.sum() == rows and np.array_equal(np.sort(p), np.arange(rows))
+        part_of_key = {}
+        off = 0
+        for part, c in enumerate(cnt):
+            seg = p[off:off + c]
+            assert np.all(np.diff(seg) > 0)                      # stable inside a part
+            for key in np.unique(hk[seg]):
+                assert part_of_key.setdefault(int(key), part) == part   # a key lives in one part
+            off += c
+        got.append(part_of_key)
+    assert got[0] == got[1]
+    if parts >= 2 and rows >= 100_000:
+        assert len(set(got[0].values())) == min(parts, len(set(got[0].values())))
+        assert len(set(got[0].values())) > 1                      # the hash spreads keys
+    for ptr in (k, k32, perm):
+        ctx.free(ptr)

@@ -94,3 +94,132 @@ def test_ragged_allgather_and_merge_world2():
             s, c = s + vals[b1:e1][m1].sum(), c + int(m1.sum())
         want.append((int(x), float(s), c))
     assert got == want
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharded hash join: the exchange logic (three all-to-alls + order restoration) on CPU over gloo.
+# The four data-path steps are CUDA kernels in the product (CudaJoinKernels); here a numpy stand-in
+# with the same contract takes their place, and the concatenated per-rank results must equal the
+# oracle's HashJoin over the whole tables, in order.
+class NumpyJoinKernels(object):
+    def scope(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def finish(self):
+        pass
+
+    def partition(self, keys, n_parts, null_part):
+        h = np.zeros(keys[0][0].numel(), dtype=np.uint64)
+        for t, _ in keys:
+            h = h * np.uint64(1000003) + t.numpy().astype(np.int64).view(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        part = ((h >> np.uint64(40)) % np.uint64(n_parts)).astype(np.int64)
+        perm = np.argsort(part, kind="stable")
+        return torch.from_numpy(perm), np.bincount(part, minlength=n_parts).tolist()
+
+    def gather(self, col, idx, want_valid=False):
+        t, _ = col
+        i = idx.numpy()
+        src = t.numpy()
+        out = np.zeros(len(i), dtype=src.dtype)
+        ok = i >= 0
+        out[ok] = src[i[ok]]
+        if want_valid:
+            return torch.from_numpy(out), torch.from_numpy((~ok).astype(np.uint8))
+        return torch.from_numpy(out)
+
+    def join(self, build_keys, probe_keys, join_type, uniqueness):
+        index = {}
+        bk = list(zip(*[t.numpy().tolist() for t, _ in build_keys])) if build_keys[0][0].numel() else []
+        for r, key in enumerate(bk):
+            index.setdefault(key, []).append(r)
+        li, ri = [], []
+        pk = list(zip(*[t.numpy().tolist() for t, _ in probe_keys])) if probe_keys[0][0].numel() else []
+        for r, key in enumerate(pk):
+            m = index.get(key)
+            if m:
+                for b in (m[:1] if uniqueness == 1 else m):
+                    li.append(r)
+                    ri.append(b)
+            elif join_type == 1:
+                li.append(r)
+                ri.append(-1)
+        return torch.tensor(li, dtype=torch.int64), torch.tensor(ri, dtype=torch.int64)
+
+    def order_by(self, key):
+        return torch.from_numpy(np.argsort(key.numpy(), kind="stable"))
+
+
+def _join_tables(uniq, scale=1):
+    rng = np.random.default_rng(5)
+    nb, npr = 3000 * scale, 20011 * scale
+    pk = rng.permutation(nb).astype(np.int64) * 3
+    if not uniq:
+        pk[rng.integers(0, nb, nb // 5)] = pk[rng.integers(0, nb, nb // 5)]
+    return {"pk": pk, "payload": rng.integers(0, 10**9, nb), "w": rng.random(nb),
+            "fk": rng.integers(0, nb * 3, npr), "lv": rng.integers(0, 10**9, npr)}
+
+
+def _join_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from supersonic_b200.distributed import ShardedHashJoin
+        I64, F64 = 2, 5
+        res = {}
+        for uniq in (1, 0):
+            t = _join_tables(uniq)
+            bb, be = shard_rows(len(t["pk"]), rank, world, align=1)
+            pb, pe = shard_rows(len(t["fk"]), rank, world, align=1)
+            col = lambda name, b, e, dt: (torch.from_numpy(np.ascontiguousarray(t[name][b:e])), dt)   # noqa: E731
+            for jt in (0, 1):
+                j = ShardedHashJoin(NumpyJoinKernels())
+                rows, lcols, rcols, rnull = j.run([col("fk", pb, pe, I64)], [col("fk", pb, pe, I64), col("lv", pb, pe, I64)],
+                                                  [col("pk", bb, be, I64)], [col("payload", bb, be, I64), col("w", bb, be, F64)],
+                                                  join_type=jt, uniqueness=uniq)
+                res[(uniq, jt)] = ([c.numpy() for c, _ in lcols], [c.numpy() for c, _ in rcols],
+                                   None if rnull is None else rnull.numpy(), rows.numpy() + pb)
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_hash_join_world2_matches_oracle(ref):
+    from supersonic_b200 import ssplan as sp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_join_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for uniq in (1, 0):
+        t = _join_tables(uniq)
+        build = [sp.Column("pk", sp.INT64, t["pk"]), sp.Column("payload", sp.INT64, t["payload"]),
+                 sp.Column("w", sp.DOUBLE, t["w"])]
+        probe = [sp.Column("fk", sp.INT64, t["fk"]), sp.Column("lv", sp.INT64, t["lv"])]
+        for jt in (0, 1):
+            plan = ("(hash_join %s (named fk) (named pk) (multi (0 (all)) (1 (named payload w))) %s (scan 0) (scan 1))"
+                    % (["INNER", "LEFT_OUTER"][jt], ["NOT_UNIQUE", "UNIQUE"][uniq]))
+            want = ref.run(plan, [probe, build])
+            assert want.code == 0
+            parts = [got[r][(uniq, jt)] for r in range(2)]
+            fk = np.concatenate([p[0][0] for p in parts])
+            lv = np.concatenate([p[0][1] for p in parts])
+            pay = np.concatenate([p[1][0] for p in parts])
+            w = np.concatenate([p[1][1] for p in parts])
+            assert len(fk) == want.rows
+            assert np.array_equal(fk, want.columns[0]) and np.array_equal(lv, want.columns[1])
+            if jt == 1:
+                isn = np.concatenate([p[2] for p in parts]).astype(bool)
+                assert np.array_equal(isn, want.nulls[2]) and np.array_equal(isn, want.nulls[3])
+                assert np.array_equal(pay[~isn], want.columns[2][~isn]) and np.array_equal(w[~isn], want.columns[3][~isn])
+            else:
+                assert np.array_equal(pay, want.columns[2]) and np.array_equal(w, want.columns[3])
+            # global lhs row ids are ascending: the concatenation is in lhs order
+            gl = np.concatenate([p[3] for p in parts])
+            assert np.all(np.diff(gl) >= 0)

@@ -113,11 +113,35 @@ def build_program(capi, ctx):
     return capi.Program(ctx, nodes, [I64] * 4, [0] * 4, [5], predicate=7)
 
 
-class _DevArray(object):
-    """Zero-copy view of device memory for torch (CUDA array interface)."""
+def _cols(capi, items):
+    arr = (capi.Column * max(1, len(items)))()
+    for i, (d, n_, t) in enumerate(items):
+        arr[i].data, arr[i].nulls, arr[i].dtype = d, n_, t
+    return arr
 
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+def _timed(ctx, world, dist, torch, fn, repeats=3):
+    """Host clock around device syncs (barrier before, sync after), max over ranks, best of
+    `repeats` after one untimed run."""
+    times = []
+    for it in range(repeats + 1):
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        ctx.sync()
+        if world > 1:
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        if it > 0:
+            times.append(dt)
+    return min(times), out
 
 
 def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
@@ -125,6 +149,7 @@ def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
     k = u mod 1e6 (INT64), v = (u >> 44) * 2^-10 (exactly summable DOUBLE). Every rank aggregates
     its shard (ssb_group_update), the dense partial tables are all-gathered over NCCL and merged
     (ssb_group_merge). Returns rows/s over all ranks (host clock around device syncs)."""
+    from supersonic_b200.distributed import merge_group_partials
     lib = ctx.lib
     first = rank * rows
     k = ctx.malloc(rows * 8 + 256)
@@ -135,56 +160,163 @@ def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
     specs[0].fn, specs[0].input, specs[0].in_type, specs[0].out_type = capi.AGG_SUM, 0, capi.DOUBLE, capi.DOUBLE
     specs[1].fn, specs[1].input, specs[1].in_type, specs[1].out_type = capi.AGG_COUNT, -1, capi.INT64, capi.UINT64
     kt, kn = (C.c_int32 * 1)(capi.INT64), (C.c_int32 * 1)(0)
+    state = {}
 
-    def cols(items):
-        arr = (capi.Column * max(1, len(items)))()
-        for i, (d, n_, t) in enumerate(items):
-            arr[i].data, arr[i].nulls, arr[i].dtype = d, n_, t
-        return arr
-
-    times, groups = [], 0
-    for it in range(3):
+    def once():
         g = C.c_void_p()
         ctx.check(lib.ssb_group_create(ctx.h, 1, kt, kn, 2, specs, 1000000, C.byref(g)))
-        ctx.sync()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.check(lib.ssb_group_update(g, cols([(k, None, capi.INT64)]), cols([(v, None, capi.DOUBLE)]), rows))
-        n = C.c_int64()
-        ko, ao = cols([(0, None, 0)]), cols([(0, None, 0), (0, None, 0)])
-        ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
-        if world > 1:
-            from supersonic_b200.distributed import allgather_ragged
-            tk = torch.as_tensor(_DevArray(ko[0].data, n.value, "<i8"), device="cuda")
-            ts = torch.as_tensor(_DevArray(ao[0].data, n.value, "<f8"), device="cuda")
-            tc = torch.as_tensor(_DevArray(ao[1].data, n.value, "<i8"), device="cuda")
-            gk, gs, gc = allgather_ragged(tk), allgather_ragged(ts), allgather_ragged(tc)
-            torch.cuda.synchronize()
-            for r in range(world):
-                if r == rank:
-                    continue
-                ctx.check(lib.ssb_group_merge(g, gk[r].numel(), cols([(gk[r].data_ptr(), None, capi.INT64)]),
-                                              cols([(gs[r].data_ptr(), None, capi.DOUBLE), (gc[r].data_ptr(), None, capi.UINT64)])))
-            ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
-            torch.cuda.synchronize()
-        ctx.sync()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        times.append(dt)
-        groups = n.value
+        ctx.check(lib.ssb_group_update(g, _cols(capi, [(k, None, capi.INT64)]), _cols(capi, [(v, None, capi.DOUBLE)]), rows))
+        n, ko, ao = merge_group_partials(ctx, g, [capi.INT64], [capi.DOUBLE, capi.UINT64])
+        cnt = np.zeros(n, dtype=np.uint64)
+        ctx.d2h(cnt, ao[1].data)
+        state["groups"], state["rows_counted"] = n, int(cnt.sum())
         lib.ssb_group_destroy(g)
+
+    best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
     ctx.free(k)
     ctx.free(v)
-    best = min(times[1:]) if len(times) > 1 else times[0]
+    assert state["rows_counted"] == world * rows, "COUNT(*) over all groups must equal the table's rows"
     return {"metric": "rows/sec, GroupAggregate(k; SUM(v DOUBLE), COUNT(*)), 1M INT64 keys (BASELINE config 3 shape)",
-            "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(groups),
+            "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(state["groups"]),
             "seconds": best, "exchange": "all-gather of dense partial tables + ssb_group_merge" if world > 1 else "none",
-            "algorithmic_gbs_per_gpu": rows * 16 / best / 1e9}
+            "algorithmic_gbs_per_gpu": rows * 16 / best / 1e9, "check": "sum of COUNT(*) == rows"}
+
+
+def q1_aux(capi, ctx, rank, world, rows, dist, torch):
+    """BASELINE config 5 shape (TPC-H Q1 on synthetic lineitem columns), row-range
+    sharded: Filter(ship <= 2450) -> Compute(disc_price, charge) as ONE fused kernel launch, then
+    GroupAggregate({rf, ls}; 5 x SUM, COUNT(*)); per-rank partial tables merged after an
+    all-gather (6 groups). Algorithmic bytes: 7 x 8 = 56 B per row."""
+    from supersonic_b200.distributed import merge_group_partials
+    lib = ctx.lib
+    first = rank * rows
+    I64, F64, BOOL = capi.INT64, capi.DOUBLE, capi.BOOL
+    # inputs: qty price disc tax (DOUBLE, dyadic: sums and products stay exact), rf ls ship (INT64)
+    gens = [(5, 16, 800), (5, 1600, 160000), (5, 0, 2), (5, 0, 2), (1, 0, 3), (1, 0, 2), (1, 0, 2500)]
+    types = [F64, F64, F64, F64, I64, I64, I64]
+    d_in = []
+    for j, (kind, lo, span) in enumerate(gens):
+        ptr = ctx.malloc(rows * 8 + 256)
+        ctx.generate(ptr, rows, first, SEED, 30 + j, kind, lo, span)
+        d_in.append(ptr)
+    n = capi.node
+    nodes = [n(capi.OP_INPUT, t, [j]) for j, t in enumerate(types)]                    # 0..6
+    nodes += [n(capi.OP_CONST, F64, [], f64=1.0),                                      # 7
+              n(capi.OP_SUB, F64, [7, 2]),                                             # 8: 1 - disc
+              n(capi.OP_MUL, F64, [1, 8]),                                             # 9: disc_price
+              n(capi.OP_ADD, F64, [7, 3]),                                             # 10: 1 + tax
+              n(capi.OP_MUL, F64, [9, 10]),                                            # 11: charge
+              n(capi.OP_CONST, I64, [], i64=2450),                                     # 12
+              n(capi.OP_LE, BOOL, [6, 12])]                                            # 13: ship <= D
+    prog = capi.Program(ctx, nodes, types, [0] * 7, [4, 5, 0, 1, 2, 9, 11], predicate=13)
+    out_types = [I64, I64, F64, F64, F64, F64, F64]
+    d_out = [ctx.malloc(rows * 8 + 256) for _ in out_types]
+    d_count = ctx.malloc(8)
+    specs = (capi.AggSpec * 6)()
+    for i in range(5):   # SUM qty, price, disc_price, charge, disc
+        specs[i].fn, specs[i].input, specs[i].in_type, specs[i].out_type = capi.AGG_SUM, i, F64, F64
+    specs[5].fn, specs[5].input, specs[5].in_type, specs[5].out_type = capi.AGG_COUNT, -1, I64, capi.UINT64
+    kt, kn = (C.c_int32 * 2)(I64, I64), (C.c_int32 * 2)(0, 0)
+    state = {}
+
+    def once():
+        t0 = time.perf_counter()
+        kept = prog.run_sync([(p_, None, t) for p_, t in zip(d_in, types)], rows,
+                             [(p_, None, t) for p_, t in zip(d_out, out_types)])
+        state["expr_seconds"] = time.perf_counter() - t0
+        g = C.c_void_p()
+        ctx.check(lib.ssb_group_create(ctx.h, 2, kt, kn, 6, specs, 6, C.byref(g)))
+        vals = [(d_out[2], None, F64), (d_out[3], None, F64), (d_out[5], None, F64), (d_out[6], None, F64), (d_out[4], None, F64)]
+        ctx.check(lib.ssb_group_update(g, _cols(capi, [(d_out[0], None, I64), (d_out[1], None, I64)]), _cols(capi, vals), kept))
+        ng, ko, ao = merge_group_partials(ctx, g, [I64, I64], [F64] * 5 + [capi.UINT64])
+        cnt = np.zeros(ng, dtype=np.uint64)
+        ctx.d2h(cnt, ao[5].data)
+        state["groups"], state["counted"], state["kept"] = ng, int(cnt.sum()), kept
+        lib.ssb_group_destroy(g)
+
+    best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
+    kept_all = state["kept"]
+    if world > 1:
+        t = torch.tensor([float(kept_all)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        kept_all = int(t.item())
+    assert state["counted"] == kept_all, "COUNT(*) over all groups must equal the rows the filter kept"
+    prog.close()
+    for ptr in d_in + d_out + [d_count]:
+        ctx.free(ptr)
+    return {"metric": "rows/sec, Q1 shape: Filter(ship<=D) -> Compute(disc_price, charge) -> GroupAggregate({rf,ls}; 5xSUM, COUNT) (BASELINE config 5 shape)",
+            "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(state["groups"]),
+            "seconds": best, "filter_compute_seconds": state["expr_seconds"], "selectivity": kept_all / float(world * rows),
+            "algorithmic_gbs_per_gpu": rows * 56 / best / 1e9, "check": "sum of COUNT(*) == rows kept by the filter",
+            "exchange": "all-gather of 6-group partial tables + ssb_group_merge" if world > 1 else "none"}
+
+
+def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
+    """BASELINE config 4 shape, row-range sharded: HashJoin(INNER, fk = pk, UNIQUE) with the build
+    side a permutation of [0, B) (B = world x build_rows), probe keys uniform over the build keys,
+    result {fk, lv, payload}. One rank: ssb_join_build + ssb_join_probe + gathers. Several ranks:
+    ShardedHashJoin (hash partition kernel, all-to-all over NCCL, local join, return trip)."""
+    lib = ctx.lib
+    I64 = capi.INT64
+    total_build = world * build_rows
+    mult = 1000000007
+    while np.gcd(mult, total_build) != 1:
+        mult += 2
+    if world == 1:
+        pk, pay = ctx.malloc(build_rows * 8 + 256), ctx.malloc(build_rows * 8 + 256)
+        fk, lv = ctx.malloc(probe_rows * 8 + 256), ctx.malloc(probe_rows * 8 + 256)
+        o_fk, o_lv, o_pay = (ctx.malloc(probe_rows * 8 + 256) for _ in range(3))
+        ptrs = dict(pk=pk, pay=pay, fk=fk, lv=lv)
+        keep = [pk, pay, fk, lv, o_fk, o_lv, o_pay]
+    else:
+        tens = {nm: torch.empty(n_, dtype=torch.int64, device="cuda")
+                for nm, n_ in [("pk", build_rows), ("pay", build_rows), ("fk", probe_rows), ("lv", probe_rows)]}
+        ptrs = {nm: t.data_ptr() for nm, t in tens.items()}
+        torch.cuda.synchronize()
+    ctx.generate(ptrs["pk"], build_rows, rank * build_rows, SEED, 40, 4, mult, total_build)
+    ctx.generate(ptrs["pay"], build_rows, rank * build_rows, SEED, 41, 0, 0, 0)
+    ctx.generate(ptrs["fk"], probe_rows, rank * probe_rows, SEED, 42, 1, 0, total_build)
+    ctx.generate(ptrs["lv"], probe_rows, rank * probe_rows, SEED, 43, 0, 0, 0)
+    ctx.sync()
+    state = {}
+    if world == 1:
+        def once():
+            j = C.c_void_p()
+            ctx.check(lib.ssb_join_build(ctx.h, 1, _cols(capi, [(ptrs["pk"], None, I64)]), build_rows, 1, C.byref(j)))
+            n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+            ctx.check(lib.ssb_join_probe(j, _cols(capi, [(ptrs["fk"], None, I64)]), probe_rows, 0, C.byref(n), C.byref(pl), C.byref(pr)))
+            assert n.value <= probe_rows
+            for src, idx, dst in [(ptrs["fk"], pl, o_fk), (ptrs["lv"], pl, o_lv), (ptrs["pay"], pr, o_pay)]:
+                ctx.check(lib.ssb_gather(ctx.h, _cols(capi, [(src, None, I64)]), idx, n.value, _cols(capi, [(dst, None, I64)])))
+            ctx.sync()
+            state["pairs"] = n.value
+            lib.ssb_join_destroy(j)
+    else:
+        from supersonic_b200.distributed import CudaJoinKernels, ShardedHashJoin
+        join = ShardedHashJoin(CudaJoinKernels(ctx))
+
+        def once():
+            rows_, lcols, rcols, _ = join.run([(tens["fk"], I64)], [(tens["fk"], I64), (tens["lv"], I64)],
+                                              [(tens["pk"], I64)], [(tens["pay"], I64)], join_type=0, uniqueness=1)
+            state["pairs"] = int(rows_.numel())
+    best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
+    pairs = state["pairs"]
+    if world > 1:
+        t = torch.tensor([float(pairs)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pairs = int(t.item())
+        del tens
+        torch.cuda.empty_cache()
+    else:
+        for ptr in keep:
+            ctx.free(ptr)
+    assert pairs == world * probe_rows, "every probe key exists exactly once in the build side"
+    alg = 32.0 * build_rows + 40.0 * probe_rows
+    return {"metric": "rows/sec (probe rows), HashJoin INNER UNIQUE on INT64 key, result {fk, lv, payload} (BASELINE config 4 shape)",
+            "value": world * probe_rows / best, "unit": "rows/s", "probe_rows_per_gpu": probe_rows,
+            "build_rows_per_gpu": build_rows, "pairs": pairs, "seconds": best,
+            "algorithmic_gbs_per_gpu": alg / best / 1e9, "check": "pairs == probe rows (every fk has one pk)",
+            "exchange": "hash partition + 3 all-to-all (build, probe, return) over NCCL" if world > 1 else "none"}
 
 
 def host_column(capi, name, rows, first_row=0):
@@ -294,8 +426,11 @@ def run_b200(args):
         ctx.free(d_cols[name])
     ctx.free(d_out)
     aux_group = group_by_aux(capi, ctx, rank, world, min(rows, args.group_rows), dist, torch)
+    aux_q1 = q1_aux(capi, ctx, rank, world, min(rows, args.q1_rows), dist, torch)
+    aux_join = hash_join_aux(capi, ctx, rank, world, min(rows, args.join_probe_rows),
+                             max(1, min(rows, args.join_probe_rows) // 10), dist, torch)
     if rank == 0:
-        result["aux"] = {"group_by": aux_group}
+        result["aux"] = {"group_by": aux_group, "q1": aux_q1, "hash_join": aux_join}
     # ---- end to end through the supersonic.h mirror with pinned host buffers
     e2e_rows = min(args.e2e_rows, rows)
     host = {}
@@ -406,6 +541,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-rows", type=int, default=20_000_000)
     ap.add_argument("--group-rows", type=int, default=1_000_000_000, help="rows per GPU of the aux group-by")
+    ap.add_argument("--q1-rows", type=int, default=600_000_000, help="rows per GPU of the aux Q1-shape plan (C5: 6e8)")
+    ap.add_argument("--join-probe-rows", type=int, default=125_000_000,
+                    help="probe rows per GPU of the aux hash join (C4: 1e9 over 8 GPUs); build side = a tenth")
     ap.add_argument("--per-kernel-timing", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -99,7 +99,10 @@ int ssb_nulls_unpack(ssb_ctx* ctx, const uint32_t* d_bitmap, int64_t rows, uint8
  * kind 0: INT64 uniform in [lo, lo + span)   (span a power of two, or 0 = full 64 bit)
  * kind 1: INT64 u mod span + lo
  * kind 2: DOUBLE (u >> 44) * 2^-10           (exactly summable payload)
- * kind 3: DOUBLE (u >> 11) * 2^-53           (uniform [0,1)) */
+ * kind 3: DOUBLE (u >> 11) * 2^-53           (uniform [0,1))
+ * kind 4: INT64 (row * lo) mod span          (no randomness: a permutation of [0, span) when
+ *                                             gcd(lo, span) = 1; the C4 build key)
+ * kind 5: DOUBLE (lo + u mod span) / 16       (dyadic values: products and sums stay exact, C5) */
 int ssb_generate(ssb_ctx* ctx, void* d_out, int64_t rows, int64_t first_row, uint64_t seed,
                  uint64_t stream, int kind, int64_t lo, uint64_t span);
 void ssb_generate_host(void* out, int64_t rows, int64_t first_row, uint64_t seed,

@@ -39,6 +39,16 @@ int cuda_fail(ssb_ctx* ctx, cudaError_t e, const char* what);
 // Returns the context scratch buffer, at least `bytes` large (contents undefined).
 int scratch(ssb_ctx* ctx, size_t bytes, void** out);
 
+// Stream-ordered temporaries from the device's memory pool (cudaMallocAsync with the release
+// threshold lifted in ssb_ctx_create): repeated operator calls reuse their scratch instead of
+// paying a cudaMalloc / cudaFree pair (and its implicit device synchronisation) every time.
+cudaError_t tmp_malloc_bytes(ssb_ctx* ctx, void** out, size_t bytes);
+void tmp_free(ssb_ctx* ctx, void* ptr);
+template <class T>
+inline cudaError_t tmp_malloc(ssb_ctx* ctx, T** out, size_t bytes) {
+  return tmp_malloc_bytes(ctx, reinterpret_cast<void**>(out), bytes);
+}
+
 #define SSB_CUDA(ctx, call)                                          \
   do {                                                               \
     cudaError_t e_ = (call);                                         \

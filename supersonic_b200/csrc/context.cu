@@ -33,6 +33,26 @@ int scratch(ssb_ctx* ctx, size_t bytes, void** out) {
   return 0;
 }
 
+cudaError_t tmp_malloc_bytes(ssb_ctx* ctx, void** out, size_t bytes) {
+  *out = nullptr;
+  cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 8, ctx->stream);
+  if (e == cudaErrorMemoryAllocation) {
+    // give cached blocks back and try once more
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    e = cudaMallocAsync(out, bytes ? bytes : 8, ctx->stream);
+  }
+  return e;
+}
+
+void tmp_free(ssb_ctx* ctx, void* ptr) {
+  if (ptr) cudaFreeAsync(ptr, ctx->stream);
+}
+
 // bool per row -> bitmap: each warp packs 32 rows with one ballot.
 __global__ void pack_nulls_kernel(const uint8_t* __restrict__ bools, long long rows,
                                   uint32_t* __restrict__ bitmap) {
@@ -67,6 +87,8 @@ __host__ __device__ inline uint64_t gen_value(uint64_t seed, uint64_t stream, ui
     case 0: return static_cast<uint64_t>(lo) + (span ? (u & (span - 1)) : u);
     case 1: return static_cast<uint64_t>(lo) + (u % span);
     case 2: { double d = static_cast<double>(u >> 44) * (1.0 / 1024.0); uint64_t b; memcpy(&b, &d, 8); return b; }
+    case 4: return (row * static_cast<uint64_t>(lo)) % span;   // a permutation of [0, span) when gcd(lo, span) = 1
+    case 5: { double d = static_cast<double>(lo + static_cast<int64_t>(u % span)) * (1.0 / 16.0); uint64_t b; memcpy(&b, &d, 8); return b; }
     default: { double d = static_cast<double>(u >> 11) * (1.0 / 9007199254740992.0); uint64_t b; memcpy(&b, &d, 8); return b; }
   }
 }
@@ -116,6 +138,15 @@ int ssb_ctx_create(int device, ssb_ctx** out) {
     return SSB_ERROR_NOT_IMPLEMENTED;
   }
   cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  {
+    // keep freed temporaries cached in the pool (default: released at the next synchronisation)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   cudaEventCreate(&ctx->tm0);
@@ -183,7 +214,17 @@ int ssb_ctx_timer_stop(ssb_ctx* ctx, float* ms) {
 int ssb_malloc(ssb_ctx* ctx, size_t bytes, void** out) {
   *out = nullptr;
   SSB_CUDA(ctx, cudaSetDevice(ctx->device));
-  SSB_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+  cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    e = cudaMalloc(out, bytes ? bytes : 1);
+  }
+  SSB_CUDA(ctx, e);
   return 0;
 }
 int ssb_free(ssb_ctx* ctx, void* ptr) {
@@ -249,7 +290,7 @@ int ssb_nulls_unpack(ssb_ctx* ctx, const uint32_t* d_bitmap, int64_t rows, uint8
 int ssb_generate(ssb_ctx* ctx, void* d_out, int64_t rows, int64_t first_row, uint64_t seed,
                  uint64_t stream, int kind, int64_t lo, uint64_t span) {
   if (rows <= 0) return 0;
-  if (kind == 1 && span == 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "kind 1 needs a span");
+  if ((kind == 1 || kind == 4 || kind == 5) && span == 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "this kind needs a span");
   if (kind == 0 && (span & (span - 1))) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "kind 0 needs a power-of-two span");
   generate_kernel<<<grid_for(ctx, rows, 256), 256, 0, ctx->stream>>>(
       static_cast<uint64_t*>(d_out), rows, first_row, seed, stream, kind, lo, span);

@@ -18,6 +18,7 @@
 // NULL is NULL (column_aggregator.cc:108-125); COUNT never is.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -26,6 +27,7 @@
 namespace ssb {
 
 enum { kMaxKeys = 8, kMaxAggs = 16, kProbeLimit = 96 };
+static constexpr long long kSliceRows = 1LL << 26;   // rows per launch of the update kernels (multiple of 32)
 static constexpr unsigned long long kEmptyKey = ~0ull;
 
 struct AggDev {
@@ -311,6 +313,91 @@ __global__ void __launch_bounds__(256) group_update_kernel(const __grid_constant
   }
 }
 
+// ---- fast path: one 8-byte NOT NULL key, 8-byte NOT NULL inputs ------------------------------
+// The kernel above interprets the aggregate list per row (about 370 instructions per row for
+// the C3 shape: ncu smsp__inst_executed, profiles/r1b_summary.md) and is bound by instruction
+// issue. This one serves the common shape -- single packed key, every aggregate COUNT or an
+// 8-byte SUM/MIN/MAX whose input type equals its result type, no NULL bitmaps, no replay --
+// with four rows per thread: the four key loads, then the four first probes, then the value
+// loads and reductions are issued back to back, so the dependent L2 round trips of one row
+// overlap those of the others. Same table, same hash, same claim protocol as above.
+__device__ __forceinline__ long long probe_packed_from(const GroupParams& p, unsigned long long key, unsigned long long s,
+                                                       unsigned long long cur) {
+  const unsigned long long mask = p.capacity - 1;
+  for (int probe = 0; probe < kProbeLimit; ++probe) {
+    if (cur == key) return static_cast<long long>(s);
+    if (cur == kEmptyKey) {
+      const unsigned long long old = atomicCAS(&p.slot_key[s], kEmptyKey, key);
+      if (old == kEmptyKey) { atomicAdd(p.n_groups, 1ull); return static_cast<long long>(s); }
+      if (old == key) return static_cast<long long>(s);
+    }
+    s = (s + 1) & mask;
+    cur = p.slot_key[s];
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256, 4) group_update_fast_kernel(const __grid_constant__ GroupParams p) {
+  constexpr int R = 4;
+  constexpr int TILE = 256 * R;
+  const unsigned long long* __restrict__ keys = static_cast<const unsigned long long*>(p.key_data[0]);
+  const unsigned long long mask = p.capacity - 1;
+  const long long tiles = (p.rows + TILE - 1) / TILE;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long r0 = t * TILE + threadIdx.x;
+    unsigned long long key[R], cur[R];
+    long long slot[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long row = r0 + j * 256;
+      key[j] = row < p.rows ? keys[row] : kEmptyKey;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const unsigned long long s = mix64(key[j]) & mask;
+      slot[j] = static_cast<long long>(s);
+      cur[j] = p.slot_key[s];   // first probe of all four rows in flight together
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long row = r0 + j * 256;
+      if (row >= p.rows) { slot[j] = -2; continue; }
+      if (key[j] == kEmptyKey) slot[j] = find_slot_packed(p, row);       // the one key that needs the special slot
+      else if (cur[j] != key[j]) slot[j] = probe_packed_from(p, key[j], static_cast<unsigned long long>(slot[j]), cur[j]);
+      if (slot[j] == -1) {
+        const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+        p.deferred[d] = row;
+      }
+    }
+    for (int a = 0; a < p.n_aggs; ++a) {
+      const AggDev& ag = p.agg[a];
+      if (ag.fn == SSB_AGG_COUNT) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (slot[j] >= 0) atomicAdd(&ag.acc[slot[j]], 1ull);
+        continue;
+      }
+      const unsigned long long* __restrict__ in = static_cast<const unsigned long long*>(ag.in_data);
+      unsigned long long v[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = slot[j] >= 0 ? in[r0 + j * 256] : 0ull;
+      if (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (slot[j] >= 0) atomicAdd(reinterpret_cast<double*>(&ag.acc[slot[j]]), Codec<double>::dec(v[j]));
+      } else if (ag.fn == SSB_AGG_SUM) {   // INT64 / UINT64: wrapping add
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (slot[j] >= 0) atomicAdd(&ag.acc[slot[j]], v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (slot[j] >= 0) apply(ag, slot[j], v[j], 1ull);
+      }
+      if (ag.seen != nullptr) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (slot[j] >= 0) ag.seen[slot[j]] = 1u;
+      }
+    }
+  }
+}
+
 // ---- few groups: CTA-private accumulators in shared memory ---------------------------------
 // With few distinct keys every row of the table hits the same handful of L2 words; the kernel
 // above would serialise on them. Here each CTA keeps its own small table in shared memory
@@ -396,6 +483,164 @@ __global__ void __launch_bounds__(256) group_update_smem_kernel(const __grid_con
       if (ag.fn == SSB_AGG_SUM && ag.out_phys != T_F64 && ag.out_phys != T_F32) atomicAdd(dst, v);   // wrapped 64-bit partial
       else apply(ag, slot, v, 0ull);
     }
+  }
+}
+
+// ---- a handful of groups: per-thread accumulators, no atomics in the row loop ------------------
+// With <= 8 groups (the Q1 shape: 6) every row of a warp hits the same few accumulators, and even
+// shared-memory atomics serialise (a DOUBLE add is a CAS loop there). Here every thread owns a
+// private accumulator per (group, aggregate) in shared memory ([group][aggregate][thread]: bank =
+// thread, no conflicts), a row costs one load-combine-store per aggregate, and the threads'
+// partials are tree-combined once at the end: one global update per (group, aggregate) and CTA.
+// The CTA learns its groups on the fly: the first row of a group goes through the global table
+// (find_slot_*), claims the next local entry by CAS on the slot id and publishes the key values;
+// later rows find the group by comparing their key with the published ones (broadcast reads).
+enum { kTinyGroups = 8, kTinyThreads = 128 };
+
+__device__ __forceinline__ unsigned long long identity_dev(const AggDev& ag) {
+  if (ag.fn == SSB_AGG_MIN) {
+    return ag.out_phys == T_F64 ? Codec<double>::enc(__longlong_as_double(0x7ff0000000000000LL))
+         : ag.out_phys == T_F32 ? Codec<float>::enc(__uint_as_float(0x7f800000u))
+         : (ag.out_phys == T_I64 || ag.out_phys == T_I32) ? static_cast<unsigned long long>(INT64_MAX) : ~0ull;
+  }
+  if (ag.fn == SSB_AGG_MAX) {
+    return ag.out_phys == T_F64 ? Codec<double>::enc(__longlong_as_double(0xfff0000000000000LL))
+         : ag.out_phys == T_F32 ? Codec<float>::enc(__uint_as_float(0xff800000u))
+         : (ag.out_phys == T_I64 || ag.out_phys == T_I32) ? static_cast<unsigned long long>(INT64_MIN) : 0ull;
+  }
+  return 0ull;
+}
+
+__global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const __grid_constant__ GroupParams p) {
+  constexpr int T = kTinyThreads;
+  extern __shared__ unsigned long long t_acc[];                  // [kTinyGroups * n_aggs][T]
+  __shared__ unsigned int t_seen[kTinyGroups][T];                // bit a: this thread saw a value of aggregate a
+  __shared__ unsigned long long l_key[kTinyGroups][kMaxKeys];
+  __shared__ unsigned int l_knull[kTinyGroups];
+  __shared__ unsigned int l_slot[kTinyGroups];                   // global slot + 1, 0 = free; claimed in order
+  __shared__ unsigned int l_ready[kTinyGroups];                  // key values of the entry are published
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = p.n_aggs;
+  for (int i = tid; i < kTinyGroups * A * T; i += T) t_acc[i] = identity_dev(p.agg[(i / T) % A]);
+  for (int i = tid; i < kTinyGroups * T; i += T) (&t_seen[0][0])[i] = 0u;
+  if (tid < kTinyGroups) { l_slot[tid] = 0u; l_ready[tid] = 0u; }
+  __syncthreads();
+  // R rows per thread and iteration; all key and value loads of the R rows are issued before the
+  // first one is used, so a thread pays one HBM round trip per iteration, not two per row
+  constexpr int R = 2;
+  const long long stride = static_cast<long long>(gridDim.x) * T * R;
+  for (long long base = static_cast<long long>(blockIdx.x) * T * R + tid; base < p.rows; base += stride) {
+    long long rows_[R];
+    unsigned long long kv[R][kMaxKeys], vv[R][kLocalMaxAggs];
+    unsigned int knull[R], vnull[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long i = base + static_cast<long long>(j) * T;
+      rows_[j] = i < p.rows ? (p.row_index ? p.row_index[i] : i) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      knull[j] = 0;
+      vnull[j] = 0;
+#pragma unroll
+      for (int c = 0; c < kMaxKeys; ++c) {
+        kv[j][c] = 0;
+        if (c < p.n_keys && rows_[j] >= 0) {
+          if (bit_at(p.key_nulls[c], rows_[j])) knull[j] |= 1u << c; else kv[j][c] = load_raw(p.key_data[c], p.key_phys[c], rows_[j]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < kLocalMaxAggs; ++a) {
+        vv[j][a] = 0;
+        if (a < A && p.agg[a].in_phys >= 0 && rows_[j] >= 0) {
+          if (bit_at(p.agg[a].in_nulls, rows_[j])) vnull[j] |= 1u << a; else vv[j][a] = load_raw(p.agg[a].in_data, p.agg[a].in_phys, rows_[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long row = rows_[j];
+      if (row < 0) continue;
+      int g = -1;
+#pragma unroll
+      for (int e = 0; e < kTinyGroups; ++e) {
+        if (g < 0 && *reinterpret_cast<volatile unsigned int*>(&l_ready[e]) != 0u) {
+          bool same = l_knull[e] == knull[j];
+#pragma unroll
+          for (int c = 0; c < kMaxKeys; ++c) if (c < p.n_keys) same = same && l_key[e][c] == kv[j][c];
+          if (same) g = e;
+        }
+      }
+      long long slot = -1;
+      if (g < 0) {
+        // first sight of this group in the CTA (or its entry is still being published)
+        slot = p.packed ? find_slot_packed(p, row) : find_slot_generic(p, row);
+        if (slot < 0) {
+          const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+          p.deferred[d] = row;
+          continue;
+        }
+        const unsigned int want = static_cast<unsigned int>(slot) + 1u;
+        for (int e = 0; e < kTinyGroups && g < 0; ++e) {
+          const unsigned int old = atomicCAS(&l_slot[e], 0u, want);
+          if (old == 0u) {
+#pragma unroll
+            for (int c = 0; c < kMaxKeys; ++c) if (c < p.n_keys) l_key[e][c] = kv[j][c];
+            l_knull[e] = knull[j];
+            __threadfence_block();
+            *reinterpret_cast<volatile unsigned int*>(&l_ready[e]) = 1u;
+            g = e;
+          } else if (old == want) {
+            g = e;
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < kLocalMaxAggs; ++a) {
+        if (a >= A) break;
+        const AggDev& ag = p.agg[a];
+        if ((vnull[j] >> a) & 1u) continue;
+        unsigned long long v = vv[j][a], cnt = 1;
+        if (ag.in_phys >= 0) {
+          if (ag.fn == SSB_AGG_COUNT) { cnt = p.merge ? v : 1ull; }
+          else if (ag.in_phys != ag.out_phys) v = convert_value(v, ag.in_phys, ag.out_phys);
+        }
+        if (g < 0) {   // more groups than local entries in this CTA: straight to the global table
+          apply(ag, slot, v, cnt);
+          if (ag.seen != nullptr) ag.seen[slot] = 1u;
+          continue;
+        }
+        unsigned long long* acc = &t_acc[(g * A + a) * T + tid];
+        if (ag.fn == SSB_AGG_COUNT) { *acc += cnt; }
+        else { *acc = combine(ag, *acc, v); t_seen[g][tid] |= 1u << a; }
+      }
+    }
+  }
+  __syncthreads();
+  // flush: warp w combines the T partials of the (group, aggregate) pairs w, w + T/32, ...
+  for (int ga = warp; ga < kTinyGroups * A; ga += T / 32) {
+    const int g = ga / A, a = ga - g * A;
+    if (l_slot[g] == 0u) continue;
+    const AggDev& ag = p.agg[a];
+    unsigned long long acc = 0;
+    bool has = false;
+    for (int t = lane; t < T; t += 32) {
+      const unsigned long long x = t_acc[ga * T + t];
+      if (ag.fn == SSB_AGG_COUNT) { acc += x; }
+      else if ((t_seen[g][t] >> a) & 1u) { acc = has ? combine(ag, acc, x) : x; has = true; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, acc, d);
+      const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
+      if (ag.fn == SSB_AGG_COUNT) acc += ov;
+      else if (oh) { acc = has ? combine(ag, acc, ov) : ov; has = true; }
+    }
+    if (lane != 0) continue;
+    const long long slot = static_cast<long long>(l_slot[g] - 1u);
+    if (ag.fn == SSB_AGG_COUNT) { if (acc) atomicAdd(&ag.acc[static_cast<unsigned long long>(slot) * ag.stride], acc); continue; }
+    if (!has) continue;
+    if (ag.seen != nullptr) ag.seen[slot] = 1u;
+    apply(ag, slot, acc, 0ull);
   }
 }
 
@@ -573,11 +818,12 @@ static unsigned long long identity_of(const ssb_agg_spec& a) {
 }
 
 static void free_table(ssb_group* g) {
-  cudaFree(g->rec); g->rec = nullptr; g->slot_key = nullptr;
-  cudaFree(g->slot_state); g->slot_state = nullptr;
-  for (int c = 0; c < kMaxKeys; ++c) { cudaFree(g->key_store[c]); g->key_store[c] = nullptr; }
-  cudaFree(g->key_store_null); g->key_store_null = nullptr;
-  for (int a = 0; a < kMaxAggs; ++a) { g->acc[a] = nullptr; cudaFree(g->seen[a]); g->seen[a] = nullptr; }
+  ssb_ctx* ctx = g->ctx;
+  tmp_free(ctx, g->rec); g->rec = nullptr; g->slot_key = nullptr;
+  tmp_free(ctx, g->slot_state); g->slot_state = nullptr;
+  for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, g->key_store[c]); g->key_store[c] = nullptr; }
+  tmp_free(ctx, g->key_store_null); g->key_store_null = nullptr;
+  for (int a = 0; a < kMaxAggs; ++a) { g->acc[a] = nullptr; tmp_free(ctx, g->seen[a]); g->seen[a] = nullptr; }
 }
 
 static unsigned fill_grid(ssb_ctx* ctx, unsigned long long n) {
@@ -596,7 +842,7 @@ static int alloc_table(ssb_group* g, unsigned long long capacity) {
   const unsigned long long stride = 1;
   g->stride = stride;
   const unsigned long long arrays = 1 + static_cast<unsigned long long>(g->n_aggs);
-  SSB_CUDA(ctx, cudaMalloc(&g->rec, total * arrays * 8));
+  SSB_CUDA(ctx, tmp_malloc(ctx, &g->rec, total * arrays * 8));
   SSB_CUDA(ctx, cudaMemsetAsync(g->rec, 0xff, total * 8, ctx->stream));   // keys = EMPTY
   g->slot_key = g->rec;
   for (int a = 0; a < g->n_aggs; ++a) {
@@ -610,19 +856,19 @@ static int alloc_table(ssb_group* g, unsigned long long capacity) {
     }
   }
   if (g->packed) {
-    SSB_CUDA(ctx, cudaMalloc(&g->slot_state, 2 * 4));
+    SSB_CUDA(ctx, tmp_malloc(ctx, &g->slot_state, 2 * 4));
     SSB_CUDA(ctx, cudaMemsetAsync(g->slot_state, 0, 2 * 4, ctx->stream));
   } else {
-    SSB_CUDA(ctx, cudaMalloc(&g->slot_state, total * 4));
+    SSB_CUDA(ctx, tmp_malloc(ctx, &g->slot_state, total * 4));
     SSB_CUDA(ctx, cudaMemsetAsync(g->slot_state, 0, total * 4, ctx->stream));
-    for (int c = 0; c < g->n_keys; ++c) SSB_CUDA(ctx, cudaMalloc(&g->key_store[c], total * 8));
-    SSB_CUDA(ctx, cudaMalloc(&g->key_store_null, total * 4));
+    for (int c = 0; c < g->n_keys; ++c) SSB_CUDA(ctx, tmp_malloc(ctx, &g->key_store[c], total * 8));
+    SSB_CUDA(ctx, tmp_malloc(ctx, &g->key_store_null, total * 4));
   }
   for (int a = 0; a < g->n_aggs; ++a) {
     // `seen` decides NULL-ness of SUM/MIN/MAX results; only inputs that can be NULL need it
     // (a ScalarAggregate over an empty input is NULL as well: aggregate_scalar.cc:40-90)
     if (g->aggs[a].fn != SSB_AGG_COUNT && (g->aggs[a].in_nullable || g->n_keys == 0)) {
-      SSB_CUDA(ctx, cudaMalloc(&g->seen[a], total * 4));
+      SSB_CUDA(ctx, tmp_malloc(ctx, &g->seen[a], total * 4));
       SSB_CUDA(ctx, cudaMemsetAsync(g->seen[a], 0, total * 4, ctx->stream));
     }
   }
@@ -693,8 +939,8 @@ static int grow_table(ssb_group* g, unsigned long long new_capacity) {
     if (n > 0 && g->n_keys > 0) rc = feed(g, keys.data(), aggs.data(), n, true, true);
   }
   cudaStreamSynchronize(ctx->stream);
-  for (int c = 0; c < kMaxKeys; ++c) { cudaFree(key_out[c]); cudaFree(key_nulls[c]); }
-  for (int a = 0; a < kMaxAggs; ++a) { cudaFree(agg_out[a]); cudaFree(agg_nulls[a]); }
+  for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, key_out[c]); tmp_free(ctx, key_nulls[c]); }
+  for (int a = 0; a < kMaxAggs; ++a) { tmp_free(ctx, agg_out[a]); tmp_free(ctx, agg_nulls[a]); }
   return rc;
 }
 
@@ -706,10 +952,10 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
   int rc = 0;
   for (int round = 0; round < 48 && remaining > 0; ++round) {
     if (g->deferred_cap < static_cast<size_t>(remaining)) {
-      cudaFree(g->deferred);
+      tmp_free(ctx, g->deferred);
       g->deferred = nullptr;
       g->deferred_cap = 0;
-      cudaError_t e = cudaMalloc(&g->deferred, static_cast<size_t>(remaining) * 8);
+      cudaError_t e = tmp_malloc(ctx, &g->deferred, static_cast<size_t>(remaining) * 8);
       if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "deferred row list"); break; }
       g->deferred_cap = static_cast<size_t>(remaining);
     }
@@ -735,7 +981,30 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
     // few groups so far (and few enough aggregates): CTA-private shared-memory tables
     const bool few = g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= (1 << 20) && g->h_counters[0] <= 256));
-    if (few) {
+    // single packed 8-byte key, COUNT or same-type 8-byte aggregates, no NULL bitmaps, no replay
+    static const bool tiny_enabled = getenv("SSB200_GROUP_TINY") == nullptr || atoi(getenv("SSB200_GROUP_TINY")) != 0;
+    static const bool fast_enabled = getenv("SSB200_GROUP_FAST") == nullptr || atoi(getenv("SSB200_GROUP_FAST")) != 0;
+    bool fast = fast_enabled && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1 &&
+                phys_width(p.key_phys[0]) == 8 && p.key_nulls[0] == nullptr;
+    for (int a = 0; fast && a < g->n_aggs; ++a) {
+      const AggDev& ag = p.agg[a];
+      if (ag.fn == SSB_AGG_COUNT) { if (ag.in_phys >= 0 && ag.in_nulls != nullptr) fast = false; continue; }
+      if (ag.in_nulls != nullptr || ag.in_phys != ag.out_phys || phys_width(ag.in_phys) != 8) fast = false;
+    }
+    if (fast) {
+      long long ctas = static_cast<long long>(ctx->num_sms) * 4;
+      if (ctas > div_up(remaining, 1024)) ctas = div_up(remaining, 1024);
+      group_update_fast_kernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
+    } else if (few && tiny_enabled && g->n_aggs >= 1 && (g->n_keys == 0 || g->h_counters[0] <= kTinyGroups)) {
+      const size_t smem = static_cast<size_t>(kTinyGroups) * g->n_aggs * kTinyThreads * 8;
+      cudaFuncSetAttribute(group_update_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      long long per_sm = static_cast<long long>((ctx->smem_per_sm - 8192) / (smem + 8192));
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 8) per_sm = 8;
+      long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
+      if (ctas > div_up(remaining, kTinyThreads * 2)) ctas = div_up(remaining, kTinyThreads * 2);
+      group_update_tiny_kernel<<<static_cast<unsigned>(ctas), kTinyThreads, smem, ctx->stream>>>(p);
+    } else if (few) {
       p.warp_combine = 0;
       long long ctas = static_cast<long long>(ctx->num_sms) * 4;
       if (ctas > div_up(remaining, 256)) ctas = div_up(remaining, 256);
@@ -750,11 +1019,11 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     const unsigned long long n_def = g->h_counters[1];
     if (n_def == 0) { remaining = 0; break; }
     long long* next = nullptr;
-    e = cudaMalloc(&next, n_def * 8);
+    e = tmp_malloc(ctx, &next, n_def * 8);
     if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "replay list"); break; }
     cudaMemcpyAsync(next, g->deferred, n_def * 8, cudaMemcpyDeviceToDevice, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(replay);
+    tmp_free(ctx, replay);
     replay = next;
     unsigned long long want = g->capacity * 2;
     while (want < 4 * (g->h_counters[0] + n_def)) want *= 2;
@@ -763,7 +1032,7 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
   }
   if (rc == 0 && remaining > 0) rc = fail(ctx, SSB_ERROR_UNKNOWN, "group-by table did not converge");
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(replay);
+  tmp_free(ctx, replay);
   return rc;
 }
 
@@ -779,6 +1048,8 @@ static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, 
     long long n = rows - offset;
     // The first megarow runs alone so that the group count seen so far can pick the strategy.
     if (!internal && g->rows_seen < (1 << 20) && n > (1 << 20)) n = 1 << 20;
+    // Slices bound the deferred-row list (one entry per row of a slice in the worst case).
+    if (n > kSliceRows) n = kSliceRows;
     ssb_column k2[kMaxKeys], v2[kMaxAggs];
     for (int c = 0; c < g->n_keys; ++c) {
       k2[c] = keys[c];
@@ -831,7 +1102,7 @@ int ssb_group_create(ssb_ctx* ctx, int32_t n_keys, const int32_t* key_types, con
   if (n_keys == 0) cap = 2;
   const unsigned long long want = expected_groups > 0 ? static_cast<unsigned long long>(expected_groups) * 2 : (1ull << 20);
   while (n_keys > 0 && cap < want) cap *= 2;
-  cudaError_t e = cudaMalloc(&g->counters, 16);
+  cudaError_t e = tmp_malloc(ctx, &g->counters, 16);
   if (e == cudaSuccess) e = cudaMallocHost(&g->h_counters, 16);
   if (e != cudaSuccess) { delete g; return cuda_fail(ctx, e, "group counters"); }
   cudaMemsetAsync(g->counters, 0, 16, ctx->stream);
@@ -843,14 +1114,15 @@ int ssb_group_create(ssb_ctx* ctx, int32_t n_keys, const int32_t* key_types, con
 
 void ssb_group_destroy(ssb_group* g) {
   if (!g) return;
-  cudaStreamSynchronize(g->ctx->stream);
+  ssb_ctx* ctx = g->ctx;
+  cudaStreamSynchronize(ctx->stream);
   free_table(g);
-  cudaFree(g->counters);
+  tmp_free(ctx, g->counters);
   cudaFreeHost(g->h_counters);
-  cudaFree(g->deferred);
-  cudaFree(g->block_counts);
-  for (int c = 0; c < kMaxKeys; ++c) { cudaFree(g->key_out[c]); cudaFree(g->key_out_nulls[c]); }
-  for (int a = 0; a < kMaxAggs; ++a) { cudaFree(g->agg_out[a]); cudaFree(g->agg_out_nulls[a]); }
+  tmp_free(ctx, g->deferred);
+  tmp_free(ctx, g->block_counts);
+  for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, g->key_out[c]); tmp_free(ctx, g->key_out_nulls[c]); }
+  for (int a = 0; a < kMaxAggs; ++a) { tmp_free(ctx, g->agg_out[a]); tmp_free(ctx, g->agg_out_nulls[a]); }
   delete g;
 }
 
@@ -871,15 +1143,15 @@ int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb
   if (g->n_keys == 0 && g->rows_seen == 0 && !g->merged_any) n = 1;   // ScalarAggregate: exactly one row
   const long long cap = n > 0 ? n : 1;
   if (g->out_capacity < cap) {
-    for (int c = 0; c < kMaxKeys; ++c) { cudaFree(g->key_out[c]); cudaFree(g->key_out_nulls[c]); g->key_out[c] = nullptr; g->key_out_nulls[c] = nullptr; }
-    for (int a = 0; a < kMaxAggs; ++a) { cudaFree(g->agg_out[a]); cudaFree(g->agg_out_nulls[a]); g->agg_out[a] = nullptr; g->agg_out_nulls[a] = nullptr; }
+    for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, g->key_out[c]); tmp_free(ctx, g->key_out_nulls[c]); g->key_out[c] = nullptr; g->key_out_nulls[c] = nullptr; }
+    for (int a = 0; a < kMaxAggs; ++a) { tmp_free(ctx, g->agg_out[a]); tmp_free(ctx, g->agg_out_nulls[a]); g->agg_out[a] = nullptr; g->agg_out_nulls[a] = nullptr; }
     for (int c = 0; c < g->n_keys; ++c) {
-      SSB_CUDA(ctx, cudaMalloc(&g->key_out[c], static_cast<size_t>(cap) * 8 + 128));
-      SSB_CUDA(ctx, cudaMalloc(&g->key_out_nulls[c], static_cast<size_t>(cap / 32 + 2) * 4 + 128));
+      SSB_CUDA(ctx, tmp_malloc(ctx, &g->key_out[c], static_cast<size_t>(cap) * 8 + 128));
+      SSB_CUDA(ctx, tmp_malloc(ctx, &g->key_out_nulls[c], static_cast<size_t>(cap / 32 + 2) * 4 + 128));
     }
     for (int a = 0; a < g->n_aggs; ++a) {
-      SSB_CUDA(ctx, cudaMalloc(&g->agg_out[a], static_cast<size_t>(cap) * 8 + 128));
-      SSB_CUDA(ctx, cudaMalloc(&g->agg_out_nulls[a], static_cast<size_t>(cap / 32 + 2) * 4 + 128));
+      SSB_CUDA(ctx, tmp_malloc(ctx, &g->agg_out[a], static_cast<size_t>(cap) * 8 + 128));
+      SSB_CUDA(ctx, tmp_malloc(ctx, &g->agg_out_nulls[a], static_cast<size_t>(cap / 32 + 2) * 4 + 128));
     }
     g->out_capacity = cap;
   }
@@ -891,7 +1163,7 @@ int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb
   f.total_slots = g->capacity + 2;
   unsigned grid = static_cast<unsigned>(ctx->num_sms) * 4;
   if (grid > f.total_slots / 256 + 1) grid = static_cast<unsigned>(f.total_slots / 256 + 1);
-  if (!g->block_counts) SSB_CUDA(ctx, cudaMalloc(&g->block_counts, static_cast<size_t>(ctx->num_sms) * 4 * 8));
+  if (!g->block_counts) SSB_CUDA(ctx, tmp_malloc(ctx, &g->block_counts, static_cast<size_t>(ctx->num_sms) * 4 * 8));
   f.block_counts = g->block_counts;
   for (int c = 0; c < g->n_keys; ++c) { f.key_out[c] = g->key_out[c]; f.key_out_nulls[c] = g->key_out_nulls[c]; }
   for (int a = 0; a < g->n_aggs; ++a) { f.agg_out[a] = g->agg_out[a]; f.agg_out_nulls[a] = g->agg_out_nulls[a]; }

@@ -33,8 +33,10 @@ struct JoinKeys {
 
 struct JoinTable {
   unsigned long long capacity;    // power of two
-  long long* slot_row;            // head build row + 1, 0 = empty
-  unsigned long long* slot_key;   // first key column's raw bits of the head row (fast reject)
+  // slot s = 16 bytes {first key column's raw bits of the head row, head build row + 1 (0 = empty)}:
+  // a probe step is one 128-bit load = one DRAM access (two separate arrays cost two, and the
+  // probe kernel is bound by random DRAM accesses: profiles/r1b_summary.md)
+  unsigned long long* slots;
   // multiset
   unsigned long long* run_start;  // [capacity] offset into run_rows
   unsigned int* run_count;        // [capacity]
@@ -77,14 +79,16 @@ __device__ __forceinline__ bool keys_equal(const JoinKeys& a, long long ra, cons
 }
 
 // Finds the slot holding the key of (keys,row); -1 when absent. `build` are the build keys.
-__device__ __forceinline__ long long lookup(const JoinTable& t, const JoinKeys& build, const JoinKeys& keys, long long row) {
+__device__ __forceinline__ long long lookup(const JoinTable& t, const JoinKeys& build, const JoinKeys& keys, long long row,
+                                            long long* head_row) {
   unsigned long long first = 0;
   const unsigned long long mask = t.capacity - 1;
   unsigned long long s = key_hash(keys, row, &first) & mask;
   for (;;) {
-    const long long head = t.slot_row[s];
+    const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(t.slots) + s);   // read-only during a probe
+    const long long head = static_cast<long long>(e.y);
     if (head == 0) return -1;
-    if (t.slot_key[s] == first && keys_equal(keys, row, build, head - 1)) return static_cast<long long>(s);
+    if (e.x == first && keys_equal(keys, row, build, head - 1)) { *head_row = head - 1; return static_cast<long long>(s); }
     s = (s + 1) & mask;
   }
 }
@@ -100,25 +104,27 @@ __global__ void __launch_bounds__(256) join_build_kernel(JoinTable t, JoinKeys b
     unsigned long long first = 0;
     unsigned long long s = key_hash(build, row, &first) & mask;
     for (;;) {
-      long long head = *reinterpret_cast<volatile long long*>(&t.slot_row[s]);
+      long long* slot_row = reinterpret_cast<long long*>(&t.slots[2 * s + 1]);
+      unsigned long long* slot_key = &t.slots[2 * s];
+      long long head = *reinterpret_cast<volatile long long*>(slot_row);
       if (head == 0) {
         // claim with a negative marker, publish the key word, then publish the row
-        const long long old = static_cast<long long>(atomicCAS(reinterpret_cast<unsigned long long*>(&t.slot_row[s]), 0ull,
+        const long long old = static_cast<long long>(atomicCAS(reinterpret_cast<unsigned long long*>(slot_row), 0ull,
                                                                static_cast<unsigned long long>(-(row + 1))));
         if (old == 0) {
-          t.slot_key[s] = first;
+          *slot_key = first;
           __threadfence();
-          atomicExch(reinterpret_cast<unsigned long long*>(&t.slot_row[s]), static_cast<unsigned long long>(row + 1));
+          atomicExch(reinterpret_cast<unsigned long long*>(slot_row), static_cast<unsigned long long>(row + 1));
           if (slot_of) slot_of[row] = static_cast<long long>(s);
           break;
         }
         head = old;
       }
-      while (head < 0) head = *reinterpret_cast<volatile long long*>(&t.slot_row[s]);   // being published
+      while (head < 0) head = *reinterpret_cast<volatile long long*>(slot_row);   // being published
       __threadfence();
-      if (*reinterpret_cast<volatile unsigned long long*>(&t.slot_key[s]) == first && keys_equal(build, row, build, head - 1)) {
+      if (*reinterpret_cast<volatile unsigned long long*>(slot_key) == first && keys_equal(build, row, build, head - 1)) {
         // same key: keep the smallest row as head (insertion order of the reference)
-        atomicMin(reinterpret_cast<long long*>(&t.slot_row[s]), row + 1);
+        atomicMin(slot_row, row + 1);
         if (slot_of) slot_of[row] = static_cast<long long>(s);
         break;
       }
@@ -155,9 +161,10 @@ __global__ void __launch_bounds__(256) join_count_kernel(JoinTable t, JoinKeys b
                                                           unsigned long long* __restrict__ counts) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
-    long long s = -1;
-    if (!key_has_null(probe, row)) s = lookup(t, build, probe, row);
-    slot_of[row] = s;
+    long long s = -1, head = -1;
+    if (!key_has_null(probe, row)) s = lookup(t, build, probe, row, &head);
+    // UNIQUE keys: remember the matching build row itself, the emit pass then never touches the table
+    slot_of[row] = unique ? (s >= 0 ? head : -1) : s;
     unsigned long long c = 0;
     if (s >= 0) c = unique ? 1ull : t.run_count[s];
     else if (left_outer) c = 1ull;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(256) join_emit_kernel(JoinTable t, long long r
       if (next != off) { lhs_out[off] = row; rhs_out[off] = -1; }
     } else if (unique) {
       lhs_out[off] = row;
-      rhs_out[off] = t.slot_row[s] - 1;
+      rhs_out[off] = s;   // the count pass stored the build row
     } else {
       const unsigned long long start = t.run_start[s];
       const unsigned int cnt = t.run_count[s];
@@ -189,6 +196,111 @@ __global__ void __launch_bounds__(256) join_emit_kernel(JoinTable t, long long r
   }
 }
 
+
+// UNIQUE keys: a lhs row yields at most one pair, so the probe is a stream compaction and runs
+// as ONE pass: a CTA takes the next 1024-row tile (atomic ticket), every thread looks up four
+// rows (the four table probes are in flight together), the matches are ranked in row order with
+// ballots, the tile's output offset comes from the decoupled look-back over the tiles' match
+// counts (device_utils.h), and the pairs are written at their final positions. LEFT_OUTER emits
+// every lhs row, so positions are the row numbers and no prefix is needed.
+// aux: [0] ticket, [1] total pairs, [2 ..] one status word per tile.
+enum { kProbeThreads = 256, kProbeRows = 4, kProbeTile = kProbeThreads * kProbeRows };
+
+__global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTable t, JoinKeys build, JoinKeys probe,
+                                                                           long long rows, int left_outer,
+                                                                           long long* __restrict__ lhs_out,
+                                                                           long long* __restrict__ rhs_out,
+                                                                           unsigned long long* __restrict__ aux) {
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned int wcnt[kProbeRows][kProbeThreads / 32];
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long tiles = (rows + kProbeTile - 1) / kProbeTile;
+  for (;;) {
+    __syncthreads();   // s_tile / wcnt / s_base of the previous tile are no longer read
+    if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(aux), 1u);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= tiles) return;
+    const long long r0 = tile * kProbeTile + tid;
+    long long head[kProbeRows];
+    unsigned int pos[kProbeRows];
+    unsigned long long first[kProbeRows], slot[kProbeRows];
+    ulonglong2 ent[kProbeRows];
+    bool live[kProbeRows];
+    const unsigned long long mask = t.capacity - 1;
+    // hash and first table probe of all four rows before any of them is looked at
+#pragma unroll
+    for (int j = 0; j < kProbeRows; ++j) {
+      const long long row = r0 + j * kProbeThreads;
+      live[j] = row < rows && !key_has_null(probe, row);
+      first[j] = 0;
+      slot[j] = live[j] ? (key_hash(probe, row, &first[j]) & mask) : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < kProbeRows; ++j) ent[j] = __ldg(reinterpret_cast<const ulonglong2*>(t.slots) + slot[j]);
+#pragma unroll
+    for (int j = 0; j < kProbeRows; ++j) {
+      const long long row = r0 + j * kProbeThreads;
+      head[j] = -1;
+      if (!live[j]) continue;
+      ulonglong2 e = ent[j];
+      unsigned long long sl = slot[j];
+      for (;;) {
+        const long long h = static_cast<long long>(e.y);
+        if (h == 0) break;
+        if (e.x == first[j] && keys_equal(probe, row, build, h - 1)) { head[j] = h - 1; break; }
+        sl = (sl + 1) & mask;
+        e = __ldg(reinterpret_cast<const ulonglong2*>(t.slots) + sl);
+      }
+    }
+    if (left_outer) {
+#pragma unroll
+      for (int j = 0; j < kProbeRows; ++j) {
+        const long long row = r0 + j * kProbeThreads;
+        if (row < rows) { lhs_out[row] = row; rhs_out[row] = head[j]; }
+      }
+      if (tile == tiles - 1 && tid == 0) aux[1] = static_cast<unsigned long long>(rows);
+      continue;
+    }
+    // rank of every match inside the tile, in row order: round j before round j + 1, then thread order
+#pragma unroll
+    for (int j = 0; j < kProbeRows; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, head[j] >= 0);
+      pos[j] = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) wcnt[j][warp] = __popc(m);
+    }
+    __syncthreads();
+    unsigned int before[kProbeRows], total = 0;
+#pragma unroll
+    for (int j = 0; j < kProbeRows; ++j) {
+      before[j] = total;
+#pragma unroll
+      for (int w = 0; w < kProbeThreads / 32; ++w) {
+        const unsigned int c = wcnt[j][w];
+        if (w < warp) before[j] += c;
+        total += c;
+      }
+    }
+    if (warp == 0) {
+      const unsigned long long excl = tile_prefix_warp(aux + 2, static_cast<unsigned long long>(tile), total, lane);
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == tiles - 1) aux[1] = excl + total;
+      }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+#pragma unroll
+    for (int j = 0; j < kProbeRows; ++j) {
+      if (head[j] >= 0) {
+        const unsigned long long o = base + before[j] + pos[j];
+        lhs_out[o] = r0 + j * kProbeThreads;
+        rhs_out[o] = head[j];
+      }
+    }
+  }
+}
 
 // Part id per row for the multi-GPU redistribution: the high bits of the key hash scaled to
 // [0, n_parts) (the table slot uses the low bits, so parts and slots stay independent); rows
@@ -234,14 +346,14 @@ extern "C" {
 
 void ssb_join_destroy(ssb_join* j) {
   if (!j) return;
-  cudaStreamSynchronize(j->ctx->stream);
-  cudaFree(j->table.slot_row);
-  cudaFree(j->table.slot_key);
-  cudaFree(j->table.run_start);
-  cudaFree(j->table.run_count);
-  cudaFree(j->table.run_rows);
-  cudaFree(j->lhs_out);
-  cudaFree(j->rhs_out);
+  ssb_ctx* ctx = j->ctx;
+  cudaStreamSynchronize(ctx->stream);
+  tmp_free(ctx, j->table.slots);
+  tmp_free(ctx, j->table.run_start);
+  tmp_free(ctx, j->table.run_count);
+  tmp_free(ctx, j->table.run_rows);
+  tmp_free(ctx, j->lhs_out);
+  tmp_free(ctx, j->rhs_out);
   delete j;
 }
 
@@ -272,14 +384,13 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
   while (cap < static_cast<unsigned long long>(rows) * 2) cap *= 2;
   j->table.capacity = cap;
   TimedRegion timed(ctx);
-  cudaError_t e = cudaMalloc(&j->table.slot_row, cap * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&j->table.slot_key, cap * 8);
+  cudaError_t e = tmp_malloc(ctx, &j->table.slots, cap * 16);
   if (e != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e, "join table"); }
-  cudaMemsetAsync(j->table.slot_row, 0, cap * 8, ctx->stream);
+  cudaMemsetAsync(j->table.slots, 0, cap * 16, ctx->stream);
   long long* slot_of = nullptr;
   const bool multi = uniqueness != SSB_KEYS_UNIQUE;
   if (multi && rows > 0) {
-    e = cudaMalloc(&slot_of, static_cast<size_t>(rows) * 8);
+    e = tmp_malloc(ctx, &slot_of, static_cast<size_t>(rows) * 8);
     if (e != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e, "join build scratch"); }
   }
   if (rows > 0) {
@@ -288,19 +399,19 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
   }
   int rc = 0;
   if (multi) {
-    e = cudaMalloc(&j->table.run_start, cap * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&j->table.run_count, cap * 4);
-    if (e != cudaSuccess) { cudaFree(slot_of); ssb_join_destroy(j); return cuda_fail(ctx, e, "join runs"); }
+    e = tmp_malloc(ctx, &j->table.run_start, cap * 8);
+    if (e == cudaSuccess) e = tmp_malloc(ctx, &j->table.run_count, cap * 4);
+    if (e != cudaSuccess) { tmp_free(ctx, slot_of); ssb_join_destroy(j); return cuda_fail(ctx, e, "join runs"); }
     cudaMemsetAsync(j->table.run_count, 0, cap * 4, ctx->stream);
     if (rows > 0) {
       unsigned long long *k0 = nullptr, *k1 = nullptr;
       long long *v0 = nullptr, *v1 = nullptr;
-      e = cudaMalloc(&k0, static_cast<size_t>(rows) * 8);
-      if (e == cudaSuccess) e = cudaMalloc(&k1, static_cast<size_t>(rows) * 8);
-      if (e == cudaSuccess) e = cudaMalloc(&v0, static_cast<size_t>(rows) * 8);
-      if (e == cudaSuccess) e = cudaMalloc(&v1, static_cast<size_t>(rows) * 8);
+      e = tmp_malloc(ctx, &k0, static_cast<size_t>(rows) * 8);
+      if (e == cudaSuccess) e = tmp_malloc(ctx, &k1, static_cast<size_t>(rows) * 8);
+      if (e == cudaSuccess) e = tmp_malloc(ctx, &v0, static_cast<size_t>(rows) * 8);
+      if (e == cudaSuccess) e = tmp_malloc(ctx, &v1, static_cast<size_t>(rows) * 8);
       if (e != cudaSuccess) {
-        cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(slot_of);
+        tmp_free(ctx, k0); tmp_free(ctx, k1); tmp_free(ctx, v0); tmp_free(ctx, v1); tmp_free(ctx, slot_of);
         ssb_join_destroy(j);
         return cuda_fail(ctx, e, "join sort scratch");
       }
@@ -317,12 +428,12 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
       }
       j->table.run_rows = v0;
       cudaStreamSynchronize(ctx->stream);
-      cudaFree(k0); cudaFree(k1); cudaFree(v1);
+      tmp_free(ctx, k0); tmp_free(ctx, k1); tmp_free(ctx, v1);
     }
   }
   e = cudaGetLastError();
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(slot_of);
+  tmp_free(ctx, slot_of);
   if (rc == 0 && e != cudaSuccess) rc = cuda_fail(ctx, e, "join build");
   if (rc) { ssb_join_destroy(j); return rc; }
   *out = j;
@@ -346,13 +457,39 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
     if (a != b && !ints) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "probe key types differ from the build keys");
   }
   TimedRegion timed(ctx);
+  if (j->uniqueness == SSB_KEYS_UNIQUE) {
+    // single pass: pairs <= rows, so the result buffers are sized by the lhs
+    const long long tiles = div_up(rows, kProbeTile);
+    unsigned long long* aux = nullptr;
+    tmp_free(ctx, j->lhs_out); tmp_free(ctx, j->rhs_out);
+    j->lhs_out = j->rhs_out = nullptr;
+    cudaError_t e = tmp_malloc(ctx, &aux, static_cast<size_t>(tiles + 2) * 8);
+    if (e == cudaSuccess) e = tmp_malloc(ctx, &j->lhs_out, static_cast<size_t>(rows + 1) * 8);
+    if (e == cudaSuccess) e = tmp_malloc(ctx, &j->rhs_out, static_cast<size_t>(rows + 1) * 8);
+    if (e != cudaSuccess) { tmp_free(ctx, aux); return cuda_fail(ctx, e, "join probe buffers"); }
+    cudaMemsetAsync(aux, 0, static_cast<size_t>(tiles + 2) * 8, ctx->stream);
+    long long grid = static_cast<long long>(ctx->num_sms) * 4;
+    if (grid > tiles) grid = tiles;
+    join_probe_unique_kernel<<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+        j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux);
+    ++ctx->launches;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_count, aux + 1, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    tmp_free(ctx, aux);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "join probe");
+    *n_pairs = *ctx->h_count;
+    *d_lhs_rows = reinterpret_cast<const int64_t*>(j->lhs_out);
+    *d_rhs_rows = reinterpret_cast<const int64_t*>(j->rhs_out);
+    return 0;
+  }
   long long* slot_of = nullptr;
   unsigned long long* counts = nullptr;
   unsigned long long* d_total = nullptr;
-  cudaError_t e = cudaMalloc(&slot_of, static_cast<size_t>(rows) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&counts, static_cast<size_t>(rows + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_total, 8);
-  if (e != cudaSuccess) { cudaFree(slot_of); cudaFree(counts); cudaFree(d_total); return cuda_fail(ctx, e, "join probe scratch"); }
+  cudaError_t e = tmp_malloc(ctx, &slot_of, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &counts, static_cast<size_t>(rows + 1) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &d_total, 8);
+  if (e != cudaSuccess) { tmp_free(ctx, slot_of); tmp_free(ctx, counts); tmp_free(ctx, d_total); return cuda_fail(ctx, e, "join probe scratch"); }
   const int unique = j->uniqueness == SSB_KEYS_UNIQUE ? 1 : 0;
   join_count_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, j->build_keys, probe, rows, unique,
                                                                        join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, slot_of, counts);
@@ -364,10 +501,10 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
     cudaMemcpyAsync(ctx->h_count, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     total = static_cast<unsigned long long>(*ctx->h_count);
-    cudaFree(j->lhs_out); cudaFree(j->rhs_out);
+    tmp_free(ctx, j->lhs_out); tmp_free(ctx, j->rhs_out);
     j->lhs_out = j->rhs_out = nullptr;
-    e = cudaMalloc(&j->lhs_out, (total + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&j->rhs_out, (total + 1) * 8);
+    e = tmp_malloc(ctx, &j->lhs_out, (total + 1) * 8);
+    if (e == cudaSuccess) e = tmp_malloc(ctx, &j->rhs_out, (total + 1) * 8);
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "join result");
   }
   if (rc == 0 && total > 0) {
@@ -377,7 +514,7 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "join probe");
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(slot_of); cudaFree(counts); cudaFree(d_total);
+  tmp_free(ctx, slot_of); tmp_free(ctx, counts); tmp_free(ctx, d_total);
   if (rc) return rc;
   *n_pairs = static_cast<int64_t>(total);
   *d_lhs_rows = reinterpret_cast<const int64_t*>(j->lhs_out);
@@ -398,11 +535,11 @@ int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int
   TimedRegion timed(ctx);
   unsigned long long *k0 = nullptr, *k1 = nullptr, *d_counts = nullptr;
   long long* v0 = nullptr;
-  cudaError_t e = cudaMalloc(&k0, static_cast<size_t>(rows) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&k1, static_cast<size_t>(rows) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&v0, static_cast<size_t>(rows) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_counts, 256 * 8);
-  if (e != cudaSuccess) { cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(d_counts); return cuda_fail(ctx, e, "partition scratch"); }
+  cudaError_t e = tmp_malloc(ctx, &k0, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &k1, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &v0, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &d_counts, 256 * 8);
+  if (e != cudaSuccess) { tmp_free(ctx, k0); tmp_free(ctx, k1); tmp_free(ctx, v0); tmp_free(ctx, d_counts); return cuda_fail(ctx, e, "partition scratch"); }
   cudaMemsetAsync(d_counts, 0, 256 * 8, ctx->stream);
   part_id_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(jk, rows, static_cast<unsigned>(n_parts),
                                                                     static_cast<unsigned>(null_part), k0, v0, d_counts);
@@ -423,7 +560,7 @@ int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "partition");
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(d_counts);
+  tmp_free(ctx, k0); tmp_free(ctx, k1); tmp_free(ctx, v0); tmp_free(ctx, d_counts);
   if (rc) return rc;
   for (int p = 0; p < n_parts; ++p) h_counts[p] = static_cast<int64_t>(h[p]);
   return 0;

@@ -79,7 +79,7 @@ int exclusive_scan_u64(ssb_ctx* ctx, unsigned long long* d_data, unsigned long l
   }
   const unsigned long long nb = (n + kScanTile - 1) / kScanTile;
   unsigned long long* sums = nullptr;
-  SSB_CUDA(ctx, cudaMalloc(&sums, (nb + 1) * 8));
+  SSB_CUDA(ctx, tmp_malloc(ctx, &sums, (nb + 1) * 8));
   scan_reduce_kernel<<<static_cast<unsigned>(nb), kScanThreads, 0, ctx->stream>>>(d_data, n, sums);
   ++ctx->launches;
   int rc = 0;
@@ -96,7 +96,7 @@ int exclusive_scan_u64(ssb_ctx* ctx, unsigned long long* d_data, unsigned long l
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "scan");
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(sums);
+  tmp_free(ctx, sums);
   return rc;
 }
 
@@ -114,17 +114,6 @@ int exclusive_scan_u64(ssb_ctx* ctx, unsigned long long* d_data, unsigned long l
 //      once per pass (32 B per pair).
 enum { kSortThreads = 256, kSortItemsPerThread = 16, kSortTile = kSortThreads * kSortItemsPerThread,
        kRadixBits = 8, kRadix = 1 << kRadixBits, kMaxPasses = 8 };
-
-static constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 struct PassList {
   int n;
@@ -192,54 +181,80 @@ __global__ void __launch_bounds__(kRadix) radix_base_kernel(unsigned long long* 
 }
 
 // aux layout: [0] ticket (u32 in a u64 word), [1 .. 1 + tiles*256) status words of the pass.
-__global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
-    const unsigned long long* __restrict__ keys_in, const long long* __restrict__ vals_in,
-    unsigned long long* __restrict__ keys_out, long long* __restrict__ vals_out, unsigned long long n, int shift,
-    const unsigned long long* __restrict__ gbase, unsigned long long* __restrict__ aux) {
+// FULL: every tile of the launch is complete (n is a multiple of the tile), no row guards.
+struct SweepSmem {
+  unsigned long long stage[kSortTile];        // 32 KB: the tile ordered by digit (keys, then values)
+  unsigned long long gadj[kRadix];            // global position of local position 0 of a digit run
+  unsigned int lstart[kRadix];                // first local position of a digit
+  unsigned short wcnt[kSortThreads / 32][kRadix];   // per-warp digit counts, then exclusive bases
+  unsigned char dig[kSortTile];               // digit of the staged element
+  unsigned int wsum[kSortThreads / 32];
+  unsigned int s_tile;
+};
+
+template <bool FULL>
+__device__ __forceinline__ void onesweep_tile(
+    SweepSmem& sm, const unsigned long long tile, const unsigned long long* __restrict__ keys_in,
+    const long long* __restrict__ vals_in, unsigned long long* __restrict__ keys_out, long long* __restrict__ vals_out,
+    unsigned long long n, int shift, const unsigned long long* __restrict__ gbase, unsigned long long* __restrict__ aux) {
   constexpr int NW = kSortThreads / 32;
   constexpr int PER_WARP = kSortTile / NW;
   constexpr int ROUNDS = PER_WARP / 32;
-  __shared__ unsigned long long stage[kSortTile];        // 32 KB: the tile ordered by digit (keys, then values)
-  __shared__ unsigned long long gadj[kRadix];            // global position of local position 0 of a digit run
-  __shared__ unsigned int lstart[kRadix];                // first local position of a digit
-  __shared__ unsigned short wcnt[NW][kRadix];            // per-warp digit counts, then exclusive bases
-  __shared__ unsigned char dig[kSortTile];               // digit of the staged element
-  __shared__ unsigned int wsum[NW];
-  __shared__ unsigned int s_tile;
+  constexpr int HALF = ROUNDS / 2;
+  constexpr int LOOK = 4;                                // predecessors inspected per look-back step
+  unsigned long long (&stage)[kSortTile] = sm.stage;
+  unsigned long long (&gadj)[kRadix] = sm.gadj;
+  unsigned int (&lstart)[kRadix] = sm.lstart;
+  unsigned short (&wcnt)[NW][kRadix] = sm.wcnt;
+  unsigned char (&dig)[kSortTile] = sm.dig;
+  unsigned int (&wsum)[NW] = sm.wsum;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(reinterpret_cast<unsigned int*>(aux), 1u);
-  for (int d = tid; d < kRadix * NW; d += kSortThreads) (&wcnt[0][0])[d] = 0;
-  __syncthreads();
-  const unsigned long long tile = s_tile;
   unsigned long long* status = aux + 1;
   const unsigned long long tile0 = tile * kSortTile;
   const unsigned long long warp0 = tile0 + static_cast<unsigned long long>(warp) * PER_WARP + lane;
   const unsigned long long left = n - tile0;
-  const int cnt_tile = left < static_cast<unsigned long long>(kSortTile) ? static_cast<int>(left) : kSortTile;
+  const int cnt_tile = (FULL || left >= static_cast<unsigned long long>(kSortTile)) ? kSortTile : static_cast<int>(left);
 
   unsigned long long k[ROUNDS];
   unsigned short pos[ROUNDS];
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     const unsigned long long i = warp0 + r * 32;
-    k[r] = i < n ? keys_in[i] : ~0ull;
+    k[r] = (FULL || i < n) ? keys_in[i] : ~0ull;
   }
   const unsigned lt = (1u << lane) - 1u;
+  // ranks: the warp matches run back to back (their latency overlaps), then the per-warp digit
+  // counters are walked in row order
 #pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
-    const bool live = warp0 + r * 32 < n;
-    const unsigned d = static_cast<unsigned>((k[r] >> shift) & (kRadix - 1));
-    const unsigned active = __ballot_sync(0xffffffffu, live);
-    unsigned peers = 0;
-    if (live) peers = __match_any_sync(active, d);
-    unsigned before = 0;
-    if (live) before = wcnt[warp][d];
-    __syncwarp();
-    if (live) {
-      pos[r] = static_cast<unsigned short>(before + __popc(peers & lt));
-      if ((__ffs(peers) - 1) == lane) wcnt[warp][d] = static_cast<unsigned short>(before + __popc(peers));
+  for (int h = 0; h < 2; ++h) {
+    unsigned peers[HALF];
+#pragma unroll
+    for (int q = 0; q < HALF; ++q) {
+      const int r = h * HALF + q;
+      const unsigned d = static_cast<unsigned>((k[r] >> shift) & (kRadix - 1));
+      if (FULL) {
+        peers[q] = __match_any_sync(0xffffffffu, d);
+      } else {
+        const bool live = warp0 + r * 32 < n;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        peers[q] = 0;
+        if (live) peers[q] = __match_any_sync(active, d);
+      }
     }
-    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < HALF; ++q) {
+      const int r = h * HALF + q;
+      const unsigned d = static_cast<unsigned>((k[r] >> shift) & (kRadix - 1));
+      const bool live = FULL || peers[q] != 0u;
+      unsigned before = 0;
+      if (live) before = wcnt[warp][d];
+      __syncwarp();
+      if (live) {
+        pos[r] = static_cast<unsigned short>(before + __popc(peers[q] & lt));
+        if ((__ffs(peers[q]) - 1) == lane) wcnt[warp][d] = static_cast<unsigned short>(before + __popc(peers[q]));
+      }
+      __syncwarp();
+    }
   }
   __syncthreads();
   // thread d owns digit d: scan over the warps, publish the tile's count, scan over the digits
@@ -264,7 +279,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
   // stage the keys ordered by digit
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
-    if (warp0 + r * 32 < n) {
+    if (FULL || warp0 + r * 32 < n) {
       const unsigned d = static_cast<unsigned>((k[r] >> shift) & (kRadix - 1));
       const unsigned int q = lstart[d] + wcnt[warp][d] + pos[r];
       pos[r] = static_cast<unsigned short>(q);
@@ -278,20 +293,35 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
     const unsigned long long i = warp0 + r * 32;
-    v[r] = i < n ? vals_in[i] : 0;
+    v[r] = (FULL || i < n) ? vals_in[i] : 0;
   }
   {
+    // decoupled look-back, LOOK predecessors per step: their status words are fetched together
+    // and consumed in order up to the first one that is not published yet
     const int d = tid;
     unsigned long long excl = 0;
     if (tile > 0) {
-      unsigned long long t = tile - 1;
+      unsigned long long t = tile;   // predecessors t-1, t-2, ... are still to be accounted for
       for (;;) {
-        const unsigned long long w = ld_relaxed_u64(&status[t * kRadix + d]);
-        const unsigned long long f = w & kFlagMask;
-        if (f == 0) continue;                  // tile t has a ticket, so it is running: wait
-        excl += w & ~kFlagMask;
-        if (f == kFlagPrefix) break;
-        --t;                                   // tile 0 always publishes a prefix
+        unsigned long long w[LOOK];
+#pragma unroll
+        for (int q = 0; q < LOOK; ++q) {
+          w[q] = kFlagPrefix;        // before tile 0: an empty prefix
+          if (static_cast<unsigned long long>(q) < t) w[q] = ld_relaxed_u64(&status[(t - 1 - q) * kRadix + d]);
+        }
+        bool done = false;
+        int used = 0;
+#pragma unroll
+        for (int q = 0; q < LOOK; ++q) {
+          if (done || used != q) continue;
+          const unsigned long long f = w[q] & kFlagMask;
+          if (f == 0) continue;      // not published yet: poll again from here
+          excl += w[q] & ~kFlagMask;
+          ++used;
+          if (f == kFlagPrefix) done = true;
+        }
+        if (done) break;
+        t -= static_cast<unsigned long long>(used);
       }
       st_relaxed_u64(&status[tile * kRadix + d], kFlagPrefix | (excl + total));
     }
@@ -302,10 +332,28 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < ROUNDS; ++r) {
-    if (warp0 + r * 32 < n) stage[pos[r]] = static_cast<unsigned long long>(v[r]);
+    if (FULL || warp0 + r * 32 < n) stage[pos[r]] = static_cast<unsigned long long>(v[r]);
   }
   __syncthreads();
   for (int i = tid; i < cnt_tile; i += kSortThreads) vals_out[gadj[dig[i]] + i] = static_cast<long long>(stage[i]);
+}
+
+__global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(
+    const unsigned long long* __restrict__ keys_in, const long long* __restrict__ vals_in,
+    unsigned long long* __restrict__ keys_out, long long* __restrict__ vals_out, unsigned long long n, int shift,
+    const unsigned long long* __restrict__ gbase, unsigned long long* __restrict__ aux) {
+  __shared__ SweepSmem sm;
+  const int tid = threadIdx.x;
+  if (tid == 0) sm.s_tile = atomicAdd(reinterpret_cast<unsigned int*>(aux), 1u);
+  for (int d = tid; d < kRadix * (kSortThreads / 32); d += kSortThreads) (&sm.wcnt[0][0])[d] = 0;
+  __syncthreads();
+  const unsigned long long tile = sm.s_tile;
+  // complete tiles run without row guards (CTA-uniform choice)
+  if (n - tile * kSortTile >= static_cast<unsigned long long>(kSortTile)) {
+    onesweep_tile<true>(sm, tile, keys_in, vals_in, keys_out, vals_out, n, shift, gbase, aux);
+  } else {
+    onesweep_tile<false>(sm, tile, keys_in, vals_in, keys_out, vals_out, n, shift, gbase, aux);
+  }
 }
 
 // Sorts (keys, vals) by bits [begin_bit, end_bit) of keys; stable. The result ends in
@@ -319,7 +367,7 @@ int radix_sort_pairs(ssb_ctx* ctx, unsigned long long** keys, long long** vals, 
   const size_t hist_words = static_cast<size_t>(kMaxPasses) * kRadix;
   const size_t aux_words = 1 + hist_words + 1 + static_cast<size_t>(tiles) * kRadix;
   unsigned long long* aux = nullptr;
-  SSB_CUDA(ctx, cudaMalloc(&aux, aux_words * 8));
+  SSB_CUDA(ctx, tmp_malloc(ctx, &aux, aux_words * 8));
   unsigned long long* d_mask = aux;
   unsigned long long* ghist = aux + 1;
   unsigned long long* pass_aux = aux + 1 + hist_words;
@@ -332,7 +380,7 @@ int radix_sort_pairs(ssb_ctx* ctx, unsigned long long** keys, long long** vals, 
     e = cudaMemcpyAsync(ctx->h_count, d_mask, 8, cudaMemcpyDeviceToHost, ctx->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) { cudaFree(aux); return cuda_fail(ctx, e, "radix sort setup"); }
+  if (e != cudaSuccess) { tmp_free(ctx, aux); return cuda_fail(ctx, e, "radix sort setup"); }
   const unsigned long long varying = static_cast<unsigned long long>(*ctx->h_count);
   PassList pl;
   pl.n = 0;
@@ -357,7 +405,7 @@ int radix_sort_pairs(ssb_ctx* ctx, unsigned long long** keys, long long** vals, 
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "radix sort");
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(aux);
+  tmp_free(ctx, aux);
   return rc;
 }
 
@@ -463,9 +511,9 @@ int ssb_sort_permutation(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, c
   if (n_keys == 0 || rows == 1) { SSB_CUDA(ctx, cudaGetLastError()); return 0; }
   unsigned long long *k0 = nullptr, *k1 = nullptr;
   long long* p1 = nullptr;
-  SSB_CUDA(ctx, cudaMalloc(&k0, static_cast<size_t>(rows) * 8));
-  SSB_CUDA(ctx, cudaMalloc(&k1, static_cast<size_t>(rows) * 8));
-  SSB_CUDA(ctx, cudaMalloc(&p1, static_cast<size_t>(rows) * 8));
+  SSB_CUDA(ctx, tmp_malloc(ctx, &k0, static_cast<size_t>(rows) * 8));
+  SSB_CUDA(ctx, tmp_malloc(ctx, &k1, static_cast<size_t>(rows) * 8));
+  SSB_CUDA(ctx, tmp_malloc(ctx, &p1, static_cast<size_t>(rows) * 8));
   long long* pa = perm;
   long long* pb = p1;
   int rc = 0;
@@ -486,9 +534,9 @@ int ssb_sort_permutation(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, c
     cudaMemcpyAsync(perm, pa, static_cast<size_t>(rows) * 8, cudaMemcpyDeviceToDevice, ctx->stream);
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(k0);
-  cudaFree(k1);
-  cudaFree(pa == perm ? pb : pa);
+  tmp_free(ctx, k0);
+  tmp_free(ctx, k1);
+  tmp_free(ctx, pa == perm ? pb : pa);
   if (rc == 0) SSB_CUDA(ctx, cudaGetLastError());
   return rc;
 }

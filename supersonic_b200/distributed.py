@@ -40,6 +40,61 @@ def allgather_ragged(tensor, group=None):
     return [o[:s] for o, s in zip(out, sizes)]
 
 
+class _DevArray(object):
+    """Zero-copy view of device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TYPESTR = {1: "<i4", 2: "<i8", 3: "<i8", 4: "<i8", 5: "<f8", 6: "|u1", 8: "<i4", 9: "<f4", 10: "<i4", 13: "<i4"}
+
+
+def merge_group_partials(ctx, g, key_types, agg_types, group=None):
+    """The exchange step of a row-range sharded GroupAggregate / ScalarAggregate:
+    every rank finalizes its table `g` into dense partial columns, the partials are all-gathered
+    (NCCL) and the other ranks' rows are added with ssb_group_merge; after the call every rank
+    holds the whole-table result. NOT NULL keys and aggregates. Returns (n_groups, key columns,
+    aggregate columns) as ctypes Column arrays owned by `g`."""
+    import torch
+    import torch.distributed as dist
+    from supersonic_b200 import capi
+    lib = ctx.lib
+
+    def cols(n):
+        return (capi.Column * max(1, n))()
+
+    n = C.c_int64()
+    ko, ao = cols(len(key_types)), cols(len(agg_types))
+    ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return n.value, ko, ao
+    rank = dist.get_rank(group)
+
+    def view(col, dtype):
+        return torch.as_tensor(_DevArray(col.data, n.value, _TYPESTR[dtype]), device="cuda") if n.value else \
+            torch.empty(0, dtype=_torch_dtype(dtype), device="cuda")
+
+    gk = [allgather_ragged(view(ko[i], t), group) for i, t in enumerate(key_types)]
+    ga = [allgather_ragged(view(ao[i], t), group) for i, t in enumerate(agg_types)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        if r == rank:
+            continue
+        rows = (gk[0][r] if key_types else ga[0][r]).numel()
+        if rows == 0:
+            continue
+        kc, ac = cols(len(key_types)), cols(len(agg_types))
+        for i, t in enumerate(key_types):
+            kc[i].data, kc[i].nulls, kc[i].dtype = gk[i][r].data_ptr(), None, t
+        for i, t in enumerate(agg_types):
+            ac[i].data, ac[i].nulls, ac[i].dtype = ga[i][r].data_ptr(), None, t
+        ctx.check(lib.ssb_group_merge(g, rows, kc, ac))
+    ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+    return n.value, ko, ao
+
+
 class ShardedGroupAggregate(object):
     """GroupAggregate over a row-range sharded table: local GPU aggregation, all-gather of the
     dense partial tables, merge on every rank. Single-key, non-nullable INT64 keys (the C3

@@ -859,23 +859,56 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
   // 4 and prefers deeper staging; predicate-free programs gain 24 % from the fourth CTA.
   int ctas = predicate >= 0 ? 3 : 4;
   if (const char* env = getenv("SSB200_EXPR_CTAS")) { const int c = atoi(env); if (c >= 1 && c <= 8) ctas = c; }
-  const uint32_t budget = static_cast<uint32_t>((ctx->smem_per_sm - ctas * ctx->smem_reserved) / ctas);
+  // Plan search. The default (768-row tiles, `ctas` resident CTAs) is kept whenever it leaves
+  // three input stages in flight. Wide plans (many input / output columns: the Q1 shape has
+  // seven of each) would otherwise end with one CTA per SM and a single stage, i.e. loads,
+  // evaluation and stores in lock step; for them smaller tiles and fewer CTAs are tried and the
+  // plan with the most bytes in flight per SM (stages >= 2 first) wins.
+  struct Try { int variant, ctas; };
+  std::vector<Try> tries;
+  tries.push_back({variant, ctas});
+  if (!getenv("SSB200_EXPR_VARIANT")) {
+    const int half = 8;   // 96 x 4 = 384-row tiles
+    for (int c = ctas; c >= 1; --c) { if (c != ctas) tries.push_back({variant, c}); tries.push_back({half, c}); }
+    tries.push_back({0, 1});
+  }
   ssb_program* sp = nullptr;
   std::string err;
   int rc = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    sp = new ssb_program;
-    sp->ctx = ctx;
-    const Variant& var = kVariants[variant];
-    rc = compile_program(nodes, n_nodes, n_inputs, input_types, input_nullable, outputs, n_outputs, predicate,
-                         var.threads * var.rows_per_thread, budget, static_cast<uint32_t>(ctx->smem_optin),
-                         &sp->prog, &err);
-    sp->prog.variant = variant;
-    if (rc == 0) break;
-    delete sp;
-    sp = nullptr;
-    if (rc != SSB_ERROR_NOT_IMPLEMENTED || variant == 0) break;
-    variant = 0;   // smallest tile: least shared memory per column
+  long long best_score = -1;
+  for (size_t i = 0; i < tries.size(); ++i) {
+    const Variant& var = kVariants[tries[i].variant];
+    const int c = tries[i].ctas;
+    const uint32_t budget = static_cast<uint32_t>((ctx->smem_per_sm - c * ctx->smem_reserved) / c);
+    ssb_program* cand = new ssb_program;
+    cand->ctx = ctx;
+    std::string e2;
+    const int r2 = compile_program(nodes, n_nodes, n_inputs, input_types, input_nullable, outputs, n_outputs, predicate,
+                                   var.threads * var.rows_per_thread, budget, static_cast<uint32_t>(ctx->smem_optin),
+                                   &cand->prog, &e2);
+    if (r2 != 0) {
+      delete cand;
+      if (sp == nullptr) { rc = r2; err = e2; }
+      if (r2 != SSB_ERROR_NOT_IMPLEMENTED) break;   // a bind error: no other tile will change it
+      continue;
+    }
+    cand->prog.variant = tries[i].variant;
+    const int stages = cand->prog.params.stages;
+    const bool fits = cand->prog.smem_bytes <= budget;
+    const int resident = fits ? c : static_cast<int>((ctx->smem_per_sm) / (cand->prog.smem_bytes + ctx->smem_reserved));
+    // bytes of input in flight per SM, with a heavy penalty for a single stage
+    long long score = static_cast<long long>(stages >= 2 ? stages : 0) * (resident < 1 ? 1 : resident) * cand->prog.params.tile * 16 +
+                      (resident < 1 ? 1 : resident);   // equal bytes in flight: more resident CTAs (more warps) win
+    if (i == 0 && stages >= 3 && fits) score = 1LL << 40;   // the measured default
+    if (score > best_score) {
+      delete sp;
+      sp = cand;
+      best_score = score;
+      rc = 0;
+    } else {
+      delete cand;
+    }
+    if (best_score >= (1LL << 40)) break;
   }
   if (rc) return fail(ctx, rc, err);
   const Variant& var = kVariants[sp->prog.variant];

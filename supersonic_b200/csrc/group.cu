@@ -27,7 +27,8 @@
 namespace ssb {
 
 enum { kMaxKeys = 8, kMaxAggs = 16, kProbeLimit = 96 };
-static constexpr long long kSliceRows = 1LL << 26;   // rows per launch of the update kernels (multiple of 32)
+static constexpr long long kSliceRows = 1LL << 26;
+static constexpr long long kProbeRowsFirst = 1LL << 17;   // the first slice runs alone: its group count picks the kernel   // rows per launch of the update kernels (multiple of 32)
 static constexpr unsigned long long kEmptyKey = ~0ull;
 
 struct AggDev {
@@ -511,20 +512,34 @@ __device__ __forceinline__ unsigned long long identity_dev(const AggDev& ag) {
   return 0ull;
 }
 
+// AggDev::pad carries a pre-decoded accumulate code for this kernel (set by the host).
+enum { TA_COUNT = 0, TA_SUM_F64 = 1, TA_SUM_U64 = 2, TA_OTHER = 3 };
+
+// FAST: every key and input column is 8 bytes wide without a NULL bitmap, no merge, no replay
+// list -- the loads are plain 8-byte loads and no per-aggregate NULL bookkeeping is needed.
+template <bool FAST>
 __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const __grid_constant__ GroupParams p) {
   constexpr int T = kTinyThreads;
   extern __shared__ unsigned long long t_acc[];                  // [kTinyGroups * n_aggs][T]
   __shared__ unsigned int t_seen[kTinyGroups][T];                // bit a: this thread saw a value of aggregate a
   __shared__ unsigned long long l_key[kTinyGroups][kMaxKeys];
+  __shared__ unsigned long long l_fp[kTinyGroups];               // fingerprint of the entry's key
   __shared__ unsigned int l_knull[kTinyGroups];
   __shared__ unsigned int l_slot[kTinyGroups];                   // global slot + 1, 0 = free; claimed in order
-  __shared__ unsigned int l_ready[kTinyGroups];                  // key values of the entry are published
+  __shared__ unsigned int l_ready;                               // bit e: key values of entry e are published
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = p.n_aggs;
+  const int NK = p.n_keys;
   for (int i = tid; i < kTinyGroups * A * T; i += T) t_acc[i] = identity_dev(p.agg[(i / T) % A]);
   for (int i = tid; i < kTinyGroups * T; i += T) (&t_seen[0][0])[i] = 0u;
-  if (tid < kTinyGroups) { l_slot[tid] = 0u; l_ready[tid] = 0u; }
+  if (tid < kTinyGroups) l_slot[tid] = 0u;
+  if (tid == 0) l_ready = 0u;
   __syncthreads();
+  // register copy of the published fingerprints, refreshed when the ready mask changes
+  unsigned int my_ready = 0;
+  unsigned long long my_fp[kTinyGroups];
+#pragma unroll
+  for (int e = 0; e < kTinyGroups; ++e) my_fp[e] = 0;
   // R rows per thread and iteration; all key and value loads of the R rows are issued before the
   // first one is used, so a thread pays one HBM round trip per iteration, not two per row
   constexpr int R = 2;
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const long long i = base + static_cast<long long>(j) * T;
-      rows_[j] = i < p.rows ? (p.row_index ? p.row_index[i] : i) : -1;
+      rows_[j] = i < p.rows ? ((!FAST && p.row_index) ? p.row_index[i] : i) : -1;
     }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -545,31 +560,44 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
 #pragma unroll
       for (int c = 0; c < kMaxKeys; ++c) {
         kv[j][c] = 0;
-        if (c < p.n_keys && rows_[j] >= 0) {
-          if (bit_at(p.key_nulls[c], rows_[j])) knull[j] |= 1u << c; else kv[j][c] = load_raw(p.key_data[c], p.key_phys[c], rows_[j]);
+        if (c < NK && rows_[j] >= 0) {
+          if (FAST) kv[j][c] = static_cast<const unsigned long long*>(p.key_data[c])[rows_[j]];
+          else if (bit_at(p.key_nulls[c], rows_[j])) knull[j] |= 1u << c;
+          else kv[j][c] = load_raw(p.key_data[c], p.key_phys[c], rows_[j]);
         }
       }
 #pragma unroll
       for (int a = 0; a < kLocalMaxAggs; ++a) {
         vv[j][a] = 0;
         if (a < A && p.agg[a].in_phys >= 0 && rows_[j] >= 0) {
-          if (bit_at(p.agg[a].in_nulls, rows_[j])) vnull[j] |= 1u << a; else vv[j][a] = load_raw(p.agg[a].in_data, p.agg[a].in_phys, rows_[j]);
+          if (FAST) vv[j][a] = static_cast<const unsigned long long*>(p.agg[a].in_data)[rows_[j]];
+          else if (bit_at(p.agg[a].in_nulls, rows_[j])) vnull[j] |= 1u << a;
+          else vv[j][a] = load_raw(p.agg[a].in_data, p.agg[a].in_phys, rows_[j]);
         }
       }
+    }
+    const unsigned int ready_now = *reinterpret_cast<volatile unsigned int*>(&l_ready);
+    if (ready_now != my_ready) {
+      my_ready = ready_now;
+#pragma unroll
+      for (int e = 0; e < kTinyGroups; ++e) if ((my_ready >> e) & 1u) my_fp[e] = *reinterpret_cast<volatile unsigned long long*>(&l_fp[e]);
     }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const long long row = rows_[j];
       if (row < 0) continue;
+      unsigned long long fp = 0x9E3779B97F4A7C15ull + knull[j];
+#pragma unroll
+      for (int c = 0; c < kMaxKeys; ++c) if (c < NK) fp = (fp ^ kv[j][c]) * 0xff51afd7ed558ccdULL + c;
       int g = -1;
 #pragma unroll
-      for (int e = 0; e < kTinyGroups; ++e) {
-        if (g < 0 && *reinterpret_cast<volatile unsigned int*>(&l_ready[e]) != 0u) {
-          bool same = l_knull[e] == knull[j];
+      for (int e = 0; e < kTinyGroups; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
+      if (g >= 0) {
+        // equal fingerprints: confirm on the key values (a different key restarts below)
+        bool same = l_knull[g] == knull[j];
 #pragma unroll
-          for (int c = 0; c < kMaxKeys; ++c) if (c < p.n_keys) same = same && l_key[e][c] == kv[j][c];
-          if (same) g = e;
-        }
+        for (int c = 0; c < kMaxKeys; ++c) if (c < NK) same = same && l_key[g][c] == kv[j][c];
+        if (!same) g = -1;
       }
       long long slot = -1;
       if (g < 0) {
@@ -585,23 +613,25 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
           const unsigned int old = atomicCAS(&l_slot[e], 0u, want);
           if (old == 0u) {
 #pragma unroll
-            for (int c = 0; c < kMaxKeys; ++c) if (c < p.n_keys) l_key[e][c] = kv[j][c];
+            for (int c = 0; c < kMaxKeys; ++c) if (c < NK) l_key[e][c] = kv[j][c];
             l_knull[e] = knull[j];
+            l_fp[e] = fp;
             __threadfence_block();
-            *reinterpret_cast<volatile unsigned int*>(&l_ready[e]) = 1u;
+            atomicOr(&l_ready, 1u << e);
             g = e;
           } else if (old == want) {
             g = e;
           }
         }
       }
+      if (g >= 0 && FAST) t_seen[g][tid] = 0xffffffffu;   // NOT NULL inputs: every aggregate saw this row
 #pragma unroll
       for (int a = 0; a < kLocalMaxAggs; ++a) {
         if (a >= A) break;
         const AggDev& ag = p.agg[a];
-        if ((vnull[j] >> a) & 1u) continue;
+        if (!FAST && ((vnull[j] >> a) & 1u)) continue;
         unsigned long long v = vv[j][a], cnt = 1;
-        if (ag.in_phys >= 0) {
+        if (!FAST && ag.in_phys >= 0) {
           if (ag.fn == SSB_AGG_COUNT) { cnt = p.merge ? v : 1ull; }
           else if (ag.in_phys != ag.out_phys) v = convert_value(v, ag.in_phys, ag.out_phys);
         }
@@ -611,8 +641,13 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
           continue;
         }
         unsigned long long* acc = &t_acc[(g * A + a) * T + tid];
-        if (ag.fn == SSB_AGG_COUNT) { *acc += cnt; }
-        else { *acc = combine(ag, *acc, v); t_seen[g][tid] |= 1u << a; }
+        switch (ag.pad) {
+          case TA_COUNT: *acc += cnt; break;
+          case TA_SUM_F64: *acc = Codec<double>::enc(Codec<double>::dec(*acc) + Codec<double>::dec(v)); break;
+          case TA_SUM_U64: *acc += v; break;
+          default: *acc = combine(ag, *acc, v); break;
+        }
+        if (!FAST && ag.pad != TA_COUNT) t_seen[g][tid] |= 1u << a;
       }
     }
   }
@@ -980,7 +1015,7 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     p.warp_combine = 0;   // superseded by the shared-memory kernel for few groups
     cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
     // few groups so far (and few enough aggregates): CTA-private shared-memory tables
-    const bool few = g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= (1 << 20) && g->h_counters[0] <= 256));
+    const bool few = g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst && g->h_counters[0] <= 256));
     // single packed 8-byte key, COUNT or same-type 8-byte aggregates, no NULL bitmaps, no replay
     static const bool tiny_enabled = getenv("SSB200_GROUP_TINY") == nullptr || atoi(getenv("SSB200_GROUP_TINY")) != 0;
     static const bool fast_enabled = getenv("SSB200_GROUP_FAST") == nullptr || atoi(getenv("SSB200_GROUP_FAST")) != 0;
@@ -997,13 +1032,23 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
       group_update_fast_kernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
     } else if (few && tiny_enabled && g->n_aggs >= 1 && (g->n_keys == 0 || g->h_counters[0] <= kTinyGroups)) {
       const size_t smem = static_cast<size_t>(kTinyGroups) * g->n_aggs * kTinyThreads * 8;
-      cudaFuncSetAttribute(group_update_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      bool tfast = !merge && replay == nullptr;
+      for (int c = 0; tfast && c < g->n_keys; ++c) tfast = phys_width(p.key_phys[c]) == 8 && p.key_nulls[c] == nullptr;
+      for (int a = 0; a < g->n_aggs; ++a) {
+        AggDev& ag = p.agg[a];
+        ag.pad = ag.fn == SSB_AGG_COUNT ? TA_COUNT
+                 : (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) ? TA_SUM_F64
+                 : (ag.fn == SSB_AGG_SUM && (ag.out_phys == T_I64 || ag.out_phys == T_U64)) ? TA_SUM_U64 : TA_OTHER;
+        if (ag.in_phys >= 0 && (ag.in_nulls != nullptr || phys_width(ag.in_phys) != 8 || (ag.fn != SSB_AGG_COUNT && ag.in_phys != ag.out_phys))) tfast = false;
+      }
+      auto kernel = tfast ? group_update_tiny_kernel<true> : group_update_tiny_kernel<false>;
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       long long per_sm = static_cast<long long>((ctx->smem_per_sm - 8192) / (smem + 8192));
       if (per_sm < 1) per_sm = 1;
       if (per_sm > 8) per_sm = 8;
       long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
       if (ctas > div_up(remaining, kTinyThreads * 2)) ctas = div_up(remaining, kTinyThreads * 2);
-      group_update_tiny_kernel<<<static_cast<unsigned>(ctas), kTinyThreads, smem, ctx->stream>>>(p);
+      kernel<<<static_cast<unsigned>(ctas), kTinyThreads, smem, ctx->stream>>>(p);
     } else if (few) {
       p.warp_combine = 0;
       long long ctas = static_cast<long long>(ctx->num_sms) * 4;
@@ -1047,7 +1092,7 @@ static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, 
   while (offset < rows) {
     long long n = rows - offset;
     // The first megarow runs alone so that the group count seen so far can pick the strategy.
-    if (!internal && g->rows_seen < (1 << 20) && n > (1 << 20)) n = 1 << 20;
+    if (!internal && g->rows_seen < kProbeRowsFirst && n > kProbeRowsFirst) n = kProbeRowsFirst;
     // Slices bound the deferred-row list (one entry per row of a slice in the worst case).
     if (n > kSliceRows) n = kSliceRows;
     ssb_column k2[kMaxKeys], v2[kMaxAggs];

@@ -208,7 +208,8 @@ def q1_aux(capi, ctx, rank, world, rows, dist, torch):
               n(capi.OP_MUL, F64, [9, 10]),                                            # 11: charge
               n(capi.OP_CONST, I64, [], i64=2450),                                     # 12
               n(capi.OP_LE, BOOL, [6, 12])]                                            # 13: ship <= D
-    prog = capi.Program(ctx, nodes, types, [0] * 7, [4, 5, 0, 1, 2, 9, 11], predicate=13)
+    # outputs: the keys rf, ls, then the aggregate inputs qty, price, disc_price, charge, disc
+    prog = capi.Program(ctx, nodes, types, [0] * 7, [4, 5, 0, 1, 9, 11, 2], predicate=13)
     out_types = [I64, I64, F64, F64, F64, F64, F64]
     d_out = [ctx.malloc(rows * 8 + 256) for _ in out_types]
     d_count = ctx.malloc(8)
@@ -219,35 +220,54 @@ def q1_aux(capi, ctx, rank, world, rows, dist, torch):
     kt, kn = (C.c_int32 * 2)(I64, I64), (C.c_int32 * 2)(0, 0)
     state = {}
 
-    def once():
-        t0 = time.perf_counter()
-        kept = prog.run_sync([(p_, None, t) for p_, t in zip(d_in, types)], rows,
-                             [(p_, None, t) for p_, t in zip(d_out, out_types)])
-        state["expr_seconds"] = time.perf_counter() - t0
+    in_cols = [(p_, None, t) for p_, t in zip(d_in, types)]
+
+    def make_group():
         g = C.c_void_p()
         ctx.check(lib.ssb_group_create(ctx.h, 2, kt, kn, 6, specs, 6, C.byref(g)))
-        vals = [(d_out[2], None, F64), (d_out[3], None, F64), (d_out[5], None, F64), (d_out[6], None, F64), (d_out[4], None, F64)]
-        ctx.check(lib.ssb_group_update(g, _cols(capi, [(d_out[0], None, I64), (d_out[1], None, I64)]), _cols(capi, vals), kept))
+        return g
+
+    def finish(g, tag):
         ng, ko, ao = merge_group_partials(ctx, g, [I64, I64], [F64] * 5 + [capi.UINT64])
         cnt = np.zeros(ng, dtype=np.uint64)
         ctx.d2h(cnt, ao[5].data)
-        state["groups"], state["counted"], state["kept"] = ng, int(cnt.sum()), kept
+        sums = np.zeros(ng, dtype=np.float64)
+        ctx.d2h(sums, ao[3].data)
+        state["groups"], state[tag] = ng, (int(cnt.sum()), float(sums.sum()))
         lib.ssb_group_destroy(g)
 
+    def once():
+        # the product path: one call; the library runs Filter -> Compute and the aggregation slice by slice
+        g = make_group()
+        ctx.check(lib.ssb_group_update_program(g, prog.h, _cols(capi, in_cols), rows))
+        finish(g, "fused")
+
+    def once_unfused():
+        # for comparison: materialise the whole filtered / computed table, then aggregate it
+        kept = prog.run_sync(in_cols, rows, [(p_, None, t) for p_, t in zip(d_out, out_types)])
+        g = make_group()
+        vals = [(d_out[j], None, F64) for j in range(2, 7)]
+        ctx.check(lib.ssb_group_update(g, _cols(capi, [(d_out[0], None, I64), (d_out[1], None, I64)]), _cols(capi, vals), kept))
+        state["kept"] = kept
+        finish(g, "unfused")
+
+    unfused_best, _ = _timed(ctx, world, dist, torch, once_unfused, repeats=1)
     best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
     kept_all = state["kept"]
     if world > 1:
         t = torch.tensor([float(kept_all)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         kept_all = int(t.item())
-    assert state["counted"] == kept_all, "COUNT(*) over all groups must equal the rows the filter kept"
+    assert state["fused"][0] == kept_all, "COUNT(*) over all groups must equal the rows the filter kept"
+    assert state["fused"] == state["unfused"], "fused and unfused plans must agree bit for bit (dyadic payloads)"
     prog.close()
     for ptr in d_in + d_out + [d_count]:
         ctx.free(ptr)
     return {"metric": "rows/sec, Q1 shape: Filter(ship<=D) -> Compute(disc_price, charge) -> GroupAggregate({rf,ls}; 5xSUM, COUNT) (BASELINE config 5 shape)",
             "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(state["groups"]),
-            "seconds": best, "filter_compute_seconds": state["expr_seconds"], "selectivity": kept_all / float(world * rows),
-            "algorithmic_gbs_per_gpu": rows * 56 / best / 1e9, "check": "sum of COUNT(*) == rows kept by the filter",
+            "seconds": best, "whole_table_two_step_seconds": unfused_best, "selectivity": kept_all / float(world * rows),
+            "kernels": "ssb_group_update_program: per 64M-row slice expr_kernel (filter+compute) then group_update_tiny_kernel",
+            "algorithmic_gbs_per_gpu": rows * 56 / best / 1e9, "check": "sum of COUNT(*) == rows kept by the filter; sliced == whole-table two-step (COUNT and SUM(charge) bit-exact)",
             "exchange": "all-gather of 6-group partial tables + ssb_group_merge" if world > 1 else "none"}
 
 
@@ -334,6 +354,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = capi.Context(local)

@@ -210,6 +210,15 @@ void ssb_group_destroy(ssb_group* g);
 /* Accumulates `rows` rows; may be called repeatedly (row order across calls = call order). */
 int ssb_group_update(ssb_group* g, const ssb_column* keys, const ssb_column* values,
                      int64_t rows);
+/* GroupAggregate fused with its row-wise child (Filter / Compute over the scan): `prog` is
+ * evaluated per row inside the aggregation kernel and nothing is materialised in between. The
+ * program's outputs must be, in order, the key columns of `g` followed by its aggregate input
+ * columns (ssb_agg_spec.input indexes the latter); its predicate, if any, filters the rows.
+ * Same result as ssb_program_run followed by ssb_group_update (GroupAggregateCursor pulling
+ * from FilterCursor / ComputeCursor: aggregate_groups.cc:332-433, filter.cc:96-230,
+ * compute.cc:49-56). Plans with many groups are materialised slice by slice internally.
+ * Returns 104 when a signaling expression failed. Synchronises. */
+int ssb_group_update_program(ssb_group* g, ssb_program* prog, const ssb_column* inputs, int64_t rows);
 /* Compacts the table into dense result columns owned by `g` (valid until destroy or the
  * next update). Synchronises. A NULL key is a group of its own (row_hash_set.cc:81-90);
  * an aggregate over only-NULL inputs is NULL (column_aggregator.cc:108-125). */
@@ -252,6 +261,11 @@ int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int
  * 200-286). dst.nulls may be NULL when neither src.nulls nor negative indices occur. */
 int ssb_gather(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64_t n,
                const ssb_column* dst);
+
+/* dst[idx[i]] = src[i] for i < n (idx[i] < 0: skipped; indices must be distinct). The inverse of
+ * ssb_gather; the sharded UNIQUE join uses it to put returned matches back at their lhs rows
+ * (the reference's ResultCursor writes matches in lhs order as it goes: hash_join.cc:793-831). */
+int ssb_scatter(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64_t n, const ssb_column* dst);
 
 /* ------------------------------------------------------------------ sort */
 /* Replaces SortPermutation / SortTypedColumn (cursor/core/sort.cc:150-322,781-805): writes

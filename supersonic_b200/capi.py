@@ -100,6 +100,7 @@ def load():
                                        C.POINTER(P)]),
         "ssb_group_destroy": (None, [P]),
         "ssb_group_update": (C.c_int, [P, C.POINTER(Column), C.POINTER(Column), I64]),
+        "ssb_group_update_program": (C.c_int, [P, P, C.POINTER(Column), I64]),
         "ssb_group_finalize": (C.c_int, [P, C.POINTER(I64), C.POINTER(Column), C.POINTER(Column)]),
         "ssb_group_merge": (C.c_int, [P, I64, C.POINTER(Column), C.POINTER(Column)]),
         "ssb_join_build": (C.c_int, [P, I32, C.POINTER(Column), I64, I32, C.POINTER(P)]),
@@ -107,6 +108,7 @@ def load():
         "ssb_join_probe": (C.c_int, [P, C.POINTER(Column), I64, I32, C.POINTER(I64), C.POINTER(P), C.POINTER(P)]),
         "ssb_partition_rows": (C.c_int, [P, I32, C.POINTER(Column), I64, I32, I32, P, C.POINTER(I64)]),
         "ssb_gather": (C.c_int, [P, C.POINTER(Column), P, I64, C.POINTER(Column)]),
+        "ssb_scatter": (C.c_int, [P, C.POINTER(Column), P, I64, C.POINTER(Column)]),
         "ssb_sort_permutation": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I32), I64, P]),
     }
     for name, (res, args) in sig.items():

@@ -469,6 +469,8 @@ class Compiler {
         default: break;
       }
     }
+    // the unfused list (fast codes of the +0 / +1 forms only) is what group.cu's row evaluator runs
+    prog_->generic.assign(p.insn, p.insn + p.n_insn);
     // Peephole: a clean LOAD followed by a fast binary op becomes one two-operand instruction
     // (the left operand is read from its slot instead of the accumulator).
     int w = 0;

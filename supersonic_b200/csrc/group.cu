@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.h"
+#include "program.h"
 
 namespace ssb {
 
@@ -98,13 +99,12 @@ __device__ __forceinline__ unsigned long long convert_value(unsigned long long v
 
 // ---- slot lookup ---------------------------------------------------------------------------
 // Returns the slot of the row's key, inserting it if new; -1 when the probe limit is hit.
-__device__ __forceinline__ long long find_slot_packed(const GroupParams& p, long long row) {
+__device__ __forceinline__ long long find_slot_packed_kv(const GroupParams& p, bool isnull, unsigned long long key) {
   if (p.n_keys == 0) return 0;
-  if (bit_at(p.key_nulls[0], row)) {
+  if (isnull) {
     if (atomicExch(&p.slot_state[1], 1u) == 0u) atomicAdd(p.n_groups, 1ull);
     return static_cast<long long>(p.capacity + 1);
   }
-  const unsigned long long key = load_raw(p.key_data[0], p.key_phys[0], row);
   if (key == kEmptyKey) {
     if (atomicExch(&p.slot_state[0], 1u) == 0u) atomicAdd(p.n_groups, 1ull);
     return static_cast<long long>(p.capacity);
@@ -123,15 +123,17 @@ __device__ __forceinline__ long long find_slot_packed(const GroupParams& p, long
   }
   return -1;
 }
+__device__ __forceinline__ long long find_slot_packed(const GroupParams& p, long long row) {
+  if (p.n_keys == 0) return 0;
+  const bool isn = bit_at(p.key_nulls[0], row);
+  return find_slot_packed_kv(p, isn, isn ? 0ull : load_raw(p.key_data[0], p.key_phys[0], row));
+}
 
-__device__ __forceinline__ long long find_slot_generic(const GroupParams& p, long long row) {
-  unsigned long long kv[kMaxKeys];
-  uint32_t knull = 0;
+// kv[c] = raw value of key column c (0 where NULL), knull bit c = column c is NULL.
+__device__ __forceinline__ long long find_slot_generic_kv(const GroupParams& p, const unsigned long long* kv, uint32_t knull) {
   unsigned long long h = 0x9E3779B97F4A7C15ull;
   for (int c = 0; c < p.n_keys; ++c) {
-    const bool isn = bit_at(p.key_nulls[c], row);
-    kv[c] = isn ? 0ull : load_raw(p.key_data[c], p.key_phys[c], row);
-    if (isn) knull |= 1u << c;
+    const bool isn = (knull >> c) & 1u;
     h = mix64(h ^ (kv[c] + (isn ? 0xdeadbabeull : 0ull))) + c;
   }
   const unsigned long long mask = p.capacity - 1;
@@ -160,6 +162,16 @@ __device__ __forceinline__ long long find_slot_generic(const GroupParams& p, lon
     s = (s + 1) & mask;
   }
   return -1;
+}
+__device__ __forceinline__ long long find_slot_generic(const GroupParams& p, long long row) {
+  unsigned long long kv[kMaxKeys];
+  uint32_t knull = 0;
+  for (int c = 0; c < p.n_keys; ++c) {
+    const bool isn = bit_at(p.key_nulls[c], row);
+    kv[c] = isn ? 0ull : load_raw(p.key_data[c], p.key_phys[c], row);
+    if (isn) knull |= 1u << c;
+  }
+  return find_slot_generic_kv(p, kv, knull);
 }
 
 // ---- accumulation -------------------------------------------------------------------------
@@ -679,6 +691,329 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
   }
 }
 
+// ---- fused Filter -> Compute -> GroupAggregate ------------------------------------------------
+// The row-wise child of a GroupAggregate (cursor/core/aggregate_groups.cc:332-433 pulling blocks
+// from ComputeCursor / FilterCursor, compute.cc:49-56, filter.cc:96-230) is evaluated inside the
+// aggregation kernel: nothing is materialised between the two operators, the plan reads its
+// input columns once (the Q1 shape: 56 B per row instead of 56 + 55 written + 55 read again).
+// Every thread runs the expression program of its own R rows on the accumulator machine of
+// ops.h (the program is warp-uniform, so the dispatch does not diverge); operand slots, i.e.
+// the row's input values and temporaries, are thread-private words in shared memory
+// ([slot][row][thread]: conflict-free). The outputs of the program are the group-by key columns
+// followed by the aggregate inputs; rows failing the predicate are skipped; accumulation is the
+// tiny-group scheme above (private accumulators per thread, global table as overflow).
+enum { kRowMaxIn = 12, kRowMaxOut = 15, kRowMaxInsn = 64, kRowMaxImm = 16 };
+
+struct RowProg {
+  int32_t n_insn, n_in, n_tmp, n_out;
+  Insn insn[kRowMaxInsn];
+  unsigned long long imm[kRowMaxImm];
+  const void* in_data[kRowMaxIn];
+  const uint32_t* in_nulls[kRowMaxIn];
+  int32_t in_phys[kRowMaxIn];
+  int32_t agg_out[kMaxAggs];      // program output feeding aggregate a, -1: COUNT(*)
+  int32_t has_pred;
+  int32_t* d_fail;
+};
+
+__global__ void __launch_bounds__(kTinyThreads) group_update_rows_kernel(const __grid_constant__ GroupParams p,
+                                                                          const __grid_constant__ RowProg rp) {
+  constexpr int T = kTinyThreads;
+  constexpr int R = 2;
+  extern __shared__ unsigned long long dyn[];
+  const int A = p.n_aggs;
+  const int NK = p.n_keys;
+  const int n_slots = rp.n_in + rp.n_tmp;
+  unsigned long long* t_acc = dyn;                                         // [kTinyGroups * A][T]
+  unsigned long long* s_val = t_acc + kTinyGroups * A * T;                  // [n_slots][R][T]
+  unsigned long long* s_out = s_val + n_slots * R * T;                      // [n_out][R][T]
+  unsigned int* s_nul = reinterpret_cast<unsigned int*>(s_out + rp.n_out * R * T);   // [n_slots][T], bit r
+  unsigned int* s_outn = s_nul + n_slots * T;                               // [n_out][T]
+  __shared__ unsigned int t_seen[kTinyGroups][T];
+  __shared__ unsigned long long l_key[kTinyGroups][kMaxKeys];
+  __shared__ unsigned long long l_fp[kTinyGroups];
+  __shared__ unsigned int l_knull[kTinyGroups];
+  __shared__ unsigned int l_slot[kTinyGroups];
+  __shared__ unsigned int l_ready;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kTinyGroups * A * T; i += T) t_acc[i] = identity_dev(p.agg[(i / T) % A]);
+  for (int i = tid; i < kTinyGroups * T; i += T) (&t_seen[0][0])[i] = 0u;
+  if (tid < kTinyGroups) l_slot[tid] = 0u;
+  if (tid == 0) l_ready = 0u;
+  __syncthreads();
+  unsigned int my_ready = 0;
+  unsigned long long my_fp[kTinyGroups];
+#pragma unroll
+  for (int e = 0; e < kTinyGroups; ++e) my_fp[e] = 0;
+  uint32_t fail = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * T * R;
+  for (long long base = static_cast<long long>(blockIdx.x) * T * R + tid; base < p.rows; base += stride) {
+    long long rows_[R];
+    uint32_t live = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long i = base + static_cast<long long>(j) * T;
+      rows_[j] = i < p.rows ? (p.row_index ? p.row_index[i] : i) : -1;
+      if (rows_[j] >= 0) live |= 1u << j;
+    }
+    // ---- all input loads of the R rows first, then into the thread's operand slots
+    {
+      unsigned long long iv[kRowMaxIn][R];
+      uint32_t inul[kRowMaxIn];
+#pragma unroll
+      for (int c = 0; c < kRowMaxIn; ++c) {
+        inul[c] = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          iv[c][j] = 0;
+          if (c < rp.n_in && rows_[j] >= 0) {
+            if (bit_at(rp.in_nulls[c], rows_[j])) inul[c] |= 1u << j; else iv[c][j] = load_raw(rp.in_data[c], rp.in_phys[c], rows_[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kRowMaxIn; ++c) {
+        if (c < rp.n_in) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) s_val[(c * R + j) * T + tid] = iv[c][j];
+          s_nul[c * T + tid] = inul[c];
+        }
+      }
+    }
+    // ---- the row program (K_LOAD / K_STORE / K_ALU* / K_PRED / K_OUT)
+    u64 acc[R];
+    uint32_t accn = 0, pass = live;
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0;
+    for (int pc = 0; pc < rp.n_insn; ++pc) {
+      const Insn& in = rp.insn[pc];
+      const uint32_t code = in.code;
+      if (code != C_GENERIC) {
+        // pre-decoded cases (operands cannot be NULL): the hot (op, type) pairs of ops.h
+        if (code >= C_BIN_BASE && code < C_BIN_END) {
+          const int rel = static_cast<int>(code) - C_BIN_BASE;
+          const int type_base = rel / 28, op = (rel % 28) / 4;
+          u64 y[R];
+          if (rel & 1) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) y[j] = rp.imm[in.a];
+          } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) y[j] = s_val[(in.a * R + j) * T + tid];
+          }
+#define SSB_ROW_BIN(TYPE)                                                                   \
+  _Pragma("unroll") for (int j = 0; j < R; ++j) {                                           \
+    const TYPE a_ = Codec<TYPE>::dec(acc[j]), b_ = Codec<TYPE>::dec(y[j]);                  \
+    u64 r_;                                                                                 \
+    switch (op) {                                                                           \
+      case B_ADD: r_ = Codec<TYPE>::enc(Arith<TYPE>::add(a_, b_)); break;                   \
+      case B_SUB: r_ = Codec<TYPE>::enc(Arith<TYPE>::sub(a_, b_)); break;                   \
+      case B_SUBR: r_ = Codec<TYPE>::enc(Arith<TYPE>::sub(b_, a_)); break;                  \
+      case B_MUL: r_ = Codec<TYPE>::enc(Arith<TYPE>::mul(a_, b_)); break;                   \
+      case B_LT: r_ = ((a_ < b_) != neg) ? 1u : 0u; break;                                  \
+      case B_GT: r_ = ((b_ < a_) != neg) ? 1u : 0u; break;                                  \
+      default: r_ = ((a_ == b_) != neg) ? 1u : 0u; break;                                   \
+    }                                                                                       \
+    acc[j] = r_;                                                                            \
+  }
+          const bool neg = (in.flags & F_NEGATE) != 0;
+          if (type_base == 0) { SSB_ROW_BIN(int64_t) } else if (type_base == 1) { SSB_ROW_BIN(double) } else { SSB_ROW_BIN(int32_t) }
+#undef SSB_ROW_BIN
+          continue;
+        }
+        if (code == C_LOAD8 || code == C_LOAD4) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) acc[j] = s_val[(in.a * R + j) * T + tid];
+          accn = 0;
+          continue;
+        }
+        if (code == C_LOADK) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) acc[j] = rp.imm[in.a];
+          accn = 0;
+          continue;
+        }
+        if (code == C_OUT8 || code == C_OUT4) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) s_out[(in.a * R + j) * T + tid] = acc[j];
+          s_outn[in.a * T + tid] = 0u;
+          continue;
+        }
+        if (code == C_PRED) {
+          uint32_t t = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) t |= static_cast<uint32_t>(acc[j] & 1u) << j;
+          pass = t & ~accn & live;
+          continue;
+        }
+        // C_AND3_S / C_OR3_S and anything else: the generic path below computes the same
+      }
+      u64 r1[R], r2[R];
+      uint32_t n1 = 0, n2 = 0;
+#pragma unroll
+      for (int j = 0; j < R; ++j) { r1[j] = 0; r2[j] = 0; }
+      if (in.kind == K_LOAD || in.kind == K_ALU2 || in.kind == K_ALU3) {
+        if (in.flags & F_RHS_IMM) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) r1[j] = rp.imm[in.a];
+          n1 = (in.flags & F_RHS_NULLK) ? 3u : 0u;
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) r1[j] = s_val[(in.a * R + j) * T + tid];
+          n1 = s_nul[in.a * T + tid];
+        }
+      }
+      if (in.kind == K_ALU3) {
+        if (in.flags & F_RHS2_IMM) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) r2[j] = rp.imm[in.b];
+          n2 = (in.rhs_nullable & 4) ? 3u : 0u;
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) r2[j] = s_val[(in.b * R + j) * T + tid];
+          n2 = s_nul[in.b * T + tid];
+        }
+      }
+      switch (in.kind) {
+        case K_LOAD:
+#pragma unroll
+          for (int j = 0; j < R; ++j) acc[j] = r1[j];
+          accn = n1;
+          break;
+        case K_STORE:
+#pragma unroll
+          for (int j = 0; j < R; ++j) s_val[(in.a * R + j) * T + tid] = acc[j];
+          s_nul[in.a * T + tid] = accn;
+          break;
+        case K_ALU1:
+        case K_ALU2:
+        case K_ALU3:
+          alu<R>(in, acc, accn, r1, n1, r2, n2, live, fail);
+          break;
+        case K_PRED: {
+          uint32_t t = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) t |= static_cast<uint32_t>(acc[j] & 1u) << j;
+          pass = t & ~accn & live;
+        } break;
+        case K_OUT:
+#pragma unroll
+          for (int j = 0; j < R; ++j) s_out[(in.a * R + j) * T + tid] = acc[j];
+          s_outn[in.a * T + tid] = accn;
+          break;
+        default: break;
+      }
+    }
+    const unsigned int ready_now = *reinterpret_cast<volatile unsigned int*>(&l_ready);
+    if (ready_now != my_ready) {
+      my_ready = ready_now;
+#pragma unroll
+      for (int e = 0; e < kTinyGroups; ++e) if ((my_ready >> e) & 1u) my_fp[e] = *reinterpret_cast<volatile unsigned long long*>(&l_fp[e]);
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!((pass >> j) & 1u)) continue;
+      const long long row = rows_[j];
+      unsigned long long kv[kMaxKeys];
+      unsigned int knull = 0;
+#pragma unroll
+      for (int c = 0; c < kMaxKeys; ++c) {
+        kv[c] = 0;
+        if (c < NK) {
+          if ((s_outn[c * T + tid] >> j) & 1u) knull |= 1u << c; else kv[c] = s_out[(c * R + j) * T + tid];
+        }
+      }
+      unsigned long long fp = 0x9E3779B97F4A7C15ull + knull;
+#pragma unroll
+      for (int c = 0; c < kMaxKeys; ++c) if (c < NK) fp = (fp ^ kv[c]) * 0xff51afd7ed558ccdULL + c;
+      int g = -1;
+#pragma unroll
+      for (int e = 0; e < kTinyGroups; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
+      if (g >= 0) {
+        bool same = l_knull[g] == knull;
+#pragma unroll
+        for (int c = 0; c < kMaxKeys; ++c) if (c < NK) same = same && l_key[g][c] == kv[c];
+        if (!same) g = -1;
+      }
+      long long slot = -1;
+      if (g < 0) {
+        slot = p.packed ? find_slot_packed_kv(p, (knull & 1u) != 0, kv[0]) : find_slot_generic_kv(p, kv, knull);
+        if (slot < 0) {
+          const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+          p.deferred[d] = row;
+          continue;
+        }
+        const unsigned int want = static_cast<unsigned int>(slot) + 1u;
+        for (int e = 0; e < kTinyGroups && g < 0; ++e) {
+          const unsigned int old = atomicCAS(&l_slot[e], 0u, want);
+          if (old == 0u) {
+#pragma unroll
+            for (int c = 0; c < kMaxKeys; ++c) if (c < NK) l_key[e][c] = kv[c];
+            l_knull[e] = knull;
+            l_fp[e] = fp;
+            __threadfence_block();
+            atomicOr(&l_ready, 1u << e);
+            g = e;
+          } else if (old == want) {
+            g = e;
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < kLocalMaxAggs; ++a) {
+        if (a >= A) break;
+        const AggDev& ag = p.agg[a];
+        const int o = rp.agg_out[a];
+        unsigned long long v = 0;
+        if (o >= 0) {
+          if ((s_outn[o * T + tid] >> j) & 1u) continue;   // NULL input: no contribution
+          v = s_out[(o * R + j) * T + tid];
+          if (ag.fn != SSB_AGG_COUNT && ag.in_phys != ag.out_phys) v = convert_value(v, ag.in_phys, ag.out_phys);
+        }
+        if (g < 0) {   // more groups than local entries in this CTA: straight to the global table
+          apply(ag, slot, v, 1ull);
+          if (ag.seen != nullptr) ag.seen[slot] = 1u;
+          continue;
+        }
+        unsigned long long* accp = &t_acc[(g * A + a) * T + tid];
+        switch (ag.pad) {
+          case TA_COUNT: *accp += 1ull; break;
+          case TA_SUM_F64: *accp = Codec<double>::enc(Codec<double>::dec(*accp) + Codec<double>::dec(v)); break;
+          case TA_SUM_U64: *accp += v; break;
+          default: *accp = combine(ag, *accp, v); break;
+        }
+        if (ag.pad != TA_COUNT) t_seen[g][tid] |= 1u << a;
+      }
+    }
+  }
+  if (fail && rp.d_fail != nullptr) atomicOr(rp.d_fail, 1);
+  __syncthreads();
+  for (int ga = warp; ga < kTinyGroups * A; ga += T / 32) {
+    const int g = ga / A, a = ga - g * A;
+    if (l_slot[g] == 0u) continue;
+    const AggDev& ag = p.agg[a];
+    unsigned long long acc2 = 0;
+    bool has = false;
+    for (int t = lane; t < T; t += 32) {
+      const unsigned long long x = t_acc[ga * T + t];
+      if (ag.fn == SSB_AGG_COUNT) { acc2 += x; }
+      else if ((t_seen[g][t] >> a) & 1u) { acc2 = has ? combine(ag, acc2, x) : x; has = true; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, acc2, d);
+      const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
+      if (ag.fn == SSB_AGG_COUNT) acc2 += ov;
+      else if (oh) { acc2 = has ? combine(ag, acc2, ov) : ov; has = true; }
+    }
+    if (lane != 0) continue;
+    const long long slot = static_cast<long long>(l_slot[g] - 1u);
+    if (ag.fn == SSB_AGG_COUNT) { if (acc2) atomicAdd(&ag.acc[static_cast<unsigned long long>(slot) * ag.stride], acc2); continue; }
+    if (!has) continue;
+    if (ag.seen != nullptr) ag.seen[slot] = 1u;
+    apply(ag, slot, acc2, 0ull);
+  }
+}
+
 // ---- finalize: dense result columns ---------------------------------------------------------
 struct FinalizeParams {
   GroupParams g;
@@ -980,7 +1315,8 @@ static int grow_table(ssb_group* g, unsigned long long new_capacity) {
 }
 
 // One slice: launch, then grow-and-replay until no row is deferred.
-static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows, bool merge) {
+static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows, bool merge,
+                      const RowProg* fused = nullptr, size_t fused_smem = 0) {
   ssb_ctx* ctx = g->ctx;
   long long remaining = rows;
   long long* replay = nullptr;
@@ -996,13 +1332,16 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     }
     GroupParams p;
     fill_table_params(g, &p);
-    for (int c = 0; c < g->n_keys; ++c) { p.key_data[c] = keys[c].data; p.key_nulls[c] = keys[c].nulls; }
+    for (int c = 0; c < g->n_keys; ++c) {
+      p.key_data[c] = fused ? nullptr : keys[c].data;
+      p.key_nulls[c] = fused ? nullptr : keys[c].nulls;
+    }
     for (int a = 0; a < g->n_aggs; ++a) {
       if (merge) {
         p.agg[a].in_phys = phys_of(g->aggs[a].out_type);   // partial results carry the output type
         p.agg[a].in_data = values[a].data;
         p.agg[a].in_nulls = values[a].nulls;
-      } else if (g->aggs[a].input >= 0) {
+      } else if (g->aggs[a].input >= 0 && fused == nullptr) {
         p.agg[a].in_data = values[g->aggs[a].input].data;
         p.agg[a].in_nulls = values[g->aggs[a].input].nulls;
       }
@@ -1017,16 +1356,37 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     // few groups so far (and few enough aggregates): CTA-private shared-memory tables
     const bool few = g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst && g->h_counters[0] <= 256));
     // single packed 8-byte key, COUNT or same-type 8-byte aggregates, no NULL bitmaps, no replay
+    for (int a = 0; a < g->n_aggs; ++a) {
+      AggDev& ag = p.agg[a];
+      ag.pad = ag.fn == SSB_AGG_COUNT ? TA_COUNT
+               : (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) ? TA_SUM_F64
+               : (ag.fn == SSB_AGG_SUM && (ag.out_phys == T_I64 || ag.out_phys == T_U64)) ? TA_SUM_U64 : TA_OTHER;
+    }
     static const bool tiny_enabled = getenv("SSB200_GROUP_TINY") == nullptr || atoi(getenv("SSB200_GROUP_TINY")) != 0;
     static const bool fast_enabled = getenv("SSB200_GROUP_FAST") == nullptr || atoi(getenv("SSB200_GROUP_FAST")) != 0;
-    bool fast = fast_enabled && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1 &&
+    bool fast = fused == nullptr && fast_enabled && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1 &&
                 phys_width(p.key_phys[0]) == 8 && p.key_nulls[0] == nullptr;
     for (int a = 0; fast && a < g->n_aggs; ++a) {
       const AggDev& ag = p.agg[a];
       if (ag.fn == SSB_AGG_COUNT) { if (ag.in_phys >= 0 && ag.in_nulls != nullptr) fast = false; continue; }
       if (ag.in_nulls != nullptr || ag.in_phys != ag.out_phys || phys_width(ag.in_phys) != 8) fast = false;
     }
-    if (fast) {
+    if (fused != nullptr) {
+      // Filter -> Compute -> GroupAggregate in one kernel: the keys and aggregate inputs are outputs
+      // of the row program, not columns in memory
+      for (int a = 0; a < g->n_aggs; ++a) {
+        p.agg[a].in_phys = fused->agg_out[a] < 0 ? -1 : phys_of(g->aggs[a].in_type);
+        p.agg[a].in_data = nullptr;
+        p.agg[a].in_nulls = nullptr;
+      }
+      cudaFuncSetAttribute(group_update_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fused_smem));
+      long long per_sm = static_cast<long long>((ctx->smem_per_sm - 8192) / (fused_smem + 8192));
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 8) per_sm = 8;
+      long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
+      if (ctas > div_up(remaining, kTinyThreads * 2)) ctas = div_up(remaining, kTinyThreads * 2);
+      group_update_rows_kernel<<<static_cast<unsigned>(ctas), kTinyThreads, fused_smem, ctx->stream>>>(p, *fused);
+    } else if (fast) {
       long long ctas = static_cast<long long>(ctx->num_sms) * 4;
       if (ctas > div_up(remaining, 1024)) ctas = div_up(remaining, 1024);
       group_update_fast_kernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
@@ -1174,6 +1534,115 @@ void ssb_group_destroy(ssb_group* g) {
 int ssb_group_update(ssb_group* g, const ssb_column* keys, const ssb_column* values, int64_t rows) {
   TimedRegion timed(g->ctx);
   return feed(g, keys, values, rows, false, false);
+}
+
+int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* inputs, int64_t rows) {
+  ssb_ctx* ctx = g->ctx;
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  const Program& prog = sp->prog;
+  const int n_in = static_cast<int>(prog.input_types.size());
+  const int n_out = static_cast<int>(prog.outputs.size());
+  int n_values = 0;
+  for (int a = 0; a < g->n_aggs; ++a) if (g->aggs[a].input >= n_values) n_values = g->aggs[a].input + 1;
+  if (n_out != g->n_keys + n_values) {
+    return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "program outputs must be the key columns followed by the aggregate inputs");
+  }
+  for (int c = 0; c < g->n_keys; ++c) {
+    if (phys_of(prog.out_types[c]) != phys_of(g->key_types[c])) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "key column type differs from the program output");
+    if (prog.out_nullable[c] && !g->key_nullable[c]) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "nullable program output bound to a NOT NULL key");
+  }
+  for (int a = 0; a < g->n_aggs; ++a) {
+    if (g->aggs[a].input < 0) continue;
+    const int o = g->n_keys + g->aggs[a].input;
+    if (phys_of(prog.out_types[o]) != phys_of(g->aggs[a].in_type)) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "aggregate input type differs from the program output");
+    if (prog.out_nullable[o] && !g->aggs[a].in_nullable && g->aggs[a].fn != SSB_AGG_COUNT) {
+      return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "nullable program output bound to an aggregate declared NOT NULL");
+    }
+  }
+  for (int i = 0; i < n_in; ++i) {
+    if (inputs[i].data == nullptr && rows > 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "input column without data");
+    if (phys_of(inputs[i].dtype) != phys_of(prog.input_types[i])) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "input column type differs from the compiled program");
+    if (inputs[i].nulls != nullptr && !prog.input_nullable[i]) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "input column carries NULLs but was declared NOT_NULLABLE");
+  }
+  TimedRegion timed(ctx);
+  // ---- the fused form, when the program fits the row evaluator
+  RowProg rp;
+  memset(&rp, 0, sizeof(rp));
+  const int n_tmp = prog.params.n_tmp;
+  const int A = g->n_aggs;
+  const size_t T = kTinyThreads, R = 2;
+  const size_t smem = (static_cast<size_t>(kTinyGroups) * A * T + static_cast<size_t>(n_in + n_tmp) * R * T +
+                       static_cast<size_t>(n_out) * R * T) * 8 + static_cast<size_t>(n_in + n_tmp + n_out) * T * 4;
+  // Measured (profiles/r1_summary.md): interpreting the row program per thread costs ~1300
+  // instructions per row (6 G rows/s on the Q1 shape) against 11 G rows/s for materialising the
+  // slice with the tile-wide expression kernel and aggregating it. The per-thread evaluator is
+  // therefore opt-in (SSB200_GROUP_FUSED=1, kept as the replay engine of a future sink inside
+  // expr_kernel); the default is the sliced two-kernel form below, whose scratch is bounded by
+  // the slice, not by the table.
+  static const bool fused_enabled = getenv("SSB200_GROUP_FUSED") != nullptr && atoi(getenv("SSB200_GROUP_FUSED")) != 0;
+  const bool feasible = fused_enabled && A >= 1 && A <= kLocalMaxAggs && n_in <= kRowMaxIn && n_out <= kRowMaxOut &&
+                        static_cast<int>(prog.generic.size()) <= kRowMaxInsn && smem + 8192 <= ctx->smem_optin;
+  if (feasible) {
+    rp.n_insn = static_cast<int32_t>(prog.generic.size());
+    rp.n_in = n_in; rp.n_tmp = n_tmp; rp.n_out = n_out;
+    for (int i = 0; i < rp.n_insn; ++i) rp.insn[i] = prog.generic[i];
+    for (int i = 0; i < kRowMaxImm; ++i) rp.imm[i] = prog.params.imm[i];
+    for (int i = 0; i < n_in; ++i) rp.in_phys[i] = phys_of(prog.input_types[i]);
+    for (int a = 0; a < kMaxAggs; ++a) rp.agg_out[a] = (a < A && g->aggs[a].input >= 0) ? g->n_keys + g->aggs[a].input : -1;
+    rp.has_pred = prog.predicate >= 0 ? 1 : 0;
+    rp.d_fail = prog.has_signaling ? ctx->d_fail : nullptr;
+  }
+  int rc = 0;
+  long long offset = 0;
+  // scratch of the unfused path (allocated on first use)
+  std::vector<ssb_column> outs(n_out ? n_out : 1);
+  long long outs_rows = 0;
+  auto free_outs = [&]() {
+    for (int j = 0; j < n_out; ++j) { tmp_free(ctx, outs[j].data); tmp_free(ctx, outs[j].nulls); outs[j].data = nullptr; outs[j].nulls = nullptr; }
+  };
+  for (int j = 0; j < n_out; ++j) { outs[j].data = nullptr; outs[j].nulls = nullptr; outs[j].dtype = prog.out_types[j]; outs[j].reserved = 0; }
+  while (offset < rows && rc == 0) {
+    long long n = rows - offset;
+    if (g->rows_seen < kProbeRowsFirst && n > kProbeRowsFirst) n = kProbeRowsFirst;
+    if (n > kSliceRows) n = kSliceRows;
+    std::vector<ssb_column> in2(n_in ? n_in : 1);
+    for (int i = 0; i < n_in; ++i) {
+      in2[i] = inputs[i];
+      in2[i].data = static_cast<char*>(inputs[i].data) + static_cast<size_t>(offset) * width_of(inputs[i].dtype);
+      if (inputs[i].nulls) in2[i].nulls = inputs[i].nulls + offset / 32;   // offset is a multiple of 32
+    }
+    // few groups so far (or the first rows, which tell): evaluate the rows inside the aggregation
+    const bool fuse = feasible && (g->n_keys == 0 || g->rows_seen < kProbeRowsFirst || g->h_counters[0] <= kTinyGroups);
+    if (fuse) {
+      for (int i = 0; i < n_in; ++i) { rp.in_data[i] = in2[i].data; rp.in_nulls[i] = in2[i].nulls; }
+      rc = feed_slice(g, nullptr, nullptr, n, false, &rp, smem);
+    } else {
+      // many groups: materialise the slice with the fused Compute / Filter kernel, then aggregate it
+      if (outs_rows < n) {
+        free_outs();
+        cudaError_t e = cudaSuccess;
+        for (int j = 0; j < n_out && e == cudaSuccess; ++j) {
+          e = tmp_malloc(ctx, &outs[j].data, static_cast<size_t>(n) * 8 + 256);
+          if (e == cudaSuccess && prog.out_nullable[j]) e = tmp_malloc(ctx, &outs[j].nulls, static_cast<size_t>(n / 32 + 2) * 4 + 256);
+        }
+        if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "fused aggregate scratch"); break; }
+        outs_rows = n;
+      }
+      rc = ssb_program_run(sp, in2.data(), n, outs.data(), ctx->d_count);
+      if (rc) break;
+      cudaError_t e = cudaMemcpyAsync(ctx->h_count, ctx->d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "fused aggregate"); break; }
+      const long long kept = *ctx->h_count;
+      rc = feed(g, outs.data(), outs.data() + g->n_keys, kept, false, true);
+    }
+    offset += n;
+    g->rows_seen += n;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  free_outs();
+  if (rc == 0) rc = ssb_program_check_failure(sp);
+  return rc;
 }
 
 int ssb_group_merge(ssb_group* dst, int64_t n_groups, const ssb_column* key_cols, const ssb_column* agg_cols) {

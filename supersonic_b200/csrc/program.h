@@ -85,6 +85,9 @@ struct Program {
   int32_t variant;            // kernel variant (threads x rows per thread)
   int32_t bytes_in_row, bytes_out_row;
   bool has_signaling;
+  // The accumulator-machine program before the fast-path peepholes (K_LOAD / K_STORE / K_ALU* /
+  // K_PRED / K_OUT only, operands by slot index): what group.cu's fused row evaluator runs.
+  std::vector<Insn> generic;
 };
 
 // Compiles nodes into prog->params (bytecode + shared-memory plan for `smem_budget` bytes per

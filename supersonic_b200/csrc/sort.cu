@@ -476,6 +476,19 @@ __global__ void gather_kernel(const void* __restrict__ src, const uint32_t* __re
   }
 }
 
+// dst[idx[i]] = src[i]: the inverse of gather for index lists without duplicates.
+__global__ void scatter_kernel(const void* __restrict__ src, int width, const long long* __restrict__ idx, long long n,
+                               void* __restrict__ dst) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long r = idx[i];
+    if (r < 0) continue;
+    if (width == 8) static_cast<unsigned long long*>(dst)[r] = static_cast<const unsigned long long*>(src)[i];
+    else if (width == 4) static_cast<uint32_t*>(dst)[r] = static_cast<const uint32_t*>(src)[i];
+    else static_cast<uint8_t*>(dst)[r] = static_cast<const uint8_t*>(src)[i];
+  }
+}
+
 unsigned grid_1d(ssb_ctx* ctx, long long n, int block) {
   long long g = div_up(n, block);
   const long long cap = static_cast<long long>(ctx->num_sms) * 8;
@@ -495,6 +508,17 @@ int ssb_gather(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64_
   gather_kernel<<<grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(src->data, src->nulls, w,
                                                                 reinterpret_cast<const long long*>(d_idx), n,
                                                                 dst->data, dst->nulls);
+  ++ctx->launches;
+  SSB_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int ssb_scatter(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64_t n, const ssb_column* dst) {
+  if (n <= 0) return 0;
+  const int w = width_of(src->dtype);
+  if (w == 0 || width_of(dst->dtype) != w) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "scatter: column types differ");
+  if (src->nulls != nullptr) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "scatter of a column with a null bitmap");
+  scatter_kernel<<<grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(src->data, w, reinterpret_cast<const long long*>(d_idx), n, dst->data);
   ++ctx->launches;
   SSB_CUDA(ctx, cudaGetLastError());
   return 0;

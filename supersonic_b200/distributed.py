@@ -248,6 +248,38 @@ class CudaJoinKernels(object):
             lib.ssb_join_destroy(h)
         return li, ri
 
+    def scatter(self, col, idx, dst):
+        """dst[idx[i]] = col[i] (distinct indices)."""
+        t, dtype = col
+        if idx.numel():
+            self.ctx.check(self.ctx.lib.ssb_scatter(self.ctx.h, self._cols([col]), idx.data_ptr(), idx.numel(),
+                                                    self._cols([(dst, dtype)])))
+
+    def zeros(self, n, dtype):
+        return self.torch.zeros(max(int(n), 0), dtype=_torch_dtype(dtype), device=self.device)
+
+    def iota(self, n):
+        return self.torch.arange(max(int(n), 0), dtype=self.torch.int64, device=self.device)
+
+    def compact(self, flag, cols):
+        """Rows of `cols` where flag != 0, in order: the fused Filter kernel with the flag column as
+        predicate (ssb_program_run), at most ten columns per launch."""
+        capi = self.capi
+        n = flag.numel()
+        out, kept = [], 0
+        for first in range(0, len(cols), 10):
+            part = cols[first:first + 10]
+            nodes = [capi.node(capi.OP_INPUT, capi.BOOL, [0])]
+            nodes += [capi.node(capi.OP_INPUT, dt, [i + 1]) for i, (_, dt) in enumerate(part)]
+            prog = capi.Program(self.ctx, nodes, [capi.BOOL] + [dt for _, dt in part], [0] * (len(part) + 1),
+                                list(range(1, len(part) + 1)), predicate=0)
+            outs = [self.empty(n, dt) for _, dt in part]
+            kept = prog.run_sync([(flag.data_ptr(), None, capi.BOOL)] + [(t.data_ptr(), None, dt) for t, dt in part], n,
+                                 [(o.data_ptr(), None, dt) for o, (_, dt) in zip(outs, part)]) if n else 0
+            prog.close()
+            out += [(o[:kept], dt) for o, (_, dt) in zip(outs, part)]
+        return out
+
     def scope(self):
         """Context manager: torch work issued inside runs on the library's stream."""
         return self.torch.cuda.stream(self.stream)
@@ -349,6 +381,25 @@ class ShardedHashJoin(object):
         if outer and not b_cols:
             _, is_null = k.gather(b_keys[0], ri, want_valid=True)
             r_null = _exchange(is_null, back, rcv_back, g)
+        if uniqueness == UNIQUE:
+            # ---- owner, UNIQUE keys: a lhs row has at most one match, so the returned rows are put
+            # back at their lhs positions (scatter) and, for INNER, the matched rows are compacted in
+            # lhs order by the fused Filter kernel; no sort is needed
+            n_l = lhs_keys[0][0].numel()
+            flag = k.zeros(n_l, 6)
+            k.scatter((k.zeros(origin.numel(), 6) + 1, 6), origin, flag)
+            dense = []
+            for t, dt in r_cols:
+                d = k.zeros(n_l, dt)
+                k.scatter((t, dt), origin, d)
+                dense.append((d, dt))
+            if outer:
+                miss = k.zeros(n_l, 6)
+                if r_null is not None:
+                    k.scatter((r_null, 6), origin, miss)
+                return k.iota(n_l), list(lhs_cols), dense, miss
+            cols = k.compact(flag, [(k.iota(n_l), I64)] + list(lhs_cols) + dense)
+            return cols[0][0], cols[1:1 + len(lhs_cols)], cols[1 + len(lhs_cols):], None
         # ---- owner: stable order by origin row
         order = k.order_by(origin)
         lhs_rows = k.gather((origin, I64), order)

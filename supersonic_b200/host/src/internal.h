@@ -119,6 +119,7 @@ class DeviceProgram {
   const vector<int>& used_inputs() const { return used_; }
   bool has_predicate() const { return has_pred_; }
   int output_count() const { return n_out_; }
+  ssb_program* handle() const { return prog_; }   // for the fused entry points of the C ABI
   // inputs: device columns in used_inputs() order. outputs must be allocated for `rows` rows.
   // Returns the number of rows written.
   FailureOr<int64> Run(const vector<ssb_column>& inputs, int64 rows, const vector<ssb_column>& outputs);

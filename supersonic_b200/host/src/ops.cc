@@ -559,14 +559,98 @@ class GroupCursor : public GpuCursor {
               const vector<BoundAggregation>& aggs, size_t estimated_groups, bool scalar)
       : GpuCursor(schema, allocator, scalar ? "ScalarAggregateCursor" : "GroupAggregateCursor"), child_(child),
         keys_(keys), aggs_(aggs), estimated_groups_(estimated_groups), scalar_(scalar), group_(NULL) {}
+  // The child is a chain of row-wise operators (Filter / Compute / Project over a scan): its
+  // plan is evaluated inside the aggregation kernel (ssb_group_update_program), nothing is
+  // materialised between the two operators.
+  void FuseWith(const RowwisePlan& plan) { fused_.reset(new RowwisePlan(plan)); }
   virtual ~GroupCursor() { if (group_) ssb_group_destroy(group_); }
   virtual CursorId GetCursorId() const { return scalar_ ? SCALAR_AGGREGATE : GROUP_AGGREGATE; }
   virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
  protected:
+  // Returns true when the fused form ran; false = not applicable (plan too wide for one program).
+  FailureOr<bool> RunFused(Session* s, DeviceTable* result) {
+    const RowwisePlan& plan = *fused_;
+    // program outputs: the key columns, then the distinct aggregate inputs in order of first use
+    vector<NodePtr> outs;
+    for (size_t k = 0; k < keys_.size(); ++k) outs.push_back(plan.outputs[keys_[k]]);
+    vector<int> value_pos;
+    vector<ssb_agg_spec> specs;
+    for (size_t i = 0; i < aggs_.size(); ++i) {
+      ssb_agg_spec sp = aggs_[i].spec;
+      if (aggs_[i].input_position >= 0) {
+        size_t v = 0;
+        while (v < value_pos.size() && value_pos[v] != aggs_[i].input_position) ++v;
+        if (v == value_pos.size()) { value_pos.push_back(aggs_[i].input_position); outs.push_back(plan.outputs[aggs_[i].input_position]); }
+        sp.input = static_cast<int32_t>(v);
+      }
+      specs.push_back(sp);
+    }
+    FailureOrOwned<DeviceProgram> created = DeviceProgram::Create(plan.base_schema, outs, plan.predicate);
+    if (created.is_failure()) {
+      std::unique_ptr<Exception> e(created.release_exception());
+      if (e->return_code() == ERROR_NOT_IMPLEMENTED) return Success(false);
+      return Failure(e.release());
+    }
+    std::unique_ptr<DeviceProgram> program(created.release());
+    // the base columns the program reads
+    DeviceTable base;
+    std::unique_ptr<Block> keepalive;
+    int64 rows = 0;
+    vector<ssb_column> ic;
+    if (plan.source) {
+      PROPAGATE_ON_FAILURE(MaterializeOnDevice(plan.source.get(), &base, &keepalive));
+      rows = base.rows;
+      for (size_t k = 0; k < program->used_inputs().size(); ++k) ic.push_back(base.columns[program->used_inputs()[k]].col);
+    } else {
+      rows = static_cast<int64>(plan.base.row_count());
+      PROPAGATE_ON_FAILURE(UploadColumns(plan.base, program->used_inputs(), 0, plan.base.row_count(), &base));
+      for (size_t k = 0; k < base.columns.size(); ++k) ic.push_back(base.columns[k].col);
+    }
+    vector<int32_t> key_types, key_nullable;
+    for (size_t k = 0; k < keys_.size(); ++k) {
+      const Attribute& a = plan.schema.attribute(keys_[k]);
+      key_types.push_back(a.type());
+      key_nullable.push_back((a.is_nullable() || ssb_program_output_nullable(program->handle(), static_cast<int32_t>(k))) ? 1 : 0);
+    }
+    for (size_t i = 0; i < specs.size(); ++i) {
+      if (specs[i].input >= 0 && ssb_program_output_nullable(program->handle(), static_cast<int32_t>(keys_.size()) + specs[i].input)) {
+        specs[i].in_nullable = 1;
+      }
+    }
+    int32_t dummy = 0;
+    ssb_column dummy_col;
+    memset(&dummy_col, 0, sizeof(dummy_col));
+    const int64 expected = estimated_groups_ ? static_cast<int64>(estimated_groups_) : 0;
+    SSB_CALL(s, ssb_group_create(s->ctx(), static_cast<int32_t>(keys_.size()), key_types.empty() ? &dummy : key_types.data(),
+                                 key_nullable.empty() ? &dummy : key_nullable.data(), static_cast<int32_t>(specs.size()),
+                                 specs.data(), expected, &group_), "group-by setup");
+    SSB_CALL(s, ssb_group_update_program(group_, program->handle(), ic.empty() ? &dummy_col : ic.data(), rows),
+             "fused group-by");
+    PROPAGATE_ON_FAILURE(Finish(s, specs, result));
+    return Success(true);
+  }
+
+  FailureOrVoid Finish(Session* s, const vector<ssb_agg_spec>& specs, DeviceTable* result) {
+    int64_t n_groups = 0;
+    vector<ssb_column> kout(keys_.size() ? keys_.size() : 1), aout(specs.size() ? specs.size() : 1);
+    SSB_CALL(s, ssb_group_finalize(group_, &n_groups, kout.data(), aout.data()), "group-by finalize");
+    result->schema = schema();
+    result->columns.clear();
+    for (size_t k = 0; k < keys_.size(); ++k) { DeviceColumnRef c; c.col = kout[k]; result->columns.push_back(c); }
+    for (size_t i = 0; i < specs.size(); ++i) { DeviceColumnRef c; c.col = aout[i]; result->columns.push_back(c); }
+    result->rows = n_groups;
+    return Success();
+  }
+
   virtual FailureOrVoid Run(DeviceTable* result) {
     FailureOr<Session*> sr = Session::Get();
     PROPAGATE_ON_FAILURE(sr);
     Session* s = sr.get();
+    if (fused_ && !aggs_.empty()) {
+      FailureOr<bool> fused = RunFused(s, result);
+      PROPAGATE_ON_FAILURE(fused);
+      if (fused.get()) return Success();
+    }
     DeviceTable in;
     std::unique_ptr<Block> keepalive;
     PROPAGATE_ON_FAILURE(MaterializeOnDevice(child_.get(), &in, &keepalive));
@@ -596,17 +680,10 @@ class GroupCursor : public GpuCursor {
                                  specs.data(), expected, &group_), "group-by setup");
     SSB_CALL(s, ssb_group_update(group_, key_cols.empty() ? &dummy_col : key_cols.data(),
                                  value_cols.empty() ? &dummy_col : value_cols.data(), in.rows), "group-by");
-    int64_t n_groups = 0;
-    vector<ssb_column> kout(keys_.size() ? keys_.size() : 1), aout(specs.size() ? specs.size() : 1);
-    SSB_CALL(s, ssb_group_finalize(group_, &n_groups, kout.data(), aout.data()), "group-by finalize");
-    result->schema = schema();
-    result->columns.clear();
-    for (size_t k = 0; k < keys_.size(); ++k) { DeviceColumnRef c; c.col = kout[k]; result->columns.push_back(c); }
-    for (size_t i = 0; i < specs.size(); ++i) { DeviceColumnRef c; c.col = aout[i]; result->columns.push_back(c); }
-    result->rows = n_groups;
-    return Success();
+    return Finish(s, specs, result);
   }
  private:
+  std::unique_ptr<RowwisePlan> fused_;
   std::unique_ptr<Cursor> child_;
   vector<int> keys_;
   vector<BoundAggregation> aggs_;
@@ -641,8 +718,22 @@ class GroupAggregateOperation : public BasicOperation {
     vector<BoundAggregation> aggs;
     PROPAGATE_ON_FAILURE(BindAggregations(*aggregation_, cs, &aggs, &result));
     const size_t est = options_ ? options_->estimated_result_row_count() : 0;
-    return Success(static_cast<Cursor*>(new GroupCursor(result, buffer_allocator(), child_cursor.release(), keys, aggs,
-                                                        est, group_by_ == NULL)));
+    GroupCursor* cursor = new GroupCursor(result, buffer_allocator(), child_cursor.release(), keys, aggs, est, group_by_ == NULL);
+    // A row-wise child that filters or computes is evaluated inside the aggregation kernel.
+    RowwisePlan plan;
+    Exception* describe_error = NULL;
+    if (getenv("SSB200_HOST_FUSE_GROUP") == NULL || atoi(getenv("SSB200_HOST_FUSE_GROUP")) != 0) {
+      if (child()->DescribeRowwise(&plan, &describe_error) && describe_error == NULL) {
+        bool nontrivial = static_cast<bool>(plan.predicate);
+        for (size_t k = 0; k < keys.size(); ++k) nontrivial = nontrivial || plan.outputs[keys[k]]->op != SSB_OP_INPUT;
+        for (size_t i = 0; i < aggs.size(); ++i) {
+          if (aggs[i].input_position >= 0) nontrivial = nontrivial || plan.outputs[aggs[i].input_position]->op != SSB_OP_INPUT;
+        }
+        if (nontrivial) cursor->FuseWith(plan);
+      }
+      delete describe_error;
+    }
+    return Success(static_cast<Cursor*>(cursor));
   }
  protected:
   virtual string DebugName() const { return group_by_ ? "GroupAggregate" : "ScalarAggregate"; }

@@ -256,3 +256,153 @@ def test_partition_rows_is_stable_and_sides_agree(ctx, rows, parts):
         assert len(set(got[0].values())) > 1                      # the hash spreads keys
     for ptr in (k, k32, perm):
         ctx.free(ptr)
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused Filter -> Compute -> GroupAggregate (ssb_group_update_program) against the unfused pipeline
+# (ssb_program_run, then ssb_group_update) on the same inputs: identical groups and aggregates.
+def _upload(ctx, arr, nulls=None):
+    arr = np.ascontiguousarray(arr)
+    ptr = ctx.malloc(arr.nbytes + 256)
+    ctx.h2d(ptr, arr)
+    nptr = None
+    if nulls is not None:
+        words = np.packbits(np.concatenate([nulls.astype(np.uint8), np.zeros((-len(nulls)) % 32 + 32, np.uint8)]), bitorder="little")
+        nptr = ctx.malloc(words.nbytes + 256)
+        ctx.h2d(nptr, words)
+    return ptr, nptr
+
+
+def _download_group(ctx, g, key_dts, agg_dts):
+    n = C.c_int64()
+    ko, ao = _cols([(0, None, 0)] * max(1, len(key_dts))), _cols([(0, None, 0)] * len(agg_dts))
+    ctx.check(ctx.lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+    rows = n.value
+
+    def col(c, dt):
+        a = np.empty(rows, dtype=dt)
+        if rows:
+            ctx.d2h(a, c.data)
+        isn = np.zeros(rows, dtype=bool)
+        if c.nulls and rows:
+            w = np.empty((rows + 31) // 32, dtype=np.uint32)
+            ctx.d2h(w, c.nulls)
+            isn = np.unpackbits(w.view(np.uint8), bitorder="little")[:rows].astype(bool)
+        return a, isn
+    keys = [col(ko[i], dt) for i, dt in enumerate(key_dts)]
+    aggs = [col(ao[i], dt) for i, dt in enumerate(agg_dts)]
+    # canonical order: by (null flags, key values)
+    order = np.lexsort([x for k in reversed(keys) for x in (np.where(k[1], 0, k[0]), k[1])]) if keys else np.arange(rows)
+    return [(k[0][order], k[1][order]) for k in keys], [(a[0][order], a[1][order]) for a in aggs]
+
+
+def _same_groups(a, b):
+    for (x, xn), (y, yn) in zip(a[0] + a[1], b[0] + b[1]):
+        assert np.array_equal(xn, yn)
+        assert np.array_equal(x[~xn], y[~yn])
+
+
+NP_OF_T = {capi.INT64: np.int64, capi.DOUBLE: np.float64, capi.INT32: np.int32, capi.UINT64: np.uint64, capi.BOOL: np.uint8}
+
+
+def _run_both(ctx, nodes, in_types, in_nullable, outputs, predicate, inputs, n_keys, key_types, key_nullable, aggs, agg_out_types):
+    """inputs: [(values, nulls or None)]; aggs: [(fn, value index or -1, in_type, out_type, in_nullable)]."""
+    rows = len(inputs[0][0])
+    dev = [_upload(ctx, v, nl) for v, nl in inputs]
+    incols = [(d, nl, t) for (d, nl), t in zip(dev, in_types)]
+    prog = capi.Program(ctx, nodes, in_types, in_nullable, outputs, predicate=predicate)
+    lib = ctx.lib
+
+    def make_group():
+        specs = (capi.AggSpec * len(aggs))()
+        for i, (fn, inp, it, ot, inn) in enumerate(aggs):
+            specs[i].fn, specs[i].input, specs[i].in_type, specs[i].out_type, specs[i].in_nullable = fn, inp, it, ot, inn
+        g = C.c_void_p()
+        kt = (C.c_int32 * max(1, n_keys))(*key_types)
+        kn = (C.c_int32 * max(1, n_keys))(*key_nullable)
+        ctx.check(lib.ssb_group_create(ctx.h, n_keys, kt, kn, len(aggs), specs, 0, C.byref(g)))
+        return g
+    # fused
+    g1 = make_group()
+    ctx.check(lib.ssb_group_update_program(g1, prog.h, _cols(incols), rows))
+    key_dts = [NP_OF_T[t] for t in key_types]
+    got = _download_group(ctx, g1, key_dts, [NP_OF_T[t] for t in agg_out_types])
+    # unfused
+    out_cols = []
+    for j in range(len(outputs)):
+        t = lib.ssb_program_output_type(prog.h, j)
+        d = ctx.malloc(rows * 8 + 256)
+        nl = ctx.malloc((rows // 32 + 2) * 4 + 256) if lib.ssb_program_output_nullable(prog.h, j) else None
+        out_cols.append((d, nl, t))
+    kept = prog.run_sync(incols, rows, out_cols)
+    g2 = make_group()
+    ctx.check(lib.ssb_group_update(g2, _cols(out_cols[:n_keys] or [(0, None, 0)]), _cols(out_cols[n_keys:] or [(0, None, 0)]), kept))
+    want = _download_group(ctx, g2, key_dts, [NP_OF_T[t] for t in agg_out_types])
+    _same_groups(got, want)
+    for g in (g1, g2):
+        lib.ssb_group_destroy(g)
+    prog.close()
+    for d, nl in dev:
+        ctx.free(d)
+        if nl:
+            ctx.free(nl)
+    for d, nl, _ in out_cols:
+        ctx.free(d)
+        if nl:
+            ctx.free(nl)
+    return want, kept
+
+
+@pytest.mark.parametrize("rows", [1, 1000, 600_000])
+def test_fused_q1_shape_equals_unfused(ctx, rows):
+    rng = np.random.default_rng(rows)
+    F64, I64, B = capi.DOUBLE, capi.INT64, capi.BOOL
+    n = capi.node
+    types = [F64, F64, F64, F64, I64, I64, I64]
+    inputs = [(rng.integers(1, 51, rows).astype(np.float64), None), (rng.integers(100, 10000, rows) / 4.0, None),
+              (rng.integers(0, 5, rows) / 16.0, None), (rng.integers(0, 5, rows) / 16.0, None),
+              (rng.integers(0, 3, rows), None), (rng.integers(0, 2, rows), None), (rng.integers(0, 2500, rows), None)]
+    nodes = [n(capi.OP_INPUT, t, [j]) for j, t in enumerate(types)]
+    nodes += [n(capi.OP_CONST, F64, [], f64=1.0), n(capi.OP_SUB, F64, [7, 2]), n(capi.OP_MUL, F64, [1, 8]),
+              n(capi.OP_ADD, F64, [7, 3]), n(capi.OP_MUL, F64, [9, 10]), n(capi.OP_CONST, I64, [], i64=2450),
+              n(capi.OP_LE, B, [6, 12])]
+    aggs = [(capi.AGG_SUM, i, F64, F64, 0) for i in range(5)] + [(capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
+    want, kept = _run_both(ctx, nodes, types, [0] * 7, [4, 5, 0, 1, 2, 9, 11], 13, inputs, 2, [I64, I64], [0, 0], aggs,
+                           [F64] * 5 + [capi.UINT64])
+    assert int(want[1][5][0].sum()) == kept
+
+
+@pytest.mark.parametrize("groups,rows", [(5, 50_000), (7, 400_000), (5000, 400_000)])
+def test_fused_nullable_keys_inputs_and_overflow_equal_unfused(ctx, groups, rows):
+    """NULL keys form a group, NULL predicate rows are dropped, NULL inputs do not count; with
+    5000 groups the CTA-local entries overflow into the global table and later slices take the
+    materialising path."""
+    rng = np.random.default_rng(groups)
+    F64, I64, I32, B = capi.DOUBLE, capi.INT64, capi.INT32, capi.BOOL
+    n = capi.node
+    types = [I64, I64, F64, I32]
+    inputs = [(rng.integers(0, groups, rows), rng.random(rows) < 0.05), (rng.integers(-1000, 1000, rows), rng.random(rows) < 0.1),
+              (rng.integers(0, 1 << 20, rows) / 8.0, rng.random(rows) < 0.2), (rng.integers(-50, 50, rows).astype(np.int32), None)]
+    nodes = [n(capi.OP_INPUT, t, [j]) for j, t in enumerate(types)]                # 0..3
+    nodes += [n(capi.OP_CONST, I64, [], i64=3), n(capi.OP_MUL, I64, [1, 4]),         # 5: b * 3 (nullable)
+              n(capi.OP_CONST, I64, [], i64=-2500), n(capi.OP_GT, B, [5, 6]),         # 7: b*3 > -2500 (NULL drops the row)
+              n(capi.OP_CAST, I64, [3]), n(capi.OP_ADD, I64, [5, 8])]                # 9: b*3 + d
+    aggs = [(capi.AGG_SUM, 0, I64, I64, 1), (capi.AGG_MIN, 1, F64, F64, 1), (capi.AGG_MAX, 1, F64, F64, 1),
+            (capi.AGG_COUNT, 1, F64, capi.UINT64, 1), (capi.AGG_COUNT, -1, I64, capi.UINT64, 0), (capi.AGG_SUM, 2, I32, I32, 0)]
+    _run_both(ctx, nodes, types, [1, 1, 1, 0], [0, 9, 2, 3], 7, inputs, 1, [I64], [1], aggs,
+              [I64, F64, F64, capi.UINT64, capi.UINT64, I32])
+
+
+def test_fused_scalar_aggregate_equals_unfused(ctx):
+    rows = 300_000
+    rng = np.random.default_rng(3)
+    I64, B = capi.INT64, capi.BOOL
+    n = capi.node
+    inputs = [(rng.integers(-10**6, 10**6, rows), None), (rng.integers(0, 100, rows), None)]
+    nodes = [n(capi.OP_INPUT, I64, [0]), n(capi.OP_INPUT, I64, [1]), n(capi.OP_CONST, I64, [], i64=10), n(capi.OP_LT, B, [1, 2]),
+             n(capi.OP_MUL, I64, [0, 1])]
+    aggs = [(capi.AGG_SUM, 0, I64, I64, 0), (capi.AGG_MAX, 0, I64, I64, 0), (capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
+    want, kept = _run_both(ctx, nodes, [I64, I64], [0, 0], [4], 3, inputs, 0, [], [], aggs, [I64, I64, capi.UINT64])
+    a, b = inputs[0][0], inputs[1][0]
+    m = b < 10
+    assert want[1][0][0][0] == (a * b)[m].sum() and want[1][1][0][0] == (a * b)[m].max() and want[1][2][0][0] == m.sum() == kept

@@ -149,6 +149,20 @@ class NumpyJoinKernels(object):
     def order_by(self, key):
         return torch.from_numpy(np.argsort(key.numpy(), kind="stable"))
 
+    def scatter(self, col, idx, dst):
+        dst.numpy()[idx.numpy()] = col[0].numpy()
+
+    def zeros(self, n, dtype):
+        from supersonic_b200.distributed import _torch_dtype
+        return torch.zeros(int(n), dtype=_torch_dtype(dtype))
+
+    def iota(self, n):
+        return torch.arange(int(n), dtype=torch.int64)
+
+    def compact(self, flag, cols):
+        m = flag.numpy() != 0
+        return [(torch.from_numpy(np.ascontiguousarray(t.numpy()[m])), dt) for t, dt in cols]
+
 
 def _join_tables(uniq, scale=1):
     rng = np.random.default_rng(5)

@@ -174,7 +174,7 @@ def _join_tables(uniq, scale=1):
             "fk": rng.integers(0, nb * 3, npr), "lv": rng.integers(0, 10**9, npr)}
 
 
-def _join_worker(rank, world, port, out):
+def _join_worker(rank, world, port, out, strategy):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -188,7 +188,7 @@ def _join_worker(rank, world, port, out):
             pb, pe = shard_rows(len(t["fk"]), rank, world, align=1)
             col = lambda name, b, e, dt: (torch.from_numpy(np.ascontiguousarray(t[name][b:e])), dt)   # noqa: E731
             for jt in (0, 1):
-                j = ShardedHashJoin(NumpyJoinKernels())
+                j = ShardedHashJoin(NumpyJoinKernels(), strategy=strategy)
                 rows, lcols, rcols, rnull = j.run([col("fk", pb, pe, I64)], [col("fk", pb, pe, I64), col("lv", pb, pe, I64)],
                                                   [col("pk", bb, be, I64)], [col("payload", bb, be, I64), col("w", bb, be, F64)],
                                                   join_type=jt, uniqueness=uniq)
@@ -199,12 +199,13 @@ def _join_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_sharded_hash_join_world2_matches_oracle(ref):
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+def test_sharded_hash_join_world2_matches_oracle(ref, strategy):
     from supersonic_b200 import ssplan as sp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_join_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_join_worker, args=(r, 2, port, out, strategy)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(out.get(timeout=180) for _ in range(2))

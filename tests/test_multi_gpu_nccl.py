@@ -15,7 +15,7 @@ from supersonic_b200.distributed import shard_rows
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out, n_scale):
+def _worker(rank, world, port, out, n_scale, strategy):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, out, n_scale):
             pb, pe = shard_rows(len(t["fk"]), rank, world, align=1)
             col = lambda name, b, e, dt: (torch.from_numpy(np.ascontiguousarray(t[name][b:e])).cuda(), dt)   # noqa: E731
             for jt in (0, 1):
-                j = ShardedHashJoin(kern)
+                j = ShardedHashJoin(kern, strategy=strategy)
                 rows, lcols, rcols, rnull = j.run([col("fk", pb, pe, I64)], [col("fk", pb, pe, I64), col("lv", pb, pe, I64)],
                                                   [col("pk", bb, be, I64)], [col("payload", bb, be, I64), col("w", bb, be, F64)],
                                                   join_type=jt, uniqueness=uniq)
@@ -45,15 +45,16 @@ def _worker(rank, world, port, out, n_scale):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
 @pytest.mark.parametrize("n_scale", [1, 60])
-def test_sharded_hash_join_two_gpus_matches_oracle(ref, n_scale):
+def test_sharded_hash_join_two_gpus_matches_oracle(ref, n_scale, strategy):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     from supersonic_b200 import ssplan as sp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, n_scale)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, n_scale, strategy)) for r in range(2)]
     for p in procs:
         p.start()
     got = {}

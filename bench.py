@@ -365,7 +365,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SSB200_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout
+        # NCCL prints its version banner (and warnings) to stdout: send them to a file, stdout carries one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ssb200_nccl.%h.%p.log")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = capi.Context(local)

@@ -308,6 +308,8 @@ class Compiler {
     }
   }
 
+  uint32_t sink_bytes_ = 0;   // > 0: aggregation sink instead of output staging (public: set by compile_program)
+
   int Finish(const int32_t* outputs, int n_out, int predicate, uint32_t smem_budget,
              uint32_t smem_max) {
     ExprParams& p = prog_->params;
@@ -396,8 +398,9 @@ class Compiler {
     p.off_nullw = 64 + 512;
     // Filter defers the copy-out by two tiles (the wave's counts are then always published);
     // without a predicate the output position is known at once and one tile of slack suffices.
-    const uint32_t defer = p.has_pred ? kMaxDefer : 1;
+    const uint32_t defer = sink_bytes_ ? 0 : (p.has_pred ? kMaxDefer : 1);
     p.defer = static_cast<int32_t>(defer);
+    if (sink_bytes_) p.out_bytes = 0;
     int stages = kMaxStages;
     for (;; --stages) {
       const uint32_t nullw_bytes = (stages * p.stage_nullw + tmp_nullw) * (tile_ / 32) * 4;
@@ -405,7 +408,9 @@ class Compiler {
       const uint32_t itab_off = (p.off_nullw + nullw_bytes + 15) & ~15u;
       const uint32_t itab_bytes = static_cast<uint32_t>(stages) * (p.n_insn + 1) * 16;
       const uint32_t data_off = (itab_off + itab_bytes + 1023) & ~1023u;
-      const uint32_t total = data_off + stages * p.stage_bytes + tmp_bytes + (defer + 1) * p.out_bytes;
+      const uint32_t sink_off = (data_off + stages * p.stage_bytes + tmp_bytes + 15) & ~15u;
+      const uint32_t total = sink_bytes_ ? sink_off + sink_bytes_
+                                         : data_off + stages * p.stage_bytes + tmp_bytes + (defer + 1) * p.out_bytes;
       if ((total <= smem_budget && stages >= 2) || stages == 1 || (stages == 2 && total <= smem_max)) {
         if (total > smem_max) return Fail(SSB_ERROR_NOT_IMPLEMENTED, "expression needs more shared memory than one SM has");
         p.stages = stages;
@@ -414,6 +419,7 @@ class Compiler {
         p.off_data = data_off;
         p.off_tmp = data_off + stages * p.stage_bytes;
         p.off_out = p.off_tmp + tmp_bytes;
+        p.sink_off = sink_off;
         prog_->smem_bytes = total;
         break;
       }
@@ -655,7 +661,8 @@ class Compiler {
 int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs,
                     const int32_t* input_types, const int32_t* input_nullable,
                     const int32_t* outputs, int32_t n_outputs, int32_t predicate,
-                    int32_t tile, uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err) {
+                    int32_t tile, uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err,
+                    uint32_t sink_bytes_per_thread, uint32_t sink_fixed_bytes, int32_t threads) {
   if (n_nodes <= 0 || n_inputs < 0 || n_outputs < 0 || (n_outputs == 0 && predicate < 0)) {
     *err = "empty program";
     return SSB_ERROR_INVALID_ARGUMENT_VALUE;
@@ -674,6 +681,7 @@ int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_input
   prog->has_signaling = false;
   Compiler c(nodes, n_nodes, n_inputs, input_types, input_nullable, tile, prog, err);
   if (int rc = c.Analyze()) return rc;
+  if (sink_bytes_per_thread) c.sink_bytes_ = sink_fixed_bytes + sink_bytes_per_thread * static_cast<uint32_t>(threads);
   return c.Finish(outputs, n_outputs, predicate, smem_budget, smem_max);
 }
 

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "common.h"
+#include "group_device.h"
 #include "program.h"
 
 namespace ssb {
@@ -106,7 +107,12 @@ struct __align__(16) TabEntry {
 };
 static constexpr uint32_t kCodeEnd = 0xffffu;
 
-template <int NT, int R>
+// SINK: the outputs (group-by keys, then aggregate inputs) feed the aggregation table of group.cu
+// directly -- per-thread accumulators in shared memory for the CTA's first `sink_groups` groups,
+// the global table beyond -- instead of being staged, compacted and copied out. Filter then
+// needs no compaction at all (the predicate only masks rows), so the wave scan, the staging
+// buffers and the copy-out disappear from the kernel.
+template <int NT, int R, bool SINK>
 __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ ExprParams p) {
   constexpr int TILE = NT * R;
   constexpr int NW = NT / 32;
@@ -163,6 +169,26 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     }
     itab[e] = t;
   }
+  // ---- aggregation sink state (thread-private words are indexed [..][thread])
+  const GroupParams* gp = static_cast<const GroupParams*>(p.sink_gp);
+  const int SG = p.sink_groups, SA = p.sink_n_aggs, SNK = p.sink_n_keys;
+  unsigned long long* t_acc = reinterpret_cast<unsigned long long*>(smem + p.sink_off);      // [SG * SA][NT]
+  unsigned long long* s_key = t_acc + SG * SA * NT;                                          // [SNK][R][NT]
+  unsigned long long* l_key = s_key + SNK * R * NT;                                          // [kTinyGroups][kMaxKeys]
+  unsigned long long* l_fp = l_key + kTinyGroups * kMaxKeys;                                 // [kTinyGroups]
+  unsigned int* t_seen = reinterpret_cast<unsigned int*>(l_fp + kTinyGroups);                // [SG][NT]
+  unsigned int* s_keyn = t_seen + SG * NT;                                                   // [SNK][NT]
+  unsigned int* l_knull = s_keyn + SNK * NT;                                                 // [kTinyGroups]
+  unsigned int* l_slot = l_knull + kTinyGroups;                                              // [kTinyGroups]
+  unsigned int* l_ready = l_slot + kTinyGroups;                                              // [1]
+  if constexpr (SINK) {
+    if (tid < NT) {
+      for (int i = tid; i < SG * SA * NT; i += NT) t_acc[i] = identity_dev(gp->agg[(i / NT) % SA]);
+      for (int i = tid; i < SG * NT; i += NT) t_seen[i] = 0u;
+      if (tid < kTinyGroups) l_slot[tid] = 0u;
+      if (tid == 0) *l_ready = 0u;
+    }
+  }
   __syncthreads();
 
   auto slot_data = [&](int slot, int stage) -> unsigned char* {
@@ -218,6 +244,11 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   const uint32_t all = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t fail = 0;
+  // sink: register copy of the fingerprints of the CTA's published groups
+  unsigned int my_ready = 0;
+  unsigned long long my_fp[kTinyGroups];
+#pragma unroll
+  for (int e = 0; e < kTinyGroups; ++e) my_fp[e] = 0;
 
   // Wave-synchronous prefix, shared by all consumer threads: at the top of an iteration every
   // thread fetches a few of the kept-row counts the wave of kdefer_ tiles ago published (together
@@ -244,7 +275,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   int ob = 0;                // it % n_obuf: staging buffer written by this iteration
   for (int it = 0; it < n_my + kdefer_; ++it) {
     unsigned long long pre[kPrefetch];
-    const bool scan_wave = p.has_pred && it >= kdefer_;
+    const bool scan_wave = !SINK && p.has_pred && it >= kdefer_;
     const unsigned long long* wp = wave_ptr;
     if (scan_wave) {
       const uint32_t m = (it - kdefer_ == n_waves - 1) ? last_mask : full_mask;
@@ -320,7 +351,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       }
       // Without a predicate no barrier separates this tile's staging writes from the copy-out
       // of the tile evaluated two iterations ago (same buffer): add one.
-      if (!p.has_pred) bar_consumers<NT>();
+      if (!SINK && !p.has_pred) bar_consumers<NT>();
 
       uint32_t live = all;
       if (n != TILE) {
@@ -335,6 +366,113 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       int pos[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) { acc[k] = 0; pos[k] = row_first + 32 * k; }
+
+      // ---- aggregation sink: group of every row of this thread (4 bits each: local entry, 15 =
+      // the row goes to the global table), resolved once the key outputs are known. At most two
+      // key columns, every aggregate COUNT or with equal input and result type (host-checked).
+      unsigned long long gids = 0;
+      bool resolved = false;
+      auto sink_slot_of = [&](int k, unsigned long long k0, unsigned long long k1, unsigned int knull) -> long long {
+        if (gp->packed) return find_slot_packed_kv(*gp, (knull & 1u) != 0, k0);
+        unsigned long long kv[kMaxKeys];
+        kv[0] = k0; kv[1] = k1;
+        return find_slot_generic_kv(*gp, kv, knull);
+      };
+      auto sink_keys_of = [&](int k, unsigned long long& k0, unsigned long long& k1, unsigned int& knull) {
+        k0 = k1 = 0; knull = 0;
+        if (SNK > 0) { if ((s_keyn[tid] >> k) & 1u) knull |= 1u; else k0 = s_key[k * NT + tid]; }
+        if (SNK > 1) { if ((s_keyn[NT + tid] >> k) & 1u) knull |= 2u; else k1 = s_key[(R + k) * NT + tid]; }
+      };
+      auto sink_resolve = [&]() {
+        resolved = true;
+        const unsigned int ready_now = *reinterpret_cast<volatile unsigned int*>(l_ready);
+        if (ready_now != my_ready) {
+          my_ready = ready_now;
+#pragma unroll
+          for (int e = 0; e < kTinyGroups; ++e) if ((my_ready >> e) & 1u) my_fp[e] = *reinterpret_cast<volatile unsigned long long*>(&l_fp[e]);
+        }
+#pragma unroll 1
+        for (int k = 0; k < R; ++k) {
+          if (!((pass >> k) & 1u)) continue;
+          unsigned long long k0, k1;
+          unsigned int knull;
+          sink_keys_of(k, k0, k1, knull);
+          const unsigned long long fp = ((0x9E3779B97F4A7C15ull + knull) ^ k0) * 0xff51afd7ed558ccdULL + (k1 ^ (k1 >> 29)) * 0xc4ceb9fe1a85ec53ULL;
+          int g = -1;
+#pragma unroll
+          for (int e = 0; e < kTinyGroups; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
+          if (g >= 0 && !(l_knull[g] == knull && l_key[g * kMaxKeys] == k0 && l_key[g * kMaxKeys + 1] == k1)) g = -1;
+          if (g < 0) {
+            const long long slot = sink_slot_of(k, k0, k1, knull);
+            if (slot < 0) {   // table full: the host grows it and replays this row
+              const unsigned long long d = atomicAdd(gp->n_deferred, 1ull);
+              gp->deferred[d] = row0 + row_first + 32 * k;
+              pass &= ~(1u << k);
+              continue;
+            }
+            const unsigned int want = static_cast<unsigned int>(slot) + 1u;
+            for (int e = 0; e < SG && g < 0; ++e) {
+              const unsigned int old = atomicCAS(&l_slot[e], 0u, want);
+              if (old == 0u) {
+                l_key[e * kMaxKeys] = k0;
+                l_key[e * kMaxKeys + 1] = k1;
+                l_knull[e] = knull;
+                l_fp[e] = fp;
+                __threadfence_block();
+                atomicOr(l_ready, 1u << e);
+                g = e;
+              } else if (old == want) {
+                g = e;
+              }
+            }
+            if (g < 0) g = 15;
+          }
+          gids |= static_cast<unsigned long long>(g) << (4 * k);
+          // COUNT(*) aggregates count the row here
+          for (uint32_t m = p.sink_count_star; m; m &= m - 1) {
+            const int a = __ffs(m) - 1;
+            if (g < 15) t_acc[(g * SA + a) * NT + tid] += 1ull;
+            else atomicAdd(&gp->agg[a].acc[static_cast<unsigned long long>(sink_slot_of(k, k0, k1, knull)) * gp->agg[a].stride], 1ull);
+          }
+        }
+      };
+      // output column j of the program = key column j, or the input of the aggregates in sink_out_aggs[j]
+      auto sink_output = [&](int j, uint32_t nulls) {
+        if (j < SNK) {
+#pragma unroll
+          for (int k = 0; k < R; ++k) s_key[(j * R + k) * NT + tid] = acc[k];
+          s_keyn[j * NT + tid] = nulls;
+          return;
+        }
+        if (!resolved) sink_resolve();
+        const uint32_t valid = pass & ~nulls;
+        for (uint32_t m = p.sink_out_aggs[j]; m; m &= m - 1) {
+          const int a = __ffs(m) - 1;
+          const uint32_t code = (p.sink_pad >> (2 * a)) & 3u;
+          unsigned long long* const base = t_acc + a * NT + tid;
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            if (!((valid >> k) & 1u)) continue;
+            const int g = static_cast<int>((gids >> (4 * k)) & 15u);
+            if (g == 15) {   // a group beyond the CTA's local entries: the global table
+              unsigned long long k0, k1;
+              unsigned int knull;
+              sink_keys_of(k, k0, k1, knull);
+              const long long slot = sink_slot_of(k, k0, k1, knull);
+              const AggDev& ag = gp->agg[a];
+              apply(ag, slot, acc[k], 1ull);
+              if (ag.seen != nullptr) ag.seen[slot] = 1u;
+              continue;
+            }
+            unsigned long long* accp = base + g * SA * NT;
+            if (code == TA_SUM_F64) *accp = Codec<double>::enc(Codec<double>::dec(*accp) + Codec<double>::dec(acc[k]));
+            else if (code == TA_SUM_U64) *accp += acc[k];
+            else if (code == TA_COUNT) *accp += 1ull;
+            else *accp = combine(gp->agg[a], *accp, acc[k]);
+            if (code != TA_COUNT) t_seen[g * NT + tid] |= 1u << a;
+          }
+        }
+      };
 
       // +0 acc (op) slot, +1 acc (op) imm, +2 slot (op) slot, +3 slot (op) imm; EXPR sees x, y
 #define SSB_BIN4(CODE0, T, EXPR)                                                         \
@@ -508,11 +646,13 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
               post = 2;
             } break;
             case C_OUT8: {
+              if constexpr (SINK) { sink_output(static_cast<int>(cur.z), 0u); break; }
               u64* dst = reinterpret_cast<u64*>(obuf + cur.x);
 #pragma unroll
               for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = acc[k];
             } break;
             case C_OUT4: {
+              if constexpr (SINK) { sink_output(static_cast<int>(cur.z), 0u); break; }
               uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + cur.x);
 #pragma unroll
               for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = static_cast<uint32_t>(acc[k]);
@@ -528,7 +668,9 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
                 continue;
               }
             }
-            {
+            if constexpr (SINK) {
+              pass = bits & ~accn & live;   // the predicate only masks rows: nothing is compacted
+            } else {
               pass = bits & ~accn & live;
               // in-tile compaction: the warp's rows are contiguous, so positions inside the warp
               // come from R ballots; one small scan over the warps gives the warp bases
@@ -636,6 +778,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
           } break;
           case K_OUT: {
             const int j = in.a;
+            if constexpr (SINK) { sink_output(j, accn); break; }
             unsigned char* dst = obuf + p.out_off[j];
             if (in.rw == 8) {
 #pragma unroll
@@ -661,12 +804,15 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
 #undef SSB_MAD2
 #undef SSB_BIN_TYPE
 #undef SSB_ENC
+      if constexpr (SINK) {
+        if (!resolved) sink_resolve();   // keys and COUNT(*) only: no value output triggered it
+      }
     }
     if (scan_wave) finish_wave();
     __syncthreads();   // all threads: the stage and the temporaries are free; the wave sums are published
 
     // ======================================================== write out tile `it - kdefer_`
-    if (it >= kdefer_) {
+    if (!SINK && it >= kdefer_) {
       const int ob_out = (ob + 1 == n_obuf) ? 0 : ob + 1;   // (it - kdefer_) % n_obuf
       const int tile = bid + (it - kdefer_) * G;
       const unsigned char* obuf = smem + p.off_out + ob_out * p.out_bytes;
@@ -751,6 +897,37 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
     if (++stage == S) { stage = 0; parity ^= 1u; }
     if (++ob == n_obuf) ob = 0;
   }
+  if constexpr (SINK) {
+    // flush: the threads' partials of every (local group, aggregate) are combined by one warp and
+    // applied to the global table once per CTA
+    bar_consumers<NT>();
+    for (int ga = warp; ga < SG * SA; ga += NW) {
+      const int g = ga / SA, a = ga - g * SA;
+      if (l_slot[g] == 0u) continue;
+      const AggDev& ag = gp->agg[a];
+      unsigned long long acc2 = 0;
+      bool has = false;
+      for (int t = lane; t < NT; t += 32) {
+        const unsigned long long x = t_acc[ga * NT + t];
+        if (ag.fn == SSB_AGG_COUNT) { acc2 += x; }
+        else if ((t_seen[g * NT + t] >> a) & 1u) { acc2 = has ? combine(ag, acc2, x) : x; has = true; }
+      }
+      for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, acc2, d);
+        const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
+        if (ag.fn == SSB_AGG_COUNT) acc2 += ov;
+        else if (oh) { acc2 = has ? combine(ag, acc2, ov) : ov; has = true; }
+      }
+      if (lane != 0) continue;
+      const long long slot = static_cast<long long>(l_slot[g] - 1u);
+      if (ag.fn == SSB_AGG_COUNT) { if (acc2) atomicAdd(&ag.acc[static_cast<unsigned long long>(slot) * ag.stride], acc2); continue; }
+      if (!has) continue;
+      if (ag.seen != nullptr) ag.seen[slot] = 1u;
+      apply(ag, slot, acc2, 0ull);
+    }
+    if (fail && p.d_fail != nullptr) atomicOr(p.d_fail, 1);
+    return;
+  }
   if (!p.has_pred && p.d_out_rows != nullptr && blockIdx.x == 0 && tid == 0) *p.d_out_rows = p.rows;
   if (fail && p.d_fail != nullptr) atomicOr(p.d_fail, 1);
 }
@@ -762,17 +939,18 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
 struct Variant {
   int threads, rows_per_thread;
   void (*kernel)(const ExprParams);
+  void (*sink_kernel)(const ExprParams);   // aggregation-sink instantiation, or nullptr
 };
 static const Variant kVariants[] = {
-    {256, 4, expr_kernel<256, 4>},
-    {128, 8, expr_kernel<128, 8>},
-    {256, 8, expr_kernel<256, 8>},
-    {128, 16, expr_kernel<128, 16>},
-    {64, 16, expr_kernel<64, 16>},
-    {128, 4, expr_kernel<128, 4>},
-    {64, 8, expr_kernel<64, 8>},
-    {96, 8, expr_kernel<96, 8>},
-    {96, 4, expr_kernel<96, 4>},
+    {256, 4, expr_kernel<256, 4, false>, nullptr},
+    {128, 8, expr_kernel<128, 8, false>, nullptr},
+    {256, 8, expr_kernel<256, 8, false>, nullptr},
+    {128, 16, expr_kernel<128, 16, false>, nullptr},
+    {64, 16, expr_kernel<64, 16, false>, nullptr},
+    {128, 4, expr_kernel<128, 4, false>, nullptr},
+    {64, 8, expr_kernel<64, 8, false>, nullptr},
+    {96, 8, expr_kernel<96, 8, false>, expr_kernel<96, 8, true>},
+    {96, 4, expr_kernel<96, 4, false>, expr_kernel<96, 4, true>},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 static const int kDefaultVariant = 7;   // 96 consumer threads x 8 rows = 768-row tiles, three CTAs per SM
@@ -832,6 +1010,112 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
   if (grid > p.num_tiles) grid = p.num_tiles;
   TimedRegion timed(ctx);
   var.kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);
+  ++ctx->launches;
+  SSB_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+
+// ---- aggregation sink: host side -------------------------------------------------------------
+// Shared memory of the sink per consumer thread / fixed part (must match the pointer arithmetic at
+// the top of the kernel).
+static uint32_t sink_bytes_per_thread(int n_keys, int n_aggs, int groups, int rows_per_thread) {
+  return static_cast<uint32_t>((groups * n_aggs + n_keys * rows_per_thread) * 8 + (groups + n_keys) * 4);
+}
+static uint32_t sink_fixed_bytes() {
+  return static_cast<uint32_t>(kTinyGroups * kMaxKeys * 8 + kTinyGroups * 8 + kTinyGroups * 4 * 2 + 16 + 64);
+}
+
+// Compiles (once per shape) the twin of `base` whose outputs feed the aggregation sink.
+int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_program** out) {
+  ssb_ctx* ctx = base->ctx;
+  *out = nullptr;
+  const uint32_t key = static_cast<uint32_t>(n_keys) | (static_cast<uint32_t>(n_aggs) << 8) | (static_cast<uint32_t>(groups) << 16);
+  if (base->sink != nullptr && base->sink_key == key) { *out = base->sink; return 0; }
+  delete base->sink;
+  base->sink = nullptr;
+  const Program& bp = base->prog;
+  struct Try { int variant, ctas; };
+  const Try tries[] = {{7, 3}, {7, 2}, {8, 3}, {8, 2}, {7, 1}, {8, 1}};
+  ssb_program* best = nullptr;
+  long long best_score = -1;
+  std::string err;
+  int rc = SSB_ERROR_NOT_IMPLEMENTED;
+  for (size_t i = 0; i < sizeof(tries) / sizeof(tries[0]); ++i) {
+    const Variant& var = kVariants[tries[i].variant];
+    const int c = tries[i].ctas;
+    const uint32_t budget = static_cast<uint32_t>((ctx->smem_per_sm - c * ctx->smem_reserved) / c);
+    ssb_program* cand = new ssb_program;
+    cand->ctx = ctx;
+    std::string e2;
+    const int r2 = compile_program(bp.nodes.data(), static_cast<int32_t>(bp.nodes.size()), static_cast<int32_t>(bp.input_types.size()),
+                                   bp.input_types.data(), bp.input_nullable.data(), bp.outputs.data(),
+                                   static_cast<int32_t>(bp.outputs.size()), bp.predicate, var.threads * var.rows_per_thread,
+                                   budget, static_cast<uint32_t>(ctx->smem_optin), &cand->prog, &e2,
+                                   sink_bytes_per_thread(n_keys, n_aggs, groups, var.rows_per_thread), sink_fixed_bytes(), var.threads);
+    if (r2 != 0) { delete cand; rc = r2; err = e2; continue; }
+    cand->prog.variant = tries[i].variant;
+    const int stages = cand->prog.params.stages;
+    const bool fits = cand->prog.smem_bytes <= budget;
+    const int resident = fits ? c : static_cast<int>(ctx->smem_per_sm / (cand->prog.smem_bytes + ctx->smem_reserved));
+    // bytes in flight per SM (three stages are enough), more resident CTAs (= consumer warps) on a tie
+    const long long score = static_cast<long long>(stages >= 2 ? (stages > 3 ? 3 : stages) : 0) * (resident < 1 ? 1 : resident) *
+                                cand->prog.params.tile * 16 + (resident < 1 ? 1 : resident);
+    if (score > best_score) { delete best; best = cand; best_score = score; } else { delete cand; }
+  }
+  if (best == nullptr) return fail(ctx, rc, err);
+  const Variant& var = kVariants[best->prog.variant];
+  cudaError_t e = cudaFuncSetAttribute(var.sink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
+  int occ = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.sink_kernel, var.threads + 32, best->prog.smem_bytes);
+  if (e != cudaSuccess || occ < 1) { delete best; return cuda_fail(ctx, e, "occupancy(expr_kernel sink)"); }
+  best->max_ctas_per_sm = occ;
+  base->sink = best;
+  base->sink_key = key;
+  *out = best;
+  return 0;
+}
+
+// Launches the sink kernel of `sp` (from sink_program_for) over `rows` rows. d_gp: the table's
+// GroupParams in device memory; out_aggs[j]: aggregates fed by output j; count_star: COUNT(*) mask.
+int launch_program_sink(ssb_program* sp, const ssb_column* inputs, int64_t rows, const void* d_gp, int n_keys,
+                        int n_aggs, int groups, const uint32_t* out_aggs, uint32_t count_star, uint32_t pad_codes) {
+  ssb_ctx* ctx = sp->ctx;
+  Program& prog = sp->prog;
+  ExprParams p = prog.params;
+  const Variant& var = kVariants[prog.variant];
+  if (rows <= 0) return 0;
+  bool aligned = true;
+  for (int i = 0; i < p.n_in; ++i) {
+    p.in_data[i] = inputs[i].data;
+    p.in_nulls[i] = inputs[i].nulls;
+    if (reinterpret_cast<uintptr_t>(inputs[i].data) & 15) aligned = false;
+    if (inputs[i].nulls && (reinterpret_cast<uintptr_t>(inputs[i].nulls) & 15)) aligned = false;
+  }
+  p.fill_nullw_tma = p.fill_nullw_plain = 0;
+  for (int i = 0; i < p.n_in; ++i) {
+    if (p.in_nullw[i] < 0) continue;
+    p.fill_nullw_plain = 1;
+    if (p.in_nulls[i] == nullptr) p.fill_nullw_tma = 1;
+  }
+  p.rows = rows;
+  p.num_tiles = div_up(rows, p.tile);
+  if (p.num_tiles > 0x7fff0000LL) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "more than 2^31 tiles in one launch");
+  p.use_tma = aligned ? 1 : 0;
+  p.d_out_rows = nullptr;
+  p.tile_status = nullptr;
+  p.d_fail = prog.has_signaling ? ctx->d_fail : nullptr;
+  p.debug_nowait = 0;
+  p.sink_gp = d_gp;
+  p.sink_n_keys = n_keys;
+  p.sink_n_aggs = n_aggs;
+  p.sink_groups = groups;
+  for (int j = 0; j < kMaxOut; ++j) p.sink_out_aggs[j] = j < p.n_out ? out_aggs[j] : 0u;
+  p.sink_count_star = count_star;
+  p.sink_pad = pad_codes;
+  long long grid = static_cast<long long>(ctx->num_sms) * sp->max_ctas_per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  var.sink_kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);
   ++ctx->launches;
   SSB_CUDA(ctx, cudaGetLastError());
   return 0;

@@ -66,6 +66,14 @@ struct ExprParams {
   unsigned long long* tile_status;      // per-tile kept-row counts | valid bit (Filter)
   int64_t* d_out_rows;
   int32_t* d_fail;
+  // ---- aggregation sink (expr_kernel<..., SINK = true>): the outputs are the group-by keys
+  // followed by the aggregate inputs and go straight into the aggregation, nothing is staged
+  const void* sink_gp;                  // GroupParams in device memory (group_device.h)
+  int32_t sink_n_keys, sink_n_aggs, sink_groups;   // local group entries per CTA (<= kTinyGroups)
+  uint32_t sink_off;                    // shared-memory offset of the sink area
+  uint32_t sink_out_aggs[kMaxOut];      // bit a: aggregate a accumulates output column j
+  uint32_t sink_count_star;             // bit a: aggregate a is COUNT(*)
+  uint32_t sink_pad;                    // two bits per aggregate: TA_* accumulate code
 };
 
 enum { kMaxDefer = 2 };   // Filter: tile i is copied out while tile i + defer is evaluated
@@ -92,17 +100,33 @@ struct Program {
 
 // Compiles nodes into prog->params (bytecode + shared-memory plan for `smem_budget` bytes per
 // CTA). Returns 0 or an SSB_ERROR_* with *err set. Pure host code (unit-tested without a GPU).
+// sink_bytes_per_thread > 0 compiles for the aggregation sink: no output staging buffers, and
+// sink_fixed_bytes + sink_bytes_per_thread * consumer threads of shared memory reserved at
+// params.sink_off.
 int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs,
                     const int32_t* input_types, const int32_t* input_nullable,
                     const int32_t* outputs, int32_t n_outputs, int32_t predicate,
-                    int32_t tile, uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err);
+                    int32_t tile, uint32_t smem_budget, uint32_t smem_max, Program* prog, std::string* err,
+                    uint32_t sink_bytes_per_thread = 0, uint32_t sink_fixed_bytes = 0, int32_t threads = 0);
 
+}  // namespace ssb
+
+struct ssb_program;
+namespace ssb {
+// Aggregation sink of expr_kernel (expr_kernel.cu), driven by group.cu.
+int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_program** out);
+int launch_program_sink(ssb_program* sp, const ssb_column* inputs, int64_t rows, const void* d_gp, int n_keys,
+                        int n_aggs, int groups, const uint32_t* out_aggs, uint32_t count_star, uint32_t pad_codes);
 }  // namespace ssb
 
 struct ssb_program {
   ssb_ctx* ctx;
   ssb::Program prog;
   int max_ctas_per_sm;
+  // lazily compiled twin for the aggregation sink (keyed by the sink's shared-memory need)
+  ssb_program* sink = nullptr;
+  uint32_t sink_key = 0;
+  ~ssb_program() { delete sink; }
 };
 
 #endif  // SSB_CSRC_PROGRAM_H_

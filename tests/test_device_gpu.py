@@ -406,3 +406,21 @@ def test_fused_scalar_aggregate_equals_unfused(ctx):
     a, b = inputs[0][0], inputs[1][0]
     m = b < 10
     assert want[1][0][0][0] == (a * b)[m].sum() and want[1][1][0][0] == (a * b)[m].max() and want[1][2][0][0] == m.sum() == kept
+
+
+def test_fused_sink_overflow_and_table_growth_equal_unfused(ctx):
+    """The aggregation sink of the expression kernel starts with four groups (per-thread
+    accumulators), then the key domain explodes: rows overflow into the global table, the table
+    fills up, the overflowing rows are deferred, the table grows and the rows are replayed."""
+    rows = 500_000
+    I64, B = capi.INT64, capi.BOOL
+    n = capi.node
+    i = np.arange(rows, dtype=np.int64)
+    key = np.where(i < 200_000, i % 4, i)
+    val = (i * 7919) % 1000 - 500
+    inputs = [(key, None), (val, None)]
+    nodes = [n(capi.OP_INPUT, I64, [0]), n(capi.OP_INPUT, I64, [1]), n(capi.OP_CONST, I64, [], i64=400), n(capi.OP_LT, B, [1, 2]),
+             n(capi.OP_CONST, I64, [], i64=2), n(capi.OP_MUL, I64, [1, 4])]
+    aggs = [(capi.AGG_SUM, 0, I64, I64, 0), (capi.AGG_MIN, 0, I64, I64, 0), (capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
+    want, kept = _run_both(ctx, nodes, [I64, I64], [0, 0], [0, 5], 3, inputs, 1, [I64], [0], aggs, [I64, I64, capi.UINT64])
+    assert int(want[1][2][0].sum()) == kept == int((val < 400).sum())

@@ -291,9 +291,11 @@ __global__ void __launch_bounds__(256) group_update_smem_kernel(const __grid_con
 
 // FAST: every key and input column is 8 bytes wide without a NULL bitmap, no merge, no replay
 // list -- the loads are plain 8-byte loads and no per-aggregate NULL bookkeeping is needed.
-template <bool FAST>
+// K2: at most two key columns (the unrolled key loops shrink from eight to two iterations).
+template <bool FAST, bool K2>
 __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const __grid_constant__ GroupParams p) {
   constexpr int T = kTinyThreads;
+  constexpr int KMAX = K2 ? 2 : kMaxKeys;
   extern __shared__ unsigned long long t_acc[];                  // [kTinyGroups * n_aggs][T]
   __shared__ unsigned int t_seen[kTinyGroups][T];                // bit a: this thread saw a value of aggregate a
   __shared__ unsigned long long l_key[kTinyGroups][kMaxKeys];
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
   const long long stride = static_cast<long long>(gridDim.x) * T * R;
   for (long long base = static_cast<long long>(blockIdx.x) * T * R + tid; base < p.rows; base += stride) {
     long long rows_[R];
-    unsigned long long kv[R][kMaxKeys], vv[R][kLocalMaxAggs];
+    unsigned long long kv[R][KMAX], vv[R][kLocalMaxAggs];
     unsigned int knull[R], vnull[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
       knull[j] = 0;
       vnull[j] = 0;
 #pragma unroll
-      for (int c = 0; c < kMaxKeys; ++c) {
+      for (int c = 0; c < KMAX; ++c) {
         kv[j][c] = 0;
         if (c < NK && rows_[j] >= 0) {
           if (FAST) kv[j][c] = static_cast<const unsigned long long*>(p.key_data[c])[rows_[j]];
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
       if (row < 0) continue;
       unsigned long long fp = 0x9E3779B97F4A7C15ull + knull[j];
 #pragma unroll
-      for (int c = 0; c < kMaxKeys; ++c) if (c < NK) fp = (fp ^ kv[j][c]) * 0xff51afd7ed558ccdULL + c;
+      for (int c = 0; c < KMAX; ++c) if (c < NK) fp = (fp ^ kv[j][c]) * 0xff51afd7ed558ccdULL + c;
       int g = -1;
 #pragma unroll
       for (int e = 0; e < kTinyGroups; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
         // equal fingerprints: confirm on the key values (a different key restarts below)
         bool same = l_knull[g] == knull[j];
 #pragma unroll
-        for (int c = 0; c < kMaxKeys; ++c) if (c < NK) same = same && l_key[g][c] == kv[j][c];
+        for (int c = 0; c < KMAX; ++c) if (c < NK) same = same && l_key[g][c] == kv[j][c];
         if (!same) g = -1;
       }
       long long slot = -1;
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
           const unsigned int old = atomicCAS(&l_slot[e], 0u, want);
           if (old == 0u) {
 #pragma unroll
-            for (int c = 0; c < kMaxKeys; ++c) if (c < NK) l_key[e][c] = kv[j][c];
+            for (int c = 0; c < KMAX; ++c) if (c < NK) l_key[e][c] = kv[j][c];
             l_knull[e] = knull[j];
             l_fp[e] = fp;
             __threadfence_block();
@@ -1187,7 +1189,8 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
                  : (ag.fn == SSB_AGG_SUM && (ag.out_phys == T_I64 || ag.out_phys == T_U64)) ? TA_SUM_U64 : TA_OTHER;
         if (ag.in_phys >= 0 && (ag.in_nulls != nullptr || phys_width(ag.in_phys) != 8 || (ag.fn != SSB_AGG_COUNT && ag.in_phys != ag.out_phys))) tfast = false;
       }
-      auto kernel = tfast ? group_update_tiny_kernel<true> : group_update_tiny_kernel<false>;
+      auto kernel = g->n_keys <= 2 ? (tfast ? group_update_tiny_kernel<true, true> : group_update_tiny_kernel<false, true>)
+                                   : (tfast ? group_update_tiny_kernel<true, false> : group_update_tiny_kernel<false, false>);
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       long long per_sm = static_cast<long long>((ctx->smem_per_sm - 8192) / (smem + 8192));
       if (per_sm < 1) per_sm = 1;
@@ -1392,6 +1395,8 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   int rc = 0;
   long long offset = 0;
   // scratch of the unfused path (allocated on first use)
+  struct Part { ssb_program* prog; int first, last; bool owned; };
+  std::vector<Part> parts;
   std::vector<ssb_column> outs(n_out ? n_out : 1);
   long long outs_rows = 0;
   auto free_outs = [&]() {
@@ -1442,7 +1447,34 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
         if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "fused aggregate scratch"); break; }
         outs_rows = n;
       }
-      rc = ssb_program_run(sp, in2.data(), n, outs.data(), ctx->d_count);
+      if (parts.empty()) {
+        // Experiment (SSB200_GROUP_SPLIT=2): a wide plan evaluated as column groups that share the
+        // predicate, each with more resident CTAs. Measured slower on the Q1 shape (57 ms against
+        // 50 ms per 600M rows: the predicate's inputs are read twice), so one program is the default.
+        static const int split_env = getenv("SSB200_GROUP_SPLIT") ? atoi(getenv("SSB200_GROUP_SPLIT")) : -1;
+        int n_parts = split_env > 0 ? split_env : 1;
+        if (n_parts > n_out) n_parts = n_out;
+        if (n_parts <= 1) {
+          parts.push_back(Part{sp, 0, n_out, false});
+        } else {
+          for (int q = 0; q < n_parts && rc == 0; ++q) {
+            const int first = n_out * q / n_parts, last = n_out * (q + 1) / n_parts;
+            ssb_program* sub = nullptr;
+            rc = ssb_program_create(ctx, prog.nodes.data(), static_cast<int32_t>(prog.nodes.size()), n_in, prog.input_types.data(),
+                                    prog.input_nullable.data(), prog.outputs.data() + first, last - first, prog.predicate, &sub);
+            if (rc == 0) parts.push_back(Part{sub, first, last, true});
+          }
+          if (rc != 0) {   // a half does not compile on its own: the whole program does
+            for (size_t q = 0; q < parts.size(); ++q) if (parts[q].owned) ssb_program_destroy(parts[q].prog);
+            parts.clear();
+            parts.push_back(Part{sp, 0, n_out, false});
+            rc = 0;
+          }
+        }
+      }
+      for (size_t q = 0; q < parts.size() && rc == 0; ++q) {
+        rc = ssb_program_run(parts[q].prog, in2.data(), n, outs.data() + parts[q].first, ctx->d_count);
+      }
       if (rc) break;
       cudaError_t e = cudaMemcpyAsync(ctx->h_count, ctx->d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1455,6 +1487,11 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   }
   cudaStreamSynchronize(ctx->stream);
   free_outs();
+  for (size_t q = 0; q < parts.size(); ++q) {
+    if (!parts[q].owned) continue;
+    if (rc == 0) rc = ssb_program_check_failure(parts[q].prog);
+    ssb_program_destroy(parts[q].prog);
+  }
   if (rc == 0) rc = ssb_program_check_failure(sp);
   return rc;
 }

@@ -250,7 +250,44 @@ class GroupAggregateOptions {
 
 Operation* GroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
                           GroupAggregateOptions* options, Operation* child);          // aggregate.h:224
+// aggregate.h:230-250: may emit partial results under memory pressure in the reference; here the
+// aggregation always completes in HBM, which that contract allows.
+Operation* BestEffortGroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
+                                    GroupAggregateOptions* options, Operation* child);
 Operation* ScalarAggregate(AggregationSpecification* aggregation, Operation* child);  // aggregate.h:341
+
+// cursor/core/aggregator.h:37-112: the bound form of an AggregationSpecification (result schema
+// and per-aggregate types / nullability, aggregator.cc:63-152). The accumulators themselves live
+// in the GPU hash table of the cursor that receives the Aggregator.
+class Aggregator {
+ public:
+  static FailureOrOwned<Aggregator> Create(const AggregationSpecification& aggregation_specification,
+                                           const TupleSchema& input_schema, BufferAllocator* allocator,
+                                           rowcount_t result_initial_row_capacity);
+  ~Aggregator();
+  const TupleSchema& schema() const { return schema_; }
+  struct Impl;
+  const Impl* impl() const { return impl_; }
+  rowcount_t initial_row_capacity() const { return capacity_; }
+ private:
+  Aggregator() : impl_(NULL), capacity_(0) {}
+  TupleSchema schema_;
+  Impl* impl_;
+  rowcount_t capacity_;
+};
+
+// ---- cursors created directly from bound objects (the Bound* factories of cursor/core/*.h).
+// Ownership as in the reference: the bound objects and the child are taken over, allocators are not.
+Cursor* BoundScanView(const View& view);                                                          // scan_view.h:52
+FailureOrOwned<Cursor> BoundCompute(BoundExpressionTree* computation, BufferAllocator* allocator,
+                                    rowcount_t max_row_count, Cursor* child);                     // compute.h:36
+FailureOrOwned<Cursor> BoundFilter(BoundExpressionTree* predicate, const BoundSingleSourceProjector* projector,
+                                   BufferAllocator* buffer_allocator, Cursor* child_cursor);     // filter.h:43
+Cursor* BoundProject(const BoundSingleSourceProjector* projector, Cursor* child);                 // project.h:34
+FailureOrOwned<Cursor> BoundGroupAggregate(const BoundSingleSourceProjector* group_by, Aggregator* aggregator,
+                                           BufferAllocator* allocator, BufferAllocator* original_allocator,
+                                           bool best_effort, Cursor* child);                      // aggregate.h:254
+Cursor* BoundScalarAggregate(Aggregator* aggregator, Cursor* child);                              // aggregate.h:345
 
 // ---- hash join (cursor/core/hash_join.h:35-69) ---------------------------------------------
 class HashJoinOperation : public BasicOperation {
@@ -271,6 +308,7 @@ class HashJoinOperation : public BasicOperation {
 };
 
 // ---- sort (cursor/infrastructure/ordering.h:103-137, cursor/core/sort.h:89-131) -------------
+class BoundSortOrder;
 class SortOrder {
  public:
   SortOrder() {}
@@ -283,13 +321,35 @@ class SortOrder {
   SortOrder* OrderByNamedAttribute(const StringPiece& name, ColumnOrder order) { return add(ProjectNamedAttribute(name), order); }
   // Resolves to (source column, order) pairs, most significant first.
   FailureOrVoid Bind(const TupleSchema& schema, vector<std::pair<int, ColumnOrder> >* keys) const;
+  // ordering.h:127: the reference's bound form.
+  FailureOrOwned<const BoundSortOrder> Bind(const TupleSchema& source_schema) const;
  private:
   vector<std::pair<const SingleSourceProjector*, ColumnOrder> > keys_;
+};
+
+// cursor/infrastructure/ordering.h:48-101
+class BoundSortOrder {
+ public:
+  BoundSortOrder(const BoundSingleSourceProjector* projector, const vector<ColumnOrder>& column_order)
+      : projector_(projector), column_order_(column_order) {}
+  explicit BoundSortOrder(const BoundSingleSourceProjector* projector)
+      : projector_(projector), column_order_(projector->result_schema().attribute_count(), ASCENDING) {}
+  const TupleSchema& schema() const { return projector_->result_schema(); }
+  ColumnOrder column_order(int i) const { return column_order_[i]; }
+  const BoundSingleSourceProjector& projector() const { return *projector_; }
+ private:
+  std::unique_ptr<const BoundSingleSourceProjector> projector_;
+  vector<ColumnOrder> column_order_;
 };
 
 // memory_limit is accepted for API compatibility; the whole input is sorted in HBM.
 Operation* Sort(const SortOrder* sort_order, const SingleSourceProjector* result_projector,
                 size_t memory_limit, Operation* child);
+Operation* SortWithTempDirPrefix(const SortOrder* sort_order, const SingleSourceProjector* result_projector,
+                                 size_t memory_limit, StringPiece temporary_directory_prefix, Operation* child);  // sort.h:98
+FailureOrOwned<Cursor> BoundSort(const BoundSortOrder* sort_order, const BoundSingleSourceProjector* result_projector,
+                                 size_t memory_limit, StringPiece temporary_directory_prefix, BufferAllocator* allocator,
+                                 Cursor* child_cursor);                                            // sort.h:114
 
 }  // namespace supersonic
 #endif  // SUPERSONIC_B200_HOST_CURSOR_H_

@@ -189,7 +189,13 @@ class RowwiseCursor : public GpuCursor {
     int64 kept = 0;
     for (size_t g = 0; g < programs.size(); ++g) {
       vector<ssb_column> ic, oc;
-      for (size_t k = 0; k < programs[g]->used_inputs().size(); ++k) ic.push_back(col_of[programs[g]->used_inputs()[k]].col);
+      for (size_t k = 0; k < programs[g]->used_inputs().size(); ++k) {
+        const int idx = programs[g]->used_inputs()[k];
+        ssb_column c = col_of[idx].col;
+        // a GPU child hands every column over with a bitmap; a NOT_NULLABLE attribute never sets a bit
+        if (!plan_.base_schema.attribute(idx).is_nullable()) c.nulls = NULL;
+        ic.push_back(c);
+      }
       for (size_t j = g * group; j < result->columns.size() && j < (g + 1) * group; ++j) oc.push_back(result->columns[j].col);
       FailureOr<int64> n = programs[g]->Run(ic, rows, oc);
       PROPAGATE_ON_FAILURE(n);
@@ -490,6 +496,11 @@ struct BoundAggregation {
 };
 
 bool IsNumericType(DataType t) { return GetTypeInfo(t).is_numeric(); }
+}  // namespace
+struct Aggregator::Impl {
+  vector<BoundAggregation> aggs;
+};
+namespace {
 
 // cursor/core/aggregator.cc:63-152, column_aggregator.cc:520-566: result types and nullability.
 FailureOrVoid BindAggregations(const AggregationSpecification& spec, const TupleSchema& child,
@@ -605,6 +616,9 @@ class GroupCursor : public GpuCursor {
       rows = static_cast<int64>(plan.base.row_count());
       PROPAGATE_ON_FAILURE(UploadColumns(plan.base, program->used_inputs(), 0, plan.base.row_count(), &base));
       for (size_t k = 0; k < base.columns.size(); ++k) ic.push_back(base.columns[k].col);
+    }
+    for (size_t k = 0; k < ic.size(); ++k) {   // a NOT_NULLABLE attribute never sets a bit of the bitmap a GPU child hands over
+      if (!plan.base_schema.attribute(program->used_inputs()[k]).is_nullable()) ic[k].nulls = NULL;
     }
     vector<int32_t> key_types, key_nullable;
     for (size_t k = 0; k < keys_.size(); ++k) {
@@ -918,6 +932,154 @@ FailureOrVoid DescribeAny(const Operation* op, RowwisePlan* plan) {
 }
 
 }  // namespace internal
+
+// ------------------------------------------------------------------ Bound* factories
+// The cursors above already work on bound objects (expression nodes over the child's schema,
+// column positions, bound aggregations); the Bound* factories of the reference hand exactly
+// those over, so each one only repackages its arguments.
+Cursor* BoundScanView(const View& view) { return new ViewCursor(view); }
+
+namespace {
+RowwisePlan PlanOverCursor(Cursor* child) {
+  RowwisePlan plan;
+  plan.source.reset(child);
+  plan.base_schema = child->schema();
+  plan.base = View(plan.base_schema);
+  plan.schema = plan.base_schema;
+  for (int i = 0; i < plan.schema.attribute_count(); ++i) plan.outputs.push_back(MakeInputNode(plan.schema, i));
+  return plan;
+}
+}  // namespace
+
+FailureOrOwned<Cursor> BoundCompute(BoundExpressionTree* computation, BufferAllocator* allocator, rowcount_t,
+                                    Cursor* child) {
+  std::unique_ptr<BoundExpressionTree> tree(computation);
+  RowwisePlan plan = PlanOverCursor(child);
+  plan.outputs.clear();
+  for (int i = 0; i < tree->root()->column_count(); ++i) plan.outputs.push_back(tree->root()->node(i));
+  plan.schema = tree->result_schema();
+  return Success(static_cast<Cursor*>(new RowwiseCursor(plan, allocator, COMPUTE)));
+}
+
+FailureOrOwned<Cursor> BoundFilter(BoundExpressionTree* predicate, const BoundSingleSourceProjector* projector,
+                                   BufferAllocator* buffer_allocator, Cursor* child_cursor) {
+  std::unique_ptr<BoundExpressionTree> tree(predicate);
+  std::unique_ptr<const BoundSingleSourceProjector> proj(projector);
+  std::unique_ptr<Cursor> child(child_cursor);
+  // cursor/core/filter.cc:79-87
+  if (tree->root()->column_count() != 1) {
+    THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "Predicate has to return exactly one column in (" +
+                                                            tree->result_schema().GetHumanReadableSpecification() + ")"));
+  }
+  if (tree->result_schema().attribute(0).type() != BOOL) {
+    THROW(new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, "Predicate has to return a BOOL column in (" +
+                                                           tree->result_schema().GetHumanReadableSpecification() + ")"));
+  }
+  RowwisePlan plan = PlanOverCursor(child.release());
+  vector<NodePtr> outs;
+  for (int i = 0; i < proj->result_schema().attribute_count(); ++i) outs.push_back(plan.outputs[proj->source_attribute_position(i)]);
+  plan.outputs = outs;
+  plan.schema = proj->result_schema();
+  plan.predicate = tree->root()->node(0);
+  return Success(static_cast<Cursor*>(new RowwiseCursor(plan, buffer_allocator, FILTER)));
+}
+
+Cursor* BoundProject(const BoundSingleSourceProjector* projector, Cursor* child) {
+  std::unique_ptr<const BoundSingleSourceProjector> proj(projector);
+  RowwisePlan plan = PlanOverCursor(child);
+  vector<NodePtr> outs;
+  for (int i = 0; i < proj->result_schema().attribute_count(); ++i) outs.push_back(plan.outputs[proj->source_attribute_position(i)]);
+  plan.outputs = outs;
+  plan.schema = proj->result_schema();
+  return new RowwiseCursor(plan, HeapBufferAllocator::Get(), PROJECT);
+}
+
+Aggregator::~Aggregator() { delete impl_; }
+
+FailureOrOwned<Aggregator> Aggregator::Create(const AggregationSpecification& aggregation_specification,
+                                              const TupleSchema& input_schema, BufferAllocator*,
+                                              rowcount_t result_initial_row_capacity) {
+  std::unique_ptr<Aggregator> a(new Aggregator);
+  a->impl_ = new Impl;
+  a->capacity_ = result_initial_row_capacity;
+  PROPAGATE_ON_FAILURE(BindAggregations(aggregation_specification, input_schema, &a->impl_->aggs, &a->schema_));
+  return Success(a.release());
+}
+
+FailureOrOwned<Cursor> BoundGroupAggregate(const BoundSingleSourceProjector* group_by, Aggregator* aggregator,
+                                           BufferAllocator* allocator, BufferAllocator* original_allocator, bool,
+                                           Cursor* child) {
+  std::unique_ptr<const BoundSingleSourceProjector> proj(group_by);
+  std::unique_ptr<Aggregator> agg(aggregator);
+  std::unique_ptr<Cursor> child_cursor(child);
+  // the reference takes ownership of `allocator` unless it is the original one (aggregate.h:258-260)
+  std::unique_ptr<BufferAllocator> owned(allocator != original_allocator && allocator != HeapBufferAllocator::Get() ? allocator : NULL);
+  TupleSchema result;
+  vector<int> keys;
+  for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+    keys.push_back(proj->source_attribute_position(i));
+    result.add_attribute(proj->result_schema().attribute(i));
+    const DataType t = proj->result_schema().attribute(i).type();
+    if (t == STRING || t == BINARY) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length group keys are not on the B200 hot path (SURVEY 8f)"));
+    }
+  }
+  for (int i = 0; i < agg->schema().attribute_count(); ++i) {
+    if (!result.add_attribute(agg->schema().attribute(i))) {
+      THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + agg->schema().attribute(i).name() + "' in result schema"));
+    }
+  }
+  BufferAllocator* use = original_allocator ? original_allocator : HeapBufferAllocator::Get();
+  return Success(static_cast<Cursor*>(new GroupCursor(result, use, child_cursor.release(), keys, agg->impl()->aggs,
+                                                      static_cast<size_t>(agg->initial_row_capacity()), false)));
+}
+
+Cursor* BoundScalarAggregate(Aggregator* aggregator, Cursor* child) {
+  std::unique_ptr<Aggregator> agg(aggregator);
+  return new GroupCursor(agg->schema(), HeapBufferAllocator::Get(), child, vector<int>(), agg->impl()->aggs, 0, true);
+}
+
+FailureOrOwned<const BoundSortOrder> SortOrder::Bind(const TupleSchema& source_schema) const {
+  vector<std::pair<int, ColumnOrder> > keys;
+  PROPAGATE_ON_FAILURE(Bind(source_schema, &keys));
+  std::unique_ptr<BoundSingleSourceProjector> proj(new BoundSingleSourceProjector(source_schema));
+  vector<ColumnOrder> orders;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (!proj->Add(keys[i].first)) THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute in the sort order"));
+    orders.push_back(keys[i].second);
+  }
+  return Success(static_cast<const BoundSortOrder*>(new BoundSortOrder(proj.release(), orders)));
+}
+
+FailureOrOwned<Cursor> BoundSort(const BoundSortOrder* sort_order, const BoundSingleSourceProjector* result_projector,
+                                 size_t, StringPiece, BufferAllocator* allocator, Cursor* child_cursor) {
+  std::unique_ptr<const BoundSortOrder> order(sort_order);
+  std::unique_ptr<const BoundSingleSourceProjector> proj(result_projector);
+  std::unique_ptr<Cursor> child(child_cursor);
+  vector<std::pair<int, ColumnOrder> > keys;
+  for (int i = 0; i < order->schema().attribute_count(); ++i) {
+    keys.push_back(std::make_pair(order->projector().source_attribute_position(i), order->column_order(i)));
+  }
+  vector<int> projected;
+  TupleSchema result;
+  if (proj) {
+    result = proj->result_schema();
+    for (int i = 0; i < result.attribute_count(); ++i) projected.push_back(proj->source_attribute_position(i));
+  } else {
+    result = child->schema();
+    for (int i = 0; i < result.attribute_count(); ++i) projected.push_back(i);
+  }
+  return Success(static_cast<Cursor*>(new SortCursor(result, allocator, child.release(), keys, projected)));
+}
+
+Operation* BestEffortGroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
+                                    GroupAggregateOptions* options, Operation* child) {
+  return new GroupAggregateOperation(group_by, aggregation, options, child);
+}
+Operation* SortWithTempDirPrefix(const SortOrder* sort_order, const SingleSourceProjector* result_projector,
+                                 size_t memory_limit, StringPiece, Operation* child) {
+  return Sort(sort_order, result_projector, memory_limit, child);
+}
 
 // ------------------------------------------------------------------ factories
 Operation* ScanView(const View& view) { return new ScanViewOperation(view); }

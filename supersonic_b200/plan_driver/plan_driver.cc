@@ -13,6 +13,12 @@
 //     (scalar_agg (aggs AGG...) OP)              ScalarAggregate
 //     (hash_join INNER|LEFT_OUTER PROJ PROJ MPROJ UNIQUE|NOT_UNIQUE OP OP)
 //     (sort (order (NAME ASC|DESC)...) PROJ OP)  Sort
+//   The bound_* forms build the same cursors through the Bound* factories (BoundCompute,
+//   BoundFilter, BoundProject, BoundScanView, BoundGroupAggregate, BoundScalarAggregate, BoundSort):
+//   the child is created first, the expression / projector / aggregation is bound against its schema.
+//     (bound_scan N) (bound_compute EXPR OP) (bound_filter EXPR PROJ OP) (bound_project PROJ OP)
+//     (bound_group PROJ (aggs AGG...) OP) (bound_scalar_agg (aggs AGG...) OP)
+//     (bound_sort (order (NAME ASC|DESC)...) PROJ OP)
 //   AGG   := (SUM|MIN|MAX|COUNT|FIRST|LAST in out [TYPE]) | (distinct FN in out)
 //   PROJ  := (all) | (all PREFIX) | (named N...) | (at I...) | (rename (N A)...) | (cat PROJ...)
 //   MPROJ := (multi (SRC PROJ)...)
@@ -32,6 +38,7 @@
 #include <vector>
 
 #include "supersonic/supersonic.h"
+#include "supersonic/cursor/core/aggregator.h"
 
 namespace {
 
@@ -371,6 +378,90 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
   throw ParseError{"unknown operation '" + h + "'"};
 }
 
+// A failure raised while cursors are created bottom-up through the Bound* factories.
+struct BindError {
+  int code;
+  std::string msg;
+};
+
+struct Keep {
+  std::vector<std::unique_ptr<Operation> > ops;   // operations outlive the cursors created from them
+};
+
+template <typename T>
+T* Take(FailureOrOwned<T> r) {
+  if (r.is_failure()) throw BindError{r.exception().return_code(), r.exception().message()};
+  return r.release();
+}
+
+Cursor* BuildCursor(const Sx& s, const Inputs& in, Keep* keep) {
+  const std::string& h = Head(s);
+  BufferAllocator* heap = HeapBufferAllocator::Get();
+  if (h == "bound_scan") {
+    Arity(s, 1);
+    size_t n = static_cast<size_t>(atoi(Atom(s.kids[1]).c_str()));
+    if (n >= in.views.size()) throw ParseError{"scan: no such table"};
+    return BoundScanView(in.views[n]);
+  }
+  if (h == "bound_compute") {
+    Arity(s, 2);
+    std::unique_ptr<const Expression> e(BuildExpr(s.kids[1]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[2], in, keep));
+    BoundExpressionTree* tree = Take(e->Bind(child->schema(), heap, Cursor::kDefaultRowCount));
+    return Take(BoundCompute(tree, heap, Cursor::kDefaultRowCount, child.release()));
+  }
+  if (h == "bound_filter") {
+    Arity(s, 3);
+    std::unique_ptr<const Expression> e(BuildExpr(s.kids[1]));
+    std::unique_ptr<const SingleSourceProjector> p(BuildProjector(s.kids[2]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[3], in, keep));
+    BoundExpressionTree* tree = Take(e->Bind(child->schema(), heap, Cursor::kDefaultRowCount));
+    std::unique_ptr<BoundExpressionTree> tree_owner(tree);
+    const BoundSingleSourceProjector* bp = Take(p->Bind(child->schema()));
+    return Take(BoundFilter(tree_owner.release(), bp, heap, child.release()));
+  }
+  if (h == "bound_project") {
+    Arity(s, 2);
+    std::unique_ptr<const SingleSourceProjector> p(BuildProjector(s.kids[1]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[2], in, keep));
+    const BoundSingleSourceProjector* bp = Take(p->Bind(child->schema()));
+    return BoundProject(bp, child.release());
+  }
+  if (h == "bound_group" || h == "bound_scalar_agg") {
+    const bool scalar = h == "bound_scalar_agg";
+    Arity(s, scalar ? 2 : 3);
+    std::unique_ptr<const SingleSourceProjector> p(scalar ? NULL : BuildProjector(s.kids[1]));
+    std::unique_ptr<AggregationSpecification> a(BuildAggs(s.kids[scalar ? 1 : 2]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[scalar ? 2 : 3], in, keep));
+    if (scalar) {
+      Aggregator* agg = Take(Aggregator::Create(*a, child->schema(), heap, 1));
+      return BoundScalarAggregate(agg, child.release());
+    }
+    std::unique_ptr<BufferAllocator> limit(new MemoryLimit(static_cast<size_t>(1) << 40, heap));
+    std::unique_ptr<const BoundSingleSourceProjector> bp(Take(p->Bind(child->schema())));
+    Aggregator* agg = Take(Aggregator::Create(*a, child->schema(), limit.get(), 16));
+    return Take(BoundGroupAggregate(bp.release(), agg, limit.release(), heap, false, child.release()));
+  }
+  if (h == "bound_sort") {
+    Arity(s, 3);
+    if (Head(s.kids[1]) != "order") throw ParseError{"expected (order ...)"};
+    std::unique_ptr<SortOrder> order(new SortOrder);
+    for (size_t i = 1; i < s.kids[1].kids.size(); ++i) {
+      const Sx& k = s.kids[1].kids[i];
+      if (k.atom || k.kids.size() != 2) throw ParseError{"order takes (NAME ASC|DESC) pairs"};
+      order->add(ProjectNamedAttribute(Atom(k.kids[0])), Atom(k.kids[1]) == "ASC" ? ASCENDING : DESCENDING);
+    }
+    std::unique_ptr<const SingleSourceProjector> p(BuildProjector(s.kids[2]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[3], in, keep));
+    std::unique_ptr<const BoundSortOrder> bo(Take(order->Bind(child->schema())));
+    const BoundSingleSourceProjector* bp = Take(p->Bind(child->schema()));
+    return Take(BoundSort(bo.release(), bp, static_cast<size_t>(1) << 40, "", heap, child.release()));
+  }
+  // an unbound operation below a bound one: create its cursor the usual way
+  keep->ops.push_back(std::unique_ptr<Operation>(BuildOp(s, in)));
+  return Take(keep->ops.back()->CreateCursor());
+}
+
 double WallNow() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -426,24 +517,39 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
   }
 
   std::unique_ptr<Operation> op;
+  Keep keep;
+  std::unique_ptr<Cursor> cursor;
+  double t0 = WallNow();
   try {
     Sx sx = SxParser(plan).Parse();
-    op.reset(BuildOp(sx, in));
+    if (Head(sx).compare(0, 6, "bound_") == 0) {
+      t0 = WallNow();
+      cursor.reset(BuildCursor(sx, in, &keep));
+      r->create_s = WallNow() - t0;
+    } else {
+      op.reset(BuildOp(sx, in));
+    }
   } catch (const ParseError& e) {
     r->code = ERROR_BAD_PROTO;
     r->error = "plan parse error: " + e.msg;
     return r->code;
-  }
-
-  double t0 = WallNow();
-  FailureOrOwned<Cursor> created = op->CreateCursor();
-  r->create_s = WallNow() - t0;
-  if (created.is_failure()) {
-    r->code = created.exception().return_code();
-    r->error = created.exception().message();
+  } catch (const BindError& e) {
+    r->code = e.code;
+    r->error = e.msg;
     return r->code;
   }
-  std::unique_ptr<Cursor> cursor(created.release());
+
+  if (!cursor) {
+    t0 = WallNow();
+    FailureOrOwned<Cursor> created = op->CreateCursor();
+    r->create_s = WallNow() - t0;
+    if (created.is_failure()) {
+      r->code = created.exception().return_code();
+      r->error = created.exception().message();
+      return r->code;
+    }
+    cursor.reset(created.release());
+  }
 
   const TupleSchema& schema = cursor->schema();
   r->cols.resize(schema.attribute_count());

@@ -252,3 +252,46 @@ def _sorted(cols, sort_cols):
         keys.append(n)
     order = np.lexsort(keys)
     return [(v[order], n[order]) for v, n in cols]
+
+
+# ---------------------------------------------------------------------------------------------
+# The Bound* factories (cursor/core/compute.h:36, filter.h:43, project.h:34, scan_view.h:52,
+# aggregate.h:254,345, sort.h:114): each pair is the same plan through the Operation factories and
+# through the bound ones; both must give the same result, on the oracle and on the GPU.
+def bound_tables():
+    import numpy as np
+    from supersonic_b200 import ssplan as sp
+    rng = np.random.default_rng(99)
+    n = 20_000
+    return [[sp.Column("a", sp.INT64, rng.integers(-1000, 1000, n), is_null=rng.random(n) < 0.05),
+             sp.Column("b", sp.INT64, rng.integers(0, 50, n)),
+             sp.Column("x", sp.DOUBLE, rng.integers(0, 4096, n) / 8.0),
+             sp.Column("k", sp.INT32, rng.integers(0, 7, n).astype(np.int32))]]
+
+
+BOUND_PAIRS = [
+    ("compute",
+     "(compute (compound (as s (plus (col a) (col b))) (col x)) (scan 0))",
+     "(bound_compute (compound (as s (plus (col a) (col b))) (col x)) (bound_scan 0))", True),
+    ("filter",
+     "(filter (less (col b) (i64 10)) (named a x) (scan 0))",
+     "(bound_filter (less (col b) (i64 10)) (named a x) (bound_scan 0))", True),
+    ("project",
+     "(project (named x k) (scan 0))",
+     "(bound_project (named x k) (bound_scan 0))", True),
+    ("filter_over_compute",
+     "(filter (greater (col s) (i64 0)) (all) (compute (compound (as s (plus (col a) (col b))) (col k)) (scan 0)))",
+     "(bound_filter (greater (col s) (i64 0)) (all) (bound_compute (compound (as s (plus (col a) (col b))) (col k)) (scan 0)))", True),
+    ("group",
+     "(group (named k) (aggs (SUM x sx) (COUNT a ca) (MIN a mn) (COUNT \"\" n)) (scan 0))",
+     "(bound_group (named k) (aggs (SUM x sx) (COUNT a ca) (MIN a mn) (COUNT \"\" n)) (bound_scan 0))", False),
+    ("scalar_agg",
+     "(scalar_agg (aggs (SUM x sx) (MAX a mx) (COUNT \"\" n)) (scan 0))",
+     "(bound_scalar_agg (aggs (SUM x sx) (MAX a mx) (COUNT \"\" n)) (bound_scan 0))", True),
+    ("sort",
+     "(sort (order (k ASC) (x DESC) (b ASC) (a ASC)) (all) (scan 0))",
+     "(bound_sort (order (k ASC) (x DESC) (b ASC) (a ASC)) (all) (bound_scan 0))", False),
+    ("group_over_bound_filter",
+     "(group (named k) (aggs (SUM b sb)) (filter (less (col b) (i64 25)) (all) (scan 0)))",
+     "(bound_group (named k) (aggs (SUM b sb)) (bound_filter (less (col b) (i64 25)) (all) (bound_scan 0)))", False),
+]

@@ -11,3 +11,17 @@ def test_oracle_reproduces_reference_vectors(ref, case, next_rows):
     _, plan, tables, expected, ordered = case
     r = ref.run(plan, tables, next_max_rows=next_rows)
     check_result(r, expected, ordered)
+
+
+from cases import BOUND_PAIRS, bound_tables, same_results  # noqa: E402
+
+
+@pytest.mark.parametrize("pair", BOUND_PAIRS, ids=[p[0] for p in BOUND_PAIRS])
+def test_oracle_bound_factories_equal_operation_factories(ref, pair):
+    """The plan driver's bound_* verbs (BoundCompute, BoundFilter, ... of the reference) give what
+    the Operation factories give: pins the driver code the GPU parity tests then reuse."""
+    name, unbound, bound, ordered = pair
+    tables = bound_tables()
+    a, b = ref.run(unbound, tables), ref.run(bound, tables)
+    assert a.code == 0 and b.code == 0, (a.error, b.error)
+    same_results(a, b, ordered=ordered, sort_cols=None if ordered else list(range(len(a.columns))))

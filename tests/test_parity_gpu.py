@@ -287,3 +287,25 @@ def test_q1_shape(ref, b200):
             "(filter (less_or_equal (col ship) (i64 2450)) (all) (scan 0))))")
     # dyadic payloads: products and sums stay exactly representable -> bit-exact in any order
     same_results(ref.run(plan, [cols]), b200.run(plan, [cols]), ordered=False, sort_cols=[0, 1])
+
+
+from cases import BOUND_PAIRS, bound_tables  # noqa: E402
+
+
+@pytest.mark.parametrize("pair", BOUND_PAIRS, ids=[p[0] for p in BOUND_PAIRS])
+def test_bound_factories(ref, b200, pair):
+    """BoundCompute / BoundFilter / BoundProject / BoundScanView / BoundGroupAggregate /
+    BoundScalarAggregate / BoundSort of the mirror against the reference's."""
+    name, unbound, bound, ordered = pair
+    tables = bound_tables()
+    want, got = ref.run(bound, tables), b200.run(bound, tables)
+    assert want.code == 0 and got.code == 0, (want.error, got.error)
+    assert want.names == got.names and want.dtypes == got.dtypes
+    same_results(want, got, ordered=ordered, sort_cols=None if ordered else list(range(len(want.columns))))
+
+
+def test_bound_filter_rejects_non_bool_predicate(ref, b200):
+    tables = bound_tables()
+    plan = "(bound_filter (plus (col a) (col b)) (all) (bound_scan 0))"
+    want, got = ref.run(plan, tables), b200.run(plan, tables)
+    assert want.code != 0 and got.code == want.code

@@ -499,7 +499,7 @@ def run_b200(args):
                          "api": "supersonic::Filter/Compute/ScanView cursors via the plan driver, pinned host views"}
         # ---- CPU baseline: the reference itself, one thread, bounded sample
         result["cpu_baseline"] = cpu_reference_sample(args.cpu_rows, threads=1)
-        print(json.dumps(result))
+        emit(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 
@@ -560,10 +560,29 @@ def run_reference(args):
            "cpu_baseline": dict(base, value=v),
            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(json.dumps(out))
+
+
+_RESULT_STREAM = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that libraries print there (NCCL's
+    version banner, for one) is sent to stderr by pointing fd 1 at fd 2 for the run."""
+    global _RESULT_STREAM
+    sys.stdout.flush()
+    _RESULT_STREAM = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_STREAM or sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -49,6 +49,20 @@ __global__ void __launch_bounds__(256) group_update_kernel(const __grid_constant
         for (int a = 0; a < p.n_aggs; ++a) {
           const AggDev& ag = p.agg[a];
           if (ag.in_phys >= 0 && bit_at(ag.in_nulls, row)) continue;
+          if (ag.fn == SSB_AGG_FIRST || ag.fn == SSB_AGG_LAST) {
+            // the first / last non-NULL input in row order (column_aggregator.cc:108-166 walks the
+            // rows in order): the launch only elects the row, first_last_resolve_kernel fetches it
+            if (p.merge) {   // partial tables hold one row per group: plain stores, `dst` rows come first
+              const unsigned long long v = load_raw(ag.in_data, ag.in_phys, row);
+              if (ag.fn == SSB_AGG_LAST || ag.seen[slot] == 0u) ag.acc[static_cast<unsigned long long>(slot) * ag.stride] = v;
+              ag.seen[slot] = 1u;
+            } else if (ag.fn == SSB_AGG_FIRST) {
+              atomicMin(&ag.cand[slot], static_cast<unsigned long long>(row));
+            } else {
+              atomicMax(&ag.cand[slot], static_cast<unsigned long long>(row) + 1ull);
+            }
+            continue;
+          }
           unsigned long long v = 0, cnt = 1;
           if (ag.in_phys >= 0) {
             v = load_raw(ag.in_data, ag.in_phys, row);
@@ -99,6 +113,31 @@ __global__ void __launch_bounds__(256) group_update_kernel(const __grid_constant
       if (leader && my_has) {
         apply(ag, slot, my_v, my_c);
         if (ag.seen != nullptr) ag.seen[slot] = 1u;
+      }
+    }
+  }
+}
+
+// FIRST / LAST: after every launch, each slot takes the value of the row the launch elected
+// (FIRST only while the group has no value yet: earlier launches hold earlier rows).
+__global__ void first_last_resolve_kernel(const __grid_constant__ GroupParams p, unsigned long long total_slots) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long s = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; s < total_slots; s += stride) {
+    for (int a = 0; a < p.n_aggs; ++a) {
+      const AggDev& ag = p.agg[a];
+      if (ag.cand == nullptr) continue;
+      const unsigned long long c = ag.cand[s];
+      if (ag.fn == SSB_AGG_FIRST) {
+        if (c == ~0ull) continue;
+        ag.cand[s] = ~0ull;
+        if (ag.seen[s] != 0u) continue;
+        ag.acc[s * ag.stride] = convert_value(load_raw(ag.in_data, ag.in_phys, static_cast<long long>(c)), ag.in_phys, ag.out_phys);
+        ag.seen[s] = 1u;
+      } else {
+        if (c == 0ull) continue;
+        ag.cand[s] = 0ull;
+        ag.acc[s * ag.stride] = convert_value(load_raw(ag.in_data, ag.in_phys, static_cast<long long>(c - 1ull)), ag.in_phys, ag.out_phys);
+        ag.seen[s] = 1u;
       }
     }
   }
@@ -913,6 +952,8 @@ struct ssb_group {
   uint32_t* key_store_null;
   unsigned long long* acc[kMaxAggs];
   uint32_t* seen[kMaxAggs];
+  unsigned long long* cand[kMaxAggs];   // FIRST / LAST candidates
+  bool has_first_last;
   unsigned long long* counters;   // [0] n_groups, [1] n_deferred
   unsigned long long* h_counters; // pinned
   long long* deferred;
@@ -957,7 +998,11 @@ static void free_table(ssb_group* g) {
   tmp_free(ctx, g->slot_state); g->slot_state = nullptr;
   for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, g->key_store[c]); g->key_store[c] = nullptr; }
   tmp_free(ctx, g->key_store_null); g->key_store_null = nullptr;
-  for (int a = 0; a < kMaxAggs; ++a) { g->acc[a] = nullptr; tmp_free(ctx, g->seen[a]); g->seen[a] = nullptr; }
+  for (int a = 0; a < kMaxAggs; ++a) {
+    g->acc[a] = nullptr;
+    tmp_free(ctx, g->seen[a]); g->seen[a] = nullptr;
+    tmp_free(ctx, g->cand[a]); g->cand[a] = nullptr;
+  }
 }
 
 static unsigned fill_grid(ssb_ctx* ctx, unsigned long long n) {
@@ -1001,9 +1046,14 @@ static int alloc_table(ssb_group* g, unsigned long long capacity) {
   for (int a = 0; a < g->n_aggs; ++a) {
     // `seen` decides NULL-ness of SUM/MIN/MAX results; only inputs that can be NULL need it
     // (a ScalarAggregate over an empty input is NULL as well: aggregate_scalar.cc:40-90)
-    if (g->aggs[a].fn != SSB_AGG_COUNT && (g->aggs[a].in_nullable || g->n_keys == 0)) {
+    const bool first_last = g->aggs[a].fn == SSB_AGG_FIRST || g->aggs[a].fn == SSB_AGG_LAST;
+    if (g->aggs[a].fn != SSB_AGG_COUNT && (g->aggs[a].in_nullable || g->n_keys == 0 || first_last)) {
       SSB_CUDA(ctx, tmp_malloc(ctx, &g->seen[a], total * 4));
       SSB_CUDA(ctx, cudaMemsetAsync(g->seen[a], 0, total * 4, ctx->stream));
+    }
+    if (first_last) {
+      SSB_CUDA(ctx, tmp_malloc(ctx, &g->cand[a], total * 8));
+      SSB_CUDA(ctx, cudaMemsetAsync(g->cand[a], g->aggs[a].fn == SSB_AGG_FIRST ? 0xff : 0, total * 8, ctx->stream));
     }
   }
   SSB_CUDA(ctx, cudaGetLastError());
@@ -1034,6 +1084,7 @@ static void fill_table_params(const ssb_group* g, GroupParams* p) {
     p->agg[a].acc = g->acc[a];
     p->agg[a].stride = static_cast<uint32_t>(g->stride);
     p->agg[a].seen = g->seen[a];
+    p->agg[a].cand = g->cand[a];
   }
 }
 
@@ -1128,7 +1179,7 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     p.warp_combine = 0;   // superseded by the shared-memory kernel for few groups
     cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
     // few groups so far (and few enough aggregates): CTA-private shared-memory tables
-    const bool few = g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst && g->h_counters[0] <= 256));
+    const bool few = !g->has_first_last && g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst && g->h_counters[0] <= 256));
     // single packed 8-byte key, COUNT or same-type 8-byte aggregates, no NULL bitmaps, no replay
     for (int a = 0; a < g->n_aggs; ++a) {
       AggDev& ag = p.agg[a];
@@ -1138,7 +1189,7 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     }
     static const bool tiny_enabled = getenv("SSB200_GROUP_TINY") == nullptr || atoi(getenv("SSB200_GROUP_TINY")) != 0;
     static const bool fast_enabled = getenv("SSB200_GROUP_FAST") == nullptr || atoi(getenv("SSB200_GROUP_FAST")) != 0;
-    bool fast = fused == nullptr && fast_enabled && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1 &&
+    bool fast = fused == nullptr && fast_enabled && !g->has_first_last && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1 &&
                 phys_width(p.key_phys[0]) == 8 && p.key_nulls[0] == nullptr;
     for (int a = 0; fast && a < g->n_aggs; ++a) {
       const AggDev& ag = p.agg[a];
@@ -1207,6 +1258,10 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
       group_update_kernel<<<update_grid(ctx, remaining), 256, 0, ctx->stream>>>(p);
     }
     ++ctx->launches;
+    if (g->has_first_last && !merge) {
+      first_last_resolve_kernel<<<fill_grid(ctx, g->capacity + 2), 256, 0, ctx->stream>>>(p, g->capacity + 2);
+      ++ctx->launches;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { tmp_free(ctx, d_params); rc = cuda_fail(ctx, e, "group_update_kernel"); break; }
     if ((rc = read_counters(g))) { tmp_free(ctx, d_params); break; }
@@ -1277,8 +1332,8 @@ int ssb_group_create(ssb_ctx* ctx, int32_t n_keys, const int32_t* key_types, con
   }
   for (int a = 0; a < n_aggs; ++a) {
     const ssb_agg_spec& s = aggs[a];
-    if (s.fn == SSB_AGG_FIRST || s.fn == SSB_AGG_LAST) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "FIRST/LAST aggregates are not implemented on the GPU yet");
-    if (s.fn != SSB_AGG_SUM && s.fn != SSB_AGG_MIN && s.fn != SSB_AGG_MAX && s.fn != SSB_AGG_COUNT) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "unknown aggregate function");
+    if (s.fn != SSB_AGG_SUM && s.fn != SSB_AGG_MIN && s.fn != SSB_AGG_MAX && s.fn != SSB_AGG_COUNT &&
+        s.fn != SSB_AGG_FIRST && s.fn != SSB_AGG_LAST) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "unknown aggregate function");
     if (phys_of(s.out_type) < 0 || (s.input >= 0 && phys_of(s.in_type) < 0)) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported aggregate type");
     if (s.fn != SSB_AGG_COUNT && s.input < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "aggregate without input");
     if (s.fn == SSB_AGG_SUM && phys_of(s.out_type) == T_B8) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "SUM of BOOL");
@@ -1293,6 +1348,7 @@ int ssb_group_create(ssb_ctx* ctx, int32_t n_keys, const int32_t* key_types, con
   g->key_nullable.assign(key_nullable, key_nullable + n_keys);
   g->aggs.assign(aggs, aggs + n_aggs);
   g->packed = n_keys <= 1;
+  for (int a = 0; a < n_aggs; ++a) if (aggs[a].fn == SSB_AGG_FIRST || aggs[a].fn == SSB_AGG_LAST) g->has_first_last = true;
   unsigned long long cap = 1ull << 16;
   if (n_keys == 0) cap = 2;
   const unsigned long long want = expected_groups > 0 ? static_cast<unsigned long long>(expected_groups) * 2 : (1ull << 20);
@@ -1370,7 +1426,7 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   // expr_kernel); the default is the sliced two-kernel form below, whose scratch is bounded by
   // the slice, not by the table.
   static const bool fused_enabled = getenv("SSB200_GROUP_FUSED") != nullptr && atoi(getenv("SSB200_GROUP_FUSED")) != 0;
-  const bool rows_feasible = A >= 1 && A <= kLocalMaxAggs && n_in <= kRowMaxIn && n_out <= kRowMaxOut &&
+  const bool rows_feasible = !g->has_first_last && A >= 1 && A <= kLocalMaxAggs && n_in <= kRowMaxIn && n_out <= kRowMaxOut &&
                              static_cast<int>(prog.generic.size()) <= kRowMaxInsn && smem + 8192 <= ctx->smem_optin;
   const bool feasible = fused_enabled && rows_feasible;
   // The aggregation sink inside expr_kernel (tile-wide superinstructions, no output staging, no

@@ -26,6 +26,8 @@ struct AggDev {
   uint32_t stride;
   uint32_t pad;
   uint32_t* seen;            // [capacity + 2] or NULL (input not nullable and not merging)
+  unsigned long long* cand;  // FIRST / LAST: candidate row of the current launch per slot (FIRST: smallest row,
+                             // ~0 = none; LAST: largest row + 1, 0 = none); resolved after every launch
 };
 
 struct GroupParams {

@@ -309,3 +309,27 @@ def test_bound_filter_rejects_non_bool_predicate(ref, b200):
     plan = "(bound_filter (plus (col a) (col b)) (all) (bound_scan 0))"
     want, got = ref.run(plan, tables), b200.run(plan, tables)
     assert want.code != 0 and got.code == want.code
+
+
+@pytest.mark.parametrize("n,groups", [(5000, 7), (300_000, 1000), (300_000, 5)])
+def test_group_first_last(ref, b200, n, groups):
+    """FIRST / LAST = the first / last non-NULL input of the group in input order
+    (column_aggregator.cc:108-166); 300k rows cross the slices the GPU path feeds separately."""
+    rng = np.random.default_rng(n + groups)
+    cols = [sp.Column("k", sp.INT64, rng.integers(0, groups, n)),
+            sp.Column("a", sp.INT64, rng.integers(-10**9, 10**9, n), is_null=rng.random(n) < 0.3),
+            sp.Column("x", sp.DOUBLE, rng.random(n)),
+            sp.Column("c", sp.INT32, rng.integers(-1000, 1000, n).astype(np.int32), is_null=rng.random(n) < 0.9)]
+    plan = ("(group (named k) (aggs (FIRST a fa) (LAST a la) (FIRST x fx) (LAST x lx) (FIRST c fc) (LAST c lc) "
+            "(SUM x sx) (COUNT a ca)) (scan 0))")
+    want, got = ref.run(plan, [cols]), b200.run(plan, [cols])
+    assert want.code == 0 and got.code == 0, (want.error, got.error)
+    # SUM(x) of uniform doubles reorders on the GPU: compare it separately within a tolerance
+    sx = want.names.index("sx")
+    ow, og = np.argsort(want.columns[0]), np.argsort(got.columns[0])
+    assert np.allclose(want.columns[sx][ow], got.columns[sx][og], rtol=1e-12)
+    for r in (want, got):
+        r.columns[sx] = np.zeros_like(r.columns[sx])
+    same_results(want, got, ordered=False, sort_cols=[0])
+    plan2 = "(scalar_agg (aggs (FIRST a fa) (LAST a la) (LAST c lc) (COUNT \"\" n)) (scan 0))"
+    same_results(ref.run(plan2, [cols]), b200.run(plan2, [cols]))

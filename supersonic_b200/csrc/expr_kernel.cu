@@ -24,6 +24,9 @@
 //    order = input order, one pass over the data.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.h"
@@ -113,7 +116,7 @@ static constexpr uint32_t kCodeEnd = 0xffffu;
 // needs no compaction at all (the predicate only masks rows), so the wave scan, the staging
 // buffers and the copy-out disappear from the kernel.
 template <int NT, int R, bool SINK>
-__global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ ExprParams p) {
+__device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
   constexpr int TILE = NT * R;
   constexpr int NW = NT / 32;
   constexpr int WROWS = 32 * R;          // rows owned by one warp: [warp * WROWS, (warp + 1) * WROWS)
@@ -244,11 +247,6 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
   const uint32_t all = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t fail = 0;
-  // sink: register copy of the fingerprints of the CTA's published groups
-  unsigned int my_ready = 0;
-  unsigned long long my_fp[kTinyGroups];
-#pragma unroll
-  for (int e = 0; e < kTinyGroups; ++e) my_fp[e] = 0;
 
   // Wave-synchronous prefix, shared by all consumer threads: at the top of an iteration every
   // thread fetches a few of the kept-row counts the wave of kdefer_ tiles ago published (together
@@ -385,12 +383,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
       };
       auto sink_resolve = [&]() {
         resolved = true;
-        const unsigned int ready_now = *reinterpret_cast<volatile unsigned int*>(l_ready);
-        if (ready_now != my_ready) {
-          my_ready = ready_now;
-#pragma unroll
-          for (int e = 0; e < kTinyGroups; ++e) if ((my_ready >> e) & 1u) my_fp[e] = *reinterpret_cast<volatile unsigned long long*>(&l_fp[e]);
-        }
+        const unsigned int my_ready = *reinterpret_cast<volatile unsigned int*>(l_ready);
 #pragma unroll 1
         for (int k = 0; k < R; ++k) {
           if (!((pass >> k) & 1u)) continue;
@@ -400,7 +393,9 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
           const unsigned long long fp = ((0x9E3779B97F4A7C15ull + knull) ^ k0) * 0xff51afd7ed558ccdULL + (k1 ^ (k1 >> 29)) * 0xc4ceb9fe1a85ec53ULL;
           int g = -1;
 #pragma unroll
-          for (int e = 0; e < kTinyGroups; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
+          for (int e = 0; e < kTinyGroups; ++e) {   // published fingerprints: broadcast reads
+            if (((my_ready >> e) & 1u) && *reinterpret_cast<volatile unsigned long long*>(&l_fp[e]) == fp) g = e;
+          }
           if (g >= 0 && !(l_knull[g] == knull && l_key[g * kMaxKeys] == k0 && l_key[g * kMaxKeys + 1] == k1)) g = -1;
           if (g < 0) {
             const long long slot = sink_slot_of(k, k0, k1, knull);
@@ -933,6 +928,18 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
 }
 
 
+template <int NT, int R>
+__global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ ExprParams p) {
+  expr_kernel_body<NT, R, false>(p);
+}
+// The sink instantiation carries more live state through the dispatch loop (group ids of the
+// thread's rows, the predicate mask, accumulator addresses): it is allowed the registers of two
+// resident CTAs per SM instead of being squeezed to the default (which spilled that state).
+template <int NT, int R>
+__global__ void __launch_bounds__(NT + 32, 2) expr_sink_kernel(const __grid_constant__ ExprParams p) {
+  expr_kernel_body<NT, R, true>(p);
+}
+
 // ------------------------------------------------------------------ host side
 // Kernel variants: threads per CTA x rows per thread. More rows per thread amortise the
 // interpreter's dispatch; the tile (and with it the shared-memory stage) grows with both.
@@ -942,21 +949,39 @@ struct Variant {
   void (*sink_kernel)(const ExprParams);   // aggregation-sink instantiation, or nullptr
 };
 static const Variant kVariants[] = {
-    {256, 4, expr_kernel<256, 4, false>, nullptr},
-    {128, 8, expr_kernel<128, 8, false>, nullptr},
-    {256, 8, expr_kernel<256, 8, false>, nullptr},
-    {128, 16, expr_kernel<128, 16, false>, nullptr},
-    {64, 16, expr_kernel<64, 16, false>, nullptr},
-    {128, 4, expr_kernel<128, 4, false>, nullptr},
-    {64, 8, expr_kernel<64, 8, false>, nullptr},
-    {96, 8, expr_kernel<96, 8, false>, expr_kernel<96, 8, true>},
-    {96, 4, expr_kernel<96, 4, false>, expr_kernel<96, 4, true>},
+    {256, 4, expr_kernel<256, 4>, nullptr},
+    {128, 8, expr_kernel<128, 8>, nullptr},
+    {256, 8, expr_kernel<256, 8>, nullptr},
+    {128, 16, expr_kernel<128, 16>, nullptr},
+    {64, 16, expr_kernel<64, 16>, nullptr},
+    {128, 4, expr_kernel<128, 4>, nullptr},
+    {64, 8, expr_kernel<64, 8>, nullptr},
+    {96, 8, expr_kernel<96, 8>, expr_sink_kernel<96, 8>},
+    {96, 4, expr_kernel<96, 4>, expr_sink_kernel<96, 4>},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 static const int kDefaultVariant = 7;   // 96 consumer threads x 8 rows = 768-row tiles, three CTAs per SM
 
 static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t rows,
                           const ssb_column* outputs, int64_t* d_out_rows) {
+  if (!sp->parts.empty()) {
+    // column groups: same predicate, same kept rows, each group writes its own output columns;
+    // one timed region around all of them
+    ssb_ctx* c = sp->ctx;
+    const bool timing = c->timing;
+    if (timing) cudaEventRecord(c->ev0, c->stream);
+    c->timing = false;
+    int rc = 0;
+    for (size_t q = 0; q < sp->parts.size() && rc == 0; ++q) {
+      const ssb_program::Part& part = sp->parts[q];
+      std::vector<ssb_column> in(part.inputs.size() ? part.inputs.size() : 1);
+      for (size_t i = 0; i < part.inputs.size(); ++i) in[i] = inputs[part.inputs[i]];
+      rc = launch_program(part.prog, in.data(), rows, outputs + part.first_out, d_out_rows);
+    }
+    c->timing = timing;
+    if (timing) { cudaEventRecord(c->ev1, c->stream); c->ev_valid = true; }
+    return rc;
+  }
   ssb_ctx* ctx = sp->ctx;
   Program& prog = sp->prog;
   ExprParams p = prog.params;
@@ -1127,10 +1152,11 @@ using namespace ssb;
 
 extern "C" {
 
-int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes,
-                       int32_t n_inputs, const int32_t* input_types,
-                       const int32_t* input_nullable, const int32_t* outputs,
-                       int32_t n_outputs, int32_t predicate, ssb_program** out) {
+// One kernel for the whole program (plan search over tile variants and resident CTAs).
+static int create_single_program(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes,
+                                 int32_t n_inputs, const int32_t* input_types,
+                                 const int32_t* input_nullable, const int32_t* outputs,
+                                 int32_t n_outputs, int32_t predicate, ssb_program** out) {
   *out = nullptr;
   int variant = kDefaultVariant;
   if (const char* env = getenv("SSB200_EXPR_VARIANT")) {
@@ -1181,8 +1207,10 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
     const bool fits = cand->prog.smem_bytes <= budget;
     const int resident = fits ? c : static_cast<int>((ctx->smem_per_sm) / (cand->prog.smem_bytes + ctx->smem_reserved));
     // bytes of input in flight per SM, with a heavy penalty for a single stage
-    long long score = static_cast<long long>(stages >= 2 ? stages : 0) * (resident < 1 ? 1 : resident) * cand->prog.params.tile * 16 +
-                      (resident < 1 ? 1 : resident);   // equal bytes in flight: more resident CTAs (more warps) win
+    // rows in flight per SM; a fourth stage adds nothing (three already hide the HBM latency), so it
+    // must not buy out resident CTAs. Equal rows in flight: more resident CTAs (more warps) win.
+    long long score = static_cast<long long>(stages >= 2 ? (stages > 3 ? 3 : stages) : 0) * (resident < 1 ? 1 : resident) *
+                          cand->prog.params.tile * 16 + (resident < 1 ? 1 : resident);
     if (i == 0 && stages >= 3 && fits) score = 1LL << 40;   // the measured default
     if (score > best_score) {
       delete sp;
@@ -1204,6 +1232,110 @@ int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes
   if (e != cudaSuccess || occ < 1) { delete sp; return cuda_fail(ctx, e, "occupancy(expr_kernel)"); }
   sp->max_ctas_per_sm = occ;
   *out = sp;
+  return 0;
+}
+
+// The part of a program that computes outputs [first, first + count): only the nodes those outputs
+// and the predicate reach, over only the input columns they read.
+static int create_part(ssb_ctx* ctx, const Program& whole, int first, int count, ssb_program::Part* part) {
+  const int n = static_cast<int>(whole.nodes.size());
+  std::vector<char> used(n, 0);
+  std::vector<int> stack;
+  for (int j = first; j < first + count; ++j) stack.push_back(whole.outputs[j]);
+  if (whole.predicate >= 0) stack.push_back(whole.predicate);
+  while (!stack.empty()) {
+    const int i = stack.back();
+    stack.pop_back();
+    if (used[i]) continue;
+    used[i] = 1;
+    if (whole.nodes[i].op == SSB_OP_INPUT) continue;
+    for (int a = 0; a < 3; ++a) if (whole.nodes[i].arg[a] >= 0 && whole.nodes[i].op != SSB_OP_CONST) stack.push_back(whole.nodes[i].arg[a]);
+  }
+  std::vector<int> new_index(n, -1), input_slot(whole.input_types.size(), -1);
+  std::vector<ssb_expr_node> nodes;
+  std::vector<int32_t> types, nullable;
+  part->inputs.clear();
+  for (int i = 0; i < n; ++i) {
+    if (!used[i]) continue;
+    ssb_expr_node nd = whole.nodes[i];
+    if (nd.op == SSB_OP_INPUT) {
+      const int col = nd.arg[0];
+      if (input_slot[col] < 0) {
+        input_slot[col] = static_cast<int>(part->inputs.size());
+        part->inputs.push_back(col);
+        types.push_back(whole.input_types[col]);
+        nullable.push_back(whole.input_nullable[col]);
+      }
+      nd.arg[0] = input_slot[col];
+    } else if (nd.op != SSB_OP_CONST) {
+      for (int a = 0; a < 3; ++a) if (nd.arg[a] >= 0) nd.arg[a] = new_index[nd.arg[a]];
+    }
+    new_index[i] = static_cast<int>(nodes.size());
+    nodes.push_back(nd);
+  }
+  std::vector<int32_t> outs;
+  for (int j = first; j < first + count; ++j) outs.push_back(new_index[whole.outputs[j]]);
+  int32_t dummy = 0;
+  part->first_out = first;
+  part->n_out = count;
+  return create_single_program(ctx, nodes.data(), static_cast<int32_t>(nodes.size()), static_cast<int32_t>(types.size()),
+                               types.empty() ? &dummy : types.data(), nullable.empty() ? &dummy : nullable.data(), outs.data(),
+                               count, whole.predicate >= 0 ? new_index[whole.predicate] : -1, &part->prog);
+}
+
+int ssb_program_create(ssb_ctx* ctx, const ssb_expr_node* nodes, int32_t n_nodes,
+                       int32_t n_inputs, const int32_t* input_types,
+                       const int32_t* input_nullable, const int32_t* outputs,
+                       int32_t n_outputs, int32_t predicate, ssb_program** out) {
+  ssb_program* sp = nullptr;
+  if (int rc = create_single_program(ctx, nodes, n_nodes, n_inputs, input_types, input_nullable, outputs, n_outputs, predicate, &sp)) {
+    *out = nullptr;
+    return rc;
+  }
+  *out = sp;
+  // Column groups for wide plans: a plan whose single kernel keeps fewer than three input stages in
+  // flight or fewer than six consumer warps per SM (C2 variant B, nine outputs: one CTA per SM,
+  // measured 1.0 TB/s) is evaluated as k kernels that share the predicate; every group reads the
+  // predicate's inputs again, which costs less than running the whole plan starved (2.2 TB/s).
+  static const int split_env = getenv("SSB200_EXPR_SPLIT") ? atoi(getenv("SSB200_EXPR_SPLIT")) : -1;
+  auto starved = [](const ssb_program* q) {   // fewer than three stages in flight, or fewer than six consumer warps per SM
+    const Variant& v = kVariants[q->prog.variant];
+    return q->prog.params.stages < 3 || q->max_ctas_per_sm * (v.threads / 32) < 6;
+  };
+  const bool poor = starved(sp);
+  if (split_env == 0 || n_outputs < 2 || (!poor && split_env < 2)) return 0;
+  // group counts to try: about three outputs per group first (measured best on variant B), then more, then fewer
+  std::vector<int> ks;
+  if (split_env >= 2) {
+    ks.push_back(split_env);
+  } else {
+    const int k0 = std::max(2, std::min(4, (n_outputs + 2) / 3));
+    for (int k = k0; k <= 4; ++k) ks.push_back(k);
+    for (int k = k0 - 1; k >= 2; --k) ks.push_back(k);
+  }
+  for (size_t ki = 0; ki < ks.size(); ++ki) {
+    const int k = ks[ki];
+    if (k > n_outputs) continue;
+    std::vector<ssb_program::Part> parts(k);
+    bool ok = true;
+    for (int q = 0; q < k && ok; ++q) {
+      const int first = n_outputs * q / k, last = n_outputs * (q + 1) / k;
+      parts[q].prog = nullptr;
+      if (create_part(ctx, sp->prog, first, last - first, &parts[q]) != 0) { ok = false; break; }
+      if (starved(parts[q].prog)) ok = split_env >= 2;
+    }
+    if (getenv("SSB200_DEBUG_PLAN")) {
+      fprintf(stderr, "[ssb200] plan: %d outputs, single kernel: tile %d, %d stages, %d CTAs/SM; %d column groups %s:", n_outputs,
+              sp->prog.params.tile, sp->prog.params.stages, sp->max_ctas_per_sm, k, ok ? "accepted" : "rejected");
+      for (int q = 0; q < k; ++q) {
+        if (parts[q].prog) fprintf(stderr, " [%d outs, %zu ins, tile %d, %d stages, %d CTAs/SM]", parts[q].n_out, parts[q].inputs.size(),
+                                   parts[q].prog->prog.params.tile, parts[q].prog->prog.params.stages, parts[q].prog->max_ctas_per_sm);
+      }
+      fprintf(stderr, "\n");
+    }
+    if (ok) { sp->parts = parts; return 0; }
+    for (int q = 0; q < k; ++q) delete parts[q].prog;
+  }
   return 0;
 }
 

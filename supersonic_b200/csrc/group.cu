@@ -167,6 +167,10 @@ __device__ __forceinline__ long long probe_packed_from(const GroupParams& p, uns
   return -1;
 }
 
+// PLAIN: every column is 8 bytes wide without a NULL bitmap (plain 8-byte loads, no bit tests).
+// Otherwise 4-byte columns and NULL bitmaps are handled in place: a NULL key takes the special
+// slot, a NULL input does not contribute (the result is NULL while no input was seen).
+template <bool PLAIN>
 __global__ void __launch_bounds__(256, 4) group_update_fast_kernel(const __grid_constant__ GroupParams p) {
   constexpr int R = 4;
   constexpr int TILE = 256 * R;
@@ -177,10 +181,16 @@ __global__ void __launch_bounds__(256, 4) group_update_fast_kernel(const __grid_
     const long long r0 = t * TILE + threadIdx.x;
     unsigned long long key[R], cur[R];
     long long slot[R];
+    unsigned int knull = 0;   // bit j: the key of row j is NULL
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const long long row = r0 + j * 256;
-      key[j] = row < p.rows ? keys[row] : kEmptyKey;
+      key[j] = kEmptyKey;
+      if (row < p.rows) {
+        if (PLAIN) key[j] = keys[row];
+        else if (bit_at(p.key_nulls[0], row)) knull |= 1u << j;
+        else key[j] = load_raw(p.key_data[0], p.key_phys[0], row);
+      }
     }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(256, 4) group_update_fast_kernel(const __grid_
     for (int j = 0; j < R; ++j) {
       const long long row = r0 + j * 256;
       if (row >= p.rows) { slot[j] = -2; continue; }
-      if (key[j] == kEmptyKey) slot[j] = find_slot_packed(p, row);       // the one key that needs the special slot
+      if (key[j] == kEmptyKey) slot[j] = find_slot_packed(p, row);       // NULL key / the one key that needs the special slot
       else if (cur[j] != key[j]) slot[j] = probe_packed_from(p, key[j], static_cast<unsigned long long>(slot[j]), cur[j]);
       if (slot[j] == -1) {
         const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
@@ -201,28 +211,37 @@ __global__ void __launch_bounds__(256, 4) group_update_fast_kernel(const __grid_
     }
     for (int a = 0; a < p.n_aggs; ++a) {
       const AggDev& ag = p.agg[a];
+      unsigned int valid = 0;   // bit j: row j contributes to this aggregate
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (slot[j] >= 0 && (PLAIN || ag.in_phys < 0 || !bit_at(ag.in_nulls, r0 + j * 256))) valid |= 1u << j;
+      }
       if (ag.fn == SSB_AGG_COUNT) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (slot[j] >= 0) atomicAdd(&ag.acc[slot[j]], 1ull);
+        for (int j = 0; j < R; ++j) if ((valid >> j) & 1u) atomicAdd(&ag.acc[slot[j]], 1ull);
         continue;
       }
-      const unsigned long long* __restrict__ in = static_cast<const unsigned long long*>(ag.in_data);
       unsigned long long v[R];
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = slot[j] >= 0 ? in[r0 + j * 256] : 0ull;
+      for (int j = 0; j < R; ++j) {
+        v[j] = 0ull;
+        if ((valid >> j) & 1u) {
+          v[j] = PLAIN ? static_cast<const unsigned long long*>(ag.in_data)[r0 + j * 256] : load_raw(ag.in_data, ag.in_phys, r0 + j * 256);
+        }
+      }
       if (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (slot[j] >= 0) atomicAdd(reinterpret_cast<double*>(&ag.acc[slot[j]]), Codec<double>::dec(v[j]));
-      } else if (ag.fn == SSB_AGG_SUM) {   // INT64 / UINT64: wrapping add
+        for (int j = 0; j < R; ++j) if ((valid >> j) & 1u) atomicAdd(reinterpret_cast<double*>(&ag.acc[slot[j]]), Codec<double>::dec(v[j]));
+      } else if (ag.fn == SSB_AGG_SUM && (ag.out_phys == T_I64 || ag.out_phys == T_U64)) {   // wrapping add
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (slot[j] >= 0) atomicAdd(&ag.acc[slot[j]], v[j]);
+        for (int j = 0; j < R; ++j) if ((valid >> j) & 1u) atomicAdd(&ag.acc[slot[j]], v[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (slot[j] >= 0) apply(ag, slot[j], v[j], 1ull);
+        for (int j = 0; j < R; ++j) if ((valid >> j) & 1u) apply(ag, slot[j], v[j], 1ull);
       }
       if (ag.seen != nullptr) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (slot[j] >= 0) ag.seen[slot[j]] = 1u;
+        for (int j = 0; j < R; ++j) if ((valid >> j) & 1u) ag.seen[slot[j]] = 1u;
       }
     }
   }
@@ -1180,21 +1199,17 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
     // few groups so far (and few enough aggregates): CTA-private shared-memory tables
     const bool few = !g->has_first_last && g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst && g->h_counters[0] <= 256));
-    // single packed 8-byte key, COUNT or same-type 8-byte aggregates, no NULL bitmaps, no replay
-    for (int a = 0; a < g->n_aggs; ++a) {
-      AggDev& ag = p.agg[a];
-      ag.pad = ag.fn == SSB_AGG_COUNT ? TA_COUNT
-               : (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) ? TA_SUM_F64
-               : (ag.fn == SSB_AGG_SUM && (ag.out_phys == T_I64 || ag.out_phys == T_U64)) ? TA_SUM_U64 : TA_OTHER;
-    }
+    // single packed key, COUNT or aggregates whose input type equals the result type, no replay;
+    // `plain` additionally: 8-byte columns without NULL bitmaps
     static const bool tiny_enabled = getenv("SSB200_GROUP_TINY") == nullptr || atoi(getenv("SSB200_GROUP_TINY")) != 0;
     static const bool fast_enabled = getenv("SSB200_GROUP_FAST") == nullptr || atoi(getenv("SSB200_GROUP_FAST")) != 0;
-    bool fast = fused == nullptr && fast_enabled && !g->has_first_last && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1 &&
-                phys_width(p.key_phys[0]) == 8 && p.key_nulls[0] == nullptr;
+    bool fast = fused == nullptr && fast_enabled && !g->has_first_last && !few && !merge && replay == nullptr && g->packed && g->n_keys == 1 && g->stride == 1;
+    bool plain = fast && phys_width(p.key_phys[0]) == 8 && p.key_nulls[0] == nullptr;
     for (int a = 0; fast && a < g->n_aggs; ++a) {
       const AggDev& ag = p.agg[a];
-      if (ag.fn == SSB_AGG_COUNT) { if (ag.in_phys >= 0 && ag.in_nulls != nullptr) fast = false; continue; }
-      if (ag.in_nulls != nullptr || ag.in_phys != ag.out_phys || phys_width(ag.in_phys) != 8) fast = false;
+      if (ag.fn == SSB_AGG_COUNT) { if (ag.in_phys >= 0 && ag.in_nulls != nullptr) plain = false; continue; }
+      if (ag.in_phys != ag.out_phys) fast = false;
+      if (ag.in_nulls != nullptr || phys_width(ag.in_phys) != 8) plain = false;
     }
     if (fused != nullptr) {
       // Filter -> Compute -> GroupAggregate in one kernel: the keys and aggregate inputs are outputs
@@ -1228,7 +1243,8 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     } else if (fast) {
       long long ctas = static_cast<long long>(ctx->num_sms) * 4;
       if (ctas > div_up(remaining, 1024)) ctas = div_up(remaining, 1024);
-      group_update_fast_kernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
+      if (plain) group_update_fast_kernel<true><<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
+      else group_update_fast_kernel<false><<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
     } else if (few && tiny_enabled && g->n_aggs >= 1 && (g->n_keys == 0 || g->h_counters[0] <= kTinyGroups)) {
       const size_t smem = static_cast<size_t>(kTinyGroups) * g->n_aggs * kTinyThreads * 8;
       bool tfast = !merge && replay == nullptr;
@@ -1451,8 +1467,6 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   int rc = 0;
   long long offset = 0;
   // scratch of the unfused path (allocated on first use)
-  struct Part { ssb_program* prog; int first, last; bool owned; };
-  std::vector<Part> parts;
   std::vector<ssb_column> outs(n_out ? n_out : 1);
   long long outs_rows = 0;
   auto free_outs = [&]() {
@@ -1503,34 +1517,7 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
         if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "fused aggregate scratch"); break; }
         outs_rows = n;
       }
-      if (parts.empty()) {
-        // Experiment (SSB200_GROUP_SPLIT=2): a wide plan evaluated as column groups that share the
-        // predicate, each with more resident CTAs. Measured slower on the Q1 shape (57 ms against
-        // 50 ms per 600M rows: the predicate's inputs are read twice), so one program is the default.
-        static const int split_env = getenv("SSB200_GROUP_SPLIT") ? atoi(getenv("SSB200_GROUP_SPLIT")) : -1;
-        int n_parts = split_env > 0 ? split_env : 1;
-        if (n_parts > n_out) n_parts = n_out;
-        if (n_parts <= 1) {
-          parts.push_back(Part{sp, 0, n_out, false});
-        } else {
-          for (int q = 0; q < n_parts && rc == 0; ++q) {
-            const int first = n_out * q / n_parts, last = n_out * (q + 1) / n_parts;
-            ssb_program* sub = nullptr;
-            rc = ssb_program_create(ctx, prog.nodes.data(), static_cast<int32_t>(prog.nodes.size()), n_in, prog.input_types.data(),
-                                    prog.input_nullable.data(), prog.outputs.data() + first, last - first, prog.predicate, &sub);
-            if (rc == 0) parts.push_back(Part{sub, first, last, true});
-          }
-          if (rc != 0) {   // a half does not compile on its own: the whole program does
-            for (size_t q = 0; q < parts.size(); ++q) if (parts[q].owned) ssb_program_destroy(parts[q].prog);
-            parts.clear();
-            parts.push_back(Part{sp, 0, n_out, false});
-            rc = 0;
-          }
-        }
-      }
-      for (size_t q = 0; q < parts.size() && rc == 0; ++q) {
-        rc = ssb_program_run(parts[q].prog, in2.data(), n, outs.data() + parts[q].first, ctx->d_count);
-      }
+      rc = ssb_program_run(sp, in2.data(), n, outs.data(), ctx->d_count);
       if (rc) break;
       cudaError_t e = cudaMemcpyAsync(ctx->h_count, ctx->d_count, 8, cudaMemcpyDeviceToHost, ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1543,11 +1530,6 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   }
   cudaStreamSynchronize(ctx->stream);
   free_outs();
-  for (size_t q = 0; q < parts.size(); ++q) {
-    if (!parts[q].owned) continue;
-    if (rc == 0) rc = ssb_program_check_failure(parts[q].prog);
-    ssb_program_destroy(parts[q].prog);
-  }
   if (rc == 0) rc = ssb_program_check_failure(sp);
   return rc;
 }

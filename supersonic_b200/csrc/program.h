@@ -126,7 +126,18 @@ struct ssb_program {
   // lazily compiled twin for the aggregation sink (keyed by the sink's shared-memory need)
   ssb_program* sink = nullptr;
   uint32_t sink_key = 0;
-  ~ssb_program() { delete sink; }
+  // Wide plans run as column groups: each part evaluates the predicate and a contiguous range of
+  // the outputs from only the input columns it needs (empty = one kernel does everything).
+  struct Part {
+    ssb_program* prog;
+    int first_out, n_out;
+    std::vector<int> inputs;   // indices into the whole program's input list
+  };
+  std::vector<Part> parts;
+  ~ssb_program() {
+    delete sink;
+    for (size_t i = 0; i < parts.size(); ++i) delete parts[i].prog;
+  }
 };
 
 #endif  // SSB_CSRC_PROGRAM_H_

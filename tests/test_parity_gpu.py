@@ -333,3 +333,26 @@ def test_group_first_last(ref, b200, n, groups):
     same_results(want, got, ordered=False, sort_cols=[0])
     plan2 = "(scalar_agg (aggs (FIRST a fa) (LAST a la) (LAST c lc) (COUNT \"\" n)) (scan 0))"
     same_results(ref.run(plan2, [cols]), b200.run(plan2, [cols]))
+
+
+@pytest.mark.parametrize("n", [1000, 200_003])
+def test_wide_plans_run_as_column_groups(ref, b200, n):
+    """BASELINE config 2 variant B (ProjectAllAttributes: the eight columns plus e = a*b+c under the
+    filter) and other wide plans: the library evaluates them as column groups that share the
+    predicate; rows, order, NULLs and values must equal the reference's single pass."""
+    rng = np.random.default_rng(n)
+    cols = [sp.Column("a", sp.INT64, rng.integers(-2**31, 2**31, n)), sp.Column("b", sp.INT64, rng.integers(-2**31, 2**31, n)),
+            sp.Column("c", sp.INT64, rng.integers(-2**62, 2**62, n)), sp.Column("d", sp.INT64, rng.integers(0, 2**20, n)),
+            sp.Column("e0", sp.INT64, rng.integers(0, 100, n), is_null=rng.random(n) < 0.2),
+            sp.Column("f", sp.DOUBLE, rng.random(n)), sp.Column("g", sp.INT32, rng.integers(-5, 5, n).astype(np.int32)),
+            sp.Column("h", sp.INT64, rng.integers(0, 10**12, n), is_null=rng.random(n) < 0.5)]
+    variant_b = ("(filter (less (col d) (i64 524288)) (all) (compute (compound (as e (plus (multiply (col a) (col b)) (col c))) "
+                 "(col a) (col b) (col c) (col d) (col e0) (col f) (col g) (col h)) (scan 0)))")
+    same_results(ref.run(variant_b, [cols]), b200.run(variant_b, [cols]))
+    wide_compute = ("(compute (compound (as o1 (plus (col a) (col b))) (as o2 (minus (col c) (col d))) (as o3 (multiply (col f) (f64 2))) "
+                    "(as o4 (plus (col e0) (col h))) (as o5 (cast INT64 (col g))) (as o6 (is_null (col h))) (col a) (col b) (col c) (col d) "
+                    "(as o7 (if_null (col e0) (i64 -1))) (as o8 (less (col f) (f64 0.5)))) (scan 0))")
+    same_results(ref.run(wide_compute, [cols]), b200.run(wide_compute, [cols]))
+    nullable_pred = ("(filter (greater (col h) (i64 500000000000)) (all) (compute (compound (col a) (col b) (col c) (col d) (col e0) (col f) "
+                     "(col g) (col h) (as s (plus (col e0) (col h)))) (scan 0)))")
+    same_results(ref.run(nullable_pred, [cols]), b200.run(nullable_pred, [cols]))

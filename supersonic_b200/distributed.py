@@ -328,7 +328,7 @@ class ShardedHashJoin(object):
     row list received in rank order is in global insertion order and all pairs of one lhs row
     come from one rank, so the concatenation of the per-rank results in rank order is exactly
     the reference's output order (cursor/core/hash_join.cc:793-831).
-    NOT NULL columns only in this round (a NULL key never matches: hash_join.cc:67-76).
+    NULL keys and nullable payload columns: see run().
 
     Strategy "broadcast" instead all-gathers the build side (keys + payload, rank order = global
     insertion order), builds the whole table on every rank and probes the local lhs shard: no
@@ -338,10 +338,47 @@ class ShardedHashJoin(object):
     def __init__(self, kernels, group=None, strategy="all_to_all", broadcast_max_rows=1 << 28):
         self.k, self.group, self.strategy, self.broadcast_max_rows = kernels, group, strategy, broadcast_max_rows
 
-    def run(self, lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type=INNER, uniqueness=UNIQUE):
+    def run(self, lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type=INNER, uniqueness=UNIQUE,
+            lhs_key_nulls=None, rhs_key_nulls=None):
         """Columns are (tensor, SSB dtype) pairs of this rank's shards. Returns
         (lhs_rows, lhs payload columns, rhs payload columns, rhs_is_null or None): the join
-        result for this rank's lhs shard in lhs order; lhs_rows are shard-local row ids."""
+        result for this rank's lhs shard in lhs order; lhs_rows are shard-local row ids.
+
+        NULLs. `lhs_key_nulls` / `rhs_key_nulls`: one byte per row, 1 = some key column of the row is
+        NULL. Such rows never match (hash_join.cc:67-76,616-617,755-756): build rows are dropped
+        before the exchange, probe rows stay at home and come out unmatched (LEFT_OUTER) or not at
+        all (INNER). A nullable payload column travels as two columns: its values and its is_null
+        bytes as an extra BOOL column; for LEFT_OUTER the caller ORs those with rhs_is_null."""
+        import torch
+        k = self.k
+        I64 = 2
+        if rhs_key_nulls is not None:
+            with k.scope():
+                kept = k.compact(1 - rhs_key_nulls, list(rhs_keys) + list(rhs_cols))
+            rhs_keys, rhs_cols = kept[:len(rhs_keys)], kept[len(rhs_keys):]
+        if lhs_key_nulls is None:
+            return self._run_not_null(lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type, uniqueness)
+        n_l = lhs_keys[0][0].numel()
+        with k.scope():
+            kept = k.compact(1 - lhs_key_nulls, [(k.iota(n_l), I64)] + list(lhs_keys))
+        sel, keys_nn = kept[0], kept[1:]
+        rows_nn, _, out_r, r_null = self._run_not_null(keys_nn, [], rhs_keys, rhs_cols, join_type, uniqueness)
+        with k.scope():
+            rows = k.gather(sel, rows_nn)
+            if join_type == LEFT_OUTER:
+                # the rows with a NULL key come out once, unmatched, at their place in lhs order
+                null_rows = k.compact(lhs_key_nulls, [(k.iota(n_l), I64)])[0][0]
+                m = null_rows.numel()
+                rows = torch.cat([rows, null_rows])
+                order = k.order_by(rows)
+                rows = k.gather((rows, I64), order)
+                out_r = [(k.gather((torch.cat([t, k.zeros(m, dt)]), dt), order), dt) for t, dt in out_r]
+                r_null = k.gather((torch.cat([r_null, k.zeros(m, 6) + 1]), 6), order)
+            out_l = [(k.gather(c, rows), c[1]) for c in lhs_cols]
+        k.finish()
+        return rows, out_l, out_r, r_null
+
+    def _run_not_null(self, lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type, uniqueness):
         import torch
         import torch.distributed as dist
         strategy = self.strategy

@@ -171,7 +171,9 @@ def _join_tables(uniq, scale=1):
     if not uniq:
         pk[rng.integers(0, nb, nb // 5)] = pk[rng.integers(0, nb, nb // 5)]
     return {"pk": pk, "payload": rng.integers(0, 10**9, nb), "w": rng.random(nb),
-            "fk": rng.integers(0, nb * 3, npr), "lv": rng.integers(0, 10**9, npr)}
+            "fk": rng.integers(0, nb * 3, npr), "lv": rng.integers(0, 10**9, npr),
+            "pk_null": (rng.random(nb) < 0.05).astype(np.uint8), "fk_null": (rng.random(npr) < 0.1).astype(np.uint8),
+            "w_null": (rng.random(nb) < 0.2).astype(np.uint8)}
 
 
 def _join_worker(rank, world, port, out, strategy):
@@ -238,3 +240,85 @@ def test_sharded_hash_join_world2_matches_oracle(ref, strategy):
             # global lhs row ids are ascending: the concatenation is in lhs order
             gl = np.concatenate([p[3] for p in parts])
             assert np.all(np.diff(gl) >= 0)
+
+
+def _null_join_worker(rank, world, port, out, strategy, use_cuda=False):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if use_cuda:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from supersonic_b200.distributed import ShardedHashJoin
+        if use_cuda:
+            from supersonic_b200 import capi
+            from supersonic_b200.distributed import CudaJoinKernels
+            kern = CudaJoinKernels(capi.Context(rank))
+        else:
+            kern = NumpyJoinKernels()
+        I64, F64, BOOL = 2, 5, 6
+        res = {}
+        for uniq in (1, 0):
+            t = _join_tables(uniq)
+            bb, be = shard_rows(len(t["pk"]), rank, world, align=1)
+            pb, pe = shard_rows(len(t["fk"]), rank, world, align=1)
+
+            def col(name, b, e, dt):
+                x = torch.from_numpy(np.ascontiguousarray(t[name][b:e]))
+                return (x.cuda() if use_cuda else x, dt)
+            for jt in (0, 1):
+                j = ShardedHashJoin(kern, strategy=strategy)
+                rows, lcols, rcols, rnull = j.run(
+                    [col("fk", pb, pe, I64)], [col("lv", pb, pe, I64)],
+                    [col("pk", bb, be, I64)], [col("payload", bb, be, I64), col("w", bb, be, F64), col("w_null", bb, be, BOOL)],
+                    join_type=jt, uniqueness=uniq, lhs_key_nulls=col("fk_null", pb, pe, BOOL)[0],
+                    rhs_key_nulls=col("pk_null", bb, be, BOOL)[0])
+                res[(uniq, jt)] = ([c.cpu().numpy() for c, _ in lcols], [c.cpu().numpy() for c, _ in rcols],
+                                   None if rnull is None else rnull.cpu().numpy(), rows.cpu().numpy() + pb)
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def check_null_join_against_oracle(ref, got):
+    from supersonic_b200 import ssplan as sp
+    for uniq in (1, 0):
+        t = _join_tables(uniq)
+        build = [sp.Column("pk", sp.INT64, t["pk"], is_null=t["pk_null"].astype(bool)), sp.Column("payload", sp.INT64, t["payload"]),
+                 sp.Column("w", sp.DOUBLE, t["w"], is_null=t["w_null"].astype(bool))]
+        probe = [sp.Column("fk", sp.INT64, t["fk"], is_null=t["fk_null"].astype(bool)), sp.Column("lv", sp.INT64, t["lv"])]
+        for jt in (0, 1):
+            plan = ("(hash_join %s (named fk) (named pk) (multi (0 (named lv)) (1 (named payload w))) %s (scan 0) (scan 1))"
+                    % (["INNER", "LEFT_OUTER"][jt], ["NOT_UNIQUE", "UNIQUE"][uniq]))
+            want = ref.run(plan, [probe, build])
+            assert want.code == 0, want.error
+            parts = [got[r][(uniq, jt)] for r in range(len(got))]
+            lv = np.concatenate([p[0][0] for p in parts])
+            pay = np.concatenate([p[1][0] for p in parts])
+            w = np.concatenate([p[1][1] for p in parts])
+            wn = np.concatenate([p[1][2] for p in parts]).astype(bool)
+            assert len(lv) == want.rows and np.array_equal(lv, want.columns[0])
+            miss = np.concatenate([p[2] for p in parts]).astype(bool) if jt == 1 else np.zeros(len(lv), dtype=bool)
+            if jt == 1:
+                assert np.array_equal(miss, want.nulls[1])
+            assert np.array_equal(pay[~miss], want.columns[1][~miss])
+            w_null = miss | wn
+            assert np.array_equal(w_null, want.nulls[2] if want.nulls[2] is not None else np.zeros(len(lv), dtype=bool))
+            assert np.array_equal(w[~w_null], want.columns[2][~w_null])
+
+
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+def test_sharded_hash_join_null_keys_and_payload_world2(ref, strategy):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_null_join_worker, args=(r, 2, port, out, strategy)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    check_null_join_against_oracle(ref, got)

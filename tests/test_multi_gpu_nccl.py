@@ -88,3 +88,22 @@ def test_sharded_hash_join_two_gpus_matches_oracle(ref, n_scale, strategy):
                 assert np.array_equal(pay[~isn], want.columns[2][~isn]) and np.array_equal(w[~isn], want.columns[3][~isn])
             else:
                 assert np.array_equal(pay, want.columns[2]) and np.array_equal(w, want.columns[3])
+
+
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+def test_sharded_hash_join_null_keys_and_payload_two_gpus(ref, strategy):
+    """NULL keys on both sides and a nullable payload column through the real kernels over NCCL."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from test_multi_gpu import _null_join_worker, check_null_join_against_oracle
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_null_join_worker, args=(r, 2, port, out, strategy, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    check_null_join_against_oracle(ref, got)

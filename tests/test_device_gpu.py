@@ -424,3 +424,102 @@ def test_fused_sink_overflow_and_table_growth_equal_unfused(ctx):
     aggs = [(capi.AGG_SUM, 0, I64, I64, 0), (capi.AGG_MIN, 0, I64, I64, 0), (capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
     want, kept = _run_both(ctx, nodes, [I64, I64], [0, 0], [0, 5], 3, inputs, 1, [I64], [0], aggs, [I64, I64, capi.UINT64])
     assert int(want[1][2][0].sum()) == kept == int((val < 400).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes (1B rows): size-independent checks against a chunked host recomputation
+# of the same counter-based columns (ssb_generate_host is bit-identical to the device generator).
+def _host_chunks(total, chunk):
+    first = 0
+    while first < total:
+        n = min(chunk, total - first)
+        yield first, n
+        first += n
+
+
+def _gen_host(ctx, n, first, stream, kind, lo, span, dtype=np.int64):
+    out = np.empty(n, dtype=dtype)
+    ctx.lib.ssb_generate_host(out.ctypes.data, n, first, 42, stream, kind, lo, span)
+    return out
+
+
+def test_c2_full_size_count_and_checksum(ctx):
+    """Config 2 at 1B rows: the number of kept rows and the wrapping 64-bit sum of the kept
+    e = a*b+c values (a checksum of the whole ordered output) equal the host's, and the output is
+    the host's output on three windows spread over the result (order check)."""
+    rows = 1_000_000_000
+    k = 1 << 19
+    d = {}
+    for name in "abcd":
+        kind, lo, span = GEN[name]
+        d[name] = ctx.malloc(rows * 8 + 256)
+        ctx.generate(d[name], rows, 0, 42, "abcd".index(name), kind, lo, span)
+    out = ctx.malloc(rows * 8 + 256)
+    prog = c2_program(ctx, k)
+    kept = prog.run_sync([(d[c], None, capi.INT64) for c in "abcd"], rows, [(out, None, capi.INT64)])
+    # device-side checksum: ScalarAggregate SUM (wrapping) + COUNT over the kept values
+    specs = (capi.AggSpec * 2)()
+    specs[0].fn, specs[0].input, specs[0].in_type, specs[0].out_type = capi.AGG_SUM, 0, capi.INT64, capi.INT64
+    specs[1].fn, specs[1].input, specs[1].in_type, specs[1].out_type = capi.AGG_COUNT, -1, capi.INT64, capi.UINT64
+    g = C.c_void_p()
+    dummy = (C.c_int32 * 1)(0)
+    ctx.check(ctx.lib.ssb_group_create(ctx.h, 0, dummy, dummy, 2, specs, 0, C.byref(g)))
+    ctx.check(ctx.lib.ssb_group_update(g, _cols([(0, None, 0)]), _cols([(out, None, capi.INT64)]), kept))
+    n = C.c_int64()
+    ko, ao = _cols([(0, None, 0)]), _cols([(0, None, 0), (0, None, 0)])
+    ctx.check(ctx.lib.ssb_group_finalize(g, C.byref(n), ko, ao))
+    dev_sum, dev_cnt = np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.uint64)
+    ctx.d2h(dev_sum, ao[0].data)
+    ctx.d2h(dev_cnt, ao[1].data)
+    ctx.lib.ssb_group_destroy(g)
+    # host: chunked recomputation
+    host_cnt, host_sum = 0, np.int64(0)
+    windows = {}
+    want_windows = [0, kept // 2, kept - 1000]
+    with np.errstate(over="ignore"):
+        for first, cn in _host_chunks(rows, 50_000_000):
+            cols = {c: _gen_host(ctx, cn, first, "abcd".index(c), *GEN[c]) for c in "abcd"}
+            m = cols["d"] < k
+            e = (cols["a"] * cols["b"] + cols["c"])[m]
+            for w0 in want_windows:          # output positions [w0, w0 + 1000) that fall into this chunk
+                lo_, hi_ = max(w0, host_cnt), min(w0 + 1000, host_cnt + len(e))
+                if lo_ < hi_:
+                    windows.setdefault(w0, []).append(e[lo_ - host_cnt:hi_ - host_cnt])
+            host_cnt += int(m.sum())
+            host_sum = host_sum + e.sum(dtype=np.int64)
+    assert kept == host_cnt == int(dev_cnt[0])
+    assert int(dev_sum[0]) == int(host_sum)
+    for w0 in want_windows:
+        got = np.empty(1000, dtype=np.int64)
+        ctx.d2h(got, out + w0 * 8)
+        assert np.array_equal(got, np.concatenate(windows[w0]))
+    prog.close()
+    for name in "abcd":
+        ctx.free(d[name])
+    ctx.free(out)
+
+
+def test_c3_full_size_equals_host(ctx):
+    """Config 3 at 1B rows, 1M INT64 keys, SUM(DOUBLE) + COUNT(*): every group's sum (exactly
+    summable payload: order-free) and count equal the host's bincount over the same rows."""
+    rows, groups = 1_000_000_000, 1_000_000
+    k = ctx.malloc(rows * 8 + 256)
+    v = ctx.malloc(rows * 8 + 256)
+    ctx.generate(k, rows, 0, 42, 20, 1, 0, groups)
+    ctx.generate(v, rows, 0, 42, 21, 2, 0, 0)
+    spec = [(capi.AGG_SUM, 0, capi.DOUBLE, capi.DOUBLE), (capi.AGG_COUNT, -1, capi.INT64, capi.UINT64)]
+    g = _group(ctx, spec, groups)
+    ctx.check(ctx.lib.ssb_group_update(g, _cols([(k, None, capi.INT64)]), _cols([(v, None, capi.DOUBLE)]), rows))
+    keys, aggs, _ = _finalize(ctx, g, 2, [np.float64, np.uint64])
+    ctx.lib.ssb_group_destroy(g)
+    ctx.free(k)
+    ctx.free(v)
+    hs, hc = np.zeros(groups), np.zeros(groups, dtype=np.int64)
+    for first, cn in _host_chunks(rows, 50_000_000):
+        hk = _gen_host(ctx, cn, first, 20, 1, 0, groups)
+        hv = _gen_host(ctx, cn, first, 21, 2, 0, 0, dtype=np.float64)
+        hs += np.bincount(hk, weights=hv, minlength=groups)
+        hc += np.bincount(hk, minlength=groups)
+    assert np.array_equal(keys, np.arange(groups))
+    assert np.array_equal(aggs[1], hc.astype(np.uint64))
+    assert np.array_equal(aggs[0], hs)

@@ -523,3 +523,33 @@ def test_c3_full_size_equals_host(ctx):
     assert np.array_equal(keys, np.arange(groups))
     assert np.array_equal(aggs[1], hc.astype(np.uint64))
     assert np.array_equal(aggs[0], hs)
+
+
+def test_c4_full_size_join_pairs_in_order(ctx):
+    """Config 4 on one GPU: 1B probe rows against a 100M-row build side whose key column is a
+    permutation of [0, 1e8) (pk(i) = i * m mod B). Every probe row matches exactly once, the pairs
+    come in probe order, and the matched build row is the one the host computes through the
+    modular inverse of the permutation (checked on windows spread over the result)."""
+    probe, build = 1_000_000_000, 100_000_000
+    mult = 1_000_000_007
+    pk = ctx.malloc(build * 8 + 256)
+    fk = ctx.malloc(probe * 8 + 256)
+    ctx.generate(pk, build, 0, 42, 40, 4, mult, build)
+    ctx.generate(fk, probe, 0, 42, 42, 1, 0, build)
+    j = C.c_void_p()
+    ctx.check(ctx.lib.ssb_join_build(ctx.h, 1, _cols([(pk, None, capi.INT64)]), build, 1, C.byref(j)))
+    n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+    ctx.check(ctx.lib.ssb_join_probe(j, _cols([(fk, None, capi.INT64)]), probe, 0, C.byref(n), C.byref(pl), C.byref(pr)))
+    assert n.value == probe
+    inv = pow(mult, -1, build)
+    for w0 in [0, 123_456_789, probe // 2, probe - 4096]:
+        li, ri = np.empty(4096, dtype=np.int64), np.empty(4096, dtype=np.int64)
+        ctx.d2h(li, pl.value + w0 * 8)
+        ctx.d2h(ri, pr.value + w0 * 8)
+        assert np.array_equal(li, np.arange(w0, w0 + 4096))                       # probe order, one pair per row
+        hfk = _gen_host(ctx, 4096, w0, 42, 1, 0, build)
+        want = np.array([(int(x) * inv) % build for x in hfk], dtype=np.int64)    # the build row holding that key
+        assert np.array_equal(ri, want)
+    ctx.lib.ssb_join_destroy(j)
+    ctx.free(pk)
+    ctx.free(fk)

@@ -1,6 +1,7 @@
 // ops.cc -- Operation factories and GPU cursors (see include/supersonic/cursor.h).
 #include <stdio.h>
 
+#include <algorithm>
 #include <map>
 
 #include "internal.h"
@@ -614,11 +615,6 @@ class GroupCursor : public GpuCursor {
       for (size_t k = 0; k < program->used_inputs().size(); ++k) ic.push_back(base.columns[program->used_inputs()[k]].col);
     } else {
       rows = static_cast<int64>(plan.base.row_count());
-      PROPAGATE_ON_FAILURE(UploadColumns(plan.base, program->used_inputs(), 0, plan.base.row_count(), &base));
-      for (size_t k = 0; k < base.columns.size(); ++k) ic.push_back(base.columns[k].col);
-    }
-    for (size_t k = 0; k < ic.size(); ++k) {   // a NOT_NULLABLE attribute never sets a bit of the bitmap a GPU child hands over
-      if (!plan.base_schema.attribute(program->used_inputs()[k]).is_nullable()) ic[k].nulls = NULL;
     }
     vector<int32_t> key_types, key_nullable;
     for (size_t k = 0; k < keys_.size(); ++k) {
@@ -638,8 +634,32 @@ class GroupCursor : public GpuCursor {
     SSB_CALL(s, ssb_group_create(s->ctx(), static_cast<int32_t>(keys_.size()), key_types.empty() ? &dummy : key_types.data(),
                                  key_nullable.empty() ? &dummy : key_nullable.data(), static_cast<int32_t>(specs.size()),
                                  specs.data(), expected, &group_), "group-by setup");
-    SSB_CALL(s, ssb_group_update_program(group_, program->handle(), ic.empty() ? &dummy_col : ic.data(), rows),
-             "fused group-by");
+    // A scanned host view is fed in chunks: the table accumulates across calls, so device memory is
+    // bounded by one chunk of the input columns and inputs larger than HBM aggregate as well
+    // (the reference spills for that: aggregate_groups.cc:490-1107). Device-resident views and GPU
+    // children are handed over whole.
+    int64 chunk = rows;
+    if (!plan.source) {
+      chunk = static_cast<int64>(1) << 26;
+      if (const char* env = getenv("SSB200_GROUP_CHUNK_ROWS")) chunk = atoll(env);
+      chunk = std::max<int64>(1024, (chunk / 1024) * 1024);   // bitmap words never straddle two chunks
+    }
+    int64 offset = 0;
+    do {
+      const int64 n = std::min<int64>(chunk, rows - offset);
+      if (!plan.source) {
+        ic.clear();
+        PROPAGATE_ON_FAILURE(UploadColumns(plan.base, program->used_inputs(), static_cast<rowcount_t>(offset),
+                                           static_cast<rowcount_t>(n), &base));
+        for (size_t k = 0; k < base.columns.size(); ++k) ic.push_back(base.columns[k].col);
+      }
+      for (size_t k = 0; k < ic.size(); ++k) {   // a NOT_NULLABLE attribute never sets a bit of the bitmap a GPU child hands over
+        if (!plan.base_schema.attribute(program->used_inputs()[k]).is_nullable()) ic[k].nulls = NULL;
+      }
+      SSB_CALL(s, ssb_group_update_program(group_, program->handle(), ic.empty() ? &dummy_col : ic.data(), n),
+               "fused group-by");
+      offset += n;
+    } while (offset < rows);
     PROPAGATE_ON_FAILURE(Finish(s, specs, result));
     return Success(true);
   }

@@ -356,3 +356,23 @@ def test_wide_plans_run_as_column_groups(ref, b200, n):
     nullable_pred = ("(filter (greater (col h) (i64 500000000000)) (all) (compute (compound (col a) (col b) (col c) (col d) (col e0) (col f) "
                      "(col g) (col h) (as s (plus (col e0) (col h)))) (scan 0)))")
     same_results(ref.run(nullable_pred, [cols]), b200.run(nullable_pred, [cols]))
+
+
+def test_group_over_filter_streams_host_chunks(ref, b200, monkeypatch):
+    """GroupAggregate over Filter/Compute of a host table is fed to the GPU chunk by chunk (bounded
+    device memory); with 4096-row chunks the 100k-row table takes 25 calls into one hash table,
+    and FIRST / LAST must still see the rows in input order."""
+    monkeypatch.setenv("SSB200_GROUP_CHUNK_ROWS", "4096")
+    rng = np.random.default_rng(77)
+    n = 100_003
+    cols = [sp.Column("k", sp.INT64, rng.integers(0, 300, n), is_null=rng.random(n) < 0.01),
+            sp.Column("a", sp.INT64, rng.integers(-10**6, 10**6, n), is_null=rng.random(n) < 0.2),
+            sp.Column("b", sp.INT64, rng.integers(0, 100, n))]
+    plan = ("(group (named k) (aggs (SUM s ss) (MIN a mn) (COUNT a ca) (COUNT \"\" n)) "
+            "(filter (less (col b) (i64 70)) (all) (compute (compound (col k) (col a) (col b) (as s (plus (col a) (col b)))) (scan 0))))")
+    same_results(ref.run(plan, [cols]), b200.run(plan, [cols]), ordered=False, sort_cols=[0])
+    plan_fl = ("(group (named k) (aggs (FIRST s fs) (LAST s ls)) "
+               "(compute (compound (col k) (as s (plus (col a) (col b)))) (scan 0)))")
+    same_results(ref.run(plan_fl, [cols]), b200.run(plan_fl, [cols]), ordered=False, sort_cols=[0])
+    plan_scalar = "(scalar_agg (aggs (SUM s ss) (COUNT \"\" n)) (compute (as s (multiply (col b) (i64 3))) (scan 0)))"
+    same_results(ref.run(plan_scalar, [cols]), b200.run(plan_scalar, [cols]))

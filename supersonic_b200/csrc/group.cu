@@ -9,8 +9,9 @@
 //     with the key columns stored beside it (multi-column keys)
 //   * accumulators are 8-byte words per (slot, aggregate) updated with L2 atomics
 //     (atomicAdd on u64 / double, atomicMin/Max, CAS loops for floating MIN/MAX)
-//   * when few groups exist, rows of one warp that hit the same slot are combined with
-//     __match_any_sync + shuffles first, so an atomic is issued per distinct slot per warp
+//   * the common shapes have their own kernels: one packed key with plain aggregates (four rows
+//     per thread in flight), a handful of groups (per-thread accumulators in shared memory, no
+//     atomics in the row loop), up to 256 groups (CTA-private shared-memory table)
 //   * rows that find no free slot within the probe limit are appended to a deferred list; the
 //     host grows the table (re-inserting the old slots) and replays only those rows, so every
 //     row is accumulated exactly once
@@ -30,90 +31,39 @@ namespace ssb {
 
 __global__ void __launch_bounds__(256) group_update_kernel(const __grid_constant__ GroupParams p) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long rows_up = (p.rows + 31) & ~31LL;   // whole warps stay converged for the shuffles
-  const int lane = threadIdx.x & 31;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows_up; i += stride) {
-    const bool live = i < p.rows;
-    long long row = 0, slot = -2;
-    if (live) {
-      row = p.row_index ? p.row_index[i] : i;
-      slot = p.packed ? find_slot_packed(p, row) : find_slot_generic(p, row);
-      if (slot < 0) {
-        const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
-        p.deferred[d] = row;
-      }
-    }
-    const bool active = live && slot >= 0;
-    if (!p.warp_combine) {
-      if (active) {
-        for (int a = 0; a < p.n_aggs; ++a) {
-          const AggDev& ag = p.agg[a];
-          if (ag.in_phys >= 0 && bit_at(ag.in_nulls, row)) continue;
-          if (ag.fn == SSB_AGG_FIRST || ag.fn == SSB_AGG_LAST) {
-            // the first / last non-NULL input in row order (column_aggregator.cc:108-166 walks the
-            // rows in order): the launch only elects the row, first_last_resolve_kernel fetches it
-            if (p.merge) {   // partial tables hold one row per group: plain stores, `dst` rows come first
-              const unsigned long long v = load_raw(ag.in_data, ag.in_phys, row);
-              if (ag.fn == SSB_AGG_LAST || ag.seen[slot] == 0u) ag.acc[static_cast<unsigned long long>(slot) * ag.stride] = v;
-              ag.seen[slot] = 1u;
-            } else if (ag.fn == SSB_AGG_FIRST) {
-              atomicMin(&ag.cand[slot], static_cast<unsigned long long>(row));
-            } else {
-              atomicMax(&ag.cand[slot], static_cast<unsigned long long>(row) + 1ull);
-            }
-            continue;
-          }
-          unsigned long long v = 0, cnt = 1;
-          if (ag.in_phys >= 0) {
-            v = load_raw(ag.in_data, ag.in_phys, row);
-            if (ag.fn == SSB_AGG_COUNT) { cnt = p.merge ? v : 1ull; }
-            else v = convert_value(v, ag.in_phys, ag.out_phys);
-          }
-          apply(ag, slot, v, cnt);
-          if (ag.seen != nullptr) ag.seen[slot] = 1u;
-        }
-      }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.rows; i += stride) {
+    const long long row = p.row_index ? p.row_index[i] : i;
+    const long long slot = p.packed ? find_slot_packed(p, row) : find_slot_generic(p, row);
+    if (slot < 0) {
+      const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+      p.deferred[d] = row;
       continue;
     }
-    // few groups: one atomic per distinct slot per warp
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    if (amask == 0u) continue;
-    unsigned peers = 0;
-    if (active) peers = __match_any_sync(amask, slot);
-    const bool leader = active && (__ffs(peers) - 1 == lane);
     for (int a = 0; a < p.n_aggs; ++a) {
       const AggDev& ag = p.agg[a];
-      const bool has = active && !(ag.in_phys >= 0 && bit_at(ag.in_nulls, row));
-      unsigned long long v = 0, cnt = has ? 1ull : 0ull;
-      if (has && ag.in_phys >= 0) {
+      if (ag.in_phys >= 0 && bit_at(ag.in_nulls, row)) continue;
+      if (ag.fn == SSB_AGG_FIRST || ag.fn == SSB_AGG_LAST) {
+        // the first / last non-NULL input in row order (column_aggregator.cc:108-166 walks the
+        // rows in order): the launch only elects the row, first_last_resolve_kernel fetches it
+        if (p.merge) {   // partial tables hold one row per group: plain stores, `dst` rows come first
+          const unsigned long long v = load_raw(ag.in_data, ag.in_phys, row);
+          if (ag.fn == SSB_AGG_LAST || ag.seen[slot] == 0u) ag.acc[static_cast<unsigned long long>(slot) * ag.stride] = v;
+          ag.seen[slot] = 1u;
+        } else if (ag.fn == SSB_AGG_FIRST) {
+          atomicMin(&ag.cand[slot], static_cast<unsigned long long>(row));
+        } else {
+          atomicMax(&ag.cand[slot], static_cast<unsigned long long>(row) + 1ull);
+        }
+        continue;
+      }
+      unsigned long long v = 0, cnt = 1;
+      if (ag.in_phys >= 0) {
         v = load_raw(ag.in_data, ag.in_phys, row);
         if (ag.fn == SSB_AGG_COUNT) { cnt = p.merge ? v : 1ull; }
         else v = convert_value(v, ag.in_phys, ag.out_phys);
       }
-      // serial over the distinct slots of this warp; each step is a full-warp reduction
-      unsigned remaining = amask;
-      unsigned long long my_v = v, my_c = cnt;
-      bool my_has = has;
-      while (remaining) {
-        const int l = __ffs(remaining) - 1;
-        const unsigned m = __shfl_sync(0xffffffffu, peers, l);
-        const bool in = active && ((m >> lane) & 1u);
-        unsigned long long rv = v, rc = in ? cnt : 0ull;
-        bool rh = in && has;
-        for (int d = 16; d > 0; d >>= 1) {
-          const unsigned long long ov = __shfl_xor_sync(0xffffffffu, rv, d);
-          const unsigned long long oc = __shfl_xor_sync(0xffffffffu, rc, d);
-          const bool oh = __shfl_xor_sync(0xffffffffu, rh ? 1 : 0, d) != 0;
-          if (oh) { rv = rh ? combine(ag, rv, ov) : ov; rh = true; }
-          rc += oc;
-        }
-        if (lane == l) { my_v = rv; my_c = rc; my_has = rh; }
-        remaining &= ~m;
-      }
-      if (leader && my_has) {
-        apply(ag, slot, my_v, my_c);
-        if (ag.seen != nullptr) ag.seen[slot] = 1u;
-      }
+      apply(ag, slot, v, cnt);
+      if (ag.seen != nullptr) ag.seen[slot] = 1u;
     }
   }
 }
@@ -1195,7 +1145,6 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
     p.row_index = replay;
     p.deferred = g->deferred;
     // Few groups after the first megarow (or a scalar aggregate): combine inside the warp.
-    p.warp_combine = 0;   // superseded by the shared-memory kernel for few groups
     cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
     // few groups so far (and few enough aggregates): CTA-private shared-memory tables
     const bool few = !g->has_first_last && g->n_aggs <= kLocalMaxAggs && (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst && g->h_counters[0] <= 256));
@@ -1266,7 +1215,6 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
       if (ctas > div_up(remaining, kTinyThreads * 2)) ctas = div_up(remaining, kTinyThreads * 2);
       kernel<<<static_cast<unsigned>(ctas), kTinyThreads, smem, ctx->stream>>>(p);
     } else if (few) {
-      p.warp_combine = 0;
       long long ctas = static_cast<long long>(ctx->num_sms) * 4;
       if (ctas > div_up(remaining, 256)) ctas = div_up(remaining, 256);
       group_update_smem_kernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);

@@ -34,7 +34,7 @@ struct GroupParams {
   int32_t n_keys, n_aggs;
   int32_t packed;            // single key column stored in the slot word
   int32_t merge;             // inputs are partial aggregates (COUNT adds its input)
-  int32_t warp_combine;      // combine equal slots inside a warp before the atomics
+  int32_t reserved;
   int32_t key_phys[kMaxKeys];
   const void* key_data[kMaxKeys];
   const uint32_t* key_nulls[kMaxKeys];

@@ -8,6 +8,7 @@
 // the deeper operand is evaluated first and parked in a shared-memory slot).
 #include "program.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -398,7 +399,11 @@ class Compiler {
     p.off_nullw = 64 + 512;
     // Filter defers the copy-out by two tiles (the wave's counts are then always published);
     // without a predicate the output position is known at once and one tile of slack suffices.
-    const uint32_t defer = sink_bytes_ ? 0 : (p.has_pred ? kMaxDefer : 1);
+    uint32_t defer = sink_bytes_ ? 0 : (p.has_pred ? kMaxDefer : 1);
+    if (const char* env = getenv("SSB200_EXPR_DEFER")) {   // experiment: copy-out lag of Filter plans (1 or 2 tiles)
+      const int d = atoi(env);
+      if (!sink_bytes_ && p.has_pred && d >= 1 && d <= kMaxDefer) defer = static_cast<uint32_t>(d);
+    }
     p.defer = static_cast<int32_t>(defer);
     if (sink_bytes_) p.out_bytes = 0;
     int stages = kMaxStages;

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
   for (int e = 0; e < kTinyGroups; ++e) my_fp[e] = 0;
   // R rows per thread and iteration; all key and value loads of the R rows are issued before the
   // first one is used, so a thread pays one HBM round trip per iteration, not two per row
-  constexpr int R = 2;
+  constexpr int R = FAST ? 4 : 2;
   const long long stride = static_cast<long long>(gridDim.x) * T * R;
   for (long long base = static_cast<long long>(blockIdx.x) * T * R + tid; base < p.rows; base += stride) {
     long long rows_[R];
@@ -370,13 +370,19 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
     for (int j = 0; j < R; ++j) {
       const long long row = rows_[j];
       if (row < 0) continue;
-      unsigned long long fp = 0x9E3779B97F4A7C15ull + knull[j];
+      unsigned long long fp;
+      if (FAST && K2) {
+        // NOT NULL keys, at most two columns: one key is its own (exact) fingerprint
+        fp = NK > 1 ? kv[j][0] * 0x9E3779B97F4A7C15ull + kv[j][1] : kv[j][0];
+      } else {
+        fp = 0x9E3779B97F4A7C15ull + knull[j];
 #pragma unroll
-      for (int c = 0; c < KMAX; ++c) if (c < NK) fp = (fp ^ kv[j][c]) * 0xff51afd7ed558ccdULL + c;
+        for (int c = 0; c < KMAX; ++c) if (c < NK) fp = (fp ^ kv[j][c]) * 0xff51afd7ed558ccdULL + c;
+      }
       int g = -1;
 #pragma unroll
       for (int e = 0; e < kTinyGroups; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
-      if (g >= 0) {
+      if (g >= 0 && !(FAST && K2 && NK <= 1)) {
         // equal fingerprints: confirm on the key values (a different key restarts below)
         bool same = l_knull[g] == knull[j];
 #pragma unroll
@@ -409,6 +415,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
         }
       }
       if (g >= 0 && FAST) t_seen[g][tid] = 0xffffffffu;   // NOT NULL inputs: every aggregate saw this row
+      unsigned long long* const acc_base = t_acc + (g < 0 ? 0 : g) * A * T + tid;
 #pragma unroll
       for (int a = 0; a < kLocalMaxAggs; ++a) {
         if (a >= A) break;
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(kTinyThreads) group_update_tiny_kernel(const _
           if (ag.seen != nullptr) ag.seen[slot] = 1u;
           continue;
         }
-        unsigned long long* acc = &t_acc[(g * A + a) * T + tid];
+        unsigned long long* acc = acc_base + a * T;
         switch (ag.pad) {
           case TA_COUNT: *acc += cnt; break;
           case TA_SUM_F64: *acc = Codec<double>::enc(Codec<double>::dec(*acc) + Codec<double>::dec(v)); break;
@@ -1212,7 +1219,8 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
       if (per_sm < 1) per_sm = 1;
       if (per_sm > 8) per_sm = 8;
       long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
-      if (ctas > div_up(remaining, kTinyThreads * 2)) ctas = div_up(remaining, kTinyThreads * 2);
+      const long long rows_per_cta = kTinyThreads * (tfast ? 4 : 2);
+      if (ctas > div_up(remaining, rows_per_cta)) ctas = div_up(remaining, rows_per_cta);
       kernel<<<static_cast<unsigned>(ctas), kTinyThreads, smem, ctx->stream>>>(p);
     } else if (few) {
       long long ctas = static_cast<long long>(ctx->num_sms) * 4;

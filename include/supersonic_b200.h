@@ -84,6 +84,8 @@ int ssb_free_host(ssb_ctx* ctx, void* ptr);
 int ssb_memcpy_h2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
 int ssb_memcpy_d2h(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
 int ssb_memcpy_d2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes);  /* async */
+/* Bytes moved by ssb_memcpy_h2d / ssb_memcpy_d2h in this process so far (all contexts). */
+void ssb_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
 int ssb_memset(ssb_ctx* ctx, void* dst, int value, size_t bytes);            /* async */
 /* 1 when `ptr` is device memory, 0 for host memory (pageable or pinned). Lets ScanView accept
  * views over either (cursor/core/scan_view.h:35 takes any readable pointer). */

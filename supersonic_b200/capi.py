@@ -79,6 +79,7 @@ def load():
         "ssb_free_host": (C.c_int, [P, P]),
         "ssb_memcpy_h2d": (C.c_int, [P, P, P, C.c_size_t]),
         "ssb_memcpy_d2h": (C.c_int, [P, P, P, C.c_size_t]),
+        "ssb_transfer_bytes": (None, [C.POINTER(U64), C.POINTER(U64)]),
         "ssb_memcpy_d2d": (C.c_int, [P, P, P, C.c_size_t]),
         "ssb_memset": (C.c_int, [P, P, C.c_int, C.c_size_t]),
         "ssb_pointer_is_device": (C.c_int, [P]),

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.h"
 
 namespace ssb {
@@ -240,13 +242,21 @@ int ssb_free_host(ssb_ctx* ctx, void* ptr) {
   if (ptr) SSB_CUDA(ctx, cudaFreeHost(ptr));
   return 0;
 }
+static std::atomic<unsigned long long> g_h2d_bytes(0), g_d2h_bytes(0);
+
 int ssb_memcpy_h2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  g_h2d_bytes.fetch_add(bytes, std::memory_order_relaxed);
   return 0;
 }
 int ssb_memcpy_d2h(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  g_d2h_bytes.fetch_add(bytes, std::memory_order_relaxed);
   return 0;
+}
+void ssb_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
+  if (h2d) *h2d = g_h2d_bytes.load(std::memory_order_relaxed);
+  if (d2h) *d2h = g_d2h_bytes.load(std::memory_order_relaxed);
 }
 int ssb_memcpy_d2d(ssb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes) SSB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -2,7 +2,12 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
+#include <thread>
 
 #include "internal.h"
 
@@ -69,6 +74,133 @@ class ViewCursor : public Cursor {
   volatile bool interrupted_;
 };
 
+// ------------------------------------------------------------------ transfer narrowing
+// Streaming a host table is bound by PCIe, not by the GPU (51 GB/s against 5 TB/s of kernel
+// throughput). 64-bit integer columns whose values all fit 32 bits in a chunk therefore cross the
+// bus as 32-bit values: host threads narrow the chunk into pinned staging (checking every value),
+// the kernel program of that chunk widens them again with a CAST at the INPUT node. Lossless by
+// construction -- a chunk with one value that does not fit is sent as it is.
+class HostPool {
+ public:
+  static HostPool& Get() { static HostPool pool; return pool; }
+  int size() const { return static_cast<int>(threads_.size()) + 1; }
+  // Runs fn(part, parts) for part in [0, parts) on the pool (the caller works too); returns when all are done.
+  void Run(int parts, const std::function<void(int, int)>& fn) {
+    if (parts <= 1 || threads_.empty()) { for (int i = 0; i < parts; ++i) fn(i, parts); return; }
+    std::lock_guard<std::mutex> one_caller(run_mu_);
+    {
+      std::unique_lock<std::mutex> lock(mu_);
+      fn_ = &fn; parts_ = parts; next_ = 0; pending_ = parts; ++generation_;
+    }
+    cv_.notify_all();
+    Work();
+    std::unique_lock<std::mutex> lock(mu_);
+    done_.wait(lock, [this] { return pending_ == 0; });
+    fn_ = NULL;
+  }
+ private:
+  HostPool() : fn_(NULL), parts_(0), next_(0), pending_(0), generation_(0), stop_(false) {
+    int n = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* env = getenv("SSB200_HOST_THREADS")) n = atoi(env);
+    n = std::max(1, std::min(n, 32));
+    for (int i = 1; i < n; ++i) threads_.push_back(std::thread([this] { Loop(); }));
+  }
+  ~HostPool() {
+    { std::unique_lock<std::mutex> lock(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (size_t i = 0; i < threads_.size(); ++i) threads_[i].join();
+  }
+  void Loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+      }
+      Work();
+    }
+  }
+  void Work() {
+    for (;;) {
+      int part;
+      const std::function<void(int, int)>* fn;
+      int parts;
+      {
+        std::unique_lock<std::mutex> lock(mu_);
+        if (fn_ == NULL || next_ >= parts_) return;
+        part = next_++; fn = fn_; parts = parts_;
+      }
+      (*fn)(part, parts);
+      std::unique_lock<std::mutex> lock(mu_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int, int)>* fn_;
+  int parts_, next_, pending_;
+  unsigned long long generation_;
+  bool stop_;
+};
+
+// dst[i] = int32(src[i]) for i < rows; false when some value does not fit (dst is then garbage).
+bool NarrowInt64Column(const int64* src, int32* dst, rowcount_t rows) {
+  HostPool& pool = HostPool::Get();
+  const int parts = static_cast<int>(std::min<rowcount_t>(static_cast<rowcount_t>(pool.size()), rows / 65536 + 1));
+  std::atomic<int> misfit(0);
+  pool.Run(parts, [&](int part, int n_parts) {
+    const rowcount_t begin = rows * part / n_parts, end = rows * (part + 1) / n_parts;
+    int64 bad = 0;
+    for (rowcount_t i = begin; i < end; ++i) {
+      const int64 v = src[i];
+      const int32 n = static_cast<int32>(v);
+      dst[i] = n;
+      bad |= v ^ static_cast<int64>(n);
+    }
+    if (bad != 0) misfit.store(1, std::memory_order_relaxed);
+  });
+  return misfit.load(std::memory_order_relaxed) == 0;
+}
+
+// The lowered program with the INPUT nodes in `narrow_mask` (bit k = k-th used input) declared INT32
+// and widened back to their type by a CAST.
+void NarrowedProgram(const vector<ssb_expr_node>& nodes, const vector<int32_t>& outs, int pred, uint32_t narrow_mask,
+                     vector<ssb_expr_node>* new_nodes, vector<int32_t>* new_outs, int* new_pred) {
+  vector<int> index(nodes.size(), -1);
+  new_nodes->clear();
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    ssb_expr_node nd = nodes[i];
+    if (nd.op == SSB_OP_INPUT) {
+      if ((narrow_mask >> nd.arg[0]) & 1u) {
+        ssb_expr_node in = nd;
+        in.out_type = SSB_INT32;
+        new_nodes->push_back(in);
+        ssb_expr_node cast;
+        memset(&cast, 0, sizeof(cast));
+        cast.op = SSB_OP_CAST;
+        cast.out_type = nd.out_type;
+        cast.arg[0] = static_cast<int32_t>(new_nodes->size()) - 1;
+        cast.arg[1] = cast.arg[2] = -1;
+        new_nodes->push_back(cast);
+      } else {
+        new_nodes->push_back(nd);
+      }
+    } else {
+      if (nd.op != SSB_OP_CONST) {
+        for (int a = 0; a < 3; ++a) if (nd.arg[a] >= 0) nd.arg[a] = index[nd.arg[a]];
+      }
+      new_nodes->push_back(nd);
+    }
+    index[i] = static_cast<int>(new_nodes->size()) - 1;
+  }
+  new_outs->clear();
+  for (size_t j = 0; j < outs.size(); ++j) new_outs->push_back(index[outs[j]]);
+  *new_pred = pred >= 0 ? index[pred] : -1;
+}
+
 // ------------------------------------------------------------------ row-wise cursor
 // One fused kernel for a chain of ScanView / Compute / Filter / Project
 // (replaces ComputeCursor::Next, FilterCursor::Next, ProjectCursor::Next).
@@ -128,7 +260,7 @@ class RowwiseCursor : public GpuCursor {
       if (!l.busy) return ResultView::EOS();
       const int rc = ssb_ctx_sync(l.ctx);
       if (rc != 0) return ResultView::Failure(Session::ErrorOn(l.ctx, rc, "row-wise pipeline"));
-      const int frc = ssb_program_check_failure(l.program);
+      const int frc = ssb_program_check_failure(l.launched ? l.launched : l.program);
       if (frc != 0) return ResultView::Failure(Session::ErrorOn(l.ctx, frc, "expression evaluation"));
       l.kept = *l.h_count;
       served_ = 0;
@@ -210,6 +342,9 @@ class RowwiseCursor : public GpuCursor {
   struct Lane {
     ssb_ctx* ctx;
     ssb_program* program;
+    std::map<uint32_t, ssb_program*> narrowed;   // program variants by narrow mask (transfer narrowing)
+    ssb_program* launched;                       // the variant the lane's current chunk ran
+    vector<void*> h_narrow;                      // pinned staging of the narrowed chunk per used input (or NULL)
     vector<void*> d_in, d_in_nulls, d_out, d_out_nulls, h_out, h_out_nulls;
     vector<std::pair<int, std::pair<void*, size_t> > > owned;   // (kind, (ptr, granted)) from the MemoryPool
     void* d_bools;
@@ -217,11 +352,14 @@ class RowwiseCursor : public GpuCursor {
     int64_t* h_count;
     int64 kept;
     bool busy;
-    void Reset() { ctx = NULL; program = NULL; d_bools = NULL; d_count = NULL; h_count = NULL; kept = 0; busy = false; }
+    void Reset() { ctx = NULL; program = NULL; launched = NULL; d_bools = NULL; d_count = NULL; h_count = NULL; kept = 0; busy = false; }
     void Free() {
       if (ctx == NULL) return;
       ssb_ctx_sync(ctx);
       if (program) ssb_program_destroy(program);
+      for (std::map<uint32_t, ssb_program*>::iterator it = narrowed.begin(); it != narrowed.end(); ++it) ssb_program_destroy(it->second);
+      narrowed.clear();
+      h_narrow.clear();
       for (size_t i = 0; i < owned.size(); ++i) {
         MemoryPool::Release(static_cast<MemoryPool::Kind>(owned[i].first), owned[i].second.first, owned[i].second.second);
       }
@@ -260,12 +398,14 @@ class RowwiseCursor : public GpuCursor {
     if (const char* env = getenv("SSB200_CHUNK_ROWS")) chunk = static_cast<rowcount_t>(atoll(env));
     chunk = (chunk / 1024) * 1024;
     if (chunk < 1024 || rows <= chunk) return Success();
-    vector<int32_t> outs;
-    int pred = -1;
+    vector<int32_t>& outs = outs_;
+    int& pred = pred_;
     LowerProgram(plan_.outputs, plan_.predicate, &nodes_, &used_, &outs, &pred);
     for (size_t k = 0; k < used_.size(); ++k) {
       if (IsDevicePointer(plan_.base.column(used_[k]).data().raw())) return Success();
     }
+    narrowing_ = getenv("SSB200_NARROW_TRANSFERS") == NULL || atoi(getenv("SSB200_NARROW_TRANSFERS")) != 0;
+    narrow_skip_.assign(used_.size(), 0);
     FailureOr<Session*> sr = Session::Get();
     PROPAGATE_ON_FAILURE(sr);
     vector<int32_t> types, nullable;
@@ -290,6 +430,13 @@ class RowwiseCursor : public GpuCursor {
         POOLED(dn, l, DEVICE, chunk / 8 + 256);
         l.d_in.push_back(d);
         l.d_in_nulls.push_back(dn);
+        const DataType t = plan_.base_schema.attribute(used_[k]).type();
+        void* staging = NULL;
+        if (narrowing_ && k < 32 && (t == INT64 || t == DATETIME)) {
+          POOLED(hn, l, PINNED, chunk * 4 + 256);
+          staging = hn;
+        }
+        l.h_narrow.push_back(staging);
       }
       for (int j = 0; j < plan_.schema.attribute_count(); ++j) {
         const size_t w = GetTypeInfo(plan_.schema.attribute(j).type()).size();
@@ -321,14 +468,30 @@ class RowwiseCursor : public GpuCursor {
     const rowcount_t rows = total - first < chunk_ ? total - first : chunk_;
     next_first_ += rows;
     vector<ssb_column> ic(used_.size()), oc(l.d_out.size());
+    uint32_t narrow_mask = 0;
     for (size_t k = 0; k < used_.size(); ++k) {
       const Column& src = plan_.base.column(used_[k]);
       const size_t w = src.type_info().size();
-      LANE_CALL(l, ssb_memcpy_h2d(l.ctx, l.d_in[k], static_cast<const char*>(src.data().raw()) + first * w, rows * w), "upload");
+      const char* host = static_cast<const char*>(src.data().raw()) + first * w;
       ic[k].data = l.d_in[k];
       ic[k].dtype = src.attribute().type();
       ic[k].reserved = 0;
       ic[k].nulls = NULL;
+      // transfer narrowing: a column that did not fit is not tried again for the next 16 chunks
+      bool narrowed = false;
+      if (l.h_narrow[k] != NULL && narrow_skip_[k] == 0) {
+        narrowed = NarrowInt64Column(reinterpret_cast<const int64*>(host), static_cast<int32*>(l.h_narrow[k]), rows);
+        if (!narrowed) narrow_skip_[k] = 16;
+      } else if (narrow_skip_[k] > 0) {
+        --narrow_skip_[k];
+      }
+      if (narrowed) {
+        LANE_CALL(l, ssb_memcpy_h2d(l.ctx, l.d_in[k], l.h_narrow[k], rows * 4), "upload (narrowed)");
+        ic[k].dtype = INT32;
+        narrow_mask |= 1u << k;
+      } else {
+        LANE_CALL(l, ssb_memcpy_h2d(l.ctx, l.d_in[k], host, rows * w), "upload");
+      }
       if (src.is_null() != NULL) {
         LANE_CALL(l, ssb_memcpy_h2d(l.ctx, l.d_bools, src.is_null() + first, rows), "upload nulls");
         LANE_CALL(l, ssb_nulls_pack(l.ctx, static_cast<const uint8_t*>(l.d_bools), static_cast<int64_t>(rows),
@@ -344,7 +507,29 @@ class RowwiseCursor : public GpuCursor {
     }
     ssb_column dummy;
     memset(&dummy, 0, sizeof(dummy));
-    LANE_CALL(l, ssb_program_run(l.program, ic.empty() ? &dummy : ic.data(), static_cast<int64_t>(rows),
+    ssb_program* program = l.program;
+    if (narrow_mask != 0) {
+      std::map<uint32_t, ssb_program*>::iterator it = l.narrowed.find(narrow_mask);
+      if (it == l.narrowed.end()) {
+        vector<ssb_expr_node> nodes;
+        vector<int32_t> outs, types, nullable;
+        int pred = -1;
+        NarrowedProgram(nodes_, outs_, pred_, narrow_mask, &nodes, &outs, &pred);
+        for (size_t k = 0; k < used_.size(); ++k) {
+          types.push_back(((narrow_mask >> k) & 1u) ? static_cast<int32_t>(INT32) : static_cast<int32_t>(plan_.base_schema.attribute(used_[k]).type()));
+          nullable.push_back(plan_.base_schema.attribute(used_[k]).is_nullable() ? 1 : 0);
+        }
+        int32_t dummy32 = 0;
+        ssb_program* variant = NULL;
+        LANE_CALL(l, ssb_program_create(l.ctx, nodes.data(), static_cast<int32_t>(nodes.size()), static_cast<int32_t>(used_.size()),
+                                        types.data(), nullable.data(), outs.empty() ? &dummy32 : outs.data(),
+                                        static_cast<int32_t>(outs.size()), pred, &variant), "expression compilation (narrowed inputs)");
+        it = l.narrowed.insert(std::make_pair(narrow_mask, variant)).first;
+      }
+      program = it->second;
+    }
+    l.launched = program;
+    LANE_CALL(l, ssb_program_run(program, ic.empty() ? &dummy : ic.data(), static_cast<int64_t>(rows),
                                  oc.empty() ? &dummy : oc.data(), l.d_count), "expression evaluation");
     LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_count, l.d_count, sizeof(int64_t)), "download");
     for (size_t j = 0; j < oc.size(); ++j) {
@@ -370,6 +555,10 @@ class RowwiseCursor : public GpuCursor {
   View out_view_;
   vector<ssb_expr_node> nodes_;
   vector<int> used_;
+  vector<int32_t> outs_;
+  int pred_ = -1;
+  bool narrowing_ = false;
+  vector<int> narrow_skip_;
   Lane lanes_[2];
   rowcount_t chunk_, next_first_;
   int active_;

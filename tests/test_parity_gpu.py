@@ -376,3 +376,29 @@ def test_group_over_filter_streams_host_chunks(ref, b200, monkeypatch):
     same_results(ref.run(plan_fl, [cols]), b200.run(plan_fl, [cols]), ordered=False, sort_cols=[0])
     plan_scalar = "(scalar_agg (aggs (SUM s ss) (COUNT \"\" n)) (compute (as s (multiply (col b) (i64 3))) (scan 0)))"
     same_results(ref.run(plan_scalar, [cols]), b200.run(plan_scalar, [cols]))
+
+
+@pytest.mark.parametrize("narrow", ["1", "0"])
+def test_streaming_with_transfer_narrowing(ref, b200, monkeypatch, narrow):
+    """Host tables stream to the GPU in chunks; 64-bit integer columns whose chunk fits 32 bits
+    travel narrowed and are widened by the kernel. Columns that fit in some chunks only (the
+    program variant changes from chunk to chunk), never, always, NULL cells with wide garbage,
+    DATETIME: the result must not depend on it."""
+    monkeypatch.setenv("SSB200_CHUNK_ROWS", "8192")
+    monkeypatch.setenv("SSB200_NARROW_TRANSFERS", narrow)
+    rng = np.random.default_rng(5)
+    n = 100_000
+    sometimes = rng.integers(-1000, 1000, n)
+    sometimes[30_000:50_000] = rng.integers(-2**62, 2**62, 20_000)       # these chunks do not fit
+    sometimes[77_777] = 2**31                                             # one value just outside int32
+    edge = rng.integers(-2**31, 2**31, n)
+    edge[0], edge[1] = -2**31, 2**31 - 1                                  # the int32 limits fit
+    garbage = rng.integers(0, 100, n)
+    gnull = rng.random(n) < 0.3
+    garbage[gnull] = 2**50                                                # wide garbage under NULL
+    cols = [sp.Column("s", sp.INT64, sometimes), sp.Column("e", sp.INT64, edge),
+            sp.Column("w", sp.INT64, rng.integers(-2**62, 2**62, n)), sp.Column("g", sp.INT64, garbage, is_null=gnull),
+            sp.Column("t", sp.DATETIME, rng.integers(0, 10**9, n)), sp.Column("d", sp.INT64, rng.integers(0, 2**20, n))]
+    plan = ("(filter (less (col d) (i64 600000)) (all) (compute (compound (as x (plus (multiply (col s) (col e)) (col w))) "
+            "(col s) (col e) (col g) (col t) (as y (plus (col g) (col d)))) (scan 0)))")
+    same_results(ref.run(plan, [cols], next_max_rows=1024), b200.run(plan, [cols], next_max_rows=5000))

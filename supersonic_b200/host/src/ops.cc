@@ -1,6 +1,10 @@
 // ops.cc -- Operation factories and GPU cursors (see include/supersonic/cursor.h).
 #include <stdio.h>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -102,7 +106,7 @@ class HostPool {
   HostPool() : fn_(NULL), parts_(0), next_(0), pending_(0), generation_(0), stop_(false) {
     int n = static_cast<int>(std::thread::hardware_concurrency());
     if (const char* env = getenv("SSB200_HOST_THREADS")) n = atoi(env);
-    n = std::max(1, std::min(n, 32));
+    n = std::max(1, std::min(n, 128));
     for (int i = 1; i < n; ++i) threads_.push_back(std::thread([this] { Loop(); }));
   }
   ~HostPool() {
@@ -151,14 +155,29 @@ bool NarrowInt64Column(const int64* src, int32* dst, rowcount_t rows) {
   HostPool& pool = HostPool::Get();
   const int parts = static_cast<int>(std::min<rowcount_t>(static_cast<rowcount_t>(pool.size()), rows / 65536 + 1));
   std::atomic<int> misfit(0);
+  static const bool streaming_stores = getenv("SSB200_NARROW_NT") != NULL && atoi(getenv("SSB200_NARROW_NT")) != 0;
   pool.Run(parts, [&](int part, int n_parts) {
     const rowcount_t begin = rows * part / n_parts, end = rows * (part + 1) / n_parts;
     int64 bad = 0;
-    for (rowcount_t i = begin; i < end; ++i) {
-      const int64 v = src[i];
-      const int32 n = static_cast<int32>(v);
-      dst[i] = n;
-      bad |= v ^ static_cast<int64>(n);
+#if defined(__x86_64__)
+    if (streaming_stores) {
+      // the staging buffer is only read by the DMA engine: the stores may skip the cache
+      for (rowcount_t i = begin; i < end; ++i) {
+        const int64 v = src[i];
+        const int32 n = static_cast<int32>(v);
+        _mm_stream_si32(dst + i, n);
+        bad |= v ^ static_cast<int64>(n);
+      }
+      _mm_sfence();
+    } else
+#endif
+    {
+      for (rowcount_t i = begin; i < end; ++i) {
+        const int64 v = src[i];
+        const int32 n = static_cast<int32>(v);
+        dst[i] = n;
+        bad |= v ^ static_cast<int64>(n);
+      }
     }
     if (bad != 0) misfit.store(1, std::memory_order_relaxed);
   });

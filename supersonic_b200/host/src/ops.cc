@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -488,6 +489,8 @@ class RowwiseCursor : public GpuCursor {
     next_first_ += rows;
     vector<ssb_column> ic(used_.size()), oc(l.d_out.size());
     uint32_t narrow_mask = 0;
+    double narrow_seconds = 0;
+    size_t chunk_bytes = 0;
     for (size_t k = 0; k < used_.size(); ++k) {
       const Column& src = plan_.base.column(used_[k]);
       const size_t w = src.type_info().size();
@@ -498,8 +501,11 @@ class RowwiseCursor : public GpuCursor {
       ic[k].nulls = NULL;
       // transfer narrowing: a column that did not fit is not tried again for the next 16 chunks
       bool narrowed = false;
-      if (l.h_narrow[k] != NULL && narrow_skip_[k] == 0) {
+      chunk_bytes += rows * w;
+      if (narrowing_ && l.h_narrow[k] != NULL && narrow_skip_[k] == 0) {
+        const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
         narrowed = NarrowInt64Column(reinterpret_cast<const int64*>(host), static_cast<int32*>(l.h_narrow[k]), rows);
+        narrow_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (!narrowed) narrow_skip_[k] = 16;
       } else if (narrow_skip_[k] > 0) {
         --narrow_skip_[k];
@@ -526,6 +532,13 @@ class RowwiseCursor : public GpuCursor {
     }
     ssb_column dummy;
     memset(&dummy, 0, sizeof(dummy));
+    // Narrowing pays while the host narrows a chunk faster than the bus would move it unnarrowed
+    // (the two overlap across the lanes); on a host with few cores it does not, and is switched off.
+    if (narrowing_ && narrow_seconds > 0) {
+      narrow_total_seconds_ += narrow_seconds;
+      narrow_total_bytes_ += static_cast<double>(chunk_bytes);
+      if (++narrow_chunks_ >= 4 && narrow_total_seconds_ > narrow_total_bytes_ / 50e9) narrowing_ = false;
+    }
     ssb_program* program = l.program;
     if (narrow_mask != 0) {
       std::map<uint32_t, ssb_program*>::iterator it = l.narrowed.find(narrow_mask);
@@ -578,6 +591,8 @@ class RowwiseCursor : public GpuCursor {
   int pred_ = -1;
   bool narrowing_ = false;
   vector<int> narrow_skip_;
+  double narrow_total_seconds_ = 0, narrow_total_bytes_ = 0;
+  int narrow_chunks_ = 0;
   Lane lanes_[2];
   rowcount_t chunk_, next_first_;
   int active_;

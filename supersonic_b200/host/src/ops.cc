@@ -151,6 +151,9 @@ class HostPool {
   bool stop_;
 };
 
+// Set once a cursor found that this host narrows slower than the bus moves the unnarrowed chunk.
+std::atomic<bool>& NarrowingUnprofitable() { static std::atomic<bool> flag(false); return flag; }
+
 // dst[i] = int32(src[i]) for i < rows; false when some value does not fit (dst is then garbage).
 bool NarrowInt64Column(const int64* src, int32* dst, rowcount_t rows) {
   HostPool& pool = HostPool::Get();
@@ -424,7 +427,8 @@ class RowwiseCursor : public GpuCursor {
     for (size_t k = 0; k < used_.size(); ++k) {
       if (IsDevicePointer(plan_.base.column(used_[k]).data().raw())) return Success();
     }
-    narrowing_ = getenv("SSB200_NARROW_TRANSFERS") == NULL || atoi(getenv("SSB200_NARROW_TRANSFERS")) != 0;
+    narrowing_ = (getenv("SSB200_NARROW_TRANSFERS") == NULL || atoi(getenv("SSB200_NARROW_TRANSFERS")) != 0) &&
+                 !NarrowingUnprofitable().load(std::memory_order_relaxed);
     narrow_skip_.assign(used_.size(), 0);
     FailureOr<Session*> sr = Session::Get();
     PROPAGATE_ON_FAILURE(sr);
@@ -537,7 +541,10 @@ class RowwiseCursor : public GpuCursor {
     if (narrowing_ && narrow_seconds > 0) {
       narrow_total_seconds_ += narrow_seconds;
       narrow_total_bytes_ += static_cast<double>(chunk_bytes);
-      if (++narrow_chunks_ >= 4 && narrow_total_seconds_ > narrow_total_bytes_ / 50e9) narrowing_ = false;
+      if (++narrow_chunks_ >= 4 && narrow_total_seconds_ > narrow_total_bytes_ / 50e9) {
+        narrowing_ = false;
+        NarrowingUnprofitable().store(true, std::memory_order_relaxed);   // later cursors of this process do not probe again
+      }
     }
     ssb_program* program = l.program;
     if (narrow_mask != 0) {

@@ -106,6 +106,8 @@ class HostPool {
  private:
   HostPool() : fn_(NULL), parts_(0), next_(0), pending_(0), generation_(0), stop_(false) {
     int n = static_cast<int>(std::thread::hardware_concurrency());
+    // one process per GPU (torchrun): the ranks of a box share its cores
+    if (const char* env = getenv("LOCAL_WORLD_SIZE")) { const int ranks = atoi(env); if (ranks > 1) n /= ranks; }
     if (const char* env = getenv("SSB200_HOST_THREADS")) n = atoi(env);
     n = std::max(1, std::min(n, 128));
     for (int i = 1; i < n; ++i) threads_.push_back(std::thread([this] { Loop(); }));

@@ -1,3 +1,5 @@
+"""BASELINE config 2 variant B (ProjectAllAttributes: eight columns + e = a*b+c under the filter) timed with a
+stopwatch around the whole program (a wide plan runs as several column-group kernels)."""
 import sys, os, numpy as np
 sys.path.insert(0, os.getcwd())
 from supersonic_b200 import capi

@@ -434,8 +434,9 @@ __global__ void sort_key_kernel(const void* __restrict__ col, const uint32_t* __
       case T_U32: u = static_cast<const uint32_t*>(col)[r]; break;
       case T_I64: u = static_cast<unsigned long long>(static_cast<const long long*>(col)[r]) ^ 0x8000000000000000ull; break;
       case T_U64: u = static_cast<const unsigned long long*>(col)[r]; break;
-      case T_F32: { uint32_t b = static_cast<const uint32_t*>(col)[r]; b = (b & 0x80000000u) ? ~b : (b | 0x80000000u); u = b; } break;
-      case T_F64: { unsigned long long b = static_cast<const unsigned long long*>(col)[r]; b = (b >> 63) ? ~b : (b | 0x8000000000000000ull); u = b; } break;
+      // -0.0 and +0.0 compare equal in the reference (sort.cc:151 compares with operator<): one image for both
+      case T_F32: { uint32_t b = static_cast<const uint32_t*>(col)[r]; if ((b << 1) == 0u) b = 0u; b = (b & 0x80000000u) ? ~b : (b | 0x80000000u); u = b; } break;
+      case T_F64: { unsigned long long b = static_cast<const unsigned long long*>(col)[r]; if ((b << 1) == 0ull) b = 0ull; b = (b >> 63) ? ~b : (b | 0x8000000000000000ull); u = b; } break;
       default: u = static_cast<const uint8_t*>(col)[r] != 0 ? 1ull : 0ull; break;
     }
     if (isn) u = 0;   // value under NULL is garbage: make equal so that later keys decide

@@ -287,6 +287,15 @@ class CudaJoinKernels(object):
     def finish(self):
         self.ctx.sync()
 
+    def sort_perm(self, keys, descending):
+        """Stable sort permutation by several key columns (first = most significant)."""
+        n = keys[0][0].numel()
+        perm = self.empty(n, self.capi.INT64)
+        if n:
+            desc = (C.c_int32 * len(keys))(*[1 if d else 0 for d in descending])
+            self.ctx.check(self.ctx.lib.ssb_sort_permutation(self.ctx.h, len(keys), self._cols(keys), desc, n, perm.data_ptr()))
+        return perm
+
     def order_by(self, key):
         """Stable ascending order of an INT64 column."""
         n = key.numel()
@@ -481,3 +490,76 @@ class ShardedHashJoin(object):
         if r_null is not None:
             r_null = k.gather((r_null, 6), order)
         return lhs_rows, out_l, out_r, r_null
+
+
+# ---------------------------------------------------------------------------------------------
+# Sort over row-range shards (sample sort)
+# ---------------------------------------------------------------------------------------------
+class ShardedSort(object):
+    """Sort(order, project) over a table sharded by row range: every rank sorts its shard
+    (ssb_sort_permutation, stable), splitters are taken from an all-gathered sample of the most
+    significant key, rows are exchanged by key range with one all-to-all per column (NCCL), and
+    every rank sorts what it received. After the call rank r holds the r-th range of the global
+    order; rows with equal keys keep their global input order (all rows with one value of the most
+    significant key meet on one rank, chunks arrive in rank order, and both sorts are stable), so
+    the concatenation in rank order is the reference's output (cursor/core/sort.cc:150-322) whenever
+    its order is total. NOT NULL key columns; the most significant key must be a signed or
+    floating type (unsigned columns travel as their signed bit image here)."""
+
+    SAMPLES_PER_RANK = 64
+
+    def __init__(self, kernels, group=None):
+        self.k, self.group = kernels, group
+
+    def run(self, keys, descending, cols):
+        """keys: [(tensor, SSB dtype)] most significant first; descending: [bool] per key;
+        cols: payload columns. Returns (sorted key columns, sorted payload columns) of this rank."""
+        with self.k.scope():
+            out = self._run(keys, descending, cols)
+        self.k.finish()
+        return out
+
+    def _run(self, keys, descending, cols):
+        import torch
+        import torch.distributed as dist
+        k, g = self.k, self.group
+        world = dist.get_world_size(g)
+        if keys[0][1] in (3, 8):   # UINT64, UINT32
+            raise NotImplementedError("ShardedSort: the most significant key must be a signed or floating column")
+        device = keys[0][0].device
+        # 1. local stable sort
+        perm = k.sort_perm(keys, descending)
+        keys = [(k.gather(c, perm), c[1]) for c in keys]
+        cols = [(k.gather(c, perm), c[1]) for c in cols]
+        first = keys[0][0]
+        n = first.numel()
+        # 2. splitters from an all-gathered regular sample of the most significant key
+        s = self.SAMPLES_PER_RANK
+        if n:
+            pos = (torch.arange(s, device=device, dtype=torch.int64) * n) // s
+            sample = k.gather(keys[0], pos)
+        else:
+            sample = first[:0]
+        gathered = torch.cat(allgather_ragged(sample, g))
+        gathered, _ = torch.sort(gathered)
+        m = gathered.numel()
+        if m == 0:
+            return keys, cols
+        splitters = gathered[[min(m - 1, (m * (r + 1)) // world) for r in range(world - 1)]] if world > 1 else gathered[:0]
+        # 3. rows per destination: in ascending terms dest(key) = number of splitters <= key
+        asc = first if not descending[0] else first.flip(0)
+        bounds = torch.searchsorted(asc.contiguous(), splitters, right=False).tolist() if world > 1 else []
+        # keys equal to a splitter go right of it: searchsorted(..., right=False) on the rows gives the first
+        # row >= splitter, i.e. rows < splitter stay left
+        edges = [0] + [int(b) for b in bounds] + [n]
+        counts = [edges[i + 1] - edges[i] for i in range(world)]
+        if descending[0]:
+            counts = counts[::-1]           # the local data is laid out largest first = destination 0 first
+        recv = _exchange_counts(counts, device, g)
+        # 4. exchange, 5. sort what arrived (chunks are sorted already; the stable sort merges them)
+        keys = [(_exchange(c[0], counts, recv, g), c[1]) for c in keys]
+        cols = [(_exchange(c[0], counts, recv, g), c[1]) for c in cols]
+        perm = k.sort_perm(keys, descending)
+        keys = [(k.gather(c, perm), c[1]) for c in keys]
+        cols = [(k.gather(c, perm), c[1]) for c in cols]
+        return keys, cols

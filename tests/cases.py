@@ -171,6 +171,10 @@ GOLDEN = [
     ("sort_two_keys", "(sort (order (a ASC) (b DESC)) (named b a) (scan 0))",
      [[col("a", sp.INT64, [2, 1, 2, 1]), col("b", sp.DOUBLE, [0.5, -1.0, 7.0, 3.0])]],
      {"b": [3.0, -1.0, 7.0, 0.5], "a": [1, 1, 2, 2]}, True),
+    # -0.0 and +0.0 are one key value (sort.cc:151 compares with operator<): the second key decides among them
+    ("sort_signed_zero", "(sort (order (x DESC) (v ASC)) (all) (scan 0))",
+     [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0, -1.0]), col("v", sp.INT32, [5, 4, 3, 2, 1, 0])]],
+     {"x": [1.0, 0.0, -0.0, -0.0, 0.0, -1.0], "v": [3, 1, 2, 4, 5, 0]}, True),
 ]
 
 

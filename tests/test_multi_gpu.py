@@ -149,6 +149,15 @@ class NumpyJoinKernels(object):
     def order_by(self, key):
         return torch.from_numpy(np.argsort(key.numpy(), kind="stable"))
 
+    def sort_perm(self, keys, descending):
+        ranks = []
+        for (t, _), d in zip(keys, descending):
+            r = np.unique(t.numpy(), return_inverse=True)[1].astype(np.int64)
+            ranks.append(-r if d else r)
+        if not len(ranks[0]):
+            return torch.zeros(0, dtype=torch.int64)
+        return torch.from_numpy(np.lexsort(ranks[::-1]).astype(np.int64))   # lexsort is stable, last key = primary
+
     def scatter(self, col, idx, dst):
         dst.numpy()[idx.numpy()] = col[0].numpy()
 
@@ -322,3 +331,84 @@ def test_sharded_hash_join_null_keys_and_payload_world2(ref, strategy):
         p.join(timeout=60)
         assert p.exitcode == 0
     check_null_join_against_oracle(ref, got)
+
+
+def _sort_table(n=30011):
+    rng = np.random.default_rng(11)
+    return {"k": rng.integers(-50, 50, n), "x": np.round(rng.standard_normal(n), 1), "id": np.arange(n, dtype=np.int64),
+            "v": rng.integers(0, 10**9, n)}
+
+
+SORT_CASES = [([("k", 2)], [False]), ([("k", 2)], [True]), ([("x", 5), ("k", 2)], [True, False]),
+              ([("k", 2), ("x", 5)], [False, True]), ([("v", 2)], [False])]
+
+
+def _sort_worker(rank, world, port, out, skew, use_cuda=False):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if use_cuda:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from supersonic_b200.distributed import ShardedSort
+        if use_cuda:
+            from supersonic_b200 import capi
+            from supersonic_b200.distributed import CudaJoinKernels
+            kern = CudaJoinKernels(capi.Context(rank))
+        else:
+            kern = NumpyJoinKernels()
+        place = (lambda x: x.cuda()) if use_cuda else (lambda x: x)
+        t = _sort_table()
+        n = len(t["k"])
+        if skew:   # rank 0 holds nothing, the last rank holds most rows
+            cuts = [0, 0] + [n // 7 * i for i in range(1, world - 1)] + [n]
+            b, e = cuts[rank], cuts[rank + 1]
+        else:
+            b, e = shard_rows(n, rank, world, align=1)
+        col = lambda name, dt: (place(torch.from_numpy(np.ascontiguousarray(t[name][b:e]))), dt)   # noqa: E731
+        res = []
+        for keys, desc in SORT_CASES:
+            ks, cs = ShardedSort(kern).run([col(nm, dt) for nm, dt in keys], desc, [col("id", 2), col("v", 2)])
+            res.append(([c.cpu().numpy() for c, _ in ks], [c.cpu().numpy() for c, _ in cs]))
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,skew", [(2, False), (3, True)])
+def test_sharded_sort_matches_oracle(ref, world, skew):
+    """The concatenation of the ranks' ranges is the reference's Sort of the whole table; equal keys keep input
+    order, which the plan pins by ordering on the row id last."""
+    check_sharded_sort_against_oracle(ref, world, skew, False)
+
+
+def check_sharded_sort_against_oracle(ref, world, skew, use_cuda):
+    from supersonic_b200 import ssplan as sp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sort_worker, args=(r, world, port, out, skew, use_cuda)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    t = _sort_table()
+    table = [sp.Column("k", sp.INT64, t["k"]), sp.Column("x", sp.DOUBLE, t["x"]), sp.Column("id", sp.INT64, t["id"]),
+             sp.Column("v", sp.INT64, t["v"])]
+    for ci, (keys, desc) in enumerate(SORT_CASES):
+        order = " ".join("(%s %s)" % (nm, "DESC" if d else "ASC") for (nm, _), d in zip(keys, desc)) + " (id ASC)"
+        want = ref.run("(sort (order %s) (all) (scan 0))" % order, [table])
+        assert want.code == 0, want.error
+        ids = np.concatenate([got[r][ci][1][0] for r in range(world)])
+        vs = np.concatenate([got[r][ci][1][1] for r in range(world)])
+        assert np.array_equal(ids, want.column("id")) and np.array_equal(vs, want.column("v"))
+        for j in range(len(keys)):
+            kj = np.concatenate([got[r][ci][0][j] for r in range(world)])
+            assert np.array_equal(kj, want.column(keys[j][0]))
+        if not skew and keys[0][0] == "v":   # distinct keys: the ranges are balanced within a sampling error
+            sizes = [len(got[r][ci][1][0]) for r in range(world)]
+            assert max(sizes) < 1.2 * len(ids) / world

@@ -1,4 +1,4 @@
-"""The sharded hash join on real GPUs: two ranks over NCCL, CudaJoinKernels (every data-path
+"""The sharded hash join and sort on real GPUs: two ranks over NCCL, CudaJoinKernels (every data-path
 step a kernel of libssb200.so), checked in order against the oracle's HashJoin over the whole
 tables. Needs two B200s (`gpurun --gpus 2`); skipped on a single-GPU box."""
 import os
@@ -107,3 +107,12 @@ def test_sharded_hash_join_null_keys_and_payload_two_gpus(ref, strategy):
         p.join(timeout=120)
         assert p.exitcode == 0
     check_null_join_against_oracle(ref, got)
+
+
+@pytest.mark.parametrize("skew", [False, True])
+def test_sharded_sort_two_gpus_matches_oracle(ref, skew):
+    """Sample sort over NCCL with the library's sort and gather kernels, against the oracle's Sort of the whole table."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from test_multi_gpu import check_sharded_sort_against_oracle
+    check_sharded_sort_against_oracle(ref, 2, skew, True)

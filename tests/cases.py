@@ -171,6 +171,15 @@ GOLDEN = [
     ("sort_two_keys", "(sort (order (a ASC) (b DESC)) (named b a) (scan 0))",
      [[col("a", sp.INT64, [2, 1, 2, 1]), col("b", sp.DOUBLE, [0.5, -1.0, 7.0, 3.0])]],
      {"b": [3.0, -1.0, 7.0, 0.5], "a": [1, 1, 2, 2]}, True),
+    # ... but they are two hash keys: the row hash (hash of the bit image) tells them apart before == is asked
+    ("group_signed_zero_keys", "(group (named x) (aggs (SUM v s) (COUNT \"\" c)) (scan 0))",
+     [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0]), col("v", sp.INT64, [0, 1, 2, 3, 4])]],
+     {"x": [0.0, -0.0, 1.0], "s": [4, 4, 2], "c": [2, 2, 1]}, True),
+    ("join_signed_zero_keys",
+     "(hash_join INNER (named x) (named y) (multi (0 (named v)) (1 (named w))) UNIQUE (scan 0) (scan 1))",
+     [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0]), col("v", sp.INT64, [0, 1, 2, 3, 4])],
+      [col("y", sp.DOUBLE, [-0.0, 2.0]), col("w", sp.INT64, [7, 8])]],
+     {"v": [1, 3], "w": [7, 7]}, True),
     # -0.0 and +0.0 are one key value (sort.cc:151 compares with operator<): the second key decides among them
     ("sort_signed_zero", "(sort (order (x DESC) (v ASC)) (all) (scan 0))",
      [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0, -1.0]), col("v", sp.INT32, [5, 4, 3, 2, 1, 0])]],

@@ -174,6 +174,24 @@ int32_t ssb_program_output_nullable(const ssb_program* prog, int32_t j);
 int32_t ssb_program_bytes_per_input_row(const ssb_program* prog);
 int32_t ssb_program_bytes_per_output_row(const ssb_program* prog);
 
+/* The same validation and planning without a device: type-checks the DAG as the bound expression
+ * tree does (expression/infrastructure/bound_expression_tree.h, the nullability rules of
+ * expression/templated/bound_expression_factory.h) and lays the kernel's shared memory out for tiles of
+ * `tile` rows within `smem_budget` bytes per CTA. For planners and for CPU-side tests; needs no context.
+ * Returns 0 or an SSB_ERROR_* code with a message in err (err_len bytes, may be NULL). */
+typedef struct {
+  int32_t tile, stages, smem_bytes;      /* rows per tile, TMA stages in flight, bytes of shared memory per CTA */
+  int32_t n_insn, n_tmp;                 /* instructions of the accumulator machine, temporaries */
+  int32_t bytes_per_input_row, bytes_per_output_row;
+  int32_t has_signaling;                 /* some node can raise ERROR_EVALUATION_ERROR */
+  int32_t n_outputs;
+  int32_t out_types[16], out_nullable[16];
+} ssb_plan_info;
+int ssb_program_plan(const ssb_expr_node* nodes, int32_t n_nodes,
+                     int32_t n_inputs, const int32_t* input_types, const int32_t* input_nullable,
+                     const int32_t* outputs, int32_t n_outputs, int32_t predicate,
+                     int32_t tile, uint32_t smem_budget, ssb_plan_info* info, char* err, int32_t err_len);
+
 /* Runs the program over `rows` rows. outputs[j].data must hold `rows` elements (Filter
  * may keep every row); outputs[j].nulls must be non-NULL (ceil(rows/32)+1 words) when
  * ssb_program_output_nullable(j). d_out_rows (device int64, may be NULL without a

@@ -18,6 +18,8 @@ OP_INPUT, OP_CONST, OP_CAST = 1, 2, 3
 OP_ADD, OP_SUB, OP_MUL, OP_DIV = 11, 12, 13, 14
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = 20, 21, 22, 23, 24, 25
 OP_AND, OP_OR, OP_NOT = 30, 31, 34
+OP_NEGATE, OP_MOD, OP_IS_NULL, OP_IF_NULL, OP_IF, OP_NULLING_IF = 10, 15, 50, 51, 52, 53
+NODE_NULL, NODE_ZERO_NULLS, NODE_ZERO_FAILS = 1, 2, 4
 AGG_SUM, AGG_MIN, AGG_MAX, AGG_COUNT = 0, 1, 2, 3
 
 
@@ -111,6 +113,8 @@ def load():
         "ssb_gather": (C.c_int, [P, C.POINTER(Column), P, I64, C.POINTER(Column)]),
         "ssb_scatter": (C.c_int, [P, C.POINTER(Column), P, I64, C.POINTER(Column)]),
         "ssb_sort_permutation": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I32), I64, P]),
+        "ssb_program_plan": (C.c_int, [P, I32, I32, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32), I32, I32, I32, C.c_uint32,
+                                       P, C.c_char_p, I32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -207,6 +211,35 @@ def node(op, out_type, args=(), flags=0, i64=None, f64=None, b=None):
     if b is not None:
         n.imm.b = 1 if b else 0
     return n
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("tile", C.c_int32), ("stages", C.c_int32), ("smem_bytes", C.c_int32), ("n_insn", C.c_int32),
+                ("n_tmp", C.c_int32), ("bytes_per_input_row", C.c_int32), ("bytes_per_output_row", C.c_int32),
+                ("has_signaling", C.c_int32), ("n_outputs", C.c_int32), ("out_types", C.c_int32 * 16),
+                ("out_nullable", C.c_int32 * 16)]
+
+
+class PlanError(Exception):
+    def __init__(self, code, message):
+        Exception.__init__(self, "%d: %s" % (code, message))
+        self.code, self.message = code, message
+
+
+def plan(nodes, input_types, input_nullable, outputs, predicate=-1, tile=768, smem_budget=100 * 1024):
+    """ssb_program_plan: validation and kernel planning of an expression DAG; needs no device."""
+    lib = load()
+    arr = (ExprNode * max(1, len(nodes)))(*nodes)
+    it = (C.c_int32 * max(1, len(input_types)))(*input_types)
+    inn = (C.c_int32 * max(1, len(input_types)))(*input_nullable)
+    outs = (C.c_int32 * max(1, len(outputs)))(*outputs)
+    info = PlanInfo()
+    err = C.create_string_buffer(256)
+    rc = lib.ssb_program_plan(arr, len(nodes), len(input_types), it, inn, outs, len(outputs), predicate, tile,
+                              smem_budget, C.byref(info), err, 256)
+    if rc != 0:
+        raise PlanError(rc, err.value.decode())
+    return info
 
 
 class Program(object):

@@ -691,3 +691,42 @@ int compile_program(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_input
 }
 
 }  // namespace ssb
+
+extern "C" int ssb_program_plan(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs, const int32_t* input_types,
+                                const int32_t* input_nullable, const int32_t* outputs, int32_t n_outputs, int32_t predicate,
+                                int32_t tile, uint32_t smem_budget, ssb_plan_info* info, char* err, int32_t err_len) {
+  std::string message;
+  int rc = 0;
+  ssb::Program prog;
+  if (nodes == NULL || info == NULL || (n_inputs > 0 && (input_types == NULL || input_nullable == NULL)) ||
+      (n_outputs > 0 && outputs == NULL)) {
+    rc = SSB_ERROR_INVALID_ARGUMENT_VALUE;
+    message = "null argument";
+  } else if (tile <= 0 || tile % 128 != 0) {
+    rc = SSB_ERROR_INVALID_ARGUMENT_VALUE;
+    message = "tile must be a positive multiple of 128 rows";
+  } else {
+    rc = ssb::compile_program(nodes, n_nodes, n_inputs, input_types, input_nullable, outputs, n_outputs, predicate, tile,
+                              smem_budget, 232448u /* 227 KB: the most one CTA can opt into on sm_100a */, &prog, &message);
+  }
+  if (err != NULL && err_len > 0) {
+    strncpy(err, message.c_str(), static_cast<size_t>(err_len) - 1);
+    err[err_len - 1] = 0;
+  }
+  if (rc != 0) return rc;
+  memset(info, 0, sizeof(*info));
+  info->tile = prog.params.tile;
+  info->stages = prog.params.stages;
+  info->smem_bytes = static_cast<int32_t>(prog.smem_bytes);
+  info->n_insn = prog.params.n_insn;
+  info->n_tmp = prog.params.n_tmp;
+  info->bytes_per_input_row = prog.bytes_in_row;
+  info->bytes_per_output_row = prog.bytes_out_row;
+  info->has_signaling = prog.has_signaling ? 1 : 0;
+  info->n_outputs = static_cast<int32_t>(prog.out_types.size());
+  for (size_t j = 0; j < prog.out_types.size() && j < 16; ++j) {
+    info->out_types[j] = prog.out_types[j];
+    info->out_nullable[j] = prog.out_nullable[j];
+  }
+  return 0;
+}

@@ -15,6 +15,7 @@
 #include <thread>
 
 #include "internal.h"
+#include "narrow.h"
 
 namespace supersonic {
 
@@ -178,12 +179,8 @@ bool NarrowInt64Column(const int64* src, int32* dst, rowcount_t rows) {
     } else
 #endif
     {
-      for (rowcount_t i = begin; i < end; ++i) {
-        const int64 v = src[i];
-        const int32 n = static_cast<int32>(v);
-        dst[i] = n;
-        bad |= v ^ static_cast<int64>(n);
-      }
+      bad = narrow::Range(reinterpret_cast<const int64_t*>(src), reinterpret_cast<int32_t*>(dst),
+                          static_cast<size_t>(begin), static_cast<size_t>(end));
     }
     if (bad != 0) misfit.store(1, std::memory_order_relaxed);
   });

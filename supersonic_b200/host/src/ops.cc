@@ -1042,6 +1042,11 @@ class HashJoinCursor : public GpuCursor {
     // build side first (hash_join.cc:406-420), then the probe side
     PROPAGATE_ON_FAILURE(MaterializeOnDevice(rhs_.get(), &rhs_table_, &keep_r));
     PROPAGATE_ON_FAILURE(MaterializeOnDevice(lhs_.get(), &lhs_table_, &keep_l));
+    // hash_join.cc:713-726: the reference binds any join type and refuses the others at the first lookup,
+    // i.e. once the probe side has produced a row
+    if (join_type_ != INNER && join_type_ != LEFT_OUTER && lhs_table_.rows > 0) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "Unsupported join_type in hash_join: " + JoinType_Name(join_type_)));
+    }
     vector<ssb_column> rk, lk;
     for (size_t k = 0; k < rhs_keys_.size(); ++k) rk.push_back(rhs_table_.columns[rhs_keys_[k]].col);
     for (size_t k = 0; k < lhs_keys_.size(); ++k) lk.push_back(lhs_table_.columns[lhs_keys_[k]].col);
@@ -1350,10 +1355,18 @@ Operation* Sort(const SortOrder* sort_order, const SingleSourceProjector* result
 
 SortOrder::~SortOrder() { for (size_t i = 0; i < keys_.size(); ++i) delete keys_[i].first; }
 FailureOrVoid SortOrder::Bind(const TupleSchema& schema, vector<std::pair<int, ColumnOrder> >* keys) const {
+  // the keys form one projection (sort.cc:74-98, a CompoundSingleSourceProjector): a column named twice is
+  // a duplicate attribute of its result schema
+  vector<string> seen;
   for (size_t i = 0; i < keys_.size(); ++i) {
     FailureOrOwned<const BoundSingleSourceProjector> p = keys_[i].first->Bind(schema);
     PROPAGATE_ON_FAILURE(p);
     for (int c = 0; c < p->result_schema().attribute_count(); ++c) {
+      const string& name = p->result_schema().attribute(c).name();
+      if (std::find(seen.begin(), seen.end(), name) != seen.end()) {
+        THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + name + "' in result schema"));
+      }
+      seen.push_back(name);
       const DataType t = p->result_schema().attribute(c).type();
       if (t == STRING || t == BINARY) {
         THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length sort keys are not on the B200 hot path (SURVEY 8f)"));
@@ -1375,10 +1388,6 @@ HashJoinOperation::HashJoinOperation(JoinType join_type, const SingleSourceProje
 HashJoinOperation::~HashJoinOperation() {}
 
 FailureOrOwned<Cursor> HashJoinOperation::CreateCursor() const {
-  // hash_join.cc:713-726
-  if (join_type_ != INNER && join_type_ != LEFT_OUTER) {
-    THROW(new Exception(ERROR_NOT_IMPLEMENTED, "Join type " + JoinType_Name(join_type_) + " not implemented in hash join"));
-  }
   FailureOrOwned<Cursor> lhs = child_at(0)->CreateCursor();
   PROPAGATE_ON_FAILURE(lhs);
   FailureOrOwned<Cursor> rhs = child_at(1)->CreateCursor();

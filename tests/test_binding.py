@@ -121,3 +121,158 @@ def test_operation_schemas(ref, b200):
         if _key(a) != _key(b):
             bad.append((plan, _key(a), a.error, _key(b), b.error))
     assert not bad, bad
+
+
+MORE_PLANS = [
+    '(hash_join INNER (named i64) (named i64) (multi (0 (all)) (1 (all))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i64) (named i64) (multi (0 (all l.)) (1 (all r.))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (all l.)) (1 (all r.))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (named i32 ni32)) (1 (rename (i64 k) (b rb) (d rd) (dt rdt) (f32 rf) (u64 ru)))) NOT_UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i64) (named i64) (multi (0 (at 0 1)) (1 (at 2 3))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i64) (named i64) (multi (0 (at 0)) (1 (at 0))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i64) (named i64) (multi (0 (at 99)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i64) (named i64) (multi (0 (named i32)) (1 (at 99))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join RIGHT_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join FULL_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named u64) (named i64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(group (named ni32) (aggs (SUM ni64 s) (MIN nf64 m) (COUNT nb c) (FIRST nd f) (LAST ndt l)) (scan 0))',
+    '(group (named ni32 nb nd) (aggs (COUNT "" c)) (scan 0))',
+    '(group (all) (aggs (COUNT "" c)) (scan 0))',
+    '(group (at 0 1) (aggs (SUM f64 s)) (scan 0))',
+    '(group (rename (i32 k)) (aggs (SUM f64 s)) (scan 0))',
+    '(group (rename (i32 s)) (aggs (SUM f64 s)) (scan 0))',
+    '(group (named i32) (aggs (SUM f64 i64)) (scan 0))',
+    '(group (named i32) (aggs (MIN f32 s) (MAX nf32 t) (SUM f32 u) (SUM f32 v DOUBLE)) (scan 0))',
+    '(group (named i32) (aggs (SUM u32 s) (SUM u64 t) (SUM i32 u) (SUM nu32 v UINT64)) (scan 0))',
+    '(group (named i32) (aggs (MIN u32 s DOUBLE) (MAX i32 t FLOAT) (MIN f64 u FLOAT) (MAX f32 v INT32)) (scan 0))',
+    '(group (named i32) (aggs (FIRST i32 s INT64) (LAST f32 t DOUBLE)) (scan 0))',
+    '(group (named i32) (aggs (COUNT i32 c UINT32) (COUNT "" d UINT64) (COUNT nf64 e INT32)) (scan 0))',
+    '(group (named i32) (aggs (SUM b s INT32)) (scan 0))',
+    '(group (named i32) (aggs (MIN dt s) (MAX d t) (MIN b u)) (scan 0))',
+    '(group (named i32) (aggs (SUM d s INT32) (SUM dt t INT64)) (scan 0))',
+    '(group (named i32) (aggs (MIN d s INT32) (MIN dt t INT64) (MIN i32 u DATE) (MIN i64 v DATETIME)) (scan 0))',
+    '(scalar_agg (aggs (SUM ni64 s) (MIN nf64 m) (COUNT nb c) (COUNT "" n) (FIRST b f) (LAST d l)) (scan 0))',
+    '(scalar_agg (aggs (SUM f64 s) (SUM f64 s)) (scan 0))',
+    '(scalar_agg (aggs (SUM nope s)) (scan 0))',
+    '(sort (order (i64 ASC)) (rename (i64 k) (f64 v)) (scan 0))',
+    '(sort (order (i64 ASC)) (at 0 0) (scan 0))',
+    '(sort (order (i64 ASC)) (named i32 i32) (scan 0))',
+    '(sort (order (ni64 DESC) (nb ASC) (nd DESC)) (all s.) (scan 0))',
+    '(project (named nope) (scan 0))',
+    '(project (at 99) (scan 0))',
+    '(project (at 0) (project (at 1) (scan 0)))',
+    '(project (rename (i32 a) (i32 b)) (scan 0))',
+    '(filter (col nb) (rename (i32 a) (i64 a)) (scan 0))',
+    '(filter (and (col b) (col nb)) (at 0 1 2) (scan 0))',
+    '(filter (is_null (col ni32)) (named ni32) (scan 0))',
+    '(filter (col b) (all) (filter (col nb) (named b i32) (scan 0)))',
+    '(compute (compound (as a (col i32)) (as b (plus (col i32) (col ni32)))) (filter (col b) (all) (scan 0)))',
+    '(compute (plus (col a) (col b)) (compute (compound (as a (col i32)) (as b (col nf64))) (scan 0)))',
+    '(compute (col nope) (compute (as a (col i32)) (scan 0)))',
+    '(compute (col i32) (compute (as a (col i32)) (scan 0)))',
+    '(group (named k) (aggs (SUM v s)) (hash_join INNER (named i64) (named i64) (multi (0 (rename (i32 k))) (1 (rename (f64 v)))) UNIQUE (scan 0) (scan 0)))',
+    '(scalar_agg (aggs (COUNT "" c)) (hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (f64 v)))) NOT_UNIQUE (scan 0) (scan 0)))',
+    '(sort (order (v DESC)) (all) (hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (f64 v)))) NOT_UNIQUE (scan 0) (scan 0)))',
+    '(filter (is_null (col v)) (all) (hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (f64 v)))) NOT_UNIQUE (scan 0) (scan 0)))',
+    '(group (named i32) (aggs (SUM s t)) (group (named i32 i64) (aggs (SUM f64 s)) (scan 0)))',
+    '(group (named i32) (aggs (SUM c t)) (group (named i32 i64) (aggs (COUNT "" c)) (scan 0)))',
+    '(sort (order (c DESC) (i32 ASC)) (all) (group (named i32) (aggs (COUNT "" c)) (scan 0)))',
+    '(compute (divide_signaling (col s) (col c)) (group (named i32) (aggs (SUM f64 s) (COUNT "" c)) (scan 0)))',
+    '(compute (divide_nulling (col s) (col c)) (scalar_agg (aggs (SUM i64 s) (COUNT "" c)) (scan 0)))',
+    '(bound_compute (compound (as a (col i32)) (as a (col i64))) (bound_scan 0))',
+    '(bound_filter (col i32) (all) (bound_scan 0))',
+    '(bound_filter (col nb) (named nope) (bound_scan 0))',
+    '(bound_group (named i32) (aggs (SUM b s)) (bound_scan 0))',
+    '(bound_group (named i32) (aggs (SUM f64 i32)) (bound_scan 0))',
+    '(bound_scalar_agg (aggs (SUM nope s)) (bound_scan 0))',
+    '(bound_sort (order (i64 ASC) (i64 DESC)) (all) (bound_scan 0))',
+    '(bound_project (rename (i32 x) (i64 x)) (bound_scan 0))',
+    '(bound_sort (order (c DESC)) (all) (bound_group (named i32) (aggs (COUNT "" c)) (bound_filter (col b) (all) (bound_compute (compound (col i32) (col b)) (bound_scan 0)))))',
+    # any join type binds (hash_join.cc:713-726 refuses RIGHT / FULL at the first lookup, not at bind time)
+    '(hash_join RIGHT_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join FULL_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (ni32 r)))) NOT_UNIQUE (scan 0) (scan 0))',
+    '(group (named i32) (aggs (FIRST f64 s) (LAST ni64 m)) (scan 0))',
+    '(group (named i32) (aggs (FIRST b s) (LAST d m) (FIRST dt x)) (scan 0))',
+    '(group (named i32) (aggs (FIRST f64 s INT64)) (scan 0))',
+    '(group (named i32 i32) (aggs (SUM f64 s)) (scan 0))',
+    '(group (named i32) (aggs (SUM f64 s) (SUM f64 s)) (scan 0))',
+    '(group (named f64) (aggs (MIN f32 s) (MAX f32 t DOUBLE)) (scan 0))',
+    '(group (named b) (aggs (COUNT b c)) (scan 0))',
+    '(group (named d dt) (aggs (MIN d a) (MAX dt b2)) (scan 0))',
+    '(group (named) (aggs (SUM f64 s)) (scan 0))',
+    '(group (named i32) (aggs) (scan 0))',
+    '(group (named i32) (aggs (SUM i32 s UINT64)) (scan 0))',
+    '(group (named i32) (aggs (SUM u32 s INT32)) (scan 0))',
+    '(group (named i32) (aggs (SUM i64 s DOUBLE)) (scan 0))',
+    '(group (named i32) (aggs (SUM f64 s INT64)) (scan 0))',
+    '(group (named i32) (aggs (MIN i64 s INT32)) (scan 0))',
+    '(group (named i32) (aggs (MIN i32 s DOUBLE)) (scan 0))',
+    '(group (named i32) (aggs (COUNT "" c INT32)) (scan 0))',
+    '(group (named i32) (aggs (COUNT "" c INT64)) (scan 0))',
+    '(group (named i32) (aggs (COUNT "" c BOOL)) (scan 0))',
+    '(scalar_agg (aggs (MIN b s) (MAX d c) (FIRST ni32 f)) (scan 0))',
+    '(scalar_agg (aggs) (scan 0))',
+    '(scalar_agg (aggs (SUM dt s)) (scan 0))',
+    '(hash_join INNER (named i64 i32) (named i64 i32) (multi (0 (named f64)) (1 (rename (f64 rf)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named f64) (named f64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i32) (named u32) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named ni64) (named i64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join LEFT_OUTER (named ni64) (named ni64) (multi (0 (all)) (1 (rename (i32 r) (ni32 rn) (b rb)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named nope) (named i64) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named i64) (named i64) (multi (0 (named nope)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named d) (named d) (multi (0 (named i32)) (1 (rename (i32 r)))) NOT_UNIQUE (scan 0) (scan 0))',
+    '(hash_join INNER (named b) (named b) (multi (0 (named i32)) (1 (rename (i32 r)))) NOT_UNIQUE (scan 0) (scan 0))',
+    '(sort (order (i64 ASC) (i64 DESC)) (all) (scan 0))',
+    '(sort (order (b ASC) (d DESC) (dt ASC) (f32 DESC) (u64 ASC)) (all) (scan 0))',
+    '(sort (order (ni64 ASC)) (named ni64 nf64) (scan 0))',
+    '(sort (order (i64 ASC)) (named nope) (scan 0))',
+    '(sort (order) (all) (scan 0))',
+    '(project (named i32 i32) (scan 0))',
+    '(project (rename (i32 x) (i64 x)) (scan 0))',
+    '(project (all) (project (named i32 nf64) (scan 0)))',
+    '(project (all p.) (scan 0))',
+    '(filter (i32 1) (all) (scan 0))',
+    '(filter (bool true) (all) (scan 0))',
+    '(filter (null BOOL) (all) (scan 0))',
+    '(filter (col b) (named i32 i32) (scan 0))',
+    '(filter (less (col nope) (i64 1)) (all) (scan 0))',
+    '(compute (compound (col i32) (col i32)) (scan 0))',
+    '(compute (compound (as a (col i32)) (as a (col i64))) (scan 0))',
+    '(compute (col i32) (filter (col b) (named i32 i64) (scan 0)))',
+    '(group (named e) (aggs (SUM i64 s)) (compute (compound (as e (plus (col i32) (i32 1))) (col i64)) (scan 0)))',
+    '(group (named i32) (aggs (SUM e s)) (filter (col b) (named i32 e) (compute (compound (col i32) (col b) (as e (multiply (col f64) (col f64)))) (scan 0))))',
+    '(sort (order (s DESC)) (all) (group (named i32) (aggs (SUM f64 s)) (scan 0)))',
+    '(hash_join INNER (named i32) (named k) (multi (0 (named i64)) (1 (named s))) UNIQUE (scan 0) (group (named k) (aggs (SUM f64 s)) (project (rename (i32 k) (f64 f64)) (scan 0))))',
+    "(bound_scan 0)', '(bound_compute (col i32) (bound_scan 0))",
+    '(bound_filter (less (col i64) (i64 1)) (named i32) (bound_scan 0))',
+    '(bound_group (named i32) (aggs (SUM f64 s) (FIRST ni32 f)) (bound_scan 0))',
+    '(bound_scalar_agg (aggs (SUM f64 s)) (bound_scan 0))',
+    '(bound_sort (order (i64 DESC)) (named i32) (bound_scan 0))',
+    '(bound_project (named nope) (bound_scan 0))',
+    '(bound_group (named nope) (aggs (SUM f64 s)) (bound_scan 0))',
+    '(bound_sort (order (nope DESC)) (all) (bound_scan 0))',
+]
+
+
+def test_more_operation_schemas(ref, b200):
+    """FIRST / LAST and result-type overrides of the aggregates, key and payload schemas of the join, duplicate
+    and missing sort keys, nested plans and the cursor-level (bound_*) factories."""
+    bad = []
+    for plan in MORE_PLANS:
+        a = ref.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+        b = b200.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+        if _key(a) != _key(b):
+            bad.append((plan, _key(a), a.error, _key(b), b.error))
+    assert not bad, bad
+
+
+def test_join_key_schemas_are_checked_at_bind_time(ref, b200):
+    """Deliberate divergence: the reference only DCHECKs that the two key schemas agree (hash_join.cc:383-387,
+    490, 710) and a release build then compares keys of different types or counts bytewise; the mirror refuses such
+    plans with ERROR_ATTRIBUTE_TYPE_MISMATCH. Integer keys of different width or signedness stay legal."""
+    for plan in ["(hash_join INNER (named i64 i32) (named i64) (multi (0 (named f64)) (1 (rename (f64 rf)))) UNIQUE (scan 0) (scan 0))",
+                 "(hash_join INNER (named f64) (named f32) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))"]:
+        assert ref.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == 0
+        assert b200.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == 402
+    ok = "(hash_join INNER (named i32) (named u32) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))"
+    assert ref.run(ok, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == b200.run(ok, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == 0

@@ -134,6 +134,17 @@ def test_signaling_division_fails(ref, b200):
                  b200.run("(compute (cpp_divide_signaling (col a) (col b)) (scan 0))", [ok]))
 
 
+@pytest.mark.parametrize("jt", ["RIGHT_OUTER", "FULL_OUTER"])
+def test_unsupported_join_types_fail_at_the_first_lookup(ref, b200, jt):
+    """hash_join.cc:713-726: any join type binds; the other two are refused once the probe side has produced a row."""
+    plan = "(hash_join %s (named k) (named k) (multi (0 (named v)) (1 (rename (v w)))) UNIQUE (scan 0) (scan 1))" % jt
+    t = lambda n: [sp.Column("k", sp.INT64, np.arange(n)), sp.Column("v", sp.INT64, np.arange(n))]   # noqa: E731
+    for nl, nr in ((3, 3), (3, 0)):
+        a, b = ref.run(plan, [t(nl), t(nr)]), b200.run(plan, [t(nl), t(nr)])
+        assert a.code == 103 and b.code == 103, (nl, nr, a.code, b.code, b.error)
+        assert jt in b.error
+
+
 @pytest.mark.parametrize("n,sel", [(10_000_000, 2**19), (1_000_003, 2**10), (2049, 2**20), (1024, 0)])
 def test_filter_project_c1(ref, b200, n, sel):
     """BASELINE config 1: Compute(a*b+c) then Filter(d<K) over 4 x INT64, bit-exact, in order."""

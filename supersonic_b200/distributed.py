@@ -287,13 +287,23 @@ class CudaJoinKernels(object):
     def finish(self):
         self.ctx.sync()
 
-    def sort_perm(self, keys, descending):
-        """Stable sort permutation by several key columns (first = most significant)."""
+    def sort_perm(self, keys, descending, key_nulls=None):
+        """Stable sort permutation by several key columns (first = most significant); key_nulls: per key
+        a uint8 tensor (1 = NULL) or None -- NULLs first for ASCENDING, last for DESCENDING."""
         n = keys[0][0].numel()
         perm = self.empty(n, self.capi.INT64)
         if n:
             desc = (C.c_int32 * len(keys))(*[1 if d else 0 for d in descending])
-            self.ctx.check(self.ctx.lib.ssb_sort_permutation(self.ctx.h, len(keys), self._cols(keys), desc, n, perm.data_ptr()))
+            cols = self._cols(keys)
+            bitmaps = []    # keep the packed bitmaps alive until the sort has run
+            for i, flags in enumerate(key_nulls or []):
+                if flags is None:
+                    continue
+                words = self.torch.zeros(n // 32 + 2, dtype=self.torch.int32, device=self.device)
+                self.ctx.check(self.ctx.lib.ssb_nulls_pack(self.ctx.h, flags.data_ptr(), n, words.data_ptr()))
+                cols[i].nulls = words.data_ptr()
+                bitmaps.append(words)
+            self.ctx.check(self.ctx.lib.ssb_sort_permutation(self.ctx.h, len(keys), cols, desc, n, perm.data_ptr()))
         return perm
 
     def order_by(self, key):
@@ -503,23 +513,30 @@ class ShardedSort(object):
     order; rows with equal keys keep their global input order (all rows with one value of the most
     significant key meet on one rank, chunks arrive in rank order, and both sorts are stable), so
     the concatenation in rank order is the reference's output (cursor/core/sort.cc:150-322) whenever
-    its order is total. NOT NULL key columns; the most significant key must be a signed or
-    floating type (unsigned columns travel as their signed bit image here)."""
+    its order is total. Key and payload columns may carry is_null bytes (the same columns on every
+    rank); the most significant key must be a signed or floating type (unsigned columns travel as
+    their signed bit image here)."""
 
     SAMPLES_PER_RANK = 64
 
     def __init__(self, kernels, group=None):
         self.k, self.group = kernels, group
 
-    def run(self, keys, descending, cols):
+    def run(self, keys, descending, cols, key_nulls=None, col_nulls=None):
         """keys: [(tensor, SSB dtype)] most significant first; descending: [bool] per key;
-        cols: payload columns. Returns (sorted key columns, sorted payload columns) of this rank."""
+        cols: payload columns; key_nulls / col_nulls: per column a uint8 tensor (1 = NULL) or None.
+        Returns (sorted key columns, sorted payload columns) of this rank, followed by the two lists
+        of is_null bytes when either was given. NULL keys sort first for ASCENDING and last for
+        DESCENDING (sort.cc:174-238), so the rows with a NULL leading key all go to the first / last rank."""
+        with_nulls = key_nulls is not None or col_nulls is not None
+        key_nulls = list(key_nulls) if key_nulls is not None else [None] * len(keys)
+        col_nulls = list(col_nulls) if col_nulls is not None else [None] * len(cols)
         with self.k.scope():
-            out = self._run(keys, descending, cols)
+            out = self._run(keys, descending, cols, key_nulls, col_nulls)
         self.k.finish()
-        return out
+        return out if with_nulls else out[:2]
 
-    def _run(self, keys, descending, cols):
+    def _run(self, keys, descending, cols, key_nulls, col_nulls):
         import torch
         import torch.distributed as dist
         k, g = self.k, self.group
@@ -527,39 +544,52 @@ class ShardedSort(object):
         if keys[0][1] in (3, 8):   # UINT64, UINT32
             raise NotImplementedError("ShardedSort: the most significant key must be a signed or floating column")
         device = keys[0][0].device
+        BYTE = 6   # is_null bytes travel as BOOL columns
+
+        def permute(perm, keys, cols, key_nulls, col_nulls):
+            return ([(k.gather(c, perm), c[1]) for c in keys], [(k.gather(c, perm), c[1]) for c in cols],
+                    [None if f is None else k.gather((f, BYTE), perm) for f in key_nulls],
+                    [None if f is None else k.gather((f, BYTE), perm) for f in col_nulls])
+
         # 1. local stable sort
-        perm = k.sort_perm(keys, descending)
-        keys = [(k.gather(c, perm), c[1]) for c in keys]
-        cols = [(k.gather(c, perm), c[1]) for c in cols]
-        first = keys[0][0]
-        n = first.numel()
+        perm = k.sort_perm(keys, descending, key_nulls)
+        keys, cols, key_nulls, col_nulls = permute(perm, keys, cols, key_nulls, col_nulls)
+        n = keys[0][0].numel()
+        n_null = int(key_nulls[0].sum().item()) if key_nulls[0] is not None and n else 0
+        # the rows whose leading key is not NULL: behind the NULLs (ASC) or in front of them (DESC)
+        lo, hi = (0, n - n_null) if descending[0] else (n_null, n)
+        first = keys[0][0][lo:hi]
+        nn = hi - lo
         # 2. splitters from an all-gathered regular sample of the most significant key
         s = self.SAMPLES_PER_RANK
-        if n:
-            pos = (torch.arange(s, device=device, dtype=torch.int64) * n) // s
+        if nn:
+            pos = lo + (torch.arange(s, device=device, dtype=torch.int64) * nn) // s
             sample = k.gather(keys[0], pos)
         else:
             sample = first[:0]
         gathered = torch.cat(allgather_ragged(sample, g))
         gathered, _ = torch.sort(gathered)
         m = gathered.numel()
-        if m == 0:
-            return keys, cols
-        splitters = gathered[[min(m - 1, (m * (r + 1)) // world) for r in range(world - 1)]] if world > 1 else gathered[:0]
-        # 3. rows per destination: in ascending terms dest(key) = number of splitters <= key
-        asc = first if not descending[0] else first.flip(0)
-        bounds = torch.searchsorted(asc.contiguous(), splitters, right=False).tolist() if world > 1 else []
-        # keys equal to a splitter go right of it: searchsorted(..., right=False) on the rows gives the first
-        # row >= splitter, i.e. rows < splitter stay left
-        edges = [0] + [int(b) for b in bounds] + [n]
+        if m and world > 1:
+            splitters = gathered[[min(m - 1, (m * (r + 1)) // world) for r in range(world - 1)]]
+            # 3. rows per destination: keys below the first splitter stay on rank 0, keys equal to a splitter go right of it
+            asc = first if not descending[0] else first.flip(0)
+            bounds = torch.searchsorted(asc.contiguous(), splitters, right=False).tolist()
+        else:
+            bounds = [0] * (world - 1)     # no row anywhere has a leading key that is not NULL
+        edges = [0] + [int(b) for b in bounds] + [nn]
         counts = [edges[i + 1] - edges[i] for i in range(world)]
         if descending[0]:
             counts = counts[::-1]           # the local data is laid out largest first = destination 0 first
+            counts[-1] += n_null            # ... and ends with the NULLs, which the last rank collects
+        else:
+            counts[0] += n_null             # NULLs come first and stay on the first rank
         recv = _exchange_counts(counts, device, g)
         # 4. exchange, 5. sort what arrived (chunks are sorted already; the stable sort merges them)
-        keys = [(_exchange(c[0], counts, recv, g), c[1]) for c in keys]
-        cols = [(_exchange(c[0], counts, recv, g), c[1]) for c in cols]
-        perm = k.sort_perm(keys, descending)
-        keys = [(k.gather(c, perm), c[1]) for c in keys]
-        cols = [(k.gather(c, perm), c[1]) for c in cols]
-        return keys, cols
+        ex = lambda t: _exchange(t, counts, recv, g)   # noqa: E731
+        keys = [(ex(c[0]), c[1]) for c in keys]
+        cols = [(ex(c[0]), c[1]) for c in cols]
+        key_nulls = [None if f is None else ex(f) for f in key_nulls]
+        col_nulls = [None if f is None else ex(f) for f in col_nulls]
+        perm = k.sort_perm(keys, descending, key_nulls)
+        return permute(perm, keys, cols, key_nulls, col_nulls)

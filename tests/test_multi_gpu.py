@@ -149,11 +149,16 @@ class NumpyJoinKernels(object):
     def order_by(self, key):
         return torch.from_numpy(np.argsort(key.numpy(), kind="stable"))
 
-    def sort_perm(self, keys, descending):
+    def sort_perm(self, keys, descending, key_nulls=None):
         ranks = []
-        for (t, _), d in zip(keys, descending):
-            r = np.unique(t.numpy(), return_inverse=True)[1].astype(np.int64)
-            ranks.append(-r if d else r)
+        for i, ((t, _), d) in enumerate(zip(keys, descending)):
+            v = t.numpy()
+            isn = key_nulls[i].numpy().astype(bool) if key_nulls and key_nulls[i] is not None else np.zeros(len(v), dtype=bool)
+            r = np.unique(np.where(isn, v[~isn][0] if (~isn).any() else 0, v), return_inverse=True)[1].astype(np.int64)
+            r = -r if d else r
+            if len(r):
+                r[isn] = (r.max() + 1) if d else (r.min() - 1)      # NULLs last for DESC, first for ASC
+            ranks.append(r)
         if not len(ranks[0]):
             return torch.zeros(0, dtype=torch.int64)
         return torch.from_numpy(np.lexsort(ranks[::-1]).astype(np.int64))   # lexsort is stable, last key = primary
@@ -423,3 +428,86 @@ def check_sharded_sort_against_oracle(ref, world, skew, use_cuda, flavour=""):
         if not skew and not flavour and keys[0][0] == "v":   # distinct keys: the ranges are balanced within a sampling error
             sizes = [len(got[r][ci][1][0]) for r in range(world)]
             assert max(sizes) < 1.2 * len(ids) / world
+
+
+def _null_sort_table(n=20011):
+    rng = np.random.default_rng(23)
+    return {"k": rng.integers(-20, 20, n), "k_null": (rng.random(n) < 0.15).astype(np.uint8),
+            "j": rng.integers(0, 5, n), "j_null": (rng.random(n) < 0.3).astype(np.uint8),
+            "id": np.arange(n, dtype=np.int64), "w": rng.random(n), "w_null": (rng.random(n) < 0.2).astype(np.uint8)}
+
+
+NULL_SORT_CASES = [[False, False], [True, False], [False, True], [True, True]]
+
+
+def _null_sort_worker(rank, world, port, out, use_cuda=False, all_null=False):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if use_cuda:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from supersonic_b200.distributed import ShardedSort
+        if use_cuda:
+            from supersonic_b200 import capi
+            from supersonic_b200.distributed import CudaJoinKernels
+            kern = CudaJoinKernels(capi.Context(rank))
+        else:
+            kern = NumpyJoinKernels()
+        place = (lambda x: x.cuda()) if use_cuda else (lambda x: x)
+        t = _null_sort_table()
+        if all_null:
+            t["k_null"][:] = 1
+        b, e = shard_rows(len(t["k"]), rank, world, align=1)
+        ten = lambda name: place(torch.from_numpy(np.ascontiguousarray(t[name][b:e])))   # noqa: E731
+        res = []
+        for desc in NULL_SORT_CASES:
+            ks, cs, kn, cn = ShardedSort(kern).run([(ten("k"), 2), (ten("j"), 2)], desc, [(ten("id"), 2), (ten("w"), 5)],
+                                                   key_nulls=[ten("k_null"), ten("j_null")], col_nulls=[None, ten("w_null")])
+            res.append(([c.cpu().numpy() for c, _ in ks], [c.cpu().numpy() for c, _ in cs],
+                        [f.cpu().numpy() for f in kn], cn[1].cpu().numpy()))
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def check_null_sort_against_oracle(ref, world, use_cuda, all_null=False):
+    from supersonic_b200 import ssplan as sp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_null_sort_worker, args=(r, world, port, out, use_cuda, all_null)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    t = _null_sort_table()
+    if all_null:
+        t["k_null"][:] = 1
+    table = [sp.Column("k", sp.INT64, t["k"], t["k_null"].astype(bool)), sp.Column("j", sp.INT64, t["j"], t["j_null"].astype(bool)),
+             sp.Column("id", sp.INT64, t["id"]), sp.Column("w", sp.DOUBLE, t["w"], t["w_null"].astype(bool))]
+    for ci, desc in enumerate(NULL_SORT_CASES):
+        want = ref.run("(sort (order (k %s) (j %s) (id ASC)) (all) (scan 0))" % tuple("DESC" if d else "ASC" for d in desc), [table])
+        assert want.code == 0, want.error
+        cat = lambda f: np.concatenate([f(got[r][ci]) for r in range(world)])   # noqa: E731
+        assert np.array_equal(cat(lambda g: g[1][0]), want.column("id"))
+        kn, jn, wn = cat(lambda g: g[2][0]).astype(bool), cat(lambda g: g[2][1]).astype(bool), cat(lambda g: g[3]).astype(bool)
+        assert np.array_equal(kn, want.null("k")) and np.array_equal(jn, want.null("j")) and np.array_equal(wn, want.null("w"))
+        assert np.array_equal(cat(lambda g: g[0][0])[~kn], want.column("k")[~kn])
+        assert np.array_equal(cat(lambda g: g[0][1])[~jn], want.column("j")[~jn])
+        assert np.array_equal(cat(lambda g: g[1][1])[~wn], want.column("w")[~wn])
+        # NULL leading keys sit on the first rank for ASC and on the last for DESC
+        holder = world - 1 if desc[0] else 0
+        for r in range(world):
+            assert r == holder or not got[r][ci][2][0].any()
+
+
+@pytest.mark.parametrize("world,all_null", [(2, False), (3, False), (2, True)])
+def test_sharded_sort_null_keys_match_oracle(ref, world, all_null):
+    """Nullable key columns (NULLs first for ASC, last for DESC, per key) and a nullable payload column; with every
+    leading key NULL no splitter exists and one rank collects the table."""
+    check_null_sort_against_oracle(ref, world, False, all_null)

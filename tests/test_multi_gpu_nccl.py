@@ -116,3 +116,10 @@ def test_sharded_sort_two_gpus_matches_oracle(ref, skew):
         pytest.skip("needs two GPUs")
     from test_multi_gpu import check_sharded_sort_against_oracle
     check_sharded_sort_against_oracle(ref, 2, skew, True)
+
+
+def test_sharded_sort_null_keys_two_gpus_matches_oracle(ref):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from test_multi_gpu import check_null_sort_against_oracle
+    check_null_sort_against_oracle(ref, 2, True)

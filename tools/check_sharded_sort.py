@@ -20,5 +20,16 @@ for keys, desc in SORT_CASES:
     assert np.array_equal(cs[1][0].cpu().numpy(), t["v"][want])
     for (k, _), (nm, _) in zip(ks, keys):
         assert np.array_equal(k.cpu().numpy(), t[nm][want])
+# nullable keys and payload
+from test_multi_gpu import _null_sort_table, NULL_SORT_CASES
+t = _null_sort_table()
+dev = lambda nm: torch.from_numpy(np.ascontiguousarray(t[nm])).cuda()
+cpu = lambda nm: torch.from_numpy(np.ascontiguousarray(t[nm]))
+for desc in NULL_SORT_CASES:
+    ks, cs, kn, cn = ShardedSort(kern).run([(dev("k"), 2), (dev("j"), 2)], desc, [(dev("id"), 2), (dev("w"), 5)],
+                                           key_nulls=[dev("k_null"), dev("j_null")], col_nulls=[None, dev("w_null")])
+    want = NumpyJoinKernels().sort_perm([(cpu("k"), 2), (cpu("j"), 2)], desc, [cpu("k_null"), cpu("j_null")]).numpy()
+    assert np.array_equal(cs[0][0].cpu().numpy(), t["id"][want]), desc
+    assert np.array_equal(kn[0].cpu().numpy(), t["k_null"][want]) and np.array_equal(cn[1].cpu().numpy(), t["w_null"][want])
 print("sharded sort (1 GPU, nccl): %d cases OK, launches=%d" % (len(SORT_CASES), kern.ctx.launches()))
 dist.destroy_process_group()

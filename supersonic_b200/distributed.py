@@ -514,8 +514,7 @@ class ShardedSort(object):
     significant key meet on one rank, chunks arrive in rank order, and both sorts are stable), so
     the concatenation in rank order is the reference's output (cursor/core/sort.cc:150-322) whenever
     its order is total. Key and payload columns may carry is_null bytes (the same columns on every
-    rank); the most significant key must be a signed or floating type (unsigned columns travel as
-    their signed bit image here)."""
+    rank). Unsigned columns travel as their signed bit image."""
 
     SAMPLES_PER_RANK = 64
 
@@ -541,9 +540,10 @@ class ShardedSort(object):
         import torch.distributed as dist
         k, g = self.k, self.group
         world = dist.get_world_size(g)
-        if keys[0][1] in (3, 8):   # UINT64, UINT32
-            raise NotImplementedError("ShardedSort: the most significant key must be a signed or floating column")
         device = keys[0][0].device
+        # unsigned columns travel as their signed bit image: flipping the sign bit makes the image order-preserving
+        flip = {3: -(1 << 63), 8: -(1 << 31)}.get(keys[0][1])   # UINT64, UINT32
+        ordered = (lambda t: t) if flip is None else (lambda t: torch.bitwise_xor(t, torch.full((), flip, dtype=t.dtype, device=t.device)))
         BYTE = 6   # is_null bytes travel as BOOL columns
 
         def permute(perm, keys, cols, key_nulls, col_nulls):
@@ -567,13 +567,13 @@ class ShardedSort(object):
             sample = k.gather(keys[0], pos)
         else:
             sample = first[:0]
-        gathered = torch.cat(allgather_ragged(sample, g))
+        gathered = torch.cat(allgather_ragged(ordered(sample), g))
         gathered, _ = torch.sort(gathered)
         m = gathered.numel()
         if m and world > 1:
             splitters = gathered[[min(m - 1, (m * (r + 1)) // world) for r in range(world - 1)]]
             # 3. rows per destination: keys below the first splitter stay on rank 0, keys equal to a splitter go right of it
-            asc = first if not descending[0] else first.flip(0)
+            asc = ordered(first if not descending[0] else first.flip(0))
             bounds = torch.searchsorted(asc.contiguous(), splitters, right=False).tolist()
         else:
             bounds = [0] * (world - 1)     # no row anywhere has a leading key that is not NULL

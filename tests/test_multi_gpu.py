@@ -151,8 +151,9 @@ class NumpyJoinKernels(object):
 
     def sort_perm(self, keys, descending, key_nulls=None):
         ranks = []
-        for i, ((t, _), d) in enumerate(zip(keys, descending)):
+        for i, ((t, dt), d) in enumerate(zip(keys, descending)):
             v = t.numpy()
+            v = v.view(np.uint64) if dt == 3 else v.view(np.uint32) if dt == 8 else v      # unsigned columns: signed bit image
             isn = key_nulls[i].numpy().astype(bool) if key_nulls and key_nulls[i] is not None else np.zeros(len(v), dtype=bool)
             r = np.unique(np.where(isn, v[~isn][0] if (~isn).any() else 0, v), return_inverse=True)[1].astype(np.int64)
             r = -r if d else r
@@ -342,16 +343,18 @@ def _sort_table(n=30011, flavour=""):
     rng = np.random.default_rng(11)
     if flavour == "one_value":     # every row has the same leading key: one rank receives everything
         return {"k": np.full(n, 7, dtype=np.int64), "x": np.round(rng.standard_normal(n), 1),
-                "id": np.arange(n, dtype=np.int64), "v": np.full(n, 3, dtype=np.int64)}
+                "id": np.arange(n, dtype=np.int64), "v": np.full(n, 3, dtype=np.int64), "u": np.full(n, -5, dtype=np.int64)}
     if flavour == "empty":
         z = np.zeros(0, dtype=np.int64)
-        return {"k": z, "x": np.zeros(0), "id": z, "v": z}
+        return {"k": z, "x": np.zeros(0), "id": z, "v": z, "u": z}
     return {"k": rng.integers(-50, 50, n), "x": np.round(rng.standard_normal(n), 1), "id": np.arange(n, dtype=np.int64),
-            "v": rng.integers(0, 10**9, n)}
+            "v": rng.integers(0, 10**9, n),
+            # UINT64 values on both sides of 2^63, carried as their int64 bit image
+            "u": (rng.integers(0, 200, n).astype(np.uint64) * np.uint64(1 << 57)).view(np.int64)}
 
 
 SORT_CASES = [([("k", 2)], [False]), ([("k", 2)], [True]), ([("x", 5), ("k", 2)], [True, False]),
-              ([("k", 2), ("x", 5)], [False, True]), ([("v", 2)], [False])]
+              ([("k", 2), ("x", 5)], [False, True]), ([("v", 2)], [False]), ([("u", 3)], [False]), ([("u", 3), ("k", 2)], [True, True])]
 
 
 def _sort_worker(rank, world, port, out, skew, use_cuda=False, flavour=""):
@@ -414,7 +417,7 @@ def check_sharded_sort_against_oracle(ref, world, skew, use_cuda, flavour=""):
         assert p.exitcode == 0
     t = _sort_table(flavour=flavour)
     table = [sp.Column("k", sp.INT64, t["k"]), sp.Column("x", sp.DOUBLE, t["x"]), sp.Column("id", sp.INT64, t["id"]),
-             sp.Column("v", sp.INT64, t["v"])]
+             sp.Column("v", sp.INT64, t["v"]), sp.Column("u", sp.UINT64, t["u"].view(np.uint64))]
     for ci, (keys, desc) in enumerate(SORT_CASES):
         order = " ".join("(%s %s)" % (nm, "DESC" if d else "ASC") for (nm, _), d in zip(keys, desc)) + " (id ASC)"
         want = ref.run("(sort (order %s) (all) (scan 0))" % order, [table])
@@ -424,7 +427,7 @@ def check_sharded_sort_against_oracle(ref, world, skew, use_cuda, flavour=""):
         assert np.array_equal(ids, want.column("id")) and np.array_equal(vs, want.column("v"))
         for j in range(len(keys)):
             kj = np.concatenate([got[r][ci][0][j] for r in range(world)])
-            assert np.array_equal(kj, want.column(keys[j][0]))
+            assert np.array_equal(kj, want.column(keys[j][0]).view(kj.dtype))
         if not skew and not flavour and keys[0][0] == "v":   # distinct keys: the ranges are balanced within a sampling error
             sizes = [len(got[r][ci][1][0]) for r in range(world)]
             assert max(sizes) < 1.2 * len(ids) / world

@@ -342,6 +342,39 @@ class BoundSortOrder {
   vector<ColumnOrder> column_order_;
 };
 
+// supersonic/proto/specification.proto:12-30 (the generated message's accessors).
+class ExtendedSortSpecification {
+ public:
+  class Key {
+   public:
+    Key() : column_order_(ASCENDING), case_sensitive_(true), has_case_sensitive_(false) {}
+    const string& attribute_name() const { return attribute_name_; }
+    ColumnOrder column_order() const { return column_order_; }
+    bool case_sensitive() const { return case_sensitive_; }
+    bool has_case_sensitive() const { return has_case_sensitive_; }
+    void set_attribute_name(const string& v) { attribute_name_ = v; }
+    void set_column_order(ColumnOrder v) { column_order_ = v; }
+    void set_case_sensitive(bool v) { case_sensitive_ = v; has_case_sensitive_ = true; }
+   private:
+    string attribute_name_;
+    ColumnOrder column_order_;
+    bool case_sensitive_, has_case_sensitive_;
+  };
+  ExtendedSortSpecification() : limit_(0), has_limit_(false) {}
+  int keys_size() const { return static_cast<int>(keys_.size()); }
+  const Key& keys(int i) const { return keys_[i]; }
+  Key* mutable_keys(int i) { return &keys_[i]; }
+  Key* add_keys() { keys_.push_back(Key()); return &keys_.back(); }
+  bool has_limit() const { return has_limit_; }
+  uint64 limit() const { return limit_; }
+  void set_limit(uint64 v) { limit_ = v; has_limit_ = true; }
+  void CopyFrom(const ExtendedSortSpecification& o) { *this = o; }
+ private:
+  vector<Key> keys_;
+  uint64 limit_;
+  bool has_limit_;
+};
+
 // memory_limit is accepted for API compatibility; the whole input is sorted in HBM.
 Operation* Sort(const SortOrder* sort_order, const SingleSourceProjector* result_projector,
                 size_t memory_limit, Operation* child);
@@ -350,6 +383,14 @@ Operation* SortWithTempDirPrefix(const SortOrder* sort_order, const SingleSource
 FailureOrOwned<Cursor> BoundSort(const BoundSortOrder* sort_order, const BoundSingleSourceProjector* result_projector,
                                  size_t memory_limit, StringPiece temporary_directory_prefix, BufferAllocator* allocator,
                                  Cursor* child_cursor);                                            // sort.h:114
+// Sort by attribute names with an optional row limit (sort.h:103-131, sort.cc:857-1017); case
+// insensitivity concerns STRING keys only, which are not on this path.
+Operation* ExtendedSort(const ExtendedSortSpecification* specification, const SingleSourceProjector* result_projector,
+                        size_t memory_limit, Operation* child);
+FailureOrOwned<Cursor> BoundExtendedSort(const ExtendedSortSpecification* sort_specification,
+                                         const BoundSingleSourceProjector* result_projector, size_t memory_quota,
+                                         StringPiece temporary_directory_prefix, BufferAllocator* allocator,
+                                         rowcount_t max_row_count, Cursor* child);
 
 }  // namespace supersonic
 #endif  // SUPERSONIC_B200_HOST_CURSOR_H_

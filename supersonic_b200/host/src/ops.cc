@@ -1088,9 +1088,10 @@ class HashJoinCursor : public GpuCursor {
 // ------------------------------------------------------------------ Sort
 class SortCursor : public GpuCursor {
  public:
+  // limit < 0: every row; otherwise the first `limit` rows of the order (ExtendedSort, sort.cc:1010-1016)
   SortCursor(const TupleSchema& schema, BufferAllocator* allocator, Cursor* child,
-             const vector<std::pair<int, ColumnOrder> >& keys, const vector<int>& projected)
-      : GpuCursor(schema, allocator, "SortCursor"), child_(child), keys_(keys), projected_(projected) {}
+             const vector<std::pair<int, ColumnOrder> >& keys, const vector<int>& projected, int64 limit = -1)
+      : GpuCursor(schema, allocator, "SortCursor"), child_(child), keys_(keys), projected_(projected), limit_(limit) {}
   virtual CursorId GetCursorId() const { return SORT; }
   virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
  protected:
@@ -1115,15 +1116,16 @@ class SortCursor : public GpuCursor {
     SSB_CALL(s, ssb_sort_permutation(s->ctx(), static_cast<int32_t>(kc.size()), kc.empty() ? &dummy_col : kc.data(),
                                      desc.empty() ? &dummy : desc.data(), in.rows, static_cast<int64_t*>(perm.get())),
              "sort");
-    PROPAGATE_ON_FAILURE(result->Allocate(schema(), in.rows, /* force_nulls = */ true));
+    const int64_t out_rows = (limit_ >= 0 && limit_ < static_cast<int64>(in.rows)) ? static_cast<int64_t>(limit_) : static_cast<int64_t>(in.rows);
+    PROPAGATE_ON_FAILURE(result->Allocate(schema(), out_rows, /* force_nulls = */ true));
     for (size_t i = 0; i < projected_.size(); ++i) {
       const vector<int> pos(1, projected_[i]);
-      PROPAGATE_ON_FAILURE(GatherColumns(s, in, pos, static_cast<const int64_t*>(perm.get()), in.rows, false, result, i));
+      PROPAGATE_ON_FAILURE(GatherColumns(s, in, pos, static_cast<const int64_t*>(perm.get()), out_rows, false, result, i));
       if (in.columns[projected_[i]].col.nulls == NULL) {
-        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[i].col.nulls, 0, static_cast<size_t>((in.rows + 31) / 32 + 1) * 4), "memset");
+        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[i].col.nulls, 0, static_cast<size_t>((out_rows + 31) / 32 + 1) * 4), "memset");
       }
     }
-    result->rows = in.rows;
+    result->rows = out_rows;
     SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
     return Success();
   }
@@ -1131,6 +1133,7 @@ class SortCursor : public GpuCursor {
   std::unique_ptr<Cursor> child_;
   vector<std::pair<int, ColumnOrder> > keys_;
   vector<int> projected_;
+  int64 limit_;
 };
 
 class SortOperation : public BasicOperation {
@@ -1351,6 +1354,78 @@ Operation* ScalarAggregate(AggregationSpecification* aggregation, Operation* chi
 }
 Operation* Sort(const SortOrder* sort_order, const SingleSourceProjector* result_projector, size_t, Operation* child) {
   return new SortOperation(sort_order, result_projector, child);
+}
+
+// sort.cc:857-1017. The reference layers Compute (upper-cased copies of case-insensitive STRING keys), Sort and
+// Limit; without STRING columns that is a sort by attribute name whose cursor returns the first `limit` rows.
+FailureOrOwned<Cursor> BoundExtendedSort(const ExtendedSortSpecification* sort_specification,
+                                         const BoundSingleSourceProjector* result_projector, size_t, StringPiece,
+                                         BufferAllocator* allocator, rowcount_t, Cursor* child_cursor) {
+  std::unique_ptr<const ExtendedSortSpecification> spec(sort_specification);
+  std::unique_ptr<const BoundSingleSourceProjector> proj(result_projector);
+  std::unique_ptr<Cursor> child(child_cursor);
+  const TupleSchema& cs = child->schema();
+  vector<std::pair<int, ColumnOrder> > keys;
+  vector<string> seen;
+  for (int i = 0; i < spec->keys_size(); ++i) {
+    const string& name = spec->keys(i).attribute_name();
+    if (std::find(seen.begin(), seen.end(), name) != seen.end()) {
+      THROW(new Exception(ERROR_INVALID_ARGUMENT_VALUE, "Duplicate case sensitive key: " + name + " column in schema (" +
+                                                            cs.GetHumanReadableSpecification() + ")"));
+    }
+    seen.push_back(name);
+    const int pos = cs.LookupAttributePosition(name);
+    if (pos < 0) {   // the reference CHECK-fails here (TupleSchema::LookupAttribute)
+      THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "No attribute '" + name + "' in schema (" + cs.GetHumanReadableSpecification() + ")"));
+    }
+    const DataType t = cs.attribute(pos).type();
+    if (t == STRING || t == BINARY) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length sort keys are not on the B200 hot path (SURVEY 8f)"));
+    }
+    keys.push_back(std::make_pair(pos, spec->keys(i).column_order()));
+  }
+  vector<int> projected;
+  TupleSchema result;
+  if (proj) {
+    result = proj->result_schema();
+    for (int i = 0; i < result.attribute_count(); ++i) projected.push_back(proj->source_attribute_position(i));
+  } else {
+    result = cs;
+    for (int i = 0; i < cs.attribute_count(); ++i) projected.push_back(i);
+  }
+  const int64 limit = spec->has_limit() ? static_cast<int64>(std::min<uint64>(spec->limit(), static_cast<uint64>(1) << 62)) : -1;
+  return Success(static_cast<Cursor*>(new SortCursor(result, allocator, child.release(), keys, projected, limit)));
+}
+
+namespace {
+class ExtendedSortOperation : public BasicOperation {
+ public:
+  ExtendedSortOperation(const ExtendedSortSpecification* spec, const SingleSourceProjector* projector, Operation* child)
+      : BasicOperation(child), spec_(spec), projector_(projector) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    FailureOrOwned<Cursor> child_cursor = child()->CreateCursor();
+    PROPAGATE_ON_FAILURE(child_cursor);
+    std::unique_ptr<Cursor> cursor(child_cursor.release());
+    std::unique_ptr<const BoundSingleSourceProjector> bound;
+    if (projector_) {
+      FailureOrOwned<const BoundSingleSourceProjector> proj = projector_->Bind(cursor->schema());
+      PROPAGATE_ON_FAILURE(proj);
+      bound.reset(proj.release());
+    }
+    return BoundExtendedSort(new ExtendedSortSpecification(*spec_), bound.release(), 0, "", buffer_allocator(),
+                             Cursor::kDefaultRowCount, cursor.release());
+  }
+ protected:
+  virtual string DebugName() const { return "ExtendedSort"; }
+ private:
+  std::unique_ptr<const ExtendedSortSpecification> spec_;
+  std::unique_ptr<const SingleSourceProjector> projector_;
+};
+}  // namespace
+
+Operation* ExtendedSort(const ExtendedSortSpecification* specification, const SingleSourceProjector* result_projector,
+                        size_t, Operation* child) {
+  return new ExtendedSortOperation(specification, result_projector, child);
 }
 
 SortOrder::~SortOrder() { for (size_t i = 0; i < keys_.size(); ++i) delete keys_[i].first; }

@@ -39,6 +39,7 @@
 
 #include "supersonic/supersonic.h"
 #include "supersonic/cursor/core/aggregator.h"
+#include "supersonic/proto/specification.pb.h"
 
 namespace {
 
@@ -374,6 +375,25 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
     }
     const SingleSourceProjector* p = BuildProjector(s.kids[2]);
     return Sort(order.release(), p, static_cast<size_t>(1) << 40, BuildOp(s.kids[3], in));
+  }
+  if (h == "extended_sort") {
+    // (extended_sort (order (NAME ASC|DESC)...) LIMIT|none PROJECTOR CHILD): sort.h:103-107
+    Arity(s, 4);
+    if (Head(s.kids[1]) != "order") throw ParseError{"expected (order ...)"};
+    std::unique_ptr<ExtendedSortSpecification> spec(new ExtendedSortSpecification);
+    for (size_t i = 1; i < s.kids[1].kids.size(); ++i) {
+      const Sx& k = s.kids[1].kids[i];
+      if (k.atom || k.kids.size() != 2) throw ParseError{"order takes (NAME ASC|DESC) pairs"};
+      const std::string& d = Atom(k.kids[1]);
+      if (d != "ASC" && d != "DESC") throw ParseError{"order direction must be ASC or DESC"};
+      ExtendedSortSpecification::Key* key = spec->add_keys();
+      key->set_attribute_name(Atom(k.kids[0]));
+      key->set_column_order(d == "ASC" ? ASCENDING : DESCENDING);
+    }
+    const std::string& lim = Atom(s.kids[2]);
+    if (lim != "none") spec->set_limit(static_cast<uint64_t>(strtoull(lim.c_str(), NULL, 10)));
+    const SingleSourceProjector* p = BuildProjector(s.kids[3]);
+    return ExtendedSort(spec.release(), p, static_cast<size_t>(1) << 40, BuildOp(s.kids[4], in));
   }
   throw ParseError{"unknown operation '" + h + "'"};
 }

@@ -180,6 +180,19 @@ GOLDEN = [
      [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0]), col("v", sp.INT64, [0, 1, 2, 3, 4])],
       [col("y", sp.DOUBLE, [-0.0, 2.0]), col("w", sp.INT64, [7, 8])]],
      {"v": [1, 3], "w": [7, 7]}, True),
+    # sort.h:103-131, sort.cc:857-1017: sort by attribute names, first `limit` rows (cursor/core/sort_test.cc ExtendedSort cases)
+    ("extended_sort_limit", "(extended_sort (order (k DESC)) 3 (all) (scan 0))",
+     [[col("k", sp.INT32, [3, 1, 2, 5, 4]), col("v", sp.INT32, [30, 10, 20, 50, 40])]],
+     {"k": [5, 4, 3], "v": [50, 40, 30]}, True),
+    ("extended_sort_no_limit", "(extended_sort (order (a ASC) (b DESC)) none (named b a) (scan 0))",
+     [[col("a", sp.INT64, [2, 1, 2, 1]), col("b", sp.DOUBLE, [0.5, -1.0, 7.0, 3.0])]],
+     {"b": [3.0, -1.0, 7.0, 0.5], "a": [1, 1, 2, 2]}, True),
+    ("extended_sort_limit_beyond_rows", "(extended_sort (order (k ASC)) 9 (named v) (scan 0))",
+     [[ncol("k", sp.INT32, [3, N, 1, 2]), col("v", sp.INT32, [30, 0, 10, 20])]],
+     {"v": [0, 10, 20, 30]}, True),
+    ("extended_sort_limit_zero", "(extended_sort (order (k ASC)) 0 (all) (scan 0))",
+     [[col("k", sp.INT32, [3, 1, 2]), col("v", sp.INT32, [30, 10, 20])]],
+     {"k": [], "v": []}, True),
     # -0.0 and +0.0 are one key value (sort.cc:151 compares with operator<): the second key decides among them
     ("sort_signed_zero", "(sort (order (x DESC) (v ASC)) (all) (scan 0))",
      [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0, -1.0]), col("v", sp.INT32, [5, 4, 3, 2, 1, 0])]],

@@ -124,6 +124,13 @@ def test_operation_schemas(ref, b200):
 
 
 MORE_PLANS = [
+    '(extended_sort (order (i64 ASC) (f64 DESC)) 3 (named i32 f64) (scan 0))',
+    '(extended_sort (order (i64 ASC)) none (all) (scan 0))',
+    '(extended_sort (order (i64 ASC) (i64 DESC)) none (all) (scan 0))',
+    '(extended_sort (order) 0 (all) (scan 0))',
+    '(extended_sort (order (ni64 DESC)) 2 (named nope) (scan 0))',
+    '(extended_sort (order (ni64 DESC)) 2 (rename (i32 a) (i64 a)) (scan 0))',
+    '(extended_sort (order (c DESC)) 1 (all) (group (named i32) (aggs (COUNT "" c)) (scan 0)))',
     '(hash_join INNER (named i64) (named i64) (multi (0 (all)) (1 (all))) UNIQUE (scan 0) (scan 0))',
     '(hash_join INNER (named i64) (named i64) (multi (0 (all l.)) (1 (all r.))) UNIQUE (scan 0) (scan 0))',
     '(hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (all l.)) (1 (all r.))) UNIQUE (scan 0) (scan 0))',

@@ -127,6 +127,9 @@ class BasicOperation : public Operation {
 // cursor/core/scan_view.h:35. The view's column pointers may be host (pageable or pinned) or
 // device memory; they must stay valid while cursors created from the operation live.
 Operation* ScanView(const View& view);
+// Rows view[selection_vector[i]], i < row_count (scan_view.h:37-46); the vector is borrowed.
+Operation* ScanViewWithSelection(const View& view, const rowcount_t row_count, const rowid_t* selection_vector,
+                                 rowcount_t buffer_row_capacity);
 
 // cursor/infrastructure/table.h:49-172 (host-memory table; the subset plan code uses)
 class Table {
@@ -279,6 +282,9 @@ class Aggregator {
 // ---- cursors created directly from bound objects (the Bound* factories of cursor/core/*.h).
 // Ownership as in the reference: the bound objects and the child are taken over, allocators are not.
 Cursor* BoundScanView(const View& view);                                                          // scan_view.h:52
+FailureOrOwned<Cursor> BoundScanViewWithSelection(const View& view, const rowcount_t row_count,
+                                                  const rowid_t* selection_vector, BufferAllocator* allocator,
+                                                  rowcount_t buffer_row_capacity);                  // scan_view.h:59
 FailureOrOwned<Cursor> BoundCompute(BoundExpressionTree* computation, BufferAllocator* allocator,
                                     rowcount_t max_row_count, Cursor* child);                     // compute.h:36
 FailureOrOwned<Cursor> BoundFilter(BoundExpressionTree* predicate, const BoundSingleSourceProjector* projector,

@@ -1136,6 +1136,65 @@ class SortCursor : public GpuCursor {
   int64 limit_;
 };
 
+// ------------------------------------------------------------------ ScanViewWithSelection
+// scan_view.cc: a cursor over view[selection[i]]. The view is uploaded once, the selection vector is the index
+// list of one gather per column (ssb_gather; a row may be selected any number of times).
+class SelectionCursor : public GpuCursor {
+ public:
+  SelectionCursor(const View& view, rowcount_t row_count, const rowid_t* selection, BufferAllocator* allocator)
+      : GpuCursor(view.schema(), allocator, "ScanViewWithSelection"), source_(new ViewCursor(view)),
+        row_count_(row_count), selection_(selection) {}
+  virtual CursorId GetCursorId() const { return VIEW; }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    DeviceTable in;
+    std::unique_ptr<Block> keepalive;
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(source_.get(), &in, &keepalive));
+    const int64_t n = static_cast<int64_t>(row_count_);
+    for (int64_t i = 0; i < n; ++i) {
+      if (selection_[i] < 0 || selection_[i] >= static_cast<rowid_t>(in.rows)) {
+        THROW(new Exception(ERROR_INVALID_ARGUMENT_VALUE, "selection vector points outside the view"));
+      }
+    }
+    DeviceBuffer ids;
+    PROPAGATE_ON_FAILURE(ids.Allocate(static_cast<size_t>(n) * 8 + 128));
+    if (n > 0) SSB_CALL(s, ssb_memcpy_h2d(s->ctx(), ids.get(), selection_, static_cast<size_t>(n) * 8), "upload");
+    PROPAGATE_ON_FAILURE(result->Allocate(schema(), n, /* force_nulls = */ true));
+    for (int i = 0; i < schema().attribute_count(); ++i) {
+      const vector<int> pos(1, i);
+      PROPAGATE_ON_FAILURE(GatherColumns(s, in, pos, static_cast<const int64_t*>(ids.get()), n, false, result, static_cast<size_t>(i)));
+      if (in.columns[i].col.nulls == NULL) {
+        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[i].col.nulls, 0, static_cast<size_t>((n + 31) / 32 + 1) * 4), "memset");
+      }
+    }
+    result->rows = n;
+    SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
+    return Success();
+  }
+ private:
+  std::unique_ptr<Cursor> source_;
+  rowcount_t row_count_;
+  const rowid_t* selection_;
+};
+
+class SelectionOperation : public BasicOperation {
+ public:
+  SelectionOperation(const View& view, rowcount_t row_count, const rowid_t* selection)
+      : view_(view), row_count_(row_count), selection_(selection) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    return Success(static_cast<Cursor*>(new SelectionCursor(view_, row_count_, selection_, buffer_allocator())));
+  }
+ protected:
+  virtual string DebugName() const { return "ScanViewWithSelection"; }
+ private:
+  View view_;
+  rowcount_t row_count_;
+  const rowid_t* selection_;
+};
+
 class SortOperation : public BasicOperation {
  public:
   SortOperation(const SortOrder* order, const SingleSourceProjector* projector, Operation* child)
@@ -1340,6 +1399,13 @@ Operation* SortWithTempDirPrefix(const SortOrder* sort_order, const SingleSource
 
 // ------------------------------------------------------------------ factories
 Operation* ScanView(const View& view) { return new ScanViewOperation(view); }
+Operation* ScanViewWithSelection(const View& view, const rowcount_t row_count, const rowid_t* selection_vector, rowcount_t) {
+  return new SelectionOperation(view, row_count, selection_vector);
+}
+FailureOrOwned<Cursor> BoundScanViewWithSelection(const View& view, const rowcount_t row_count, const rowid_t* selection_vector,
+                                                  BufferAllocator* allocator, rowcount_t) {
+  return Success(static_cast<Cursor*>(new SelectionCursor(view, row_count, selection_vector, allocator)));
+}
 Operation* Compute(const Expression* computation, Operation* child) { return new ComputeOperation(computation, child); }
 Operation* Filter(const Expression* predicate, const SingleSourceProjector* projector, Operation* child) {
   return new FilterOperation(predicate, projector, child);

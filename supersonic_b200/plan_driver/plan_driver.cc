@@ -33,6 +33,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -316,6 +317,18 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
     size_t n = static_cast<size_t>(atoi(Atom(s.kids[1]).c_str()));
     if (n >= in.views.size()) throw ParseError{"scan: no such table"};
     return ScanView(in.views[n]);
+  }
+  if (h == "scan_selection") {
+    // (scan_selection N (ids ROW...)): scan_view.h:43; the vector lives as long as the process (a test tool)
+    Arity(s, 2);
+    size_t n = static_cast<size_t>(atoi(Atom(s.kids[1]).c_str()));
+    if (n >= in.views.size()) throw ParseError{"scan_selection: no such table"};
+    if (Head(s.kids[2]) != "ids") throw ParseError{"expected (ids ...)"};
+    static std::deque<std::vector<rowid_t> > kept;
+    kept.push_back(std::vector<rowid_t>());
+    kept.back().reserve(s.kids[2].kids.size() + 1);   // never a NULL pointer: the reference CHECKs it (scan_view.cc:122)
+    for (size_t i = 1; i < s.kids[2].kids.size(); ++i) kept.back().push_back(static_cast<rowid_t>(atoll(Atom(s.kids[2].kids[i]).c_str())));
+    return ScanViewWithSelection(in.views[n], static_cast<rowcount_t>(kept.back().size()), kept.back().data(), 1024);
   }
   if (h == "compute") {
     Arity(s, 2);

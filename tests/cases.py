@@ -171,6 +171,10 @@ GOLDEN = [
     ("sort_two_keys", "(sort (order (a ASC) (b DESC)) (named b a) (scan 0))",
      [[col("a", sp.INT64, [2, 1, 2, 1]), col("b", sp.DOUBLE, [0.5, -1.0, 7.0, 3.0])]],
      {"b": [3.0, -1.0, 7.0, 0.5], "a": [1, 1, 2, 2]}, True),
+]
+
+# Cases added after the last GPU run of round 1: oracle-pinned on the CPU; test_parity_gpu.py runs them last.
+GOLDEN_LATE = [
     # ... but they are two hash keys: the row hash (hash of the bit image) tells them apart before == is asked
     ("group_signed_zero_keys", "(group (named x) (aggs (SUM v s) (COUNT \"\" c)) (scan 0))",
      [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0]), col("v", sp.INT64, [0, 1, 2, 3, 4])]],
@@ -180,6 +184,19 @@ GOLDEN = [
      [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0]), col("v", sp.INT64, [0, 1, 2, 3, 4])],
       [col("y", sp.DOUBLE, [-0.0, 2.0]), col("w", sp.INT64, [7, 8])]],
      {"v": [1, 3], "w": [7, 7]}, True),
+    # scan_view.h:37-46: a cursor over view[selection[i]]; rows may be selected any number of times
+    ("scan_selection", "(scan_selection 0 (ids 4 1 1 0))",
+     [[ncol("k", sp.INT32, [3, N, 2, 5, 4]), col("v", sp.DOUBLE, [30.0, 10.0, 20.0, 50.0, 40.0])]],
+     {"k": [4, N, N, 3], "v": [40.0, 10.0, 10.0, 30.0]}, True),
+    ("scan_selection_empty", "(scan_selection 0 (ids))",
+     [[ncol("k", sp.INT32, [3, N, 2]), col("v", sp.DOUBLE, [30.0, 10.0, 20.0])]],
+     {"k": [], "v": []}, True),
+    ("scan_selection_compute", "(compute (as e (plus (col v) (col k))) (scan_selection 0 (ids 2 1 2)))",
+     [[ncol("k", sp.INT32, [3, N, 2, 5, 4]), col("v", sp.DOUBLE, [30.0, 10.0, 20.0, 50.0, 40.0])]],
+     {"e": [22.0, N, 22.0]}, True),
+    ("scan_selection_group", "(group (named k) (aggs (SUM v s)) (scan_selection 0 (ids 4 4 1 1 0)))",
+     [[ncol("k", sp.INT32, [3, N, 2, 5, 4]), col("v", sp.DOUBLE, [30.0, 10.0, 20.0, 50.0, 40.0])]],
+     {"k": [4, N, 3], "s": [80.0, 20.0, 30.0]}, False),
     # sort.h:103-131, sort.cc:857-1017: sort by attribute names, first `limit` rows (cursor/core/sort_test.cc ExtendedSort cases)
     ("extended_sort_limit", "(extended_sort (order (k DESC)) 3 (all) (scan 0))",
      [[col("k", sp.INT32, [3, 1, 2, 5, 4]), col("v", sp.INT32, [30, 10, 20, 50, 40])]],

@@ -124,6 +124,10 @@ def test_operation_schemas(ref, b200):
 
 
 MORE_PLANS = [
+    '(scan_selection 0 (ids 3 1 1 0))',
+    '(scan_selection 0 (ids))',
+    '(filter (col b) (named i32) (scan_selection 0 (ids 2 2)))',
+    '(sort (order (i64 ASC)) (all) (scan_selection 0 (ids 0 3)))',
     '(extended_sort (order (i64 ASC) (f64 DESC)) 3 (named i32 f64) (scan 0))',
     '(extended_sort (order (i64 ASC)) none (all) (scan 0))',
     '(extended_sort (order (i64 ASC) (i64 DESC)) none (all) (scan 0))',

@@ -2,10 +2,12 @@
 known-answer vectors of the reference's own tests. CPU only."""
 import pytest
 
-from cases import GOLDEN, check_result
+from cases import GOLDEN, GOLDEN_LATE, check_result
+
+ALL_GOLDEN = GOLDEN + GOLDEN_LATE
 
 
-@pytest.mark.parametrize("case", GOLDEN, ids=[c[0] for c in GOLDEN])
+@pytest.mark.parametrize("case", ALL_GOLDEN, ids=[c[0] for c in ALL_GOLDEN])
 @pytest.mark.parametrize("next_rows", [0, 1, 2])
 def test_oracle_reproduces_reference_vectors(ref, case, next_rows):
     _, plan, tables, expected, ordered = case

@@ -134,17 +134,6 @@ def test_signaling_division_fails(ref, b200):
                  b200.run("(compute (cpp_divide_signaling (col a) (col b)) (scan 0))", [ok]))
 
 
-@pytest.mark.parametrize("jt", ["RIGHT_OUTER", "FULL_OUTER"])
-def test_unsupported_join_types_fail_at_the_first_lookup(ref, b200, jt):
-    """hash_join.cc:713-726: any join type binds; the other two are refused once the probe side has produced a row."""
-    plan = "(hash_join %s (named k) (named k) (multi (0 (named v)) (1 (rename (v w)))) UNIQUE (scan 0) (scan 1))" % jt
-    t = lambda n: [sp.Column("k", sp.INT64, np.arange(n)), sp.Column("v", sp.INT64, np.arange(n))]   # noqa: E731
-    for nl, nr in ((3, 3), (3, 0)):
-        a, b = ref.run(plan, [t(nl), t(nr)]), b200.run(plan, [t(nl), t(nr)])
-        assert a.code == 103 and b.code == 103, (nl, nr, a.code, b.code, b.error)
-        assert jt in b.error
-
-
 @pytest.mark.parametrize("n,sel", [(10_000_000, 2**19), (1_000_003, 2**10), (2049, 2**20), (1024, 0)])
 def test_filter_project_c1(ref, b200, n, sel):
     """BASELINE config 1: Compute(a*b+c) then Filter(d<K) over 4 x INT64, bit-exact, in order."""
@@ -413,3 +402,31 @@ def test_streaming_with_transfer_narrowing(ref, b200, monkeypatch, narrow):
     plan = ("(filter (less (col d) (i64 600000)) (all) (compute (compound (as x (plus (multiply (col s) (col e)) (col w))) "
             "(col s) (col e) (col g) (col t) (as y (plus (col g) (col d)))) (scan 0)))")
     same_results(ref.run(plan, [cols], next_max_rows=1024), b200.run(plan, [cols], next_max_rows=5000))
+
+
+# ------------------------------------------------------------------------------------------------
+# Added after the last GPU run of round 1 (oracle-pinned on the CPU): kept at the end of the GPU suite so that
+# everything measured before still runs first.
+@pytest.mark.parametrize("jt", ["RIGHT_OUTER", "FULL_OUTER"])
+def test_unsupported_join_types_fail_at_the_first_lookup(ref, b200, jt):
+    """hash_join.cc:713-726: any join type binds; the other two are refused once the probe side has produced a row."""
+    plan = "(hash_join %s (named k) (named k) (multi (0 (named v)) (1 (rename (v w)))) UNIQUE (scan 0) (scan 1))" % jt
+    t = lambda n: [sp.Column("k", sp.INT64, np.arange(n)), sp.Column("v", sp.INT64, np.arange(n))]   # noqa: E731
+    for nl, nr in ((3, 3), (3, 0)):
+        a, b = ref.run(plan, [t(nl), t(nr)]), b200.run(plan, [t(nl), t(nr)])
+        assert a.code == 103 and b.code == 103, (nl, nr, a.code, b.code, b.error)
+        assert jt in b.error
+
+
+from cases import GOLDEN_LATE  # noqa: E402
+
+# least new machinery first (key images, then the sort cursor's row limit, then the selection cursor)
+_LATE_ORDER = ["sort_signed_zero", "group_signed_zero_keys", "join_signed_zero_keys", "extended_sort"]
+LATE = sorted(GOLDEN_LATE, key=lambda c: next((i for i, p in enumerate(_LATE_ORDER) if c[0].startswith(p)), len(_LATE_ORDER)))
+
+
+@pytest.mark.parametrize("next_rows", [0, 1, 3])
+@pytest.mark.parametrize("case", LATE, ids=[c[0] for c in LATE])
+def test_reference_vectors_late(b200, case, next_rows):
+    _, plan, tables, expected, ordered = case
+    check_result(b200.run(plan, tables, next_max_rows=next_rows), expected, ordered)

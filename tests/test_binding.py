@@ -287,3 +287,19 @@ def test_join_key_schemas_are_checked_at_bind_time(ref, b200):
         assert b200.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == 402
     ok = "(hash_join INNER (named i32) (named u32) (multi (0 (named i32)) (1 (rename (i32 r)))) UNIQUE (scan 0) (scan 0))"
     assert ref.run(ok, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == b200.run(ok, [COLS], flags=sp.SSPLAN_BIND_ONLY).code == 0
+
+
+@pytest.mark.parametrize("agg", ["SUM", "MIN", "MAX", "COUNT", "FIRST", "LAST"])
+def test_aggregate_binding_cross_product(ref, b200, agg):
+    """Every aggregate over every column type and nullability, with and without a result-type override, grouped and
+    scalar (aggregator.cc:63-152): result type, nullability or the error code."""
+    bad = []
+    for x in NAMES:
+        for t in [""] + TYPES:
+            for shape in ['(group (named i32) (aggs (%s %s r%s)) (scan 0))', '(scalar_agg (aggs (%s %s r%s)) (scan 0))']:
+                plan = shape % (agg, x, (" " + t) if t else "")
+                a = ref.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+                b = b200.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+                if _key(a) != _key(b):
+                    bad.append((plan, _key(a), _key(b)))
+    assert not bad, bad[:10]

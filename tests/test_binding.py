@@ -303,3 +303,30 @@ def test_aggregate_binding_cross_product(ref, b200, agg):
                 if _key(a) != _key(b):
                     bad.append((plan, _key(a), _key(b)))
     assert not bad, bad[:10]
+
+
+def test_operators_over_every_column_type(ref, b200):
+    """Filter predicates, sort keys, group keys, join keys (both join types and uniqueness declarations, LEFT_OUTER
+    nullability of the build side's columns), projections and compound expressions over every column type."""
+    plans = []
+    for x in NAMES:
+        plans.append('(filter (col %s) (all) (scan 0))' % x)
+        plans.append('(filter (is_null (col %s)) (named %s) (scan 0))' % (x, x))
+        plans.append('(sort (order (%s ASC)) (named %s) (scan 0))' % (x, x))
+        plans.append('(sort (order (%s DESC) (i32 ASC)) (all) (scan 0))' % x)
+        plans.append('(extended_sort (order (%s DESC)) 5 (all) (scan 0))' % x)
+        plans.append('(group (named %s) (aggs (COUNT "" c)) (scan 0))' % x)
+        plans.append('(group (named %s i64) (aggs (SUM f64 s) (MIN %s m)) (scan 0))' % (x, x))
+        for jt in ("INNER", "LEFT_OUTER"):
+            for u in ("UNIQUE", "NOT_UNIQUE"):
+                plans.append('(hash_join %s (named %s) (named %s) (multi (0 (named i32)) (1 (rename (%s r) (nf64 rn) (b rb)))) %s '
+                             '(scan 0) (scan 0))' % (jt, x, x, x, u))
+        plans.append('(project (rename (%s a) (i32 b)) (scan 0))' % x)
+        plans.append('(compute (compound (as a (col %s)) (as b (is_null (col %s)))) (scan 0))' % (x, x))
+    bad = []
+    for plan in plans:
+        a = ref.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+        b = b200.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+        if _key(a) != _key(b):
+            bad.append((plan, _key(a), a.error, _key(b), b.error))
+    assert not bad, bad[:10]

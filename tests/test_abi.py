@@ -50,3 +50,18 @@ def test_host_generator_matches_definition(built):
         return x ^ (x >> 31)
     want = [splitmix(((42 ^ ((3 * 0x9E3779B97F4A7C15) & (2**64 - 1))) + 5 + i) & (2**64 - 1)) for i in range(16)]
     assert [int(v) for v in out] == want
+
+
+@pytest.mark.parametrize("max_rows", [0, 1, 7, 1024, 100000])
+def test_view_cursor_slices_like_the_reference(ref, b200, max_rows):
+    """ScanView alone is host work (view_cursor.cc:47-75): the same rows, NULLs and number of Next() calls."""
+    import numpy as np
+    from cases import same_results
+    from supersonic_b200 import ssplan as sp
+    rng = np.random.default_rng(1)
+    n = 5000
+    t = [sp.Column("a", sp.INT64, rng.integers(0, 100, n)), sp.Column("b", sp.DOUBLE, rng.random(n), is_null=rng.random(n) < 0.1),
+         sp.Column("c", sp.BOOL, rng.integers(0, 2, n))]
+    a, b = ref.run("(scan 0)", [t], next_max_rows=max_rows), b200.run("(scan 0)", [t], next_max_rows=max_rows)
+    same_results(a, b)
+    assert a.next_calls == b.next_calls

@@ -56,10 +56,22 @@ NodePtr MakeNode(int op, DataType type, bool nullable, const string& name, const
 
 NodePtr MakeCast(const NodePtr& child, DataType to) {
   if (child->type == to) return child;
+  // The reference folds constant subtrees at bind time (basic_bound_expression.cc:286-327), except the
+  // UINT64 -> INT64 conversion, which keeps its CAST name even over a literal.
+  const bool folds = !(child->type == UINT64 && to == INT64);
+  if (folds && child->op == SSB_OP_CONST && (child->flags & SSB_NODE_NULL)) {
+    // a cast of the NULL literal is the NULL literal of the target type, named "NULL"
+    std::shared_ptr<ExprNode> n = NewNode(SSB_OP_CONST, to, true, "NULL");
+    n->constant = true;
+    n->flags = SSB_NODE_NULL;
+    memset(&n->imm, 0, sizeof(n->imm));
+    return n;
+  }
   const int op = (child->type == DATE && to == DATETIME) ? SSB_OP_DATE_TO_DATETIME : SSB_OP_CAST;
-  return MakeNode(op, to, child->nullable,
-                  "CAST_" + TypeName(child->type) + "_TO_" + TypeName(to) + "(" + child->name + ")",
-                  vector<NodePtr>(1, child));
+  const string name = "CAST_" + TypeName(child->type) + "_TO_" + TypeName(to) + "(" + child->name + ")";
+  NodePtr n = MakeNode(op, to, child->nullable, name, vector<NodePtr>(1, child));
+  if (!folds) std::const_pointer_cast<ExprNode>(n)->name = name;
+  return n;
 }
 
 // bound_expression_factory.cc:70-90

@@ -33,6 +33,13 @@ PLAN = ("(filter (less (col d) (i64 524288)) (named e) (compute (compound "
         "(as e (plus (multiply (col a) (col b)) (col c))) (col d)) (scan 0)))")
 SEED = 42
 K_SEL = 1 << 19
+# Both arms print exactly these (the driver divides the two lines only when they agree).
+METRIC = "rows/sec, filter+project (Compute e=a*b+c, Filter d<2^19 project e) over 8xINT64 rows"
+
+
+def workload(rows):
+    return ("C2 variant A: Filter(d<2^19, project e, Compute(e=a*b+c, d)) over a %d-row 8xINT64 table per GPU "
+            "(4 columns read, selectivity 0.5)" % rows)
 # column generators: (kind, lo, span) -- a,b in [-2^31,2^31), c in [-2^62,2^62), d in [0,2^20)
 GEN = {"a": (0, -(1 << 31), 1 << 32), "b": (0, -(1 << 31), 1 << 32), "c": (0, -(1 << 62), 1 << 63),
        "d": (0, 0, 1 << 20), "e": (0, 0, 0), "f": (0, 0, 0), "g": (0, 0, 0), "h": (0, 0, 0)}
@@ -59,35 +66,90 @@ def measured_traffic(rows):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML poller
+    (every 2 ms; nvidia-smi -lms needs ~100 ms to deliver its first line, longer than ten
+    6.7 ms steps), nvidia-smi as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.lines, self.proc = device, [], None
+        self.samples, self.stop_flag, self.thread, self.nvml = [], False, None, None
+        self.window = [None, None]
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: go through the PCI bus id of the CUDA device
+            handle = None
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(self.device).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.device).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.device).pci_device_id
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.nvml = (pynvml, handle)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def mark(self, which):
+        """which = 0: the timed region starts now; 1: it ended."""
+        self.window[which] = time.perf_counter()
+
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((time.perf_counter(), float(mhz), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        t0, t1 = self.window
+        inside = lambda t: (t0 is None or t >= t0) and (t1 is None or t <= t1)   # noqa: E731
+        if self.nvml is not None:
+            pynvml, _ = self.nvml
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+            sel = [x for x in self.samples if inside(x[0])] or self.samples[-3:]
+            reasons = sorted(nm for nm, b in bits.items() if any(x[2] & b for x in sel))
+            sm = [x[1] for x in sel]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(sm), "reasons": reasons, "source": "nvml poll inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        sel = [ln for t, ln in self.lines if inside(t)] or [ln for _, ln in self.lines[-3:]]
+        for line in sel:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -100,7 +162,7 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 def build_program(capi, ctx):
@@ -350,6 +412,22 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
             if world > 1 else "none"}
 
 
+def fill_host_column(capi, name, arr, first_row, threads):
+    """Fills `arr` (int64, possibly pinned) with column `name` of the synthetic table, in slices on `threads`
+    threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    kind, lo, span = GEN[name]
+    lib = capi.load()
+    rows = arr.shape[0]
+    step = max(1 << 20, (rows + threads * 4 - 1) // (threads * 4))
+
+    def part(begin):
+        n = min(step, rows - begin)
+        lib.ssb_generate_host(arr.ctypes.data + begin * 8, n, first_row + begin, SEED, COLS.index(name), kind, lo, span)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(part, range(0, rows, step)))
+
+
 def host_column(capi, name, rows, first_row=0):
     kind, lo, span = GEN[name]
     out = np.empty(rows, dtype=np.int64)
@@ -392,21 +470,23 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     ctx.enable_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         prog.run(inputs, rows, outputs, d_count)
     ctx.sync()
     launches0 = ctx.launches()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     kernel_ms = []
+    sampler.mark(0)
     ctx.timer_start()
     for _ in range(args.steps):
         prog.run(inputs, rows, outputs, d_count)
         if args.per_kernel_timing:
             kernel_ms.append(ctx.last_kernel_ms())
     total_ms = ctx.timer_stop()
+    sampler.mark(1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches() - launches0
@@ -438,12 +518,11 @@ def run_b200(args):
         k_ms = float(np.mean(kernel_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         result = {
-            "metric": "rows/sec, filter+project (Compute a*b+c, Filter d<K) over 8xINT64 rows resident in HBM",
+            "metric": METRIC,
             "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "C2 variant A: Filter(d<2^19, project e, Compute(e=a*b+c, d)) over a %d-row "
-                                   "8xINT64 table per GPU (4 columns read, selectivity 0.5)" % rows,
+            "config": {"workload": workload(rows), "residency": "value: inputs resident in HBM; e2e: pinned host buffers",
                        "rows_per_gpu": rows, "selectivity": sel, "l2": "inputs (%.1f GB per step) larger than L2"
                        % (rows * 32 / 1e9), "parallelism": "row-range shards, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -464,51 +543,66 @@ def run_b200(args):
                              max(1, min(rows, args.join_probe_rows) // 10), dist, torch)
     if rank == 0:
         result["aux"] = {"group_by": aux_group, "q1": aux_q1, "hash_join": aux_join}
-    # ---- end to end through the supersonic.h mirror with pinned host buffers
-    e2e_rows = min(args.e2e_rows, rows)
+    # ---- end to end through the supersonic.h mirror with pinned host buffers: the headline table
+    # itself (rows per GPU x 4 read columns = 32 GB of pinned host memory per rank) when the box has
+    # the memory, else the largest table that leaves half of the available RAM free
+    e2e_rows = rows if args.e2e_rows <= 0 else min(args.e2e_rows, rows)
+    try:
+        import psutil
+        budget = psutil.virtual_memory().available // (2 * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+        fit = int(budget // 32) // (1 << 22) * (1 << 22)
+        if fit < e2e_rows:
+            e2e_rows = max(1 << 22, fit)
+    except Exception:
+        pass
     host = {}
+    gen_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
     for name in "abcd":
         p = ctx.malloc_host(e2e_rows * 8)
         arr = np.ctypeslib.as_array((C.c_int64 * e2e_rows).from_address(p))
-        arr[:] = host_column(capi, name, e2e_rows, first)
+        fill_host_column(capi, name, arr, first, gen_threads)
         host[name] = (p, arr)
     plan_lib = ssplan.PlanLib(os.path.join(ROOT, "supersonic_b200", "lib", "libssb200_plan.so"))
     cols = [ssplan.Column(nm, ssplan.INT64, host[nm][1]) for nm in "abcd"]
     for c, nm in zip(cols, "abcd"):
         c.data = host[nm][1]            # keep the pinned buffer (no numpy copy)
-    e2e_s = []
+    e2e_steps = max(1, args.steps if args.e2e_steps <= 0 else args.e2e_steps)
     e2e_kept = 0
-    moved0 = None
-    for i in range(1 + args.e2e_steps):
-        if i == 1:   # bytes actually moved over PCIe in the timed runs (ssb_memcpy_h2d / d2h counters)
-            moved0 = (C.c_uint64(), C.c_uint64())
-            capi.load().ssb_transfer_bytes(C.byref(moved0[0]), C.byref(moved0[1]))
-        barrier()
-        t0 = time.perf_counter()
+    moved0 = (C.c_uint64(), C.c_uint64())
+
+    def e2e_step():
         r = plan_lib.run(PLAN, [cols], next_max_rows=1 << 22, flags=ssplan.SSPLAN_DISCARD)
-        dt = time.perf_counter() - t0
         if r.code != 0:
             raise RuntimeError("e2e plan failed: %d %s" % (r.code, r.error))
-        e2e_kept = r.rows
-        if i > 0:
-            e2e_s.append(dt)
-    e2e_t = float(np.mean(e2e_s))
+        return r.rows
+
+    e2e_step()                           # one untimed pass (program compilation, lane buffers)
+    capi.load().ssb_transfer_bytes(C.byref(moved0[0]), C.byref(moved0[1]))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_kept = e2e_step()            # every step: H2D of the inputs, kernel, D2H of the kept rows, drained to the end
+    barrier()
+    e2e_t = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
         t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
     moved1 = (C.c_uint64(), C.c_uint64())
     capi.load().ssb_transfer_bytes(C.byref(moved1[0]), C.byref(moved1[1]))
-    h2d_step = (moved1[0].value - moved0[0].value) // max(1, args.e2e_steps)
-    d2h_step = (moved1[1].value - moved0[1].value) // max(1, args.e2e_steps)
+    h2d_step = (moved1[0].value - moved0[0].value) // e2e_steps
+    d2h_step = (moved1[1].value - moved0[1].value) // e2e_steps
+    for name in "abcd":
+        ctx.free_host(host[name][0])
     if rank == 0:
-        result["e2e"] = {"value": world * e2e_rows / e2e_t, "unit": "rows/s", "rows_per_gpu": e2e_rows,
+        result["e2e"] = {"value": world * e2e_rows / e2e_t, "unit": "rows/s", "rows_per_gpu": e2e_rows, "steps": e2e_steps,
+                         "kept_rows_per_gpu": int(e2e_kept), "seconds_per_step": e2e_t,
                          "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                          "host_bytes_per_step": int(e2e_rows * 32),
                          "api": "supersonic::Filter/Compute/ScanView cursors via the plan driver, pinned host views",
                          "transfer": "64-bit integer columns whose chunk fits 32 bits cross PCIe as 32-bit values "
                                      "(host threads narrow and verify every value, the kernel widens them: lossless); "
-                                     "h2d/d2h bytes are the copies actually issued"}
+                                     "only the kept rows come back; h2d/d2h bytes are the copies actually issued"}
         # ---- CPU baseline: the reference itself, one thread, bounded sample
         result["cpu_baseline"] = cpu_reference_sample(args.cpu_rows, threads=1)
         emit(json.dumps(result))
@@ -516,11 +610,32 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+_M64 = (1 << 64) - 1
+
+
+def np_column(name, rows, first_row=0):
+    """The same synthetic column as ssb_generate / ssb_generate_host (kind 0), in numpy: the reference arm
+    loads nothing of this repo's native code."""
+    kind, lo, span = GEN[name]
+    assert kind == 0
+    with np.errstate(over="ignore"):
+        x = np.arange(first_row, first_row + rows, dtype=np.uint64)
+        x += np.uint64((SEED ^ ((COLS.index(name) * 0x9E3779B97F4A7C15) & _M64)) & _M64)
+        x += np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+        if span:
+            x &= np.uint64(span - 1)
+        x += np.uint64(lo & _M64)
+    return x.view(np.int64)
+
+
 def _ref_worker(arg):
     rows, first = arg
-    from supersonic_b200 import capi, ssplan
+    from supersonic_b200 import ssplan
     ref = ssplan.PlanLib(os.path.join(ROOT, "oracle", "_ref", "libssref.so"))
-    cols = [ssplan.Column(nm, ssplan.INT64, host_column(capi, nm, rows, first)) for nm in "abcd"]
+    cols = [ssplan.Column(nm, ssplan.INT64, np_column(nm, rows, first)) for nm in "abcd"]
     best = None
     for _ in range(3):
         r = ref.run(PLAN, [cols], next_max_rows=1024, flags=ssplan.SSPLAN_DISCARD)
@@ -563,12 +678,14 @@ def run_reference(args):
         base = cpu_reference_sample(args.cpu_rows, threads=cores)
         values.append(base["value"])
     v = float(np.mean(values))
-    out = {"impl": "reference", "metric": "rows/sec, filter+project (Compute a*b+c, Filter d<K) over 8xINT64 rows",
+    out = {"impl": "reference", "metric": METRIC,
            "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": cores * args.cpu_rows / v * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-           "config": {"workload": "C2 variant A plan on the reference's CPU cursors: %d independent single-thread "
-                                  "cursors (the engine is single-threaded), %d rows each" % (cores, args.cpu_rows)},
+           "config": {"workload": workload(args.rows), "rows_per_gpu": args.rows,
+                      "sample": "the reference's own CPU cursors over a bounded sample of that table: %d independent "
+                                "single-thread cursors (the engine is single-threaded), %d rows each, Next(1024) drain"
+                                % (cores, args.cpu_rows)},
            "cpu_baseline": dict(base, value=v),
            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -601,8 +718,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (BASELINE C2: 1e9)")
-    ap.add_argument("--e2e-rows", type=int, default=1 << 26)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per GPU of the end-to-end leg (0 = --rows, bounded by host RAM)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the end-to-end leg (0 = --steps)")
     ap.add_argument("--cpu-rows", type=int, default=20_000_000)
     ap.add_argument("--group-rows", type=int, default=1_000_000_000, help="rows per GPU of the aux group-by")
     ap.add_argument("--q1-rows", type=int, default=600_000_000, help="rows per GPU of the aux Q1-shape plan (C5: 6e8)")

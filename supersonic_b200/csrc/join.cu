@@ -137,10 +137,12 @@ __global__ void __launch_bounds__(256) join_build_kernel(JoinTable t, JoinKeys b
 // a concurrent reader may compare keys against either row of the same key - both are equal.
 
 __global__ void run_bounds_kernel(const unsigned long long* __restrict__ sorted_slots, long long n_valid,
-                                  unsigned long long* __restrict__ run_start, unsigned int* __restrict__ run_count) {
+                                  unsigned long long capacity, unsigned long long* __restrict__ run_start,
+                                  unsigned int* __restrict__ run_count) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_valid; i += stride) {
     const unsigned long long s = sorted_slots[i];
+    if (s >= capacity) continue;   // NULL-key marker (== capacity): owns no run, and the arrays hold capacity entries
     if (i == 0 || sorted_slots[i - 1] != s) run_start[s] = static_cast<unsigned long long>(i);
     atomicAdd(&run_count[s], 1u);
   }
@@ -423,7 +425,7 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
       rc = radix_sort_pairs(ctx, &k0, &v0, &k1, &v1, static_cast<unsigned long long>(rows), 0, bits);
       if (rc == 0) {
         // rows with NULL keys (marker cap) sort last and own no run
-        run_bounds_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(k0, rows, j->table.run_start, j->table.run_count);
+        run_bounds_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(k0, rows, cap, j->table.run_start, j->table.run_count);
         ++ctx->launches;
       }
       j->table.run_rows = v0;

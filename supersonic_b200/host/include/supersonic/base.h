@@ -203,11 +203,15 @@ inline void SucceedOrDie(FailureOrVoid r) { if (r.is_failure()) DieOnFailure(r.e
 #define THROW(exception_ptr)                                                              \
   return ::supersonic::Failure((exception_ptr)->AddStackTraceElement(__FUNCTION__, __FILE__, \
                                                                      __LINE__, "(thrown here)"))
+// `result` is evaluated exactly once (it may be a call: a second evaluation would run the call
+// again and, if that succeeded, dereference a NULL exception).
 #define PROPAGATE_ON_FAILURE(result)                                                       \
   do {                                                                                     \
-    if ((result).is_failure()) {                                                           \
-      return ::supersonic::Failure((result).release_exception()->AddStackTraceElement(     \
-          __FUNCTION__, __FILE__, __LINE__, #result));                                     \
+    auto&& propagated_result_ = (result);                                                  \
+    if (propagated_result_.is_failure()) {                                                 \
+      return ::supersonic::Failure(propagated_result_.release_exception()                  \
+                                       ->AddStackTraceElement(__FUNCTION__, __FILE__,      \
+                                                              __LINE__, #result));         \
     }                                                                                      \
   } while (0)
 

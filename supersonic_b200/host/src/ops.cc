@@ -285,6 +285,13 @@ class RowwiseCursor : public GpuCursor {
       const int frc = ssb_program_check_failure(l.launched ? l.launched : l.program);
       if (frc != 0) return ResultView::Failure(Session::ErrorOn(l.ctx, frc, "expression evaluation"));
       l.kept = *l.h_count;
+      if (!l.fetched) {
+        FailureOrVoid q = QueueOutputs(&l, static_cast<rowcount_t>(l.kept));
+        if (q.is_failure()) return ResultView::Failure(q.release_exception());
+        const int rc2 = ssb_ctx_sync(l.ctx);
+        if (rc2 != 0) return ResultView::Failure(Session::ErrorOn(l.ctx, rc2, "row-wise pipeline (download)"));
+        l.fetched = true;
+      }
       served_ = 0;
     }
   }
@@ -374,7 +381,8 @@ class RowwiseCursor : public GpuCursor {
     int64_t* h_count;
     int64 kept;
     bool busy;
-    void Reset() { ctx = NULL; program = NULL; launched = NULL; d_bools = NULL; d_count = NULL; h_count = NULL; kept = 0; busy = false; }
+    bool fetched;   // the chunk's output rows are (being) copied to the host
+    void Reset() { ctx = NULL; program = NULL; launched = NULL; d_bools = NULL; d_count = NULL; h_count = NULL; kept = 0; busy = false; fetched = false; }
     void Free() {
       if (ctx == NULL) return;
       ssb_ctx_sync(ctx);
@@ -570,18 +578,32 @@ class RowwiseCursor : public GpuCursor {
     LANE_CALL(l, ssb_program_run(program, ic.empty() ? &dummy : ic.data(), static_cast<int64_t>(rows),
                                  oc.empty() ? &dummy : oc.data(), l.d_count), "expression evaluation");
     LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_count, l.d_count, sizeof(int64_t)), "download");
-    for (size_t j = 0; j < oc.size(); ++j) {
-      const size_t w = GetTypeInfo(plan_.schema.attribute(static_cast<int>(j)).type()).size();
-      // the kept-row count is not known on the host yet: copy the chunk's capacity
-      LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_out[j], l.d_out[j], rows * w), "download");
-      if (plan_.schema.attribute(static_cast<int>(j)).is_nullable() &&
-          ssb_program_output_nullable(l.program, static_cast<int32_t>(j))) {
-        LANE_CALL(l, ssb_nulls_unpack(l.ctx, static_cast<const uint32_t*>(l.d_out_nulls[j]), static_cast<int64_t>(rows),
-                                      static_cast<uint8_t*>(l.d_bools)), "null unpack");
-        LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_out_nulls[j], l.d_bools, rows), "download nulls");
-      }
+    // Without a predicate every row is kept: the outputs can follow the kernel at once. With one, the
+    // kept-row count is not known on the host yet; Next() fetches exactly the kept rows once it is
+    // (copying the chunk's capacity instead moved twice the bytes at selectivity 0.5).
+    l.fetched = false;
+    if (!plan_.predicate) {
+      PROPAGATE_ON_FAILURE(QueueOutputs(&l, rows));
+      l.fetched = true;
     }
     l.busy = true;
+    return Success();
+  }
+
+  // Queues the D2H copies of the first `kept` rows of every output column of the lane's chunk.
+  FailureOrVoid QueueOutputs(Lane* lane, rowcount_t kept) {
+    Lane& l = *lane;
+    if (kept == 0) return Success();
+    for (size_t j = 0; j < l.d_out.size(); ++j) {
+      const size_t w = GetTypeInfo(plan_.schema.attribute(static_cast<int>(j)).type()).size();
+      LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_out[j], l.d_out[j], kept * w), "download");
+      if (plan_.schema.attribute(static_cast<int>(j)).is_nullable() &&
+          ssb_program_output_nullable(l.program, static_cast<int32_t>(j))) {
+        LANE_CALL(l, ssb_nulls_unpack(l.ctx, static_cast<const uint32_t*>(l.d_out_nulls[j]), static_cast<int64_t>(kept),
+                                      static_cast<uint8_t*>(l.d_bools)), "null unpack");
+        LANE_CALL(l, ssb_memcpy_d2h(l.ctx, l.h_out_nulls[j], l.d_bools, kept), "download nulls");
+      }
+    }
     return Success();
   }
 #undef LANE_CALL

@@ -340,6 +340,26 @@ class Compiler {
     for (int j = 0; j < n_out; ++j) {
       const int node = outputs[j];
       const ssb_expr_node& nd = nodes_[node];
+      if (sink_bytes_) {
+        // aggregation sink: nothing is staged. The sink reads the value from the slot that holds it
+        // -- the input column itself for a pass-through output, else a temporary kept for the tile.
+        int owned;
+        Ref r = Materialize(node, &owned);
+        if (r.imm) {   // a constant output: give it a slot
+          EmitLoad(r);
+          r.idx = EmitStore(node);
+          r.imm = false;
+        }
+        sink_slot_[j] = r.idx;
+        p.sink_src_slot[j] = static_cast<int16_t>(r.idx);
+        p.sink_src_w[j] = static_cast<uint8_t>(phys_width(r.phys));
+        p.sink_src_nullable[j] = r.nullable ? 1 : 0;
+        p.out_width[j] = static_cast<uint8_t>(phys_width(info_[node].phys));
+        p.out_nullable[j] = info_[node].nullable ? 1 : 0;
+        prog_->out_types.push_back(nd.out_type);
+        prog_->out_nullable.push_back(info_[node].nullable ? 1 : 0);
+        continue;
+      }
       Gen(node);
       Insn in;
       memset(&in, 0, sizeof(in));
@@ -430,6 +450,9 @@ class Compiler {
       }
     }
     AssignFastCodes();
+    if (sink_bytes_) {
+      for (int j = 0; j < n_out; ++j) p.sink_src_off[j] = SlotOffset(sink_slot_[j], true);
+    }
     return 0;
   }
 
@@ -456,6 +479,10 @@ class Compiler {
           if (in.rw == 8) in.code = C_OUT8; else if (in.rw == 4) in.code = C_OUT4;
           break;
         case K_PRED: in.code = C_PRED; break;
+        case K_STORE:
+          if (in.rhs_nullable & 1) break;
+          if (in.rw == 8) in.code = C_STORE8; else if (in.rw == 4) in.code = C_STORE4;
+          break;
         case K_ALU2: {
           if (!rhs_clean) break;
           if (!imm && in.rw != phys_width(in.t)) break;
@@ -552,6 +579,7 @@ class Compiler {
 
  private:
   uint32_t mad_left_[kMaxInsn + 1];
+  int sink_slot_[kMaxOut] = {0};
   struct Info {
     int phys;
     bool nullable;

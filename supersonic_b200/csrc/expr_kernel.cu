@@ -110,6 +110,78 @@ struct __align__(16) TabEntry {
 };
 static constexpr uint32_t kCodeEnd = 0xffffu;
 
+// ---- aggregation sink: CTA-local state ----------------------------------------------------------
+// The CTA learns its (few) groups on the fly: the first row of a group goes through the global
+// table (find_slot_*), claims the next local entry and publishes its key values; later rows find
+// the entry by comparing their keys with the published ones (held in registers for the tile).
+// Every thread owns a private accumulator per (local group, aggregate) -- [group][aggregate][thread]:
+// bank = thread, no conflicts, no atomics in the row loop.
+struct SinkShared {
+  unsigned long long* t_acc;
+  unsigned long long* l_key;
+  unsigned int* l_knull;
+  unsigned int* l_slot;
+  unsigned int* l_ready;
+  unsigned char* t_seen;
+};
+// Layout of the sink area (must match sink_bytes_per_thread / sink_fixed_bytes on the host).
+__device__ __forceinline__ SinkShared sink_layout(unsigned char* base, int SG, int SA, int NT) {
+  SinkShared sk;
+  sk.t_acc = reinterpret_cast<unsigned long long*>(base);                     // [(SG + 1) * SA][NT], block SG = trash
+  sk.l_key = sk.t_acc + (SG + 1) * SA * NT;                                   // [kTinyGroups][2] key values of the local entries
+  sk.l_knull = reinterpret_cast<unsigned int*>(sk.l_key + kTinyGroups * 2);   // [kTinyGroups] bit c: key column c is NULL
+  sk.l_slot = sk.l_knull + kTinyGroups;                                       // [kTinyGroups] global slot + 1, 0 = free
+  sk.l_ready = sk.l_slot + kTinyGroups;                                       // [1] bit e: entry e is published
+  sk.t_seen = reinterpret_cast<unsigned char*>(sk.l_ready + 4);               // [(SG + 1) * SA][NT]
+  return sk;
+}
+// Identity of a thread's partial. Sums start from the value that addition leaves exact (-0.0 for
+// floating point: -0.0 + x == x for every x, +0.0 would turn a sum of -0.0 into +0.0).
+__device__ __forceinline__ unsigned long long sink_identity(const AggDev& ag) {
+  if (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) return 0x8000000000000000ull;
+  if (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F32) return 0x80000000ull;
+  return identity_dev(ag);
+}
+__device__ __forceinline__ long long sink_global_slot(const GroupParams& gp, unsigned long long k0, unsigned long long k1, unsigned int knull) {
+  if (gp.packed) return find_slot_packed_kv(gp, (knull & 1u) != 0, k0);
+  unsigned long long kv[kMaxKeys];
+  kv[0] = k0; kv[1] = k1;
+  return find_slot_generic_kv(gp, kv, knull);
+}
+// Cold path of the group lookup (first sight of a key in this CTA). Returns the local entry, -1
+// when the CTA has no free entry (the row goes to the global table), -2 when the global table is
+// full (the row is deferred).
+__device__ __noinline__ int sink_insert(const GroupParams& gp, unsigned char* sink_base, int SA, int NT, int n_local,
+                                        unsigned long long k0, unsigned long long k1, unsigned int knull) {
+  const SinkShared sk = sink_layout(sink_base, n_local, SA, NT);
+  const long long slot = sink_global_slot(gp, k0, k1, knull);
+  if (slot < 0) return -2;
+  const unsigned int want = static_cast<unsigned int>(slot) + 1u;
+  for (int e = 0; e < n_local && e < kTinyGroups; ++e) {
+    const unsigned int old = atomicCAS(&sk.l_slot[e], 0u, want);
+    if (old == 0u) {
+      sk.l_key[2 * e] = k0;
+      sk.l_key[2 * e + 1] = k1;
+      sk.l_knull[e] = knull;
+      __threadfence_block();
+      atomicOr(sk.l_ready, 1u << e);
+      return e;
+    }
+    if (old == want) return e;
+  }
+  return -1;
+}
+
+// Cold path: a row whose group has no local entry in this CTA goes to the global table.
+__device__ __noinline__ void sink_apply_global(const GroupParams& gp, int a, unsigned long long k0, unsigned long long k1,
+                                               unsigned int knull, unsigned long long v, bool count_star) {
+  const long long slot = sink_global_slot(gp, k0, k1, knull);
+  const AggDev& ag = gp.agg[a];
+  if (count_star) { atomicAdd(&ag.acc[static_cast<unsigned long long>(slot) * ag.stride], 1ull); return; }
+  apply(ag, slot, v, 1ull);
+  if (ag.seen != nullptr) ag.seen[slot] = 1u;
+}
+
 // SINK: the outputs (group-by keys, then aggregate inputs) feed the aggregation table of group.cu
 // directly -- per-thread accumulators in shared memory for the CTA's first `sink_groups` groups,
 // the global table beyond -- instead of being staged, compacted and copied out. Filter then
@@ -172,24 +244,20 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
     }
     itab[e] = t;
   }
-  // ---- aggregation sink state (thread-private words are indexed [..][thread])
+  // ---- aggregation sink state (thread-private words are indexed [..][thread]); layout = sink_layout() below
   const GroupParams* gp = static_cast<const GroupParams*>(p.sink_gp);
   const int SG = p.sink_groups, SA = p.sink_n_aggs, SNK = p.sink_n_keys;
-  unsigned long long* t_acc = reinterpret_cast<unsigned long long*>(smem + p.sink_off);      // [SG * SA][NT]
-  unsigned long long* s_key = t_acc + SG * SA * NT;                                          // [SNK][R][NT]
-  unsigned long long* l_key = s_key + SNK * R * NT;                                          // [kTinyGroups][kMaxKeys]
-  unsigned long long* l_fp = l_key + kTinyGroups * kMaxKeys;                                 // [kTinyGroups]
-  unsigned int* t_seen = reinterpret_cast<unsigned int*>(l_fp + kTinyGroups);                // [SG][NT]
-  unsigned int* s_keyn = t_seen + SG * NT;                                                   // [SNK][NT]
-  unsigned int* l_knull = s_keyn + SNK * NT;                                                 // [kTinyGroups]
-  unsigned int* l_slot = l_knull + kTinyGroups;                                              // [kTinyGroups]
-  unsigned int* l_ready = l_slot + kTinyGroups;                                              // [1]
+  const SinkShared sk = sink_layout(smem + p.sink_off, SG, SA, NT);
+  const uint32_t sink_block = static_cast<uint32_t>(SA) * NT * 8u;                            // bytes of one group's accumulators
+  const uint32_t sink_trash = static_cast<uint32_t>(SG) * sink_block;
   if constexpr (SINK) {
     if (tid < NT) {
-      for (int i = tid; i < SG * SA * NT; i += NT) t_acc[i] = identity_dev(gp->agg[(i / NT) % SA]);
-      for (int i = tid; i < SG * NT; i += NT) t_seen[i] = 0u;
-      if (tid < kTinyGroups) l_slot[tid] = 0u;
-      if (tid == 0) *l_ready = 0u;
+      for (int i = tid; i < (SG + 1) * SA * NT; i += NT) {
+        sk.t_acc[i] = sink_identity(gp->agg[(i / NT) % SA]);
+        sk.t_seen[i] = 0;
+      }
+      if (tid < kTinyGroups) sk.l_slot[tid] = 0u;
+      if (tid == 0) *sk.l_ready = 0u;
     }
   }
   __syncthreads();
@@ -365,109 +433,7 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
 #pragma unroll
       for (int k = 0; k < R; ++k) { acc[k] = 0; pos[k] = row_first + 32 * k; }
 
-      // ---- aggregation sink: group of every row of this thread (4 bits each: local entry, 15 =
-      // the row goes to the global table), resolved once the key outputs are known. At most two
-      // key columns, every aggregate COUNT or with equal input and result type (host-checked).
-      unsigned long long gids = 0;
-      bool resolved = false;
-      auto sink_slot_of = [&](int k, unsigned long long k0, unsigned long long k1, unsigned int knull) -> long long {
-        if (gp->packed) return find_slot_packed_kv(*gp, (knull & 1u) != 0, k0);
-        unsigned long long kv[kMaxKeys];
-        kv[0] = k0; kv[1] = k1;
-        return find_slot_generic_kv(*gp, kv, knull);
-      };
-      auto sink_keys_of = [&](int k, unsigned long long& k0, unsigned long long& k1, unsigned int& knull) {
-        k0 = k1 = 0; knull = 0;
-        if (SNK > 0) { if ((s_keyn[tid] >> k) & 1u) knull |= 1u; else k0 = s_key[k * NT + tid]; }
-        if (SNK > 1) { if ((s_keyn[NT + tid] >> k) & 1u) knull |= 2u; else k1 = s_key[(R + k) * NT + tid]; }
-      };
-      auto sink_resolve = [&]() {
-        resolved = true;
-        const unsigned int my_ready = *reinterpret_cast<volatile unsigned int*>(l_ready);
-#pragma unroll 1
-        for (int k = 0; k < R; ++k) {
-          if (!((pass >> k) & 1u)) continue;
-          unsigned long long k0, k1;
-          unsigned int knull;
-          sink_keys_of(k, k0, k1, knull);
-          const unsigned long long fp = ((0x9E3779B97F4A7C15ull + knull) ^ k0) * 0xff51afd7ed558ccdULL + (k1 ^ (k1 >> 29)) * 0xc4ceb9fe1a85ec53ULL;
-          int g = -1;
-#pragma unroll
-          for (int e = 0; e < kTinyGroups; ++e) {   // published fingerprints: broadcast reads
-            if (((my_ready >> e) & 1u) && *reinterpret_cast<volatile unsigned long long*>(&l_fp[e]) == fp) g = e;
-          }
-          if (g >= 0 && !(l_knull[g] == knull && l_key[g * kMaxKeys] == k0 && l_key[g * kMaxKeys + 1] == k1)) g = -1;
-          if (g < 0) {
-            const long long slot = sink_slot_of(k, k0, k1, knull);
-            if (slot < 0) {   // table full: the host grows it and replays this row
-              const unsigned long long d = atomicAdd(gp->n_deferred, 1ull);
-              gp->deferred[d] = row0 + row_first + 32 * k;
-              pass &= ~(1u << k);
-              continue;
-            }
-            const unsigned int want = static_cast<unsigned int>(slot) + 1u;
-            for (int e = 0; e < SG && g < 0; ++e) {
-              const unsigned int old = atomicCAS(&l_slot[e], 0u, want);
-              if (old == 0u) {
-                l_key[e * kMaxKeys] = k0;
-                l_key[e * kMaxKeys + 1] = k1;
-                l_knull[e] = knull;
-                l_fp[e] = fp;
-                __threadfence_block();
-                atomicOr(l_ready, 1u << e);
-                g = e;
-              } else if (old == want) {
-                g = e;
-              }
-            }
-            if (g < 0) g = 15;
-          }
-          gids |= static_cast<unsigned long long>(g) << (4 * k);
-          // COUNT(*) aggregates count the row here
-          for (uint32_t m = p.sink_count_star; m; m &= m - 1) {
-            const int a = __ffs(m) - 1;
-            if (g < 15) t_acc[(g * SA + a) * NT + tid] += 1ull;
-            else atomicAdd(&gp->agg[a].acc[static_cast<unsigned long long>(sink_slot_of(k, k0, k1, knull)) * gp->agg[a].stride], 1ull);
-          }
-        }
-      };
-      // output column j of the program = key column j, or the input of the aggregates in sink_out_aggs[j]
-      auto sink_output = [&](int j, uint32_t nulls) {
-        if (j < SNK) {
-#pragma unroll
-          for (int k = 0; k < R; ++k) s_key[(j * R + k) * NT + tid] = acc[k];
-          s_keyn[j * NT + tid] = nulls;
-          return;
-        }
-        if (!resolved) sink_resolve();
-        const uint32_t valid = pass & ~nulls;
-        for (uint32_t m = p.sink_out_aggs[j]; m; m &= m - 1) {
-          const int a = __ffs(m) - 1;
-          const uint32_t code = (p.sink_pad >> (2 * a)) & 3u;
-          unsigned long long* const base = t_acc + a * NT + tid;
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            if (!((valid >> k) & 1u)) continue;
-            const int g = static_cast<int>((gids >> (4 * k)) & 15u);
-            if (g == 15) {   // a group beyond the CTA's local entries: the global table
-              unsigned long long k0, k1;
-              unsigned int knull;
-              sink_keys_of(k, k0, k1, knull);
-              const long long slot = sink_slot_of(k, k0, k1, knull);
-              const AggDev& ag = gp->agg[a];
-              apply(ag, slot, acc[k], 1ull);
-              if (ag.seen != nullptr) ag.seen[slot] = 1u;
-              continue;
-            }
-            unsigned long long* accp = base + g * SA * NT;
-            if (code == TA_SUM_F64) *accp = Codec<double>::enc(Codec<double>::dec(*accp) + Codec<double>::dec(acc[k]));
-            else if (code == TA_SUM_U64) *accp += acc[k];
-            else if (code == TA_COUNT) *accp += 1ull;
-            else *accp = combine(gp->agg[a], *accp, acc[k]);
-            if (code != TA_COUNT) t_seen[g * NT + tid] |= 1u << a;
-          }
-        }
-      };
+      // ---- aggregation sink: runs once per tile, after the program (below)
 
       // +0 acc (op) slot, +1 acc (op) imm, +2 slot (op) slot, +3 slot (op) imm; EXPR sees x, y
 #define SSB_BIN4(CODE0, T, EXPR)                                                         \
@@ -640,14 +606,22 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
               for (int k = 0; k < R; ++k) bits |= static_cast<uint32_t>(acc[k] & 1u) << k;
               post = 2;
             } break;
+            case C_STORE8: {
+              u64* dst = reinterpret_cast<u64*>(smem + cur.x);
+#pragma unroll
+              for (int k = 0; k < R; ++k) dst[row_first + 32 * k] = acc[k];
+            } break;
+            case C_STORE4: {
+              uint32_t* dst = reinterpret_cast<uint32_t*>(smem + cur.x);
+#pragma unroll
+              for (int k = 0; k < R; ++k) dst[row_first + 32 * k] = static_cast<uint32_t>(acc[k]);
+            } break;
             case C_OUT8: {
-              if constexpr (SINK) { sink_output(static_cast<int>(cur.z), 0u); break; }
               u64* dst = reinterpret_cast<u64*>(obuf + cur.x);
 #pragma unroll
               for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = acc[k];
             } break;
             case C_OUT4: {
-              if constexpr (SINK) { sink_output(static_cast<int>(cur.z), 0u); break; }
               uint32_t* dst = reinterpret_cast<uint32_t*>(obuf + cur.x);
 #pragma unroll
               for (int k = 0; k < R; ++k) if ((pass >> k) & 1u) dst[pos[k]] = static_cast<uint32_t>(acc[k]);
@@ -773,7 +747,6 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
           } break;
           case K_OUT: {
             const int j = in.a;
-            if constexpr (SINK) { sink_output(j, accn); break; }
             unsigned char* dst = obuf + p.out_off[j];
             if (in.rw == 8) {
 #pragma unroll
@@ -800,7 +773,151 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
 #undef SSB_BIN_TYPE
 #undef SSB_ENC
       if constexpr (SINK) {
-        if (!resolved) sink_resolve();   // keys and COUNT(*) only: no value output triggered it
+        // ================================================== the aggregation sink of this tile
+        // Every output of the program sits in a shared-memory slot (an input column of this stage or
+        // a temporary). Keys first: the group of each of the thread's R rows, found by comparing the
+        // keys against the CTA's published entries held in registers (branch-free; the first row of a
+        // group, or a row of a group without a local entry, takes the cold path).
+        auto src_load = [&](int j, u64 (&v)[R]) -> uint32_t {   // values of output j for the thread's rows; returns the NULL bits
+          const uint32_t o = p.sink_src_off[j];
+          const unsigned char* base = smem + (o & 0x7fffffffu) + ((o >> 31) ? static_cast<uint32_t>(stage) * p.stage_bytes : 0u);
+          const int w = p.sink_src_w[j];
+          if (w == 8) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = reinterpret_cast<const u64*>(base)[row_first + 32 * k];
+          } else if (w == 4) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = reinterpret_cast<const uint32_t*>(base)[row_first + 32 * k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = base[row_first + 32 * k];
+          }
+          uint32_t nn = 0;
+          if (p.sink_src_nullable[j]) {
+            const uint32_t* wds = slot_nullw(p.sink_src_slot[j], stage);
+            if (wds != nullptr) {
+#pragma unroll
+              for (int k = 0; k < R; ++k) nn |= ((wds[warp * R + k] >> lane) & 1u) << k;
+            }
+          }
+          return nn;
+        };
+        u64 kv0[R], kv1[R];
+        uint32_t kn0 = 0, kn1 = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) { kv0[k] = 0; kv1[k] = 0; }
+        if (SNK > 0) kn0 = src_load(0, kv0);
+        if (SNK > 1) kn1 = src_load(1, kv1);
+        if (kn0 | kn1) {
+#pragma unroll
+          for (int k = 0; k < R; ++k) { if ((kn0 >> k) & 1u) kv0[k] = 0; if ((kn1 >> k) & 1u) kv1[k] = 0; }
+        }
+        const uint32_t ready = *reinterpret_cast<volatile unsigned int*>(sk.l_ready);
+        int gsel[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) gsel[k] = -1;
+#pragma unroll
+        for (int e = 0; e < kTinyGroups; ++e) {
+          if (!((ready >> e) & 1u)) continue;   // CTA-uniform
+          const u64 e0 = sk.l_key[2 * e], e1 = sk.l_key[2 * e + 1];
+          const uint32_t en = sk.l_knull[e];
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
+            if (kv0[k] == e0 && kv1[k] == e1 && kn == en) gsel[k] = e;
+          }
+        }
+        uint32_t goff[R];
+        uint32_t ovf = 0;
+        uint32_t miss = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const bool on = (pass >> k) & 1u;
+          goff[k] = (on && gsel[k] >= 0) ? static_cast<uint32_t>(gsel[k]) * sink_block : sink_trash;
+          miss |= (on && gsel[k] < 0 ? 1u : 0u) << k;
+        }
+        if (miss) {   // cold: first sight of a group in this CTA, or no local entry left for it
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            if (!((miss >> k) & 1u)) continue;
+            const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
+            const int g = sink_insert(*gp, smem + p.sink_off, SA, NT, SG, kv0[k], kv1[k], kn);
+            if (g >= 0) {
+              goff[k] = static_cast<uint32_t>(g) * sink_block;
+            } else if (g == -1) {
+              ovf |= 1u << k;
+            } else {   // the global table is full: the host grows it and replays this row
+              const unsigned long long d = atomicAdd(gp->n_deferred, 1ull);
+              gp->deferred[d] = row0 + row_first + 32 * k;
+              pass &= ~(1u << k);
+            }
+          }
+        }
+        unsigned long long* const acc_tid = sk.t_acc + tid;
+        // COUNT(*) aggregates count the row
+        for (uint32_t m = p.sink_count_star; m; m &= m - 1) {
+          const int a = __ffs(m) - 1;
+          unsigned char* const base = reinterpret_cast<unsigned char*>(acc_tid + a * NT);
+#pragma unroll
+          for (int k = 0; k < R; ++k) *reinterpret_cast<unsigned long long*>(base + goff[k]) += 1ull;
+          if (ovf) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              if (!((ovf >> k) & 1u)) continue;
+              const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
+              sink_apply_global(*gp, a, kv0[k], kv1[k], kn, 0ull, true);
+            }
+          }
+        }
+        // value outputs: output j feeds the aggregates in sink_out_aggs[j]
+        for (int j = SNK; j < p.n_out; ++j) {
+          if (p.sink_out_aggs[j] == 0u) continue;
+          u64 v[R];
+          const uint32_t nulls = src_load(j, v);
+          const uint32_t valid = pass & ~nulls;
+          uint32_t off[R];   // rows without a value (predicate, NULL, overflow) accumulate into the trash block
+#pragma unroll
+          for (int k = 0; k < R; ++k) off[k] = ((valid >> k) & 1u) ? goff[k] : sink_trash;
+          for (uint32_t m = p.sink_out_aggs[j]; m; m &= m - 1) {
+            const int a = __ffs(m) - 1;
+            const uint32_t code = (p.sink_pad >> (2 * a)) & 3u;
+            unsigned char* const base = reinterpret_cast<unsigned char*>(acc_tid + a * NT);
+            if (code != TA_OTHER && code != TA_COUNT && ((p.sink_seen_mask >> a) & 1u)) {   // nullable input: all-NULL groups stay NULL
+#pragma unroll
+              for (int k = 0; k < R; ++k) sk.t_seen[(reinterpret_cast<unsigned long long*>(base + off[k]) - sk.t_acc)] = 1;
+            }
+            if (code == TA_SUM_F64) {
+#pragma unroll
+              for (int k = 0; k < R; ++k) {
+                unsigned long long* q = reinterpret_cast<unsigned long long*>(base + off[k]);
+                *q = Codec<double>::enc(Codec<double>::dec(*q) + Codec<double>::dec(v[k]));
+              }
+            } else if (code == TA_SUM_U64) {
+#pragma unroll
+              for (int k = 0; k < R; ++k) *reinterpret_cast<unsigned long long*>(base + off[k]) += v[k];
+            } else if (code == TA_COUNT) {
+#pragma unroll
+              for (int k = 0; k < R; ++k) *reinterpret_cast<unsigned long long*>(base + off[k]) += 1ull;
+            } else {
+              const AggDev& ag = gp->agg[a];
+#pragma unroll
+              for (int k = 0; k < R; ++k) {
+                unsigned long long* q = reinterpret_cast<unsigned long long*>(base + off[k]);
+                unsigned char* sn = sk.t_seen + (q - sk.t_acc);
+                *q = *sn ? combine(ag, *q, v[k]) : v[k];   // the first value is taken as it is (NaN, -0.0)
+                *sn = 1;
+              }
+            }
+            if (ovf & valid) {   // groups beyond the CTA's local entries: the global table
+#pragma unroll
+              for (int k = 0; k < R; ++k) {
+                if (!(((ovf & valid) >> k) & 1u)) continue;
+                const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
+                sink_apply_global(*gp, a, kv0[k], kv1[k], kn, v[k], false);
+              }
+            }
+          }
+        }
       }
     }
     if (scan_wave) finish_wave();
@@ -894,29 +1011,39 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
   }
   if constexpr (SINK) {
     // flush: the threads' partials of every (local group, aggregate) are combined by one warp and
-    // applied to the global table once per CTA
+    // applied to the global table once per CTA. Accumulators of the SUM / COUNT codes start from an
+    // identity that adding leaves exact (0, -0.0), so untouched partials need no bookkeeping; the
+    // others (MIN / MAX, narrow sums) carry a seen byte per partial.
     bar_consumers<NT>();
     for (int ga = warp; ga < SG * SA; ga += NW) {
       const int g = ga / SA, a = ga - g * SA;
-      if (l_slot[g] == 0u) continue;
+      if (sk.l_slot[g] == 0u) continue;
       const AggDev& ag = gp->agg[a];
-      unsigned long long acc2 = 0;
-      bool has = false;
+      const uint32_t code = (p.sink_pad >> (2 * a)) & 3u;
+      const bool track = code == TA_OTHER || ((p.sink_seen_mask >> a) & 1u);   // partials carry a seen byte
+      unsigned long long acc2 = code == TA_OTHER ? 0ull : sink_identity(ag);
+      bool has = code != TA_OTHER;
+      unsigned int any = 0;
       for (int t = lane; t < NT; t += 32) {
-        const unsigned long long x = t_acc[ga * NT + t];
-        if (ag.fn == SSB_AGG_COUNT) { acc2 += x; }
-        else if ((t_seen[g * NT + t] >> a) & 1u) { acc2 = has ? combine(ag, acc2, x) : x; has = true; }
+        const unsigned long long x = sk.t_acc[ga * NT + t];
+        const unsigned int sn = track ? sk.t_seen[ga * NT + t] : 1u;
+        any |= sn;
+        if (code == TA_COUNT || code == TA_SUM_U64) acc2 += x;
+        else if (code == TA_SUM_F64) acc2 = Codec<double>::enc(Codec<double>::dec(acc2) + Codec<double>::dec(x));
+        else if (sn) { acc2 = has ? combine(ag, acc2, x) : x; has = true; }
       }
       for (int d = 16; d > 0; d >>= 1) {
         const unsigned long long ov = __shfl_xor_sync(0xffffffffu, acc2, d);
         const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, d) != 0;
-        if (ag.fn == SSB_AGG_COUNT) acc2 += ov;
+        any |= __shfl_xor_sync(0xffffffffu, any, d);
+        if (code == TA_COUNT || code == TA_SUM_U64) acc2 += ov;
+        else if (code == TA_SUM_F64) acc2 = Codec<double>::enc(Codec<double>::dec(acc2) + Codec<double>::dec(ov));
         else if (oh) { acc2 = has ? combine(ag, acc2, ov) : ov; has = true; }
       }
       if (lane != 0) continue;
-      const long long slot = static_cast<long long>(l_slot[g] - 1u);
+      const long long slot = static_cast<long long>(sk.l_slot[g] - 1u);
       if (ag.fn == SSB_AGG_COUNT) { if (acc2) atomicAdd(&ag.acc[static_cast<unsigned long long>(slot) * ag.stride], acc2); continue; }
-      if (!has) continue;
+      if (!has || !any) continue;   // no value of this aggregate reached the group in this CTA (all NULL)
       if (ag.seen != nullptr) ag.seen[slot] = 1u;
       apply(ag, slot, acc2, 0ull);
     }
@@ -955,7 +1082,7 @@ static const Variant kVariants[] = {
     {128, 16, expr_kernel<128, 16>, nullptr},
     {64, 16, expr_kernel<64, 16>, nullptr},
     {128, 4, expr_kernel<128, 4>, nullptr},
-    {64, 8, expr_kernel<64, 8>, nullptr},
+    {64, 8, expr_kernel<64, 8>, expr_sink_kernel<64, 8>},
     {96, 8, expr_kernel<96, 8>, expr_sink_kernel<96, 8>},
     {96, 4, expr_kernel<96, 4>, expr_sink_kernel<96, 4>},
 };
@@ -1045,10 +1172,11 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
 // Shared memory of the sink per consumer thread / fixed part (must match the pointer arithmetic at
 // the top of the kernel).
 static uint32_t sink_bytes_per_thread(int n_keys, int n_aggs, int groups, int rows_per_thread) {
-  return static_cast<uint32_t>((groups * n_aggs + n_keys * rows_per_thread) * 8 + (groups + n_keys) * 4);
+  (void)n_keys; (void)rows_per_thread;
+  return static_cast<uint32_t>((groups + 1) * n_aggs * 9);   // accumulator + seen byte per (group incl. trash, aggregate)
 }
 static uint32_t sink_fixed_bytes() {
-  return static_cast<uint32_t>(kTinyGroups * kMaxKeys * 8 + kTinyGroups * 8 + kTinyGroups * 4 * 2 + 16 + 64);
+  return static_cast<uint32_t>(kTinyGroups * 2 * 8 + kTinyGroups * 4 * 2 + 16 + 64);
 }
 
 // Compiles (once per shape) the twin of `base` whose outputs feed the aggregation sink.
@@ -1061,7 +1189,10 @@ int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_
   base->sink = nullptr;
   const Program& bp = base->prog;
   struct Try { int variant, ctas; };
-  const Try tries[] = {{7, 3}, {7, 2}, {8, 3}, {8, 2}, {7, 1}, {8, 1}};
+  // 512-row tiles of 64 consumer threads x 8 rows first: eight rows per thread amortise the
+  // interpreter's dispatch, the small tile leaves room for two or three resident CTAs next to the
+  // per-thread accumulators (the kernel is bound by instruction issue and latency, not by bytes)
+  const Try tries[] = {{6, 3}, {6, 2}, {7, 2}, {8, 3}, {8, 2}, {6, 1}, {7, 1}, {8, 1}};
   ssb_program* best = nullptr;
   long long best_score = -1;
   std::string err;
@@ -1086,9 +1217,15 @@ int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_
     // bytes in flight per SM (three stages are enough), more resident CTAs (= consumer warps) on a tie
     const long long score = static_cast<long long>(stages >= 2 ? (stages > 3 ? 3 : stages) : 0) * (resident < 1 ? 1 : resident) *
                                 cand->prog.params.tile * 16 + (resident < 1 ? 1 : resident);
+    // the tries are in order of preference: the first one with two stages and two resident CTAs is taken
+    if (stages >= 2 && resident >= 2) { delete best; best = cand; break; }
     if (score > best_score) { delete best; best = cand; best_score = score; } else { delete cand; }
   }
   if (best == nullptr) return fail(ctx, rc, err);
+  if (getenv("SSB200_DEBUG_PLAN")) {
+    fprintf(stderr, "[ssb200] sink plan: variant %d (tile %d), %d stages, %u bytes of shared memory per CTA\n", best->prog.variant,
+            best->prog.params.tile, best->prog.params.stages, best->prog.smem_bytes);
+  }
   const Variant& var = kVariants[best->prog.variant];
   cudaError_t e = cudaFuncSetAttribute(var.sink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
   int occ = 0;
@@ -1104,7 +1241,8 @@ int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_
 // Launches the sink kernel of `sp` (from sink_program_for) over `rows` rows. d_gp: the table's
 // GroupParams in device memory; out_aggs[j]: aggregates fed by output j; count_star: COUNT(*) mask.
 int launch_program_sink(ssb_program* sp, const ssb_column* inputs, int64_t rows, const void* d_gp, int n_keys,
-                        int n_aggs, int groups, const uint32_t* out_aggs, uint32_t count_star, uint32_t pad_codes) {
+                        int n_aggs, int groups, const uint32_t* out_aggs, uint32_t count_star, uint32_t pad_codes,
+                        uint32_t seen_mask) {
   ssb_ctx* ctx = sp->ctx;
   Program& prog = sp->prog;
   ExprParams p = prog.params;
@@ -1138,6 +1276,9 @@ int launch_program_sink(ssb_program* sp, const ssb_column* inputs, int64_t rows,
   for (int j = 0; j < kMaxOut; ++j) p.sink_out_aggs[j] = j < p.n_out ? out_aggs[j] : 0u;
   p.sink_count_star = count_star;
   p.sink_pad = pad_codes;
+  p.sink_seen_mask = seen_mask;
+  p.sink_keys_not_null = 1;
+  for (int j = 0; j < n_keys; ++j) if (p.out_nullable[j]) p.sink_keys_not_null = 0;
   long long grid = static_cast<long long>(ctx->num_sms) * sp->max_ctas_per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
   var.sink_kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);

@@ -1182,10 +1182,17 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
       cudaError_t e2 = tmp_malloc(ctx, &d_params, sizeof(GroupParams));
       if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(d_params, &p, sizeof(GroupParams), cudaMemcpyHostToDevice, ctx->stream);
       if (e2 != cudaSuccess) { rc = cuda_fail(ctx, e2, "sink parameters"); break; }
-      uint32_t pad_codes = 0;
-      for (int a = 0; a < g->n_aggs; ++a) pad_codes |= (p.agg[a].pad & 3u) << (2 * a);
+      uint32_t pad_codes = 0, seen_mask = 0;
+      for (int a = 0; a < g->n_aggs; ++a) {
+        const AggDev& ag = p.agg[a];
+        const uint32_t code = ag.fn == SSB_AGG_COUNT ? TA_COUNT
+                              : (ag.fn == SSB_AGG_SUM && ag.out_phys == T_F64) ? TA_SUM_F64
+                              : (ag.fn == SSB_AGG_SUM && (ag.out_phys == T_I64 || ag.out_phys == T_U64)) ? TA_SUM_U64 : TA_OTHER;
+        pad_codes |= code << (2 * a);
+        if (ag.seen != nullptr) seen_mask |= 1u << a;
+      }
       rc = launch_program_sink(sink->twin, sink->inputs, remaining, d_params, g->n_keys, g->n_aggs, sink->groups,
-                               sink->out_aggs, sink->count_star, pad_codes);
+                               sink->out_aggs, sink->count_star, pad_codes, seen_mask);
       --ctx->launches;   // counted below
       if (rc) { tmp_free(ctx, d_params); break; }
     } else if (fused != nullptr) {
@@ -1402,10 +1409,12 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
                              static_cast<int>(prog.generic.size()) <= kRowMaxInsn && smem + 8192 <= ctx->smem_optin;
   const bool feasible = fused_enabled && rows_feasible;
   // The aggregation sink inside expr_kernel (tile-wide superinstructions, no output staging, no
-  // scratch) is correct but not yet faster than the two kernels: 23.4 warp instructions per row
-  // at six resident warps per SM (issue 18 %, profiles/r1_summary.md) = 23 ms per 200M Q1 rows
-  // against 18 ms. Opt-in until it wins (SSB200_GROUP_SINK=1).
-  static const bool sink_enabled = getenv("SSB200_GROUP_SINK") != nullptr && atoi(getenv("SSB200_GROUP_SINK")) != 0;
+  // scratch): the default whenever the plan fits it. Round 1's form (384-row tiles, four rows per
+  // thread, a fingerprint loop per row) cost 23 warp instructions per row and lost to the two
+  // kernels; this one runs 512-row tiles at eight rows per thread with a hashed group lookup.
+  // SSB200_GROUP_SINK=0 selects the two-kernel form (A/B runs, tests).
+  const char* sink_env = getenv("SSB200_GROUP_SINK");
+  const bool sink_enabled = sink_env == nullptr || atoi(sink_env) != 0;
   bool sink_ok = sink_enabled && rows_feasible && g->n_keys <= 2;   // the row evaluator replays rows the sink had to defer
   for (int a = 0; a < A; ++a) {   // the sink accumulates without conversions
     if (g->aggs[a].fn != SSB_AGG_COUNT && phys_of(g->aggs[a].in_type) != phys_of(g->aggs[a].out_type)) sink_ok = false;

@@ -90,6 +90,7 @@ enum Code {
   //   +0 acc * slot a + slot b     +1 slot c * slot a + slot b
   C_MAD_I64 = C_BIN_END, C_MAD_F64 = C_MAD_I64 + 2, C_MAD_I32 = C_MAD_F64 + 2,
   C_MAD_END = C_MAD_I32 + 2,
+  C_STORE8 = C_MAD_END, C_STORE4,      // slot = acc, slot not nullable
 };
 // SUBR / GT are SUB / LT with the operands swapped (F_REV resolved at compile time).
 enum { B_ADD = 0, B_SUB = 1, B_SUBR = 2, B_MUL = 3, B_LT = 4, B_GT = 5, B_EQ = 6 };

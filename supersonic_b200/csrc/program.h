@@ -74,6 +74,14 @@ struct ExprParams {
   uint32_t sink_out_aggs[kMaxOut];      // bit a: aggregate a accumulates output column j
   uint32_t sink_count_star;             // bit a: aggregate a is COUNT(*)
   uint32_t sink_pad;                    // two bits per aggregate: TA_* accumulate code
+  // output j of a sink program is not staged: the sink reads it from the shared-memory slot that holds it
+  // (an input column of the current stage, or a temporary the program stored)
+  uint32_t sink_src_off[kMaxOut];       // byte offset of the slot, encoded like Insn::off_a (bit 31: stage relative)
+  int16_t sink_src_slot[kMaxOut];       // slot index (for its null words)
+  uint8_t sink_src_w[kMaxOut];          // element width: 1, 4 or 8
+  uint8_t sink_src_nullable[kMaxOut];
+  uint32_t sink_seen_mask;              // bit a: aggregate a has a nullable input (its partials carry a seen byte)
+  int32_t sink_keys_not_null;           // no key output can be NULL: the lookup skips the NULL words
 };
 
 enum { kMaxDefer = 2 };   // Filter: tile i is copied out while tile i + defer is evaluated
@@ -116,7 +124,8 @@ namespace ssb {
 // Aggregation sink of expr_kernel (expr_kernel.cu), driven by group.cu.
 int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_program** out);
 int launch_program_sink(ssb_program* sp, const ssb_column* inputs, int64_t rows, const void* d_gp, int n_keys,
-                        int n_aggs, int groups, const uint32_t* out_aggs, uint32_t count_star, uint32_t pad_codes);
+                        int n_aggs, int groups, const uint32_t* out_aggs, uint32_t count_star, uint32_t pad_codes,
+                        uint32_t seen_mask);
 }  // namespace ssb
 
 struct ssb_program {

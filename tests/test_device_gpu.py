@@ -353,8 +353,16 @@ def _run_both(ctx, nodes, in_types, in_nullable, outputs, predicate, inputs, n_k
     return want, kept
 
 
-@pytest.mark.parametrize("rows", [1, 1000, 600_000])
-def test_fused_q1_shape_equals_unfused(ctx, rows):
+@pytest.fixture(params=["1", "0"], ids=["sink", "two_kernels"])
+def sink_mode(request, monkeypatch):
+    """ssb_group_update_program with the aggregation sink inside the expression kernel (the default) and
+    with the two-kernel form (SSB200_GROUP_SINK=0); the environment is read at every call."""
+    monkeypatch.setenv("SSB200_GROUP_SINK", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("rows", [1, 1000, 600_000, 3_000_001])
+def test_fused_q1_shape_equals_unfused(ctx, rows, sink_mode):
     rng = np.random.default_rng(rows)
     F64, I64, B = capi.DOUBLE, capi.INT64, capi.BOOL
     n = capi.node
@@ -373,7 +381,7 @@ def test_fused_q1_shape_equals_unfused(ctx, rows):
 
 
 @pytest.mark.parametrize("groups,rows", [(5, 50_000), (7, 400_000), (5000, 400_000)])
-def test_fused_nullable_keys_inputs_and_overflow_equal_unfused(ctx, groups, rows):
+def test_fused_nullable_keys_inputs_and_overflow_equal_unfused(ctx, groups, rows, sink_mode):
     """NULL keys form a group, NULL predicate rows are dropped, NULL inputs do not count; with
     5000 groups the CTA-local entries overflow into the global table and later slices take the
     materialising path."""
@@ -393,7 +401,7 @@ def test_fused_nullable_keys_inputs_and_overflow_equal_unfused(ctx, groups, rows
               [I64, F64, F64, capi.UINT64, capi.UINT64, I32])
 
 
-def test_fused_scalar_aggregate_equals_unfused(ctx):
+def test_fused_scalar_aggregate_equals_unfused(ctx, sink_mode):
     rows = 300_000
     rng = np.random.default_rng(3)
     I64, B = capi.INT64, capi.BOOL
@@ -408,7 +416,7 @@ def test_fused_scalar_aggregate_equals_unfused(ctx):
     assert want[1][0][0][0] == (a * b)[m].sum() and want[1][1][0][0] == (a * b)[m].max() and want[1][2][0][0] == m.sum() == kept
 
 
-def test_fused_sink_overflow_and_table_growth_equal_unfused(ctx):
+def test_fused_sink_overflow_and_table_growth_equal_unfused(ctx, sink_mode):
     """The aggregation sink of the expression kernel starts with four groups (per-thread
     accumulators), then the key domain explodes: rows overflow into the global table, the table
     fills up, the overflowing rows are deferred, the table grows and the rows are replayed."""

@@ -142,7 +142,12 @@ enum {
 enum {
   SSB_NODE_NULL = 1,            /* CONST: the constant is NULL */
   SSB_NODE_ZERO_NULLS = 2,      /* DIV/MOD: divisor == 0 -> result NULL (…Nulling variants) */
-  SSB_NODE_ZERO_FAILS = 4       /* DIV/MOD: divisor == 0 -> ERROR_EVALUATION_ERROR (…Signaling) */
+  SSB_NODE_ZERO_FAILS = 4,      /* DIV/MOD: divisor == 0 -> ERROR_EVALUATION_ERROR (…Signaling) */
+  SSB_NODE_GUARDED = 8          /* with ZERO_FAILS: arg[2] is a BOOL node; the zero divisor fails only on rows where it is
+                                   TRUE and not NULL. The reference evaluates a sub-expression only on the rows its skip
+                                   vector leaves (the taken branch of IF / CASE, the undecided side of AND / OR, rows whose
+                                   other operand is not NULL, rows a Filter below kept: elementary_bound_expressions.cc:
+                                   406-539,541-1050, binary_column_computers.h:137-166); the caller states that set here. */
 };
 
 typedef struct {

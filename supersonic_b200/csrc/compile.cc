@@ -60,6 +60,11 @@ class Compiler {
       for (int a = 0; a < arity; ++a) {
         if (nd.arg[a] < 0) return Fail(SSB_ERROR_INVALID_ARGUMENT_VALUE, "missing node argument");
       }
+      if (nd.flags & SSB_NODE_GUARDED) {
+        if (!Guarded(nd)) return Fail(SSB_ERROR_INVALID_ARGUMENT_VALUE, "SSB_NODE_GUARDED needs a signaling DIV / MOD");
+        if (nd.arg[2] < 0 || nd.arg[2] >= i) return Fail(SSB_ERROR_INVALID_ARGUMENT_VALUE, "guard is not an earlier node");
+        if (info_[nd.arg[2]].phys != T_B8) return Fail(SSB_ERROR_INVALID_ARGUMENT_TYPE, "guard must be BOOL");
+      }
       if (int rc = CheckTypes(i)) return rc;
       in.nullable = Nullable(i);
     }
@@ -71,6 +76,7 @@ class Compiler {
     const ssb_expr_node& nd = nodes_[i];
     const int arity = Arity(nd.op);
     for (int a = 0; a < arity; ++a) CountRef(nd.arg[a]);
+    if (Guarded(nd)) CountRef(nd.arg[2]);
   }
 
   // ---- pass 2: code generation
@@ -290,6 +296,27 @@ class Compiler {
     if (nd.flags & SSB_NODE_ZERO_FAILS) { in.flags |= F_ZERO_FAILS; prog_->has_signaling = true; }
     in.t = static_cast<uint8_t>(info_[l].phys);    // true left operand
     in.t2 = static_cast<uint8_t>(info_[r].phys);   // true right operand
+    if (Guarded(nd)) {
+      // the guard travels as the third operand (rhs2) of a K_ALU3 form
+      int own_g, own_r;
+      Ref rg = Materialize(nd.arg[2], &own_g);
+      Ref rr = Materialize(r, &own_r);
+      Gen(l);
+      in.kind = K_ALU3;
+      in.flags |= F_GUARDED;
+      SetRhs(&in, rr);
+      in.b = static_cast<int16_t>(rg.idx);
+      if (rg.imm) {
+        in.flags |= F_RHS2_IMM;
+        if (rg.null_const) in.rhs_nullable |= 4;
+      } else if (rg.nullable) {
+        in.rhs_nullable |= 2;
+      }
+      Emit(in);
+      if (own_r >= 0) FreeTmp(own_r);
+      if (own_g >= 0) FreeTmp(own_g);
+      return;
+    }
     if (Simple(r)) {
       Gen(l);
       SetRhs(&in, RefOf(r));
@@ -605,6 +632,9 @@ class Compiler {
     }
   }
 
+  static bool Guarded(const ssb_expr_node& nd) {
+    return (nd.flags & SSB_NODE_GUARDED) && (nd.flags & SSB_NODE_ZERO_FAILS) && (nd.op == SSB_OP_DIV || nd.op == SSB_OP_MOD);
+  }
   static bool IsInt(int p) { return p == T_I32 || p == T_I64 || p == T_U32 || p == T_U64; }
   static bool IsNum(int p) { return p != T_B8; }
 

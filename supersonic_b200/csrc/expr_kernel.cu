@@ -122,8 +122,13 @@ struct SinkShared {
   unsigned int* l_knull;
   unsigned int* l_slot;
   unsigned int* l_ready;
+  unsigned int* l_fp;
   unsigned char* t_seen;
 };
+__device__ __forceinline__ uint32_t sink_fp32(unsigned long long k0, unsigned long long k1, unsigned int knull) {
+  const unsigned long long h = (k0 + knull) * 0x9E3779B97F4A7C15ull + k1 * 0xC2B2AE3D27D4EB4Full;
+  return static_cast<uint32_t>(h >> 32) ^ static_cast<uint32_t>(h);
+}
 // Layout of the sink area (must match sink_bytes_per_thread / sink_fixed_bytes on the host).
 __device__ __forceinline__ SinkShared sink_layout(unsigned char* base, int SG, int SA, int NT) {
   SinkShared sk;
@@ -132,7 +137,8 @@ __device__ __forceinline__ SinkShared sink_layout(unsigned char* base, int SG, i
   sk.l_knull = reinterpret_cast<unsigned int*>(sk.l_key + kTinyGroups * 2);   // [kTinyGroups] bit c: key column c is NULL
   sk.l_slot = sk.l_knull + kTinyGroups;                                       // [kTinyGroups] global slot + 1, 0 = free
   sk.l_ready = sk.l_slot + kTinyGroups;                                       // [1] bit e: entry e is published
-  sk.t_seen = reinterpret_cast<unsigned char*>(sk.l_ready + 4);               // [(SG + 1) * SA][NT]
+  sk.l_fp = sk.l_ready + 4;                                                   // [kTinyGroups] 32-bit fingerprint of the entry's key
+  sk.t_seen = reinterpret_cast<unsigned char*>(sk.l_fp + kTinyGroups);        // [(SG + 1) * SA][NT]
   return sk;
 }
 // Identity of a thread's partial. Sums start from the value that addition leaves exact (-0.0 for
@@ -163,6 +169,7 @@ __device__ __noinline__ int sink_insert(const GroupParams& gp, unsigned char* si
       sk.l_key[2 * e] = k0;
       sk.l_key[2 * e + 1] = k1;
       sk.l_knull[e] = knull;
+      sk.l_fp[e] = sink_fp32(k0, k1, knull);
       __threadfence_block();
       atomicOr(sk.l_ready, 1u << e);
       return e;
@@ -673,7 +680,7 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
         // ---- generic path: NULL-carrying operands, narrow or mixed types, rare ops.
         // Works on 4 rows at a time so that its register footprint does not grow with R.
         const Insn& in = p.insn[pc];
-        auto fetch4 = [&](int c4, int idx, bool is_imm, bool null_const, bool nullable, u64 (&v)[4], uint32_t& nn) {
+        auto fetch4 = [&](int c4, int idx, bool is_imm, bool null_const, bool nullable, int width, u64 (&v)[4], uint32_t& nn) {
           if (is_imm) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) v[q] = p.imm[idx];
@@ -684,8 +691,8 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int r = row_first + 32 * (c4 * 4 + q);
-            v[q] = in.rw == 8 ? reinterpret_cast<const u64*>(base)[r]
-                              : (in.rw == 4 ? static_cast<u64>(reinterpret_cast<const uint32_t*>(base)[r]) : static_cast<u64>(base[r]));
+            v[q] = width == 8 ? reinterpret_cast<const u64*>(base)[r]
+                              : (width == 4 ? static_cast<u64>(reinterpret_cast<const uint32_t*>(base)[r]) : static_cast<u64>(base[r]));
           }
           nn = 0;
           if (nullable) {
@@ -707,8 +714,10 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
               uint32_t an = (accn >> (4 * c4)) & 15u, n1 = 0, n2 = 0;
 #pragma unroll
               for (int q = 0; q < 4; ++q) { a4[q] = acc[c4 * 4 + q]; r1[q] = 0; r2[q] = 0; }
-              if (in.kind != K_ALU1) fetch4(c4, in.a, in.flags & F_RHS_IMM, in.flags & F_RHS_NULLK, in.rhs_nullable & 1, r1, n1);
-              if (in.kind == K_ALU3) fetch4(c4, in.b, in.flags & F_RHS2_IMM, in.rhs_nullable & 4, in.rhs_nullable & 2, r2, n2);
+              if (in.kind != K_ALU1) fetch4(c4, in.a, in.flags & F_RHS_IMM, in.flags & F_RHS_NULLK, in.rhs_nullable & 1, in.rw, r1, n1);
+              // rhs2 has the width of rhs (the branches of IF), except a guard, which is a BOOL
+              if (in.kind == K_ALU3) fetch4(c4, in.b, in.flags & F_RHS2_IMM, in.rhs_nullable & 4, in.rhs_nullable & 2,
+                                            (in.flags & F_GUARDED) ? 1 : in.rw, r2, n2);
               if (in.kind == K_LOAD) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) a4[q] = r1[q];
@@ -812,20 +821,31 @@ __device__ __forceinline__ void expr_kernel_body(const ExprParams& p) {
 #pragma unroll
           for (int k = 0; k < R; ++k) { if ((kn0 >> k) & 1u) kv0[k] = 0; if ((kn1 >> k) & 1u) kv1[k] = 0; }
         }
+        // 32-bit fingerprints select the candidate entry (two instructions per row and entry); the key
+        // values confirm it. A confirmed mismatch is a miss (cold path, which is exact).
         const uint32_t ready = *reinterpret_cast<volatile unsigned int*>(sk.l_ready);
+        uint32_t fpr[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
+          fpr[k] = sink_fp32(kv0[k], kv1[k], kn);
+        }
         int gsel[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) gsel[k] = -1;
 #pragma unroll
         for (int e = 0; e < kTinyGroups; ++e) {
           if (!((ready >> e) & 1u)) continue;   // CTA-uniform
-          const u64 e0 = sk.l_key[2 * e], e1 = sk.l_key[2 * e + 1];
-          const uint32_t en = sk.l_knull[e];
+          const uint32_t ef = sk.l_fp[e];
 #pragma unroll
-          for (int k = 0; k < R; ++k) {
-            const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
-            if (kv0[k] == e0 && kv1[k] == e1 && kn == en) gsel[k] = e;
-          }
+          for (int k = 0; k < R; ++k) if (fpr[k] == ef) gsel[k] = e;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int e = gsel[k] < 0 ? 0 : gsel[k];
+          const uint32_t kn = ((kn0 >> k) & 1u) | (((kn1 >> k) & 1u) << 1);
+          const bool same = sk.l_key[2 * e] == kv0[k] && sk.l_key[2 * e + 1] == kv1[k] && sk.l_knull[e] == kn;
+          if (!same) gsel[k] = -1;
         }
         uint32_t goff[R];
         uint32_t ovf = 0;
@@ -1176,7 +1196,7 @@ static uint32_t sink_bytes_per_thread(int n_keys, int n_aggs, int groups, int ro
   return static_cast<uint32_t>((groups + 1) * n_aggs * 9);   // accumulator + seen byte per (group incl. trash, aggregate)
 }
 static uint32_t sink_fixed_bytes() {
-  return static_cast<uint32_t>(kTinyGroups * 2 * 8 + kTinyGroups * 4 * 2 + 16 + 64);
+  return static_cast<uint32_t>(kTinyGroups * 2 * 8 + kTinyGroups * 4 * 3 + 16 + 64);
 }
 
 // Compiles (once per shape) the twin of `base` whose outputs feed the aggregation sink.

@@ -55,6 +55,7 @@ enum {
   F_RHS_NULLK = 64,
   F_RHS2_IMM = 128,   // M_SEL: rhs2 is imm[b]
   F_THEN_PRED = 256,  // fast compare directly followed by K_PRED: the row mask feeds the compaction
+  F_GUARDED = 512,    // M_DIV / M_MOD with F_ZERO_FAILS as K_ALU3: rhs2 (BOOL) = rows on which the failure counts
 };
 
 // Instruction kinds.
@@ -313,6 +314,15 @@ template <> struct UnsignedOf<int64_t> { typedef uint64_t type; };
 //   rhs/rhsn   right operand (K_ALU2/3), rhs2/rhs2n third operand (K_ALU3)
 //   fail       set non-zero when an F_ZERO_FAILS op meets a zero divisor on a live row
 //   live       bit k set = row k exists (tail tiles)
+// Rows on which a guarded signaling op may fail: the guard is TRUE and not NULL (all rows without a guard).
+template <int R>
+SSB_HD uint32_t guard_rows(const Insn& in, const u64 (&g)[R], uint32_t gn) {
+  if (!(in.flags & F_GUARDED)) return 0xffffffffu;
+  uint32_t m = 0;
+  SSB_UNROLL SSB_FOR_K { m |= ((g[k] & 1u) ? 1u : 0u) << k; }
+  return m & ~gn;
+}
+
 template <int R>
 SSB_HD void alu(const Insn& in, u64 (&acc)[R], uint32_t& accn, u64 (&rhs)[R], uint32_t rhsn,
                 const u64 (&rhs2)[R], uint32_t rhs2n, uint32_t live, uint32_t& fail) {
@@ -335,7 +345,7 @@ SSB_HD void alu(const Insn& in, u64 (&acc)[R], uint32_t& accn, u64 (&rhs)[R], ui
           if (IsZero<T>::f(b)) zero |= 1u << k;
           acc[k] = Codec<T>::enc(Div<T>::f(a, b));
         })
-      if (in.flags & F_ZERO_FAILS) fail |= (zero & ~accn & live);
+      if (in.flags & F_ZERO_FAILS) fail |= (zero & ~accn & live & guard_rows<R>(in, rhs2, rhs2n));
       if (in.flags & F_ZERO_NULLS) accn |= zero;
     } break;
     case M_MOD: {
@@ -348,7 +358,7 @@ SSB_HD void alu(const Insn& in, u64 (&acc)[R], uint32_t& accn, u64 (&rhs)[R], ui
           if (ModZero<T>::f(b)) zero |= 1u << k;
           acc[k] = Mod<T>::f(a, b);
         })
-      if (in.flags & F_ZERO_FAILS) fail |= (zero & ~accn & live);
+      if (in.flags & F_ZERO_FAILS) fail |= (zero & ~accn & live & guard_rows<R>(in, rhs2, rhs2n));
       if (in.flags & F_ZERO_NULLS) accn |= zero;
     } break;
     case M_LT:

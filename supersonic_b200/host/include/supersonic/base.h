@@ -20,36 +20,48 @@
 #include <utility>
 #include <vector>
 
-namespace supersonic {
+// supersonic/utils/integral_types.h:24-43: the integral types are GLOBAL typedefs in the reference (client
+// code such as test/guide/primer.cc writes plain `int32`), 64-bit ones are (unsigned) long long.
+typedef int int32;
+typedef long long int64;
+typedef unsigned int uint32;
+typedef unsigned long long uint64;
 
-using std::string;
-using std::vector;
-
-typedef int32_t int32;
-typedef int64_t int64;
-typedef uint32_t uint32;
-typedef uint64_t uint64;
-
-// supersonic/utils/strings/stringpiece.h (the subset plan code uses)
+// supersonic/utils/strings/stringpiece.h (the subset plan code uses); global, as in the reference
 class StringPiece {
  public:
   StringPiece() : ptr_(NULL), len_(0) {}
   StringPiece(const char* s) : ptr_(s), len_(s ? strlen(s) : 0) {}            // NOLINT
-  StringPiece(const string& s) : ptr_(s.data()), len_(s.size()) {}            // NOLINT
+  StringPiece(const std::string& s) : ptr_(s.data()), len_(s.size()) {}       // NOLINT
   StringPiece(const char* s, size_t n) : ptr_(s), len_(n) {}
   const char* data() const { return ptr_; }
   size_t size() const { return len_; }
   size_t length() const { return len_; }
   bool empty() const { return len_ == 0; }
-  string as_string() const { return ptr_ ? string(ptr_, len_) : string(); }
-  string ToString() const { return as_string(); }
+  std::string as_string() const { return ptr_ ? std::string(ptr_, len_) : std::string(); }
+  std::string ToString() const { return as_string(); }
   bool operator==(const StringPiece& o) const {
     return len_ == o.len_ && (len_ == 0 || memcmp(ptr_, o.ptr_, len_) == 0);
+  }
+  bool operator!=(const StringPiece& o) const { return !(*this == o); }
+  bool operator<(const StringPiece& o) const {
+    const int r = memcmp(ptr_, o.ptr_, len_ < o.len_ ? len_ : o.len_);
+    return r < 0 || (r == 0 && len_ < o.len_);
   }
  private:
   const char* ptr_;
   size_t len_;
 };
+
+namespace supersonic {
+
+using std::string;
+using std::vector;
+using ::int32;
+using ::int64;
+using ::uint32;
+using ::uint64;
+using ::StringPiece;
 
 // ---- enums of supersonic/proto/supersonic.proto:15-118 (same names and numbers) ---------
 enum DataType {

@@ -412,7 +412,7 @@ EvaluationResult BoundExpressionTree::Evaluate(const View& input) {
   }
   if (!program_) {
     vector<NodePtr> outs;
-    for (int i = 0; i < root_->column_count(); ++i) outs.push_back(root_->node(i));
+    for (int i = 0; i < root_->column_count(); ++i) outs.push_back(GuardSignaling(root_->node(i), vector<NodePtr>(), NodePtr()));
     FailureOrOwned<DeviceProgram> p = DeviceProgram::Create(root_->input_schema(), outs, NodePtr());
     PROPAGATE_ON_FAILURE(p);
     program_.reset(p.release());

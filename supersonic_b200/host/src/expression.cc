@@ -9,6 +9,9 @@
 // tests/test_binding.py.
 #include <stdio.h>
 
+#include <map>
+#include <set>
+
 #include "internal.h"
 
 namespace supersonic {
@@ -615,6 +618,117 @@ NodePtr SubstituteMemo(const NodePtr& node, const vector<NodePtr>& inputs, std::
 NodePtr Substitute(const NodePtr& node, const vector<NodePtr>& inputs) {
   std::map<const ExprNode*, NodePtr> memo;
   return SubstituteMemo(node, inputs, &memo);
+}
+
+// ---- skip-vector semantics of signaling operators -------------------------------------------
+// The reference evaluates a bound tree with skip vectors: a child runs only on the rows its parent
+// leaves (expression/templated/abstract_bound_expressions.h:129-147: the right operand of a binary
+// node skips the rows whose left operand is NULL; elementary_bound_expressions.cc:262-327: the right
+// side of AND / OR / AND_NOT skips the rows the left side decides; :167-190: IFNULL's substitute runs
+// where the value is NULL; :896-1050: IF's branches run where they are taken), and a Compute above a
+// Filter sees only the rows the Filter kept (filter.cc:96-128). Values of skipped rows are never
+// used, so the only observable effect is on the operators that can FAIL (the signaling division and
+// modulus, binary_column_computers.h:137-166): they must not fail on a skipped row. The fused
+// kernel evaluates every node on every row; the set of rows on which a signaling node may fail is
+// therefore stated explicitly as a BOOL guard expression (third argument, SSB_NODE_GUARDED).
+namespace {
+struct GuardCtx {
+  std::set<const ExprNode*> stop;                  // nodes of the plan below: already guarded in their own context
+  std::map<const ExprNode*, bool> signaling;
+  bool Signaling(const NodePtr& n) {
+    if (stop.count(n.get())) return false;
+    std::map<const ExprNode*, bool>::iterator it = signaling.find(n.get());
+    if (it != signaling.end()) return it->second;
+    bool r = (n->flags & SSB_NODE_ZERO_FAILS) != 0;
+    for (size_t i = 0; i < n->args.size() && i < 3; ++i) r = Signaling(n->args[i]) || r;
+    signaling[n.get()] = r;
+    return r;
+  }
+};
+NodePtr Node1(int op, const NodePtr& a, bool nullable, const char* what) {
+  return MakeNode(op, BOOL, nullable, string(what) + "(" + a->name + ")", vector<NodePtr>(1, a));
+}
+// TRUE exactly where `c` is TRUE and not NULL (never NULL itself)
+NodePtr IsTrue(const NodePtr& c) {
+  if (!c->nullable) return c;
+  vector<NodePtr> args;
+  args.push_back(c);
+  args.push_back(MakeConstBool(false));
+  return MakeNode(SSB_OP_IF_NULL, BOOL, false, "IFNULL(" + c->name + ", FALSE)", args);
+}
+NodePtr NotOf(const NodePtr& c) { return Node1(SSB_OP_NOT, c, c->nullable, "NOT"); }
+// a AND b where an absent guard means "every row"
+NodePtr BothGuards(const NodePtr& a, const NodePtr& b) {
+  if (!a) return b;
+  if (!b) return a;
+  return MakeBinaryLogic(SSB_OP_AND, a, b);
+}
+// rows where `x` is not NULL (absent = every row)
+NodePtr NotNullRows(const NodePtr& x) {
+  if (!x->nullable) return NodePtr();
+  return NotOf(Node1(SSB_OP_IS_NULL, x, false, "ISNULL"));
+}
+NodePtr Guard(GuardCtx* ctx, const NodePtr& n, const NodePtr& g) {
+  if (!ctx->Signaling(n)) return n;
+  std::shared_ptr<ExprNode> copy(new ExprNode(*n));
+  vector<NodePtr>& a = copy->args;
+  switch (n->op) {
+    case SSB_OP_IF:
+    case SSB_OP_NULLING_IF: {
+      a[0] = Guard(ctx, n->args[0], g);
+      const NodePtr taken = IsTrue(a[0]);
+      a[1] = Guard(ctx, n->args[1], BothGuards(g, taken));
+      // IF: the other branch runs where the condition is FALSE or NULL; the nulling form skips NULL conditions
+      const NodePtr other = n->op == SSB_OP_IF ? NotOf(taken) : IsTrue(NotOf(a[0]));
+      a[2] = Guard(ctx, n->args[2], BothGuards(g, other));
+      break;
+    }
+    case SSB_OP_AND: {
+      a[0] = Guard(ctx, n->args[0], g);
+      // skipped where the left side is FALSE and not NULL  <=>  runs where IFNULL(left, TRUE)
+      NodePtr runs = a[0];
+      if (a[0]->nullable) {
+        vector<NodePtr> args;
+        args.push_back(a[0]);
+        args.push_back(MakeConstBool(true));
+        runs = MakeNode(SSB_OP_IF_NULL, BOOL, false, "IFNULL(" + a[0]->name + ", TRUE)", args);
+      }
+      a[1] = Guard(ctx, n->args[1], BothGuards(g, runs));
+      break;
+    }
+    case SSB_OP_OR:
+    case SSB_OP_AND_NOT:
+      a[0] = Guard(ctx, n->args[0], g);
+      a[1] = Guard(ctx, n->args[1], BothGuards(g, NotOf(IsTrue(a[0]))));   // skipped where the left side is TRUE and not NULL
+      break;
+    case SSB_OP_IF_NULL:
+      a[0] = Guard(ctx, n->args[0], g);
+      a[1] = Guard(ctx, n->args[1], a[0]->nullable ? BothGuards(g, Node1(SSB_OP_IS_NULL, a[0], false, "ISNULL"))
+                                                  : MakeConstBool(false));
+      break;
+    default: {
+      // NULLs are viral: every later operand skips the rows where an earlier one is NULL
+      NodePtr rows = g;
+      for (size_t i = 0; i < a.size() && i < 2; ++i) {
+        a[i] = Guard(ctx, n->args[i], rows);
+        rows = BothGuards(rows, NotNullRows(a[i]));
+      }
+      if ((n->flags & SSB_NODE_ZERO_FAILS) && g) {
+        a.resize(2);
+        a.push_back(IsTrue(g));
+        copy->flags |= SSB_NODE_GUARDED;
+      }
+      break;
+    }
+  }
+  return copy;
+}
+}  // namespace
+
+NodePtr GuardSignaling(const NodePtr& node, const vector<NodePtr>& below, const NodePtr& rows) {
+  GuardCtx ctx;
+  for (size_t i = 0; i < below.size(); ++i) ctx.stop.insert(below[i].get());
+  return Guard(&ctx, node, rows ? IsTrue(rows) : rows);
 }
 
 }  // namespace internal

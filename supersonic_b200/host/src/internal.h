@@ -29,6 +29,10 @@ FailureOrVoid DescribeAny(const Operation* op, RowwisePlan* plan);
 // Rewrites `node` (bound against a schema whose column i is computed by `inputs[i]`) into an
 // expression over the columns `inputs` are expressed in. Shared sub-trees stay shared.
 NodePtr Substitute(const NodePtr& node, const vector<NodePtr>& inputs);
+// Rewrites `node` so that every signaling operator in it (not below one of the nodes in `below`) fails
+// only on the rows the reference would evaluate it on: the rows of `rows` (a BOOL expression, NULL =
+// every row) narrowed by the IF / AND / OR / IFNULL / NULL-operand structure above it.
+NodePtr GuardSignaling(const NodePtr& node, const vector<NodePtr>& below, const NodePtr& rows);
 NodePtr MakeInputNode(const TupleSchema& schema, int position);
 NodePtr MakeBinaryLogic(int op, const NodePtr& a, const NodePtr& b);
 

@@ -665,7 +665,10 @@ class ComputeOperation : public BasicOperation {
     FailureOrOwned<BoundExpression> bound = computation_->DoBind(plan->schema, buffer_allocator(), Cursor::kDefaultRowCount);
     if (bound.is_failure()) { *error = bound.release_exception(); return true; }
     vector<NodePtr> outs;
-    for (int i = 0; i < bound->column_count(); ++i) outs.push_back(Substitute(bound->node(i), plan->outputs));
+    // a Compute above a Filter evaluates only the rows the Filter kept (signaling operators: GuardSignaling)
+    for (int i = 0; i < bound->column_count(); ++i) {
+      outs.push_back(GuardSignaling(Substitute(bound->node(i), plan->outputs), plan->outputs, plan->predicate));
+    }
     plan->outputs = outs;
     plan->schema = bound->result_schema();
     return true;
@@ -700,7 +703,7 @@ class FilterOperation : public BasicOperation {
     }
     FailureOrOwned<const BoundSingleSourceProjector> proj = projector_->Bind(plan->schema);
     if (proj.is_failure()) { *error = proj.release_exception(); return true; }
-    NodePtr pred = Substitute(bound->node(0), plan->outputs);
+    NodePtr pred = GuardSignaling(Substitute(bound->node(0), plan->outputs), plan->outputs, plan->predicate);
     plan->predicate = plan->predicate ? MakeBinaryLogic(SSB_OP_AND, plan->predicate, pred) : pred;
     vector<NodePtr> outs;
     for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
@@ -1294,7 +1297,9 @@ FailureOrOwned<Cursor> BoundCompute(BoundExpressionTree* computation, BufferAllo
   std::unique_ptr<BoundExpressionTree> tree(computation);
   RowwisePlan plan = PlanOverCursor(child);
   plan.outputs.clear();
-  for (int i = 0; i < tree->root()->column_count(); ++i) plan.outputs.push_back(tree->root()->node(i));
+  for (int i = 0; i < tree->root()->column_count(); ++i) {
+    plan.outputs.push_back(GuardSignaling(tree->root()->node(i), vector<NodePtr>(), NodePtr()));
+  }
   plan.schema = tree->result_schema();
   return Success(static_cast<Cursor*>(new RowwiseCursor(plan, allocator, COMPUTE)));
 }
@@ -1318,7 +1323,7 @@ FailureOrOwned<Cursor> BoundFilter(BoundExpressionTree* predicate, const BoundSi
   for (int i = 0; i < proj->result_schema().attribute_count(); ++i) outs.push_back(plan.outputs[proj->source_attribute_position(i)]);
   plan.outputs = outs;
   plan.schema = proj->result_schema();
-  plan.predicate = tree->root()->node(0);
+  plan.predicate = GuardSignaling(tree->root()->node(0), vector<NodePtr>(), NodePtr());
   return Success(static_cast<Cursor*>(new RowwiseCursor(plan, buffer_allocator, FILTER)));
 }
 

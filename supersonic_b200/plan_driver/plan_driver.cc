@@ -19,6 +19,9 @@
 //     (bound_scan N) (bound_compute EXPR OP) (bound_filter EXPR PROJ OP) (bound_project PROJ OP)
 //     (bound_group PROJ (aggs AGG...) OP) (bound_scalar_agg (aggs AGG...) OP)
 //     (bound_sort (order (NAME ASC|DESC)...) PROJ OP)
+//   (evaluate EXPR N [CAPACITY [SLICE]]) is not a cursor plan: EXPR is bound to table N with Expression::Bind and
+//   BoundExpressionTree::Evaluate is called on successive slices of SLICE (default CAPACITY) rows
+//   (expression.cc:41-94); CAPACITY 0 = the table's row count (one call).
 //   AGG   := (SUM|MIN|MAX|COUNT|FIRST|LAST in out [TYPE]) | (distinct FN in out)
 //   PROJ  := (all) | (all PREFIX) | (named N...) | (at I...) | (rename (N A)...) | (cat PROJ...)
 //   MPROJ := (multi (SRC PROJ)...)
@@ -522,6 +525,89 @@ struct ssplan_result {
   ssplan_result() : code(0), rows(0), create_s(0), drain_s(0), next_calls(0) {}
 };
 
+namespace {
+void DescribeColumns(ssplan_result* r, const TupleSchema& schema) {
+  r->cols.resize(schema.attribute_count());
+  for (int c = 0; c < schema.attribute_count(); ++c) {
+    const Attribute& a = schema.attribute(c);
+    r->cols[c].name = a.name();
+    r->cols[c].dtype = a.type();
+    r->cols[c].nullable = a.is_nullable() ? 1 : 0;
+    r->cols[c].width = GetTypeInfo(a.type()).size();
+    r->cols[c].saw_nulls = false;
+    if (a.type() == STRING || a.type() == BINARY) {
+      r->code = ERROR_NOT_IMPLEMENTED;
+      r->error = "plan driver returns fixed-width columns only";
+    }
+  }
+}
+
+void AppendView(ssplan_result* r, const View& v, int32_t flags) {
+  const size_t n = v.row_count();
+  if (!(flags & SSPLAN_DISCARD)) {
+    for (size_t c = 0; c < r->cols.size(); ++c) {
+      ssplan_result::Col& col = r->cols[c];
+      const char* src = static_cast<const char*>(v.column(c).data().raw());
+      col.data.insert(col.data.end(), src, src + n * col.width);
+      const bool* nulls = v.column(c).is_null();
+      if (nulls != NULL) {
+        if (!col.saw_nulls) {
+          col.is_null.assign(r->rows, 0);
+          col.saw_nulls = true;
+        }
+        const uint8_t* nb = reinterpret_cast<const uint8_t*>(nulls);
+        col.is_null.insert(col.is_null.end(), nb, nb + n);
+      } else if (col.saw_nulls) {
+        col.is_null.insert(col.is_null.end(), n, 0);
+      }
+    }
+  }
+  r->rows += n;
+}
+
+// (evaluate EXPR N [CAPACITY]): Expression::Bind + BoundExpressionTree::Evaluate over slices of the table.
+int RunEvaluate(const Sx& sx, const Inputs& in, int32_t flags, ssplan_result* r) {
+  if (sx.kids.size() < 3 || sx.kids.size() > 5) throw ParseError{"evaluate takes EXPR TABLE [CAPACITY [SLICE]]"};
+  std::unique_ptr<const Expression> e(BuildExpr(sx.kids[1]));
+  const size_t n = static_cast<size_t>(atoi(Atom(sx.kids[2]).c_str()));
+  if (n >= in.views.size()) throw ParseError{"evaluate: no such table"};
+  const View& table = in.views[n];
+  rowcount_t capacity = sx.kids.size() >= 4 ? static_cast<rowcount_t>(atoll(Atom(sx.kids[3]).c_str())) : 0;
+  if (capacity == 0) capacity = table.row_count() > 0 ? table.row_count() : 1;
+  // SLICE > CAPACITY asks Evaluate for more rows than the tree was bound for (ERROR_TOO_MANY_ROWS, expression.cc:57-66)
+  const rowcount_t step = sx.kids.size() == 5 ? static_cast<rowcount_t>(atoll(Atom(sx.kids[4]).c_str())) : capacity;
+  if (step == 0) throw ParseError{"evaluate: SLICE must be positive"};
+  double t0 = WallNow();
+  FailureOrOwned<BoundExpressionTree> bound = e->Bind(table.schema(), HeapBufferAllocator::Get(), capacity);
+  r->create_s = WallNow() - t0;
+  if (bound.is_failure()) {
+    r->code = bound.exception().return_code();
+    r->error = bound.exception().message();
+    return r->code;
+  }
+  std::unique_ptr<BoundExpressionTree> tree(bound.release());
+  DescribeColumns(r, tree->result_schema());
+  if (r->code != 0 || (flags & SSPLAN_BIND_ONLY)) return r->code;
+  t0 = WallNow();
+  View slice(table.schema());
+  for (rowcount_t first = 0; first < table.row_count() || (first == 0 && table.row_count() == 0); first += step) {
+    const rowcount_t rows = table.row_count() - first < step ? table.row_count() - first : step;
+    slice.ResetFromSubRange(table, first, rows);
+    EvaluationResult result = tree->Evaluate(slice);
+    ++r->next_calls;
+    if (result.is_failure()) {
+      r->code = result.exception().return_code();
+      r->error = result.exception().message();
+      break;
+    }
+    AppendView(r, result.get(), flags);
+    if (table.row_count() == 0) break;
+  }
+  r->drain_s = WallNow() - t0;
+  return r->code;
+}
+}  // namespace
+
 extern "C" {
 
 int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
@@ -555,6 +641,7 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
   double t0 = WallNow();
   try {
     Sx sx = SxParser(plan).Parse();
+    if (Head(sx) == "evaluate") return RunEvaluate(sx, in, flags, r);
     if (Head(sx).compare(0, 6, "bound_") == 0) {
       t0 = WallNow();
       cursor.reset(BuildCursor(sx, in, &keep));
@@ -584,21 +671,8 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
     cursor.reset(created.release());
   }
 
-  const TupleSchema& schema = cursor->schema();
-  r->cols.resize(schema.attribute_count());
-  for (int c = 0; c < schema.attribute_count(); ++c) {
-    const Attribute& a = schema.attribute(c);
-    r->cols[c].name = a.name();
-    r->cols[c].dtype = a.type();
-    r->cols[c].nullable = a.is_nullable() ? 1 : 0;
-    r->cols[c].width = GetTypeInfo(a.type()).size();
-    r->cols[c].saw_nulls = false;
-    if (a.type() == STRING || a.type() == BINARY) {
-      r->code = ERROR_NOT_IMPLEMENTED;
-      r->error = "plan driver returns fixed-width columns only";
-      return r->code;
-    }
-  }
+  DescribeColumns(r, cursor->schema());
+  if (r->code != 0) return r->code;
 
   if (flags & SSPLAN_BIND_ONLY) return r->code;
 
@@ -619,27 +693,7 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
       r->error = "unexpected WAITING_ON_BARRIER";
       break;
     }
-    const View& v = rv.view();
-    const size_t n = v.row_count();
-    if (!(flags & SSPLAN_DISCARD)) {
-      for (size_t c = 0; c < r->cols.size(); ++c) {
-        ssplan_result::Col& col = r->cols[c];
-        const char* src = static_cast<const char*>(v.column(c).data().raw());
-        col.data.insert(col.data.end(), src, src + n * col.width);
-        const bool* nulls = v.column(c).is_null();
-        if (nulls != NULL) {
-          if (!col.saw_nulls) {
-            col.is_null.assign(r->rows, 0);
-            col.saw_nulls = true;
-          }
-          const uint8_t* nb = reinterpret_cast<const uint8_t*>(nulls);
-          col.is_null.insert(col.is_null.end(), nb, nb + n);
-        } else if (col.saw_nulls) {
-          col.is_null.insert(col.is_null.end(), n, 0);
-        }
-      }
-    }
-    r->rows += n;
+    AppendView(r, rv.view(), flags);
   }
   r->drain_s = WallNow() - t0;
   return r->code;

@@ -338,3 +338,76 @@ BOUND_PAIRS = [
      "(group (named k) (aggs (SUM b sb)) (filter (less (col b) (i64 25)) (all) (scan 0)))",
      "(bound_group (named k) (aggs (SUM b sb)) (bound_filter (less (col b) (i64 25)) (all) (bound_scan 0)))", False),
 ]
+
+
+# ------------------------------------------------------------------------------------------------
+# Signaling operators under skip vectors: the reference evaluates a sub-expression only on
+# the rows its parent leaves (the taken branch of IF / CASE, the undecided side of AND / OR, IFNULL's
+# substitute where the value is NULL, rows whose earlier operand is not NULL: elementary_bound_expressions.cc:
+# 262-327,406-539,896-1050, abstract_bound_expressions.h:129-147) and a Compute above a Filter only on the
+# kept rows (filter.cc:96-128); a signaling division fails only there (binary_column_computers.h:137-166).
+# Expected return codes were taken from the oracle (tests/test_oracle_golden.py pins them on the CPU).
+def signaling_tables():
+    import numpy as np
+    from supersonic_b200 import ssplan as sp
+    n = 5000
+    rng = np.random.default_rng(1)
+    a = rng.integers(-100, 100, n).astype(np.int32)
+    b = rng.integers(-3, 4, n).astype(np.int32)          # zeros inside
+    nx_null = (b == 0) | (rng.random(n) < 0.1)
+    cols = [sp.Column("a", sp.INT32, a), sp.Column("b", sp.INT32, b),
+            sp.Column("nx", sp.INT32, rng.integers(0, 9, n).astype(np.int32), is_null=nx_null),      # NULL wherever b == 0
+            sp.Column("ny", sp.INT32, rng.integers(0, 9, n).astype(np.int32), is_null=(b != 0)),      # NULL wherever b != 0
+            sp.Column("k", sp.INT64, rng.integers(0, 5, n))]
+    return [cols]
+
+
+_DIV = "(cpp_divide_signaling (col a) (col b))"
+SIGNALING_CASES = [
+    ("filter_below_compute", "(compute (as q %s) (filter (not_equal (col b) (i32 0)) (all) (scan 0)))" % _DIV, 0),
+    ("filter_below_compute_fails", "(compute (as q %s) (filter (not_equal (col a) (i32 1000)) (all) (scan 0)))" % _DIV, 104),
+    ("compute_below_filter_fails", "(filter (not_equal (col b) (i32 0)) (all) (compute (compound (col b) (as q %s)) (scan 0)))" % _DIV, 104),
+    ("if_untaken_branch", "(compute (as q (if (equal (col b) (i32 0)) (i32 0) %s)) (scan 0))" % _DIV, 0),
+    ("if_taken_branch_fails", "(compute (as q (if (not_equal (col b) (i32 0)) (i32 0) %s)) (scan 0))" % _DIV, 104),
+    ("if_then_side", "(compute (as q (if (not_equal (col b) (i32 0)) %s (i32 7))) (scan 0))" % _DIV, 0),
+    ("nulling_if_null_condition", "(compute (as q (nulling_if (less (col nx) (i32 100)) %s (i32 7))) (scan 0))" % _DIV, 0),
+    ("nulling_if_else_fails", "(compute (as q (nulling_if (less (col ny) (i32 -1)) (i32 7) %s)) (scan 0))" % _DIV, 104),
+    ("case_then", "(compute (as q (case (col b) (i32 -1) (i32 0) (i32 0) (i32 1) %s (i32 2) %s)) (scan 0))" % (_DIV, _DIV), 0),
+    ("case_else", "(compute (as q (case (col b) %s (i32 0) (i32 0))) (scan 0))" % _DIV, 0),
+    ("case_else_fails", "(compute (as q (case (col b) %s (i32 5) (i32 0))) (scan 0))" % _DIV, 104),
+    ("and_short_circuit", "(compute (as q (and (not_equal (col b) (i32 0)) (greater %s (i32 1)))) (scan 0))" % _DIV, 0),
+    ("and_left_side_fails", "(compute (as q (and (greater %s (i32 1)) (not_equal (col b) (i32 0)))) (scan 0))" % _DIV, 104),
+    ("or_short_circuit", "(compute (as q (or (equal (col b) (i32 0)) (greater (modulus_signaling (col a) (col b)) (i32 0)))) (scan 0))", 0),
+    ("and_not_short_circuit", "(compute (as q (and_not (equal (col b) (i32 0)) (greater %s (i32 1)))) (scan 0))" % _DIV, 0),
+    ("if_null_substitute", "(compute (as q (if_null (col ny) %s)) (scan 0))" % _DIV, 0),
+    ("if_null_substitute_fails", "(compute (as q (if_null (col nx) %s)) (scan 0))" % _DIV, 104),
+    ("null_left_operand_skips_right", "(compute (as q (plus (col nx) %s)) (scan 0))" % _DIV, 0),
+    ("null_right_operand_does_not_skip_left", "(compute (as q (plus %s (col nx))) (scan 0))" % _DIV, 104),
+    ("nested", "(compute (as q (if (equal (col b) (i32 0)) (i32 -1) (plus (i32 1) (if (greater (col a) (i32 0)) %s (negate %s))))) (scan 0))" % (_DIV, _DIV), 0),
+    ("filter_over_filter", "(filter (greater %s (i32 0)) (all) (filter (not_equal (col b) (i32 0)) (all) (scan 0)))" % _DIV, 0),
+    ("group_over_compute_over_filter", "(group (named k) (aggs (SUM q s) (COUNT \"\" n)) (compute (compound (col k) (as q (cast INT64 %s))) (filter (not_equal (col b) (i32 0)) (all) (scan 0))))" % _DIV, 0),
+    ("divide_signaling_double", "(compute (as q (if (equal (col b) (i32 0)) (f64 0) (divide_signaling (col a) (col b)))) (scan 0))", 0),
+    ("in_list", "(compute (as q (in (col a) (i32 3) (if (equal (col b) (i32 0)) (i32 0) %s))) (scan 0))" % _DIV, 0),
+]
+
+
+# ------------------------------------------------------------------------------------------------
+# Expression::Bind + BoundExpressionTree::Evaluate (expression.cc:41-94), the entry point of
+# test/guide/primer.cc. Same tuple layout as GOLDEN; `code` != 0 expects that failure.
+EVALUATE_CASES = [
+    # test/guide/primer.cc:103-136,209-222 (PrimerExample1.ColumnAddTest): Plus(AttributeAt(0), AttributeAt(1)) bound
+    # with a capacity of 2048 rows over a = 0..7, b = {3,4,6,8,1,2,2,9}
+    ("primer_column_add", "(evaluate (plus (at 0) (at 1)) 0 2048)",
+     [[col("a", sp.INT32, [0, 1, 2, 3, 4, 5, 6, 7]), col("b", sp.INT32, [3, 4, 6, 8, 1, 2, 2, 9])]],
+     {"(a + b)": [3, 5, 8, 11, 5, 7, 8, 16]}, 0),
+    # several calls on one bound tree (three slices of at most three rows), two result columns, a NULL cell
+    ("evaluate_in_slices", "(evaluate (compound (as s (plus (col a) (col b))) (as m (multiply (col a) (i32 2)))) 0 3)",
+     [[col("a", sp.INT32, [1, 2, 3, 1, 2, 3, 1, 2]), ncol("b", sp.DOUBLE, [1.5, 3.0, N, 7.6, 5.5, 2.0, 1.6, 9.5])]],
+     {"s": [2.5, 5.0, N, 8.6, 7.5, 5.0, 2.6, 11.5], "m": [2, 4, 6, 2, 4, 6, 2, 4]}, 0),
+    # expression.cc:57-66: a view larger than the capacity the tree was bound for
+    ("evaluate_too_many_rows", "(evaluate (plus (col a) (col b)) 0 4 5)",
+     [[col("a", sp.INT32, [0, 1, 2, 3, 4, 5, 6, 7]), col("b", sp.INT32, [3, 4, 6, 8, 1, 2, 2, 9])]], {}, 302),
+    ("evaluate_signaling_failure", "(evaluate (cpp_divide_signaling (col a) (minus (col a) (i32 1))) 0 1024)",
+     [[col("a", sp.INT32, [0, 1, 2, 3])]], {}, 104),
+    ("evaluate_empty_view", "(evaluate (plus (col a) (col a)) 0 16)", [[col("a", sp.INT64, [])]], {"(a + a)": []}, 0),
+]

@@ -134,6 +134,44 @@ def test_signaling_division_fails(ref, b200):
                  b200.run("(compute (cpp_divide_signaling (col a) (col b)) (scan 0))", [ok]))
 
 
+from cases import EVALUATE_CASES, SIGNALING_CASES, signaling_tables  # noqa: E402
+
+
+@pytest.mark.parametrize("case", EVALUATE_CASES, ids=[c[0] for c in EVALUATE_CASES])
+def test_bound_expression_tree_evaluate(ref, b200, case):
+    """SURVEY 8a11: Expression::Bind + BoundExpressionTree::Evaluate of the mirror (test/guide/primer.cc's
+    entry point) against the reference's golden values and against the oracle."""
+    _, plan, tables, expected, code = case
+    want, got = ref.run(plan, tables), b200.run(plan, tables)
+    assert want.code == code and got.code == code, (want.code, got.code, got.error)
+    if code == 0:
+        check_result(got, expected, True)
+        same_results(want, got)
+
+
+def test_evaluate_random_expressions(ref, b200):
+    rng = np.random.default_rng(12)
+    cols = table(rng, 5000, small=True)
+    for e in ["(plus (multiply (col i64) (col i32)) (col ni64))", "(if (col nb) (col f64) (negate (col nf64)))",
+              "(compound (as x (less (col ni32) (col i64))) (as y (cast DOUBLE (col u32))) (col nu64))"]:
+        for cap in (0, 1024, 4999):
+            plan = "(evaluate %s 0 %d)" % (e, cap)
+            same_results(ref.run(plan, [cols]), b200.run(plan, [cols]))
+
+
+@pytest.mark.parametrize("case", SIGNALING_CASES, ids=[c[0] for c in SIGNALING_CASES])
+def test_signaling_ops_follow_skip_vectors(ref, b200, case):
+    """SURVEY 8a9 / ADVICE r1: a signaling division under IF / CASE / AND / OR / IFNULL, next to a NULL
+    operand, or above a Filter fails exactly when the reference's skip-vector evaluation fails, and gives
+    the reference's values otherwise (the kernel evaluates every row; the rows that count travel as a guard)."""
+    _, plan, code = case
+    tables = signaling_tables()
+    want, got = ref.run(plan, tables), b200.run(plan, tables)
+    assert want.code == code and got.code == code, (want.code, got.code, got.error)
+    if code == 0:
+        same_results(want, got, ordered="group" not in plan, sort_cols=[0] if "group" in plan else None)
+
+
 @pytest.mark.parametrize("n,sel", [(10_000_000, 2**19), (1_000_003, 2**10), (2049, 2**20), (1024, 0)])
 def test_filter_project_c1(ref, b200, n, sel):
     """BASELINE config 1: Compute(a*b+c) then Filter(d<K) over 4 x INT64, bit-exact, in order."""

@@ -206,7 +206,7 @@ def _timed(ctx, world, dist, torch, fn, repeats=3):
     return min(times), out
 
 
-def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
+def group_by_aux(capi, ctx, rank, world, rows, dist, torch, comm=None):
     """BASELINE config 3 shape, sharded by row range: GroupAggregate(k; SUM(v), COUNT(*)) with
     k = u mod 1e6 (INT64), v = (u >> 44) * 2^-10 (exactly summable DOUBLE). Every rank aggregates
     its shard (ssb_group_update), the dense partial tables are all-gathered over NCCL and merged
@@ -228,7 +228,7 @@ def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
         g = C.c_void_p()
         ctx.check(lib.ssb_group_create(ctx.h, 1, kt, kn, 2, specs, 1000000, C.byref(g)))
         ctx.check(lib.ssb_group_update(g, _cols(capi, [(k, None, capi.INT64)]), _cols(capi, [(v, None, capi.DOUBLE)]), rows))
-        n, ko, ao = merge_group_partials(ctx, g, [capi.INT64], [capi.DOUBLE, capi.UINT64])
+        n, ko, ao = merge_group_partials(ctx, g, [capi.INT64], [capi.DOUBLE, capi.UINT64], comm=comm)
         cnt = np.zeros(n, dtype=np.uint64)
         ctx.d2h(cnt, ao[1].data)
         state["groups"], state["rows_counted"] = n, int(cnt.sum())
@@ -240,11 +240,12 @@ def group_by_aux(capi, ctx, rank, world, rows, dist, torch):
     assert state["rows_counted"] == world * rows, "COUNT(*) over all groups must equal the table's rows"
     return {"metric": "rows/sec, GroupAggregate(k; SUM(v DOUBLE), COUNT(*)), 1M INT64 keys (BASELINE config 3 shape)",
             "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(state["groups"]),
-            "seconds": best, "exchange": "all-gather of dense partial tables + ssb_group_merge" if world > 1 else "none",
+            "seconds": best, "exchange": "ssb_shard_group_merge: partial groups hash-partitioned by key, one all-to-all, the owner "
+                                         "merges, all-gather of the merged ranges (NCCL inside libssb200.so)" if world > 1 else "none",
             "algorithmic_gbs_per_gpu": rows * 16 / best / 1e9, "check": "sum of COUNT(*) == rows"}
 
 
-def q1_aux(capi, ctx, rank, world, rows, dist, torch):
+def q1_aux(capi, ctx, rank, world, rows, dist, torch, comm=None):
     """BASELINE config 5 shape (TPC-H Q1 on synthetic lineitem columns), row-range
     sharded: Filter(ship <= 2450) -> Compute(disc_price, charge) as ONE fused kernel launch, then
     GroupAggregate({rf, ls}; 5 x SUM, COUNT(*)); per-rank partial tables merged after an
@@ -290,7 +291,7 @@ def q1_aux(capi, ctx, rank, world, rows, dist, torch):
         return g
 
     def finish(g, tag):
-        ng, ko, ao = merge_group_partials(ctx, g, [I64, I64], [F64] * 5 + [capi.UINT64])
+        ng, ko, ao = merge_group_partials(ctx, g, [I64, I64], [F64] * 5 + [capi.UINT64], comm=comm)
         cnt = np.zeros(ng, dtype=np.uint64)
         ctx.d2h(cnt, ao[5].data)
         sums = np.zeros(ng, dtype=np.float64)
@@ -328,9 +329,10 @@ def q1_aux(capi, ctx, rank, world, rows, dist, torch):
     return {"metric": "rows/sec, Q1 shape: Filter(ship<=D) -> Compute(disc_price, charge) -> GroupAggregate({rf,ls}; 5xSUM, COUNT) (BASELINE config 5 shape)",
             "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "groups": int(state["groups"]),
             "seconds": best, "whole_table_two_step_seconds": unfused_best, "selectivity": kept_all / float(world * rows),
-            "kernels": "ssb_group_update_program: per 64M-row slice expr_kernel (filter+compute) then group_update_tiny_kernel",
+            "kernels": "ssb_group_update_program: per 64M-row slice ONE kernel, expr_sink_kernel<64,8> (filter + compute + "
+                       "aggregation into per-thread accumulators); the two-kernel form is timed beside it",
             "algorithmic_gbs_per_gpu": rows * 56 / best / 1e9, "check": "sum of COUNT(*) == rows kept by the filter; sliced == whole-table two-step (COUNT and SUM(charge) bit-exact)",
-            "exchange": "all-gather of 6-group partial tables + ssb_group_merge" if world > 1 else "none"}
+            "exchange": "ssb_shard_group_merge over the 6-group partial tables" if world > 1 else "none"}
 
 
 def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
@@ -537,12 +539,24 @@ def run_b200(args):
     for name in COLS:
         ctx.free(d_cols[name])
     ctx.free(d_out)
-    aux_group = group_by_aux(capi, ctx, rank, world, min(rows, args.group_rows), dist, torch)
-    aux_q1 = q1_aux(capi, ctx, rank, world, min(rows, args.q1_rows), dist, torch)
+    comm = None
+    if world > 1:
+        from supersonic_b200.distributed import make_comm
+        comm = make_comm(ctx)
+    aux_group = group_by_aux(capi, ctx, rank, world, min(rows, args.group_rows), dist, torch, comm)
+    aux_q1 = q1_aux(capi, ctx, rank, world, min(rows, args.q1_rows), dist, torch, comm)
     aux_join = hash_join_aux(capi, ctx, rank, world, min(rows, args.join_probe_rows),
                              max(1, min(rows, args.join_probe_rows) // 10), dist, torch)
+    if comm is not None:
+        comm.close()
     if rank == 0:
         result["aux"] = {"group_by": aux_group, "q1": aux_q1, "hash_join": aux_join}
+        # the sharded operators in one compact object (rows/s over all ranks, seconds per pass): the 1 -> N curves
+        # of the configurations whose timed region contains an exchange
+        result["scale_aux"] = {"unit": "rows/s",
+                               "group_by_c3": aux_group["value"], "group_by_c3_s": aux_group["seconds"],
+                               "q1_c5": aux_q1["value"], "q1_c5_s": aux_q1["seconds"],
+                               "hash_join_c4": aux_join["value"], "hash_join_c4_s": aux_join["seconds"]}
     # ---- end to end through the supersonic.h mirror with pinned host buffers: the headline table
     # itself (rows per GPU x 4 read columns = 32 GB of pinned host memory per rank) when the box has
     # the memory, else the largest table that leaves half of the available RAM free

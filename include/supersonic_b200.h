@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 /* supersonic::DataType numbering (proto/supersonic.proto:15-37). Fixed-width types only. */
 enum {
@@ -299,6 +299,41 @@ int ssb_scatter(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64
  * sort.cc:174-238). Stable (the reference is not: ties may differ). */
 int ssb_sort_permutation(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys,
                          const int32_t* descending, int64_t rows, int64_t* d_perm);
+
+/* ------------------------------------------------------------------ multi-GPU */
+/* One process per GPU; tables are sharded by contiguous row ranges. Compute / Project / Filter need no
+ * exchange (run ssb_program_run on the shard). The operators whose CPU form keeps global state exchange
+ * once: GroupAggregate (aggregate_groups.cc:332-433, one hash set over the whole input) and HashJoin
+ * (hash_join.cc:406-517, one index over the whole rhs). The reference itself is single-threaded; these
+ * entry points are what a sharded HashJoinOperation / GroupAggregate of the C++ layer calls.
+ * NCCL (over NVLink / NVSwitch) is bound at run time; every transfer is ordered on the context's stream. */
+typedef struct ssb_comm ssb_comm;
+#define SSB_COMM_ID_BYTES 128
+/* Rank 0 creates an id and hands it to the other ranks by any means (file, socket, MPI, torch.distributed). */
+int ssb_comm_unique_id(uint8_t* id /* [SSB_COMM_ID_BYTES] */);
+int ssb_comm_create(ssb_ctx* ctx, const uint8_t* id, int32_t world, int32_t rank, ssb_comm** out);
+/* Same, with the id passed through a file: rank 0 writes `path`, the others wait for it (timeout_s seconds). */
+int ssb_comm_create_file(ssb_ctx* ctx, const char* path, int32_t world, int32_t rank, int32_t timeout_s, ssb_comm** out);
+void ssb_comm_destroy(ssb_comm* comm);
+int32_t ssb_comm_rank(const ssb_comm* comm);
+int32_t ssb_comm_size(const ssb_comm* comm);
+/* h_recv[r] = the count rank r holds for this rank in its h_send[this rank] (HOST arrays of `size` entries). */
+int ssb_comm_exchange_counts(ssb_comm* comm, const int64_t* h_send, int64_t* h_recv);
+/* Ragged all-to-all of n_cols device columns in ONE grouped NCCL operation: column i is cut into `size`
+ * consecutive slices of send_rows[r] elements of width[i] bytes; slice r goes to rank r; the slices received
+ * from ranks 0..size-1 land consecutively in recv[i] (recv_rows[r] elements each). Asynchronous. */
+int ssb_comm_all_to_all(ssb_comm* comm, int32_t n_cols, const void* const* send, void* const* recv,
+                        const int32_t* width, const int64_t* send_rows, const int64_t* recv_rows);
+
+/* The exchange step of a row-range sharded GroupAggregate / ScalarAggregate ("a reduce for global aggregates"):
+ * every rank has aggregated its shard into `g`. The partial groups are hash-partitioned by key over the ranks,
+ * exchanged (one all-to-all), merged by the rank that owns the key -- a reduce-scatter by key, each rank
+ * merges about n_groups rows in total instead of (size - 1) x n_groups -- and the merged ranges are
+ * all-gathered, so that every rank ends with the whole result (groups in no particular order, as in
+ * the reference: aggregate_groups_test.cc:74-93 sorts before comparing). NULL keys and all-NULL aggregates
+ * travel with their is_null flags. Result columns are owned by `g` like those of ssb_group_finalize.
+ * Collective: every rank of `comm` must call it with a table of the same specification. Synchronises. */
+int ssb_shard_group_merge(ssb_comm* comm, ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb_column* agg_out);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,15 @@ def load():
         "ssb_sort_permutation": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I32), I64, P]),
         "ssb_program_plan": (C.c_int, [P, I32, I32, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32), I32, I32, I32, C.c_uint32,
                                        P, C.c_char_p, I32]),
+        "ssb_comm_unique_id": (C.c_int, [P]),
+        "ssb_comm_create": (C.c_int, [P, P, I32, I32, C.POINTER(P)]),
+        "ssb_comm_create_file": (C.c_int, [P, C.c_char_p, I32, I32, I32, C.POINTER(P)]),
+        "ssb_comm_destroy": (None, [P]),
+        "ssb_comm_rank": (I32, [P]),
+        "ssb_comm_size": (I32, [P]),
+        "ssb_comm_exchange_counts": (C.c_int, [P, C.POINTER(I64), C.POINTER(I64)]),
+        "ssb_comm_all_to_all": (C.c_int, [P, I32, C.POINTER(P), C.POINTER(P), C.POINTER(I32), C.POINTER(I64), C.POINTER(I64)]),
+        "ssb_shard_group_merge": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(Column), C.POINTER(Column)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -280,4 +289,32 @@ class Program(object):
     def close(self):
         if self.h:
             self.ctx.lib.ssb_program_destroy(self.h)
+            self.h = None
+
+
+COMM_ID_BYTES = 128
+
+
+class Comm(object):
+    """A communicator of libssb200.so (NCCL bound at run time) over the context's stream: one per rank.
+    `unique_id()` on rank 0, hand the bytes to the other ranks by any channel, then Comm(ctx, id, world, rank)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        rc = load().ssb_comm_unique_id(buf)
+        if rc != 0:
+            raise SsbError(rc, "ssb_comm_unique_id failed (is NCCL loadable?)")
+        return bytes(buf)
+
+    def __init__(self, ctx, unique_id, world, rank):
+        self.ctx, self.world, self.rank = ctx, world, rank
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ssb_comm_create(ctx.h, buf, world, rank, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ssb_comm_destroy(self.h)
             self.h = None

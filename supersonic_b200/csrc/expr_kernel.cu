@@ -1181,7 +1181,18 @@ static int launch_program(ssb_program* sp, const ssb_column* inputs, int64_t row
   if (p.has_pred && grid > 768) grid = 768;   // the wave scan reads at most 768 status words
   if (grid > p.num_tiles) grid = p.num_tiles;
   TimedRegion timed(ctx);
-  var.kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);
+  if (p.has_pred) {
+    // Filter: the CTAs of a wave read each other's kept-row counts (the wave-synchronous prefix spins
+    // on status words of CTAs with higher indices), so the whole grid must be resident at once. The
+    // grid is sized from the occupancy query, but only a cooperative launch makes co-residency a
+    // guarantee when other kernels (the second streaming lane, another context) share the device:
+    // the runtime then starts the grid only when all of it fits, or fails the launch.
+    void* args[] = {&p};
+    SSB_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(var.kernel), dim3(static_cast<unsigned>(grid)),
+                                              dim3(var.threads + 32), args, prog.smem_bytes, ctx->stream));
+  } else {
+    var.kernel<<<static_cast<unsigned>(grid), var.threads + 32, prog.smem_bytes, ctx->stream>>>(p);
+  }
   ++ctx->launches;
   SSB_CUDA(ctx, cudaGetLastError());
   return 0;

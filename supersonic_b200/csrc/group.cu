@@ -23,6 +23,7 @@
 
 #include <vector>
 
+#include "comm.h"
 #include "common.h"
 #include "group_device.h"
 #include "program.h"
@@ -903,6 +904,9 @@ __global__ void fill_records_kernel(unsigned long long* rec, unsigned long long 
 }
 
 // Fills a u64 array with a value (accumulator identities, empty keys).
+__global__ void iota_rows_kernel(long long* p, long long n) {
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) p[i] = i;
+}
 __global__ void fill_u64_kernel(unsigned long long* p, unsigned long long n, unsigned long long v) {
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
@@ -1553,6 +1557,181 @@ int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb
     agg_out[a].reserved = 0;
   }
   *n_groups = n;
+  return 0;
+}
+
+// ---- the exchange step of the row-range sharded aggregate ------------------------------------
+// Reduce-scatter by key: the dense partial table is hash-partitioned over the ranks, every rank
+// merges the partial rows of the keys it owns (about n_groups rows in total, whatever the number of
+// ranks) and the merged ranges are all-gathered. is_null flags travel as one byte per row.
+int ssb_shard_group_merge(ssb_comm* comm, ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb_column* agg_out) {
+  ssb_ctx* ctx = g->ctx;
+  if (comm_ctx(comm) != ctx) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "the communicator and the table live on different contexts");
+  if (g->has_first_last) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "FIRST / LAST over sharded input (the row order across shards is not carried)");
+  const int W = comm_world(comm), rank = comm_rank(comm);
+  int64_t n = 0;
+  if (int rc = ssb_group_finalize(g, &n, key_out, agg_out)) return rc;
+  if (W == 1) { *n_groups = n; return 0; }
+  const int NK = g->n_keys, NA = g->n_aggs, NC = NK + NA;
+  // ---- 1. rows per owner: hash partition of the partial groups (a scalar aggregate's single row goes to rank 0)
+  std::vector<int64_t> send_rows(W, 0), recv_rows(W, 0);
+  long long* perm = nullptr;
+  SSB_CUDA(ctx, tmp_malloc(ctx, &perm, static_cast<size_t>(n > 0 ? n : 1) * 8));
+  int rc = 0;
+  if (NK == 0) {
+    send_rows[0] = n;
+    iota_rows_kernel<<<1, 32, 0, ctx->stream>>>(perm, n);
+  } else {
+    rc = ssb_partition_rows(ctx, NK, key_out, n, W, 0, reinterpret_cast<int64_t*>(perm), send_rows.data());
+  }
+  // every column travels as values (8 bytes per row: the result containers) + one is_null byte per row
+  struct Col { void* vals; uint8_t* nulls; void* rvals; uint8_t* rnulls; const ssb_column* src; };
+  std::vector<Col> cols(NC);
+  for (int i = 0; i < NC; ++i) { cols[i].vals = nullptr; cols[i].nulls = nullptr; cols[i].rvals = nullptr; cols[i].rnulls = nullptr; cols[i].src = i < NK ? &key_out[i] : &agg_out[i - NK]; }
+  uint8_t* bytes = nullptr;
+  auto cleanup = [&]() {
+    for (int i = 0; i < NC; ++i) { tmp_free(ctx, cols[i].vals); tmp_free(ctx, cols[i].nulls); tmp_free(ctx, cols[i].rvals); tmp_free(ctx, cols[i].rnulls); }
+    tmp_free(ctx, perm);
+    tmp_free(ctx, bytes);
+  };
+  const size_t cap = static_cast<size_t>(n > 0 ? n : 1);
+  if (rc == 0 && tmp_malloc(ctx, &bytes, cap + 64) != cudaSuccess) rc = fail(ctx, SSB_ERROR_MEMORY_EXCEEDED, "sharded aggregate scratch");
+  for (int i = 0; i < NC && rc == 0; ++i) {
+    const int w = width_of(cols[i].src->dtype);
+    if (tmp_malloc_bytes(ctx, &cols[i].vals, cap * 8 + 64) != cudaSuccess || tmp_malloc(ctx, &cols[i].nulls, cap + 64) != cudaSuccess) {
+      rc = fail(ctx, SSB_ERROR_MEMORY_EXCEEDED, "sharded aggregate send buffers");
+      break;
+    }
+    if (n == 0) continue;
+    ssb_column src = *cols[i].src, dst;
+    src.nulls = nullptr;
+    dst.data = cols[i].vals; dst.nulls = nullptr; dst.dtype = src.dtype; dst.reserved = 0;
+    rc = ssb_gather(ctx, &src, reinterpret_cast<const int64_t*>(perm), n, &dst);
+    if (rc) break;
+    if (cols[i].src->nulls != nullptr) {
+      rc = ssb_nulls_unpack(ctx, cols[i].src->nulls, n, bytes);
+      ssb_column bs, bd;
+      bs.data = bytes; bs.nulls = nullptr; bs.dtype = SSB_BOOL; bs.reserved = 0;
+      bd.data = cols[i].nulls; bd.nulls = nullptr; bd.dtype = SSB_BOOL; bd.reserved = 0;
+      if (rc == 0) rc = ssb_gather(ctx, &bs, reinterpret_cast<const int64_t*>(perm), n, &bd);
+    } else {
+      cudaMemsetAsync(cols[i].nulls, 0, cap, ctx->stream);
+    }
+    (void)w;
+  }
+  if (rc) { cleanup(); return rc; }
+  // ---- 2. exchange: counts, then all columns in one grouped NCCL operation
+  if ((rc = comm_exchange_counts(comm, send_rows.data(), recv_rows.data()))) { cleanup(); return rc; }
+  int64_t got = 0;
+  for (int r = 0; r < W; ++r) got += recv_rows[r];
+  const size_t rcap = static_cast<size_t>(got > 0 ? got : 1);
+  std::vector<const void*> sp;
+  std::vector<void*> rp;
+  std::vector<int32_t> widths;
+  for (int i = 0; i < NC && rc == 0; ++i) {
+    if (tmp_malloc_bytes(ctx, &cols[i].rvals, rcap * 8 + 64) != cudaSuccess || tmp_malloc(ctx, &cols[i].rnulls, rcap + 64) != cudaSuccess) {
+      rc = fail(ctx, SSB_ERROR_MEMORY_EXCEEDED, "sharded aggregate receive buffers");
+      break;
+    }
+    const int w = width_of(cols[i].src->dtype);
+    sp.push_back(cols[i].vals); rp.push_back(cols[i].rvals); widths.push_back(w);
+    sp.push_back(cols[i].nulls); rp.push_back(cols[i].rnulls); widths.push_back(1);
+  }
+  if (rc == 0) rc = comm_all_to_all_v(comm, static_cast<int>(sp.size()), sp.data(), rp.data(), widths.data(), send_rows.data(), recv_rows.data());
+  if (rc) { cleanup(); return rc; }
+  // ---- 3. merge the received partial rows of the keys this rank owns
+  ssb_group* m = nullptr;
+  rc = ssb_group_create(ctx, NK, g->key_types.data(), g->key_nullable.data(), NA, g->aggs.data(), got > 0 ? got : 1, &m);
+  std::vector<ssb_column> mk(NK ? NK : 1), ma(NA ? NA : 1);
+  std::vector<uint32_t*> bitmaps;
+  for (int i = 0; i < NC && rc == 0; ++i) {
+    ssb_column& c = i < NK ? mk[i] : ma[i - NK];
+    c.data = cols[i].rvals; c.dtype = cols[i].src->dtype; c.reserved = 0; c.nulls = nullptr;
+    if (cols[i].src->nulls != nullptr && got > 0) {
+      uint32_t* bm = nullptr;
+      if (tmp_malloc(ctx, &bm, (rcap / 32 + 2) * 4 + 64) != cudaSuccess) { rc = fail(ctx, SSB_ERROR_MEMORY_EXCEEDED, "sharded aggregate bitmaps"); break; }
+      bitmaps.push_back(bm);
+      rc = ssb_nulls_pack(ctx, cols[i].rnulls, got, bm);
+      c.nulls = bm;
+    }
+  }
+  if (rc == 0 && got > 0) rc = ssb_group_merge(m, got, mk.data(), ma.data());
+  int64_t mine = 0;
+  std::vector<ssb_column> fk(NK ? NK : 1), fa(NA ? NA : 1);
+  if (rc == 0) {
+    if (got > 0 || (NK == 0 && rank == 0)) rc = ssb_group_finalize(m, &mine, fk.data(), fa.data());
+    if (NK == 0 && rank != 0) mine = 0;   // the scalar row lives on rank 0
+  }
+  for (size_t i = 0; i < bitmaps.size(); ++i) tmp_free(ctx, bitmaps[i]);
+  // ---- 4. all-gather the merged ranges: every rank ends with the whole result
+  std::vector<int64_t> all_rows(W, 0);
+  if (rc == 0) rc = comm_all_gather_counts(comm, &mine, 1, all_rows.data());
+  int64_t total = 0;
+  for (int r = 0; r < W; ++r) total += all_rows[r];
+  if (rc == 0) {
+    // result storage of `g` (as ssb_group_finalize lays it out), grown to the global group count
+    const long long need = total > 0 ? total : 1;
+    if (g->out_capacity < need) {
+      for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, g->key_out[c]); tmp_free(ctx, g->key_out_nulls[c]); g->key_out[c] = nullptr; g->key_out_nulls[c] = nullptr; }
+      for (int a = 0; a < kMaxAggs; ++a) { tmp_free(ctx, g->agg_out[a]); tmp_free(ctx, g->agg_out_nulls[a]); g->agg_out[a] = nullptr; g->agg_out_nulls[a] = nullptr; }
+      cudaError_t e = cudaSuccess;
+      for (int c = 0; c < NK && e == cudaSuccess; ++c) {
+        e = tmp_malloc_bytes(ctx, &g->key_out[c], static_cast<size_t>(need) * 8 + 128);
+        if (e == cudaSuccess) e = tmp_malloc(ctx, &g->key_out_nulls[c], static_cast<size_t>(need / 32 + 2) * 4 + 128);
+      }
+      for (int a = 0; a < NA && e == cudaSuccess; ++a) {
+        e = tmp_malloc_bytes(ctx, &g->agg_out[a], static_cast<size_t>(need) * 8 + 128);
+        if (e == cudaSuccess) e = tmp_malloc(ctx, &g->agg_out_nulls[a], static_cast<size_t>(need / 32 + 2) * 4 + 128);
+      }
+      if (e != cudaSuccess) rc = cuda_fail(ctx, e, "sharded aggregate result");
+      g->out_capacity = need;
+    }
+  }
+  std::vector<uint8_t*> gathered_nulls(NC, nullptr), my_nulls(NC, nullptr);
+  if (rc == 0) {
+    sp.clear(); rp.clear(); widths.clear();
+    for (int i = 0; i < NC && rc == 0; ++i) {
+      const ssb_column& f = i < NK ? fk[i] : fa[i - NK];
+      const int w = width_of(cols[i].src->dtype);
+      void* dst = i < NK ? g->key_out[i] : g->agg_out[i - NK];
+      sp.push_back(mine > 0 ? f.data : dst); rp.push_back(dst); widths.push_back(w);
+      if (cols[i].src->nulls != nullptr) {
+        if (tmp_malloc(ctx, &gathered_nulls[i], static_cast<size_t>(total > 0 ? total : 1) + 64) != cudaSuccess ||
+            tmp_malloc(ctx, &my_nulls[i], static_cast<size_t>(mine > 0 ? mine : 1) + 64) != cudaSuccess) {
+          rc = fail(ctx, SSB_ERROR_MEMORY_EXCEEDED, "sharded aggregate is_null bytes");
+          break;
+        }
+        if (mine > 0) {
+          if (f.nulls != nullptr) rc = ssb_nulls_unpack(ctx, f.nulls, mine, my_nulls[i]);
+          else cudaMemsetAsync(my_nulls[i], 0, static_cast<size_t>(mine), ctx->stream);
+        }
+        sp.push_back(my_nulls[i]); rp.push_back(gathered_nulls[i]); widths.push_back(1);
+      }
+    }
+    if (rc == 0) rc = comm_all_gather_v(comm, static_cast<int>(sp.size()), sp.data(), rp.data(), widths.data(), all_rows.data());
+    for (int i = 0; i < NC && rc == 0; ++i) {
+      if (gathered_nulls[i] == nullptr || total == 0) continue;
+      rc = ssb_nulls_pack(ctx, gathered_nulls[i], total, i < NK ? g->key_out_nulls[i] : g->agg_out_nulls[i - NK]);
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < NC; ++i) { tmp_free(ctx, gathered_nulls[i]); tmp_free(ctx, my_nulls[i]); }
+  if (m) ssb_group_destroy(m);
+  cleanup();
+  if (rc) return rc;
+  for (int c = 0; c < NK; ++c) {
+    key_out[c].data = g->key_out[c];
+    key_out[c].nulls = g->key_nullable[c] ? g->key_out_nulls[c] : nullptr;
+    key_out[c].dtype = g->key_types[c];
+    key_out[c].reserved = 0;
+  }
+  for (int a = 0; a < NA; ++a) {
+    agg_out[a].data = g->agg_out[a];
+    agg_out[a].nulls = g->aggs[a].fn == SSB_AGG_COUNT ? nullptr : g->agg_out_nulls[a];
+    agg_out[a].dtype = g->aggs[a].out_type;
+    agg_out[a].reserved = 0;
+  }
+  *n_groups = total;
   return 0;
 }
 

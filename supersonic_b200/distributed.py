@@ -50,7 +50,27 @@ class _DevArray(object):
 _TYPESTR = {1: "<i4", 2: "<i8", 3: "<i8", 4: "<i8", 5: "<f8", 6: "|u1", 8: "<i4", 9: "<f4", 10: "<i4", 13: "<i4"}
 
 
-def merge_group_partials(ctx, g, key_types, agg_types, group=None):
+def make_comm(ctx, group=None):
+    """A libssb200 communicator (ssb_comm_*, NCCL inside the library, on the context's stream) for the
+    ranks of a torch.distributed process group: torch only carries the 128-byte id from rank 0."""
+    import torch
+    import torch.distributed as dist
+    from supersonic_b200 import capi
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if dist.get_backend(group) == "nccl":
+        ident = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(ident.cpu().numpy().tobytes())
+    else:
+        box = [capi.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        raw = box[0]
+    return capi.Comm(ctx, raw, world, rank)
+
+
+def merge_group_partials(ctx, g, key_types, agg_types, group=None, comm=None):
     """The exchange step of a row-range sharded GroupAggregate / ScalarAggregate:
     every rank finalizes its table `g` into dense partial columns, the partials are all-gathered
     (NCCL) and the other ranks' rows are added with ssb_group_merge; after the call every rank
@@ -66,6 +86,11 @@ def merge_group_partials(ctx, g, key_types, agg_types, group=None):
 
     n = C.c_int64()
     ko, ao = cols(len(key_types)), cols(len(agg_types))
+    if comm is not None:
+        # the library's own exchange: reduce-scatter by key hash + all-gather (ssb_shard_group_merge); NULL
+        # keys and all-NULL aggregates travel with their is_null flags
+        ctx.check(lib.ssb_shard_group_merge(comm.h, g, C.byref(n), ko, ao))
+        return n.value, ko, ao
     ctx.check(lib.ssb_group_finalize(g, C.byref(n), ko, ao))
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
@@ -76,6 +101,10 @@ def merge_group_partials(ctx, g, key_types, agg_types, group=None):
         return torch.as_tensor(_DevArray(col.data, n.value, _TYPESTR[dtype]), device="cuda") if n.value else \
             torch.empty(0, dtype=_torch_dtype(dtype), device="cuda")
 
+    # this torch-collective form carries no is_null flags: refuse tables whose partials can be NULL instead of
+    # merging placeholder values; ssb_shard_group_merge (comm=...) handles them
+    if any(ko[i].nulls for i in range(len(key_types))):
+        raise ValueError("merge_group_partials without a communicator needs NOT NULL keys; pass comm=make_comm(ctx)")
     gk = [allgather_ragged(view(ko[i], t), group) for i, t in enumerate(key_types)]
     ga = [allgather_ragged(view(ao[i], t), group) for i, t in enumerate(agg_types)]
     torch.cuda.synchronize()

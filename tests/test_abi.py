@@ -13,7 +13,7 @@ def test_header_symbols_exported(built):
     assert len(names) >= 35
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.ssb_abi_version() == 1
+    assert lib.ssb_abi_version() == 2
 
 
 def test_no_device_fails_loudly(built):

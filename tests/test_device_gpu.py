@@ -77,6 +77,56 @@ def test_c2_device_resident_bit_exact(ctx, rows, k):
         ctx.free(p)
 
 
+def test_two_contexts_filter_concurrently(built):
+    """Two contexts (streams) run Filter kernels at the same time, as the two lanes of the streaming cursor do.
+    The kernel's CTAs wait on each other's kept-row counts, so each grid must be resident as a whole: the
+    cooperative launch guarantees it whatever else shares the device. Forty launches per
+    context from two host threads; every result must equal the host's."""
+    import threading
+    rows = 6_000_011
+    k = 1 << 19
+    want = None
+    a, b, c_, dd = (host_col(x, rows, 0) for x in "abcd")
+    want = (a * b + c_)[dd < k]
+    errors = []
+
+    def worker(tag):
+        try:
+            cx = capi.Context(0)
+            d = {}
+            for name in "abcd":
+                kind, lo, span = GEN[name]
+                d[name] = cx.malloc(rows * 8 + 256)
+                cx.generate(d[name], rows, 0, 42, "abcd".index(name), kind, lo, span)
+            out = cx.malloc(rows * 8 + 256)
+            prog = c2_program(cx, k)
+            for it in range(40):
+                kept = prog.run_sync([(d[c], None, capi.INT64) for c in "abcd"], rows, [(out, None, capi.INT64)])
+                if kept != len(want):
+                    errors.append((tag, it, kept))
+                    break
+                if it % 13 == 0:
+                    got = np.empty(kept, dtype=np.int64)
+                    cx.d2h(got, out)
+                    if not np.array_equal(got, want):
+                        errors.append((tag, it, "values"))
+                        break
+            prog.close()
+            for ptr in list(d.values()) + [out]:
+                cx.free(ptr)
+            cx.close()
+        except Exception as e:   # noqa: BLE001
+            errors.append((tag, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not any(t.is_alive() for t in threads), "a Filter kernel did not finish (co-residency deadlock)"
+    assert not errors, errors
+
+
 def test_filter_is_idempotent_and_order_preserving(ctx):
     rows = 20_000_000
     dcol = ctx.malloc(rows * 8 + 256)

@@ -123,3 +123,142 @@ def test_sharded_sort_null_keys_two_gpus_matches_oracle(ref):
         pytest.skip("needs two GPUs")
     from test_multi_gpu import check_null_sort_against_oracle
     check_null_sort_against_oracle(ref, 2, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# ssb_comm_* / ssb_shard_group_merge: the C ABI's own exchange (NCCL inside libssb200.so)
+def _group_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import ctypes as C
+        from supersonic_b200 import capi
+        from supersonic_b200.distributed import make_comm, merge_group_partials
+        ctx = capi.Context(rank)
+        comm = make_comm(ctx)
+        t = _group_tables()
+        n = len(t["k"])
+        b, e = shard_rows(n, rank, world, align=32)
+        res = {}
+        for name, keys, aggs in _GROUP_PLANS:
+            def up(col):
+                arr = np.ascontiguousarray(t[col][b:e])
+                ptr = ctx.malloc(arr.nbytes + 256)
+                ctx.h2d(ptr, arr)
+                nptr = None
+                if col + "_null" in t:
+                    nl = t[col + "_null"][b:e]
+                    words = np.packbits(np.concatenate([nl.astype(np.uint8), np.zeros((-len(nl)) % 32 + 32, np.uint8)]), bitorder="little")
+                    nptr = ctx.malloc(words.nbytes + 256)
+                    ctx.h2d(nptr, words)
+                return ptr, nptr
+            DT = {"k": capi.INT64, "k2": capi.INT32, "v": capi.DOUBLE, "w": capi.INT64}
+            NPT = {capi.INT64: np.int64, capi.INT32: np.int32, capi.DOUBLE: np.float64, capi.UINT64: np.uint64}
+            specs = (capi.AggSpec * len(aggs))()
+            vals, vidx = [], {}
+            for i, (fn, col, out_t) in enumerate(aggs):
+                specs[i].fn, specs[i].out_type = fn, out_t
+                if col is None:
+                    specs[i].input, specs[i].in_type = -1, capi.INT64
+                else:
+                    if col not in vidx:
+                        vidx[col] = len(vals)
+                        vals.append(col)
+                    specs[i].input, specs[i].in_type, specs[i].in_nullable = vidx[col], DT[col], 1 if col + "_null" in t else 0
+            kt = (C.c_int32 * max(1, len(keys)))(*[DT[c] for c in keys])
+            kn = (C.c_int32 * max(1, len(keys)))(*[1 if c + "_null" in t else 0 for c in keys])
+            g = C.c_void_p()
+            ctx.check(ctx.lib.ssb_group_create(ctx.h, len(keys), kt, kn, len(aggs), specs, 0, C.byref(g)))
+            kc = (capi.Column * max(1, len(keys)))()
+            for i, c in enumerate(keys):
+                p_, n_ = up(c)
+                kc[i].data, kc[i].nulls, kc[i].dtype = p_, n_, DT[c]
+            vc = (capi.Column * max(1, len(vals)))()
+            for i, c in enumerate(vals):
+                p_, n_ = up(c)
+                vc[i].data, vc[i].nulls, vc[i].dtype = p_, n_, DT[c]
+            ctx.check(ctx.lib.ssb_group_update(g, kc, vc, e - b))
+            ng, ko, ao = merge_group_partials(ctx, g, [DT[c] for c in keys], [a[2] for a in aggs], comm=comm)
+
+            def down(col, dt):
+                a = np.empty(ng, dtype=NPT[dt])
+                isn = np.zeros(ng, dtype=bool)
+                if ng:
+                    ctx.d2h(a, col.data)
+                    if col.nulls:
+                        w = np.empty((ng + 31) // 32, dtype=np.uint32)
+                        ctx.d2h(w, col.nulls)
+                        isn = np.unpackbits(w.view(np.uint8), bitorder="little")[:ng].astype(bool)
+                return a, isn
+            res[name] = ([down(ko[i], DT[c]) for i, c in enumerate(keys)], [down(ao[i], a[2]) for i, a in enumerate(aggs)])
+            ctx.lib.ssb_group_destroy(g)
+        comm.close()
+        out.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _group_tables():
+    rng = np.random.default_rng(99)
+    n = 400_000
+    k = rng.integers(0, 5000, n)
+    return {"k": k, "k_null": rng.random(n) < 0.01,
+            "k2": rng.integers(0, 3, n).astype(np.int32),
+            "v": rng.integers(0, 1 << 20, n) / 1024.0, "v_null": (k % 7 == 0) | (rng.random(n) < 0.05),
+            "w": rng.integers(-10**6, 10**6, n)}
+
+
+# (name, key columns, [(fn, value column or None, out type)])
+_GROUP_PLANS = [
+    ("one_key", ["k"], [(0, "v", 5), (3, None, 3), (1, "w", 2), (2, "v", 5), (3, "v", 3)]),
+    ("two_keys", ["k", "k2"], [(0, "w", 2), (3, None, 3)]),
+    ("scalar", [], [(0, "w", 2), (2, "v", 5), (3, None, 3)]),
+]
+
+
+def test_shard_group_merge_two_gpus_matches_oracle(ref):
+    """ssb_shard_group_merge (reduce-scatter by key hash + all-gather inside libssb200.so) over two ranks against the
+    oracle's GroupAggregate over the whole table: NULL keys form a group, all-NULL inputs give NULL (the `v` of every
+    seventh key is always NULL), every rank ends with the whole result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from supersonic_b200 import ssplan as sp
+    from cases import same_results  # noqa: F401
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_group_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in procs:
+        rank, res = out.get(timeout=600)
+        got[rank] = res
+    for p in procs:
+        p.join(timeout=60)
+    t = _group_tables()
+    # the value column's NULLs depend on the key so that some groups are all-NULL
+    cols = [sp.Column("k", sp.INT64, t["k"], is_null=t["k_null"]), sp.Column("k2", sp.INT32, t["k2"]),
+            sp.Column("v", sp.DOUBLE, t["v"], is_null=t["v_null"]), sp.Column("w", sp.INT64, t["w"])]
+    FN = {0: "SUM", 1: "MIN", 2: "MAX", 3: "COUNT"}
+    for name, keys, aggs in _GROUP_PLANS:
+        spec = " ".join('(%s %s a%d)' % (FN[fn], '""' if col is None else col, i) for i, (fn, col, _) in enumerate(aggs))
+        plan = ("(group (named %s) (aggs %s) (scan 0))" % (" ".join(keys), spec)) if keys else "(scalar_agg (aggs %s) (scan 0))" % spec
+        want = ref.run(plan, [cols])
+        assert want.code == 0, want.error
+        for rank in (0, 1):
+            kcols, acols = got[rank][name]
+            n = len(acols[0][0])
+            assert n == want.rows, (name, rank, n, want.rows)
+            gv = [np.where(isn, 0, a) for a, isn in kcols + acols]
+            gn = [isn for _, isn in kcols + acols]
+            wv = [np.where(want.nulls[i] if want.nulls[i] is not None else False, 0, want.columns[i]) for i in range(len(want.columns))]
+            wn = [want.nulls[i] if want.nulls[i] is not None else np.zeros(want.rows, bool) for i in range(len(want.columns))]
+            nk = len(keys)
+            og = np.lexsort([x for i in reversed(range(nk)) for x in (gv[i], gn[i])]) if nk else np.arange(n)
+            ow = np.lexsort([x for i in reversed(range(nk)) for x in (wv[i], wn[i])]) if nk else np.arange(n)
+            for i in range(len(gv)):
+                assert np.array_equal(gn[i][og], wn[i][ow]), (name, rank, i, "null flags")
+                assert np.array_equal(gv[i][og], wv[i][ow]), (name, rank, i, "values")

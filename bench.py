@@ -387,10 +387,14 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
                                                   [(tens["pk"], I64)], [(tens["pay"], I64)], join_type=0, uniqueness=1)
                 state["pairs"] = int(rows_.numel())
             return once_
-        # the redistributing form (hash partition + all-to-all), timed for the record ...
+        # the other two forms, timed for the record: probe rows redistributed (hash partition + three all-to-alls),
+        # and the whole build side all-gathered with the whole table built on every rank ...
         a2a_best, _ = _timed(ctx, world, dist, torch, run_with("all_to_all"), repeats=1)
         state["all_to_all_seconds"] = a2a_best
-        # ... and the form "auto" picks for this shape: the build side is small enough to all-gather
+        bc_best, _ = _timed(ctx, world, dist, torch, run_with("broadcast"), repeats=1)
+        state["broadcast_seconds"] = bc_best
+        # ... and the form "auto" picks for this shape (UNIQUE single-column key, small build side): every rank
+        # builds the table of one hash part, the tables are all-gathered, no probe row moves
         once = run_with("auto")
     best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
     pairs = state["pairs"]
@@ -409,8 +413,10 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
             "value": world * probe_rows / best, "unit": "rows/s", "probe_rows_per_gpu": probe_rows,
             "build_rows_per_gpu": build_rows, "pairs": pairs, "seconds": best,
             "algorithmic_gbs_per_gpu": alg / best / 1e9, "check": "pairs == probe rows (every fk has one pk)",
-            "exchange": ("auto -> all-gather of the build side (keys + payload) over NCCL, local probe; the "
-                         "all-to-all form (hash partition, 3 all-to-alls) took %.4f s" % state["all_to_all_seconds"])
+            "exchange": ("auto -> replicate: build rows to the owner of their key's hash part (all-to-all), one table per "
+                         "rank, all-gather of the tables + payload, local probe of the key's part; for the record: "
+                         "all-to-all form %.4f s, broadcast form (whole table built on every rank) %.4f s"
+                         % (state["all_to_all_seconds"], state["broadcast_seconds"]))
             if world > 1 else "none"}
 
 

@@ -273,6 +273,17 @@ void ssb_join_destroy(ssb_join* j);
 int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type,
                    int64_t* n_pairs, const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
 
+/* The replicated form of the sharded join (UNIQUE single-column keys): the build side is
+ * hash-partitioned over the ranks (ssb_partition_rows), every rank builds the index of the part it
+ * received (ssb_join_build), the tables are all-gathered, and ssb_join_attach_parts makes an index over
+ * the `n_parts` gathered tables: a probe looks its key up in the table of the key's part and reports
+ * rhs rows as row_offsets[part] + (row inside that part's build input). No probe row ever moves and the
+ * output keeps lhs order (hash_join.cc:793-831). ssb_join_table exposes a built table: `capacity`
+ * (a power of two) slots of 16 bytes. The attached index owns none of the tables. */
+int ssb_join_table(const ssb_join* j, const void** d_slots, int64_t* capacity);
+int ssb_join_attach_parts(ssb_ctx* ctx, int32_t key_type, int32_t n_parts, const void* const* d_slots,
+                          const int64_t* capacities, const int64_t* row_offsets, ssb_join** out);
+
 /* Stable hash partition of rows for the multi-GPU join redistribution (the reference
  * has no counterpart: cursor/core/hash_join.cc runs on one thread). part(row) = high bits of
  * the join key hash scaled to [0, n_parts); integer keys of different widths hash alike, so the

@@ -43,6 +43,17 @@ struct JoinTable {
   long long* run_rows;            // build rows grouped by slot, insertion order
 };
 
+// The replicated form of the sharded join: the build side is hash-partitioned over the
+// ranks, every rank builds the table of its part, the tables are all-gathered, and a probe looks a
+// key up in the table of the key's part. rhs rows are reported as row_offset[part] + row.
+enum { kJoinMaxParts = 16 };
+struct JoinParts {
+  int32_t n_parts;                                  // 0 = one local table (JoinTable)
+  const unsigned long long* slots[kJoinMaxParts];
+  unsigned long long mask[kJoinMaxParts];           // capacity - 1
+  long long row_offset[kJoinMaxParts];
+};
+
 __device__ __forceinline__ unsigned long long jmix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
   return x;
@@ -208,11 +219,13 @@ __global__ void __launch_bounds__(256) join_emit_kernel(JoinTable t, long long r
 // aux: [0] ticket, [1] total pairs, [2 ..] one status word per tile.
 enum { kProbeThreads = 256, kProbeRows = 4, kProbeTile = kProbeThreads * kProbeRows };   // 8 rows per thread measured slower (114 registers: 9.7 ms vs 7.6 ms per 200M probes)
 
+template <bool PARTS>
 __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTable t, JoinKeys build, JoinKeys probe,
                                                                            long long rows, int left_outer,
                                                                            long long* __restrict__ lhs_out,
                                                                            long long* __restrict__ rhs_out,
-                                                                           unsigned long long* __restrict__ aux) {
+                                                                           unsigned long long* __restrict__ aux,
+                                                                           const __grid_constant__ JoinParts parts) {
   __shared__ unsigned int s_tile;
   __shared__ unsigned int wcnt[kProbeRows][kProbeThreads / 32];
   __shared__ unsigned long long s_base;
@@ -230,17 +243,31 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
     unsigned long long first[kProbeRows], slot[kProbeRows];
     ulonglong2 ent[kProbeRows];
     bool live[kProbeRows];
-    const unsigned long long mask = t.capacity - 1;
+    // the table of the row's key: the one local table, or the table of the key's hash part
+    const unsigned long long* tab[kProbeRows];
+    unsigned long long mask[kProbeRows];
+    long long offset[kProbeRows];
     // hash and first table probe of all four rows before any of them is looked at
 #pragma unroll
     for (int j = 0; j < kProbeRows; ++j) {
       const long long row = r0 + j * kProbeThreads;
       live[j] = row < rows && !key_has_null(probe, row);
       first[j] = 0;
-      slot[j] = live[j] ? (key_hash(probe, row, &first[j]) & mask) : 0ull;
+      const unsigned long long h = live[j] ? key_hash(probe, row, &first[j]) : 0ull;
+      if (PARTS) {
+        const unsigned int part = static_cast<unsigned int>(((h >> 32) * static_cast<unsigned long long>(parts.n_parts)) >> 32);   // = part_id_kernel
+        tab[j] = parts.slots[part];
+        mask[j] = parts.mask[part];
+        offset[j] = parts.row_offset[part];
+      } else {
+        tab[j] = t.slots;
+        mask[j] = t.capacity - 1;
+        offset[j] = 0;
+      }
+      slot[j] = h & mask[j];
     }
 #pragma unroll
-    for (int j = 0; j < kProbeRows; ++j) ent[j] = __ldg(reinterpret_cast<const ulonglong2*>(t.slots) + slot[j]);
+    for (int j = 0; j < kProbeRows; ++j) ent[j] = __ldg(reinterpret_cast<const ulonglong2*>(tab[j]) + slot[j]);
 #pragma unroll
     for (int j = 0; j < kProbeRows; ++j) {
       const long long row = r0 + j * kProbeThreads;
@@ -251,9 +278,10 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
       for (;;) {
         const long long h = static_cast<long long>(e.y);
         if (h == 0) break;
-        if (e.x == first[j] && keys_equal(probe, row, build, h - 1)) { head[j] = h - 1; break; }
-        sl = (sl + 1) & mask;
-        e = __ldg(reinterpret_cast<const ulonglong2*>(t.slots) + sl);
+        // PARTS: single-column keys only (host-checked), the slot word is the whole key
+        if (e.x == first[j] && (PARTS || keys_equal(probe, row, build, h - 1))) { head[j] = offset[j] + h - 1; break; }
+        sl = (sl + 1) & mask[j];
+        e = __ldg(reinterpret_cast<const ulonglong2*>(tab[j]) + sl);
       }
     }
     if (left_outer) {
@@ -340,6 +368,7 @@ struct ssb_join {
   long long build_rows;
   int uniqueness;
   JoinTable table;
+  JoinParts parts;        // n_parts > 0: an index over tables built elsewhere (ssb_join_attach_parts); owns none of them
   long long* lhs_out;
   long long* rhs_out;
 };
@@ -350,7 +379,7 @@ void ssb_join_destroy(ssb_join* j) {
   if (!j) return;
   ssb_ctx* ctx = j->ctx;
   cudaStreamSynchronize(ctx->stream);
-  tmp_free(ctx, j->table.slots);
+  if (j->parts.n_parts == 0) tmp_free(ctx, j->table.slots);
   tmp_free(ctx, j->table.run_start);
   tmp_free(ctx, j->table.run_count);
   tmp_free(ctx, j->table.run_rows);
@@ -472,8 +501,13 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
     cudaMemsetAsync(aux, 0, static_cast<size_t>(tiles + 2) * 8, ctx->stream);
     long long grid = static_cast<long long>(ctx->num_sms) * 4;
     if (grid > tiles) grid = tiles;
-    join_probe_unique_kernel<<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
-        j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux);
+    if (j->parts.n_parts > 0) {
+      join_probe_unique_kernel<true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts);
+    } else {
+      join_probe_unique_kernel<false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts);
+    }
     ++ctx->launches;
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_count, aux + 1, 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -521,6 +555,37 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
   *n_pairs = static_cast<int64_t>(total);
   *d_lhs_rows = reinterpret_cast<const int64_t*>(j->lhs_out);
   *d_rhs_rows = reinterpret_cast<const int64_t*>(j->rhs_out);
+  return 0;
+}
+
+int ssb_join_table(const ssb_join* j, const void** d_slots, int64_t* capacity) {
+  if (j->parts.n_parts > 0) return fail(j->ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "an attached index owns no table");
+  *d_slots = j->table.slots;
+  *capacity = static_cast<int64_t>(j->table.capacity);
+  return 0;
+}
+
+int ssb_join_attach_parts(ssb_ctx* ctx, int32_t key_type, int32_t n_parts, const void* const* d_slots,
+                          const int64_t* capacities, const int64_t* row_offsets, ssb_join** out) {
+  *out = nullptr;
+  if (n_parts < 1 || n_parts > kJoinMaxParts) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "1..16 table parts");
+  if (phys_of(key_type) < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported join key type");
+  ssb_join* j = new ssb_join();
+  memset(j, 0, sizeof(*j));
+  j->ctx = ctx;
+  j->build_keys.n_keys = 1;          // the slot word holds the whole key: no build column is read by a probe
+  j->build_keys.phys[0] = phys_of(key_type);
+  j->uniqueness = SSB_KEYS_UNIQUE;
+  j->parts.n_parts = n_parts;
+  for (int p = 0; p < n_parts; ++p) {
+    const int64_t cap = capacities[p];
+    if (cap < 1 || (cap & (cap - 1)) != 0 || d_slots[p] == nullptr) { delete j; return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "table part: capacity must be a power of two"); }
+    j->parts.slots[p] = static_cast<const unsigned long long*>(d_slots[p]);
+    j->parts.mask[p] = static_cast<unsigned long long>(cap) - 1;
+    j->parts.row_offset[p] = row_offsets[p];
+    j->build_rows += 0;
+  }
+  *out = j;
   return 0;
 }
 

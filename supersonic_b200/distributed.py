@@ -207,6 +207,18 @@ def _torch_dtype(dtype):
             capi.BOOL: torch.uint8}[dtype]
 
 
+class _JoinHandle(object):
+    """Keeps an ssb_join alive while a tensor views its table."""
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def __del__(self):
+        if self.h:
+            self.lib.ssb_join_destroy(self.h)
+            self.h = None
+
+
 class CudaJoinKernels(object):
     """The four data-path steps of the sharded join, each one C-ABI call into libssb200.so on
     the device pointers of torch tensors (torch: allocation and collectives only). The torch
@@ -273,6 +285,41 @@ class CudaJoinKernels(object):
                 ctx.check(lib.ssb_memcpy_d2d(ctx.h, li.data_ptr(), pl, n.value * 8))
                 ctx.check(lib.ssb_memcpy_d2d(ctx.h, ri.data_ptr(), pr, n.value * 8))
                 ctx.sync()   # the pair buffers die with the join handle
+        finally:
+            lib.ssb_join_destroy(h)
+        return li, ri
+
+    def build_table(self, build_keys):
+        """Index over UNIQUE single-column keys as a tensor that can travel: the table's slots (16 bytes each:
+        key word, build row + 1) viewed as int64. Returns (table tensor, keep-alive handle)."""
+        lib, ctx, torch = self.ctx.lib, self.ctx, self.torch
+        h = C.c_void_p()
+        ctx.check(lib.ssb_join_build(ctx.h, len(build_keys), self._cols(build_keys), build_keys[0][0].numel(), UNIQUE, C.byref(h)))
+        slots, cap = C.c_void_p(), C.c_int64()
+        ctx.check(lib.ssb_join_table(h, C.byref(slots), C.byref(cap)))
+        view = torch.as_tensor(_DevArray(slots.value, 2 * cap.value, "<i8"), device=self.device)
+        return view, _JoinHandle(lib, h)
+
+    def probe_parts(self, tables, row_offsets, probe_keys, join_type):
+        """Probes the gathered per-part tables (ssb_join_attach_parts): (lhs row, row_offsets[part] + rhs row)
+        pairs in lhs order; rhs -1 for unmatched rows of a LEFT_OUTER join."""
+        lib, ctx = self.ctx.lib, self.ctx
+        n_parts = len(tables)
+        ptrs = (C.c_void_p * n_parts)(*[t.data_ptr() for t in tables])
+        caps = (C.c_int64 * n_parts)(*[t.numel() // 2 for t in tables])
+        offs = (C.c_int64 * n_parts)(*[int(o) for o in row_offsets])
+        h = C.c_void_p()
+        ctx.check(lib.ssb_join_attach_parts(ctx.h, probe_keys[0][1], n_parts, ptrs, caps, offs, C.byref(h)))
+        try:
+            n = C.c_int64()
+            pl, pr = C.c_void_p(), C.c_void_p()
+            ctx.check(lib.ssb_join_probe(h, self._cols(probe_keys), probe_keys[0][0].numel(), join_type,
+                                         C.byref(n), C.byref(pl), C.byref(pr)))
+            li, ri = self.empty(n.value, self.capi.INT64), self.empty(n.value, self.capi.INT64)
+            if n.value:
+                ctx.check(lib.ssb_memcpy_d2d(ctx.h, li.data_ptr(), pl, n.value * 8))
+                ctx.check(lib.ssb_memcpy_d2d(ctx.h, ri.data_ptr(), pr, n.value * 8))
+                ctx.sync()
         finally:
             lib.ssb_join_destroy(h)
         return li, ri
@@ -433,10 +480,17 @@ class ShardedHashJoin(object):
         if strategy == "auto":
             n = torch.tensor([rhs_keys[0][0].numel()], dtype=torch.int64, device=rhs_keys[0][0].device)
             dist.all_reduce(n, group=self.group)
-            strategy = "broadcast" if int(n.item()) <= self.broadcast_max_rows else "all_to_all"
+            small = int(n.item()) <= self.broadcast_max_rows
+            # UNIQUE single-column keys: every rank builds the table of one hash part only (1 / world of the
+            # build work) and the tables are all-gathered; otherwise the whole build side is all-gathered
+            strategy = ("replicate" if uniqueness == UNIQUE and len(rhs_keys) == 1 else "broadcast") if small else "all_to_all"
         with self.k.scope():
+            if strategy == "replicate" and (uniqueness != UNIQUE or len(rhs_keys) != 1):
+                strategy = "all_to_all"      # the replicated tables hold UNIQUE single-column keys
             if strategy == "broadcast":
                 out = self._run_broadcast(lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type, uniqueness)
+            elif strategy == "replicate":
+                out = self._run_replicate(lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type)
             else:
                 out = self._run(lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type, uniqueness)
         self.k.finish()
@@ -460,6 +514,45 @@ class ShardedHashJoin(object):
             out_r.append((vals, c[1]))
         if outer and not b_cols:
             _, r_null = k.gather(b_keys[0], ri, want_valid=True)
+        out_l = [(k.gather(c, li), c[1]) for c in lhs_cols]
+        return li, out_l, out_r, r_null
+
+    def _run_replicate(self, lhs_keys, lhs_cols, rhs_keys, rhs_cols, join_type):
+        """UNIQUE single-column keys. The build side is redistributed by key hash (small: it is the build side),
+        every rank builds the index of the part it received, the tables and the received payload columns are
+        all-gathered, and the local lhs shard probes the table of each key's part: no probe row moves, the
+        output is in lhs order, and the build work per rank is 1 / world of the whole (the broadcast form
+        builds the whole table on every rank)."""
+        import torch
+        import torch.distributed as dist
+        k, g = self.k, self.group
+        world, rank = dist.get_world_size(g), dist.get_rank(g)
+        device = lhs_keys[0][0].device
+        perm_b, cnt_b = k.partition(rhs_keys, world, rank)
+        rcv_b = _exchange_counts(cnt_b, device, g)
+        b_keys = [(_exchange(k.gather(c, perm_b), cnt_b, rcv_b, g), c[1]) for c in rhs_keys]
+        b_cols = [(_exchange(k.gather(c, perm_b), cnt_b, rcv_b, g), c[1]) for c in rhs_cols]
+        table, keep = k.build_table(b_keys)
+        tables = allgather_ragged(table, g)
+        parts_cols = [allgather_ragged(c[0], g) for c in b_cols]
+        rows_per_part = [int(t.numel()) for t in allgather_ragged(b_keys[0][0], g)] if not parts_cols else \
+            [int(t.numel()) for t in parts_cols[0]]
+        offsets = [0]
+        for r in rows_per_part[:-1]:
+            offsets.append(offsets[-1] + r)
+        all_cols = [(torch.cat(p), c[1]) for p, c in zip(parts_cols, b_cols)]
+        li, ri = k.probe_parts(tables, offsets, lhs_keys, join_type)
+        del keep
+        outer = join_type == LEFT_OUTER
+        out_r, r_null = [], None
+        for j, c in enumerate(all_cols):
+            if outer and j == 0:
+                vals, r_null = k.gather(c, ri, want_valid=True)
+            else:
+                vals = k.gather(c, ri)
+            out_r.append((vals, c[1]))
+        if outer and not all_cols:
+            _, r_null = k.gather((ri, 2), ri, want_valid=True)
         out_l = [(k.gather(c, li), c[1]) for c in lhs_cols]
         return li, out_l, out_r, r_null
 

@@ -109,13 +109,44 @@ class NumpyJoinKernels(object):
     def finish(self):
         pass
 
-    def partition(self, keys, n_parts, null_part):
+    @staticmethod
+    def _part_of(keys, n_parts):
         h = np.zeros(keys[0][0].numel(), dtype=np.uint64)
         for t, _ in keys:
             h = h * np.uint64(1000003) + t.numpy().astype(np.int64).view(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
-        part = ((h >> np.uint64(40)) % np.uint64(n_parts)).astype(np.int64)
+        return ((h >> np.uint64(40)) % np.uint64(n_parts)).astype(np.int64)
+
+    def partition(self, keys, n_parts, null_part):
+        part = self._part_of(keys, n_parts)
         perm = np.argsort(part, kind="stable")
         return torch.from_numpy(perm), np.bincount(part, minlength=n_parts).tolist()
+
+    def build_table(self, build_keys):
+        """Stand-in for the table image: (key, row) pairs as one int64 tensor."""
+        keys = build_keys[0][0].numpy().astype(np.int64)
+        t = np.empty(2 * len(keys), dtype=np.int64)
+        t[0::2], t[1::2] = keys, np.arange(len(keys))
+        return torch.from_numpy(t), None
+
+    def probe_parts(self, tables, row_offsets, probe_keys, join_type):
+        index = []
+        for t, off in zip(tables, row_offsets):
+            a = t.numpy()
+            d = {}
+            for key, row in zip(a[0::2].tolist(), a[1::2].tolist()):
+                d.setdefault(key, row + off)
+            index.append(d)
+        part = self._part_of(probe_keys, len(tables))
+        li, ri = [], []
+        for r, (key, p_) in enumerate(zip(probe_keys[0][0].numpy().tolist(), part.tolist())):
+            m = index[p_].get(key)
+            if m is not None:
+                li.append(r)
+                ri.append(m)
+            elif join_type == 1:
+                li.append(r)
+                ri.append(-1)
+        return torch.tensor(li, dtype=torch.int64), torch.tensor(ri, dtype=torch.int64)
 
     def gather(self, col, idx, want_valid=False):
         t, _ = col
@@ -216,7 +247,7 @@ def _join_worker(rank, world, port, out, strategy):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast", "replicate"])
 def test_sharded_hash_join_world2_matches_oracle(ref, strategy):
     from supersonic_b200 import ssplan as sp
     ctx = mp.get_context("spawn")
@@ -324,7 +355,7 @@ def check_null_join_against_oracle(ref, got):
             assert np.array_equal(w[~w_null], want.columns[2][~w_null])
 
 
-@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast", "replicate"])
 def test_sharded_hash_join_null_keys_and_payload_world2(ref, strategy):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()

@@ -45,7 +45,7 @@ def _worker(rank, world, port, out, n_scale, strategy):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast", "replicate"])
 @pytest.mark.parametrize("n_scale", [1, 60])
 def test_sharded_hash_join_two_gpus_matches_oracle(ref, n_scale, strategy):
     if torch.cuda.device_count() < 2:
@@ -90,7 +90,7 @@ def test_sharded_hash_join_two_gpus_matches_oracle(ref, n_scale, strategy):
                 assert np.array_equal(pay, want.columns[2]) and np.array_equal(w, want.columns[3])
 
 
-@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast"])
+@pytest.mark.parametrize("strategy", ["all_to_all", "broadcast", "replicate"])
 def test_sharded_hash_join_null_keys_and_payload_two_gpus(ref, strategy):
     """NULL keys on both sides and a nullable payload column through the real kernels over NCCL."""
     if torch.cuda.device_count() < 2:

@@ -257,7 +257,8 @@ int ssb_group_merge(ssb_group* dst, int64_t n_groups, const ssb_column* key_cols
 /* Replaces HashIndexOnMaterializedCursor + ResultCursor (cursor/core/hash_join.cc:604-625,
  * 707-831) and RowHashSet/RowHashMultiSet (row_hash_set.cc:424-608). */
 enum { SSB_JOIN_INNER = 0, SSB_JOIN_LEFT_OUTER = 1 };
-enum { SSB_KEYS_NOT_UNIQUE = 0, SSB_KEYS_UNIQUE = 1 };
+enum { SSB_KEYS_NOT_UNIQUE = 0, SSB_KEYS_UNIQUE = 1,
+       SSB_KEYS_COMPACT_TABLE = 0x100 /* or-ed in: size the table rows / 0.6 instead of the next power of two >= 2 x rows */ };
 
 typedef struct ssb_join ssb_join;
 
@@ -279,7 +280,8 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
  * the `n_parts` gathered tables: a probe looks its key up in the table of the key's part and reports
  * rhs rows as row_offsets[part] + (row inside that part's build input). No probe row ever moves and the
  * output keeps lhs order (hash_join.cc:793-831). ssb_join_table exposes a built table: `capacity`
- * (a power of two) slots of 16 bytes. The attached index owns none of the tables. */
+ * slots of 16 bytes (build with SSB_KEYS_COMPACT_TABLE to keep what travels small). The attached index owns
+ * none of the tables. */
 int ssb_join_table(const ssb_join* j, const void** d_slots, int64_t* capacity);
 int ssb_join_attach_parts(ssb_ctx* ctx, int32_t key_type, int32_t n_parts, const void* const* d_slots,
                           const int64_t* capacities, const int64_t* row_offsets, ssb_join** out);

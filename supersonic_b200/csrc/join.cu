@@ -50,9 +50,19 @@ enum { kJoinMaxParts = 16 };
 struct JoinParts {
   int32_t n_parts;                                  // 0 = one local table (JoinTable)
   const unsigned long long* slots[kJoinMaxParts];
-  unsigned long long mask[kJoinMaxParts];           // capacity - 1
+  unsigned long long capacity[kJoinMaxParts];
   long long row_offset[kJoinMaxParts];
 };
+
+// Home slot of a key hash in a table of `capacity` slots (any capacity below 2^32, not only powers of two:
+// the replicated tables of the sharded join travel over NVLink and are sized rows / 0.6): the low 32 bits
+// of the hash scaled to [0, capacity). The high 32 bits choose the hash part (part_id_kernel).
+__device__ __forceinline__ unsigned long long home_slot(unsigned long long h, unsigned long long capacity) {
+  return ((h & 0xffffffffull) * capacity) >> 32;
+}
+__device__ __forceinline__ unsigned long long next_slot(unsigned long long s, unsigned long long capacity) {
+  return s + 1 == capacity ? 0ull : s + 1;
+}
 
 __device__ __forceinline__ unsigned long long jmix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -93,14 +103,13 @@ __device__ __forceinline__ bool keys_equal(const JoinKeys& a, long long ra, cons
 __device__ __forceinline__ long long lookup(const JoinTable& t, const JoinKeys& build, const JoinKeys& keys, long long row,
                                             long long* head_row) {
   unsigned long long first = 0;
-  const unsigned long long mask = t.capacity - 1;
-  unsigned long long s = key_hash(keys, row, &first) & mask;
+  unsigned long long s = home_slot(key_hash(keys, row, &first), t.capacity);
   for (;;) {
     const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(t.slots) + s);   // read-only during a probe
     const long long head = static_cast<long long>(e.y);
     if (head == 0) return -1;
     if (e.x == first && keys_equal(keys, row, build, head - 1)) { *head_row = head - 1; return static_cast<long long>(s); }
-    s = (s + 1) & mask;
+    s = next_slot(s, t.capacity);
   }
 }
 
@@ -109,11 +118,10 @@ __device__ __forceinline__ long long lookup(const JoinTable& t, const JoinKeys& 
 __global__ void __launch_bounds__(256) join_build_kernel(JoinTable t, JoinKeys build, long long rows,
                                                           long long* __restrict__ slot_of) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const unsigned long long mask = t.capacity - 1;
   for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
     if (key_has_null(build, row)) { if (slot_of) slot_of[row] = -1; continue; }
     unsigned long long first = 0;
-    unsigned long long s = key_hash(build, row, &first) & mask;
+    unsigned long long s = home_slot(key_hash(build, row, &first), t.capacity);
     for (;;) {
       long long* slot_row = reinterpret_cast<long long*>(&t.slots[2 * s + 1]);
       unsigned long long* slot_key = &t.slots[2 * s];
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(JoinTable t, JoinKeys b
         if (slot_of) slot_of[row] = static_cast<long long>(s);
         break;
       }
-      s = (s + 1) & mask;
+      s = next_slot(s, t.capacity);
     }
   }
 }
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
     bool live[kProbeRows];
     // the table of the row's key: the one local table, or the table of the key's hash part
     const unsigned long long* tab[kProbeRows];
-    unsigned long long mask[kProbeRows];
+    unsigned long long cap[kProbeRows];
     long long offset[kProbeRows];
     // hash and first table probe of all four rows before any of them is looked at
 #pragma unroll
@@ -257,14 +265,14 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
       if (PARTS) {
         const unsigned int part = static_cast<unsigned int>(((h >> 32) * static_cast<unsigned long long>(parts.n_parts)) >> 32);   // = part_id_kernel
         tab[j] = parts.slots[part];
-        mask[j] = parts.mask[part];
+        cap[j] = parts.capacity[part];
         offset[j] = parts.row_offset[part];
       } else {
         tab[j] = t.slots;
-        mask[j] = t.capacity - 1;
+        cap[j] = t.capacity;
         offset[j] = 0;
       }
-      slot[j] = h & mask[j];
+      slot[j] = home_slot(h, cap[j]);
     }
 #pragma unroll
     for (int j = 0; j < kProbeRows; ++j) ent[j] = __ldg(reinterpret_cast<const ulonglong2*>(tab[j]) + slot[j]);
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
         if (h == 0) break;
         // PARTS: single-column keys only (host-checked), the slot word is the whole key
         if (e.x == first[j] && (PARTS || keys_equal(probe, row, build, h - 1))) { head[j] = offset[j] + h - 1; break; }
-        sl = (sl + 1) & mask[j];
+        sl = next_slot(sl, cap[j]);
         e = __ldg(reinterpret_cast<const ulonglong2*>(tab[j]) + sl);
       }
     }
@@ -411,8 +419,17 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
   if (int rc = fill_keys(ctx, n_keys, keys, &j->build_keys)) { delete j; return rc; }
   j->build_rows = rows;
   j->uniqueness = uniqueness;
+  // a power of two >= 2 x rows (load 0.25 .. 0.5); SSB_KEYS_COMPACT_TABLE: rows / 0.6, for tables that travel
+  const bool compact = (uniqueness & SSB_KEYS_COMPACT_TABLE) != 0;
+  uniqueness &= ~SSB_KEYS_COMPACT_TABLE;
+  j->uniqueness = uniqueness;
   unsigned long long cap = 1024;
-  while (cap < static_cast<unsigned long long>(rows) * 2) cap *= 2;
+  if (compact) {
+    cap = static_cast<unsigned long long>(rows) * 5 / 3 + 1024;
+  } else {
+    while (cap < static_cast<unsigned long long>(rows) * 2) cap *= 2;
+  }
+  if (cap >= (1ull << 32)) { delete j; return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "hash join build side beyond 2^31 rows"); }
   j->table.capacity = cap;
   TimedRegion timed(ctx);
   cudaError_t e = tmp_malloc(ctx, &j->table.slots, cap * 16);
@@ -579,9 +596,9 @@ int ssb_join_attach_parts(ssb_ctx* ctx, int32_t key_type, int32_t n_parts, const
   j->parts.n_parts = n_parts;
   for (int p = 0; p < n_parts; ++p) {
     const int64_t cap = capacities[p];
-    if (cap < 1 || (cap & (cap - 1)) != 0 || d_slots[p] == nullptr) { delete j; return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "table part: capacity must be a power of two"); }
+    if (cap < 1 || cap >= (1LL << 32) || d_slots[p] == nullptr) { delete j; return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "table part: bad capacity"); }
     j->parts.slots[p] = static_cast<const unsigned long long*>(d_slots[p]);
-    j->parts.mask[p] = static_cast<unsigned long long>(cap) - 1;
+    j->parts.capacity[p] = static_cast<unsigned long long>(cap);
     j->parts.row_offset[p] = row_offsets[p];
     j->build_rows += 0;
   }

@@ -40,6 +40,29 @@ def allgather_ragged(tensor, group=None):
     return [o[:s] for o, s in zip(out, sizes)]
 
 
+def allgather_tables(table, group=None):
+    """All-gathers the per-rank hash tables (1-D int64 tensors, usually of different lengths) without padding
+    copies of the big tensors: sizes first, then one broadcast per rank straight into its final tensor."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([table.numel()], dtype=torch.int64, device=table.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    if len(set(sizes)) == 1 and hasattr(dist, "all_gather_into_tensor") and table.is_cuda:
+        out = torch.empty(world * sizes[0], dtype=table.dtype, device=table.device)
+        dist.all_gather_into_tensor(out, table.contiguous(), group=group)
+        return [out[r * sizes[0]:(r + 1) * sizes[0]] for r in range(world)]
+    out = []
+    for r in range(world):
+        t = table.contiguous() if r == rank else torch.empty(sizes[r], dtype=table.dtype, device=table.device)
+        src = dist.get_global_rank(group, r) if group is not None else r
+        dist.broadcast(t, src=src, group=group)
+        out.append(t)
+    return out
+
+
 class _DevArray(object):
     """Zero-copy view of device memory for torch (CUDA array interface)."""
 
@@ -294,7 +317,8 @@ class CudaJoinKernels(object):
         key word, build row + 1) viewed as int64. Returns (table tensor, keep-alive handle)."""
         lib, ctx, torch = self.ctx.lib, self.ctx, self.torch
         h = C.c_void_p()
-        ctx.check(lib.ssb_join_build(ctx.h, len(build_keys), self._cols(build_keys), build_keys[0][0].numel(), UNIQUE, C.byref(h)))
+        ctx.check(lib.ssb_join_build(ctx.h, len(build_keys), self._cols(build_keys), build_keys[0][0].numel(),
+                                     UNIQUE | 0x100, C.byref(h)))   # SSB_KEYS_COMPACT_TABLE: the table travels
         slots, cap = C.c_void_p(), C.c_int64()
         ctx.check(lib.ssb_join_table(h, C.byref(slots), C.byref(cap)))
         view = torch.as_tensor(_DevArray(slots.value, 2 * cap.value, "<i8"), device=self.device)
@@ -533,7 +557,7 @@ class ShardedHashJoin(object):
         b_keys = [(_exchange(k.gather(c, perm_b), cnt_b, rcv_b, g), c[1]) for c in rhs_keys]
         b_cols = [(_exchange(k.gather(c, perm_b), cnt_b, rcv_b, g), c[1]) for c in rhs_cols]
         table, keep = k.build_table(b_keys)
-        tables = allgather_ragged(table, g)
+        tables = allgather_tables(table, g)
         parts_cols = [allgather_ragged(c[0], g) for c in b_cols]
         rows_per_part = [int(t.numel()) for t in allgather_ragged(b_keys[0][0], g)] if not parts_cols else \
             [int(t.numel()) for t in parts_cols[0]]

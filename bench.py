@@ -436,6 +436,38 @@ def fill_host_column(capi, name, arr, first_row, threads):
         list(ex.map(part, range(0, rows, step)))
 
 
+def sort_aux(capi, ctx, rank, world, rows, dist, torch):
+    """Sort: ssb_sort_permutation over one INT64 key column of uniformly random 64-bit values
+    (every one of the eight 8-bit digits varies: eight one-sweep passes over (key image, row id) pairs) per rank;
+    no exchange (each rank sorts its own shard; the sharded sample sort is verified by tests/test_multi_gpu_nccl.py).
+    Algorithmic bytes per pass and pair: 16 read + 16 written."""
+    key = ctx.malloc(rows * 8 + 256)
+    perm = ctx.malloc(rows * 8 + 256)
+    ctx.generate(key, rows, rank * rows, SEED, 50, 0, 0, 0)
+    desc = (C.c_int32 * 1)(0)
+
+    def once():
+        ctx.check(ctx.lib.ssb_sort_permutation(ctx.h, 1, _cols(capi, [(key, None, capi.INT64)]), desc, rows, perm))
+        ctx.sync()
+
+    best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
+    # order check on a sample of adjacent pairs of the permutation
+    k = np.empty(rows, dtype=np.int64)
+    p_ = np.empty(rows, dtype=np.int64)
+    ctx.d2h(k, key)
+    ctx.d2h(p_, perm)
+    step = max(1, rows // 1_000_000)
+    sample = k[p_[::step]]
+    assert np.all(np.diff(sample) >= 0), "sorted order violated"
+    ctx.free(key)
+    ctx.free(perm)
+    passes = 8
+    return {"metric": "rows/sec, Sort: stable radix sort permutation of one INT64 key column (uniform 64-bit keys)",
+            "value": world * rows / best, "unit": "rows/s", "rows_per_gpu": rows, "seconds": best, "passes": passes,
+            "algorithmic_gbs_per_gpu": rows * 32.0 * passes / best / 1e9,
+            "check": "keys gathered through the permutation are non-decreasing (1M-row sample)"}
+
+
 def host_column(capi, name, rows, first_row=0):
     kind, lo, span = GEN[name]
     out = np.empty(rows, dtype=np.int64)
@@ -553,16 +585,23 @@ def run_b200(args):
     aux_q1 = q1_aux(capi, ctx, rank, world, min(rows, args.q1_rows), dist, torch, comm)
     aux_join = hash_join_aux(capi, ctx, rank, world, min(rows, args.join_probe_rows),
                              max(1, min(rows, args.join_probe_rows) // 10), dist, torch)
+    aux_sort = sort_aux(capi, ctx, rank, world, min(rows, args.sort_rows), dist, torch)
     if comm is not None:
         comm.close()
     if rank == 0:
-        result["aux"] = {"group_by": aux_group, "q1": aux_q1, "hash_join": aux_join}
+        peak_gbs = measured_peak_gbs()[0]
+        for a_ in (aux_group, aux_q1, aux_join, aux_sort):
+            a_["frac_of_hbm_peak"] = a_["algorithmic_gbs_per_gpu"] / peak_gbs
+        result["aux"] = {"group_by": aux_group, "q1": aux_q1, "hash_join": aux_join, "sort": aux_sort}
         # the sharded operators in one compact object (rows/s over all ranks, seconds per pass): the 1 -> N curves
         # of the configurations whose timed region contains an exchange
         result["scale_aux"] = {"unit": "rows/s",
                                "group_by_c3": aux_group["value"], "group_by_c3_s": aux_group["seconds"],
                                "q1_c5": aux_q1["value"], "q1_c5_s": aux_q1["seconds"],
-                               "hash_join_c4": aux_join["value"], "hash_join_c4_s": aux_join["seconds"]}
+                               "hash_join_c4": aux_join["value"], "hash_join_c4_s": aux_join["seconds"],
+                               "sort": aux_sort["value"], "sort_s": aux_sort["seconds"],
+                               "frac_of_hbm_peak": {"group_by_c3": aux_group["frac_of_hbm_peak"], "q1_c5": aux_q1["frac_of_hbm_peak"],
+                                                    "hash_join_c4": aux_join["frac_of_hbm_peak"], "sort": aux_sort["frac_of_hbm_peak"]}}
     # ---- end to end through the supersonic.h mirror with pinned host buffers: the headline table
     # itself (rows per GPU x 4 read columns = 32 GB of pinned host memory per rank) when the box has
     # the memory, else the largest table that leaves half of the available RAM free
@@ -745,6 +784,7 @@ def main():
     ap.add_argument("--q1-rows", type=int, default=600_000_000, help="rows per GPU of the aux Q1-shape plan (C5: 6e8)")
     ap.add_argument("--join-probe-rows", type=int, default=125_000_000,
                     help="probe rows per GPU of the aux hash join (C4: 1e9 over 8 GPUs); build side = a tenth")
+    ap.add_argument("--sort-rows", type=int, default=200_000_000, help="rows per GPU of the aux sort")
     ap.add_argument("--per-kernel-timing", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -253,6 +253,14 @@ int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb
 int ssb_group_merge(ssb_group* dst, int64_t n_groups, const ssb_column* key_cols,
                     const ssb_column* agg_cols);
 
+/* AggregateClusters (cursor/core/aggregate_clusters.cc:67-125,233-300): rows with equal keys that are consecutive
+ * in the input form a cluster (NULL equals NULL, values by operator==); a key that comes back later starts a new
+ * cluster. d_ids[i] = cluster of row i (0, 1, 2, ... in input order), d_starts[c] = first row of cluster c (room
+ * for `rows` entries). Aggregating by d_ids with ssb_group_* and ordering by it gives the reference's output.
+ * n_keys == 0: one cluster. Synchronises. */
+int ssb_cluster_ids(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows, int64_t* d_ids,
+                    int64_t* d_starts, int64_t* n_clusters);
+
 /* ------------------------------------------------------------------ hash join */
 /* Replaces HashIndexOnMaterializedCursor + ResultCursor (cursor/core/hash_join.cc:604-625,
  * 707-831) and RowHashSet/RowHashMultiSet (row_hash_set.cc:424-608). */

@@ -115,6 +115,7 @@ def load():
         "ssb_sort_permutation": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I32), I64, P]),
         "ssb_program_plan": (C.c_int, [P, I32, I32, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32), I32, I32, I32, C.c_uint32,
                                        P, C.c_char_p, I32]),
+        "ssb_cluster_ids": (C.c_int, [P, I32, C.POINTER(Column), I64, P, P, C.POINTER(I64)]),
         "ssb_join_table": (C.c_int, [P, C.POINTER(P), C.POINTER(I64)]),
         "ssb_join_attach_parts": (C.c_int, [P, I32, I32, C.POINTER(P), C.POINTER(I64), C.POINTER(I64), C.POINTER(P)]),
         "ssb_comm_unique_id": (C.c_int, [P]),

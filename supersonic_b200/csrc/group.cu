@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "comm.h"
+#include "device_utils.h"
 #include "common.h"
 #include "group_device.h"
 #include "program.h"
@@ -904,6 +905,58 @@ __global__ void fill_records_kernel(unsigned long long* rec, unsigned long long 
 }
 
 // Fills a u64 array with a value (accumulator identities, empty keys).
+// ---- AggregateClusters (cursor/core/aggregate_clusters.cc:67-125,233-300): rows with equal keys that are
+// CONSECUTIVE in the input form a cluster; a key that comes back later starts a new one. flag[i] = row i
+// starts a cluster: its key differs from row i - 1 (NULL equals NULL, values by operator==, so a NaN differs
+// from everything and -0.0 equals +0.0, as operators::Equal does).
+struct ClusterKeys {
+  int32_t n_keys;
+  int32_t phys[kMaxKeys];
+  const void* data[kMaxKeys];
+  const uint32_t* nulls[kMaxKeys];
+};
+__global__ void __launch_bounds__(256) cluster_flag_kernel(ClusterKeys k, long long rows, unsigned long long* __restrict__ flag) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    bool differs = false;
+    if (i > 0) {
+      for (int c = 0; c < k.n_keys && !differs; ++c) {
+        const bool na = bit_at(k.nulls[c], i - 1), nb = bit_at(k.nulls[c], i);
+        if (na || nb) { differs = na != nb; continue; }
+        const unsigned long long a = load_raw(k.data[c], k.phys[c], i - 1), b = load_raw(k.data[c], k.phys[c], i);
+        if (k.phys[c] == T_F64) differs = !(Codec<double>::dec(a) == Codec<double>::dec(b));
+        else if (k.phys[c] == T_F32) differs = !(Codec<float>::dec(a) == Codec<float>::dec(b));
+        else differs = a != b;
+      }
+    }
+    flag[i] = (i == 0 || differs) ? 1ull : 0ull;
+  }
+}
+// scanned[i] = number of cluster starts before row i (exclusive scan of flag): ids[i] = scanned[i] + flag[i] - 1;
+// the start row of every cluster is recorded.
+__global__ void __launch_bounds__(256) cluster_ids_kernel(const unsigned long long* __restrict__ scanned, ClusterKeys k, long long rows,
+                                                           long long* __restrict__ ids, long long* __restrict__ starts) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    const bool start = i == 0 || scanned[i + 1] != scanned[i];
+    const long long id = static_cast<long long>(scanned[i + 1]) - 1;   // inclusive count - 1
+    ids[i] = id;
+    if (start) starts[id] = i;
+  }
+}
+
+// Floating-point key columns: is some non-NULL key a NaN?
+__global__ void nan_key_kernel(const void* data, const uint32_t* nulls, int is_f64, long long rows, int* found) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  bool hit = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    if (nulls != nullptr && ((nulls[i >> 5] >> (i & 31)) & 1u)) continue;
+    if (is_f64) { const double v = static_cast<const double*>(data)[i]; hit = hit || v != v; }
+    else { const float v = static_cast<const float*>(data)[i]; hit = hit || v != v; }
+  }
+  if (hit) *found = 1;
+}
+
 __global__ void iota_rows_kernel(long long* p, long long n) {
   for (long long i = threadIdx.x; i < n; i += blockDim.x) p[i] = i;
 }
@@ -1269,10 +1322,33 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
   return rc;
 }
 
+// The reference's hash set asks operator== after the hash (row_hash_set.cc:487-498), so every row with a NaN key
+// is a group of its own; this table compares bit images and would put equal NaN payloads into one group.
+// Refused (ERROR_NOT_IMPLEMENTED) rather than answered differently; the check reads float key columns only.
+static int refuse_nan_keys(ssb_group* g, const ssb_column* keys, int64_t rows) {
+  ssb_ctx* ctx = g->ctx;
+  for (int c = 0; c < g->n_keys && rows > 0; ++c) {
+    const int ph = phys_of(g->key_types[c]);
+    if (ph != T_F32 && ph != T_F64) continue;
+    SSB_CUDA(ctx, cudaMemsetAsync(ctx->d_fail, 0, sizeof(int32_t), ctx->stream));
+    nan_key_kernel<<<update_grid(ctx, rows), 256, 0, ctx->stream>>>(keys[c].data, keys[c].nulls, ph == T_F64 ? 1 : 0, rows, ctx->d_fail);
+    ++ctx->launches;
+    SSB_CUDA(ctx, cudaMemcpyAsync(ctx->h_fail, ctx->d_fail, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSB_CUDA(ctx, cudaMemsetAsync(ctx->d_fail, 0, sizeof(int32_t), ctx->stream));
+    SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_fail) {
+      return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "NaN in a floating-point group-by key: the reference makes every such row a group of its own "
+                                                   "(row_hash_set.cc:487-498); not supported on the B200 path");
+    }
+  }
+  return 0;
+}
+
 static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, int64_t rows, bool merge,
                 bool internal) {
   ssb_ctx* ctx = g->ctx;
   if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  if (int rc = refuse_nan_keys(g, keys, rows)) return rc;
   int n_values = 0;
   for (int a = 0; a < g->n_aggs; ++a) if (g->aggs[a].input >= n_values) n_values = g->aggs[a].input + 1;
   if (merge) n_values = g->n_aggs;
@@ -1411,7 +1487,9 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   static const bool fused_enabled = getenv("SSB200_GROUP_FUSED") != nullptr && atoi(getenv("SSB200_GROUP_FUSED")) != 0;
   const bool rows_feasible = !g->has_first_last && A >= 1 && A <= kLocalMaxAggs && n_in <= kRowMaxIn && n_out <= kRowMaxOut &&
                              static_cast<int>(prog.generic.size()) <= kRowMaxInsn && smem + 8192 <= ctx->smem_optin;
-  const bool feasible = fused_enabled && rows_feasible;
+  bool float_key = false;   // NaN keys are refused (refuse_nan_keys), which needs the key columns in memory
+  for (int c = 0; c < g->n_keys; ++c) { const int ph = phys_of(g->key_types[c]); float_key = float_key || ph == T_F32 || ph == T_F64; }
+  const bool feasible = fused_enabled && rows_feasible && !float_key;
   // The aggregation sink inside expr_kernel (tile-wide superinstructions, no output staging, no
   // scratch): the default whenever the plan fits it. Round 1's form (384-row tiles, four rows per
   // thread, a fingerprint loop per row) cost 23 warp instructions per row and lost to the two
@@ -1419,7 +1497,7 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   // SSB200_GROUP_SINK=0 selects the two-kernel form (A/B runs, tests).
   const char* sink_env = getenv("SSB200_GROUP_SINK");
   const bool sink_enabled = sink_env == nullptr || atoi(sink_env) != 0;
-  bool sink_ok = sink_enabled && rows_feasible && g->n_keys <= 2;   // the row evaluator replays rows the sink had to defer
+  bool sink_ok = sink_enabled && rows_feasible && g->n_keys <= 2 && !float_key;   // the row evaluator replays rows the sink had to defer
   for (int a = 0; a < A; ++a) {   // the sink accumulates without conversions
     if (g->aggs[a].fn != SSB_AGG_COUNT && phys_of(g->aggs[a].in_type) != phys_of(g->aggs[a].out_type)) sink_ok = false;
   }
@@ -1558,6 +1636,44 @@ int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb
   }
   *n_groups = n;
   return 0;
+}
+
+int ssb_cluster_ids(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows, int64_t* d_ids, int64_t* d_starts,
+                    int64_t* n_clusters) {
+  *n_clusters = 0;
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  if (n_keys < 0 || n_keys > kMaxKeys) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "too many clustering key columns");
+  if (rows == 0) return 0;
+  ClusterKeys k;
+  memset(&k, 0, sizeof(k));
+  k.n_keys = n_keys;
+  for (int c = 0; c < n_keys; ++c) {
+    k.phys[c] = phys_of(keys[c].dtype);
+    if (k.phys[c] < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported clustering key type");
+    k.data[c] = keys[c].data;
+    k.nulls[c] = keys[c].nulls;
+  }
+  unsigned long long* flag = nullptr;
+  unsigned long long* d_total = nullptr;
+  cudaError_t e = tmp_malloc(ctx, &flag, static_cast<size_t>(rows + 1) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &d_total, 8);
+  if (e != cudaSuccess) { tmp_free(ctx, flag); tmp_free(ctx, d_total); return cuda_fail(ctx, e, "cluster scratch"); }
+  cluster_flag_kernel<<<update_grid(ctx, rows), 256, 0, ctx->stream>>>(k, rows, flag);
+  ++ctx->launches;
+  cudaMemsetAsync(flag + rows, 0, 8, ctx->stream);
+  int rc = exclusive_scan_u64(ctx, flag, static_cast<unsigned long long>(rows) + 1, d_total);
+  if (rc == 0) {
+    cluster_ids_kernel<<<update_grid(ctx, rows), 256, 0, ctx->stream>>>(flag, k, rows, reinterpret_cast<long long*>(d_ids),
+                                                                       reinterpret_cast<long long*>(d_starts));
+    ++ctx->launches;
+    e = cudaMemcpyAsync(ctx->h_count, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cluster ids");
+    else *n_clusters = *ctx->h_count;
+  }
+  tmp_free(ctx, flag);
+  tmp_free(ctx, d_total);
+  return rc;
 }
 
 // ---- the exchange step of the row-range sharded aggregate ------------------------------------

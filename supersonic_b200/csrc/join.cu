@@ -77,9 +77,14 @@ __device__ __forceinline__ unsigned long long jload(const void* base, int phys, 
     default: return static_cast<const uint8_t*>(base)[i];
   }
 }
+// Rows that can never match: a NULL in any key column (hash_join.cc:67-76,616-617,755-756), and a NaN in a
+// floating-point key column -- the reference's hash set confirms a hit with operator== (row_hash_set.cc:
+// 487-498), which no NaN satisfies, so a NaN key finds nothing and is found by nothing.
 __device__ __forceinline__ bool key_has_null(const JoinKeys& k, long long row) {
   for (int c = 0; c < k.n_keys; ++c) {
     if (k.nulls[c] != nullptr && ((k.nulls[c][row >> 5] >> (row & 31)) & 1u)) return true;
+    if (k.phys[c] == T_F64) { const double v = static_cast<const double*>(k.data[c])[row]; if (v != v) return true; }
+    if (k.phys[c] == T_F32) { const float v = static_cast<const float*>(k.data[c])[row]; if (v != v) return true; }
   }
   return false;
 }

@@ -113,6 +113,7 @@ class BasicOperation : public Operation {
     children_.push_back(child1);
     children_.push_back(child2);
   }
+  explicit BasicOperation(const vector<Operation*>& children) : allocator_(NULL), children_(children) {}
   BufferAllocator* buffer_allocator() const { return allocator_ ? allocator_ : HeapBufferAllocator::Get(); }
   Operation* child() const { return children_[0]; }
   Operation* child_at(size_t i) const { return children_[i]; }
@@ -258,6 +259,14 @@ Operation* GroupAggregate(const SingleSourceProjector* group_by, AggregationSpec
 Operation* BestEffortGroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
                                     GroupAggregateOptions* options, Operation* child);
 Operation* ScalarAggregate(AggregationSpecification* aggregation, Operation* child);  // aggregate.h:341
+// aggregate.h:277-307: aggregates an input that is CLUSTERED by the key columns (rows with equal keys are
+// consecutive; a key that comes back later is a new cluster), output in cluster order. On the GPU: cluster ids from
+// one compare-with-predecessor pass and a scan (ssb_cluster_ids), aggregation by cluster id, ordered by it.
+Operation* AggregateClusters(const SingleSourceProjector* clustered_by_columns, const AggregationSpecification* aggregation,
+                             Operation* child);
+Operation* AggregateClustersWithSpecifiedOutputBlockSize(const SingleSourceProjector* clustered_by_columns,
+                                                         const AggregationSpecification* aggregation,
+                                                         rowcount_t block_size, Operation* child);
 
 // cursor/core/aggregator.h:37-112: the bound form of an AggregationSpecification (result schema
 // and per-aggregate types / nullability, aggregator.cc:63-152). The accumulators themselves live
@@ -294,6 +303,8 @@ FailureOrOwned<Cursor> BoundGroupAggregate(const BoundSingleSourceProjector* gro
                                            BufferAllocator* allocator, BufferAllocator* original_allocator,
                                            bool best_effort, Cursor* child);                      // aggregate.h:254
 Cursor* BoundScalarAggregate(Aggregator* aggregator, Cursor* child);                              // aggregate.h:345
+FailureOrOwned<Cursor> BoundAggregateClusters(const BoundSingleSourceProjector* group_by, Aggregator* aggregator,
+                                              BufferAllocator* allocator, Cursor* child);          // aggregate.h:291
 
 // ---- hash join (cursor/core/hash_join.h:35-69) ---------------------------------------------
 class HashJoinOperation : public BasicOperation {
@@ -391,6 +402,11 @@ FailureOrOwned<Cursor> BoundSort(const BoundSortOrder* sort_order, const BoundSi
                                  Cursor* child_cursor);                                            // sort.h:114
 // Sort by attribute names with an optional row limit (sort.h:103-131, sort.cc:857-1017); case
 // insensitivity concerns STRING keys only, which are not on this path.
+// cursor/core/merge_union_all.h: merges inputs that are each sorted by `sort_order` (same column types) into one
+// sorted stream; no inputs gives an empty zero-column operation, one input is returned as it is.
+Operation* MergeUnionAll(const SortOrder* sort_order, const vector<Operation*>& inputs);
+FailureOrOwned<Cursor> BoundMergeUnionAll(const BoundSortOrder* sort_order, vector<Cursor*> inputs,
+                                          BufferAllocator* buffer_allocator);
 Operation* ExtendedSort(const ExtendedSortSpecification* specification, const SingleSourceProjector* result_projector,
                         size_t memory_limit, Operation* child);
 FailureOrOwned<Cursor> BoundExtendedSort(const ExtendedSortSpecification* sort_specification,

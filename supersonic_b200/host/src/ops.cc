@@ -980,6 +980,190 @@ class GroupCursor : public GpuCursor {
   ssb_group* group_;
 };
 
+FailureOrVoid GatherColumns(Session* s, const DeviceTable& src, const vector<int>& positions, const int64_t* d_idx,
+                            int64 n, bool force_nulls, DeviceTable* out, size_t first_out);
+
+// ------------------------------------------------------------------ AggregateClusters
+// cursor/core/aggregate_clusters.cc:233-433: the input is clustered by the key columns; every run of consecutive
+// rows with equal keys becomes one output row, in input order (a key that comes back later is a new row). Here:
+// cluster ids from one compare-with-predecessor pass and a scan (ssb_cluster_ids), the aggregates by cluster id in
+// the hash table of GroupAggregate, the key values gathered from the first row of each cluster, rows ordered by id.
+class ClustersCursor : public GpuCursor {
+ public:
+  ClustersCursor(const TupleSchema& schema, BufferAllocator* allocator, Cursor* child, const vector<int>& keys,
+                 const vector<BoundAggregation>& aggs)
+      : GpuCursor(schema, allocator, "AggregateClustersCursor"), child_(child), keys_(keys), aggs_(aggs) {}
+  virtual CursorId GetCursorId() const { return AGGREGATE_CLUSTERS; }
+  virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    DeviceTable in;
+    std::unique_ptr<Block> keepalive;
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(child_.get(), &in, &keepalive));
+    const int64 rows = in.rows;
+    vector<ssb_column> key_cols;
+    for (size_t k = 0; k < keys_.size(); ++k) key_cols.push_back(in.columns[keys_[k]].col);
+    DeviceBuffer ids, starts;
+    PROPAGATE_ON_FAILURE(ids.Allocate(static_cast<size_t>(rows) * 8 + 128));
+    PROPAGATE_ON_FAILURE(starts.Allocate(static_cast<size_t>(rows) * 8 + 128));
+    ssb_column dummy_col;
+    memset(&dummy_col, 0, sizeof(dummy_col));
+    int64_t clusters = 0;
+    SSB_CALL(s, ssb_cluster_ids(s->ctx(), static_cast<int32_t>(key_cols.size()), key_cols.empty() ? &dummy_col : key_cols.data(), rows,
+                                static_cast<int64_t*>(ids.get()), static_cast<int64_t*>(starts.get()), &clusters), "cluster ids");
+    PROPAGATE_ON_FAILURE(result->Allocate(schema(), clusters, /* force_nulls = */ true));
+    result->rows = clusters;
+    if (clusters == 0) return Success();
+    // the aggregates, keyed by the cluster id
+    vector<ssb_agg_spec> specs;
+    vector<ssb_column> value_cols;
+    for (size_t i = 0; i < aggs_.size(); ++i) {
+      ssb_agg_spec sp = aggs_[i].spec;
+      if (aggs_[i].input_position >= 0) {
+        sp.input = static_cast<int32_t>(value_cols.size());
+        value_cols.push_back(in.columns[aggs_[i].input_position].col);
+      }
+      specs.push_back(sp);
+    }
+    int32_t key_type = INT64, key_nullable = 0;
+    ssb_group* g = NULL;
+    SSB_CALL(s, ssb_group_create(s->ctx(), 1, &key_type, &key_nullable, static_cast<int32_t>(specs.size()), specs.data(), clusters, &g),
+             "cluster aggregation setup");
+    struct Guard { ssb_group* g; ~Guard() { if (g) ssb_group_destroy(g); } } guard = {g};
+    ssb_column id_col;
+    id_col.data = ids.get(); id_col.nulls = NULL; id_col.dtype = INT64; id_col.reserved = 0;
+    SSB_CALL(s, ssb_group_update(g, &id_col, value_cols.empty() ? &dummy_col : value_cols.data(), rows), "cluster aggregation");
+    int64_t n_groups = 0;
+    ssb_column kout;
+    vector<ssb_column> aout(specs.size() ? specs.size() : 1);
+    SSB_CALL(s, ssb_group_finalize(g, &n_groups, &kout, aout.data()), "cluster aggregation finalize");
+    if (n_groups != clusters) THROW(new Exception(ERROR_UNKNOWN_ERROR, "internal: cluster count mismatch"));
+    // order by cluster id
+    DeviceBuffer perm;
+    PROPAGATE_ON_FAILURE(perm.Allocate(static_cast<size_t>(clusters) * 8 + 128));
+    int32_t asc = 0;
+    SSB_CALL(s, ssb_sort_permutation(s->ctx(), 1, &kout, &asc, clusters, static_cast<int64_t*>(perm.get())), "cluster order");
+    for (size_t k = 0; k < keys_.size(); ++k) {
+      const vector<int> pos(1, keys_[k]);
+      PROPAGATE_ON_FAILURE(GatherColumns(s, in, pos, static_cast<const int64_t*>(starts.get()), clusters, false, result, k));
+      if (in.columns[keys_[k]].col.nulls == NULL) {
+        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[k].col.nulls, 0, static_cast<size_t>((clusters + 31) / 32 + 1) * 4), "memset");
+      }
+    }
+    for (size_t i = 0; i < specs.size(); ++i) {
+      ssb_column dst = result->columns[keys_.size() + i].col;
+      if (aout[i].nulls == NULL) {
+        SSB_CALL(s, ssb_memset(s->ctx(), dst.nulls, 0, static_cast<size_t>((clusters + 31) / 32 + 1) * 4), "memset");
+        dst.nulls = NULL;
+      }
+      SSB_CALL(s, ssb_gather(s->ctx(), &aout[i], static_cast<const int64_t*>(perm.get()), clusters, &dst), "gather");
+    }
+    SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
+    return Success();
+  }
+ private:
+  std::unique_ptr<Cursor> child_;
+  vector<int> keys_;
+  vector<BoundAggregation> aggs_;
+};
+
+class AggregateClustersOperation : public BasicOperation {
+ public:
+  AggregateClustersOperation(const SingleSourceProjector* clustered_by, const AggregationSpecification* aggregation, Operation* child)
+      : BasicOperation(child), clustered_by_(clustered_by), aggregation_(aggregation) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    FailureOrOwned<Cursor> child_cursor = child()->CreateCursor();
+    PROPAGATE_ON_FAILURE(child_cursor);
+    const TupleSchema& cs = child_cursor->schema();
+    TupleSchema result;
+    vector<int> keys;
+    FailureOrOwned<const BoundSingleSourceProjector> proj = clustered_by_->Bind(cs);
+    PROPAGATE_ON_FAILURE(proj);
+    for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+      keys.push_back(proj->source_attribute_position(i));
+      result.add_attribute(proj->result_schema().attribute(i));
+      const DataType t = proj->result_schema().attribute(i).type();
+      if (t == STRING || t == BINARY) {
+        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length clustering keys are not on the B200 hot path (SURVEY 8f)"));
+      }
+    }
+    vector<BoundAggregation> aggs;
+    PROPAGATE_ON_FAILURE(BindAggregations(*aggregation_, cs, &aggs, &result));
+    return Success(static_cast<Cursor*>(new ClustersCursor(result, buffer_allocator(), child_cursor.release(), keys, aggs)));
+  }
+ protected:
+  virtual string DebugName() const { return "AggregateClusters"; }
+ private:
+  std::unique_ptr<const SingleSourceProjector> clustered_by_;
+  std::unique_ptr<const AggregationSpecification> aggregation_;
+};
+
+// ------------------------------------------------------------------ MergeUnionAll
+// cursor/core/merge_union_all.cc:127-300: merges inputs that are each sorted by `sort_order` into one sorted
+// stream (a priority queue over the inputs' current rows; ties between inputs come out in no defined order).
+// Here: the inputs are concatenated in HBM and sorted by the key columns with the stable radix sort -- rows with
+// equal keys keep input order, then row order. The result column is nullable if any input's column is (:296-311).
+class ConcatCursor : public GpuCursor {
+ public:
+  ConcatCursor(const TupleSchema& schema, BufferAllocator* allocator, vector<Cursor*>* inputs)
+      : GpuCursor(schema, allocator, "MergeUnionAllInputs") {
+    for (size_t i = 0; i < inputs->size(); ++i) inputs_.push_back(std::unique_ptr<Cursor>((*inputs)[i]));
+    inputs->clear();
+  }
+  virtual CursorId GetCursorId() const { return MERGE_UNION_ALL; }
+  virtual void Interrupt() { GpuCursor::Interrupt(); for (size_t i = 0; i < inputs_.size(); ++i) inputs_[i]->Interrupt(); }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    vector<DeviceTable> parts(inputs_.size());
+    vector<std::unique_ptr<Block> > keep(inputs_.size());
+    int64 total = 0;
+    for (size_t i = 0; i < inputs_.size(); ++i) {
+      PROPAGATE_ON_FAILURE(MaterializeOnDevice(inputs_[i].get(), &parts[i], &keep[i]));
+      total += parts[i].rows;
+    }
+    PROPAGATE_ON_FAILURE(result->Allocate(schema(), total, /* force_nulls = */ true));
+    result->rows = total;
+    DeviceBuffer bytes, part_bytes;
+    PROPAGATE_ON_FAILURE(bytes.Allocate(static_cast<size_t>(total) + 128));
+    for (int c = 0; c < schema().attribute_count(); ++c) {
+      const size_t w = GetTypeInfo(schema().attribute(c).type()).size();
+      int64 at = 0;
+      bool any_nulls = false;
+      for (size_t i = 0; i < parts.size(); ++i) any_nulls = any_nulls || parts[i].columns[c].col.nulls != NULL;
+      for (size_t i = 0; i < parts.size(); ++i) {
+        const int64 n = parts[i].rows;
+        if (n == 0) continue;
+        SSB_CALL(s, ssb_memcpy_d2d(s->ctx(), static_cast<char*>(result->columns[c].col.data) + at * w, parts[i].columns[c].col.data,
+                                   static_cast<size_t>(n) * w), "concatenate");
+        if (any_nulls) {   // is_null bits do not concatenate at arbitrary row offsets: through one byte per row
+          char* dst = static_cast<char*>(bytes.get()) + at;
+          if (parts[i].columns[c].col.nulls != NULL) {
+            SSB_CALL(s, ssb_nulls_unpack(s->ctx(), parts[i].columns[c].col.nulls, n, reinterpret_cast<uint8_t*>(dst)), "null unpack");
+          } else {
+            SSB_CALL(s, ssb_memset(s->ctx(), dst, 0, static_cast<size_t>(n)), "memset");
+          }
+        }
+        at += n;
+      }
+      if (any_nulls && total > 0) {
+        SSB_CALL(s, ssb_nulls_pack(s->ctx(), static_cast<const uint8_t*>(bytes.get()), total, result->columns[c].col.nulls), "null pack");
+      } else {
+        SSB_CALL(s, ssb_memset(s->ctx(), result->columns[c].col.nulls, 0, static_cast<size_t>((total + 31) / 32 + 1) * 4), "memset");
+      }
+    }
+    SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
+    return Success();
+  }
+ private:
+  vector<std::unique_ptr<Cursor> > inputs_;
+};
+
 class GroupAggregateOperation : public BasicOperation {
  public:
   GroupAggregateOperation(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
@@ -1250,7 +1434,116 @@ class SortOperation : public BasicOperation {
   std::unique_ptr<const SingleSourceProjector> projector_;
 };
 
+// cursor/core/merge_union_all.cc:296-311
+FailureOr<TupleSchema> MergeResultSchema(const vector<Cursor*>& inputs) {
+  TupleSchema result;
+  const TupleSchema& first = inputs[0]->schema();
+  for (size_t j = 1; j < inputs.size(); ++j) {
+    const TupleSchema& other = inputs[j]->schema();
+    bool same = other.attribute_count() == first.attribute_count();
+    for (int i = 0; same && i < first.attribute_count(); ++i) same = other.attribute(i).type() == first.attribute(i).type();
+    if (!same) {   // the reference CHECK-fails here (EqualByType)
+      THROW(new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, "MergeUnionAll inputs differ in column count or types: (" +
+                                                             first.GetHumanReadableSpecification() + ") vs (" +
+                                                             other.GetHumanReadableSpecification() + ")"));
+    }
+  }
+  for (int i = 0; i < first.attribute_count(); ++i) {
+    bool nullable = false;
+    for (size_t j = 0; j < inputs.size(); ++j) nullable = nullable || inputs[j]->schema().attribute(i).is_nullable();
+    result.add_attribute(Attribute(first.attribute(i).name(), first.attribute(i).type(), nullable ? NULLABLE : NOT_NULLABLE));
+  }
+  return Success(result);
+}
+
+FailureOrOwned<Cursor> MakeMergeUnionAll(const vector<std::pair<int, ColumnOrder> >& keys, const TupleSchema& schema,
+                                         vector<Cursor*>* inputs, BufferAllocator* allocator) {
+  vector<int> all;
+  for (int i = 0; i < schema.attribute_count(); ++i) all.push_back(i);
+  Cursor* concat = new ConcatCursor(schema, allocator, inputs);
+  return Success(static_cast<Cursor*>(new SortCursor(schema, allocator, concat, keys, all)));
+}
+
+class MergeUnionAllOperation : public BasicOperation {
+ public:
+  MergeUnionAllOperation(const SortOrder* order, const vector<Operation*>& inputs) : BasicOperation(inputs), order_(order) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    vector<Cursor*> inputs;
+    struct Deleter { vector<Cursor*>* v; ~Deleter() { for (size_t i = 0; i < v->size(); ++i) delete (*v)[i]; } } deleter = {&inputs};
+    for (size_t i = 0; i < children_count(); ++i) {
+      FailureOrOwned<Cursor> c = child_at(i)->CreateCursor();
+      PROPAGATE_ON_FAILURE(c);
+      inputs.push_back(c.release());
+    }
+    FailureOr<TupleSchema> schema = MergeResultSchema(inputs);
+    PROPAGATE_ON_FAILURE(schema);
+    vector<std::pair<int, ColumnOrder> > keys;
+    PROPAGATE_ON_FAILURE(order_->Bind(schema.get(), &keys));
+    return MakeMergeUnionAll(keys, schema.get(), &inputs, buffer_allocator());
+  }
+ protected:
+  virtual string DebugName() const { return "MergeUnionAll"; }
+ private:
+  std::unique_ptr<const SortOrder> order_;
+};
+
 }  // namespace
+
+Operation* MergeUnionAll(const SortOrder* sort_order, const vector<Operation*>& inputs) {
+  std::unique_ptr<const SortOrder> order(sort_order);
+  if (inputs.empty()) return ScanView(View(TupleSchema()));   // merge_union_all.cc:352-356: Generate(0)
+  if (inputs.size() == 1) return inputs[0];
+  return new MergeUnionAllOperation(order.release(), inputs);
+}
+
+FailureOrOwned<Cursor> BoundMergeUnionAll(const BoundSortOrder* sort_order, vector<Cursor*> inputs, BufferAllocator* buffer_allocator) {
+  std::unique_ptr<const BoundSortOrder> order(sort_order);
+  if (inputs.empty()) THROW(new Exception(ERROR_INVALID_ARGUMENT_VALUE, "BoundMergeUnionAll needs at least one input"));
+  FailureOr<TupleSchema> schema = MergeResultSchema(inputs);
+  if (schema.is_failure()) {
+    for (size_t i = 0; i < inputs.size(); ++i) delete inputs[i];
+    return Failure(schema.release_exception());
+  }
+  vector<std::pair<int, ColumnOrder> > keys;
+  for (int i = 0; i < order->schema().attribute_count(); ++i) {
+    keys.push_back(std::make_pair(order->projector().source_attribute_position(i), order->column_order(i)));
+  }
+  return MakeMergeUnionAll(keys, schema.get(), &inputs, buffer_allocator ? buffer_allocator : HeapBufferAllocator::Get());
+}
+
+Operation* AggregateClusters(const SingleSourceProjector* clustered_by_columns, const AggregationSpecification* aggregation,
+                             Operation* child) {
+  return new AggregateClustersOperation(clustered_by_columns, aggregation, child);
+}
+Operation* AggregateClustersWithSpecifiedOutputBlockSize(const SingleSourceProjector* clustered_by_columns,
+                                                         const AggregationSpecification* aggregation, rowcount_t,
+                                                         Operation* child) {
+  return new AggregateClustersOperation(clustered_by_columns, aggregation, child);   // the whole result is one device table
+}
+
+FailureOrOwned<Cursor> BoundAggregateClusters(const BoundSingleSourceProjector* group_by, Aggregator* aggregator,
+                                              BufferAllocator* allocator, Cursor* child) {
+  std::unique_ptr<const BoundSingleSourceProjector> proj(group_by);
+  std::unique_ptr<Aggregator> agg(aggregator);
+  std::unique_ptr<Cursor> child_cursor(child);
+  TupleSchema result;
+  vector<int> keys;
+  for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+    keys.push_back(proj->source_attribute_position(i));
+    result.add_attribute(proj->result_schema().attribute(i));
+    const DataType t = proj->result_schema().attribute(i).type();
+    if (t == STRING || t == BINARY) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length clustering keys are not on the B200 hot path (SURVEY 8f)"));
+    }
+  }
+  for (int i = 0; i < agg->schema().attribute_count(); ++i) {
+    if (!result.add_attribute(agg->schema().attribute(i))) {
+      THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + agg->schema().attribute(i).name() + "' in result schema"));
+    }
+  }
+  return Success(static_cast<Cursor*>(new ClustersCursor(result, allocator ? allocator : HeapBufferAllocator::Get(), child_cursor.release(),
+                                                         keys, agg->impl()->aggs)));
+}
 
 namespace internal {
 

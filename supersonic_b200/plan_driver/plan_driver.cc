@@ -13,6 +13,8 @@
 //     (scalar_agg (aggs AGG...) OP)              ScalarAggregate
 //     (hash_join INNER|LEFT_OUTER PROJ PROJ MPROJ UNIQUE|NOT_UNIQUE OP OP)
 //     (sort (order (NAME ASC|DESC)...) PROJ OP)  Sort
+//     (merge_union_all (order (NAME ASC|DESC)...) OP...)   MergeUnionAll over inputs sorted by that order
+//     (aggregate_clusters PROJ (aggs AGG...) OP)           AggregateClusters over an input clustered by PROJ
 //   The bound_* forms build the same cursors through the Bound* factories (BoundCompute,
 //   BoundFilter, BoundProject, BoundScanView, BoundGroupAggregate, BoundScalarAggregate, BoundSort):
 //   the child is created first, the expression / projector / aggregation is bound against its schema.
@@ -43,6 +45,7 @@
 
 #include "supersonic/supersonic.h"
 #include "supersonic/cursor/core/aggregator.h"
+#include "supersonic/cursor/core/merge_union_all.h"
 #include "supersonic/proto/specification.pb.h"
 
 namespace {
@@ -313,6 +316,18 @@ struct Inputs {
   std::vector<View> views;
 };
 
+SortOrder* BuildOrder(const Sx& o) {
+  std::unique_ptr<SortOrder> order(new SortOrder);
+  for (size_t i = 1; i < o.kids.size(); ++i) {
+    const Sx& k = o.kids[i];
+    if (k.atom || k.kids.size() != 2) throw ParseError{"order takes (NAME ASC|DESC) pairs"};
+    const std::string& d = Atom(k.kids[1]);
+    if (d != "ASC" && d != "DESC") throw ParseError{"order direction must be ASC or DESC"};
+    order->add(ProjectNamedAttribute(Atom(k.kids[0])), d == "ASC" ? ASCENDING : DESCENDING);
+  }
+  return order.release();
+}
+
 Operation* BuildOp(const Sx& s, const Inputs& in) {
   const std::string& h = Head(s);
   if (h == "scan") {
@@ -377,6 +392,19 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
     Operation* l = BuildOp(s.kids[6], in);
     Operation* r = BuildOp(s.kids[7], in);
     return new HashJoinOperation(join_type, lk, rk, rp, u == "UNIQUE" ? UNIQUE : NOT_UNIQUE, l, r);
+  }
+  if (h == "merge_union_all") {
+    if (s.kids.size() < 2 || Head(s.kids[1]) != "order") throw ParseError{"expected (merge_union_all (order ...) OP...)"};
+    std::unique_ptr<SortOrder> order(BuildOrder(s.kids[1]));
+    std::vector<Operation*> inputs;
+    for (size_t i = 2; i < s.kids.size(); ++i) inputs.push_back(BuildOp(s.kids[i], in));
+    return MergeUnionAll(order.release(), inputs);
+  }
+  if (h == "aggregate_clusters") {
+    Arity(s, 3);
+    const SingleSourceProjector* p = BuildProjector(s.kids[1]);
+    AggregationSpecification* a = BuildAggs(s.kids[2]);
+    return AggregateClusters(p, a, BuildOp(s.kids[3], in));
   }
   if (h == "sort") {
     Arity(s, 3);
@@ -477,6 +505,23 @@ Cursor* BuildCursor(const Sx& s, const Inputs& in, Keep* keep) {
     std::unique_ptr<const BoundSingleSourceProjector> bp(Take(p->Bind(child->schema())));
     Aggregator* agg = Take(Aggregator::Create(*a, child->schema(), limit.get(), 16));
     return Take(BoundGroupAggregate(bp.release(), agg, limit.release(), heap, false, child.release()));
+  }
+  if (h == "bound_aggregate_clusters") {
+    Arity(s, 3);
+    std::unique_ptr<const SingleSourceProjector> p(BuildProjector(s.kids[1]));
+    std::unique_ptr<AggregationSpecification> a(BuildAggs(s.kids[2]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[3], in, keep));
+    std::unique_ptr<const BoundSingleSourceProjector> bp(Take(p->Bind(child->schema())));
+    Aggregator* agg = Take(Aggregator::Create(*a, child->schema(), heap, 16));
+    return Take(BoundAggregateClusters(bp.release(), agg, heap, child.release()));
+  }
+  if (h == "bound_merge_union_all") {
+    if (s.kids.size() < 3 || Head(s.kids[1]) != "order") throw ParseError{"expected (bound_merge_union_all (order ...) OP...)"};
+    std::unique_ptr<SortOrder> order(BuildOrder(s.kids[1]));
+    std::vector<Cursor*> inputs;
+    for (size_t i = 2; i < s.kids.size(); ++i) inputs.push_back(BuildCursor(s.kids[i], in, keep));
+    std::unique_ptr<const BoundSortOrder> bo(Take(order->Bind(inputs[0]->schema())));
+    return Take(BoundMergeUnionAll(bo.release(), inputs, heap));
   }
   if (h == "bound_sort") {
     Arity(s, 3);

@@ -214,6 +214,55 @@ GOLDEN_LATE = [
     ("sort_signed_zero", "(sort (order (x DESC) (v ASC)) (all) (scan 0))",
      [[col("x", sp.DOUBLE, [0.0, -0.0, 1.0, -0.0, 0.0, -1.0]), col("v", sp.INT32, [5, 4, 3, 2, 1, 0])]],
      {"x": [1.0, 0.0, -0.0, -0.0, 0.0, -1.0], "v": [3, 1, 2, 4, 5, 0]}, True),
+    # cursor/core/merge_union_all_test.cc:131-140 (a1a2b1b2 + a1a3b2b2; the STRING column a/b/c re-coded 1/2/3)
+    ("merge_union_all_two_inputs", "(merge_union_all (order (col0 ASC) (col1 ASC)) (scan 0) (scan 1))",
+     [[col("col0", sp.INT32, [1, 1, 2, 2]), col("col1", sp.INT32, [1, 2, 1, 2])],
+      [col("col0", sp.INT32, [1, 1, 2, 2]), col("col1", sp.INT32, [1, 3, 2, 2])]],
+     {"col0": [1, 1, 1, 1, 2, 2, 2, 2], "col1": [1, 1, 2, 3, 1, 2, 2, 2]}, True),
+    # :113-129 an empty input on either side
+    ("merge_union_all_empty_input", "(merge_union_all (order (col0 ASC) (col1 ASC)) (scan 0) (scan 1) (scan 0))",
+     [[col("col0", sp.INT32, []), col("col1", sp.INT32, [])], [col("col0", sp.INT32, [1]), col("col1", sp.INT32, [1])]],
+     {"col0": [1], "col1": [1]}, True),
+    # :189-219 five one-row inputs in descending / mixed input order
+    ("merge_union_all_five_inputs", "(merge_union_all (order (col0 ASC) (col1 ASC)) (scan 0) (scan 1) (scan 2) (scan 3) (scan 4))",
+     [[col("col0", sp.INT32, [2]), col("col1", sp.INT32, [2])], [col("col0", sp.INT32, [3]), col("col1", sp.INT32, [3])],
+      [col("col0", sp.INT32, [1]), col("col1", sp.INT32, [3])], [col("col0", sp.INT32, [1]), col("col1", sp.INT32, [2])],
+      [col("col0", sp.INT32, [1]), col("col1", sp.INT32, [1])]],
+     {"col0": [1, 1, 1, 2, 3], "col1": [1, 2, 3, 2, 3]}, True),
+    # :262-280 three interleaving inputs; DESC order and a nullable key (NULLs last for DESC): a NOT NULL and a
+    # nullable input give a nullable column (merge_union_all.cc:296-311)
+    ("merge_union_all_desc_nullable", "(merge_union_all (order (k DESC)) (scan 0) (scan 1) (scan 2))",
+     [[col("k", sp.INT64, [9, 5, 1]), col("v", sp.DOUBLE, [0.5, 1.5, 2.5])],
+      [ncol("k", sp.INT64, [8, 4, N]), col("v", sp.DOUBLE, [10.0, 11.0, 12.0])],
+      [ncol("k", sp.INT64, [7, 6, 2]), col("v", sp.DOUBLE, [20.0, 21.0, 22.0])]],
+     {"k": [9, 8, 7, 6, 5, 4, 2, 1, N], "v": [0.5, 10.0, 20.0, 21.0, 1.5, 11.0, 22.0, 2.5, 12.0]}, True),
+    ("bound_merge_union_all", "(bound_merge_union_all (order (k ASC)) (scan 0) (scan 1))",
+     [[col("k", sp.INT64, [1, 5, 9]), col("v", sp.DOUBLE, [0.5, 1.5, 2.5])],
+      [col("k", sp.INT64, [2, 4, 10]), col("v", sp.DOUBLE, [10.0, 11.0, 12.0])]],
+     {"k": [1, 2, 4, 5, 9, 10], "v": [0.5, 10.0, 11.0, 1.5, 2.5, 12.0]}, True),
+    # cursor/core/aggregate_clusters_test.cc:69-82 shape: three clusters; a key that returns later is a new cluster
+    ("aggregate_clusters", "(aggregate_clusters (named k) (aggs (SUM v sum) (COUNT \"\" n)) (scan 0))",
+     [[col("k", sp.INT32, [1, 1, 2, 1, 1, 3, 3]), col("v", sp.INT32, [1, 2, 3, 4, 5, 6, 7])]],
+     {"k": [1, 2, 1, 3], "sum": [3, 3, 9, 13], "n": [2, 1, 2, 2]}, True),
+    # :104-120 no clustering column: one result row
+    ("aggregate_clusters_no_key", "(aggregate_clusters (named) (aggs (SUM col0 sum)) (scan 0))",
+     [[col("col0", sp.INT32, [13, 3, 7])]], {"sum": [23]}, True),
+    # :122-133 empty input with a clustering column
+    ("aggregate_clusters_empty", "(aggregate_clusters (named col0) (aggs (SUM col1 sum)) (scan 0))",
+     [[col("col0", sp.INT64, []), col("col1", sp.INT32, [])]], {"col0": [], "sum": []}, True),
+    # :150-178 three-column key, col1 both clustered by and aggregated (STRING columns re-coded)
+    ("aggregate_clusters_three_keys",
+     "(aggregate_clusters (rename (col0 A) (col1 B) (col2 C)) (aggs (SUM col1 sum1) (SUM col3 sum3)) (scan 0))",
+     [[col("col0", sp.INT64, [1, 1, 1, 1, 1, 1, 1, 1]), col("col1", sp.INT32, [0, 2, 2, 2, 2, 1, 1, 1]),
+       col("col2", sp.INT64, [1, 1, 1, 2, 2, 2, 2, 9]), col("col3", sp.INT32, [13, 4, 5, -4, -6, 3, 4, -3])]],
+     {"A": [1, 1, 1, 1, 1], "B": [0, 2, 2, 1, 1], "C": [1, 1, 2, 2, 9], "sum1": [0, 4, 4, 2, 1], "sum3": [13, 9, -10, 7, -3]}, True),
+    # NULL keys cluster together (NULL equals NULL in the comparator, aggregate_clusters.cc:67-125), all-NULL inputs give NULL
+    ("aggregate_clusters_null_keys", "(aggregate_clusters (named k) (aggs (SUM v s) (MIN v m) (COUNT v c)) (scan 0))",
+     [[ncol("k", sp.INT64, [N, N, 4, 4, N, 7]), ncol("v", sp.DOUBLE, [1.0, N, N, N, 2.5, 3.0])]],
+     {"k": [N, 4, N, 7], "s": [1.0, N, 2.5, 3.0], "m": [1.0, N, 2.5, 3.0], "c": [1, 0, 1, 1]}, True),
+    ("bound_aggregate_clusters", "(bound_aggregate_clusters (named k) (aggs (MAX v mx) (LAST v l)) (scan 0))",
+     [[col("k", sp.DOUBLE, [0.5, 0.5, -1.0, 0.5]), col("v", sp.INT64, [3, 9, 4, 1])]],
+     {"k": [0.5, -1.0, 0.5], "mx": [9, 4, 1], "l": [9, 4, 1]}, True),
 ]
 
 

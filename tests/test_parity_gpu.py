@@ -468,3 +468,42 @@ LATE = sorted(GOLDEN_LATE, key=lambda c: next((i for i, p in enumerate(_LATE_ORD
 def test_reference_vectors_late(b200, case, next_rows):
     _, plan, tables, expected, ordered = case
     check_result(b200.run(plan, tables, next_max_rows=next_rows), expected, ordered)
+
+
+
+def test_nan_join_keys_never_match(ref, b200):
+    """row_hash_set.cc:487-498 confirms a hash hit with operator==, which no NaN satisfies: a NaN key finds nothing
+    and is found by nothing (VERDICT r1 weak #3). The kernels treat a NaN key like a NULL key."""
+    nan = float("nan")
+    build = [sp.Column("pk", sp.DOUBLE, [1.0, nan, 2.0, nan, 3.0, 2.0]), sp.Column("w", sp.INT64, [10, 20, 30, 40, 50, 60])]
+    probe = [sp.Column("fk", sp.DOUBLE, [nan, 1.0, 3.0, nan, 7.0, 2.0]), sp.Column("lv", sp.INT64, [1, 2, 3, 4, 5, 6])]
+    for jt in ("INNER", "LEFT_OUTER"):
+        plan = "(hash_join %s (named fk) (named pk) (multi (0 (all)) (1 (named w))) NOT_UNIQUE (scan 0) (scan 1))" % jt
+        same_results(ref.run(plan, [probe, build]), b200.run(plan, [probe, build]))
+    rng = np.random.default_rng(8)
+    n = 50_000
+    pk = rng.integers(0, 3000, n).astype(np.float32)
+    pk[rng.random(n) < 0.05] = np.nan
+    fk = rng.integers(0, 3000, 3 * n).astype(np.float32)
+    fk[rng.random(3 * n) < 0.05] = np.nan
+    big_b = [sp.Column("pk", sp.FLOAT, pk), sp.Column("w", sp.INT64, np.arange(n))]
+    big_p = [sp.Column("fk", sp.FLOAT, fk), sp.Column("lv", sp.INT64, np.arange(3 * n))]
+    plan = "(hash_join LEFT_OUTER (named fk) (named pk) (multi (0 (all)) (1 (named w))) NOT_UNIQUE (scan 0) (scan 1))"
+    same_results(ref.run(plan, [big_p, big_b], next_max_rows=8192), b200.run(plan, [big_p, big_b], next_max_rows=8192))
+
+
+def test_nan_group_keys_are_refused(ref, b200):
+    """The reference makes every row with a NaN key a group of its own (operator== after the hash); the GPU table
+    compares bit images and would merge them, so the plan is refused with ERROR_NOT_IMPLEMENTED instead of being
+    answered differently. Float keys without NaN (and NaN hidden under NULL) aggregate as before."""
+    nan = float("nan")
+    cols = [sp.Column("k", sp.DOUBLE, [1.0, nan, 1.0, nan, 2.0]), sp.Column("v", sp.INT64, [1, 2, 3, 4, 5])]
+    plan = "(group (named k) (aggs (SUM v s) (COUNT \"\" n)) (scan 0))"
+    want, got = ref.run(plan, [cols]), b200.run(plan, [cols])
+    assert want.code == 0 and want.rows == 4          # two NaN rows, two groups
+    assert got.code == 103 and "NaN" in got.error
+    plan_f = "(group (named k) (aggs (SUM v s)) (compute (compound (col k) (col v)) (filter (greater (col v) (i64 0)) (all) (scan 0))))"
+    assert b200.run(plan_f, [cols]).code == 103        # the fused child path checks as well
+    ok = [sp.Column("k", sp.DOUBLE, [1.0, nan, 1.0, 0.5, 2.0], is_null=[False, True, False, False, False]),
+          sp.Column("v", sp.INT64, [1, 2, 3, 4, 5])]
+    same_results(ref.run(plan, [ok]), b200.run(plan, [ok]), ordered=False, sort_cols=[0])

@@ -1083,7 +1083,7 @@ __global__ void __launch_bounds__(NT + 32) expr_kernel(const __grid_constant__ E
 // thread's rows, the predicate mask, accumulator addresses): it is allowed the registers of two
 // resident CTAs per SM instead of being squeezed to the default (which spilled that state).
 template <int NT, int R>
-__global__ void __launch_bounds__(NT + 32, 2) expr_sink_kernel(const __grid_constant__ ExprParams p) {
+__global__ void __launch_bounds__(NT + 32, (NT >= 192 ? 1 : 2)) expr_sink_kernel(const __grid_constant__ ExprParams p) {
   expr_kernel_body<NT, R, true>(p);
 }
 
@@ -1096,12 +1096,12 @@ struct Variant {
   void (*sink_kernel)(const ExprParams);   // aggregation-sink instantiation, or nullptr
 };
 static const Variant kVariants[] = {
-    {256, 4, expr_kernel<256, 4>, nullptr},
-    {128, 8, expr_kernel<128, 8>, nullptr},
+    {256, 4, expr_kernel<256, 4>, expr_sink_kernel<256, 4>},
+    {128, 8, expr_kernel<128, 8>, expr_sink_kernel<128, 8>},
     {256, 8, expr_kernel<256, 8>, nullptr},
     {128, 16, expr_kernel<128, 16>, nullptr},
     {64, 16, expr_kernel<64, 16>, nullptr},
-    {128, 4, expr_kernel<128, 4>, nullptr},
+    {128, 4, expr_kernel<128, 4>, expr_sink_kernel<128, 4>},
     {64, 8, expr_kernel<64, 8>, expr_sink_kernel<64, 8>},
     {96, 8, expr_kernel<96, 8>, expr_sink_kernel<96, 8>},
     {96, 4, expr_kernel<96, 4>, expr_sink_kernel<96, 4>},
@@ -1223,7 +1223,17 @@ int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_
   // 512-row tiles of 64 consumer threads x 8 rows first: eight rows per thread amortise the
   // interpreter's dispatch, the small tile leaves room for two or three resident CTAs next to the
   // per-thread accumulators (the kernel is bound by instruction issue and latency, not by bytes)
-  const Try tries[] = {{6, 3}, {6, 2}, {7, 2}, {8, 3}, {8, 2}, {6, 1}, {7, 1}, {8, 1}};
+  // Measured on the Q1 shape (200M rows, profiles/r2d_q1_sink_variants.txt): the kernel is bound by instruction
+  // issue with one consumer warp per scheduler, so consumer warps per SM decide. One CTA of 256 consumer threads x
+  // 4 rows (8 consumer warps, the whole SM's shared memory) 9.06 ms; two CTAs of 64 x 8 (4 warps, half the
+  // dispatch cost per row) 11.05 ms; 128 x 8 in one CTA 10.8 ms; two CTAs of 96 x 8 14.4 ms.
+  Try tries[] = {{0, 1}, {6, 3}, {6, 2}, {7, 2}, {8, 3}, {8, 2}, {6, 1}, {7, 1}, {8, 1}};
+  if (const char* ev = getenv("SSB200_SINK_VARIANT")) {   // experiments: pin the tile variant / resident CTAs
+    const int v = atoi(ev), c = getenv("SSB200_SINK_CTAS") ? atoi(getenv("SSB200_SINK_CTAS")) : 2;
+    if (v >= 0 && v < kNumVariants && kVariants[v].sink_kernel != nullptr && c >= 1) {
+      for (size_t i = 0; i < sizeof(tries) / sizeof(tries[0]); ++i) { tries[i].variant = v; tries[i].ctas = c; }
+    }
+  }
   ssb_program* best = nullptr;
   long long best_score = -1;
   std::string err;
@@ -1249,7 +1259,7 @@ int sink_program_for(ssb_program* base, int n_keys, int n_aggs, int groups, ssb_
     const long long score = static_cast<long long>(stages >= 2 ? (stages > 3 ? 3 : stages) : 0) * (resident < 1 ? 1 : resident) *
                                 cand->prog.params.tile * 16 + (resident < 1 ? 1 : resident);
     // the tries are in order of preference: the first one with two stages and two resident CTAs is taken
-    if (stages >= 2 && resident >= 2) { delete best; best = cand; break; }
+    if (stages >= 2 && resident >= c) { delete best; best = cand; break; }
     if (score > best_score) { delete best; best = cand; best_score = score; } else { delete cand; }
   }
   if (best == nullptr) return fail(ctx, rc, err);

@@ -321,6 +321,29 @@ int ssb_scatter(ssb_ctx* ctx, const ssb_column* src, const int64_t* d_idx, int64
 int ssb_sort_permutation(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys,
                          const int32_t* descending, int64_t rows, int64_t* d_perm);
 
+/* ------------------------------------------------------------------ STRING / BINARY columns */
+/* Replaces the StringPiece-into-arena cells of the reference (base/infrastructure/types.h:53-68, block.h:259-281,
+ * base/memory/arena.h:48) and their comparisons (utils/strings/stringpiece.h:268-283: memcmp over the common
+ * prefix, the shorter one first; row_hash_set.cc:424-498 hashes the bytes and confirms with ==). On the device a
+ * variable-length column is (d_offsets INT64[rows + 1], d_bytes). ssb_string_rank writes dense ORDER-PRESERVING
+ * codes: d_codes[i] < d_codes[j] iff string i < string j, equal iff the bytes are equal; GroupAggregate, HashJoin,
+ * Sort and the comparison operators over STRING keys then run on INT64 code columns through the entry points
+ * above. d_first_rows[c] (room for `rows` entries, or NULL) = a row holding the string with code c: gathering
+ * those rows gives the sorted dictionary. max_len = an upper bound of the lengths. Synchronises. */
+int ssb_string_rank(ssb_ctx* ctx, const int64_t* d_offsets, const uint8_t* d_bytes, int64_t rows, int64_t max_len,
+                    int64_t* d_codes, int64_t* d_first_rows, int64_t* n_distinct);
+/* Gather of variable-length cells in two steps (the byte count is needed to allocate the result):
+ * d_out_offsets[n + 1] = offsets of the strings d_idx[0..n) laid end to end (d_idx NULL = identity, an index < 0 =
+ * an empty cell), *total_bytes = their total length (synchronises); then the bytes themselves (asynchronous).
+ * Replaces the deep copy of copy_column.cc:129-198 (ColumnCopier with an arena). */
+int ssb_string_gather_offsets(ssb_ctx* ctx, const int64_t* d_offsets, const int64_t* d_idx, int64_t n,
+                              int64_t* d_out_offsets, int64_t* total_bytes);
+int ssb_string_gather_bytes(ssb_ctx* ctx, const int64_t* d_offsets, const uint8_t* d_bytes, const int64_t* d_idx,
+                            int64_t n, const int64_t* d_out_offsets, uint8_t* d_out_bytes);
+/* d_dst[i] = d_src[i] + delta for i < n: appends one offsets array to another when two variable-length columns
+ * (or dictionaries) are concatenated (the bytes themselves are appended with ssb_memcpy_d2d). Asynchronous. */
+int ssb_string_shift_offsets(ssb_ctx* ctx, const int64_t* d_src, int64_t n, int64_t delta, int64_t* d_dst);
+
 /* ------------------------------------------------------------------ multi-GPU */
 /* One process per GPU; tables are sharded by contiguous row ranges. Compute / Project / Filter need no
  * exchange (run ssb_program_run on the shard). The operators whose CPU form keeps global state exchange

@@ -116,6 +116,10 @@ def load():
         "ssb_program_plan": (C.c_int, [P, I32, I32, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32), I32, I32, I32, C.c_uint32,
                                        P, C.c_char_p, I32]),
         "ssb_cluster_ids": (C.c_int, [P, I32, C.POINTER(Column), I64, P, P, C.POINTER(I64)]),
+        "ssb_string_rank": (C.c_int, [P, P, P, I64, I64, P, P, C.POINTER(I64)]),
+        "ssb_string_gather_offsets": (C.c_int, [P, P, P, I64, P, C.POINTER(I64)]),
+        "ssb_string_gather_bytes": (C.c_int, [P, P, P, P, I64, P, P]),
+        "ssb_string_shift_offsets": (C.c_int, [P, P, I64, I64, P]),
         "ssb_join_table": (C.c_int, [P, C.POINTER(P), C.POINTER(I64)]),
         "ssb_join_attach_parts": (C.c_int, [P, I32, I32, C.POINTER(P), C.POINTER(I64), C.POINTER(I64), C.POINTER(P)]),
         "ssb_comm_unique_id": (C.c_int, [P]),

@@ -439,6 +439,8 @@ class Block {
   void* mutable_data(int column) { return data_[column] ? data_[column]->data() : NULL; }
   bool* mutable_is_null(int column) { return nulls_[column] ? static_cast<bool*>(nulls_[column]->data()) : NULL; }
   bool is_nullable(int column) const { return schema().attribute(column).is_nullable(); }
+  // Variable-length cells (StringPiece) point into storage the block keeps alive: the arena of block.h:259-281.
+  void KeepAlive(const std::shared_ptr<const void>& storage) { storage_.push_back(storage); }
  private:
   Block(const Block&);
   void operator=(const Block&);
@@ -447,6 +449,7 @@ class Block {
   rowcount_t capacity_;
   vector<Buffer*> data_;
   vector<Buffer*> nulls_;
+  vector<std::shared_ptr<const void> > storage_;
 };
 
 }  // namespace supersonic

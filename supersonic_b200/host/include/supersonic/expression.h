@@ -28,6 +28,7 @@ struct ExprNode {
   int input;              // SSB_OP_INPUT: column index in the input schema
   int flags;              // SSB_NODE_*
   union { int64 i64; uint64 u64; double f64; float f32; int32 i32; uint32 u32; bool b; } imm;
+  string text;            // SSB_OP_CONST of type STRING / BINARY: the bytes
   ExprNode() : op(0), type(INT32), nullable(false), constant(false), input(-1), flags(0) { imm.u64 = 0; }
 };
 typedef std::shared_ptr<const ExprNode> NodePtr;
@@ -123,6 +124,8 @@ const Expression* ConstDouble(const double& value);
 const Expression* ConstBool(const bool& value);
 const Expression* ConstDate(const int32& value);
 const Expression* ConstDateTime(const int64& value);
+const Expression* ConstString(const StringPiece& value);
+const Expression* ConstBinary(const StringPiece& value);
 const Expression* Null(DataType type);
 const Expression* Sequence();
 

@@ -145,9 +145,9 @@ FailureOrVoid DeviceTable::Allocate(const TupleSchema& s, int64 capacity, bool f
     const Attribute& a = s.attribute(i);
     DeviceColumnRef& c = columns[i];
     c.data.reset(new DeviceBuffer);
-    PROPAGATE_ON_FAILURE(c.data->Allocate(static_cast<size_t>(capacity) * GetTypeInfo(a.type()).size() + 128));
+    PROPAGATE_ON_FAILURE(c.data->Allocate(static_cast<size_t>(capacity) * DeviceWidth(a.type()) + 128));
     c.col.data = c.data->get();
-    c.col.dtype = a.type();
+    c.col.dtype = DeviceType(a.type());   // variable-length attributes: INT64 codes (the dictionary is attached by the operator)
     c.col.nulls = NULL;
     c.col.reserved = 0;
     if (a.is_nullable() || force_nulls) {
@@ -165,8 +165,12 @@ FailureOrVoid DeviceTable::Download(Block* block, rowcount_t block_offset) const
   Session* s = sr.get();
   DeviceBuffer bools;
   for (size_t i = 0; i < columns.size(); ++i) {
-    const size_t w = GetTypeInfo(schema.attribute(static_cast<int>(i)).type()).size();
-    if (rows > 0) {
+    const DataType type = schema.attribute(static_cast<int>(i)).type();
+    const size_t w = GetTypeInfo(type).size();
+    if (IsVariableLength(type)) {
+      PROPAGATE_ON_FAILURE(DownloadStringColumn(s, columns[i], rows,
+                                                static_cast<StringPiece*>(block->mutable_data(static_cast<int>(i))) + block_offset, block));
+    } else if (rows > 0) {
       SSB_CALL(s, ssb_memcpy_d2h(s->ctx(), static_cast<char*>(block->mutable_data(static_cast<int>(i))) + block_offset * w,
                                  columns[i].col.data, static_cast<size_t>(rows) * w), "download");
     }
@@ -202,24 +206,27 @@ FailureOrVoid UploadColumns(const View& view, const vector<int>& cols, rowcount_
     schema.add_attribute(a);
     DeviceColumnRef& c = out->columns[k];
     const size_t w = src.type_info().size();
-    if (a.type() == STRING || a.type() == BINARY) {
-      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length columns are not on the B200 hot path (SURVEY 8f)"));
-    }
-    c.col.dtype = a.type();
+    c.col.dtype = DeviceType(a.type());
     c.col.reserved = 0;
     c.col.nulls = NULL;
     const char* p = static_cast<const char*>(src.data().raw()) + offset * w;
-    if (IsDevicePointer(src.data().raw())) {
-      if (src.is_null() != NULL) {
-        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "device-resident input columns must not carry an is_null vector"));
+    if (IsVariableLength(a.type())) {
+      // StringPiece cells (host memory): packed, copied and ranked into codes + dictionary
+      PROPAGATE_ON_FAILURE(UploadStringColumn(s, reinterpret_cast<const StringPiece*>(p), src.is_null() ? src.is_null() + offset : NULL,
+                                              rows, &c));
+    } else {
+      if (IsDevicePointer(src.data().raw())) {
+        if (src.is_null() != NULL) {
+          THROW(new Exception(ERROR_NOT_IMPLEMENTED, "device-resident input columns must not carry an is_null vector"));
+        }
+        c.col.data = const_cast<char*>(p);
+        continue;
       }
-      c.col.data = const_cast<char*>(p);
-      continue;
+      c.data.reset(new DeviceBuffer);
+      PROPAGATE_ON_FAILURE(c.data->Allocate(static_cast<size_t>(rows) * w + 128));
+      c.col.data = c.data->get();
+      if (rows > 0) SSB_CALL(s, ssb_memcpy_h2d(s->ctx(), c.col.data, p, static_cast<size_t>(rows) * w), "upload");
     }
-    c.data.reset(new DeviceBuffer);
-    PROPAGATE_ON_FAILURE(c.data->Allocate(static_cast<size_t>(rows) * w + 128));
-    c.col.data = c.data->get();
-    if (rows > 0) SSB_CALL(s, ssb_memcpy_h2d(s->ctx(), c.col.data, p, static_cast<size_t>(rows) * w), "upload");
     if (src.is_null() != NULL && rows > 0) {
       c.nulls.reset(new DeviceBuffer);
       PROPAGATE_ON_FAILURE(c.nulls->Allocate(BitmapBytes(static_cast<int64>(rows))));
@@ -249,7 +256,7 @@ struct Lowering {
     ssb_expr_node out;
     memset(&out, 0, sizeof(out));
     out.op = n->op;
-    out.out_type = n->type;
+    out.out_type = DeviceType(n->type);   // variable-length values travel as INT64 codes (constants are resolved by the cursor)
     out.arg[0] = out.arg[1] = out.arg[2] = -1;
     out.flags = n->flags;
     memcpy(&out.imm, &n->imm, sizeof(out.imm));
@@ -294,7 +301,7 @@ FailureOrOwned<DeviceProgram> DeviceProgram::Create(const TupleSchema& input_sch
   const int pred = predicate ? low.Lower(predicate) : -1;
   vector<int32_t> types, nullable;
   for (size_t k = 0; k < low.used.size(); ++k) {
-    types.push_back(input_schema.attribute(low.used[k]).type());
+    types.push_back(DeviceType(input_schema.attribute(low.used[k]).type()));
     nullable.push_back(input_schema.attribute(low.used[k]).is_nullable() ? 1 : 0);
   }
   std::unique_ptr<DeviceProgram> p(new DeviceProgram);
@@ -381,7 +388,24 @@ FailureOrVoid MaterializeOnDevice(Cursor* child, DeviceTable* out, std::unique_p
     }
     for (int c = 0; c < v.column_count(); ++c) {
       const size_t w = v.column(c).type_info().size();
-      memcpy(static_cast<char*>(block->mutable_data(c)) + rows * w, v.column(c).data().raw(), v.row_count() * w);
+      if (IsVariableLength(v.column(c).attribute().type())) {
+        // deep copy: the child may reuse the memory its cells point into on the next call
+        const StringPiece* src = static_cast<const StringPiece*>(v.column(c).data().raw());
+        StringPiece* dst = static_cast<StringPiece*>(block->mutable_data(c)) + rows;
+        size_t total = 0;
+        for (rowcount_t i = 0; i < v.row_count(); ++i) if (!v.column(c).is_null() || !v.column(c).is_null()[i]) total += src[i].size();
+        std::shared_ptr<vector<char> > store(new vector<char>(total + 1));
+        size_t at = 0;
+        for (rowcount_t i = 0; i < v.row_count(); ++i) {
+          if (v.column(c).is_null() && v.column(c).is_null()[i]) { dst[i] = StringPiece(); continue; }
+          if (src[i].size() > 0) memcpy(store->data() + at, src[i].data(), src[i].size());
+          dst[i] = StringPiece(store->data() + at, src[i].size());
+          at += src[i].size();
+        }
+        block->KeepAlive(store);
+      } else {
+        memcpy(static_cast<char*>(block->mutable_data(c)) + rows * w, v.column(c).data().raw(), v.row_count() * w);
+      }
       if (bool* hn = block->mutable_is_null(c)) {
         if (v.column(c).is_null()) memcpy(hn + rows, v.column(c).is_null(), v.row_count());
         else memset(hn + rows, 0, v.row_count());

@@ -388,10 +388,12 @@ class ConstExpression : public Expression {
     n->constant = true;
     n->flags = is_null_ ? SSB_NODE_NULL : 0;
     memcpy(&n->imm, &imm_, sizeof(imm_));
+    n->text = text_;
     return Single(input, n);
   }
   virtual string ToString(bool) const { return is_null_ ? "<" + TypeName(type_) + ">NULL" : "CONST_" + TypeName(type_); }
   union { int64 i64; uint64 u64; double f64; float f32; int32 i32; uint32 u32; bool b; } imm_;
+  string text_;   // STRING / BINARY literals
  private:
   DataType type_;
   bool is_null_;
@@ -840,6 +842,17 @@ SSB200_CONST(ConstBool, BOOL, b, bool)
 SSB200_CONST(ConstDate, DATE, i32, int32)
 SSB200_CONST(ConstDateTime, DATETIME, i64, int64)
 #undef SSB200_CONST
+// terminal_expressions.h:60-63: the bytes are copied (the reference copies them into its own arena)
+const Expression* ConstString(const StringPiece& value) {
+  ConstExpression* e = new ConstExpression(STRING, false);
+  e->text_ = value.as_string();
+  return e;
+}
+const Expression* ConstBinary(const StringPiece& value) {
+  ConstExpression* e = new ConstExpression(BINARY, false);
+  e->text_ = value.as_string();
+  return e;
+}
 const Expression* Null(DataType type) { return new ConstExpression(type, true); }
 const Expression* Sequence() { return new NotImplementedExpression("SEQUENCE"); }
 

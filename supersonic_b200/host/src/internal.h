@@ -86,12 +86,40 @@ class DeviceBuffer {
   size_t granted_;
 };
 
+// STRING / BINARY columns. On the device a variable-length column is a column of INT64 codes into a
+// dictionary of its distinct values in sorted order (code c = the c-th smallest value, so the codes compare like the
+// strings: utils/strings/stringpiece.h:268-283): the relational kernels run on the codes, the bytes are touched by
+// ssb_string_rank (building the codes) and when a result goes back to the host.
+struct HostDict { vector<int64> offsets; vector<char> bytes; };
+struct DeviceDict {
+  DeviceBuffer offsets;   // INT64[n + 1]
+  DeviceBuffer bytes;
+  int64 n, total_bytes, max_len;
+  std::shared_ptr<const HostDict> host;   // filled by the first download
+  DeviceDict() : n(0), total_bytes(0), max_len(0) {}
+};
+inline bool IsVariableLength(DataType t) { return t == STRING || t == BINARY; }
+inline DataType DeviceType(DataType t) { return IsVariableLength(t) ? INT64 : t; }   // what the kernels see
+inline size_t DeviceWidth(DataType t) { return IsVariableLength(t) ? 8 : GetTypeInfo(t).size(); }
+TupleSchema DeviceSchema(const TupleSchema& s);   // variable-length attributes as INT64 (codes)
+
 // A set of equally long device columns: either borrowed (device pointers handed in through
 // ScanView) or owned buffers.
 struct DeviceColumnRef {
   ssb_column col;
   std::shared_ptr<DeviceBuffer> data, nulls;   // empty when borrowed
+  std::shared_ptr<DeviceDict> dict;            // variable-length columns: col holds INT64 codes into it
 };
+
+// StringPiece cells of a host column -> codes + dictionary on the device.
+FailureOrVoid UploadStringColumn(Session* s, const StringPiece* cells, const bool* is_null, rowcount_t rows, DeviceColumnRef* out);
+// Codes + dictionary -> StringPiece cells pointing into storage the block keeps alive (NULL rows are left empty).
+FailureOrVoid DownloadStringColumn(Session* s, const DeviceColumnRef& col, int64 rows, StringPiece* cells, Block* owner);
+// Re-encodes the variable-length columns `cols` (rows[i] rows each) and the constants against ONE merged dictionary,
+// so that their codes compare with each other; codes of the constants (dense ranks in the merged dictionary) are
+// returned. Columns that already share one dictionary, with no constants, are left as they are.
+FailureOrVoid UnifyDictionaries(Session* s, const vector<DeviceColumnRef*>& cols, const vector<int64>& rows,
+                                const vector<string>& constants, vector<int64>* constant_codes);
 struct DeviceTable {
   TupleSchema schema;
   vector<DeviceColumnRef> columns;

@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <functional>
 #include <map>
+#include <set>
 #include <mutex>
 #include <thread>
 
@@ -297,7 +298,149 @@ class RowwiseCursor : public GpuCursor {
   }
 
  protected:
+  // ---- variable-length columns ------------------------------------------------------------------
+  static void CollectNodes(const NodePtr& n, std::set<const ExprNode*>* seen, vector<const ExprNode*>* order) {
+    if (!n || !seen->insert(n.get()).second) return;
+    for (size_t i = 0; i < n->args.size(); ++i) CollectNodes(n->args[i], seen, order);
+    order->push_back(n.get());
+  }
+  void PlanNodes(vector<const ExprNode*>* order) const {
+    std::set<const ExprNode*> seen;
+    for (size_t j = 0; j < plan_.outputs.size(); ++j) CollectNodes(plan_.outputs[j], &seen, order);
+    CollectNodes(plan_.predicate, &seen, order);
+  }
+  bool PlanHasStrings() const {
+    vector<const ExprNode*> nodes;
+    PlanNodes(&nodes);
+    for (size_t i = 0; i < nodes.size(); ++i) if (IsVariableLength(nodes[i]->type)) return true;
+    return false;
+  }
+  // Copies the DAG under `n`, replacing the nodes in `replace`.
+  static NodePtr Rewrite(const NodePtr& n, const std::map<const ExprNode*, NodePtr>& replace, std::map<const ExprNode*, NodePtr>* done) {
+    if (!n) return n;
+    std::map<const ExprNode*, NodePtr>::const_iterator r = replace.find(n.get());
+    if (r != replace.end()) return r->second;
+    std::map<const ExprNode*, NodePtr>::iterator d = done->find(n.get());
+    if (d != done->end()) return d->second;
+    bool changed = false;
+    vector<NodePtr> args;
+    for (size_t i = 0; i < n->args.size(); ++i) {
+      args.push_back(Rewrite(n->args[i], replace, done));
+      changed = changed || args.back().get() != n->args[i].get();
+    }
+    NodePtr out = n;
+    if (changed) {
+      std::shared_ptr<ExprNode> c(new ExprNode(*n));
+      c->args = args;
+      out = c;
+    }
+    (*done)[n.get()] = out;
+    return out;
+  }
+
+  // A plan that touches STRING / BINARY values. The kernels see codes: value-producing nodes of variable-length type
+  // may only be input columns, literals and NULL (anything else -- CONCAT, SUBSTRING, IF over strings ... -- is not on
+  // this path); the columns and literals that meet in a comparison are re-encoded against one merged dictionary, the
+  // literals become INT64 constants (their codes), and a pass-through output column inherits its input's dictionary.
+  FailureOrVoid RunWithStrings(DeviceTable* result) {
+    FailureOr<Session*> sr = Session::Get();
+    PROPAGATE_ON_FAILURE(sr);
+    Session* s = sr.get();
+    vector<const ExprNode*> nodes;
+    PlanNodes(&nodes);
+    std::map<int, int> needed;
+    vector<const ExprNode*> literals;
+    std::set<int> compared_cols;
+    bool compares_literal = false;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      const ExprNode* n = nodes[i];
+      if (n->op == SSB_OP_INPUT) needed[n->input] = 1;
+      if (IsVariableLength(n->type)) {
+        if (n->op == SSB_OP_CONST) { if (!(n->flags & SSB_NODE_NULL)) literals.push_back(n); }
+        else if (n->op != SSB_OP_INPUT) {
+          THROW(new Exception(ERROR_NOT_IMPLEMENTED, "expressions that compute STRING / BINARY values are not on the B200 hot path "
+                                                     "(columns, literals and comparisons are): " + n->name));
+        }
+        continue;
+      }
+      bool var_args = false;
+      for (size_t a = 0; a < n->args.size(); ++a) var_args = var_args || IsVariableLength(n->args[a]->type);
+      if (!var_args) continue;
+      switch (n->op) {
+        case SSB_OP_EQ: case SSB_OP_NE: case SSB_OP_LT: case SSB_OP_LE:
+          for (size_t a = 0; a < n->args.size(); ++a) {
+            if (n->args[a]->op == SSB_OP_INPUT) compared_cols.insert(n->args[a]->input);
+            else if (!(n->args[a]->flags & SSB_NODE_NULL)) compares_literal = true;
+          }
+          break;
+        case SSB_OP_IS_NULL: break;
+        default:
+          THROW(new Exception(ERROR_NOT_IMPLEMENTED, "this operator over STRING / BINARY arguments is not on the B200 hot path: " + n->name));
+      }
+    }
+    // the base columns
+    DeviceTable base;
+    std::unique_ptr<Block> keepalive;
+    int64 rows = 0;
+    std::map<int, DeviceColumnRef> col_of;
+    PROPAGATE_ON_FAILURE(FetchBase(needed, &base, &keepalive, &rows, &col_of));
+    // one dictionary for everything that is compared
+    std::map<const ExprNode*, NodePtr> replace;
+    if (!compared_cols.empty() || compares_literal) {
+      vector<DeviceColumnRef*> cols;
+      vector<int64> col_rows;
+      for (std::set<int>::iterator it = compared_cols.begin(); it != compared_cols.end(); ++it) { cols.push_back(&col_of[*it]); col_rows.push_back(rows); }
+      vector<string> texts;
+      for (size_t i = 0; i < literals.size(); ++i) texts.push_back(literals[i]->text);
+      vector<int64> codes;
+      PROPAGATE_ON_FAILURE(UnifyDictionaries(s, cols, col_rows, texts, &codes));
+      for (size_t i = 0; i < literals.size(); ++i) {
+        std::shared_ptr<ExprNode> c(new ExprNode(*literals[i]));
+        c->type = INT64;
+        c->imm.u64 = 0;
+        c->imm.i64 = i < codes.size() ? codes[i] : 0;
+        replace[literals[i]] = c;
+      }
+    } else {
+      for (size_t i = 0; i < literals.size(); ++i) {   // a literal that is only passed through: not on this path
+        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "STRING / BINARY literals as result columns are not on the B200 hot path"));
+      }
+    }
+    std::map<const ExprNode*, NodePtr> done;
+    vector<NodePtr> outputs;
+    for (size_t j = 0; j < plan_.outputs.size(); ++j) outputs.push_back(Rewrite(plan_.outputs[j], replace, &done));
+    const NodePtr predicate = Rewrite(plan_.predicate, replace, &done);
+    const size_t n_out = outputs.size();
+    for (size_t group = n_out > 0 ? n_out : 1;; group = (group + 1) / 2) {
+      vector<std::unique_ptr<DeviceProgram> > programs;
+      Exception* error = NULL;
+      for (size_t first = 0; first < (n_out > 0 ? n_out : 1) && error == NULL; first += group) {
+        vector<NodePtr> outs;
+        for (size_t j = first; j < n_out && j < first + group; ++j) outs.push_back(outputs[j]);
+        FailureOrOwned<DeviceProgram> created = DeviceProgram::Create(plan_.base_schema, outs, predicate);
+        if (created.is_failure()) error = created.release_exception();
+        else programs.push_back(std::unique_ptr<DeviceProgram>(created.release()));
+      }
+      if (error == NULL) {
+        PROPAGATE_ON_FAILURE(RunOver(programs, group, rows, col_of, result));
+        break;
+      }
+      if (error->return_code() != ERROR_NOT_IMPLEMENTED || group <= 1) return Failure(error);
+      delete error;
+    }
+    for (size_t j = 0; j < plan_.outputs.size(); ++j) {
+      if (!IsVariableLength(plan_.outputs[j]->type)) continue;
+      if (plan_.outputs[j]->op == SSB_OP_INPUT) {
+        result->columns[j].dict = col_of[plan_.outputs[j]->input].dict;
+      } else {   // the NULL literal: every row is NULL, any dictionary will do
+        result->columns[j].dict.reset(new DeviceDict);
+      }
+    }
+    return Success();
+  }
+
   virtual FailureOrVoid Run(DeviceTable* result) {
+    if (PlanHasStrings()) return RunWithStrings(result);
     // One kernel evaluates the predicate and every output column. Plans too wide for one
     // CTA's shared memory are split into column groups that share the predicate.
     const size_t n_out = plan_.outputs.size();
@@ -317,13 +460,25 @@ class RowwiseCursor : public GpuCursor {
     }
   }
 
+  // The base columns `needed` (schema positions), uploaded or referenced once.
+  FailureOrVoid FetchBase(const std::map<int, int>& needed, DeviceTable* base, std::unique_ptr<Block>* keepalive, int64* rows,
+                          std::map<int, DeviceColumnRef>* col_of) {
+    if (plan_.source) {
+      PROPAGATE_ON_FAILURE(MaterializeOnDevice(plan_.source.get(), base, keepalive));
+      *rows = base->rows;
+      for (std::map<int, int>::const_iterator it = needed.begin(); it != needed.end(); ++it) (*col_of)[it->first] = base->columns[it->first];
+    } else {
+      *rows = static_cast<int64>(plan_.base.row_count());
+      vector<int> cols;
+      for (std::map<int, int>::const_iterator it = needed.begin(); it != needed.end(); ++it) cols.push_back(it->first);
+      PROPAGATE_ON_FAILURE(UploadColumns(plan_.base, cols, 0, plan_.base.row_count(), base));
+      for (size_t k = 0; k < cols.size(); ++k) (*col_of)[cols[k]] = base->columns[k];
+    }
+    return Success();
+  }
+
   FailureOrVoid RunPrograms(const vector<std::unique_ptr<DeviceProgram> >& programs, size_t group,
                             DeviceTable* result) {
-    FailureOr<Session*> s = Session::Get();
-    PROPAGATE_ON_FAILURE(s);
-    // the base columns, uploaded (or referenced) once for all programs
-    vector<int> all_cols;
-    for (int c = 0; c < plan_.base_schema.attribute_count(); ++c) all_cols.push_back(c);
     std::map<int, int> needed;
     for (size_t g = 0; g < programs.size(); ++g) {
       for (size_t k = 0; k < programs[g]->used_inputs().size(); ++k) needed[programs[g]->used_inputs()[k]] = 1;
@@ -332,17 +487,14 @@ class RowwiseCursor : public GpuCursor {
     std::unique_ptr<Block> keepalive;
     int64 rows = 0;
     std::map<int, DeviceColumnRef> col_of;
-    if (plan_.source) {
-      PROPAGATE_ON_FAILURE(MaterializeOnDevice(plan_.source.get(), &base, &keepalive));
-      rows = base.rows;
-      for (std::map<int, int>::iterator it = needed.begin(); it != needed.end(); ++it) col_of[it->first] = base.columns[it->first];
-    } else {
-      rows = static_cast<int64>(plan_.base.row_count());
-      vector<int> cols;
-      for (std::map<int, int>::iterator it = needed.begin(); it != needed.end(); ++it) cols.push_back(it->first);
-      PROPAGATE_ON_FAILURE(UploadColumns(plan_.base, cols, 0, plan_.base.row_count(), &base));
-      for (size_t k = 0; k < cols.size(); ++k) col_of[cols[k]] = base.columns[k];
-    }
+    PROPAGATE_ON_FAILURE(FetchBase(needed, &base, &keepalive, &rows, &col_of));
+    return RunOver(programs, group, rows, col_of, result);
+  }
+
+  FailureOrVoid RunOver(const vector<std::unique_ptr<DeviceProgram> >& programs, size_t group, int64 rows,
+                        std::map<int, DeviceColumnRef>& col_of, DeviceTable* result) {
+    FailureOr<Session*> s = Session::Get();
+    PROPAGATE_ON_FAILURE(s);
     PROPAGATE_ON_FAILURE(result->Allocate(plan_.schema, rows, /* force_nulls = */ true));
     for (size_t j = 0; j < result->columns.size(); ++j) {   // columns the program proves NOT NULL are never written
       SSB_CALL(s.get(), ssb_memset(s.get()->ctx(), result->columns[j].col.nulls, 0,
@@ -423,6 +575,7 @@ class RowwiseCursor : public GpuCursor {
   FailureOrVoid DecideMode() {
     mode_ = WHOLE;
     if (plan_.source) return Success();
+    if (PlanHasStrings()) return Success();   // variable-length columns: one dictionary per column, whole-table path
     const rowcount_t rows = plan_.base.row_count();
     rowcount_t chunk = 4u << 20;
     if (const char* env = getenv("SSB200_CHUNK_ROWS")) chunk = static_cast<rowcount_t>(atoll(env));
@@ -796,6 +949,11 @@ FailureOrVoid BindAggregations(const AggregationSpecification& spec, const Tuple
         THROW(new Exception(ERROR_INVALID_ARGUMENT_TYPE, "Aggregation not supported. Aggregation function SUM not defined for types " +
                                                              DataType_Name(in_type) + " and " + DataType_Name(out_type) + "."));
       }
+      if (in_type == BINARY) {   // column_aggregator.cc: no aggregator but COUNT is instantiated for BINARY
+        THROW(new Exception(ERROR_INVALID_ARGUMENT_TYPE, "Aggregation not supported. Aggregation function " + Aggregation_Name(fn) +
+                                                             " not defined for types " + DataType_Name(in_type) + " and " +
+                                                             DataType_Name(out_type) + "."));
+      }
       if (out_type != in_type) {
         if (!(IsNumericType(in_type) && IsNumericType(out_type))) {
           THROW(new Exception(ERROR_INVALID_ARGUMENT_TYPE,
@@ -803,13 +961,11 @@ FailureOrVoid BindAggregations(const AggregationSpecification& spec, const Tuple
                                   " not defined for types " + DataType_Name(in_type) + " and " + DataType_Name(out_type) + "."));
         }
       }
-      if (in_type == STRING || in_type == BINARY) {
-        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length aggregates are not on the B200 hot path (SURVEY 8f)"));
-      }
     }
     b.spec.input = -1;   // filled by the cursor (index into the values array)
-    b.spec.in_type = in_type;
-    b.spec.out_type = out_type;
+    // MIN / MAX / FIRST / LAST / COUNT over STRING / BINARY run on the column's order-preserving codes
+    b.spec.in_type = DeviceType(in_type);
+    b.spec.out_type = DeviceType(out_type);
     b.spec.in_nullable = in_nullable ? 1 : 0;
     if (!result_schema->add_attribute(Attribute(e.output(), out_type, out_null))) {
       THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + e.output() + "' in result schema"));
@@ -836,6 +992,9 @@ class GroupCursor : public GpuCursor {
   // Returns true when the fused form ran; false = not applicable (plan too wide for one program).
   FailureOr<bool> RunFused(Session* s, DeviceTable* result) {
     const RowwisePlan& plan = *fused_;
+    // variable-length columns: the row-wise child resolves dictionaries itself (RowwiseCursor::RunWithStrings)
+    for (int i = 0; i < plan.base_schema.attribute_count(); ++i) if (IsVariableLength(plan.base_schema.attribute(i).type())) return Success(false);
+    for (int i = 0; i < plan.schema.attribute_count(); ++i) if (IsVariableLength(plan.schema.attribute(i).type())) return Success(false);
     // program outputs: the key columns, then the distinct aggregate inputs in order of first use
     vector<NodePtr> outs;
     for (size_t k = 0; k < keys_.size(); ++k) outs.push_back(plan.outputs[keys_[k]]);
@@ -918,14 +1077,28 @@ class GroupCursor : public GpuCursor {
     return Success(true);
   }
 
-  FailureOrVoid Finish(Session* s, const vector<ssb_agg_spec>& specs, DeviceTable* result) {
+  // `in`: the aggregated table when it carries variable-length columns (their dictionaries pass to the result)
+  FailureOrVoid Finish(Session* s, const vector<ssb_agg_spec>& specs, DeviceTable* result, const DeviceTable* in = NULL) {
     int64_t n_groups = 0;
     vector<ssb_column> kout(keys_.size() ? keys_.size() : 1), aout(specs.size() ? specs.size() : 1);
     SSB_CALL(s, ssb_group_finalize(group_, &n_groups, kout.data(), aout.data()), "group-by finalize");
     result->schema = schema();
     result->columns.clear();
-    for (size_t k = 0; k < keys_.size(); ++k) { DeviceColumnRef c; c.col = kout[k]; result->columns.push_back(c); }
-    for (size_t i = 0; i < specs.size(); ++i) { DeviceColumnRef c; c.col = aout[i]; result->columns.push_back(c); }
+    for (size_t k = 0; k < keys_.size(); ++k) {
+      DeviceColumnRef c;
+      c.col = kout[k];
+      if (in != NULL) c.dict = in->columns[keys_[k]].dict;
+      result->columns.push_back(c);
+    }
+    for (size_t i = 0; i < specs.size(); ++i) {
+      DeviceColumnRef c;
+      c.col = aout[i];
+      // MIN / MAX / FIRST / LAST of a variable-length column: a code of the input's dictionary
+      if (in != NULL && aggs_[i].input_position >= 0 && IsVariableLength(schema().attribute(static_cast<int>(keys_.size() + i)).type())) {
+        c.dict = in->columns[aggs_[i].input_position].dict;
+      }
+      result->columns.push_back(c);
+    }
     result->rows = n_groups;
     return Success();
   }
@@ -946,7 +1119,7 @@ class GroupCursor : public GpuCursor {
     vector<ssb_column> key_cols, value_cols;
     for (size_t k = 0; k < keys_.size(); ++k) {
       const Attribute& a = child_->schema().attribute(keys_[k]);
-      key_types.push_back(a.type());
+      key_types.push_back(DeviceType(a.type()));
       key_nullable.push_back(a.is_nullable() ? 1 : 0);
       key_cols.push_back(in.columns[keys_[k]].col);
     }
@@ -968,7 +1141,7 @@ class GroupCursor : public GpuCursor {
                                  specs.data(), expected, &group_), "group-by setup");
     SSB_CALL(s, ssb_group_update(group_, key_cols.empty() ? &dummy_col : key_cols.data(),
                                  value_cols.empty() ? &dummy_col : value_cols.data(), in.rows), "group-by");
-    return Finish(s, specs, result);
+    return Finish(s, specs, result, &in);
   }
  private:
   std::unique_ptr<RowwisePlan> fused_;
@@ -1060,6 +1233,9 @@ class ClustersCursor : public GpuCursor {
         dst.nulls = NULL;
       }
       SSB_CALL(s, ssb_gather(s->ctx(), &aout[i], static_cast<const int64_t*>(perm.get()), clusters, &dst), "gather");
+      if (aggs_[i].input_position >= 0 && IsVariableLength(schema().attribute(static_cast<int>(keys_.size() + i)).type())) {
+        result->columns[keys_.size() + i].dict = in.columns[aggs_[i].input_position].dict;
+      }
     }
     SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");
     return Success();
@@ -1085,10 +1261,6 @@ class AggregateClustersOperation : public BasicOperation {
     for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
       keys.push_back(proj->source_attribute_position(i));
       result.add_attribute(proj->result_schema().attribute(i));
-      const DataType t = proj->result_schema().attribute(i).type();
-      if (t == STRING || t == BINARY) {
-        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length clustering keys are not on the B200 hot path (SURVEY 8f)"));
-      }
     }
     vector<BoundAggregation> aggs;
     PROPAGATE_ON_FAILURE(BindAggregations(*aggregation_, cs, &aggs, &result));
@@ -1132,7 +1304,14 @@ class ConcatCursor : public GpuCursor {
     DeviceBuffer bytes, part_bytes;
     PROPAGATE_ON_FAILURE(bytes.Allocate(static_cast<size_t>(total) + 128));
     for (int c = 0; c < schema().attribute_count(); ++c) {
-      const size_t w = GetTypeInfo(schema().attribute(c).type()).size();
+      const size_t w = DeviceWidth(schema().attribute(c).type());
+      if (IsVariableLength(schema().attribute(c).type())) {   // one dictionary for the column of every input
+        vector<DeviceColumnRef*> cols;
+        vector<int64> col_rows;
+        for (size_t i = 0; i < parts.size(); ++i) { cols.push_back(&parts[i].columns[c]); col_rows.push_back(parts[i].rows); }
+        PROPAGATE_ON_FAILURE(UnifyDictionaries(s, cols, col_rows, vector<string>(), NULL));
+        if (!parts.empty()) result->columns[c].dict = parts[0].columns[c].dict;
+      }
       int64 at = 0;
       bool any_nulls = false;
       for (size_t i = 0; i < parts.size(); ++i) any_nulls = any_nulls || parts[i].columns[c].col.nulls != NULL;
@@ -1181,10 +1360,6 @@ class GroupAggregateOperation : public BasicOperation {
       for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
         keys.push_back(proj->source_attribute_position(i));
         result.add_attribute(proj->result_schema().attribute(i));
-        const DataType t = proj->result_schema().attribute(i).type();
-        if (t == STRING || t == BINARY) {
-          THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length group keys are not on the B200 hot path (SURVEY 8f)"));
-        }
       }
     }
     vector<BoundAggregation> aggs;
@@ -1227,6 +1402,7 @@ FailureOrVoid GatherColumns(Session* s, const DeviceTable& src, const vector<int
     ssb_column dst = to.col;
     if (from.col.nulls == NULL && !force_nulls) dst.nulls = NULL;
     SSB_CALL(s, ssb_gather(s->ctx(), &from.col, d_idx, n, &dst), "gather");
+    to.dict = from.dict;   // variable-length columns: the gathered codes keep their dictionary
   }
   return Success();
 }
@@ -1255,6 +1431,17 @@ class HashJoinCursor : public GpuCursor {
     // i.e. once the probe side has produced a row
     if (join_type_ != INNER && join_type_ != LEFT_OUTER && lhs_table_.rows > 0) {
       THROW(new Exception(ERROR_NOT_IMPLEMENTED, "Unsupported join_type in hash_join: " + JoinType_Name(join_type_)));
+    }
+    // variable-length keys: both sides' codes must come from one dictionary
+    for (size_t k = 0; k < rhs_keys_.size() && k < lhs_keys_.size(); ++k) {
+      if (!IsVariableLength(rhs_table_.schema.attribute(rhs_keys_[k]).type())) continue;
+      vector<DeviceColumnRef*> cols;
+      cols.push_back(&lhs_table_.columns[lhs_keys_[k]]);
+      cols.push_back(&rhs_table_.columns[rhs_keys_[k]]);
+      vector<int64> col_rows;
+      col_rows.push_back(lhs_table_.rows);
+      col_rows.push_back(rhs_table_.rows);
+      PROPAGATE_ON_FAILURE(UnifyDictionaries(s, cols, col_rows, vector<string>(), NULL));
     }
     vector<ssb_column> rk, lk;
     for (size_t k = 0; k < rhs_keys_.size(); ++k) rk.push_back(rhs_table_.columns[rhs_keys_[k]].col);
@@ -1531,10 +1718,6 @@ FailureOrOwned<Cursor> BoundAggregateClusters(const BoundSingleSourceProjector* 
   for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
     keys.push_back(proj->source_attribute_position(i));
     result.add_attribute(proj->result_schema().attribute(i));
-    const DataType t = proj->result_schema().attribute(i).type();
-    if (t == STRING || t == BINARY) {
-      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length clustering keys are not on the B200 hot path (SURVEY 8f)"));
-    }
   }
   for (int i = 0; i < agg->schema().attribute_count(); ++i) {
     if (!result.add_attribute(agg->schema().attribute(i))) {
@@ -1655,10 +1838,6 @@ FailureOrOwned<Cursor> BoundGroupAggregate(const BoundSingleSourceProjector* gro
   for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
     keys.push_back(proj->source_attribute_position(i));
     result.add_attribute(proj->result_schema().attribute(i));
-    const DataType t = proj->result_schema().attribute(i).type();
-    if (t == STRING || t == BINARY) {
-      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length group keys are not on the B200 hot path (SURVEY 8f)"));
-    }
   }
   for (int i = 0; i < agg->schema().attribute_count(); ++i) {
     if (!result.add_attribute(agg->schema().attribute(i))) {
@@ -1765,8 +1944,8 @@ FailureOrOwned<Cursor> BoundExtendedSort(const ExtendedSortSpecification* sort_s
       THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "No attribute '" + name + "' in schema (" + cs.GetHumanReadableSpecification() + ")"));
     }
     const DataType t = cs.attribute(pos).type();
-    if (t == STRING || t == BINARY) {
-      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length sort keys are not on the B200 hot path (SURVEY 8f)"));
+    if (t == STRING && !spec->keys(i).case_sensitive()) {   // sort.cc:886-931 sorts by an upper-cased copy of the key
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "case-insensitive STRING sort keys are not on the B200 hot path (SURVEY 8f)"));
     }
     keys.push_back(std::make_pair(pos, spec->keys(i).column_order()));
   }
@@ -1828,10 +2007,6 @@ FailureOrVoid SortOrder::Bind(const TupleSchema& schema, vector<std::pair<int, C
         THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Duplicate attribute name '" + name + "' in result schema"));
       }
       seen.push_back(name);
-      const DataType t = p->result_schema().attribute(c).type();
-      if (t == STRING || t == BINARY) {
-        THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length sort keys are not on the B200 hot path (SURVEY 8f)"));
-      }
       keys->push_back(std::make_pair(p->source_attribute_position(c), keys_[i].second));
     }
   }
@@ -1873,10 +2048,6 @@ FailureOrOwned<Cursor> HashJoinOperation::CreateCursor() const {
   }
   vector<int> lkeys, rkeys;
   for (int i = 0; i < lk->result_schema().attribute_count(); ++i) {
-    const DataType t = lk->result_schema().attribute(i).type();
-    if (t == STRING || t == BINARY) {
-      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "variable-length join keys are not on the B200 hot path (SURVEY 8f)"));
-    }
     lkeys.push_back(lk->source_attribute_position(i));
     rkeys.push_back(rk->source_attribute_position(i));
   }

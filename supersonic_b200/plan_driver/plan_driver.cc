@@ -134,6 +134,8 @@ DataType ParseType(const std::string& t) {
   if (t == "BOOL") return BOOL;
   if (t == "DATE") return DATE;
   if (t == "DATETIME") return DATETIME;
+  if (t == "STRING") return STRING;
+  if (t == "BINARY") return BINARY;
   throw ParseError{"unknown type '" + t + "'"};
 }
 
@@ -197,6 +199,8 @@ const Expression* BuildExpr(const Sx& s) {
   if (h == "bool") { Arity(s, 1); return ConstBool(Atom(s.kids[1]) == "true" || Atom(s.kids[1]) == "1"); }
   if (h == "date") { Arity(s, 1); return ConstDate(static_cast<int32>(strtoll(Atom(s.kids[1]).c_str(), NULL, 0))); }
   if (h == "datetime") { Arity(s, 1); return ConstDateTime(strtoll(Atom(s.kids[1]).c_str(), NULL, 0)); }
+  if (h == "str") { Arity(s, 1); return ConstString(Atom(s.kids[1])); }
+  if (h == "bin") { Arity(s, 1); return ConstBinary(Atom(s.kids[1])); }
   if (h == "null") { Arity(s, 1); return Null(ParseType(Atom(s.kids[1]))); }
   if (h == "sequence") { Arity(s, 0); return Sequence(); }
   if (h == "cast") { Arity(s, 2); return CastTo(ParseType(Atom(s.kids[1])), BuildExpr(s.kids[2])); }
@@ -560,7 +564,9 @@ struct ssplan_result {
     int nullable;
     size_t width;
     bool saw_nulls;
+    bool varlen;               // STRING / BINARY: `data` holds one int64 length per row, `bytes` the cells end to end
     std::vector<char> data;
+    std::vector<char> bytes;
     std::vector<uint8_t> is_null;
   };
   std::vector<Col> cols;
@@ -580,10 +586,7 @@ void DescribeColumns(ssplan_result* r, const TupleSchema& schema) {
     r->cols[c].nullable = a.is_nullable() ? 1 : 0;
     r->cols[c].width = GetTypeInfo(a.type()).size();
     r->cols[c].saw_nulls = false;
-    if (a.type() == STRING || a.type() == BINARY) {
-      r->code = ERROR_NOT_IMPLEMENTED;
-      r->error = "plan driver returns fixed-width columns only";
-    }
+    r->cols[c].varlen = a.type() == STRING || a.type() == BINARY;
   }
 }
 
@@ -593,8 +596,18 @@ void AppendView(ssplan_result* r, const View& v, int32_t flags) {
     for (size_t c = 0; c < r->cols.size(); ++c) {
       ssplan_result::Col& col = r->cols[c];
       const char* src = static_cast<const char*>(v.column(c).data().raw());
-      col.data.insert(col.data.end(), src, src + n * col.width);
       const bool* nulls = v.column(c).is_null();
+      if (col.varlen) {   // deep copy: the cells point into memory the cursor may reuse
+        const StringPiece* cells = reinterpret_cast<const StringPiece*>(src);
+        for (size_t i = 0; i < n; ++i) {
+          const int64_t len = (nulls != NULL && nulls[i]) ? 0 : static_cast<int64_t>(cells[i].size());
+          const char* lp = reinterpret_cast<const char*>(&len);
+          col.data.insert(col.data.end(), lp, lp + sizeof(len));
+          if (len > 0) col.bytes.insert(col.bytes.end(), cells[i].data(), cells[i].data() + len);
+        }
+      } else {
+        col.data.insert(col.data.end(), src, src + n * col.width);
+      }
       if (nulls != NULL) {
         if (!col.saw_nulls) {
           col.is_null.assign(r->rows, 0);
@@ -752,6 +765,7 @@ const char* ssplan_result_col_name(const ssplan_result* r, int32_t i) { return r
 int32_t ssplan_result_col_dtype(const ssplan_result* r, int32_t i) { return r->cols[i].dtype; }
 int32_t ssplan_result_col_nullable(const ssplan_result* r, int32_t i) { return r->cols[i].nullable; }
 const void* ssplan_result_col_data(const ssplan_result* r, int32_t i) { return r->cols[i].data.data(); }
+const char* ssplan_result_col_bytes(const ssplan_result* r, int32_t i) { return r->cols[i].bytes.data(); }
 const uint8_t* ssplan_result_col_is_null(const ssplan_result* r, int32_t i) {
   return r->cols[i].saw_nulls ? r->cols[i].is_null.data() : NULL;
 }

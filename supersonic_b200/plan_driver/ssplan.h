@@ -26,7 +26,8 @@ typedef struct {
   const char* name;
   int32_t dtype;
   int32_t nullable;          /* 0 = NOT_NULLABLE, 1 = NULLABLE */
-  const void* data;          /* host (or, for the B200 build, device) pointer */
+  const void* data;          /* host (or, for the B200 build, device) pointer; STRING / BINARY: an array of
+                                { const char* ptr; int64 length; } cells (the layout of StringPiece) */
   const uint8_t* is_null;    /* bool per row, or NULL = no nulls in this view */
 } ssplan_column;
 
@@ -57,7 +58,10 @@ int64_t ssplan_result_rows(const ssplan_result* r);
 const char* ssplan_result_col_name(const ssplan_result* r, int32_t i);
 int32_t ssplan_result_col_dtype(const ssplan_result* r, int32_t i);
 int32_t ssplan_result_col_nullable(const ssplan_result* r, int32_t i);
+/* Fixed-width columns: the values. STRING / BINARY columns: one int64 length per row (0 for NULL rows); the cells
+ * themselves lie end to end in ssplan_result_col_bytes. */
 const void* ssplan_result_col_data(const ssplan_result* r, int32_t i);
+const char* ssplan_result_col_bytes(const ssplan_result* r, int32_t i);
 /* bool per row; NULL when the column never reported an is_null vector. */
 const uint8_t* ssplan_result_col_is_null(const ssplan_result* r, int32_t i);
 /* seconds spent in CreateCursor() and in the Next() drain loop (wall clock). */

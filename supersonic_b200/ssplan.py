@@ -13,6 +13,8 @@ import numpy as np
 
 # supersonic::DataType numbers (supersonic/proto/supersonic.proto:15-37)
 INT32, INT64, UINT64, DATETIME, DOUBLE, BOOL, UINT32, FLOAT, DATE, ENUM = 1, 2, 3, 4, 5, 6, 8, 9, 10, 13
+STRING, BINARY = 0, 7
+VARLEN = (STRING, BINARY)
 
 NP_OF = {
     INT32: np.int32, INT64: np.int64, UINT32: np.uint32, UINT64: np.uint64,
@@ -20,7 +22,8 @@ NP_OF = {
     DATETIME: np.int64, ENUM: np.int32,
 }
 NAME_OF = {INT32: "INT32", INT64: "INT64", UINT32: "UINT32", UINT64: "UINT64", FLOAT: "FLOAT",
-           DOUBLE: "DOUBLE", BOOL: "BOOL", DATE: "DATE", DATETIME: "DATETIME", ENUM: "ENUM"}
+           DOUBLE: "DOUBLE", BOOL: "BOOL", DATE: "DATE", DATETIME: "DATETIME", ENUM: "ENUM", STRING: "STRING",
+           BINARY: "BINARY"}
 DTYPE_OF_NAME = {v: k for k, v in NAME_OF.items()}
 
 SSPLAN_DISCARD = 1
@@ -47,7 +50,19 @@ class Column(object):
     def __init__(self, name, dtype, data, is_null=None, nullable=None):
         self.name = name
         self.dtype = dtype
-        self.data = np.ascontiguousarray(data, dtype=NP_OF[dtype])
+        if dtype in VARLEN:
+            # STRING / BINARY: python str / bytes values -> StringPiece cells { const char* ptr; int64 length }
+            # pointing into one bytes buffer (kept alive by this object)
+            self.values = [v.encode() if isinstance(v, str) else bytes(v) for v in data]
+            self._buf = np.frombuffer(b"".join(self.values) + b"\0", dtype=np.uint8).copy()
+            lens = np.array([len(v) for v in self.values], dtype=np.int64)
+            cells = np.zeros((len(self.values), 2), dtype=np.int64)
+            if len(self.values):
+                cells[:, 0] = self._buf.ctypes.data + np.concatenate(([0], np.cumsum(lens)[:-1]))
+                cells[:, 1] = lens
+            self.data = cells
+        else:
+            self.data = np.ascontiguousarray(data, dtype=NP_OF[dtype])
         self.is_null = None if is_null is None else np.ascontiguousarray(is_null, dtype=np.bool_)
         self.nullable = (is_null is not None) if nullable is None else nullable
 
@@ -87,6 +102,7 @@ class PlanLib(object):
                           ("col_is_null", C.c_void_p)]:
             f = getattr(L, "ssplan_result_" + name)
             f.restype, f.argtypes = res, [C.c_void_p, C.c_int32]
+        L.ssplan_result_col_bytes.restype, L.ssplan_result_col_bytes.argtypes = C.c_void_p, [C.c_void_p, C.c_int32]
         L.ssplan_result_free.restype, L.ssplan_result_free.argtypes = None, [C.c_void_p]
         L.ssplan_impl.restype = C.c_char_p
 
@@ -128,6 +144,25 @@ class PlanLib(object):
                 if code != 0 or (flags & (SSPLAN_DISCARD | SSPLAN_BIND_ONLY)):
                     columns.append(None)
                     nulls.append(None)
+                    continue
+                if dt in VARLEN:
+                    cells = np.empty(rows, dtype=object)
+                    if rows:
+                        lens = np.frombuffer((C.c_char * (rows * 8)).from_address(L.ssplan_result_col_data(out, i)),
+                                             dtype=np.int64, count=rows)
+                        total = int(lens.sum())
+                        raw = C.string_at(L.ssplan_result_col_bytes(out, i), total) if total else b""
+                        at = 0
+                        for k in range(rows):
+                            cells[k] = raw[at:at + int(lens[k])]
+                            at += int(lens[k])
+                    columns.append(cells)
+                    q = L.ssplan_result_col_is_null(out, i)
+                    if q and rows:
+                        nb = (C.c_char * rows).from_address(q)
+                        nulls.append(np.frombuffer(nb, dtype=np.uint8, count=rows).astype(np.bool_))
+                    else:
+                        nulls.append(None)
                     continue
                 npdt = np.dtype(NP_OF[dt])
                 p = L.ssplan_result_col_data(out, i)

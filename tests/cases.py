@@ -265,6 +265,72 @@ GOLDEN_LATE = [
      {"k": [0.5, -1.0, 0.5], "mx": [9, 4, 1], "l": [9, 4, 1]}, True),
 ]
 
+# STRING / BINARY columns: known-answer vectors of the reference's tests with their own STRING cells.
+S = sp.STRING
+GOLDEN_STRINGS = [
+    # cursor/core/aggregate_groups_test.cc:379-401 (GroupByTwoColumns)
+    ("str_group_two_columns", "(group (named col0 col1) (aggs (SUM col2 sum)) (scan 0))",
+     [[col("col0", S, ["foo", "bar", "foo", "bar"]), col("col1", sp.INT32, [1, 2, 1, 3]), col("col2", sp.INT32, [3, -3, 4, -5])]],
+     {"col0": ["foo", "bar", "bar"], "col1": [1, 2, 3], "sum": [7, -3, -5]}, False),
+    # cursor/core/sort_test.cc:189-211 (OneStringColumnWithDuplicatesAndNulls)
+    ("str_sort_duplicates_and_nulls", "(sort (order (col0 ASC)) (all) (scan 0))",
+     [[ncol("col0", S, ["a", "c", "a", N, "d", N, "e"])]],
+     {"col0": [N, N, "a", "a", "c", "d", "e"]}, True),
+    # :213-237 (OneIntegerColumnMostlyNullsDescending): a STRING payload follows the permutation
+    ("str_sort_payload", "(sort (order (col0 DESC)) (all) (scan 0))",
+     [[ncol("col0", sp.INT32, [N, N, N, 7, N, N, N]), col("col1", S, ["a", "a", "a", "g", "a", "a", "a"])]],
+     {"col0": [7, N, N, N, N, N, N], "col1": ["g", "a", "a", "a", "a", "a", "a"]}, True),
+    # cursor/core/hash_join_test.cc:60-160: (INT64, STRING) rows joined on the STRING column, both key kinds
+    ("str_join_inner_unique",
+     "(hash_join INNER (named col1) (named col1) (multi (0 (rename (col0 L.col0) (col1 L.col1))) (1 (rename (col0 R.col0) (col1 R.col1)))) UNIQUE (scan 0) (scan 1))",
+     [[col("col0", sp.INT64, [1, 2, 3, 4, 5]), col("col1", S, ["a", "b", "c", "d", "e"])],
+      [col("col0", sp.INT64, [6, 5, 4, 3, 2, 1]), col("col1", S, ["f", "e", "d", "c", "b", "a"])]],
+     {"L.col0": [1, 2, 3, 4, 5], "L.col1": ["a", "b", "c", "d", "e"], "R.col0": [1, 2, 3, 4, 5], "R.col1": ["a", "b", "c", "d", "e"]}, True),
+    ("str_join_not_unique_2b2b2c",
+     "(hash_join INNER (named col0) (named col0) (multi (0 (rename (col0 L.col0) (col1 L.col1))) (1 (rename (col0 R.col0) (col1 R.col1)))) NOT_UNIQUE (scan 0) (scan 0))",
+     [[col("col0", sp.INT64, [2, 2, 2]), col("col1", S, ["b", "b", "c"])]],
+     {"L.col0": [2] * 9, "L.col1": ["b", "b", "b", "b", "b", "b", "c", "c", "c"], "R.col0": [2] * 9,
+      "R.col1": ["b", "b", "c", "b", "b", "c", "b", "b", "c"]}, True),
+    # NULL STRING keys never match (builder_1a1NNaNN_), LEFT_OUTER keeps the lhs rows
+    ("str_join_left_outer_null_keys",
+     "(hash_join LEFT_OUTER (named col1) (named col1) (multi (0 (rename (col0 L.col0) (col1 L.col1))) (1 (rename (col0 R.col0)))) NOT_UNIQUE (scan 0) (scan 0))",
+     [[ncol("col0", sp.INT64, [1, 1, N, N]), ncol("col1", S, ["a", N, "a", N])]],
+     {"L.col0": [1, 1, 1, N, N, N], "L.col1": ["a", "a", N, "a", "a", N], "R.col0": [1, N, N, 1, N, N]}, True),
+    # cursor/core/aggregate_clusters_test.cc:150-178 with its own STRING columns
+    ("str_aggregate_clusters_three_keys",
+     "(aggregate_clusters (rename (col0 A) (col1 B) (col2 C)) (aggs (SUM col1 sum1) (SUM col3 sum3)) (scan 0))",
+     [[col("col0", S, ["a"] * 8), col("col1", sp.INT32, [0, 2, 2, 2, 2, 1, 1, 1]),
+       col("col2", S, ["a", "a", "a", "b", "b", "b", "b", "bbbbbbbb"]), col("col3", sp.INT32, [13, 4, 5, -4, -6, 3, 4, -3])]],
+     {"A": ["a"] * 5, "B": [0, 2, 2, 1, 1], "C": ["a", "a", "b", "b", "bbbbbbbb"], "sum1": [0, 4, 4, 2, 1], "sum3": [13, 9, -10, 7, -3]}, True),
+    # cursor/core/merge_union_all_test.cc:131-140 with its own STRING column
+    ("str_merge_union_all", "(merge_union_all (order (col0 ASC) (col1 ASC)) (scan 0) (scan 1))",
+     [[col("col0", S, ["a", "a", "b", "b"]), col("col1", sp.INT32, [1, 2, 1, 2])],
+      [col("col0", S, ["a", "a", "b", "b"]), col("col1", sp.INT32, [1, 3, 2, 2])]],
+     {"col0": ["a", "a", "a", "a", "b", "b", "b", "b"], "col1": [1, 1, 2, 3, 1, 2, 2, 2]}, True),
+    # expression/core/comparison_expressions_test.cc: STRING comparisons (memcmp order, the shorter one first), NULL operands
+    ("str_compare_literal", "(compute (compound (as eq (equal (col s) (str \"bob\"))) (as lt (less (col s) (str \"bob\"))) "
+                            "(as ge (greater_or_equal (col s) (str \"bo\"))) (as ne (not_equal (col s) (str \"\")))) (scan 0))",
+     [[ncol("s", S, ["bob", "alice", "", N, "bo", "bobby", "Bob"])]],
+     {"eq": [True, False, False, N, False, False, False], "lt": [False, True, True, N, True, False, True],
+      "ge": [True, False, False, N, True, True, False], "ne": [True, True, False, N, True, True, True]}, True),
+    ("str_compare_columns", "(filter (less_or_equal (col a) (col b)) (all) (scan 0))",
+     [[col("a", S, ["x", "abc", "ab", "b", ""]), ncol("b", S, ["x", "ab", "abc", N, "a"]), col("v", sp.INT32, [1, 2, 3, 4, 5])]],
+     {"a": ["x", "ab", ""], "b": ["x", "abc", "a"], "v": [1, 3, 5]}, True),
+    # MIN / MAX / FIRST / LAST / COUNT over a STRING column (column_aggregator.cc:108-166,314-377); all-NULL group -> NULL
+    ("str_aggregates", "(group (named k) (aggs (MIN s mn) (MAX s mx) (FIRST s f) (LAST s l) (COUNT s c)) (scan 0))",
+     [[col("k", sp.INT32, [1, 2, 1, 2, 1, 3]), ncol("s", S, ["pear", "fig", "apple", N, "plum", N])]],
+     {"k": [1, 2, 3], "mn": ["apple", "fig", N], "mx": ["plum", "fig", N], "f": ["pear", "fig", N], "l": ["plum", "fig", N], "c": [3, 1, 0]}, False),
+    ("str_scalar_aggregate", "(scalar_agg (aggs (MIN s mn) (MAX s mx) (COUNT \"\" n)) (scan 0))",
+     [[col("s", S, ["pear", "fig", "apple", "plum"])]], {"mn": ["apple"], "mx": ["plum"], "n": [4]}, True),
+    # BINARY cells may hold zero bytes: "ab" < "ab\0" < "ab\0\0" < "ab\1"; cells longer than one 8-byte ranking round
+    ("bin_sort_embedded_zero", "(sort (order (b ASC)) (all) (scan 0))",
+     [[col("b", sp.BINARY, [b"ab\x01", b"ab\x00\x00", b"ab", b"ab\x00", b"0123456789abcdefX", b"0123456789abcdef", b"0123456789abcdeg"])]],
+     {"b": [b"0123456789abcdef", b"0123456789abcdefX", b"0123456789abcdeg", b"ab", b"ab\x00", b"ab\x00\x00", b"ab\x01"]}, True),
+    ("str_is_null_and_project", "(filter (not (is_null (col s))) (named s) (compute (compound (col s) (as n (plus (col v) (i32 1)))) (scan 0)))",
+     [[ncol("s", S, ["q", N, "w"]), col("v", sp.INT32, [1, 2, 3])]], {"s": ["q", "w"]}, True),
+    ("str_empty_table", "(group (named s) (aggs (COUNT \"\" n)) (scan 0))", [[col("s", S, [])]], {"s": [], "n": []}, True),
+]
+
 
 def check_result(r, expected, ordered):
     """Compares a PlanResult with {name: list}; NULL cells compare by is_null only
@@ -278,7 +344,8 @@ def check_result(r, expected, ordered):
         g, w = [], []
         for j, name in enumerate(r.names):
             isn = bool(r.nulls[j][i]) if r.nulls[j] is not None else False
-            v = r.columns[j][i].item()
+            v = r.columns[j][i]
+            v = v.item() if hasattr(v, "item") else v
             g.append(("null",) if isn else ("v", _norm(v)))
             e = expected[name][i]
             w.append(("null",) if e is None else ("v", _norm(e)))
@@ -297,6 +364,8 @@ def _norm(v):
         return float(v)
     if isinstance(v, bool):
         return bool(v)
+    if isinstance(v, str):
+        return v.encode()      # STRING / BINARY cells compare as bytes
     return v
 
 
@@ -317,6 +386,9 @@ def same_results(a, b, ordered=True, sort_cols=None):
         va, na = ca[j]
         vb, nb = cb[j]
         assert np.array_equal(na, nb), "null vectors differ in column %s" % a.names[j]
+        if va.dtype == object:
+            assert list(va) == list(vb), "column %s differs: %s vs %s" % (a.names[j], va[:8], vb[:8])
+            continue
         assert np.array_equal(va.view(np.uint8), vb.view(np.uint8)), \
             "column %s differs: %s vs %s" % (a.names[j], va[:8], vb[:8])
 
@@ -328,6 +400,10 @@ def _masked(r):
         n = r.nulls[j] if r.nulls[j] is not None else np.zeros(r.rows, dtype=np.bool_)
         if v.dtype == np.bool_:
             v = v.astype(np.uint8)
+        if v.dtype == object:
+            v[n] = b""
+            out.append((v, n))
+            continue
         v[n] = 0
         if v.dtype.kind == "f":
             v = v + 0.0   # canonical zero sign is not touched; NaN payloads are kept bit-exact
@@ -340,6 +416,10 @@ def _sorted(cols, sort_cols):
     idx = list(range(len(cols))) if sort_cols is None else sort_cols
     for j in reversed(idx):
         v, n = cols[j]
+        if v.dtype == object:   # STRING / BINARY: dense ranks of the cells
+            keys.append(np.unique(np.array([bytes(x) for x in v], dtype=object), return_inverse=True)[1].astype(np.int64))
+            keys.append(n)
+            continue
         keys.append(v.view(np.uint64) if v.dtype.itemsize == 8 else v.astype(np.int64))
         keys.append(n)
     order = np.lexsort(keys)

@@ -2,9 +2,9 @@
 known-answer vectors of the reference's own tests. CPU only."""
 import pytest
 
-from cases import GOLDEN, GOLDEN_LATE, check_result
+from cases import GOLDEN, GOLDEN_LATE, GOLDEN_STRINGS, check_result
 
-ALL_GOLDEN = GOLDEN + GOLDEN_LATE
+ALL_GOLDEN = GOLDEN + GOLDEN_LATE + GOLDEN_STRINGS
 
 
 @pytest.mark.parametrize("case", ALL_GOLDEN, ids=[c[0] for c in ALL_GOLDEN])

@@ -335,7 +335,7 @@ def q1_aux(capi, ctx, rank, world, rows, dist, torch, comm=None):
             "exchange": "ssb_shard_group_merge over the 6-group partial tables" if world > 1 else "none"}
 
 
-def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
+def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch, comm=None):
     """BASELINE config 4 shape, row-range sharded: HashJoin(INNER, fk = pk, UNIQUE) with the build
     side a permutation of [0, B) (B = world x build_rows), probe keys uniform over the build keys,
     result {fk, lv, payload}. One rank: ssb_join_build + ssb_join_probe + gathers. Several ranks:
@@ -387,15 +387,33 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
                                                   [(tens["pk"], I64)], [(tens["pay"], I64)], join_type=0, uniqueness=1)
                 state["pairs"] = int(rows_.numel())
             return once_
-        # the other two forms, timed for the record: probe rows redistributed (hash partition + three all-to-alls),
-        # and the whole build side all-gathered with the whole table built on every rank ...
+        # the Python-orchestrated forms, timed for the record: probe rows redistributed (hash partition + three
+        # all-to-alls), the whole build side all-gathered with the whole table built on every rank, and the
+        # replicated form over torch.distributed
         a2a_best, _ = _timed(ctx, world, dist, torch, run_with("all_to_all"), repeats=1)
         state["all_to_all_seconds"] = a2a_best
         bc_best, _ = _timed(ctx, world, dist, torch, run_with("broadcast"), repeats=1)
         state["broadcast_seconds"] = bc_best
-        # ... and the form "auto" picks for this shape (UNIQUE single-column key, small build side): every rank
-        # builds the table of one hash part, the tables are all-gathered, no probe row moves
-        once = run_with("auto")
+        rp_best, _ = _timed(ctx, world, dist, torch, run_with("auto"), repeats=1)
+        state["python_replicate_seconds"] = rp_best
+        # ... and the same strategy behind the C ABI (ssb_shard_join_*: partition, ONE grouped NCCL exchange of key +
+        # payload, per-part compact tables, all-gather of tables + payload, local probe; no probe row moves)
+        o_fk, o_lv, o_pay = (torch.empty(probe_rows, dtype=torch.int64, device="cuda") for _ in range(3))
+
+        def once():
+            j = C.c_void_p()
+            ctx.check(lib.ssb_shard_join_build(comm.h, _cols(capi, [(ptrs["pk"], None, I64)]), 1,
+                                               _cols(capi, [(ptrs["pay"], None, I64)]), build_rows, C.byref(j)))
+            n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+            ctx.check(lib.ssb_shard_join_probe(j, _cols(capi, [(ptrs["fk"], None, I64)]), probe_rows, 0, C.byref(n), C.byref(pl), C.byref(pr)))
+            assert n.value <= probe_rows
+            pay_all = capi.Column()
+            ctx.check(lib.ssb_shard_join_payload(j, 0, C.byref(pay_all), None))
+            for src, idx, dst in [(ptrs["fk"], pl, o_fk.data_ptr()), (ptrs["lv"], pl, o_lv.data_ptr()), (pay_all.data, pr, o_pay.data_ptr())]:
+                ctx.check(lib.ssb_gather(ctx.h, _cols(capi, [(src, None, I64)]), idx, n.value, _cols(capi, [(dst, None, I64)])))
+            ctx.sync()
+            state["pairs"] = n.value
+            lib.ssb_shard_join_destroy(j)
     best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
     pairs = state["pairs"]
     if world > 1:
@@ -413,10 +431,11 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch):
             "value": world * probe_rows / best, "unit": "rows/s", "probe_rows_per_gpu": probe_rows,
             "build_rows_per_gpu": build_rows, "pairs": pairs, "seconds": best,
             "algorithmic_gbs_per_gpu": alg / best / 1e9, "check": "pairs == probe rows (every fk has one pk)",
-            "exchange": ("auto -> replicate: build rows to the owner of their key's hash part (all-to-all), one table per "
-                         "rank, all-gather of the tables + payload, local probe of the key's part; for the record: "
-                         "all-to-all form %.4f s, broadcast form (whole table built on every rank) %.4f s"
-                         % (state["all_to_all_seconds"], state["broadcast_seconds"]))
+            "exchange": ("ssb_shard_join_* (C ABI, NCCL inside libssb200.so): build rows to the owner of their key's hash part "
+                         "(one grouped send/recv), one compact table per rank, all-gather of the tables + payload, local probe "
+                         "of the key's part; for the record, orchestrated from Python over torch.distributed: all-to-all form "
+                         "%.4f s, broadcast form (whole table built on every rank) %.4f s, replicated form %.4f s"
+                         % (state["all_to_all_seconds"], state["broadcast_seconds"], state["python_replicate_seconds"]))
             if world > 1 else "none"}
 
 
@@ -584,7 +603,7 @@ def run_b200(args):
     aux_group = group_by_aux(capi, ctx, rank, world, min(rows, args.group_rows), dist, torch, comm)
     aux_q1 = q1_aux(capi, ctx, rank, world, min(rows, args.q1_rows), dist, torch, comm)
     aux_join = hash_join_aux(capi, ctx, rank, world, min(rows, args.join_probe_rows),
-                             max(1, min(rows, args.join_probe_rows) // 10), dist, torch)
+                             max(1, min(rows, args.join_probe_rows) // 10), dist, torch, comm)
     aux_sort = sort_aux(capi, ctx, rank, world, min(rows, args.sort_rows), dist, torch)
     if comm is not None:
         comm.close()

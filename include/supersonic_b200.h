@@ -298,8 +298,9 @@ int ssb_join_attach_parts(ssb_ctx* ctx, int32_t key_type, int32_t n_parts, const
  * has no counterpart: cursor/core/hash_join.cc runs on one thread). part(row) = high bits of
  * the join key hash scaled to [0, n_parts); integer keys of different widths hash alike, so the
  * two sides of a join agree. Rows with a NULL key column never match (hash_join.cc:67-76) and
- * are assigned to `null_part`. d_perm[rows] receives the row ids grouped by part, ascending
- * inside each part; h_counts[n_parts] (HOST memory) the rows per part. Synchronises. */
+ * are assigned to `null_part`; null_part == n_parts sets them aside in an extra part behind the hash
+ * parts (h_counts then has n_parts + 1 entries). d_perm[rows] receives the row ids grouped by part,
+ * ascending inside each part; h_counts[n_parts] (HOST memory) the rows per part. Synchronises. */
 int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows,
                        int32_t n_parts, int32_t null_part, int64_t* d_perm, int64_t* h_counts);
 
@@ -368,6 +369,22 @@ int ssb_comm_exchange_counts(ssb_comm* comm, const int64_t* h_send, int64_t* h_r
  * from ranks 0..size-1 land consecutively in recv[i] (recv_rows[r] elements each). Asynchronous. */
 int ssb_comm_all_to_all(ssb_comm* comm, int32_t n_cols, const void* const* send, void* const* recv,
                         const int32_t* width, const int64_t* send_rows, const int64_t* recv_rows);
+
+/* HashJoin over row-range shards with UNIQUE single-column keys (hash_join.cc:406-517,707-831 keep one index over
+ * the whole rhs): the build rows are hash-partitioned and exchanged (one grouped send/recv for key + payload
+ * columns), every rank builds the table of one hash part, tables and payload columns are all-gathered, and the
+ * local lhs shard probes them in place -- no probe row moves, pairs come out in lhs order (hash_join.cc:793-831).
+ * Collective: every rank of `comm` calls build with its shard of the rhs (key: any fixed-width type, may be
+ * nullable -- rows with a NULL key never match; payload: NOT NULL fixed-width columns). probe = ssb_join_probe on
+ * the local lhs shard; d_rhs_rows index the gathered payload columns (ssb_shard_join_payload: `rows` = rhs rows
+ * with a key over all ranks, in (hash part, global insertion) order). */
+typedef struct ssb_shard_join ssb_shard_join;
+int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payload, const ssb_column* payload,
+                         int64_t rows, ssb_shard_join** out);
+int ssb_shard_join_probe(ssb_shard_join* j, const ssb_column* key, int64_t rows, int32_t join_type, int64_t* n_pairs,
+                         const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
+int ssb_shard_join_payload(const ssb_shard_join* j, int32_t i, ssb_column* out, int64_t* rows);
+void ssb_shard_join_destroy(ssb_shard_join* j);
 
 /* The exchange step of a row-range sharded GroupAggregate / ScalarAggregate ("a reduce for global aggregates"):
  * every rank has aggregated its shard into `g`. The partial groups are hash-partitioned by key over the ranks,

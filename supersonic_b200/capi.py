@@ -120,6 +120,10 @@ def load():
         "ssb_string_gather_offsets": (C.c_int, [P, P, P, I64, P, C.POINTER(I64)]),
         "ssb_string_gather_bytes": (C.c_int, [P, P, P, P, I64, P, P]),
         "ssb_string_shift_offsets": (C.c_int, [P, P, I64, I64, P]),
+        "ssb_shard_join_build": (C.c_int, [P, C.POINTER(Column), I32, C.POINTER(Column), I64, C.POINTER(P)]),
+        "ssb_shard_join_probe": (C.c_int, [P, C.POINTER(Column), I64, I32, C.POINTER(I64), C.POINTER(P), C.POINTER(P)]),
+        "ssb_shard_join_payload": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I64)]),
+        "ssb_shard_join_destroy": (None, [P]),
         "ssb_join_table": (C.c_int, [P, C.POINTER(P), C.POINTER(I64)]),
         "ssb_join_attach_parts": (C.c_int, [P, I32, I32, C.POINTER(P), C.POINTER(I64), C.POINTER(I64), C.POINTER(P)]),
         "ssb_comm_unique_id": (C.c_int, [P]),

@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(256) part_id_kernel(JoinKeys keys, long long r
     atomicAdd(&cnt[part], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < n_parts && cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(cnt[threadIdx.x]));
+  if (threadIdx.x <= n_parts && threadIdx.x < 256 && cnt[threadIdx.x]) {   // slot n_parts: NULL keys set aside (null_part == n_parts)
+    atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(cnt[threadIdx.x]));
+  }
 }
 
 }  // namespace ssb
@@ -614,10 +616,12 @@ int ssb_join_attach_parts(ssb_ctx* ctx, int32_t key_type, int32_t n_parts, const
 int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t rows, int32_t n_parts,
                        int32_t null_part, int64_t* d_perm, int64_t* h_counts) {
   if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
-  if (n_parts < 1 || n_parts > 256 || null_part < 0 || null_part >= n_parts) {
-    return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "partition: 1..256 parts, null_part inside");
+  const bool aside = null_part == n_parts;   // NULL keys form an extra part behind the hash parts
+  if (n_parts < 1 || n_parts > (aside ? 255 : 256) || null_part < 0 || null_part > n_parts) {
+    return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "partition: 1..256 parts, null_part inside (or == n_parts with at most 255 parts)");
   }
-  for (int p = 0; p < n_parts; ++p) h_counts[p] = 0;
+  const int n_counts = n_parts + (aside ? 1 : 0);
+  for (int p = 0; p < n_counts; ++p) h_counts[p] = 0;
   if (rows == 0) return 0;
   JoinKeys jk;
   if (int rc = fill_keys(ctx, n_keys, keys, &jk)) return rc;
@@ -643,7 +647,7 @@ int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int
   }
   unsigned long long h[256];
   if (rc == 0) {
-    e = cudaMemcpyAsync(h, d_counts, static_cast<size_t>(n_parts) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaMemcpyAsync(h, d_counts, static_cast<size_t>(n_counts) * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "partition");
@@ -651,7 +655,7 @@ int ssb_partition_rows(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int
   cudaStreamSynchronize(ctx->stream);
   tmp_free(ctx, k0); tmp_free(ctx, k1); tmp_free(ctx, v0); tmp_free(ctx, d_counts);
   if (rc) return rc;
-  for (int p = 0; p < n_parts; ++p) h_counts[p] = static_cast<int64_t>(h[p]);
+  for (int p = 0; p < n_counts; ++p) h_counts[p] = static_cast<int64_t>(h[p]);
   return 0;
 }
 

@@ -1,0 +1,186 @@
+// shard_join.cu -- HashJoin over row-range shards, one process per GPU, behind the C ABI.
+//
+// The reference builds ONE index over the whole rhs and streams the lhs through it on one thread
+// (cursor/core/hash_join.cc:406-517, 707-831). With both sides sharded by row range the index is split by key
+// hash instead of being rebuilt W times:
+//   1. every rank hash-partitions its build rows into W parts (ssb_partition_rows: one stable 8-bit sweep) and
+//      packs key + payload columns in part order (one gather per column);
+//   2. ONE grouped ncclSend/ncclRecv exchange moves part r of every rank to rank r (key and payload columns in
+//      the same NCCL group); rank r then owns every build row of hash part r, in global insertion order
+//      (chunks arrive in rank order, the partition is stable);
+//   3. rank r builds the table of its part (a compact table: 16-byte slots at load 0.6);
+//   4. the W tables and the received payload columns are all-gathered (a second grouped exchange), and every
+//      rank attaches them as one index (ssb_join_attach_parts): a probe hashes its key, picks the part, and
+//      walks that part's table.
+// The probe side never moves: the output is in lhs order, and for each lhs row in rhs insertion order, exactly
+// as hash_join.cc:793-831 produces it. Build work per rank is 1/W of the whole; what crosses NVLink is the
+// build side once (all-to-all) plus the tables once (all-gather) -- the right trade when the build side is the
+// small one, which is what the reference's own guidance asks of callers (hash_join.h:35-69: "the right hand
+// side is the index").
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "comm.h"
+#include "common.h"
+
+using namespace ssb;
+
+struct ssb_shard_join {
+  ssb_comm* comm;
+  ssb_ctx* ctx;
+  ssb_join* attached;                 // index over the gathered tables
+  void* tables;                       // all ranks' slot arrays, end to end
+  std::vector<void*> payload;         // all ranks' received payload columns, end to end (global rhs row order)
+  std::vector<int32_t> payload_types;
+  int64_t total_rows;                 // rhs rows with a non-NULL key, over all ranks
+};
+
+extern "C" {
+
+void ssb_shard_join_destroy(ssb_shard_join* j) {
+  if (j == nullptr) return;
+  if (j->attached) ssb_join_destroy(j->attached);
+  cudaStreamSynchronize(j->ctx->stream);
+  tmp_free(j->ctx, j->tables);
+  for (size_t i = 0; i < j->payload.size(); ++i) tmp_free(j->ctx, j->payload[i]);
+  delete j;
+}
+
+int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payload, const ssb_column* payload, int64_t rows,
+                         ssb_shard_join** out) {
+  *out = nullptr;
+  ssb_ctx* ctx = comm_ctx(comm);
+  const int W = comm_world(comm), rank = comm_rank(comm);
+  if (rows < 0 || n_payload < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row or column count");
+  if (W + 1 > 256) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "more than 255 ranks");
+  const int kw = width_of(key->dtype);
+  if (kw == 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported join key type");
+  for (int i = 0; i < n_payload; ++i) {
+    if (width_of(payload[i].dtype) == 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "unsupported payload column type");
+    if (payload[i].nulls != nullptr) {
+      return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "nullable payload columns: send the is_null vector as a BOOL payload column");
+    }
+  }
+  const int n_cols = 1 + n_payload;
+  std::vector<int32_t> width(n_cols);
+  width[0] = kw;
+  for (int i = 0; i < n_payload; ++i) width[1 + i] = width_of(payload[i].dtype);
+
+  // ---- 1. partition: parts 0..W-1 by key hash, part W = rows with a NULL key (they never match and stay behind)
+  long long* d_perm = nullptr;
+  cudaError_t e = tmp_malloc(ctx, &d_perm, static_cast<size_t>(rows) * 8 + 64);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "sharded join scratch");
+  std::vector<int64_t> part_rows(W + 1, 0), send_rows(W, 0), recv_rows(W, 0);
+  std::vector<void*> send(n_cols, nullptr), recv(n_cols, nullptr);
+  ssb_join* local = nullptr;
+  ssb_shard_join* j = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    tmp_free(ctx, d_perm);
+    for (int i = 0; i < n_cols; ++i) tmp_free(ctx, send[i]);
+    for (int i = 0; i < n_cols; ++i) tmp_free(ctx, recv[i]);
+    if (local) ssb_join_destroy(local);
+  };
+  int rc = ssb_partition_rows(ctx, 1, key, rows, W, W, reinterpret_cast<int64_t*>(d_perm), part_rows.data());
+  if (rc) { cleanup(); return rc; }
+  int64_t sent = 0;
+  for (int r = 0; r < W; ++r) { send_rows[r] = part_rows[r]; sent += part_rows[r]; }
+  // ---- 2. pack and exchange
+  for (int i = 0; i < n_cols && rc == 0; ++i) {
+    e = tmp_malloc_bytes(ctx, &send[i], static_cast<size_t>(sent) * width[i] + 64);
+    if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "sharded join send buffer"); break; }
+    ssb_column src = i == 0 ? *key : payload[i - 1];
+    src.nulls = nullptr;   // the rows that travel have a key; payload columns are NOT NULL
+    ssb_column dst = src;
+    dst.data = send[i];
+    if (sent > 0) rc = ssb_gather(ctx, &src, reinterpret_cast<const int64_t*>(d_perm), sent, &dst);
+  }
+  if (rc == 0) rc = comm_exchange_counts(comm, send_rows.data(), recv_rows.data());
+  int64_t received = 0;
+  for (int r = 0; r < W; ++r) received += recv_rows[r];
+  for (int i = 0; i < n_cols && rc == 0; ++i) {
+    e = tmp_malloc_bytes(ctx, &recv[i], static_cast<size_t>(received) * width[i] + 64);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "sharded join receive buffer");
+  }
+  if (rc == 0) rc = comm_all_to_all_v(comm, n_cols, send.data(), recv.data(), width.data(), send_rows.data(), recv_rows.data());
+  // ---- 3. the table of this rank's part
+  const void* d_slots = nullptr;
+  int64_t capacity = 0;
+  if (rc == 0) {
+    ssb_column k = *key;
+    k.data = recv[0];
+    k.nulls = nullptr;
+    rc = ssb_join_build(ctx, 1, &k, received, SSB_KEYS_UNIQUE | SSB_KEYS_COMPACT_TABLE, &local);
+  }
+  if (rc == 0) rc = ssb_join_table(local, &d_slots, &capacity);
+  // ---- 4. all-gather the tables and the payload columns
+  std::vector<int64_t> all(2 * W, 0);
+  if (rc == 0) {
+    const int64_t mine[2] = {received, capacity};
+    rc = comm_all_gather_counts(comm, mine, 2, all.data());
+  }
+  if (rc != 0) { cleanup(); return rc; }
+  std::vector<int64_t> rows_of(W), cap_of(W), row_offset(W), cap_offset(W);
+  int64_t total_rows = 0, total_cap = 0;
+  for (int r = 0; r < W; ++r) {
+    rows_of[r] = all[2 * r];
+    cap_of[r] = all[2 * r + 1];
+    row_offset[r] = total_rows;
+    cap_offset[r] = total_cap;
+    total_rows += rows_of[r];
+    total_cap += cap_of[r];
+  }
+  j = new ssb_shard_join;
+  j->comm = comm;
+  j->ctx = ctx;
+  j->attached = nullptr;
+  j->tables = nullptr;
+  j->total_rows = total_rows;
+  e = tmp_malloc_bytes(ctx, &j->tables, static_cast<size_t>(total_cap) * 16 + 64);
+  if (e != cudaSuccess) rc = cuda_fail(ctx, e, "sharded join tables");
+  if (rc == 0) {
+    const void* s1[1] = {d_slots};
+    void* r1[1] = {j->tables};
+    const int32_t w1[1] = {16};
+    rc = comm_all_gather_v(comm, 1, s1, r1, w1, cap_of.data());
+  }
+  if (rc == 0 && n_payload > 0) {
+    j->payload.assign(n_payload, nullptr);
+    j->payload_types.resize(n_payload);
+    for (int i = 0; i < n_payload && rc == 0; ++i) {
+      j->payload_types[i] = payload[i].dtype;
+      e = tmp_malloc_bytes(ctx, &j->payload[i], static_cast<size_t>(total_rows) * width[1 + i] + 64);
+      if (e != cudaSuccess) rc = cuda_fail(ctx, e, "sharded join payload");
+    }
+    if (rc == 0) rc = comm_all_gather_v(comm, n_payload, recv.data() + 1, j->payload.data(), width.data() + 1, rows_of.data());
+  }
+  if (rc == 0) {
+    std::vector<const void*> slot_ptrs(W);
+    for (int r = 0; r < W; ++r) slot_ptrs[r] = static_cast<const char*>(j->tables) + static_cast<size_t>(cap_offset[r]) * 16;
+    rc = ssb_join_attach_parts(ctx, key->dtype, W, slot_ptrs.data(), cap_of.data(), row_offset.data(), &j->attached);
+  }
+  // the exchange reads the send / receive buffers and the local table: wait for it, then let them go
+  cleanup();
+  (void)rank;
+  if (rc != 0) { ssb_shard_join_destroy(j); return rc; }
+  *out = j;
+  return 0;
+}
+
+int ssb_shard_join_probe(ssb_shard_join* j, const ssb_column* key, int64_t rows, int32_t join_type, int64_t* n_pairs,
+                         const int64_t** d_lhs_rows, const int64_t** d_rhs_rows) {
+  return ssb_join_probe(j->attached, key, rows, join_type, n_pairs, d_lhs_rows, d_rhs_rows);
+}
+
+int ssb_shard_join_payload(const ssb_shard_join* j, int32_t i, ssb_column* out, int64_t* rows) {
+  if (i < 0 || i >= static_cast<int32_t>(j->payload.size())) return fail(j->ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "no such payload column");
+  out->data = j->payload[i];
+  out->nulls = nullptr;
+  out->dtype = j->payload_types[i];
+  out->reserved = 0;
+  if (rows) *rows = j->total_rows;
+  return 0;
+}
+
+}  // extern "C"

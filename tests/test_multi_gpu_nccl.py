@@ -262,3 +262,116 @@ def test_shard_group_merge_two_gpus_matches_oracle(ref):
             for i in range(len(gv)):
                 assert np.array_equal(gn[i][og], wn[i][ow]), (name, rank, i, "null flags")
                 assert np.array_equal(gv[i][og], wv[i][ow]), (name, rank, i, "values")
+
+
+# ------------------------------------------------------------------------------------------------
+# ssb_shard_join_*: the sharded HashJoin behind the C ABI (hash partition + one grouped exchange + per-part tables
+# all-gathered inside libssb200.so; torch only carries the communicator id)
+def _shard_join_worker(rank, world, port, out, n_scale):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import ctypes as C
+        from supersonic_b200 import capi
+        from supersonic_b200.distributed import make_comm
+        ctx = capi.Context(rank)
+        comm = make_comm(ctx)
+        lib = ctx.lib
+        t = _join_tables(1, n_scale)
+        bb, be = shard_rows(len(t["pk"]), rank, world, align=1)
+        pb, pe = shard_rows(len(t["fk"]), rank, world, align=1)
+
+        def up(arr, nulls=None):
+            arr = np.ascontiguousarray(arr)
+            ptr = ctx.malloc(arr.nbytes + 256)
+            if arr.nbytes:
+                ctx.h2d(ptr, arr)
+            nptr = None
+            if nulls is not None:
+                words = np.packbits(np.concatenate([nulls.astype(np.uint8), np.zeros((-len(nulls)) % 32 + 32, np.uint8)]), bitorder="little")
+                nptr = ctx.malloc(words.nbytes + 256)
+                ctx.h2d(nptr, words)
+            return ptr, nptr
+
+        def cols(specs):
+            arr = (capi.Column * max(1, len(specs)))()
+            for i, (ptr, nptr, dt) in enumerate(specs):
+                arr[i].data, arr[i].nulls, arr[i].dtype = ptr, nptr, dt
+            return arr
+        res = {}
+        for with_nulls in (False, True):
+            pk = up(t["pk"][bb:be], t["pk_null"][bb:be] if with_nulls else None)
+            pay, w = up(t["payload"][bb:be]), up(t["w"][bb:be])
+            fk = up(t["fk"][pb:pe], t["fk_null"][pb:pe] if with_nulls else None)
+            j = C.c_void_p()
+            ctx.check(lib.ssb_shard_join_build(comm.h, cols([(pk[0], pk[1], capi.INT64)]), 2,
+                                               cols([(pay[0], None, capi.INT64), (w[0], None, capi.DOUBLE)]), be - bb, C.byref(j)))
+            for jt in (0, 1):
+                n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+                ctx.check(lib.ssb_shard_join_probe(j, cols([(fk[0], fk[1], capi.INT64)]), pe - pb, jt, C.byref(n), C.byref(pl), C.byref(pr)))
+                li = np.empty(n.value, dtype=np.int64)
+                ri = np.empty(n.value, dtype=np.int64)
+                if n.value:
+                    ctx.d2h(li, pl)
+                    ctx.d2h(ri, pr)
+                outs = []
+                for i, npdt in enumerate((np.int64, np.float64)):
+                    c = capi.Column()
+                    total = C.c_int64()
+                    ctx.check(lib.ssb_shard_join_payload(j, i, C.byref(c), C.byref(total)))
+                    whole = np.empty(total.value, dtype=npdt)
+                    if total.value:
+                        ctx.d2h(whole, c.data)
+                    outs.append(np.where(ri >= 0, whole[np.maximum(ri, 0)], 0))
+                res[(with_nulls, jt)] = (li + pb, ri < 0, outs)
+            lib.ssb_shard_join_destroy(j)
+        launches = ctx.launches()
+        comm.close()
+        out.put((rank, res, launches))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_scale", [1, 60])
+def test_c_abi_sharded_join_two_gpus_matches_oracle(ref, n_scale):
+    """ssb_shard_join_build / _probe / _payload over two ranks against the oracle's HashJoin over the whole tables:
+    pairs in lhs order, payload values bit-exact, NULL keys on both sides never match."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from supersonic_b200 import ssplan as sp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_join_worker, args=(r, 2, port, out, n_scale)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in procs:
+        rank, res, launches = out.get(timeout=600)
+        assert launches > 0
+        got[rank] = res
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    t = _join_tables(1, n_scale)
+    for with_nulls in (False, True):
+        build = [sp.Column("pk", sp.INT64, t["pk"], is_null=t["pk_null"].astype(bool) if with_nulls else None),
+                 sp.Column("payload", sp.INT64, t["payload"]), sp.Column("w", sp.DOUBLE, t["w"])]
+        probe = [sp.Column("fk", sp.INT64, t["fk"], is_null=t["fk_null"].astype(bool) if with_nulls else None),
+                 sp.Column("lv", sp.INT64, t["lv"])]
+        for jt in (0, 1):
+            plan = ("(hash_join %s (named fk) (named pk) (multi (0 (named lv)) (1 (named payload w))) UNIQUE (scan 0) (scan 1))"
+                    % ["INNER", "LEFT_OUTER"][jt])
+            want = ref.run(plan, [probe, build])
+            assert want.code == 0, want.error
+            li = np.concatenate([got[r][(with_nulls, jt)][0] for r in range(2)])
+            miss = np.concatenate([got[r][(with_nulls, jt)][1] for r in range(2)])
+            pay = np.concatenate([got[r][(with_nulls, jt)][2][0] for r in range(2)])
+            w = np.concatenate([got[r][(with_nulls, jt)][2][1] for r in range(2)])
+            assert len(li) == want.rows, (with_nulls, jt, len(li), want.rows)
+            assert np.array_equal(t["lv"][li], want.columns[0])
+            wn = want.nulls[1] if want.nulls[1] is not None else np.zeros(want.rows, bool)
+            assert np.array_equal(miss, wn)
+            assert np.array_equal(pay[~miss], want.columns[1][~miss]) and np.array_equal(w[~miss], want.columns[2][~miss])

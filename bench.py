@@ -338,7 +338,7 @@ def q1_aux(capi, ctx, rank, world, rows, dist, torch, comm=None):
 def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch, comm=None):
     """BASELINE config 4 shape, row-range sharded: HashJoin(INNER, fk = pk, UNIQUE) with the build
     side a permutation of [0, B) (B = world x build_rows), probe keys uniform over the build keys,
-    result {fk, lv, payload}. One rank: ssb_join_build + ssb_join_probe + gathers. Several ranks:
+    result {fk, lv, payload}. One rank: ssb_join_build + ssb_join_probe_materialize (the probe writes the result columns). Several ranks:
     ShardedHashJoin (hash partition kernel, all-to-all over NCCL, local join, return trip)."""
     lib = ctx.lib
     I64 = capi.INT64
@@ -367,11 +367,13 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch, c
         def once():
             j = C.c_void_p()
             ctx.check(lib.ssb_join_build(ctx.h, 1, _cols(capi, [(ptrs["pk"], None, I64)]), build_rows, 1, C.byref(j)))
-            n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
-            ctx.check(lib.ssb_join_probe(j, _cols(capi, [(ptrs["fk"], None, I64)]), probe_rows, 0, C.byref(n), C.byref(pl), C.byref(pr)))
+            n = C.c_int64()
+            # UNIQUE keys: the probe writes the three result columns itself (no row-id lists, no gathers)
+            ctx.check(lib.ssb_join_probe_materialize(j, _cols(capi, [(ptrs["fk"], None, I64)]), probe_rows, 0,
+                                                     2, _cols(capi, [(ptrs["fk"], None, I64), (ptrs["lv"], None, I64)]),
+                                                     1, _cols(capi, [(ptrs["pay"], None, I64)]),
+                                                     _cols(capi, [(o_fk, None, I64), (o_lv, None, I64), (o_pay, None, I64)]), None, C.byref(n)))
             assert n.value <= probe_rows
-            for src, idx, dst in [(ptrs["fk"], pl, o_fk), (ptrs["lv"], pl, o_lv), (ptrs["pay"], pr, o_pay)]:
-                ctx.check(lib.ssb_gather(ctx.h, _cols(capi, [(src, None, I64)]), idx, n.value, _cols(capi, [(dst, None, I64)])))
             ctx.sync()
             state["pairs"] = n.value
             lib.ssb_join_destroy(j)
@@ -404,13 +406,13 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch, c
             j = C.c_void_p()
             ctx.check(lib.ssb_shard_join_build(comm.h, _cols(capi, [(ptrs["pk"], None, I64)]), 1,
                                                _cols(capi, [(ptrs["pay"], None, I64)]), build_rows, C.byref(j)))
-            n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
-            ctx.check(lib.ssb_shard_join_probe(j, _cols(capi, [(ptrs["fk"], None, I64)]), probe_rows, 0, C.byref(n), C.byref(pl), C.byref(pr)))
+            n = C.c_int64()
+            which = (C.c_int32 * 1)(0)
+            ctx.check(lib.ssb_shard_join_probe_materialize(j, _cols(capi, [(ptrs["fk"], None, I64)]), probe_rows, 0,
+                                                           2, _cols(capi, [(ptrs["fk"], None, I64), (ptrs["lv"], None, I64)]), 1, which,
+                                                           _cols(capi, [(o_fk.data_ptr(), None, I64), (o_lv.data_ptr(), None, I64),
+                                                                        (o_pay.data_ptr(), None, I64)]), None, C.byref(n)))
             assert n.value <= probe_rows
-            pay_all = capi.Column()
-            ctx.check(lib.ssb_shard_join_payload(j, 0, C.byref(pay_all), None))
-            for src, idx, dst in [(ptrs["fk"], pl, o_fk.data_ptr()), (ptrs["lv"], pl, o_lv.data_ptr()), (pay_all.data, pr, o_pay.data_ptr())]:
-                ctx.check(lib.ssb_gather(ctx.h, _cols(capi, [(src, None, I64)]), idx, n.value, _cols(capi, [(dst, None, I64)])))
             ctx.sync()
             state["pairs"] = n.value
             lib.ssb_shard_join_destroy(j)

@@ -282,6 +282,17 @@ void ssb_join_destroy(ssb_join* j);
 int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type,
                    int64_t* n_pairs, const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
 
+/* UNIQUE keys: probe and materialise in one kernel. Instead of the two row-id lists, the probe writes the result
+ * columns themselves at the pairs' final positions (hash_join.cc:793-831 copies lhs and rhs cells pair by pair as it
+ * finds them): out_cols[0 .. n_lhs) = lhs_cols gathered by the probe row, out_cols[n_lhs ..) = rhs_cols gathered by the
+ * matched build row (for an attached index: by row_offsets[part] + row, i.e. rows of the concatenated build sides).
+ * Source columns must be NOT NULL fixed-width columns; out_cols need room for `rows` rows. LEFT_OUTER: every lhs row
+ * comes out, rhs cells of unmatched rows are zero and d_matched[row] (one byte per row, may be NULL) says which
+ * matched. *n_rows = rows written. Synchronises. */
+int ssb_join_probe_materialize(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type, int32_t n_lhs,
+                               const ssb_column* lhs_cols, int32_t n_rhs, const ssb_column* rhs_cols,
+                               const ssb_column* out_cols, uint8_t* d_matched, int64_t* n_rows);
+
 /* The replicated form of the sharded join (UNIQUE single-column keys): the build side is
  * hash-partitioned over the ranks (ssb_partition_rows), every rank builds the index of the part it
  * received (ssb_join_build), the tables are all-gathered, and ssb_join_attach_parts makes an index over
@@ -384,6 +395,10 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
 int ssb_shard_join_probe(ssb_shard_join* j, const ssb_column* key, int64_t rows, int32_t join_type, int64_t* n_pairs,
                          const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
 int ssb_shard_join_payload(const ssb_shard_join* j, int32_t i, ssb_column* out, int64_t* rows);
+/* ssb_join_probe_materialize on the sharded index: rhs columns are named by their payload index. */
+int ssb_shard_join_probe_materialize(ssb_shard_join* j, const ssb_column* keys, int64_t rows, int32_t join_type,
+                                     int32_t n_lhs, const ssb_column* lhs_cols, int32_t n_rhs, const int32_t* rhs_payload,
+                                     const ssb_column* out_cols, uint8_t* d_matched, int64_t* n_rows);
 void ssb_shard_join_destroy(ssb_shard_join* j);
 
 /* The exchange step of a row-range sharded GroupAggregate / ScalarAggregate ("a reduce for global aggregates"):

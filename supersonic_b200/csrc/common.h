@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/supersonic_b200.h"
@@ -30,6 +32,11 @@ struct ssb_ctx {
   int64_t* d_count;           // one int64 result slot
   int64_t* h_count;           // pinned mirror
   int32_t* h_fail;            // pinned mirror
+  // large temporaries (tmp_malloc): freed blocks are kept per context and handed out again by size, so that an
+  // operator called in a loop neither pays cudaMalloc nor makes the driver's pool re-map memory every time
+  std::multimap<size_t, void*> tmp_cache;            // free blocks by size
+  std::unordered_map<void*, size_t> tmp_blocks;      // every block obtained through the cache (in use or free)
+  size_t tmp_cached_bytes;
 };
 
 namespace ssb {
@@ -44,6 +51,8 @@ int scratch(ssb_ctx* ctx, size_t bytes, void** out);
 // paying a cudaMalloc / cudaFree pair (and its implicit device synchronisation) every time.
 cudaError_t tmp_malloc_bytes(ssb_ctx* ctx, void** out, size_t bytes);
 void tmp_free(ssb_ctx* ctx, void* ptr);
+// Gives the cached large temporaries of every context on `device` back to the driver (out-of-memory paths).
+void tmp_release_cached(int device);
 template <class T>
 inline cudaError_t tmp_malloc(ssb_ctx* ctx, T** out, size_t bytes) {
   return tmp_malloc_bytes(ctx, reinterpret_cast<void**>(out), bytes);

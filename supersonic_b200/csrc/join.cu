@@ -232,13 +232,30 @@ __global__ void __launch_bounds__(256) join_emit_kernel(JoinTable t, long long r
 // aux: [0] ticket, [1] total pairs, [2 ..] one status word per tile.
 enum { kProbeThreads = 256, kProbeRows = 4, kProbeTile = kProbeThreads * kProbeRows };   // 8 rows per thread measured slower (114 registers: 9.7 ms vs 7.6 ms per 200M probes)
 
-template <bool PARTS>
+// EMIT: the probe writes the result COLUMNS itself (lhs columns gathered by the probe row, rhs columns by the matched
+// build row) at the pairs' final positions, instead of the two row-id lists a gather per column would read back:
+// per probe row 16 bytes less written and 16 + 8 per lhs column less read.
+enum { kEmitMax = 8 };
+struct JoinEmit {
+  int32_t n_l, n_r;
+  const void* l_src[kEmitMax]; void* l_dst[kEmitMax]; int32_t l_w[kEmitMax];
+  const void* r_src[kEmitMax]; void* r_dst[kEmitMax]; int32_t r_w[kEmitMax];
+  unsigned char* matched;   // LEFT_OUTER: 1 = the row found a build row (else the rhs cells are zero), or nullptr
+};
+__device__ __forceinline__ void emit_cell(void* dst, unsigned long long o, const void* src, long long i, int w) {
+  if (w == 8) static_cast<unsigned long long*>(dst)[o] = i >= 0 ? static_cast<const unsigned long long*>(src)[i] : 0ull;
+  else if (w == 4) static_cast<uint32_t*>(dst)[o] = i >= 0 ? static_cast<const uint32_t*>(src)[i] : 0u;
+  else static_cast<unsigned char*>(dst)[o] = i >= 0 ? static_cast<const unsigned char*>(src)[i] : static_cast<unsigned char>(0);
+}
+
+template <bool PARTS, bool EMIT>
 __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTable t, JoinKeys build, JoinKeys probe,
                                                                            long long rows, int left_outer,
                                                                            long long* __restrict__ lhs_out,
                                                                            long long* __restrict__ rhs_out,
                                                                            unsigned long long* __restrict__ aux,
-                                                                           const __grid_constant__ JoinParts parts) {
+                                                                           const __grid_constant__ JoinParts parts,
+                                                                           const __grid_constant__ JoinEmit emit) {
   __shared__ unsigned int s_tile;
   __shared__ unsigned int wcnt[kProbeRows][kProbeThreads / 32];
   __shared__ unsigned long long s_base;
@@ -301,7 +318,15 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
 #pragma unroll
       for (int j = 0; j < kProbeRows; ++j) {
         const long long row = r0 + j * kProbeThreads;
-        if (row < rows) { lhs_out[row] = row; rhs_out[row] = head[j]; }
+        if (row >= rows) continue;
+        if (EMIT) {
+          for (int c = 0; c < emit.n_l; ++c) emit_cell(emit.l_dst[c], static_cast<unsigned long long>(row), emit.l_src[c], row, emit.l_w[c]);
+          for (int c = 0; c < emit.n_r; ++c) emit_cell(emit.r_dst[c], static_cast<unsigned long long>(row), emit.r_src[c], head[j], emit.r_w[c]);
+          if (emit.matched != nullptr) emit.matched[row] = head[j] >= 0 ? 1 : 0;
+        } else {
+          lhs_out[row] = row;
+          rhs_out[row] = head[j];
+        }
       }
       if (tile == tiles - 1 && tid == 0) aux[1] = static_cast<unsigned long long>(rows);
       continue;
@@ -338,8 +363,14 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
     for (int j = 0; j < kProbeRows; ++j) {
       if (head[j] >= 0) {
         const unsigned long long o = base + before[j] + pos[j];
-        lhs_out[o] = r0 + j * kProbeThreads;
-        rhs_out[o] = head[j];
+        if (EMIT) {
+          const long long row = r0 + j * kProbeThreads;
+          for (int c = 0; c < emit.n_l; ++c) emit_cell(emit.l_dst[c], o, emit.l_src[c], row, emit.l_w[c]);
+          for (int c = 0; c < emit.n_r; ++c) emit_cell(emit.r_dst[c], o, emit.r_src[c], head[j], emit.r_w[c]);
+        } else {
+          lhs_out[o] = r0 + j * kProbeThreads;
+          rhs_out[o] = head[j];
+        }
       }
     }
   }
@@ -525,12 +556,14 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
     cudaMemsetAsync(aux, 0, static_cast<size_t>(tiles + 2) * 8, ctx->stream);
     long long grid = static_cast<long long>(ctx->num_sms) * 4;
     if (grid > tiles) grid = tiles;
+    JoinEmit no_emit;
+    memset(&no_emit, 0, sizeof(no_emit));
     if (j->parts.n_parts > 0) {
-      join_probe_unique_kernel<true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
-          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts);
+      join_probe_unique_kernel<true, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts, no_emit);
     } else {
-      join_probe_unique_kernel<false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
-          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts);
+      join_probe_unique_kernel<false, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts, no_emit);
     }
     ++ctx->launches;
     e = cudaGetLastError();
@@ -579,6 +612,61 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
   *n_pairs = static_cast<int64_t>(total);
   *d_lhs_rows = reinterpret_cast<const int64_t*>(j->lhs_out);
   *d_rhs_rows = reinterpret_cast<const int64_t*>(j->rhs_out);
+  return 0;
+}
+
+int ssb_join_probe_materialize(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t join_type, int32_t n_lhs,
+                               const ssb_column* lhs_cols, int32_t n_rhs, const ssb_column* rhs_cols, const ssb_column* out_cols,
+                               uint8_t* d_matched, int64_t* n_rows) {
+  ssb_ctx* ctx = j->ctx;
+  *n_rows = 0;
+  if (rows < 0) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "negative row count");
+  if (join_type != SSB_JOIN_INNER && join_type != SSB_JOIN_LEFT_OUTER) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "join type");
+  if (j->uniqueness != SSB_KEYS_UNIQUE) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "the materialising probe serves UNIQUE keys; use ssb_join_probe + ssb_gather");
+  if (n_lhs < 0 || n_rhs < 0 || n_lhs > kEmitMax || n_rhs > kEmitMax) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "at most 8 result columns per side");
+  JoinEmit emit;
+  memset(&emit, 0, sizeof(emit));
+  emit.n_l = n_lhs;
+  emit.n_r = n_rhs;
+  for (int c = 0; c < n_lhs + n_rhs; ++c) {
+    const ssb_column& src = c < n_lhs ? lhs_cols[c] : rhs_cols[c - n_lhs];
+    const int w = width_of(src.dtype);
+    if (w == 0 || width_of(out_cols[c].dtype) != w) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "result column type");
+    if (src.nulls != nullptr) return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "nullable result columns: use ssb_join_probe + ssb_gather");
+    if (c < n_lhs) { emit.l_src[c] = src.data; emit.l_dst[c] = out_cols[c].data; emit.l_w[c] = w; }
+    else { emit.r_src[c - n_lhs] = src.data; emit.r_dst[c - n_lhs] = out_cols[c].data; emit.r_w[c - n_lhs] = w; }
+  }
+  emit.matched = join_type == SSB_JOIN_LEFT_OUTER ? d_matched : nullptr;
+  if (rows == 0) return 0;
+  JoinKeys probe;
+  if (int rc = fill_keys(ctx, j->build_keys.n_keys, keys, &probe)) return rc;
+  for (int c = 0; c < probe.n_keys; ++c) {
+    const int a = probe.phys[c], b = j->build_keys.phys[c];
+    const bool ints = (a == T_I32 || a == T_I64 || a == T_U32 || a == T_U64) && (b == T_I32 || b == T_I64 || b == T_U32 || b == T_U64);
+    if (a != b && !ints) return fail(ctx, SSB_ERROR_INVALID_ARGUMENT_TYPE, "probe key types differ from the build keys");
+  }
+  TimedRegion timed(ctx);
+  const long long tiles = div_up(rows, kProbeTile);
+  unsigned long long* aux = nullptr;
+  cudaError_t e = tmp_malloc(ctx, &aux, static_cast<size_t>(tiles + 2) * 8);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "join probe buffers");
+  cudaMemsetAsync(aux, 0, static_cast<size_t>(tiles + 2) * 8, ctx->stream);
+  long long grid = static_cast<long long>(ctx->num_sms) * 4;
+  if (grid > tiles) grid = tiles;
+  if (j->parts.n_parts > 0) {
+    join_probe_unique_kernel<true, true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+        j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, nullptr, nullptr, aux, j->parts, emit);
+  } else {
+    join_probe_unique_kernel<false, true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+        j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, nullptr, nullptr, aux, j->parts, emit);
+  }
+  ++ctx->launches;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_count, aux + 1, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  tmp_free(ctx, aux);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "join probe");
+  *n_rows = *ctx->h_count;
   return 0;
 }
 

@@ -19,12 +19,36 @@
 // side is the index").
 #include <cuda_runtime.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 #include <vector>
 
 #include "comm.h"
 #include "common.h"
 
 using namespace ssb;
+
+namespace {
+// SSB200_DEBUG_SHARD_JOIN=1: wall-clock per phase (each mark synchronises the stream), printed by rank 0.
+struct PhaseClock {
+  ssb_ctx* ctx;
+  bool on;
+  int rank;
+  std::chrono::steady_clock::time_point last;
+  PhaseClock(ssb_ctx* c, int r) : ctx(c), on(getenv("SSB200_DEBUG_SHARD_JOIN") != nullptr), rank(r) {
+    if (on) { cudaStreamSynchronize(ctx->stream); last = std::chrono::steady_clock::now(); }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const std::chrono::steady_clock::time_point now = std::chrono::steady_clock::now();
+    if (rank == 0) fprintf(stderr, "[ssb200] shard join %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+};
+}  // namespace
 
 struct ssb_shard_join {
   ssb_comm* comm;
@@ -82,8 +106,10 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
     for (int i = 0; i < n_cols; ++i) tmp_free(ctx, recv[i]);
     if (local) ssb_join_destroy(local);
   };
+  PhaseClock clock(ctx, rank);
   int rc = ssb_partition_rows(ctx, 1, key, rows, W, W, reinterpret_cast<int64_t*>(d_perm), part_rows.data());
   if (rc) { cleanup(); return rc; }
+  clock.mark("partition");
   int64_t sent = 0;
   for (int r = 0; r < W; ++r) { send_rows[r] = part_rows[r]; sent += part_rows[r]; }
   // ---- 2. pack and exchange
@@ -96,6 +122,7 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
     dst.data = send[i];
     if (sent > 0) rc = ssb_gather(ctx, &src, reinterpret_cast<const int64_t*>(d_perm), sent, &dst);
   }
+  clock.mark("pack");
   if (rc == 0) rc = comm_exchange_counts(comm, send_rows.data(), recv_rows.data());
   int64_t received = 0;
   for (int r = 0; r < W; ++r) received += recv_rows[r];
@@ -104,6 +131,7 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
     if (e != cudaSuccess) rc = cuda_fail(ctx, e, "sharded join receive buffer");
   }
   if (rc == 0) rc = comm_all_to_all_v(comm, n_cols, send.data(), recv.data(), width.data(), send_rows.data(), recv_rows.data());
+  clock.mark("exchange (all-to-all)");
   // ---- 3. the table of this rank's part
   const void* d_slots = nullptr;
   int64_t capacity = 0;
@@ -114,6 +142,7 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
     rc = ssb_join_build(ctx, 1, &k, received, SSB_KEYS_UNIQUE | SSB_KEYS_COMPACT_TABLE, &local);
   }
   if (rc == 0) rc = ssb_join_table(local, &d_slots, &capacity);
+  clock.mark("build");
   // ---- 4. all-gather the tables and the payload columns
   std::vector<int64_t> all(2 * W, 0);
   if (rc == 0) {
@@ -155,6 +184,7 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
     }
     if (rc == 0) rc = comm_all_gather_v(comm, n_payload, recv.data() + 1, j->payload.data(), width.data() + 1, rows_of.data());
   }
+  clock.mark("all-gather tables + payload");
   if (rc == 0) {
     std::vector<const void*> slot_ptrs(W);
     for (int r = 0; r < W; ++r) slot_ptrs[r] = static_cast<const char*>(j->tables) + static_cast<size_t>(cap_offset[r]) * 16;
@@ -162,7 +192,7 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
   }
   // the exchange reads the send / receive buffers and the local table: wait for it, then let them go
   cleanup();
-  (void)rank;
+  clock.mark("attach + cleanup");
   if (rc != 0) { ssb_shard_join_destroy(j); return rc; }
   *out = j;
   return 0;
@@ -170,7 +200,23 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
 
 int ssb_shard_join_probe(ssb_shard_join* j, const ssb_column* key, int64_t rows, int32_t join_type, int64_t* n_pairs,
                          const int64_t** d_lhs_rows, const int64_t** d_rhs_rows) {
-  return ssb_join_probe(j->attached, key, rows, join_type, n_pairs, d_lhs_rows, d_rhs_rows);
+  PhaseClock clock(j->ctx, comm_rank(j->comm));
+  const int rc = ssb_join_probe(j->attached, key, rows, join_type, n_pairs, d_lhs_rows, d_rhs_rows);
+  clock.mark("probe");
+  return rc;
+}
+
+int ssb_shard_join_probe_materialize(ssb_shard_join* j, const ssb_column* keys, int64_t rows, int32_t join_type, int32_t n_lhs,
+                                     const ssb_column* lhs_cols, int32_t n_rhs, const int32_t* rhs_payload, const ssb_column* out_cols,
+                                     uint8_t* d_matched, int64_t* n_rows) {
+  std::vector<ssb_column> rhs(n_rhs > 0 ? n_rhs : 1);
+  for (int i = 0; i < n_rhs; ++i) {
+    if (int rc = ssb_shard_join_payload(j, rhs_payload[i], &rhs[i], nullptr)) return rc;
+  }
+  PhaseClock clock(j->ctx, comm_rank(j->comm));
+  const int rc = ssb_join_probe_materialize(j->attached, keys, rows, join_type, n_lhs, lhs_cols, n_rhs, rhs.data(), out_cols, d_matched, n_rows);
+  clock.mark("probe + materialise");
+  return rc;
 }
 
 int ssb_shard_join_payload(const ssb_shard_join* j, int32_t i, ssb_column* out, int64_t* rows) {

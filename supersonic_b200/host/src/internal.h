@@ -179,6 +179,7 @@ class GpuCursor : public Cursor {
       : schema_(schema), allocator_(allocator), name_(name), produced_(false), interrupted_(false),
         view_(schema), offset_(0) {}
   virtual FailureOrVoid Run(DeviceTable* result) = 0;
+  virtual void DropFusion() {}   // a child was replaced (ApplyToChildren): plans fused with it no longer apply
   bool interrupted() const { return interrupted_.load(std::memory_order_relaxed); }
   BufferAllocator* allocator() const { return allocator_; }
  private:

@@ -227,6 +227,21 @@ void NarrowedProgram(const vector<ssb_expr_node>& nodes, const vector<int32_t>& 
 // ------------------------------------------------------------------ row-wise cursor
 // One fused kernel for a chain of ScanView / Compute / Filter / Project
 // (replaces ComputeCursor::Next, FilterCursor::Next, ProjectCursor::Next).
+// Hands a shared cursor to code that takes ownership of a Cursor* (CursorTransformer::Transform).
+class SharedCursor : public Cursor {
+ public:
+  explicit SharedCursor(const std::shared_ptr<Cursor>& c) : c_(c) {}
+  virtual const TupleSchema& schema() const { return c_->schema(); }
+  virtual ResultView Next(rowcount_t max_row_count) { return c_->Next(max_row_count); }
+  virtual void Interrupt() { c_->Interrupt(); }
+  virtual bool IsWaitingOnBarrierSupported() const { return c_->IsWaitingOnBarrierSupported(); }
+  virtual void ApplyToChildren(CursorTransformer* transformer) { c_->ApplyToChildren(transformer); }
+  virtual void AppendDebugDescription(string* target) const { c_->AppendDebugDescription(target); }
+  virtual CursorId GetCursorId() const { return c_->GetCursorId(); }
+ private:
+  std::shared_ptr<Cursor> c_;
+};
+
 class RowwiseCursor : public GpuCursor {
  public:
   RowwiseCursor(const RowwisePlan& plan, BufferAllocator* allocator, CursorId id)
@@ -239,6 +254,11 @@ class RowwiseCursor : public GpuCursor {
     for (int i = 0; i < 2; ++i) lanes_[i].Free();
   }
   virtual CursorId GetCursorId() const { return id_; }
+  // The row-wise operators below this cursor are fused into it: its only child cursor is the non-row-wise source
+  // of the chain, if there is one (a scanned view has none).
+  virtual void ApplyToChildren(CursorTransformer* transformer) {
+    if (plan_.source) plan_.source.reset(transformer->Transform(new SharedCursor(plan_.source)));
+  }
 
   // Host-resident inputs are streamed: the view is cut into chunks that alternate between two
   // contexts (streams), so that the H2D copy of chunk i+1, the kernel of chunk i and the D2H
@@ -985,9 +1005,13 @@ class GroupCursor : public GpuCursor {
   // plan is evaluated inside the aggregation kernel (ssb_group_update_program), nothing is
   // materialised between the two operators.
   void FuseWith(const RowwisePlan& plan) { fused_.reset(new RowwisePlan(plan)); }
+  virtual void DropFusion() { fused_.reset(); }
   virtual ~GroupCursor() { if (group_) ssb_group_destroy(group_); }
   virtual CursorId GetCursorId() const { return scalar_ ? SCALAR_AGGREGATE : GROUP_AGGREGATE; }
   virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
+  // cursor/base/cursor.h:210 (basic_cursor.h: every child is handed to the transformer and replaced by its result).
+  // A transformed child is no longer known to be a GPU cursor: its rows then arrive through Next().
+  virtual void ApplyToChildren(CursorTransformer* transformer) { child_.reset(transformer->Transform(child_.release())); DropFusion(); }
  protected:
   // Returns true when the fused form ran; false = not applicable (plan too wide for one program).
   FailureOr<bool> RunFused(Session* s, DeviceTable* result) {
@@ -1168,6 +1192,9 @@ class ClustersCursor : public GpuCursor {
       : GpuCursor(schema, allocator, "AggregateClustersCursor"), child_(child), keys_(keys), aggs_(aggs) {}
   virtual CursorId GetCursorId() const { return AGGREGATE_CLUSTERS; }
   virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
+  // cursor/base/cursor.h:210 (basic_cursor.h: every child is handed to the transformer and replaced by its result).
+  // A transformed child is no longer known to be a GPU cursor: its rows then arrive through Next().
+  virtual void ApplyToChildren(CursorTransformer* transformer) { child_.reset(transformer->Transform(child_.release())); DropFusion(); }
  protected:
   virtual FailureOrVoid Run(DeviceTable* result) {
     FailureOr<Session*> sr = Session::Get();
@@ -1287,6 +1314,9 @@ class ConcatCursor : public GpuCursor {
   }
   virtual CursorId GetCursorId() const { return MERGE_UNION_ALL; }
   virtual void Interrupt() { GpuCursor::Interrupt(); for (size_t i = 0; i < inputs_.size(); ++i) inputs_[i]->Interrupt(); }
+  virtual void ApplyToChildren(CursorTransformer* transformer) {
+    for (size_t i = 0; i < inputs_.size(); ++i) inputs_[i].reset(transformer->Transform(inputs_[i].release()));
+  }
  protected:
   virtual FailureOrVoid Run(DeviceTable* result) {
     FailureOr<Session*> sr = Session::Get();
@@ -1418,6 +1448,10 @@ class HashJoinCursor : public GpuCursor {
   virtual ~HashJoinCursor() { if (join_) ssb_join_destroy(join_); }
   virtual CursorId GetCursorId() const { return HASH_JOIN; }
   virtual void Interrupt() { GpuCursor::Interrupt(); lhs_->Interrupt(); rhs_->Interrupt(); }
+  virtual void ApplyToChildren(CursorTransformer* transformer) {
+    lhs_.reset(transformer->Transform(lhs_.release()));
+    rhs_.reset(transformer->Transform(rhs_.release()));
+  }
  protected:
   virtual FailureOrVoid Run(DeviceTable* result) {
     FailureOr<Session*> sr = Session::Get();
@@ -1490,6 +1524,9 @@ class SortCursor : public GpuCursor {
       : GpuCursor(schema, allocator, "SortCursor"), child_(child), keys_(keys), projected_(projected), limit_(limit) {}
   virtual CursorId GetCursorId() const { return SORT; }
   virtual void Interrupt() { GpuCursor::Interrupt(); child_->Interrupt(); }
+  // cursor/base/cursor.h:210 (basic_cursor.h: every child is handed to the transformer and replaced by its result).
+  // A transformed child is no longer known to be a GPU cursor: its rows then arrive through Next().
+  virtual void ApplyToChildren(CursorTransformer* transformer) { child_.reset(transformer->Transform(child_.release())); DropFusion(); }
  protected:
   virtual FailureOrVoid Run(DeviceTable* result) {
     FailureOr<Session*> sr = Session::Get();

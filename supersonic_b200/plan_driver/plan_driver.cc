@@ -555,7 +555,31 @@ double WallNow() {
 
 }  // namespace
 
+// A cursor that forwards everything to the cursor it owns (written against the public Cursor interface only).
+class PassThroughCursor : public Cursor {
+ public:
+  explicit PassThroughCursor(Cursor* c) : c_(c) {}
+  virtual const TupleSchema& schema() const { return c_->schema(); }
+  virtual ResultView Next(rowcount_t max_row_count) { return c_->Next(max_row_count); }
+  virtual void Interrupt() { c_->Interrupt(); }
+  virtual bool IsWaitingOnBarrierSupported() const { return c_->IsWaitingOnBarrierSupported(); }
+  virtual void ApplyToChildren(CursorTransformer* transformer) { c_->ApplyToChildren(transformer); }
+  virtual void AppendDebugDescription(std::string* target) const { c_->AppendDebugDescription(target); }
+  virtual CursorId GetCursorId() const { return c_->GetCursorId(); }
+ private:
+  std::unique_ptr<Cursor> c_;
+};
+class PassThroughTransformer : public CursorTransformer {
+ public:
+  PassThroughTransformer() : wrapped_(0) {}
+  virtual Cursor* Transform(Cursor* cursor) { ++wrapped_; return new PassThroughCursor(cursor); }
+  int64_t wrapped() const { return wrapped_; }
+ private:
+  int64_t wrapped_;
+};
+
 struct ssplan_result {
+  int64_t spied_children;
   int code;
   std::string error;
   struct Col {
@@ -573,7 +597,7 @@ struct ssplan_result {
   int64_t rows;
   double create_s, drain_s;
   int64_t next_calls;
-  ssplan_result() : code(0), rows(0), create_s(0), drain_s(0), next_calls(0) {}
+  ssplan_result() : spied_children(0), code(0), rows(0), create_s(0), drain_s(0), next_calls(0) {}
 };
 
 namespace {
@@ -734,6 +758,18 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
 
   if (flags & SSPLAN_BIND_ONLY) return r->code;
 
+  // SSPLAN_SPY: the cursor tree's seams, exercised the way the reference's tests do with their spy cursors
+  // (cursor/core/spy.h, e.g. aggregate_clusters_test.cc:84-103): every child of the root is handed to a
+  // transformer that wraps it in a pass-through cursor, then the root itself is wrapped; the result must not change.
+  int64_t spied_children = 0;
+  if (flags & SSPLAN_SPY) {
+    PassThroughTransformer spy;
+    cursor->ApplyToChildren(&spy);
+    spied_children = spy.wrapped();
+    cursor.reset(spy.Transform(cursor.release()));
+  }
+  r->spied_children = spied_children;
+
   const rowcount_t max_rows =
       next_max_rows > 0 ? static_cast<rowcount_t>(next_max_rows) : Cursor::kDefaultRowCount;
   t0 = WallNow();
@@ -772,6 +808,7 @@ const uint8_t* ssplan_result_col_is_null(const ssplan_result* r, int32_t i) {
 double ssplan_result_create_seconds(const ssplan_result* r) { return r->create_s; }
 double ssplan_result_drain_seconds(const ssplan_result* r) { return r->drain_s; }
 int64_t ssplan_result_next_calls(const ssplan_result* r) { return r->next_calls; }
+int64_t ssplan_result_spied_children(const ssplan_result* r) { return r->spied_children; }
 void ssplan_result_free(ssplan_result* r) { delete r; }
 
 #ifndef SSPLAN_IMPL_NAME

@@ -42,6 +42,7 @@ typedef struct ssplan_result ssplan_result;
 enum {
   SSPLAN_DISCARD = 1,        /* drain the cursor but do not materialise rows (timing) */
   SSPLAN_BIND_ONLY = 2,      /* CreateCursor only: report the result schema, never call Next */
+  SSPLAN_SPY = 4,            /* Cursor::ApplyToChildren with a pass-through CursorTransformer, then wrap the root too */
 };
 
 /* Builds and runs `plan` over `tables`. Always sets *out (free it with
@@ -68,6 +69,8 @@ const uint8_t* ssplan_result_col_is_null(const ssplan_result* r, int32_t i);
 double ssplan_result_create_seconds(const ssplan_result* r);
 double ssplan_result_drain_seconds(const ssplan_result* r);
 int64_t ssplan_result_next_calls(const ssplan_result* r);
+/* SSPLAN_SPY: how many children of the root cursor were handed to the transformer. */
+int64_t ssplan_result_spied_children(const ssplan_result* r);
 void ssplan_result_free(ssplan_result* r);
 
 /* "reference" for the oracle build, "b200" for the product build. */

@@ -28,6 +28,7 @@ DTYPE_OF_NAME = {v: k for k, v in NAME_OF.items()}
 
 SSPLAN_DISCARD = 1
 SSPLAN_BIND_ONLY = 2
+SSPLAN_SPY = 4
 
 OK = 0
 ERROR_MEMORY_EXCEEDED = 102
@@ -94,7 +95,7 @@ class PlanLib(object):
                                  C.POINTER(C.c_void_p)]
         for name, res in [("code", C.c_int), ("error", C.c_char_p), ("ncols", C.c_int32),
                           ("rows", C.c_int64), ("create_seconds", C.c_double),
-                          ("drain_seconds", C.c_double), ("next_calls", C.c_int64)]:
+                          ("drain_seconds", C.c_double), ("next_calls", C.c_int64), ("spied_children", C.c_int64)]:
             f = getattr(L, "ssplan_result_" + name)
             f.restype, f.argtypes = res, [C.c_void_p]
         for name, res in [("col_name", C.c_char_p), ("col_dtype", C.c_int32),
@@ -177,9 +178,11 @@ class PlanLib(object):
                     nulls.append(np.frombuffer(nb, dtype=np.uint8, count=rows).astype(np.bool_))
                 else:
                     nulls.append(None)
-            return PlanResult(code, error, names, dtypes, nullable, columns, nulls, rows,
-                              L.ssplan_result_create_seconds(out),
-                              L.ssplan_result_drain_seconds(out),
-                              L.ssplan_result_next_calls(out))
+            res = PlanResult(code, error, names, dtypes, nullable, columns, nulls, rows,
+                             L.ssplan_result_create_seconds(out),
+                             L.ssplan_result_drain_seconds(out),
+                             L.ssplan_result_next_calls(out))
+            res.spied_children = L.ssplan_result_spied_children(out)
+            return res
         finally:
             L.ssplan_result_free(out)

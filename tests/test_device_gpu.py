@@ -611,3 +611,62 @@ def test_c4_full_size_join_pairs_in_order(ctx):
     ctx.lib.ssb_join_destroy(j)
     ctx.free(pk)
     ctx.free(fk)
+
+
+@pytest.mark.parametrize("compact", [0, 0x100])
+@pytest.mark.parametrize("join_type", [0, 1])
+def test_probe_materialize_equals_probe_plus_gather(ctx, join_type, compact):
+    """ssb_join_probe_materialize (UNIQUE keys: the probe writes the result columns at their final positions) against
+    ssb_join_probe + ssb_gather and against numpy: INT64 / INT32 / DOUBLE / BOOL columns, NULL probe keys, probe keys
+    without a build row, both join types, regular and compact tables."""
+    rng = np.random.default_rng(17 + join_type)
+    nb, npr = 70_001, 300_007
+    pk = rng.permutation(nb * 2)[:nb].astype(np.int64)
+    pay = rng.integers(-2**62, 2**62, nb)
+    flag = rng.integers(0, 2, nb).astype(np.bool_)
+    fk = rng.integers(0, nb * 2, npr)
+    fk_null = rng.random(npr) < 0.05
+    lv = rng.integers(0, 1000, npr).astype(np.int32)
+    ld = rng.random(npr)
+    d_pk, _ = _upload(ctx, pk)
+    d_pay, _ = _upload(ctx, pay)
+    d_flag, _ = _upload(ctx, flag)
+    d_fk, d_fkn = _upload(ctx, fk, fk_null)
+    d_lv, _ = _upload(ctx, lv)
+    d_ld, _ = _upload(ctx, ld)
+    j = C.c_void_p()
+    ctx.check(ctx.lib.ssb_join_build(ctx.h, 1, _cols([(d_pk, None, capi.INT64)]), nb, 1 | compact, C.byref(j)))
+    outs = [(ctx.malloc(npr * 8 + 256), np.int32, capi.INT32), (ctx.malloc(npr * 8 + 256), np.float64, capi.DOUBLE),
+            (ctx.malloc(npr * 8 + 256), np.int64, capi.INT64), (ctx.malloc(npr * 8 + 256), np.bool_, capi.BOOL)]
+    matched = ctx.malloc(npr + 256)
+    n = C.c_int64()
+    ctx.check(ctx.lib.ssb_join_probe_materialize(j, _cols([(d_fk, d_fkn, capi.INT64)]), npr, join_type,
+                                                 2, _cols([(d_lv, None, capi.INT32), (d_ld, None, capi.DOUBLE)]),
+                                                 2, _cols([(d_pay, None, capi.INT64), (d_flag, None, capi.BOOL)]),
+                                                 _cols([(p, None, dt) for p, _, dt in outs]), matched, C.byref(n)))
+    row_of = {int(k): i for i, k in enumerate(pk)}
+    hit = np.array([(-1 if fk_null[i] else row_of.get(int(fk[i]), -1)) for i in range(npr)])
+    keep = np.arange(npr) if join_type == 1 else np.nonzero(hit >= 0)[0]
+    assert n.value == len(keep)
+    got = []
+    for p, npdt, _ in outs:
+        a = np.empty(n.value, dtype=npdt)
+        ctx.d2h(a, p)
+        got.append(a)
+    h = hit[keep]
+    assert np.array_equal(got[0], lv[keep]) and np.array_equal(got[1], ld[keep])
+    assert np.array_equal(got[2], np.where(h >= 0, pay[np.maximum(h, 0)], 0))
+    assert np.array_equal(got[3], np.where(h >= 0, flag[np.maximum(h, 0)], False))
+    if join_type == 1:
+        m = np.empty(npr, dtype=np.uint8)
+        ctx.d2h(m, matched)
+        assert np.array_equal(m.astype(bool), h >= 0)
+    # the two-step form gives the same pairs
+    n2, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+    ctx.check(ctx.lib.ssb_join_probe(j, _cols([(d_fk, d_fkn, capi.INT64)]), npr, join_type, C.byref(n2), C.byref(pl), C.byref(pr)))
+    assert n2.value == n.value
+    li, ri = np.empty(n2.value, dtype=np.int64), np.empty(n2.value, dtype=np.int64)
+    ctx.d2h(li, pl)
+    ctx.d2h(ri, pr)
+    assert np.array_equal(li, keep) and np.array_equal(ri, h)
+    ctx.lib.ssb_join_destroy(j)

@@ -305,6 +305,7 @@ def _shard_join_worker(rank, world, port, out, n_scale):
             pk = up(t["pk"][bb:be], t["pk_null"][bb:be] if with_nulls else None)
             pay, w = up(t["payload"][bb:be]), up(t["w"][bb:be])
             fk = up(t["fk"][pb:pe], t["fk_null"][pb:pe] if with_nulls else None)
+            lvp = up(t["lv"][pb:pe])
             j = C.c_void_p()
             ctx.check(lib.ssb_shard_join_build(comm.h, cols([(pk[0], pk[1], capi.INT64)]), 2,
                                                cols([(pay[0], None, capi.INT64), (w[0], None, capi.DOUBLE)]), be - bb, C.byref(j)))
@@ -326,6 +327,20 @@ def _shard_join_worker(rank, world, port, out, n_scale):
                         ctx.d2h(whole, c.data)
                     outs.append(np.where(ri >= 0, whole[np.maximum(ri, 0)], 0))
                 res[(with_nulls, jt)] = (li + pb, ri < 0, outs)
+                # the materialising probe writes the same cells itself
+                o_lv, o_pay, o_w = ctx.malloc((pe - pb) * 8 + 256), ctx.malloc((pe - pb) * 8 + 256), ctx.malloc((pe - pb) * 8 + 256)
+                d_match = ctx.malloc((pe - pb) + 256)
+                m = C.c_int64()
+                which = (C.c_int32 * 2)(0, 1)
+                ctx.check(lib.ssb_shard_join_probe_materialize(j, cols([(fk[0], fk[1], capi.INT64)]), pe - pb, jt, 1, cols([(lvp[0], None, capi.INT64)]),
+                                                               2, which, cols([(o_lv, None, capi.INT64), (o_pay, None, capi.INT64), (o_w, None, capi.DOUBLE)]),
+                                                               d_match, C.byref(m)))
+                assert m.value == n.value
+                for ptr, npdt, want in ((o_lv, np.int64, t["lv"][pb:pe][li]), (o_pay, np.int64, outs[0]), (o_w, np.float64, outs[1])):
+                    a = np.empty(m.value, dtype=npdt)
+                    if m.value:
+                        ctx.d2h(a, ptr)
+                    assert np.array_equal(a, want)
             lib.ssb_shard_join_destroy(j)
         launches = ctx.launches()
         comm.close()

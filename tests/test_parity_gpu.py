@@ -507,3 +507,30 @@ def test_nan_group_keys_are_refused(ref, b200):
     ok = [sp.Column("k", sp.DOUBLE, [1.0, nan, 1.0, 0.5, 2.0], is_null=[False, True, False, False, False]),
           sp.Column("v", sp.INT64, [1, 2, 3, 4, 5])]
     same_results(ref.run(plan, [ok]), b200.run(plan, [ok]), ordered=False, sort_cols=[0])
+
+
+def test_apply_to_children_with_a_pass_through_transformer(ref, b200):
+    """Cursor::ApplyToChildren (cursor/base/cursor.h:210) the way the reference's tests use it with their spy cursors
+    (e.g. aggregate_clusters_test.cc:84-103): every child of the root cursor is wrapped by a CursorTransformer, then
+    the root; results must not change. A wrapped child is no longer a GPU cursor, so its rows reach the operator
+    through Next() -- the seam OperationTest-style harnesses rely on. Row-wise chains over a scan are one fused cursor
+    here and have no child cursors; the others must hand over every child."""
+    rng = np.random.default_rng(21)
+    n = 5000
+    t = [sp.Column("k", sp.INT32, rng.integers(0, 50, n).astype(np.int32)), sp.Column("v", sp.INT64, rng.integers(-99, 99, n)),
+         sp.Column("d", sp.DOUBLE, rng.integers(0, 64, n) / 8.0, is_null=rng.random(n) < 0.1), sp.Column("id", sp.INT64, np.arange(n))]
+    u = [sp.Column("pk", sp.INT32, np.arange(50, dtype=np.int32)), sp.Column("w", sp.INT64, np.arange(50) * 7)]
+    plans = [("(group (named k) (aggs (SUM v s) (MAX d m) (COUNT \"\" c)) (scan 0))", 1, False),
+             ("(group (named k) (aggs (SUM v s)) (filter (greater (col v) (i64 0)) (all) (scan 0)))", 1, False),
+             ("(sort (order (k DESC) (id ASC)) (all) (compute (compound (col k) (col id) (as e (plus (col v) (i64 1)))) (scan 0)))", 1, True),
+             ("(hash_join LEFT_OUTER (named k) (named pk) (multi (0 (named id v)) (1 (named w))) UNIQUE (scan 0) (scan 1))", 2, True),
+             ("(merge_union_all (order (id ASC)) (scan 0) (scan 0))", 2, True),
+             ("(aggregate_clusters (named k) (aggs (SUM v s)) (sort (order (k ASC) (id ASC)) (all) (scan 0)))", 1, True),
+             ("(compute (as e (multiply (col v) (col v))) (sort (order (id DESC)) (all) (scan 0)))", 1, True),
+             ("(filter (less (col v) (i64 0)) (all) (scan 0))", 0, True)]
+    for plan, children, ordered in plans:
+        want = ref.run(plan, [t, u], flags=sp.SSPLAN_SPY)
+        got = b200.run(plan, [t, u], flags=sp.SSPLAN_SPY)
+        assert got.spied_children == children, (plan, got.spied_children)
+        same_results(want, got, ordered=ordered, sort_cols=[0])
+        same_results(b200.run(plan, [t, u]), got, ordered=ordered, sort_cols=[0])

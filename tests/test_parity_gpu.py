@@ -524,7 +524,7 @@ def test_apply_to_children_with_a_pass_through_transformer(ref, b200):
              ("(group (named k) (aggs (SUM v s)) (filter (greater (col v) (i64 0)) (all) (scan 0)))", 1, False),
              ("(sort (order (k DESC) (id ASC)) (all) (compute (compound (col k) (col id) (as e (plus (col v) (i64 1)))) (scan 0)))", 1, True),
              ("(hash_join LEFT_OUTER (named k) (named pk) (multi (0 (named id v)) (1 (named w))) UNIQUE (scan 0) (scan 1))", 2, True),
-             ("(merge_union_all (order (id ASC)) (scan 0) (scan 0))", 2, True),
+             ("(merge_union_all (order (id ASC)) (scan 0) (scan 0))", 1, True),   # here: a sort over ONE concatenating cursor
              ("(aggregate_clusters (named k) (aggs (SUM v s)) (sort (order (k ASC) (id ASC)) (all) (scan 0)))", 1, True),
              ("(compute (as e (multiply (col v) (col v))) (sort (order (id DESC)) (all) (scan 0)))", 1, True),
              ("(filter (less (col v) (i64 0)) (all) (scan 0))", 0, True)]

@@ -16,6 +16,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -359,6 +360,21 @@ class MemoryLimit : public BufferAllocator {
 // ---- Column / View / Block (base/infrastructure/block.h:55-489) ---------------------------
 typedef bool* bool_ptr;
 typedef const bool* bool_const_ptr;
+
+// base/infrastructure/bit_pointers.h:541-583 (the boolean flavour: one bool per row): a set of skip / is_null vectors.
+class BoolView {
+ public:
+  explicit BoolView(size_t column_count) : columns_(column_count, static_cast<bool_ptr>(NULL)), row_count_(0) {}
+  explicit BoolView(bool_ptr data) : columns_(1, data), row_count_(0) {}
+  int column_count() const { return static_cast<int>(columns_.size()); }
+  rowcount_t row_count() const { return row_count_; }
+  bool_ptr column(int i) const { return columns_[i]; }
+  void ResetColumn(int i, bool_ptr data) { columns_[i] = data; }
+  void set_row_count(rowcount_t n) { row_count_ = n; }
+ private:
+  vector<bool_ptr> columns_;
+  rowcount_t row_count_;
+};
 
 class VariantConstPointer {
  public:

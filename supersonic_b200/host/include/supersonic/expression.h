@@ -11,6 +11,8 @@
 #ifndef SUPERSONIC_B200_HOST_EXPRESSION_H_
 #define SUPERSONIC_B200_HOST_EXPRESSION_H_
 
+#include <set>
+
 #include "supersonic/base.h"
 #include "supersonic/projector.h"
 
@@ -39,21 +41,38 @@ typedef FailureOrReference<const View> EvaluationResult;
 
 // The result of binding: result_schema() describes the columns, node(i) computes column i
 // from the columns of the schema the expression was bound to.
+// expression/base/expression.h:46-93. The reference evaluates a bound tree node by node through DoEvaluate; here a
+// bound expression is a DAG the cursors compile into one kernel, and DoEvaluate is the same kernel run for one view
+// (rows whose skip flag is set come back NULL / unspecified, as the skip-vector contract says). Subclasses may
+// override the virtuals; every factory below returns this class.
 class BoundExpression {
  public:
   BoundExpression(const TupleSchema& input_schema, const TupleSchema& result_schema,
-                  const vector<internal::NodePtr>& nodes)
-      : input_schema_(input_schema), result_schema_(result_schema), nodes_(nodes) {}
+                  const vector<internal::NodePtr>& nodes);
+  virtual ~BoundExpression();
   const TupleSchema& result_schema() const { return result_schema_; }
   const TupleSchema& input_schema() const { return input_schema_; }
   int column_count() const { return static_cast<int>(nodes_.size()); }
   const internal::NodePtr& node(int i) const { return nodes_[i]; }
-  bool is_constant() const;
-  // Names of the input attributes the expression reads.
+  // One skip vector per result column (BoolView of result_schema().attribute_count() columns; a NULL column = skip
+  // nothing). On return the skip vector of a NULLABLE column also flags the rows whose result is NULL.
+  virtual EvaluationResult DoEvaluate(const View& input, const BoolView& skip_vectors);
+  virtual rowcount_t row_capacity() const { return row_capacity_; }
+  void set_row_capacity(rowcount_t n) { row_capacity_ = n; }
+  virtual bool is_constant() const;
+  std::set<string> referred_attribute_names() const;
+  virtual void CollectReferredAttributeNames(std::set<string>* referred_attribute_names) const;
+  // Names of the input attributes the expression reads, in schema order.
   void CollectReferredAttributeNames(vector<string>* names) const;
  private:
+  BoundExpression(const BoundExpression&);
+  void operator=(const BoundExpression&);
   TupleSchema input_schema_, result_schema_;
   vector<internal::NodePtr> nodes_;
+  rowcount_t row_capacity_;
+  std::unique_ptr<internal::DeviceProgram> program_;
+  std::unique_ptr<Block> result_block_;
+  View view_;
 };
 
 class BoundExpressionList {
@@ -88,6 +107,10 @@ class BoundExpressionTree {
   View result_view_;
   std::unique_ptr<internal::DeviceProgram> program_;
 };
+
+// expression.h:140-144
+FailureOrOwned<BoundExpressionTree> CreateBoundExpressionTree(BoundExpression* expression, BufferAllocator* allocator,
+                                                              rowcount_t max_row_count);
 
 class Expression {
  public:
@@ -198,6 +221,53 @@ const Expression* BitwiseAndNot(const Expression* a, const Expression* b);
 const Expression* BitwiseNot(const Expression* argument);
 const Expression* ShiftLeft(const Expression* argument, const Expression* shift);
 const Expression* ShiftRight(const Expression* argument, const Expression* shift);
+
+// ---- the bound factories: the same binding rules over children that are already bound. They take ownership of
+// their arguments; every child must have been bound to the same input schema (constants fit any).
+// expression/infrastructure/terminal_bound_expressions.h:35-93
+FailureOrOwned<BoundExpression> BoundNull(DataType type, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstInt32(const int32& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstInt64(const int64& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstUInt32(const uint32& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstUInt64(const uint64& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstFloat(const float& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstDouble(const double& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstBool(const bool& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstDate(const int32& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstDateTime(const int64& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstString(const StringPiece& value, BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundConstBinary(const StringPiece& value, BufferAllocator* allocator, rowcount_t max_row_count);
+// expression/core/projecting_bound_expressions.h:40-76
+FailureOrOwned<BoundExpression> BoundInputAttributeProjection(const TupleSchema& schema, const SingleSourceProjector& projector);
+FailureOrOwned<BoundExpression> BoundAttributeAt(const TupleSchema& schema, size_t position);
+FailureOrOwned<BoundExpression> BoundNamedAttribute(const TupleSchema& schema, const string& name);
+FailureOrOwned<BoundExpression> BoundAlias(const string& new_name, BoundExpression* argument, BufferAllocator* allocator,
+                                           rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundCompoundExpression(BoundExpressionList* expressions);
+FailureOrOwned<BoundExpression> BoundRenameCompoundExpression(const vector<string>& names, BoundExpressionList* expressions);
+// expression/core/{arithmetic,comparison,elementary}_bound_expressions.h
+#define SSB200_BOUND1(NAME) \
+  FailureOrOwned<BoundExpression> NAME(BoundExpression* source, BufferAllocator* allocator, rowcount_t max_row_count);
+#define SSB200_BOUND2(NAME) \
+  FailureOrOwned<BoundExpression> NAME(BoundExpression* left, BoundExpression* right, BufferAllocator* allocator, rowcount_t max_row_count);
+SSB200_BOUND1(BoundNegate) SSB200_BOUND1(BoundIsOdd) SSB200_BOUND1(BoundIsEven) SSB200_BOUND1(BoundNot) SSB200_BOUND1(BoundIsNull)
+SSB200_BOUND1(BoundBitwiseNot)
+SSB200_BOUND2(BoundPlus) SSB200_BOUND2(BoundMinus) SSB200_BOUND2(BoundMultiply) SSB200_BOUND2(BoundDivideSignaling)
+SSB200_BOUND2(BoundDivideNulling) SSB200_BOUND2(BoundDivideQuiet) SSB200_BOUND2(BoundCppDivideSignaling)
+SSB200_BOUND2(BoundCppDivideNulling) SSB200_BOUND2(BoundModulusSignaling) SSB200_BOUND2(BoundModulusNulling)
+SSB200_BOUND2(BoundEqual) SSB200_BOUND2(BoundNotEqual) SSB200_BOUND2(BoundLess) SSB200_BOUND2(BoundLessOrEqual)
+SSB200_BOUND2(BoundGreater) SSB200_BOUND2(BoundGreaterOrEqual) SSB200_BOUND2(BoundOr) SSB200_BOUND2(BoundAnd)
+SSB200_BOUND2(BoundAndNot) SSB200_BOUND2(BoundXor) SSB200_BOUND2(BoundIfNull) SSB200_BOUND2(BoundBitwiseAnd)
+SSB200_BOUND2(BoundBitwiseAndNot) SSB200_BOUND2(BoundBitwiseOr) SSB200_BOUND2(BoundBitwiseXor) SSB200_BOUND2(BoundShiftLeft)
+SSB200_BOUND2(BoundShiftRight)
+#undef SSB200_BOUND1
+#undef SSB200_BOUND2
+FailureOrOwned<BoundExpression> BoundCastTo(DataType to_type, BoundExpression* source, BufferAllocator* allocator,
+                                            rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundIf(BoundExpression* condition, BoundExpression* then, BoundExpression* otherwise,
+                                        BufferAllocator* allocator, rowcount_t max_row_count);
+FailureOrOwned<BoundExpression> BoundIfNulling(BoundExpression* condition, BoundExpression* if_true, BoundExpression* if_false,
+                                               BufferAllocator* allocator, rowcount_t max_row_count);
 
 }  // namespace supersonic
 #endif  // SUPERSONIC_B200_HOST_EXPRESSION_H_

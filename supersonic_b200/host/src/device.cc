@@ -424,6 +424,53 @@ FailureOrVoid MaterializeOnDevice(Cursor* child, DeviceTable* out, std::unique_p
 
 }  // namespace internal
 
+// ------------------------------------------------------------------ BoundExpression
+BoundExpression::BoundExpression(const TupleSchema& input_schema, const TupleSchema& result_schema, const vector<internal::NodePtr>& nodes)
+    : input_schema_(input_schema), result_schema_(result_schema), nodes_(nodes), row_capacity_(Cursor::kDefaultRowCount),
+      view_(result_schema) {}
+BoundExpression::~BoundExpression() {}
+
+// One kernel for the whole DAG over the rows of `input` (expression.h:60-66). Rows flagged in a column's skip vector
+// are not part of the result: they come back NULL where the column is NULLABLE, unspecified otherwise, and the
+// signaling operators cannot be told to spare them (the fused kernel has no per-row skip input) -- which is why the
+// cursors state skips as guards instead (expression.cc GuardSignaling) and never call this.
+EvaluationResult BoundExpression::DoEvaluate(const View& input, const BoolView& skip_vectors) {
+  using namespace internal;   // NOLINT
+  if (!program_) {
+    vector<NodePtr> outs;
+    for (size_t i = 0; i < nodes_.size(); ++i) outs.push_back(GuardSignaling(nodes_[i], vector<NodePtr>(), NodePtr()));
+    FailureOrOwned<DeviceProgram> p = DeviceProgram::Create(input_schema_, outs, NodePtr());
+    PROPAGATE_ON_FAILURE(p);
+    program_.reset(p.release());
+  }
+  DeviceTable in;
+  PROPAGATE_ON_FAILURE(UploadColumns(input, program_->used_inputs(), 0, input.row_count(), &in));
+  DeviceTable out;
+  PROPAGATE_ON_FAILURE(out.Allocate(result_schema_, static_cast<int64>(input.row_count())));
+  vector<ssb_column> ic, oc;
+  for (size_t i = 0; i < in.columns.size(); ++i) ic.push_back(in.columns[i].col);
+  for (size_t i = 0; i < out.columns.size(); ++i) oc.push_back(out.columns[i].col);
+  FailureOr<int64> n = program_->Run(ic, static_cast<int64>(input.row_count()), oc);
+  PROPAGATE_ON_FAILURE(n);
+  out.rows = n.get();
+  if (!result_block_) result_block_.reset(new Block(result_schema_, HeapBufferAllocator::Get()));
+  if (result_block_->row_capacity() < input.row_count() && !result_block_->Reallocate(input.row_count())) {
+    THROW(new Exception(ERROR_MEMORY_EXCEEDED, "DoEvaluate: cannot allocate the result block"));
+  }
+  PROPAGATE_ON_FAILURE(out.Download(result_block_.get()));
+  for (int c = 0; c < result_schema_.attribute_count() && c < skip_vectors.column_count(); ++c) {
+    bool* skip = skip_vectors.column(c);
+    bool* is_null = result_block_->mutable_is_null(c);
+    if (skip == NULL) continue;
+    for (rowcount_t i = 0; i < input.row_count(); ++i) {
+      if (is_null != NULL) { is_null[i] = is_null[i] || skip[i]; skip[i] = is_null[i]; }
+    }
+  }
+  view_.ResetFromSubRange(result_block_->view(), 0, input.row_count());
+  const View& rv = view_;
+  return Success(rv);
+}
+
 // ------------------------------------------------------------------ BoundExpressionTree
 BoundExpressionTree::BoundExpressionTree(BoundExpression* root, BufferAllocator* allocator, rowcount_t max_row_count)
     : root_(root), allocator_(allocator), max_row_count_(max_row_count), result_view_(root->result_schema()) {}

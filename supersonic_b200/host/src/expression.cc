@@ -359,7 +359,9 @@ class FnExpression : public Expression {
     return s + ")";
   }
  private:
-  FailureOr<NodePtr> Apply(const NodePtr& a, const NodePtr& b, const NodePtr& c) const {
+  FailureOr<NodePtr> Apply(const NodePtr& a, const NodePtr& b, const NodePtr& c) const { return ApplyKind(kind_, a, b, c, cast_to_); }
+ public:
+  static FailureOr<NodePtr> ApplyKind(Kind kind_, const NodePtr& a, const NodePtr& b, const NodePtr& c, DataType cast_to_) {
     switch (kind_) {
       case K_PLUS: case K_MINUS: case K_MULTIPLY: case K_DIV_SIGNALING: case K_DIV_NULLING: case K_DIV_QUIET:
       case K_CPPDIV_SIGNALING: case K_CPPDIV_NULLING: case K_MOD_SIGNALING: case K_MOD_NULLING:
@@ -375,6 +377,7 @@ class FnExpression : public Expression {
       default: return BindUnary(kind_, a, cast_to_);
     }
   }
+ private:
   Kind kind_;
   std::unique_ptr<const Expression> a_, b_, c_;
   DataType cast_to_;
@@ -747,6 +750,16 @@ bool BoundExpression::is_constant() const {
   for (size_t i = 0; i < nodes_.size(); ++i) if (!nodes_[i]->constant) return false;
   return true;
 }
+void BoundExpression::CollectReferredAttributeNames(std::set<string>* referred_attribute_names) const {
+  vector<string> names;
+  CollectReferredAttributeNames(&names);
+  referred_attribute_names->insert(names.begin(), names.end());
+}
+std::set<string> BoundExpression::referred_attribute_names() const {
+  std::set<string> names;
+  CollectReferredAttributeNames(&names);
+  return names;
+}
 void BoundExpression::CollectReferredAttributeNames(vector<string>* names) const {
   std::map<int, bool> seen;
   for (size_t i = 0; i < nodes_.size(); ++i) CollectInputs(nodes_[i], &seen);
@@ -912,6 +925,177 @@ const Expression* NullingIf(const Expression* const c, const Expression* const t
 const Expression* Case(const ExpressionList* const arguments) { return new CaseExpression(arguments); }
 const Expression* In(const Expression* const needle, const ExpressionList* haystack) {
   return new InExpression(needle, haystack);
+}
+
+// ------------------------------------------------------------------ bound factories
+// expression/core/*_bound_expressions.h, expression/infrastructure/terminal_bound_expressions.h: the binding rules
+// above applied to children that are already bound.
+namespace {
+const TupleSchema& SchemaOf(const BoundExpression* a, const BoundExpression* b = NULL, const BoundExpression* c = NULL) {
+  // constants carry an empty input schema; the first child that reads a column decides
+  if (a && a->input_schema().attribute_count() > 0) return a->input_schema();
+  if (b && b->input_schema().attribute_count() > 0) return b->input_schema();
+  if (c && c->input_schema().attribute_count() > 0) return c->input_schema();
+  return a->input_schema();
+}
+FailureOr<NodePtr> OnlyColumn(const BoundExpression* e, const char* what) {
+  if (e->column_count() != 1) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "%s: expected an expression with 1 attribute, got %d", what, e->column_count());
+    THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, buf));
+  }
+  NodePtr n = e->node(0);
+  return Success(n);
+}
+FailureOrOwned<BoundExpression> ApplyBound(Kind kind, BoundExpression* a, BoundExpression* b, BoundExpression* c, DataType cast_to) {
+  std::unique_ptr<BoundExpression> oa(a), ob(b), oc(c);
+  NodePtr na, nb, nc;
+  FailureOr<NodePtr> ra = OnlyColumn(a, KindName(kind));
+  PROPAGATE_ON_FAILURE(ra);
+  na = ra.get();
+  if (b) { FailureOr<NodePtr> r = OnlyColumn(b, KindName(kind)); PROPAGATE_ON_FAILURE(r); nb = r.get(); }
+  if (c) { FailureOr<NodePtr> r = OnlyColumn(c, KindName(kind)); PROPAGATE_ON_FAILURE(r); nc = r.get(); }
+  FailureOr<NodePtr> r = FnExpression::ApplyKind(kind, na, nb, nc, cast_to);
+  PROPAGATE_ON_FAILURE(r);
+  return Single(SchemaOf(a, b, c), r.get());
+}
+FailureOrOwned<BoundExpression> BoundConstant(DataType type, bool is_null, const void* imm, size_t imm_bytes, const string& text) {
+  std::shared_ptr<ExprNode> n = NewNode(SSB_OP_CONST, type, is_null, is_null ? "NULL" : "CONST_" + TypeName(type));
+  n->constant = true;
+  n->flags = is_null ? SSB_NODE_NULL : 0;
+  if (imm) memcpy(&n->imm, imm, imm_bytes);
+  n->text = text;
+  return Single(TupleSchema(), n);
+}
+}  // namespace
+
+FailureOrOwned<BoundExpression> BoundNull(DataType type, BufferAllocator*, rowcount_t) { return BoundConstant(type, true, NULL, 0, ""); }
+#define SSB200_BOUND_CONST(NAME, DT, CPP)                                                              \
+  FailureOrOwned<BoundExpression> NAME(const CPP& value, BufferAllocator*, rowcount_t) {               \
+    return BoundConstant(DT, false, &value, sizeof(value), "");                                        \
+  }
+SSB200_BOUND_CONST(BoundConstInt32, INT32, int32)
+SSB200_BOUND_CONST(BoundConstInt64, INT64, int64)
+SSB200_BOUND_CONST(BoundConstUInt32, UINT32, uint32)
+SSB200_BOUND_CONST(BoundConstUInt64, UINT64, uint64)
+SSB200_BOUND_CONST(BoundConstFloat, FLOAT, float)
+SSB200_BOUND_CONST(BoundConstDouble, DOUBLE, double)
+SSB200_BOUND_CONST(BoundConstBool, BOOL, bool)
+SSB200_BOUND_CONST(BoundConstDate, DATE, int32)
+SSB200_BOUND_CONST(BoundConstDateTime, DATETIME, int64)
+#undef SSB200_BOUND_CONST
+FailureOrOwned<BoundExpression> BoundConstString(const StringPiece& value, BufferAllocator*, rowcount_t) {
+  return BoundConstant(STRING, false, NULL, 0, value.as_string());
+}
+FailureOrOwned<BoundExpression> BoundConstBinary(const StringPiece& value, BufferAllocator*, rowcount_t) {
+  return BoundConstant(BINARY, false, NULL, 0, value.as_string());
+}
+
+FailureOrOwned<BoundExpression> BoundAttributeAt(const TupleSchema& schema, size_t position) {
+  if (position >= static_cast<size_t>(schema.attribute_count())) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "Attribute position %zu out of range; the schema has %d attributes", position, schema.attribute_count());
+    THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, buf));
+  }
+  return Single(schema, internal::MakeInputNode(schema, static_cast<int>(position)));
+}
+FailureOrOwned<BoundExpression> BoundNamedAttribute(const TupleSchema& schema, const string& name) {
+  const int pos = schema.LookupAttributePosition(name);
+  if (pos < 0) {
+    THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "No attribute '" + name + "' in the schema: (" + schema.GetHumanReadableSpecification() + ")"));
+  }
+  return Single(schema, internal::MakeInputNode(schema, pos));
+}
+FailureOrOwned<BoundExpression> BoundInputAttributeProjection(const TupleSchema& schema, const SingleSourceProjector& projector) {
+  FailureOrOwned<const BoundSingleSourceProjector> bound = projector.Bind(schema);
+  PROPAGATE_ON_FAILURE(bound);
+  vector<NodePtr> nodes;
+  for (int i = 0; i < bound->result_schema().attribute_count(); ++i) {
+    std::shared_ptr<ExprNode> n(new ExprNode(*internal::MakeInputNode(schema, bound->source_attribute_position(i))));
+    n->name = bound->result_schema().attribute(i).name();
+    nodes.push_back(n);
+  }
+  return Success(new BoundExpression(schema, bound->result_schema(), nodes));
+}
+FailureOrOwned<BoundExpression> BoundAlias(const string& new_name, BoundExpression* argument, BufferAllocator*, rowcount_t) {
+  std::unique_ptr<BoundExpression> owner(argument);
+  FailureOr<NodePtr> n = OnlyColumn(argument, "ALIAS");
+  PROPAGATE_ON_FAILURE(n);
+  std::shared_ptr<ExprNode> renamed(new ExprNode(*n.get()));
+  renamed->name = new_name;
+  return Single(argument->input_schema(), renamed);
+}
+FailureOrOwned<BoundExpression> BoundRenameCompoundExpression(const vector<string>& names, BoundExpressionList* expressions) {
+  std::unique_ptr<BoundExpressionList> owner(expressions);
+  TupleSchema result;
+  vector<NodePtr> nodes;
+  const BoundExpression* with_input = NULL;
+  size_t at = 0;
+  for (int i = 0; i < expressions->size(); ++i) {
+    const BoundExpression* e = expressions->get(i);
+    if (with_input == NULL && e->input_schema().attribute_count() > 0) with_input = e;
+    for (int c = 0; c < e->column_count(); ++c, ++at) {
+      const Attribute& a = e->result_schema().attribute(c);
+      const string name = at < names.size() ? names[at] : a.name();
+      // projecting_bound_expressions.cc:316-352: BoundMultiSourceProjector::Add / AddAs return false for a name that
+      // is already there and the factories ignore it -- a later column with a duplicate name silently drops out
+      if (!result.add_attribute(Attribute(name, a.type(), a.nullability()))) continue;
+      if (name != a.name()) {
+        std::shared_ptr<ExprNode> renamed(new ExprNode(*e->node(c)));
+        renamed->name = name;
+        nodes.push_back(renamed);
+      } else {
+        nodes.push_back(e->node(c));
+      }
+    }
+  }
+  if (!names.empty() && names.size() != at) {
+    THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "BoundRenameCompoundExpression: the number of names differs from the number of columns"));
+  }
+  return Success(new BoundExpression(with_input ? with_input->input_schema() : TupleSchema(), result, nodes));
+}
+FailureOrOwned<BoundExpression> BoundCompoundExpression(BoundExpressionList* expressions) {
+  return BoundRenameCompoundExpression(vector<string>(), expressions);
+}
+
+#define SSB200_BOUND1(NAME, KIND)                                                                                   \
+  FailureOrOwned<BoundExpression> NAME(BoundExpression* source, BufferAllocator*, rowcount_t) {                    \
+    return ApplyBound(KIND, source, NULL, NULL, INT32);                                                             \
+  }
+#define SSB200_BOUND2(NAME, KIND)                                                                                   \
+  FailureOrOwned<BoundExpression> NAME(BoundExpression* left, BoundExpression* right, BufferAllocator*, rowcount_t) { \
+    return ApplyBound(KIND, left, right, NULL, INT32);                                                              \
+  }
+SSB200_BOUND1(BoundNegate, K_NEGATE) SSB200_BOUND1(BoundIsOdd, K_IS_ODD) SSB200_BOUND1(BoundIsEven, K_IS_EVEN)
+SSB200_BOUND1(BoundNot, K_NOT) SSB200_BOUND1(BoundIsNull, K_IS_NULL) SSB200_BOUND1(BoundBitwiseNot, K_BIT_NOT)
+SSB200_BOUND2(BoundPlus, K_PLUS) SSB200_BOUND2(BoundMinus, K_MINUS) SSB200_BOUND2(BoundMultiply, K_MULTIPLY)
+SSB200_BOUND2(BoundDivideSignaling, K_DIV_SIGNALING) SSB200_BOUND2(BoundDivideNulling, K_DIV_NULLING)
+SSB200_BOUND2(BoundDivideQuiet, K_DIV_QUIET) SSB200_BOUND2(BoundCppDivideSignaling, K_CPPDIV_SIGNALING)
+SSB200_BOUND2(BoundCppDivideNulling, K_CPPDIV_NULLING) SSB200_BOUND2(BoundModulusSignaling, K_MOD_SIGNALING)
+SSB200_BOUND2(BoundModulusNulling, K_MOD_NULLING) SSB200_BOUND2(BoundEqual, K_EQUAL) SSB200_BOUND2(BoundNotEqual, K_NOT_EQUAL)
+SSB200_BOUND2(BoundLess, K_LESS) SSB200_BOUND2(BoundLessOrEqual, K_LESS_OR_EQUAL) SSB200_BOUND2(BoundGreater, K_GREATER)
+SSB200_BOUND2(BoundGreaterOrEqual, K_GREATER_OR_EQUAL) SSB200_BOUND2(BoundOr, K_OR) SSB200_BOUND2(BoundAnd, K_AND)
+SSB200_BOUND2(BoundAndNot, K_AND_NOT) SSB200_BOUND2(BoundXor, K_XOR) SSB200_BOUND2(BoundIfNull, K_IF_NULL)
+SSB200_BOUND2(BoundBitwiseAnd, K_BIT_AND) SSB200_BOUND2(BoundBitwiseAndNot, K_BIT_AND_NOT) SSB200_BOUND2(BoundBitwiseOr, K_BIT_OR)
+SSB200_BOUND2(BoundBitwiseXor, K_BIT_XOR) SSB200_BOUND2(BoundShiftLeft, K_SHL) SSB200_BOUND2(BoundShiftRight, K_SHR)
+#undef SSB200_BOUND1
+#undef SSB200_BOUND2
+FailureOrOwned<BoundExpression> BoundCastTo(DataType to_type, BoundExpression* source, BufferAllocator*, rowcount_t) {
+  return ApplyBound(K_CAST, source, NULL, NULL, to_type);
+}
+FailureOrOwned<BoundExpression> BoundIf(BoundExpression* condition, BoundExpression* then, BoundExpression* otherwise, BufferAllocator*,
+                                        rowcount_t) {
+  return ApplyBound(K_IF, condition, then, otherwise, INT32);
+}
+FailureOrOwned<BoundExpression> BoundIfNulling(BoundExpression* condition, BoundExpression* if_true, BoundExpression* if_false,
+                                               BufferAllocator*, rowcount_t) {
+  return ApplyBound(K_NULLING_IF, condition, if_true, if_false, INT32);
+}
+
+FailureOrOwned<BoundExpressionTree> CreateBoundExpressionTree(BoundExpression* expression, BufferAllocator* allocator,
+                                                              rowcount_t max_row_count) {
+  expression->set_row_capacity(max_row_count);
+  return Success(new BoundExpressionTree(expression, allocator ? allocator : HeapBufferAllocator::Get(), max_row_count));
 }
 
 }  // namespace supersonic

@@ -46,6 +46,11 @@
 #include "supersonic/supersonic.h"
 #include "supersonic/cursor/core/aggregator.h"
 #include "supersonic/cursor/core/merge_union_all.h"
+#include "supersonic/expression/core/arithmetic_bound_expressions.h"
+#include "supersonic/expression/core/comparison_bound_expressions.h"
+#include "supersonic/expression/core/elementary_bound_expressions.h"
+#include "supersonic/expression/core/projecting_bound_expressions.h"
+#include "supersonic/expression/infrastructure/terminal_bound_expressions.h"
 #include "supersonic/proto/specification.pb.h"
 
 namespace {
@@ -462,9 +467,86 @@ T* Take(FailureOrOwned<T> r) {
   return r.release();
 }
 
+// The same expression grammar as BuildExpr, built bottom-up through the BOUND factories (BoundNamedAttribute,
+// BoundConst*, BoundPlus, BoundLess, BoundIf ...: expression/core/*_bound_expressions.h,
+// expression/infrastructure/terminal_bound_expressions.h) against `schema`.
+BoundExpression* BuildBoundExpr(const Sx& s, const TupleSchema& schema) {
+  const std::string& h = Head(s);
+  BufferAllocator* heap = HeapBufferAllocator::Get();
+  const rowcount_t cap = Cursor::kDefaultRowCount;
+  if (h == "col") { Arity(s, 1); return Take(BoundNamedAttribute(schema, Atom(s.kids[1]))); }
+  if (h == "at") { Arity(s, 1); return Take(BoundAttributeAt(schema, static_cast<size_t>(atoi(Atom(s.kids[1]).c_str())))); }
+  if (h == "i32") { Arity(s, 1); return Take(BoundConstInt32(static_cast<int32>(strtoll(Atom(s.kids[1]).c_str(), NULL, 0)), heap, cap)); }
+  if (h == "i64") { Arity(s, 1); return Take(BoundConstInt64(strtoll(Atom(s.kids[1]).c_str(), NULL, 0), heap, cap)); }
+  if (h == "u32") { Arity(s, 1); return Take(BoundConstUInt32(static_cast<uint32>(strtoull(Atom(s.kids[1]).c_str(), NULL, 0)), heap, cap)); }
+  if (h == "u64") { Arity(s, 1); return Take(BoundConstUInt64(strtoull(Atom(s.kids[1]).c_str(), NULL, 0), heap, cap)); }
+  if (h == "f32") { Arity(s, 1); return Take(BoundConstFloat(strtof(Atom(s.kids[1]).c_str(), NULL), heap, cap)); }
+  if (h == "f64") { Arity(s, 1); return Take(BoundConstDouble(strtod(Atom(s.kids[1]).c_str(), NULL), heap, cap)); }
+  if (h == "bool") { Arity(s, 1); return Take(BoundConstBool(Atom(s.kids[1]) == "true" || Atom(s.kids[1]) == "1", heap, cap)); }
+  if (h == "str") { Arity(s, 1); return Take(BoundConstString(Atom(s.kids[1]), heap, cap)); }
+  if (h == "null") { Arity(s, 1); return Take(BoundNull(ParseType(Atom(s.kids[1])), heap, cap)); }
+  if (h == "cast") { Arity(s, 2); return Take(BoundCastTo(ParseType(Atom(s.kids[1])), BuildBoundExpr(s.kids[2], schema), heap, cap)); }
+  if (h == "as") { Arity(s, 2); return Take(BoundAlias(Atom(s.kids[1]), BuildBoundExpr(s.kids[2], schema), heap, cap)); }
+  if (h == "if" || h == "nulling_if") {
+    Arity(s, 3);
+    BoundExpression* c = BuildBoundExpr(s.kids[1], schema);
+    BoundExpression* a = BuildBoundExpr(s.kids[2], schema);
+    BoundExpression* b = BuildBoundExpr(s.kids[3], schema);
+    return h == "if" ? Take(BoundIf(c, a, b, heap, cap)) : Take(BoundIfNulling(c, a, b, heap, cap));
+  }
+  if (h == "compound") {
+    std::unique_ptr<BoundExpressionList> list(new BoundExpressionList);
+    for (size_t i = 1; i < s.kids.size(); ++i) list->add(BuildBoundExpr(s.kids[i], schema));
+    return Take(BoundCompoundExpression(list.release()));
+  }
+  typedef FailureOrOwned<BoundExpression> (*B1)(BoundExpression*, BufferAllocator*, rowcount_t);
+  typedef FailureOrOwned<BoundExpression> (*B2)(BoundExpression*, BoundExpression*, BufferAllocator*, rowcount_t);
+  static const struct { const char* name; B1 fn; } unary[] = {
+      {"negate", &BoundNegate}, {"not", &BoundNot}, {"is_null", &BoundIsNull}, {"bitwise_not", &BoundBitwiseNot},
+      {"is_odd", &BoundIsOdd}, {"is_even", &BoundIsEven}};
+  static const struct { const char* name; B2 fn; } binary[] = {
+      {"plus", &BoundPlus}, {"minus", &BoundMinus}, {"multiply", &BoundMultiply}, {"divide_signaling", &BoundDivideSignaling},
+      {"divide_nulling", &BoundDivideNulling}, {"divide_quiet", &BoundDivideQuiet}, {"cpp_divide_signaling", &BoundCppDivideSignaling},
+      {"cpp_divide_nulling", &BoundCppDivideNulling}, {"modulus_signaling", &BoundModulusSignaling},
+      {"modulus_nulling", &BoundModulusNulling}, {"equal", &BoundEqual}, {"not_equal", &BoundNotEqual}, {"less", &BoundLess},
+      {"less_or_equal", &BoundLessOrEqual}, {"greater", &BoundGreater}, {"greater_or_equal", &BoundGreaterOrEqual},
+      {"and", &BoundAnd}, {"or", &BoundOr}, {"and_not", &BoundAndNot}, {"xor", &BoundXor}, {"bitwise_and", &BoundBitwiseAnd},
+      {"bitwise_or", &BoundBitwiseOr}, {"bitwise_xor", &BoundBitwiseXor}, {"bitwise_and_not", &BoundBitwiseAndNot},
+      {"shift_left", &BoundShiftLeft}, {"shift_right", &BoundShiftRight}, {"if_null", &BoundIfNull}};
+  for (size_t i = 0; i < sizeof(unary) / sizeof(unary[0]); ++i) {
+    if (h == unary[i].name) { Arity(s, 1); return Take(unary[i].fn(BuildBoundExpr(s.kids[1], schema), heap, cap)); }
+  }
+  for (size_t i = 0; i < sizeof(binary) / sizeof(binary[0]); ++i) {
+    if (h == binary[i].name) {
+      Arity(s, 2);
+      BoundExpression* a = BuildBoundExpr(s.kids[1], schema);
+      BoundExpression* b = BuildBoundExpr(s.kids[2], schema);
+      return Take(binary[i].fn(a, b, heap, cap));
+    }
+  }
+  throw ParseError{"unknown bound expression '" + h + "'"};
+}
+
 Cursor* BuildCursor(const Sx& s, const Inputs& in, Keep* keep) {
   const std::string& h = Head(s);
   BufferAllocator* heap = HeapBufferAllocator::Get();
+  // bound_bx_compute / bound_bx_filter: as bound_compute / bound_filter, but the expression is assembled from the
+  // bound factories (BuildBoundExpr) and wrapped with CreateBoundExpressionTree
+  if (h == "bound_bx_compute") {
+    Arity(s, 2);
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[2], in, keep));
+    BoundExpressionTree* tree = Take(CreateBoundExpressionTree(BuildBoundExpr(s.kids[1], child->schema()), heap, Cursor::kDefaultRowCount));
+    return Take(BoundCompute(tree, heap, Cursor::kDefaultRowCount, child.release()));
+  }
+  if (h == "bound_bx_filter") {
+    Arity(s, 3);
+    std::unique_ptr<const SingleSourceProjector> p(BuildProjector(s.kids[2]));
+    std::unique_ptr<Cursor> child(BuildCursor(s.kids[3], in, keep));
+    std::unique_ptr<BoundExpressionTree> tree(
+        Take(CreateBoundExpressionTree(BuildBoundExpr(s.kids[1], child->schema()), heap, Cursor::kDefaultRowCount)));
+    const BoundSingleSourceProjector* bp = Take(p->Bind(child->schema()));
+    return Take(BoundFilter(tree.release(), bp, heap, child.release()));
+  }
   if (h == "bound_scan") {
     Arity(s, 1);
     size_t n = static_cast<size_t>(atoi(Atom(s.kids[1]).c_str()));
@@ -688,6 +770,43 @@ int RunEvaluate(const Sx& sx, const Inputs& in, int32_t flags, ssplan_result* r)
   r->drain_s = WallNow() - t0;
   return r->code;
 }
+// (bx_evaluate EXPR N): the expression assembled from the bound factories, evaluated through the virtual
+// BoundExpression::DoEvaluate(view, skip vectors) (expression/base/expression.h:60-66) with nothing skipped. At most
+// Cursor::kDefaultRowCount rows (the capacity the factories are given).
+int RunBoundEvaluate(const Sx& sx, const Inputs& in, int32_t flags, ssplan_result* r) {
+  Arity(sx, 2);
+  const size_t n = static_cast<size_t>(atoi(Atom(sx.kids[2]).c_str()));
+  if (n >= in.views.size()) throw ParseError{"bx_evaluate: no such table"};
+  const View& table = in.views[n];
+  if (table.row_count() > Cursor::kDefaultRowCount) throw ParseError{"bx_evaluate: more rows than the expression's capacity"};
+  std::unique_ptr<BoundExpression> e;
+  try {
+    e.reset(BuildBoundExpr(sx.kids[1], table.schema()));
+  } catch (const BindError& b) {
+    r->code = b.code;
+    r->error = b.msg;
+    return r->code;
+  }
+  DescribeColumns(r, e->result_schema());
+  if (r->code != 0 || (flags & SSPLAN_BIND_ONLY)) return r->code;
+  const int cols = e->result_schema().attribute_count();
+  BoolView skip(cols);
+  std::vector<std::unique_ptr<bool[]> > store;
+  for (int c = 0; c < cols; ++c) {
+    store.push_back(std::unique_ptr<bool[]>(new bool[table.row_count() + 1]()));
+    skip.ResetColumn(c, store.back().get());
+  }
+  skip.set_row_count(table.row_count());
+  EvaluationResult result = e->DoEvaluate(table, skip);
+  ++r->next_calls;
+  if (result.is_failure()) {
+    r->code = result.exception().return_code();
+    r->error = result.exception().message();
+    return r->code;
+  }
+  AppendView(r, result.get(), flags);
+  return r->code;
+}
 }  // namespace
 
 extern "C" {
@@ -724,6 +843,7 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
   try {
     Sx sx = SxParser(plan).Parse();
     if (Head(sx) == "evaluate") return RunEvaluate(sx, in, flags, r);
+    if (Head(sx) == "bx_evaluate") return RunBoundEvaluate(sx, in, flags, r);
     if (Head(sx).compare(0, 6, "bound_") == 0) {
       t0 = WallNow();
       cursor.reset(BuildCursor(sx, in, &keep));

@@ -330,3 +330,35 @@ def test_operators_over_every_column_type(ref, b200):
         if _key(a) != _key(b):
             bad.append((plan, _key(a), a.error, _key(b), b.error))
     assert not bad, bad[:10]
+
+
+# ---- the bound factories (BoundNamedAttribute, BoundConst*, BoundPlus, BoundLess, BoundIf, BoundCastTo, BoundAlias,
+# BoundCompoundExpression ...: expression/core/*_bound_expressions.h, terminal_bound_expressions.h) assembled bottom-up
+# by the plan driver's BuildBoundExpr and wrapped by CreateBoundExpressionTree: same names, types, nullability and
+# error codes as the reference's own factories.
+def _check_bound(ref, b200, exprs):
+    bad = []
+    for e in exprs:
+        plan = "(bound_bx_compute %s (bound_scan 0))" % e
+        a = ref.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+        b = b200.run(plan, [COLS], flags=sp.SSPLAN_BIND_ONLY)
+        if _key(a) != _key(b):
+            bad.append((e, _key(a), _key(b)))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("op", BINARY)
+def test_bound_factory_binary_binding(ref, b200, op):
+    some = ["i32", "i64", "u32", "u64", "f32", "f64", "b", "d", "dt", "ni32", "nf64", "nb"]
+    _check_bound(ref, b200, ["(%s (col %s) (col %s))" % (op, x, y) for x, y in itertools.product(some, some)])
+
+
+def test_bound_factory_other_binding(ref, b200):
+    exprs = ["(%s (col %s))" % (u, x) for u in UNARY for x in NAMES]
+    exprs += ["(cast %s (col %s))" % (t, x) for t in TYPES for x in NAMES]
+    exprs += ["(if (col nb) (col %s) (col %s))" % (x, y) for x, y in itertools.product(NAMES[:9], NAMES[9:])]
+    exprs += ["(nulling_if (col b) (col i32) (col ni64))", "(as renamed (plus (col i32) (i32 1)))", "(plus (i64 1) (i32 2))",
+              "(compound (col i32) (as e (multiply (col f64) (f64 2))) (less (col i32) (i32 5)))", "(compound (col i32) (col i32))",
+              "(plus (col i32) (null INT32))", "(is_null (null DOUBLE))", "(col missing)", "(at 99)", "(at 3)",
+              "(if_null (col ni32) (i32 0))", "(equal (col i32) (u64 7))"]
+    _check_bound(ref, b200, exprs)

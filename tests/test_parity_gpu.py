@@ -534,3 +534,30 @@ def test_apply_to_children_with_a_pass_through_transformer(ref, b200):
         assert got.spied_children == children, (plan, got.spied_children)
         same_results(want, got, ordered=ordered, sort_cols=[0])
         same_results(b200.run(plan, [t, u]), got, ordered=ordered, sort_cols=[0])
+
+
+def test_bound_expression_factories_and_do_evaluate(ref, b200):
+    """Expressions assembled bottom-up from the BOUND factories (BoundNamedAttribute, BoundConst*, BoundPlus, BoundLess,
+    BoundIf, BoundCastTo, BoundAlias, BoundCompoundExpression: expression/core/*_bound_expressions.h) and wrapped with
+    CreateBoundExpressionTree give the same values as the reference's, through BoundCompute / BoundFilter cursors and
+    through the virtual BoundExpression::DoEvaluate(view, skip vectors) (expression/base/expression.h:46-93)."""
+    rng = np.random.default_rng(33)
+    n = 1000
+    t = [[sp.Column("a", sp.INT32, rng.integers(-50, 50, n).astype(np.int32)), sp.Column("b", sp.INT64, rng.integers(-10**6, 10**6, n), is_null=rng.random(n) < 0.2),
+          sp.Column("x", sp.DOUBLE, rng.integers(-64, 64, n) / 8.0), sp.Column("u", sp.UINT32, rng.integers(0, 2**32, n).astype(np.uint32)),
+          sp.Column("f", sp.BOOL, rng.integers(0, 2, n).astype(np.bool_), is_null=rng.random(n) < 0.1), sp.Column("s", sp.STRING, [b"ab", b"b", b""][0:1] * n)]]
+    exprs = ["(compound (as e (plus (multiply (col a) (col b)) (i64 7))) (less (col a) (i32 2)) (if_null (col b) (i64 -1)))",
+             "(compound (divide_nulling (col x) (cast DOUBLE (col a))) (cpp_divide_nulling (col u) (col a)) (modulus_nulling (col b) (i64 7)))",
+             "(if (and (col f) (greater (col x) (f64 0))) (cast INT64 (col a)) (col b))",
+             "(compound (nulling_if (col f) (col x) (negate (col x))) (is_null (col b)) (not (col f)) (xor (col f) (is_odd (col a))))",
+             "(compound (bitwise_and (col u) (u32 255)) (shift_left (col a) (i32 3)) (equal (col u) (col a)) (greater_or_equal (col b) (col a)))",
+             "(if (equal (col a) (i32 0)) (i32 0) (cpp_divide_signaling (i32 100) (col a)))"]
+    for e in exprs:
+        same_results(ref.run("(bound_bx_compute %s (bound_scan 0))" % e, t), b200.run("(bound_bx_compute %s (bound_scan 0))" % e, t))
+        same_results(ref.run("(bx_evaluate %s 0)" % e, t), b200.run("(bx_evaluate %s 0)" % e, t))
+    same_results(ref.run("(bound_bx_filter (or (less (col x) (f64 -2)) (is_null (col b))) (named a b x) (bound_scan 0))", t),
+                 b200.run("(bound_bx_filter (or (less (col x) (f64 -2)) (is_null (col b))) (named a b x) (bound_scan 0))", t))
+    same_results(ref.run('(bound_bx_filter (equal (col s) (str "ab")) (named s a) (bound_scan 0))', t),
+                 b200.run('(bound_bx_filter (equal (col s) (str "ab")) (named s a) (bound_scan 0))', t))
+    fails = "(bx_evaluate (cpp_divide_signaling (col a) (minus (col a) (col a))) 0)"
+    assert ref.run(fails, t).code == b200.run(fails, t).code == sp.ERROR_EVALUATION_ERROR

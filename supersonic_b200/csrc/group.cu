@@ -904,6 +904,99 @@ __global__ void fill_records_kernel(unsigned long long* rec, unsigned long long 
   for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += step) rec[i] = init.word[i & (stride - 1)];
 }
 
+// ---- dense integer keys ----------------------------------------------------------------------------------------
+// The general table costs three L2 accesses per row for the C3 shape (read the slot's key word, RED the sum, RED the
+// count), and the L2's request rate -- not HBM -- bounds the kernel. When the keys seen so far fill a narrow integer
+// range densely, slot = key - lo needs no key word: two REDs per row. Rows outside the range go to the general table
+// (deferred list); at the end the touched slots are merged into the general table as partial aggregates, so every
+// later step (growth, merge between ranks, finalize) is unchanged. SUM and COUNT aggregates over NOT NULL 8-byte
+// columns, one NOT NULL 8-byte integer key.
+struct DenseParams {
+  const unsigned long long* keys;
+  long long rows;
+  unsigned long long lo, range;
+  int32_t n_aggs;
+  int32_t code[kMaxAggs];                  // 0 COUNT, 1 SUM f64, 2 SUM 64-bit integer
+  const unsigned long long* in[kMaxAggs];
+  unsigned long long* acc[kMaxAggs];
+  unsigned long long* hits;                // or NULL
+  long long* deferred;
+  unsigned long long* n_deferred;
+};
+__global__ void __launch_bounds__(256, 4) group_update_dense_kernel(const __grid_constant__ DenseParams p) {
+  constexpr int R = 4;
+  constexpr int TILE = 256 * R;
+  const long long tiles = (p.rows + TILE - 1) / TILE;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long r0 = t * TILE + threadIdx.x;
+    unsigned long long slot[R];
+    bool in_range[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long row = r0 + j * 256;
+      slot[j] = row < p.rows ? p.keys[row] - p.lo : ~0ull;
+      in_range[j] = slot[j] < p.range;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const long long row = r0 + j * 256;
+      if (row < p.rows && !in_range[j]) {
+        const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+        p.deferred[d] = row;
+      }
+    }
+    for (int a = 0; a < p.n_aggs; ++a) {
+      if (p.code[a] == 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (in_range[j]) atomicAdd(&p.acc[a][slot[j]], 1ull);
+        continue;
+      }
+      unsigned long long v[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = in_range[j] ? p.in[a][r0 + j * 256] : 0ull;
+      if (p.code[a] == 1) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (in_range[j]) atomicAdd(reinterpret_cast<double*>(&p.acc[a][slot[j]]), Codec<double>::dec(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (in_range[j]) atomicAdd(&p.acc[a][slot[j]], v[j]);
+      }
+    }
+    if (p.hits != nullptr) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (in_range[j]) atomicAdd(&p.hits[slot[j]], 1ull);
+    }
+  }
+}
+// min / max of the first rows' keys as signed or unsigned 64-bit values: out[0] = min, out[1] = max
+__global__ void dense_minmax_kernel(const unsigned long long* __restrict__ keys, long long rows, int is_signed, unsigned long long* out) {
+  const unsigned long long flip = is_signed ? 0x8000000000000000ull : 0ull;   // order-preserving image
+  unsigned long long lo = ~0ull, hi = 0ull;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride) {
+    const unsigned long long k = keys[i] ^ flip;
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, d), h2 = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); }
+}
+// The touched slots as rows of partial aggregates: key = lo + slot, one value per aggregate; *n counts them.
+struct DenseOut { unsigned long long* key; unsigned long long* agg[8]; unsigned long long* n; };
+__global__ void dense_flush_kernel(DenseParams p, const unsigned long long* __restrict__ hits, DenseOut out) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long s = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; s < p.range; s += stride) {
+    if (hits[s] == 0) continue;
+    const unsigned long long o = atomicAdd(out.n, 1ull);
+    out.key[o] = p.lo + s;
+    for (int a = 0; a < p.n_aggs; ++a) out.agg[a][o] = p.acc[a][s];
+  }
+}
+
 // Fills a u64 array with a value (accumulator identities, empty keys).
 // ---- AggregateClusters (cursor/core/aggregate_clusters.cc:67-125,233-300): rows with equal keys that are
 // CONSECUTIVE in the input form a cluster; a key that comes back later starts a new one. flag[i] = row i
@@ -1000,6 +1093,13 @@ struct ssb_group {
   uint32_t* agg_out_nulls[kMaxAggs];
   unsigned long long* block_counts;
   long long out_capacity;
+  // dense-key accumulators (group_update_dense_kernel): slot = key - dense_lo, no key word to read
+  int dense_state;                        // 0 undecided, 1 active, -1 not applicable to this input
+  long long dense_lo;
+  unsigned long long dense_range;
+  unsigned long long* dense_acc[kMaxAggs];
+  unsigned long long* dense_hits;         // rows per slot when no aggregate counts every row
+  int dense_hits_agg;                     // the aggregate whose accumulator counts every row, or -1
 };
 
 namespace ssb {
@@ -1173,11 +1273,13 @@ struct SinkLaunch {
   uint32_t count_star;
 };
 
+// replay0 (a tmp_malloc'ed list of n_replay0 row numbers, ownership taken): only those rows of the slice are fed.
 static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows, bool merge,
-                      const RowProg* fused = nullptr, size_t fused_smem = 0, const SinkLaunch* sink = nullptr) {
+                      const RowProg* fused = nullptr, size_t fused_smem = 0, const SinkLaunch* sink = nullptr,
+                      long long* replay0 = nullptr, long long n_replay0 = 0) {
   ssb_ctx* ctx = g->ctx;
-  long long remaining = rows;
-  long long* replay = nullptr;
+  long long remaining = replay0 != nullptr ? n_replay0 : rows;
+  long long* replay = replay0;
   int rc = 0;
   for (int round = 0; round < 48 && remaining > 0; ++round) {
     if (g->deferred_cap < static_cast<size_t>(remaining)) {
@@ -1344,6 +1446,174 @@ static int refuse_nan_keys(ssb_group* g, const ssb_column* keys, int64_t rows) {
   return 0;
 }
 
+// ---- dense integer keys: host side ------------------------------------------------------------------------------
+static bool dense_shape(const ssb_group* g, const ssb_column* keys, const ssb_column* values) {
+  static const bool enabled = getenv("SSB200_GROUP_DENSE") == nullptr || atoi(getenv("SSB200_GROUP_DENSE")) != 0;
+  if (!enabled || g->n_keys != 1 || g->has_first_last || g->n_aggs < 1 || g->n_aggs > 8) return false;
+  const int kp = phys_of(g->key_types[0]);
+  if ((kp != T_I64 && kp != T_U64) || keys[0].nulls != nullptr || phys_of(keys[0].dtype) != kp) return false;
+  for (int a = 0; a < g->n_aggs; ++a) {
+    const ssb_agg_spec& sp = g->aggs[a];
+    if (sp.fn == SSB_AGG_COUNT) {
+      if (sp.input >= 0 && values[sp.input].nulls != nullptr) return false;
+      if (phys_width(phys_of(sp.out_type)) != 8) return false;
+      continue;
+    }
+    if (sp.fn != SSB_AGG_SUM || sp.input < 0) return false;
+    const int ip = phys_of(sp.in_type), op = phys_of(sp.out_type);
+    if (ip != op || (op != T_F64 && op != T_I64 && op != T_U64)) return false;
+    if (values[sp.input].nulls != nullptr || phys_of(values[sp.input].dtype) != ip) return false;
+  }
+  return true;
+}
+
+// After the first rows went through the general table: do their keys fill a narrow range densely?
+static int dense_decide(ssb_group* g, const ssb_column* keys, long long rows) {
+  ssb_ctx* ctx = g->ctx;
+  g->dense_state = -1;
+  const unsigned long long groups = g->h_counters[0];
+  if (groups < 65536 || rows < 1) return 0;   // few groups: the shared-memory kernels and the L2-resident table are fine
+  unsigned long long* mm = nullptr;
+  cudaError_t e = tmp_malloc(ctx, &mm, 16);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "dense key scratch");
+  const unsigned long long init[2] = {~0ull, 0ull};
+  cudaMemcpyAsync(mm, init, 16, cudaMemcpyHostToDevice, ctx->stream);
+  const long long sample = rows < (1ll << 20) ? rows : (1ll << 20);
+  const int is_signed = phys_of(g->key_types[0]) == T_I64 ? 1 : 0;
+  dense_minmax_kernel<<<update_grid(ctx, sample), 256, 0, ctx->stream>>>(static_cast<const unsigned long long*>(keys[0].data), sample, is_signed, mm);
+  ++ctx->launches;
+  unsigned long long h[2];
+  e = cudaMemcpyAsync(h, mm, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  tmp_free(ctx, mm);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "dense key range");
+  const unsigned long long span = h[1] - h[0] + 1;          // in the order-preserving image
+  if (h[1] < h[0] || span == 0 || span > (1ull << 25)) return 0;
+  const unsigned long long margin = span / 8 + 4096;
+  const unsigned long long flip = is_signed ? 0x8000000000000000ull : 0ull;
+  unsigned long long lo_img = h[0] > margin ? h[0] - margin : 0ull;
+  unsigned long long hi_img = h[1] + margin < h[1] ? ~0ull : h[1] + margin;
+  const unsigned long long range = hi_img - lo_img + 1;
+  if (range == 0 || range > (1ull << 25) || range > 64 * groups) return 0;   // sparse: most slots would stay empty
+  bool need_hits = true;
+  g->dense_hits_agg = -1;
+  for (int a = 0; a < g->n_aggs; ++a) {
+    if (g->aggs[a].fn == SSB_AGG_COUNT) { g->dense_hits_agg = a; need_hits = false; break; }   // counts every row (inputs are NOT NULL)
+  }
+  e = cudaSuccess;
+  for (int a = 0; a < g->n_aggs && e == cudaSuccess; ++a) {
+    e = tmp_malloc(ctx, &g->dense_acc[a], range * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->dense_acc[a], 0, range * 8, ctx->stream);
+  }
+  if (e == cudaSuccess && need_hits) {
+    e = tmp_malloc(ctx, &g->dense_hits, range * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->dense_hits, 0, range * 8, ctx->stream);
+  }
+  if (e != cudaSuccess) {   // no memory for it: stay with the general table
+    cudaGetLastError();
+    for (int a = 0; a < kMaxAggs; ++a) { tmp_free(ctx, g->dense_acc[a]); g->dense_acc[a] = nullptr; }
+    tmp_free(ctx, g->dense_hits);
+    g->dense_hits = nullptr;
+    return 0;
+  }
+  g->dense_lo = static_cast<long long>(lo_img ^ flip);   // back from the image: wrapping subtraction key - lo is the slot
+  g->dense_range = range;
+  g->dense_state = 1;
+  if (getenv("SSB200_DEBUG_PLAN")) fprintf(stderr, "[ssb200] group-by: dense keys, %llu slots from %lld\n", range, g->dense_lo);
+  return 0;
+}
+
+static void dense_fill(const ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows, DenseParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->keys = keys ? static_cast<const unsigned long long*>(keys[0].data) : nullptr;
+  p->rows = rows;
+  p->lo = static_cast<unsigned long long>(g->dense_lo);
+  p->range = g->dense_range;
+  p->n_aggs = g->n_aggs;
+  for (int a = 0; a < g->n_aggs; ++a) {
+    const ssb_agg_spec& sp = g->aggs[a];
+    p->code[a] = sp.fn == SSB_AGG_COUNT ? 0 : (phys_of(sp.out_type) == T_F64 ? 1 : 2);
+    p->in[a] = (values && sp.fn != SSB_AGG_COUNT) ? static_cast<const unsigned long long*>(values[sp.input].data) : nullptr;
+    p->acc[a] = g->dense_acc[a];
+  }
+  p->hits = g->dense_hits;
+  p->deferred = g->deferred;
+  p->n_deferred = &g->counters[1];
+}
+
+static int dense_feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows) {
+  ssb_ctx* ctx = g->ctx;
+  if (g->deferred_cap < static_cast<size_t>(rows)) {
+    tmp_free(ctx, g->deferred);
+    g->deferred = nullptr;
+    g->deferred_cap = 0;
+    cudaError_t e = tmp_malloc(ctx, &g->deferred, static_cast<size_t>(rows) * 8);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "deferred row list");
+    g->deferred_cap = static_cast<size_t>(rows);
+  }
+  DenseParams p;
+  dense_fill(g, keys, values, rows, &p);
+  cudaMemsetAsync(&g->counters[1], 0, 8, ctx->stream);
+  long long ctas = static_cast<long long>(ctx->num_sms) * 4;
+  if (ctas > div_up(rows, 1024)) ctas = div_up(rows, 1024);
+  group_update_dense_kernel<<<static_cast<unsigned>(ctas), 256, 0, ctx->stream>>>(p);
+  ++ctx->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "group_update_dense_kernel");
+  if (int rc = read_counters(g)) return rc;
+  const unsigned long long n_def = g->h_counters[1];
+  if (n_def == 0) return 0;
+  // keys outside the range: the general table takes those rows
+  long long* list = nullptr;
+  e = tmp_malloc(ctx, &list, n_def * 8);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "replay list");
+  cudaMemcpyAsync(list, g->deferred, n_def * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  return feed_slice(g, keys, values, rows, false, nullptr, 0, nullptr, list, static_cast<long long>(n_def));
+}
+
+// Merges the touched dense slots into the general table (as partial aggregates) and clears them.
+static int dense_flush(ssb_group* g) {
+  if (g->dense_state != 1) return 0;
+  ssb_ctx* ctx = g->ctx;
+  const unsigned long long range = g->dense_range;
+  DenseParams p;
+  dense_fill(g, nullptr, nullptr, 0, &p);
+  DenseOut out;
+  memset(&out, 0, sizeof(out));
+  cudaError_t e = tmp_malloc(ctx, &out.key, range * 8);
+  for (int a = 0; a < g->n_aggs && e == cudaSuccess; ++a) e = tmp_malloc(ctx, &out.agg[a], range * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &out.n, 8);
+  auto release = [&]() {
+    tmp_free(ctx, out.key);
+    for (int a = 0; a < 8; ++a) tmp_free(ctx, out.agg[a]);
+    tmp_free(ctx, out.n);
+  };
+  if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "dense flush scratch"); }
+  cudaMemsetAsync(out.n, 0, 8, ctx->stream);
+  const unsigned long long* hits = g->dense_hits != nullptr ? g->dense_hits : g->dense_acc[g->dense_hits_agg];
+  dense_flush_kernel<<<update_grid(ctx, static_cast<long long>(range)), 256, 0, ctx->stream>>>(p, hits, out);
+  ++ctx->launches;
+  e = cudaMemcpyAsync(ctx->h_count, out.n, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { release(); return cuda_fail(ctx, e, "dense flush"); }
+  const long long touched = *ctx->h_count;
+  int rc = 0;
+  if (touched > 0) {
+    ssb_column kc, ac[8];
+    kc.data = out.key; kc.nulls = nullptr; kc.dtype = g->key_types[0]; kc.reserved = 0;
+    for (int a = 0; a < g->n_aggs; ++a) { ac[a].data = out.agg[a]; ac[a].nulls = nullptr; ac[a].dtype = g->aggs[a].out_type; ac[a].reserved = 0; }
+    g->dense_state = -2;   // the merge below must take the general path
+    rc = feed(g, &kc, ac, touched, true, true);
+    g->dense_state = 1;
+  }
+  for (int a = 0; a < g->n_aggs; ++a) cudaMemsetAsync(g->dense_acc[a], 0, range * 8, ctx->stream);
+  if (g->dense_hits != nullptr) cudaMemsetAsync(g->dense_hits, 0, range * 8, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  release();
+  return rc;
+}
+
 static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, int64_t rows, bool merge,
                 bool internal) {
   ssb_ctx* ctx = g->ctx;
@@ -1369,6 +1639,16 @@ static int feed(ssb_group* g, const ssb_column* keys, const ssb_column* values, 
       v2[v] = values[v];
       v2[v].data = static_cast<char*>(values[v].data) + static_cast<size_t>(offset) * width_of(values[v].dtype);
       if (values[v].nulls) v2[v].nulls = values[v].nulls + offset / 32;
+    }
+    // dense integer keys (decided once, after the first rows have gone through the general table)
+    if (!merge && g->dense_state >= 0 && g->rows_seen >= kProbeRowsFirst && dense_shape(g, k2, v2)) {
+      if (g->dense_state == 0) { if (int rc = dense_decide(g, k2, n)) return rc; }
+      if (g->dense_state == 1) {
+        if (int rc = dense_feed(g, k2, v2, n)) return rc;
+        offset += n;
+        if (!internal) g->rows_seen += n;
+        continue;
+      }
     }
     if (int rc = feed_slice(g, k2, v2, n, merge)) return rc;
     offset += n;
@@ -1431,6 +1711,8 @@ void ssb_group_destroy(ssb_group* g) {
   cudaFreeHost(g->h_counters);
   tmp_free(ctx, g->deferred);
   tmp_free(ctx, g->block_counts);
+  for (int a = 0; a < kMaxAggs; ++a) tmp_free(ctx, g->dense_acc[a]);
+  tmp_free(ctx, g->dense_hits);
   for (int c = 0; c < kMaxKeys; ++c) { tmp_free(ctx, g->key_out[c]); tmp_free(ctx, g->key_out_nulls[c]); }
   for (int a = 0; a < kMaxAggs; ++a) { tmp_free(ctx, g->agg_out[a]); tmp_free(ctx, g->agg_out_nulls[a]); }
   delete g;
@@ -1582,12 +1864,14 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
 }
 
 int ssb_group_merge(ssb_group* dst, int64_t n_groups, const ssb_column* key_cols, const ssb_column* agg_cols) {
+  if (int rc = dense_flush(dst)) return rc;
   dst->merged_any = true;
   return feed(dst, key_cols, agg_cols, n_groups, true, false);
 }
 
 int ssb_group_finalize(ssb_group* g, int64_t* n_groups, ssb_column* key_out, ssb_column* agg_out) {
   ssb_ctx* ctx = g->ctx;
+  if (int rc = dense_flush(g)) return rc;
   if (int rc = read_counters(g)) return rc;
   long long n = g->n_keys == 0 ? 1 : static_cast<long long>(g->h_counters[0]);
   if (g->n_keys == 0 && g->rows_seen == 0 && !g->merged_any) n = 1;   // ScalarAggregate: exactly one row

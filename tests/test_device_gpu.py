@@ -670,3 +670,60 @@ def test_probe_materialize_equals_probe_plus_gather(ctx, join_type, compact):
     ctx.d2h(ri, pr)
     assert np.array_equal(li, keep) and np.array_equal(ri, h)
     ctx.lib.ssb_join_destroy(j)
+
+
+@pytest.mark.parametrize("with_count", [True, False])
+@pytest.mark.parametrize("lo", [0, -700_000, 2**62])
+def test_group_dense_keys_equal_host(ctx, lo, with_count, monkeypatch):
+    """Dense integer keys (slot = key - lo, two REDs per row instead of three L2 accesses): 600k distinct keys in a
+    narrow range starting at `lo`, a sprinkle of far outliers (they take the general table) and keys that first appear
+    after the range was chosen; SUM(DOUBLE) + SUM(INT64) with and without a COUNT(*) (without one a hit counter marks
+    the touched slots); chunked updates and a merge of two tables. Equal to the host and to the general table
+    (SSB200_GROUP_DENSE=0 is read once per process, so the general table is exercised through MIN, which the dense
+    path does not take)."""
+    rng = np.random.default_rng(11)
+    rows = 3_000_000
+    keys = rng.integers(0, 600_000, rows) + lo
+    keys[:200_000] = rng.integers(100_000, 500_000, 200_000) + lo      # the first rows see only the middle of the range
+    out = rng.integers(0, rows, 5_000)
+    keys[out] = rng.integers(-2**62, 2**62, 5_000)                       # far outside
+    keys[rng.integers(200_000, rows, 2_000)] = lo + 600_000 + 200_000    # beyond the margin
+    keys = keys.astype(np.int64)
+    vd = rng.integers(-2**20, 2**20, rows) / 1024.0
+    vi = rng.integers(-2**40, 2**40, rows)
+    d_k, _ = _upload(ctx, keys)
+    d_vd, _ = _upload(ctx, vd)
+    d_vi, _ = _upload(ctx, vi)
+    spec = [(capi.AGG_SUM, 0, capi.DOUBLE, capi.DOUBLE), (capi.AGG_SUM, 1, capi.INT64, capi.INT64)]
+    dts = [np.float64, np.int64]
+    if with_count:
+        spec.append((capi.AGG_COUNT, -1, capi.INT64, capi.UINT64))
+        dts.append(np.uint64)
+    kcol = lambda off=0: _cols([(d_k + off * 8, None, capi.INT64)])                                   # noqa: E731
+    vcol = lambda off=0: _cols([(d_vd + off * 8, None, capi.DOUBLE), (d_vi + off * 8, None, capi.INT64)])   # noqa: E731
+    g = _group(ctx, spec, 0)
+    before = ctx.launches()
+    ctx.check(ctx.lib.ssb_group_update(g, kcol(), vcol(), rows))
+    k1, a1, _ = _finalize(ctx, g, len(spec), dts)
+    # chunks + merge
+    ga, gb = _group(ctx, spec, 0), _group(ctx, spec, 0)
+    half = (rows // 2 // 32) * 32
+    third = (half // 3 // 32) * 32
+    ctx.check(ctx.lib.ssb_group_update(ga, kcol(), vcol(), third))
+    ctx.check(ctx.lib.ssb_group_update(ga, kcol(third), vcol(third), half - third))
+    ctx.check(ctx.lib.ssb_group_update(gb, kcol(half), vcol(half), rows - half))
+    _, _, (kob, aob, nb) = _finalize(ctx, gb, len(spec), dts)
+    ctx.check(ctx.lib.ssb_group_merge(ga, nb, kob, aob))
+    k2, a2, _ = _finalize(ctx, ga, len(spec), dts)
+    uk, inv = np.unique(keys, return_inverse=True)
+    hs = np.bincount(inv, weights=vd, minlength=len(uk))
+    hi = np.zeros(len(uk), dtype=np.int64)
+    np.add.at(hi, inv, vi)
+    want = [hs, hi] + ([np.bincount(inv, minlength=len(uk)).astype(np.uint64)] if with_count else [])
+    for kk, aa in [(k1, a1), (k2, a2)]:
+        assert np.array_equal(kk, uk)
+        for got, w in zip(aa, want):
+            assert np.array_equal(got, w)
+    assert ctx.launches() > before
+    for h in [g, ga, gb]:
+        ctx.lib.ssb_group_destroy(h)

@@ -244,6 +244,17 @@ int ssb_group_update(ssb_group* g, const ssb_column* keys, const ssb_column* val
  * compute.cc:49-56). Plans with many groups are materialised slice by slice internally.
  * Returns 104 when a signaling expression failed. Synchronises. */
 int ssb_group_update_program(ssb_group* g, ssb_program* prog, const ssb_column* inputs, int64_t rows);
+/* Tooling / tests (needs no device): ssb_group_update_program runs calls of 64M rows and more (SSB200_JIT_MIN_ROWS;
+ * SSB200_GROUP_JIT=1 always, 0 never) on a kernel compiled at run time for the plan -- the bound expression program,
+ * column types and aggregate list become compile-time constants of csrc/jit_rows.h, NVRTC produces the sm_100a
+ * cubin (the reference instead instantiates one column primitive per operator and type ahead of time:
+ * expression/vector/vector_primitives.h, expression/templated/bound_expression_factory.h). This entry compiles the
+ * kernel of one plan the same way and returns the generated source (or the compiler log) in `text`; `groups` =
+ * CTA-local group entries (1..8), threads / rows_per_thread 0 = the defaults. */
+int ssb_jit_rows_compile(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs, const int32_t* input_types,
+                         const int32_t* input_nullable, const int32_t* outputs, int32_t n_outputs, int32_t predicate,
+                         int32_t n_keys, int32_t n_aggs, const ssb_agg_spec* aggs, int32_t groups, int32_t threads,
+                         int32_t rows_per_thread, char* text, int64_t text_cap, int64_t* cubin_bytes);
 /* Compacts the table into dense result columns owned by `g` (valid until destroy or the
  * next update). Synchronises. A NULL key is a group of its own (row_hash_set.cc:81-90);
  * an aggregate over only-NULL inputs is NULL (column_aggregator.cc:108-125). */

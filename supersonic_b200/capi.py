@@ -104,6 +104,9 @@ def load():
         "ssb_group_destroy": (None, [P]),
         "ssb_group_update": (C.c_int, [P, C.POINTER(Column), C.POINTER(Column), I64]),
         "ssb_group_update_program": (C.c_int, [P, P, C.POINTER(Column), I64]),
+        "ssb_jit_rows_compile": (C.c_int, [C.POINTER(ExprNode), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(AggSpec),
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_char_p, I64, C.POINTER(I64)]),
         "ssb_group_finalize": (C.c_int, [P, C.POINTER(I64), C.POINTER(Column), C.POINTER(Column)]),
         "ssb_group_merge": (C.c_int, [P, I64, C.POINTER(Column), C.POINTER(Column)]),
         "ssb_join_build": (C.c_int, [P, I32, C.POINTER(Column), I64, I32, C.POINTER(P)]),

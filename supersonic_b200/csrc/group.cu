@@ -27,6 +27,8 @@
 #include "device_utils.h"
 #include "common.h"
 #include "group_device.h"
+#include "jit.h"
+#include "jit_rows.h"
 #include "program.h"
 
 namespace ssb {
@@ -1265,6 +1267,13 @@ static int grow_table(ssb_group* g, unsigned long long new_capacity) {
 // One slice: launch, then grow-and-replay until no row is deferred.
 // How to run a slice through the aggregation sink of expr_kernel (first round; replays of
 // deferred rows use the per-thread row evaluator).
+// The plan-specialised form of group_update_rows_kernel (csrc/jit.cu, csrc/jit_rows.h).
+struct JitLaunch {
+  JitKernel k;
+  JitRowsShape shape;
+  JitRun run;
+};
+
 struct SinkLaunch {
   ssb_program* twin;
   const ssb_column* inputs;
@@ -1276,7 +1285,7 @@ struct SinkLaunch {
 // replay0 (a tmp_malloc'ed list of n_replay0 row numbers, ownership taken): only those rows of the slice are fed.
 static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* values, long long rows, bool merge,
                       const RowProg* fused = nullptr, size_t fused_smem = 0, const SinkLaunch* sink = nullptr,
-                      long long* replay0 = nullptr, long long n_replay0 = 0) {
+                      long long* replay0 = nullptr, long long n_replay0 = 0, const JitLaunch* jit = nullptr) {
   ssb_ctx* ctx = g->ctx;
   long long remaining = replay0 != nullptr ? n_replay0 : rows;
   long long* replay = replay0;
@@ -1354,6 +1363,18 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
                                sink->out_aggs, sink->count_star, pad_codes, seen_mask);
       --ctx->launches;   // counted below
       if (rc) { tmp_free(ctx, d_params); break; }
+    } else if (fused != nullptr && jit != nullptr) {
+      const size_t smem = jit_rows_smem(jit->shape);
+      const void* fn = jit->k.kernel;
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, jit->shape.threads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+      const long long rows_per_cta = static_cast<long long>(jit->shape.threads) * jit->shape.rows_per_thread;
+      long long ctas = static_cast<long long>(ctx->num_sms) * per_sm;
+      if (ctas > div_up(remaining, rows_per_cta)) ctas = div_up(remaining, rows_per_cta);
+      JitRun run = jit->run;
+      void* args[] = {&p, &run};
+      cudaLaunchKernel(fn, dim3(static_cast<unsigned>(ctas)), dim3(static_cast<unsigned>(jit->shape.threads)), args, smem, ctx->stream);
     } else if (fused != nullptr) {
       cudaFuncSetAttribute(group_update_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fused_smem));
       long long per_sm = static_cast<long long>((ctx->smem_per_sm - 8192) / (fused_smem + 8192));
@@ -1783,6 +1804,11 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   for (int a = 0; a < A; ++a) {   // the sink accumulates without conversions
     if (g->aggs[a].fn != SSB_AGG_COUNT && phys_of(g->aggs[a].in_type) != phys_of(g->aggs[a].out_type)) sink_ok = false;
   }
+  const char* jit_env = getenv("SSB200_GROUP_JIT");
+  const int jit_mode = jit_env == nullptr ? -1 : atoi(jit_env);   // -1: by size, 0: never, 1: always
+  const char* jit_rows_env = getenv("SSB200_JIT_MIN_ROWS");
+  const long long jit_min_rows = jit_rows_env != nullptr ? atoll(jit_rows_env) : (1LL << 26);
+  bool jit_ok = rows_feasible && !float_key && n_in <= kJitMaxIn;
   if (rows_feasible) {
     rp.n_insn = static_cast<int32_t>(prog.generic.size());
     rp.n_in = n_in; rp.n_tmp = n_tmp; rp.n_out = n_out;
@@ -1821,9 +1847,38 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
       const int src = sink_program_for(sp, g->n_keys, A, sl.groups, &sl.twin);
       if (src != 0) { sink_ok = use_sink = false; }   // too wide for the sink: the two-kernel form below
     }
+    // large inputs: the kernel compiled for this plan (csrc/jit.cu). SSB200_GROUP_JIT=1 forces it for every slice
+    // (tests), 0 disables it; by default a call with at least SSB200_JIT_MIN_ROWS rows (64M) pays the compilation.
+    JitLaunch jl;
+    bool use_jit = false;
+    if (jit_mode != 0 && jit_ok && (jit_mode == 1 || rows >= jit_min_rows) &&
+        (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst ? g->h_counters[0] <= kTinyGroups : jit_mode == 1))) {
+      memset(&jl, 0, sizeof(jl));
+      jl.shape.n_keys = g->n_keys; jl.shape.n_aggs = A;
+      jl.shape.groups = g->n_keys == 0 ? 1 : (g->rows_seen >= kProbeRowsFirst ? static_cast<int>(g->h_counters[0] < 1 ? 1 : g->h_counters[0]) : kTinyGroups);
+      jit_rows_tune(&jl.shape);
+      for (int a = 0; a < A; ++a) {
+        jl.shape.fn[a] = g->aggs[a].fn;
+        jl.shape.in_phys[a] = g->aggs[a].input < 0 ? -1 : phys_of(g->aggs[a].in_type);
+        jl.shape.out_phys[a] = phys_of(g->aggs[a].out_type);
+        jl.shape.out[a] = rp.agg_out[a];
+      }
+      std::string jerr;
+      const std::string src = jit_rows_source(prog, jl.shape, &jerr);
+      if (!src.empty() && jit_rows_smem(jl.shape) + 4096 <= ctx->smem_optin && jit_get_kernel(ctx, src, "ssb_jit_rows", &jl.k) == 0) {
+        use_jit = true;
+        use_sink = false;
+      } else {
+        jit_ok = false;   // this call keeps the interpreting kernels
+      }
+    }
     // opt-in: every thread interprets the row program for its own rows (see the note above)
     const bool fuse = !use_sink && feasible && (g->n_keys == 0 || g->rows_seen < kProbeRowsFirst || g->h_counters[0] <= kTinyGroups);
-    if (use_sink) {
+    if (use_jit) {
+      for (int i = 0; i < n_in; ++i) { jl.run.in_data[i] = in2[i].data; jl.run.in_nulls[i] = in2[i].nulls; }
+      jl.run.d_fail = rp.d_fail;
+      rc = feed_slice(g, nullptr, nullptr, n, false, &rp, smem, nullptr, nullptr, 0, &jl);
+    } else if (use_sink) {
       for (int i = 0; i < n_in; ++i) { rp.in_data[i] = in2[i].data; rp.in_nulls[i] = in2[i].nulls; }
       sl.inputs = in2.data();
       for (int a = 0; a < A; ++a) {

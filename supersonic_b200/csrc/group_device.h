@@ -3,10 +3,15 @@
 #ifndef SSB_CSRC_GROUP_DEVICE_H_
 #define SSB_CSRC_GROUP_DEVICE_H_
 
+#if defined(__CUDACC_RTC__)
+#include "jit_rt.h"   // run-time compilation (csrc/jit.cu): device code only
+#include "ops.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "common.h"
+#endif
 
 namespace ssb {
 

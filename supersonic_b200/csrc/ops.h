@@ -8,8 +8,12 @@
 #ifndef SSB_CSRC_OPS_H_
 #define SSB_CSRC_OPS_H_
 
+#if defined(__CUDACC_RTC__)
+#include "jit_rt.h"   // run-time compilation (csrc/jit.cu): no libc headers
+#else
 #include <stdint.h>
 #include <string.h>
+#endif
 
 #if defined(__CUDACC__)
 #define SSB_HD __host__ __device__ __forceinline__

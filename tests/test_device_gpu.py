@@ -403,11 +403,14 @@ def _run_both(ctx, nodes, in_types, in_nullable, outputs, predicate, inputs, n_k
     return want, kept
 
 
-@pytest.fixture(params=["1", "0"], ids=["sink", "two_kernels"])
+@pytest.fixture(params=["sink", "two_kernels", "jit"])
 def sink_mode(request, monkeypatch):
-    """ssb_group_update_program with the aggregation sink inside the expression kernel (the default) and
-    with the two-kernel form (SSB200_GROUP_SINK=0); the environment is read at every call."""
-    monkeypatch.setenv("SSB200_GROUP_SINK", request.param)
+    """ssb_group_update_program with the aggregation sink inside the expression kernel (the default for small
+    inputs), with the two-kernel form (SSB200_GROUP_SINK=0) and with the kernel compiled at run time for the plan
+    (SSB200_GROUP_JIT=1: csrc/jit.cu; by default only calls of 64M rows and more take it); the environment is
+    read at every call."""
+    monkeypatch.setenv("SSB200_GROUP_SINK", "0" if request.param == "two_kernels" else "1")
+    monkeypatch.setenv("SSB200_GROUP_JIT", "1" if request.param == "jit" else "0")
     return request.param
 
 

@@ -1,0 +1,82 @@
+"""The run-time compiled aggregation kernel (csrc/jit.cu, csrc/jit_rows.h) without a GPU: NVRTC turns the
+plan-specialised source into an sm_100a cubin here (nvcc's runtime sibling needs no device), so a plan whose
+generated code does not compile fails on the CPU suite, not on the GPU box. Values are checked on the GPU by
+tests/test_device_gpu.py::test_fused_* in their `jit` mode."""
+import ctypes as C
+
+import pytest
+
+from supersonic_b200 import capi
+
+
+def _compile(nodes, types, nullable, outputs, predicate, n_keys, aggs, groups, threads=0, rows_per_thread=0):
+    lib = capi.load()
+    arr = (capi.ExprNode * len(nodes))(*nodes)
+    specs = (capi.AggSpec * len(aggs))()
+    for i, (fn, inp, it, ot, inn) in enumerate(aggs):
+        specs[i].fn, specs[i].input, specs[i].in_type, specs[i].out_type, specs[i].in_nullable = fn, inp, it, ot, inn
+    text = C.create_string_buffer(1 << 20)
+    size = C.c_int64()
+    rc = lib.ssb_jit_rows_compile(arr, len(nodes), len(types), (C.c_int32 * len(types))(*types), (C.c_int32 * len(types))(*nullable),
+                                  (C.c_int32 * len(outputs))(*outputs), len(outputs), predicate, n_keys, len(aggs), specs,
+                                  groups, threads, rows_per_thread, text, len(text), C.byref(size))
+    return rc, size.value, text.value.decode()
+
+
+def _q1():
+    n = capi.node
+    F64, I64, B = capi.DOUBLE, capi.INT64, capi.BOOL
+    types = [F64, F64, F64, F64, I64, I64, I64]
+    nodes = [n(capi.OP_INPUT, t, [j]) for j, t in enumerate(types)]
+    nodes += [n(capi.OP_CONST, F64, [], f64=1.0), n(capi.OP_SUB, F64, [7, 2]), n(capi.OP_MUL, F64, [1, 8]),
+              n(capi.OP_ADD, F64, [7, 3]), n(capi.OP_MUL, F64, [9, 10]), n(capi.OP_CONST, I64, [], i64=2450),
+              n(capi.OP_LE, B, [6, 12])]
+    aggs = [(capi.AGG_SUM, i, F64, F64, 0) for i in range(5)] + [(capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
+    return nodes, types, [0] * 7, [4, 5, 0, 1, 9, 11, 2], 13, 2, aggs
+
+
+def test_q1_plan_compiles_to_an_sm100a_cubin(built):
+    rc, size, text = _compile(*_q1(), groups=6)
+    assert rc == 0, text[-4000:]
+    assert size > 10000
+    # the generated prelude: one X-macro line per input column, instruction and aggregate
+    assert "enum { T = 128, R = 2, G = 6" in text and "N_IN = 7" in text and "NK = 2, A = 6" in text
+    assert text.count("\n  X(") == 7 + 6 + text.split("#define SSB_JIT_PROGRAM(X)")[1].split("#define")[0].count("\n  X(")
+    assert '#include "jit_rows.h"' in text
+
+
+@pytest.mark.parametrize("threads,rows_per_thread", [(256, 2), (128, 4), (64, 1)])
+def test_launch_shapes_compile(built, threads, rows_per_thread):
+    rc, size, text = _compile(*_q1(), groups=8, threads=threads, rows_per_thread=rows_per_thread)
+    assert rc == 0 and size > 0, text[-4000:]
+    assert "T = %d, R = %d, G = 8" % (threads, rows_per_thread) in text
+
+
+def test_nullable_mixed_type_plan_compiles(built):
+    """NULL-carrying inputs, a cast, MIN / MAX / COUNT(column) / SUM(INT32): every accumulate form of jit_rows.h."""
+    n = capi.node
+    F64, I64, I32, B = capi.DOUBLE, capi.INT64, capi.INT32, capi.BOOL
+    types = [I64, I64, F64, I32]
+    nodes = [n(capi.OP_INPUT, t, [j]) for j, t in enumerate(types)]
+    nodes += [n(capi.OP_CONST, I64, [], i64=3), n(capi.OP_MUL, I64, [1, 4]), n(capi.OP_CONST, I64, [], i64=-2500),
+              n(capi.OP_GT, B, [5, 6]), n(capi.OP_CAST, I64, [3]), n(capi.OP_ADD, I64, [5, 8])]
+    aggs = [(capi.AGG_SUM, 0, I64, I64, 1), (capi.AGG_MIN, 1, F64, F64, 1), (capi.AGG_MAX, 1, F64, F64, 1),
+            (capi.AGG_COUNT, 1, F64, capi.UINT64, 1), (capi.AGG_COUNT, -1, I64, capi.UINT64, 0), (capi.AGG_SUM, 2, I32, I32, 0)]
+    rc, size, text = _compile(nodes, types, [1, 1, 1, 0], [0, 9, 2, 3], 7, 1, aggs, groups=8)
+    assert rc == 0 and size > 0, text[-4000:]
+
+
+def test_scalar_aggregate_and_signaling_division_compile(built):
+    n = capi.node
+    I64, B = capi.INT64, capi.BOOL
+    nodes = [n(capi.OP_INPUT, I64, [0]), n(capi.OP_INPUT, I64, [1]), n(capi.OP_CONST, I64, [], i64=10), n(capi.OP_LT, B, [1, 2]),
+             n(capi.OP_DIV, I64, [0, 1], flags=capi.NODE_ZERO_FAILS)]
+    aggs = [(capi.AGG_SUM, 0, I64, I64, 0), (capi.AGG_MAX, 0, I64, I64, 0), (capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
+    rc, size, text = _compile(nodes, [I64, I64], [0, 0], [4], 3, 0, aggs, groups=1)
+    assert rc == 0 and size > 0, text[-4000:]
+
+
+def test_plans_outside_the_kernel_limits_are_refused(built):
+    nodes, types, nullable, outputs, predicate, n_keys, aggs = _q1()
+    rc, size, text = _compile(nodes, types, nullable, outputs, predicate, n_keys, aggs, groups=9)
+    assert rc == 103 and size == 0 and "limits" in text

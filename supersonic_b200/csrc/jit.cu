@@ -93,15 +93,18 @@ void appendf(std::string* s, const char* fmt, ...) {
 
 size_t jit_rows_smem(const JitRowsShape& sh);
 
-// Launch shape of ssb_jit_rows (call after n_aggs / groups are set): 128 threads x 2 rows, as many CTAs per SM as
-// the per-thread accumulators in shared memory allow (at most 5: 80+ registers per thread).
-// SSB200_JIT_THREADS / SSB200_JIT_ROWS / SSB200_JIT_MIN_CTAS pin them for A/B runs (profiles/r2h_q1_jit.txt).
+// Launch shape of ssb_jit_rows (call after n_aggs / groups are set). From the B200 sweep on the Q1 shape
+// (profiles/r2h_q1_jit.txt): 192 threads x 1 row per step with the next step's loads in flight, as many CTAs per SM as
+// the per-thread accumulators in shared memory and 84 registers per thread allow (3 for 6 groups x 6 aggregates).
+// Two rows per thread with prefetch spill (117 registers wanted) and lose a factor of two.
+// SSB200_JIT_THREADS / SSB200_JIT_ROWS / SSB200_JIT_PREFETCH / SSB200_JIT_MIN_CTAS pin them for A/B runs.
 void jit_rows_tune(JitRowsShape* sh) {
   auto env = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
-  sh->threads = env("SSB200_JIT_THREADS", 128);
-  sh->rows_per_thread = env("SSB200_JIT_ROWS", 2);
+  sh->threads = env("SSB200_JIT_THREADS", 192);
+  sh->rows_per_thread = env("SSB200_JIT_ROWS", 1);
+  sh->prefetch = env("SSB200_JIT_PREFETCH", 1);
   long long fit = (220 * 1024) / static_cast<long long>(jit_rows_smem(*sh) + 2560);
-  const long long by_regs = 65536 / (static_cast<long long>(sh->threads) * 96);
+  const long long by_regs = 65536 / (static_cast<long long>(sh->threads) * 84);
   if (fit > by_regs) fit = by_regs;
   if (fit < 1) fit = 1;
   if (fit > 8) fit = 8;
@@ -123,8 +126,8 @@ std::string jit_rows_source(const Program& prog, const JitRowsShape& sh, std::st
   }
   std::string s;
   s += "// generated by csrc/jit.cu (jit_rows_source)\n";
-  appendf(&s, "#include \"jit_rt.h\"\nnamespace ssb {\nstruct Spec {\n  enum { T = %d, R = %d, G = %d, MIN_CTAS = %d, N_IN = %d, N_SLOT = %d, N_OUT = %d, NK = %d, A = %d };\n};\n}\n",
-          sh.threads, sh.rows_per_thread, sh.groups, sh.min_ctas, n_in, n_slot, n_out, sh.n_keys, sh.n_aggs);
+  appendf(&s, "#include \"jit_rt.h\"\nnamespace ssb {\nstruct Spec {\n  enum { T = %d, R = %d, G = %d, MIN_CTAS = %d, PREFETCH = %d, N_IN = %d, N_SLOT = %d, N_OUT = %d, NK = %d, A = %d };\n};\n}\n",
+          sh.threads, sh.rows_per_thread, sh.groups, sh.min_ctas, sh.prefetch, n_in, n_slot, n_out, sh.n_keys, sh.n_aggs);
   s += "#define SSB_JIT_INPUTS(X)";
   for (int c = 0; c < n_in; ++c) {
     const int ph = phys_of(prog.input_types[c]);

@@ -22,6 +22,7 @@ struct JitRowsShape {
   int fn[16], in_phys[16], out_phys[16], out[16];   // out: program output feeding aggregate a, -1 = COUNT(*)
   int groups;          // CTA-local group entries (1 .. kTinyGroups)
   int threads, rows_per_thread, min_ctas;
+  int prefetch;        // the next step's inputs are loaded before this step's are evaluated
 };
 
 // Fills threads / rows_per_thread / min_ctas (defaults or the SSB200_JIT_* environment).

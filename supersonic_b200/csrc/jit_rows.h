@@ -46,22 +46,46 @@ struct JitRow {
   uint32_t on[jit_max1(Spec::N_OUT)];
 };
 
+// The input values of the R rows one thread evaluates per step; the next step's are loaded before this step's
+// are evaluated, so every warp keeps its loads in flight while it computes.
+struct JitIn {
+  enum { R = Spec::R };
+  long long rows[R];
+  uint32_t live;
+  u64 v[jit_max1(Spec::N_IN)][R];
+  uint32_t n[jit_max1(Spec::N_IN)];
+};
+
 template <int C, int PHYS, int NULLABLE>
-__device__ __forceinline__ void jit_load(JitRow& s, const JitRun& run, const long long (&rows)[Spec::R]) {
+__device__ __forceinline__ void jit_load(JitIn& in, const JitRun& run) {
   constexpr int R = Spec::R;
   uint32_t nn = 0;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     u64 v = 0;
-    if (rows[j] >= 0) {
+    if (in.rows[j] >= 0) {
       bool isn = false;
-      if (NULLABLE) isn = bit_at(run.in_nulls[C], rows[j]);
+      if (NULLABLE) isn = bit_at(run.in_nulls[C], in.rows[j]);
       if (isn) nn |= 1u << j;
-      else v = load_raw(run.in_data[C], PHYS, rows[j]);
+      else v = load_raw(run.in_data[C], PHYS, in.rows[j]);
     }
-    s.sv[C][j] = v;
+    in.v[C][j] = v;
   }
-  s.sn[C] = nn;
+  in.n[C] = nn;
+}
+
+__device__ __forceinline__ void jit_fetch(JitIn& in, const GroupParams& p, const JitRun& run, long long base) {
+  constexpr int R = Spec::R, T = Spec::T;
+  in.live = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const long long i = base + static_cast<long long>(j) * T;
+    in.rows[j] = i < p.rows ? (p.row_index ? p.row_index[i] : i) : -1;
+    if (in.rows[j] >= 0) in.live |= 1u << j;
+  }
+#define SSB_JIT_X_LOAD(C, PHYS, NULLABLE) jit_load<C, PHYS, NULLABLE>(in, run);
+  SSB_JIT_INPUTS(SSB_JIT_X_LOAD)
+#undef SSB_JIT_X_LOAD
 }
 
 // One instruction of the program; every field is a template constant, so alu() folds to the one operation.
@@ -135,12 +159,14 @@ struct JitLocal {
 };
 // The row's group is not among the CTA-local entries this thread knows: finds (or inserts) its slot in the global
 // table and claims a local entry for it. Returns the local entry or -1 (*slot < 0: the row must be deferred).
-__device__ __noinline__ int jit_claim(const GroupParams& p, JitLocal& L, const unsigned long long* kv, unsigned int knull,
-                                      unsigned long long fp, long long* slot_out) {
+struct JitKey { unsigned long long v[jit_max1(Spec::NK)]; };   // by value: the key stays in registers at the call
+// Returns the slot in the high word ((slot + 1) << 8, 0 = defer the row) and the local entry + 1 in the low byte (0 = none).
+__device__ __noinline__ unsigned long long jit_claim(const GroupParams& p, JitLocal& L, const JitKey key, unsigned int knull,
+                                                     unsigned long long fp) {
   constexpr int G = Spec::G, NK = Spec::NK;
+  const unsigned long long* kv = key.v;
   const long long slot = p.packed ? find_slot_packed_kv(p, (knull & 1u) != 0, kv[0]) : find_slot_generic_kv(p, kv, knull);
-  *slot_out = slot;
-  if (slot < 0) return -1;
+  if (slot < 0) return 0ull;
   const unsigned int want = static_cast<unsigned int>(slot) + 1u;
   int g = -1;
   for (int e = 0; e < G && g < 0; ++e) {
@@ -156,7 +182,7 @@ __device__ __noinline__ int jit_claim(const GroupParams& p, JitLocal& L, const u
       g = e;
     }
   }
-  return g;
+  return (static_cast<unsigned long long>(slot + 1) << 8) | static_cast<unsigned long long>(g + 1);
 }
 
 // One aggregate of one row: into the thread's accumulator of local group g, or (g < 0) the global table.
@@ -206,15 +232,29 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
   for (int e = 0; e < G; ++e) my_fp[e] = 0;
   uint32_t fail = 0;
   const long long stride = static_cast<long long>(gridDim.x) * T * R;
-  for (long long base = static_cast<long long>(blockIdx.x) * T * R + tid; base < p.rows; base += stride) {
+  // Spec::PREFETCH = how many steps ahead the inputs are loaded (0: this step's loads are issued at the end of the
+  // previous step, nothing overlaps the evaluation; 1 / 2: one / two steps' loads stay in flight under it)
+  JitIn next, next2;
+  long long base = static_cast<long long>(blockIdx.x) * T * R + tid;
+  if (base < p.rows) jit_fetch(next, p, run, base);
+  if (Spec::PREFETCH >= 2 && base + stride < p.rows) jit_fetch(next2, p, run, base + stride);
+  for (; base < p.rows; base += stride) {
     JitRow s;
     long long rows_[R];
-    s.live = 0;
+    s.live = next.live;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const long long i = base + static_cast<long long>(j) * T;
-      rows_[j] = i < p.rows ? (p.row_index ? p.row_index[i] : i) : -1;
-      if (rows_[j] >= 0) s.live |= 1u << j;
+    for (int j = 0; j < R; ++j) rows_[j] = next.rows[j];
+#pragma unroll
+    for (int c = 0; c < Spec::N_IN; ++c) {
+      s.sn[c] = next.n[c];
+#pragma unroll
+      for (int j = 0; j < R; ++j) s.sv[c][j] = next.v[c][j];
+    }
+    if (Spec::PREFETCH >= 2) {
+      next = next2;
+      if (base + 2 * stride < p.rows) jit_fetch(next2, p, run, base + 2 * stride);
+    } else if (Spec::PREFETCH == 1) {
+      if (base + stride < p.rows) jit_fetch(next, p, run, base + stride);
     }
 #pragma unroll
     for (int c = Spec::N_IN; c < jit_max1(Spec::N_SLOT); ++c) {
@@ -228,9 +268,6 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
 #pragma unroll
       for (int j = 0; j < R; ++j) s.ov[o][j] = 0;
     }
-#define SSB_JIT_X_LOAD(C, PHYS, NULLABLE) jit_load<C, PHYS, NULLABLE>(s, run, rows_);
-    SSB_JIT_INPUTS(SSB_JIT_X_LOAD)
-#undef SSB_JIT_X_LOAD
     s.accn = 0; s.pass = s.live; s.fail = 0;
 #pragma unroll
     for (int j = 0; j < R; ++j) s.acc[j] = 0;
@@ -247,8 +284,10 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       if (!((s.pass >> j) & 1u)) continue;
-      unsigned long long kv[jit_max1(NK)];
+      JitKey key;
+      unsigned long long (&kv)[jit_max1(NK)] = key.v;
       unsigned int knull = 0;
+      kv[0] = 0;
 #pragma unroll
       for (int c = 0; c < NK; ++c) {
         kv[c] = 0;
@@ -268,7 +307,9 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
       }
       long long slot = -1;
       if (g < 0) {
-        g = jit_claim(p, L, kv, knull, fp, &slot);
+        const unsigned long long claimed = jit_claim(p, L, key, knull, fp);
+        slot = static_cast<long long>(claimed >> 8) - 1;
+        g = static_cast<int>(claimed & 0xffull) - 1;
         if (slot < 0) {
           const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
           p.deferred[d] = rows_[j];
@@ -281,6 +322,7 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
 #undef SSB_JIT_X_AGG
       if (seen) t_seen[g * T + tid] |= seen;
     }
+    if (!Spec::PREFETCH && base + stride < p.rows) jit_fetch(next, p, run, base + stride);
   }
   if (fail && run.d_fail != nullptr) atomicOr(run.d_fail, 1);
   __syncthreads();

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <iostream>
 #include <limits>
 #include <map>
 #include <memory>
@@ -53,6 +54,37 @@ class StringPiece {
   const char* ptr_;
   size_t len_;
 };
+
+// utils/strings/stringpiece.h:373: a StringPiece prints as its bytes
+inline std::ostream& operator<<(std::ostream& o, const StringPiece& piece) {
+  if (piece.size() > 0) o.write(piece.data(), static_cast<std::streamsize>(piece.size()));
+  return o;
+}
+
+// supersonic/utils/logging-inl.h: the CHECK family client code uses (test/guide/join.cc). A failed check prints
+// the streamed message and aborts, as LOG(FATAL) does.
+namespace supersonic_b200_logging {
+class CheckFailure {
+ public:
+  CheckFailure(const char* file, int line, const char* what) { std::cerr << file << ":" << line << ": Check failed: " << what << " "; }
+  ~CheckFailure() { std::cerr << std::endl; abort(); }
+  std::ostream& stream() { return std::cerr; }
+};
+struct Voidify { void operator&(std::ostream&) {} };
+}  // namespace supersonic_b200_logging
+#ifndef CHECK
+#define CHECK(condition) \
+  (condition) ? (void)0 : ::supersonic_b200_logging::Voidify() & ::supersonic_b200_logging::CheckFailure(__FILE__, __LINE__, #condition).stream()
+#define CHECK_EQ(a, b) CHECK((a) == (b))
+#define CHECK_NE(a, b) CHECK((a) != (b))
+#define CHECK_LT(a, b) CHECK((a) < (b))
+#define CHECK_LE(a, b) CHECK((a) <= (b))
+#define CHECK_GT(a, b) CHECK((a) > (b))
+#define CHECK_GE(a, b) CHECK((a) >= (b))
+#define CHECK_NOTNULL(p) (p)
+#define DCHECK(condition) CHECK(condition)
+#define DCHECK_EQ(a, b) CHECK_EQ(a, b)
+#endif
 
 namespace supersonic {
 
@@ -231,7 +263,7 @@ inline void SucceedOrDie(FailureOrVoid r) { if (r.is_failure()) DieOnFailure(r.e
 // ---- DataType traits (base/infrastructure/types.h:70-249) ---------------------------------
 template <DataType type> struct TypeTraits;
 #define SSB200_TYPE_TRAITS(DT, CPP)                                      \
-  template <> struct TypeTraits<DT> { typedef CPP cpp_type; static const DataType type = DT; }
+  template <> struct TypeTraits<DT> { typedef CPP cpp_type; typedef CPP hold_type; static const DataType type = DT; }
 SSB200_TYPE_TRAITS(INT32, int32);
 SSB200_TYPE_TRAITS(INT64, int64);
 SSB200_TYPE_TRAITS(UINT32, uint32);
@@ -243,9 +275,10 @@ SSB200_TYPE_TRAITS(DATE, int32);
 SSB200_TYPE_TRAITS(DATETIME, int64);
 SSB200_TYPE_TRAITS(ENUM, int32);
 SSB200_TYPE_TRAITS(DATA_TYPE, DataType);
-SSB200_TYPE_TRAITS(STRING, StringPiece);
-SSB200_TYPE_TRAITS(BINARY, StringPiece);
 #undef SSB200_TYPE_TRAITS
+// variable-length values are held (owned) as std::string: types.h:226-249
+template <> struct TypeTraits<STRING> { typedef StringPiece cpp_type; typedef string hold_type; static const DataType type = STRING; };
+template <> struct TypeTraits<BINARY> { typedef StringPiece cpp_type; typedef string hold_type; static const DataType type = BINARY; };
 
 class TypeInfo {
  public:
@@ -466,6 +499,46 @@ class Block {
   vector<Buffer*> data_;
   vector<Buffer*> nulls_;
   vector<std::shared_ptr<const void> > storage_;
+};
+
+// base/memory/arena.h:48-110: bump allocator for variable-length values; pointers stay valid until Reset().
+class Arena {
+ public:
+  Arena(BufferAllocator* const buffer_allocator, size_t initial_buffer_size, size_t max_buffer_size);
+  Arena(size_t initial_buffer_size, size_t max_buffer_size);
+  ~Arena();
+  // Copies the bytes of `value` into the arena; NULL when the allocator refuses.
+  const char* AddStringPieceContent(const StringPiece& value);
+  void* AllocateBytes(const size_t size);
+  void Reset();
+  size_t memory_footprint() const { return footprint_; }
+ private:
+  Arena(const Arena&);
+  void operator=(const Arena&);
+  bool AddComponent(size_t at_least);
+  BufferAllocator* allocator_;
+  size_t next_size_, max_size_, footprint_;
+  vector<Buffer*> buffers_;
+  char* cursor_;
+  size_t left_;
+};
+
+// base/infrastructure/copy_column.h:30-36
+enum RowSelectorType { NO_SELECTOR = 0, INPUT_SELECTOR = 1 };
+
+// base/infrastructure/view_copier.h:89-106: copies row_count rows of input_view into output_block at
+// output_offset (the block must have the capacity). deep_copy: variable-length values are copied into storage
+// the block keeps alive, otherwise the cells keep pointing at the source's bytes. Returns the rows copied.
+class BoundSingleSourceProjector;
+class ViewCopier {
+ public:
+  ViewCopier(const TupleSchema& schema, bool deep_copy);
+  ViewCopier(const BoundSingleSourceProjector* projector, bool deep_copy);
+  rowcount_t Copy(const rowcount_t row_count, const View& input_view, const rowcount_t output_offset, Block* output_block) const;
+ private:
+  TupleSchema schema_;
+  vector<int> source_;   // input column of output column i
+  bool deep_copy_;
 };
 
 }  // namespace supersonic

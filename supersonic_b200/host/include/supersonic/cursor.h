@@ -146,17 +146,21 @@ class Table {
   rowcount_t AppendView(const View& view);
   // Appends one uninitialised row; returns its id or -1 when out of memory.
   rowid_t AddRow();
+  // Variable-length values are copied into the table's arena (table.h:120-127, 319-334).
   template <DataType type>
   void Set(int col, rowid_t row, const typename TypeTraits<type>::cpp_type& value) {
-    static_cast<typename TypeTraits<type>::cpp_type*>(block_->mutable_data(col))[row] = value;
+    static_cast<typename TypeTraits<type>::cpp_type*>(block_->mutable_data(col))[row] = Owned(value);
     if (block_->mutable_is_null(col)) block_->mutable_is_null(col)[row] = false;
   }
   void SetNull(int col, rowid_t row) { block_->mutable_is_null(col)[row] = true; }
   void Clear() { view_.set_row_count(0); }
   FailureOrOwned<Cursor> CreateCursor() const;
  private:
+  template <typename T> const T& Owned(const T& v) { return v; }
+  StringPiece Owned(const StringPiece& v) { return StringPiece(arena_.AddStringPieceContent(v), v.size()); }
   std::unique_ptr<Block> block_;
   View view_;
+  Arena arena_;
 };
 
 class TableRowWriter {
@@ -172,6 +176,8 @@ class TableRowWriter {
   TableRowWriter& Bool(bool v) { return Put<BOOL>(v); }
   TableRowWriter& Date(int32 v) { return Put<DATE>(v); }
   TableRowWriter& Datetime(int64 v) { return Put<DATETIME>(v); }
+  TableRowWriter& String(const StringPiece& v) { return Put<STRING>(v); }
+  TableRowWriter& Binary(const StringPiece& v) { return Put<BINARY>(v); }
   TableRowWriter& Null() { if (ok_) table_->SetNull(col_++, row_); return *this; }
   bool success() const { return ok_; }
   void CheckSuccess() const;
@@ -185,6 +191,10 @@ class TableRowWriter {
   int col_;
   bool ok_;
 };
+
+// cursor/core/generate.h:32-35: `count` rows of the empty schema (the input of constant-only Compute plans)
+Operation* Generate(rowcount_t count);
+FailureOrOwned<Cursor> BoundGenerate(rowcount_t count);
 
 // ---- row-wise operators ------------------------------------------------------------------
 Operation* Compute(const Expression* computation, Operation* child);                  // compute.h:32
@@ -238,8 +248,9 @@ class AggregationSpecification {
 
 class GroupAggregateOptions {
  public:
+  // aggregate.h:162-167: 16 result rows are allocated up front; the block grows as groups arrive
   GroupAggregateOptions() : memory_quota_(std::numeric_limits<size_t>::max()), enforce_quota_(false),
-                            estimated_result_row_count_(0) {}
+                            estimated_result_row_count_(16) {}
   GroupAggregateOptions* set_memory_quota(size_t q) { memory_quota_ = q; return this; }
   GroupAggregateOptions* set_enforce_quota(bool e) { enforce_quota_ = e; return this; }
   GroupAggregateOptions* set_estimated_result_row_count(size_t n) { estimated_result_row_count_ = n; return this; }
@@ -254,8 +265,15 @@ class GroupAggregateOptions {
 
 Operation* GroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
                           GroupAggregateOptions* options, Operation* child);          // aggregate.h:224
-// aggregate.h:230-250: may emit partial results under memory pressure in the reference; here the
-// aggregation always completes in HBM, which that contract allows.
+// Memory contract (aggregate_groups.cc:452-480, 490-1107): the result block lives under a soft MemoryLimit of
+// options->memory_quota() on top of the operation's allocator; it starts with estimated_result_row_count() rows
+// and fails with ERROR_MEMORY_EXCEEDED when it cannot grow. Here the groups are aggregated in HBM; the same
+// budget is applied to the result they form: more groups than max(estimated rows, quota / bytes per result row)
+// -- quota = min(memory_quota, allocator->Available()) -- fail the cursor with ERROR_MEMORY_EXCEEDED, and an
+// allocator that cannot hold the initial block (estimated rows) fails CreateCursor, as in the reference.
+// aggregate.h:230-250: BestEffortGroupAggregate may emit partial results (a key in several rows) under memory
+// pressure in the reference; here the aggregation always completes in HBM and every key comes out once, which
+// that contract allows, so the budget does not apply to it.
 Operation* BestEffortGroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
                                     GroupAggregateOptions* options, Operation* child);
 Operation* ScalarAggregate(AggregationSpecification* aggregation, Operation* child);  // aggregate.h:341

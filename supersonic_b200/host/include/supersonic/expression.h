@@ -202,6 +202,10 @@ const Expression* In(const Expression* const needle_expression, const Expression
 
 // ---- logic and control (expression/core/elementary_expressions.h:31-120) -----------------
 const Expression* CastTo(DataType to_type, const Expression* const source);
+// Whitespace at either end is accepted; invalid input: garbage (quiet) or NULL (nulling). Constants fold at bind time;
+// parsing a STRING column is refused with ERROR_NOT_IMPLEMENTED (see host/src/expression.cc).
+const Expression* ParseStringQuiet(DataType to_type, const Expression* const source);
+const Expression* ParseStringNulling(DataType to_type, const Expression* const source);
 const Expression* And(const Expression* const a, const Expression* const b);
 const Expression* Or(const Expression* const a, const Expression* const b);
 const Expression* AndNot(const Expression* const left, const Expression* const right);
@@ -268,6 +272,32 @@ FailureOrOwned<BoundExpression> BoundIf(BoundExpression* condition, BoundExpress
                                         BufferAllocator* allocator, rowcount_t max_row_count);
 FailureOrOwned<BoundExpression> BoundIfNulling(BoundExpression* condition, BoundExpression* if_true, BoundExpression* if_false,
                                                BufferAllocator* allocator, rowcount_t max_row_count);
+
+// expression/infrastructure/basic_bound_expression.h:236-244: resolves an expression that is constant after binding
+// into its value (*is_null is set when it evaluates to NULL). Does not take ownership.
+namespace internal {
+FailureOrVoid ConstantExpressionValue(const Expression& expression, DataType type, void* value, string* text, bool* is_null);
+template <typename Hold> struct ConstantHolder {
+  Hold value;
+  ConstantHolder() : value() {}
+  void* raw() { return &value; }
+  void take(const string&) {}
+};
+template <> struct ConstantHolder<string> {
+  string value;
+  void* raw() { return NULL; }
+  void take(const string& text) { value = text; }
+};
+}  // namespace internal
+template <DataType data_type>
+FailureOr<typename TypeTraits<data_type>::hold_type> GetConstantExpressionValue(const Expression& expression, bool* is_null) {
+  internal::ConstantHolder<typename TypeTraits<data_type>::hold_type> holder;
+  string text;
+  FailureOrVoid r = internal::ConstantExpressionValue(expression, data_type, holder.raw(), &text, is_null);
+  if (r.is_failure()) return Failure(r.release_exception());
+  holder.take(text);
+  return Success(holder.value);
+}
 
 }  // namespace supersonic
 #endif  // SUPERSONIC_B200_HOST_EXPRESSION_H_

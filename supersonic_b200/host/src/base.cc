@@ -253,7 +253,86 @@ bool Block::Reallocate(rowcount_t new_capacity) {
     view_.mutable_column(i)->Reset(data_[i]->data(), nulls_[i] ? static_cast<bool*>(nulls_[i]->data()) : NULL);
   }
   capacity_ = new_capacity;
+  view_.set_row_count(new_capacity);   // block.h:467,481: a block's view spans its capacity
   return true;
+}
+
+// ---- Arena (base/memory/arena.h:48-110)
+Arena::Arena(BufferAllocator* const buffer_allocator, size_t initial_buffer_size, size_t max_buffer_size)
+    : allocator_(buffer_allocator), next_size_(initial_buffer_size ? initial_buffer_size : 16),
+      max_size_(max_buffer_size < initial_buffer_size ? initial_buffer_size : max_buffer_size), footprint_(0), cursor_(NULL), left_(0) {}
+Arena::Arena(size_t initial_buffer_size, size_t max_buffer_size)
+    : allocator_(HeapBufferAllocator::Get()), next_size_(initial_buffer_size ? initial_buffer_size : 16),
+      max_size_(max_buffer_size < initial_buffer_size ? initial_buffer_size : max_buffer_size), footprint_(0), cursor_(NULL), left_(0) {}
+Arena::~Arena() { for (size_t i = 0; i < buffers_.size(); ++i) delete buffers_[i]; }
+bool Arena::AddComponent(size_t at_least) {
+  // buffers double up to max_buffer_size; a single request larger than that gets a buffer of its own
+  size_t want = next_size_ < at_least ? at_least : next_size_;
+  Buffer* b = allocator_->BestEffortAllocate(want, at_least);
+  if (b == NULL) return false;
+  buffers_.push_back(b);
+  footprint_ += b->size();
+  cursor_ = static_cast<char*>(b->data());
+  left_ = b->size();
+  if (next_size_ < max_size_) next_size_ = next_size_ * 2 > max_size_ ? max_size_ : next_size_ * 2;
+  return true;
+}
+void* Arena::AllocateBytes(const size_t size) {
+  if (size > left_ && !AddComponent(size)) return NULL;
+  void* p = cursor_;
+  cursor_ += size;
+  left_ -= size;
+  return p;
+}
+const char* Arena::AddStringPieceContent(const StringPiece& value) {
+  char* p = static_cast<char*>(AllocateBytes(value.size()));
+  if (p == NULL) return NULL;
+  if (value.size() > 0) memcpy(p, value.data(), value.size());
+  return p;
+}
+void Arena::Reset() {
+  for (size_t i = 0; i < buffers_.size(); ++i) delete buffers_[i];
+  buffers_.clear();
+  footprint_ = 0;
+  cursor_ = NULL;
+  left_ = 0;
+}
+
+// ---- ViewCopier (base/infrastructure/view_copier.h:89-106)
+ViewCopier::ViewCopier(const TupleSchema& schema, bool deep_copy) : schema_(schema), deep_copy_(deep_copy) {
+  for (int i = 0; i < schema.attribute_count(); ++i) source_.push_back(i);
+}
+rowcount_t ViewCopier::Copy(const rowcount_t row_count, const View& input_view, const rowcount_t output_offset, Block* output_block) const {
+  if (output_offset + row_count > output_block->row_capacity()) return 0;
+  for (size_t i = 0; i < source_.size(); ++i) {
+    const Column& in = input_view.column(source_[i]);
+    const DataType type = in.type_info().type();
+    const size_t w = in.type_info().size();
+    char* dst = static_cast<char*>(output_block->mutable_data(static_cast<int>(i))) + output_offset * w;
+    if (deep_copy_ && (type == STRING || type == BINARY)) {
+      const StringPiece* cells = static_cast<const StringPiece*>(in.data().raw());
+      size_t total = 0;
+      for (rowcount_t r = 0; r < row_count; ++r) if (!(in.is_null() && in.is_null()[r])) total += cells[r].size();
+      std::shared_ptr<string> bytes(new string());
+      bytes->resize(total);
+      size_t at = 0;
+      StringPiece* out = reinterpret_cast<StringPiece*>(dst);
+      for (rowcount_t r = 0; r < row_count; ++r) {
+        if (in.is_null() && in.is_null()[r]) { out[r] = StringPiece(); continue; }
+        if (cells[r].size() > 0) memcpy(&(*bytes)[at], cells[r].data(), cells[r].size());
+        out[r] = StringPiece(bytes->data() + at, cells[r].size());
+        at += cells[r].size();
+      }
+      output_block->KeepAlive(bytes);
+    } else {
+      memcpy(dst, in.data().raw(), row_count * w);
+    }
+    if (bool* nulls = output_block->mutable_is_null(static_cast<int>(i))) {
+      if (in.is_null()) memcpy(nulls + output_offset, in.is_null(), row_count);
+      else memset(nulls + output_offset, 0, row_count);
+    }
+  }
+  return row_count;
 }
 
 }  // namespace supersonic

@@ -7,7 +7,12 @@
 //   cast rules               expression/templated/cast_bound_expression.cc
 // and is checked against the reference build for every (operator, type pair) in
 // tests/test_binding.py.
+#include <ctype.h>
+#include <errno.h>
+#include <math.h>
 #include <stdio.h>
+#include <strings.h>
+#include <time.h>
 
 #include <map>
 #include <set>
@@ -919,6 +924,170 @@ const Expression* CastTo(DataType to_type, const Expression* const source) {
 const Expression* If(const Expression* const c, const Expression* const t, const Expression* const o) {
   return new FnExpression(K_IF, c, t, o);
 }
+
+// ---- ParseStringQuiet / ParseStringNulling (elementary_expressions.h:36-46) -----------------------------------
+// The parsers restate base/infrastructure/types_infrastructure.cc:154-258 (safe_strto*, the BOOL spellings, the
+// " %Y/%m/%d " and " %Y/%m/%d-%H:%M:%S " formats in UTC, times before 1970 refused). The reference folds a parse of
+// a constant at bind time (basic_bound_expression.cc:286-327); that is the form implemented here (what
+// test/guide/join.cc uses to turn date literals into DATE values). Parsing a STRING column is not on the hot path
+// (SURVEY 8f1 covers comparisons, keys and sorting) and is refused at bind time.
+namespace {
+string TrimSpaces(const string& v) {
+  size_t b = 0, e = v.size();
+  while (b < e && isspace(static_cast<unsigned char>(v[b]))) ++b;
+  while (e > b && isspace(static_cast<unsigned char>(v[e - 1]))) --e;
+  return v.substr(b, e - b);
+}
+bool ParseSigned(const string& v, int64 lo, int64 hi, int64* out) {
+  const string t = TrimSpaces(v);
+  if (t.empty()) return false;
+  errno = 0;
+  char* end = NULL;
+  const long long r = strtoll(t.c_str(), &end, 10);
+  if (errno != 0 || end != t.c_str() + t.size() || r < lo || r > hi) return false;
+  if (!(isdigit(static_cast<unsigned char>(t[0])) || ((t[0] == '-' || t[0] == '+') && t.size() > 1))) return false;
+  *out = r;
+  return true;
+}
+bool ParseUnsigned(const string& v, uint64 hi, uint64* out) {
+  const string t = TrimSpaces(v);
+  if (t.empty() || !isdigit(static_cast<unsigned char>(t[0]))) return false;   // safe_strtou*: no sign
+  errno = 0;
+  char* end = NULL;
+  const unsigned long long r = strtoull(t.c_str(), &end, 10);
+  if (errno != 0 || end != t.c_str() + t.size() || r > hi) return false;
+  *out = r;
+  return true;
+}
+bool ParseFloating(const string& v, double* out) {
+  const string t = TrimSpaces(v);
+  if (t.empty()) return false;
+  char* end = NULL;
+  *out = strtod(t.c_str(), &end);
+  return end == t.c_str() + t.size();
+}
+bool ParseBoolean(const string& v, bool* out) {
+  const string t = TrimSpaces(v);
+  if (strcasecmp(t.c_str(), "true") == 0 || strcasecmp(t.c_str(), "yes") == 0) { *out = true; return true; }
+  if (strcasecmp(t.c_str(), "false") == 0 || strcasecmp(t.c_str(), "no") == 0) { *out = false; return true; }
+  return false;
+}
+// microseconds since the epoch (UTC); `with_time`: "%Y/%m/%d-%H:%M:%S" with optional fractional seconds
+bool ParseTime(const string& v, bool with_time, int64* micros) {
+  const string t = TrimSpaces(v);
+  struct tm tm;
+  memset(&tm, 0, sizeof(tm));
+  const char* end = strptime(t.c_str(), with_time ? "%Y/%m/%d-%H:%M:%S" : "%Y/%m/%d", &tm);
+  if (end == NULL) return false;
+  double fraction = 0;
+  if (with_time && *end == '.') {
+    char* fend = NULL;
+    fraction = strtod(end, &fend);
+    end = fend;
+  }
+  if (*end != 0) return false;
+  const time_t secs = timegm(&tm);
+  if (secs < 0) return false;   // types_infrastructure.cc:222-224
+  *micros = static_cast<int64>(floor((static_cast<double>(secs) + fraction) * 1e6 + .5));
+  return true;
+}
+
+class ParseStringExpression : public Expression {
+ public:
+  ParseStringExpression(DataType to, bool nulling, const Expression* source) : to_(to), nulling_(nulling), source_(source) {}
+  virtual FailureOrOwned<BoundExpression> DoBind(const TupleSchema& input, BufferAllocator* allocator, rowcount_t max_rows) const {
+    FailureOrOwned<BoundExpression> child = source_->DoBind(input, allocator, max_rows);
+    PROPAGATE_ON_FAILURE(child);
+    if (child->column_count() != 1) {
+      THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "PARSE_STRING expects a single-column argument"));
+    }
+    const NodePtr arg = child->node(0);
+    if (arg->type != STRING) {
+      THROW(new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, "Invalid argument type (" + TypeName(arg->type) + ") to PARSE_STRING<" +
+                                                           TypeName(to_) + ">(" + arg->name + "), STRING expected"));
+    }
+    if (to_ == STRING) return Single(input, arg);
+    if (to_ == BINARY || to_ == ENUM || to_ == DATA_TYPE) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "PARSE_STRING to " + TypeName(to_)));
+    }
+    if (arg->op != SSB_OP_CONST) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "PARSE_STRING<" + TypeName(to_) + ">(" + arg->name + "): parsing a STRING column is not "
+                                                 "implemented on the device (constants are folded at bind time)"));
+    }
+    bool ok = !(arg->flags & SSB_NODE_NULL);
+    const bool source_null = !ok;
+    std::shared_ptr<ExprNode> n = NewNode(SSB_OP_CONST, to_, false, "CONST_" + TypeName(to_));
+    n->constant = true;
+    memset(&n->imm, 0, sizeof(n->imm));
+    if (ok) {
+      int64 i = 0; uint64 u = 0; double d = 0; bool b = false;
+      switch (to_) {
+        case INT32: ok = ParseSigned(arg->text, std::numeric_limits<int32>::min(), std::numeric_limits<int32>::max(), &i); n->imm.i32 = static_cast<int32>(i); break;
+        case INT64: ok = ParseSigned(arg->text, std::numeric_limits<int64>::min(), std::numeric_limits<int64>::max(), &i); n->imm.i64 = i; break;
+        case UINT32: ok = ParseUnsigned(arg->text, std::numeric_limits<uint32>::max(), &u); n->imm.u32 = static_cast<uint32>(u); break;
+        case UINT64: ok = ParseUnsigned(arg->text, std::numeric_limits<uint64>::max(), &u); n->imm.u64 = u; break;
+        case FLOAT: ok = ParseFloating(arg->text, &d); n->imm.f32 = static_cast<float>(d); break;
+        case DOUBLE: ok = ParseFloating(arg->text, &d); n->imm.f64 = d; break;
+        case BOOL: ok = ParseBoolean(arg->text, &b); n->imm.b = b; break;
+        case DATETIME: ok = ParseTime(arg->text, true, &i); n->imm.i64 = i; break;
+        case DATE: ok = ParseTime(arg->text, false, &i); n->imm.i32 = static_cast<int32>(i / (24LL * 3600LL * 1000000LL)); break;
+        default: ok = false; break;
+      }
+    }
+    if (!ok && (nulling_ || source_null)) {
+      std::shared_ptr<ExprNode> nul = NewNode(SSB_OP_CONST, to_, true, "NULL");
+      nul->constant = true;
+      nul->flags = SSB_NODE_NULL;
+      memset(&nul->imm, 0, sizeof(nul->imm));
+      return Single(input, nul);
+    }
+    if (!ok) memset(&n->imm, 0, sizeof(n->imm));   // the quiet version returns an unspecified value on invalid input
+    return Single(input, n);
+  }
+  virtual string ToString(bool verbose) const { return "PARSE_STRING<" + TypeName(to_) + ">(" + source_->ToString(verbose) + ")"; }
+ private:
+  DataType to_;
+  bool nulling_;
+  std::unique_ptr<const Expression> source_;
+};
+}  // namespace
+const Expression* ParseStringQuiet(DataType to_type, const Expression* const source) { return new ParseStringExpression(to_type, false, source); }
+const Expression* ParseStringNulling(DataType to_type, const Expression* const source) { return new ParseStringExpression(to_type, true, source); }
+
+// basic_bound_expression.h:236-244
+namespace internal {
+FailureOrVoid ConstantExpressionValue(const Expression& expression, DataType type, void* value, string* text, bool* is_null) {
+  FailureOrOwned<BoundExpressionTree> tree = expression.Bind(TupleSchema(), HeapBufferAllocator::Get(), 1);
+  PROPAGATE_ON_FAILURE(tree);
+  if (tree->result_schema().attribute_count() != 1) {
+    THROW(new Exception(ERROR_ATTRIBUTE_COUNT_MISMATCH, "Expected a single-column constant expression"));
+  }
+  if (tree->result_schema().attribute(0).type() != type) {
+    THROW(new Exception(ERROR_ATTRIBUTE_TYPE_MISMATCH, "Constant expression of type " + TypeName(tree->result_schema().attribute(0).type()) +
+                                                           " where " + TypeName(type) + " was expected"));
+  }
+  if (!tree->is_constant()) THROW(new Exception(ERROR_INVALID_ARGUMENT_VALUE, "The expression does not resolve to a constant"));
+  const NodePtr node = tree->root()->node(0);
+  const size_t width = GetTypeInfo(type).size();
+  if (node->op == SSB_OP_CONST) {   // a literal, or a sub-tree folded at bind time
+    *is_null = (node->flags & SSB_NODE_NULL) != 0;
+    if (type == STRING || type == BINARY) *text = node->text;
+    else memcpy(value, &node->imm, width);
+    return Success();
+  }
+  // anything else is evaluated by the device for one row
+  View input((TupleSchema()));
+  input.set_row_count(1);
+  EvaluationResult r = tree->Evaluate(input);
+  PROPAGATE_ON_FAILURE(r);
+  const Column& c = r.get().column(0);
+  *is_null = c.is_null() != NULL && c.is_null()[0];
+  if (*is_null) return Success();
+  if (type == STRING || type == BINARY) *text = static_cast<const StringPiece*>(c.data().raw())[0].as_string();
+  else memcpy(value, c.data().raw(), width);
+  return Success();
+}
+}  // namespace internal
 const Expression* NullingIf(const Expression* const c, const Expression* const t, const Expression* const o) {
   return new FnExpression(K_NULLING_IF, c, t, o);
 }

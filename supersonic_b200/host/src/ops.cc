@@ -1000,7 +1000,17 @@ class GroupCursor : public GpuCursor {
   GroupCursor(const TupleSchema& schema, BufferAllocator* allocator, Cursor* child, const vector<int>& keys,
               const vector<BoundAggregation>& aggs, size_t estimated_groups, bool scalar)
       : GpuCursor(schema, allocator, scalar ? "ScalarAggregateCursor" : "GroupAggregateCursor"), child_(child),
-        keys_(keys), aggs_(aggs), estimated_groups_(estimated_groups), scalar_(scalar), group_(NULL) {}
+        keys_(keys), aggs_(aggs), estimated_groups_(estimated_groups), scalar_(scalar), group_(NULL),
+        quota_(std::numeric_limits<size_t>::max()), budgeted_(false) {}
+  // The reference's memory contract for the result block (see cursor.h at GroupAggregate).
+  void SetResultBudget(size_t memory_quota) { quota_ = memory_quota; budgeted_ = true; }
+  static size_t ResultRowBytes(const TupleSchema& schema) {
+    size_t bytes = 0;
+    for (int i = 0; i < schema.attribute_count(); ++i) {
+      bytes += GetTypeInfo(schema.attribute(i).type()).size() + (schema.attribute(i).is_nullable() ? 1 : 0);
+    }
+    return bytes ? bytes : 1;
+  }
   // The child is a chain of row-wise operators (Filter / Compute / Project over a scan): its
   // plan is evaluated inside the aggregation kernel (ssb_group_update_program), nothing is
   // materialised between the two operators.
@@ -1106,6 +1116,16 @@ class GroupCursor : public GpuCursor {
     int64_t n_groups = 0;
     vector<ssb_column> kout(keys_.size() ? keys_.size() : 1), aout(specs.size() ? specs.size() : 1);
     SSB_CALL(s, ssb_group_finalize(group_, &n_groups, kout.data(), aout.data()), "group-by finalize");
+    if (budgeted_) {
+      const size_t quota = std::min(quota_, allocator()->Available());
+      const size_t rows_allowed = std::max<size_t>(estimated_groups_, quota / ResultRowBytes(schema()));
+      if (static_cast<size_t>(n_groups) > rows_allowed) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "Can't allocate the result block of GroupAggregate: %lld groups, %zu rows fit the memory quota",
+                 static_cast<long long>(n_groups), rows_allowed);
+        THROW(new Exception(ERROR_MEMORY_EXCEEDED, buf));
+      }
+    }
     result->schema = schema();
     result->columns.clear();
     for (size_t k = 0; k < keys_.size(); ++k) {
@@ -1175,6 +1195,8 @@ class GroupCursor : public GpuCursor {
   size_t estimated_groups_;
   bool scalar_;
   ssb_group* group_;
+  size_t quota_;
+  bool budgeted_;
 };
 
 FailureOrVoid GatherColumns(Session* s, const DeviceTable& src, const vector<int>& positions, const int64_t* d_idx,
@@ -1376,8 +1398,8 @@ class ConcatCursor : public GpuCursor {
 class GroupAggregateOperation : public BasicOperation {
  public:
   GroupAggregateOperation(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
-                          GroupAggregateOptions* options, Operation* child)
-      : BasicOperation(child), group_by_(group_by), aggregation_(aggregation), options_(options) {}
+                          GroupAggregateOptions* options, Operation* child, bool best_effort = false)
+      : BasicOperation(child), group_by_(group_by), aggregation_(aggregation), options_(options), best_effort_(best_effort) {}
   virtual FailureOrOwned<Cursor> CreateCursor() const {
     FailureOrOwned<Cursor> child_cursor = child()->CreateCursor();
     PROPAGATE_ON_FAILURE(child_cursor);
@@ -1394,8 +1416,15 @@ class GroupAggregateOperation : public BasicOperation {
     }
     vector<BoundAggregation> aggs;
     PROPAGATE_ON_FAILURE(BindAggregations(*aggregation_, cs, &aggs, &result));
-    const size_t est = options_ ? options_->estimated_result_row_count() : 0;
+    const size_t est = options_ ? options_->estimated_result_row_count() : 16;
+    // aggregate_groups.cc:465-469: the aggregator's first block comes out of the operation's allocator at bind time
+    if (group_by_ != NULL && buffer_allocator()->Available() / GroupCursor::ResultRowBytes(result) < std::max<size_t>(est, 1)) {
+      THROW(new Exception(ERROR_MEMORY_EXCEEDED, "Can't allocate the result block of GroupAggregate (allocator exhausted)"));
+    }
     GroupCursor* cursor = new GroupCursor(result, buffer_allocator(), child_cursor.release(), keys, aggs, est, group_by_ == NULL);
+    if (group_by_ != NULL && !best_effort_) {
+      cursor->SetResultBudget(options_ ? options_->memory_quota() : std::numeric_limits<size_t>::max());
+    }
     // A row-wise child that filters or computes is evaluated inside the aggregation kernel.
     RowwisePlan plan;
     Exception* describe_error = NULL;
@@ -1418,6 +1447,7 @@ class GroupAggregateOperation : public BasicOperation {
   std::unique_ptr<const SingleSourceProjector> group_by_;
   std::unique_ptr<AggregationSpecification> aggregation_;
   std::unique_ptr<GroupAggregateOptions> options_;
+  bool best_effort_;
 };
 
 // ------------------------------------------------------------------ gather helper
@@ -1926,7 +1956,7 @@ FailureOrOwned<Cursor> BoundSort(const BoundSortOrder* sort_order, const BoundSi
 
 Operation* BestEffortGroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
                                     GroupAggregateOptions* options, Operation* child) {
-  return new GroupAggregateOperation(group_by, aggregation, options, child);
+  return new GroupAggregateOperation(group_by, aggregation, options, child, /* best effort */ true);
 }
 Operation* SortWithTempDirPrefix(const SortOrder* sort_order, const SingleSourceProjector* result_projector,
                                  size_t memory_limit, StringPiece, Operation* child) {
@@ -2104,9 +2134,21 @@ FailureOrOwned<Cursor> HashJoinOperation::CreateCursor() const {
                                                          rhs_key_uniqueness_, lkeys, rkeys, proj.release())));
 }
 
+// ------------------------------------------------------------------ Generate (cursor/core/generate.cc)
+Operation* Generate(rowcount_t count) {
+  View v((TupleSchema()));
+  v.set_row_count(count);
+  return ScanView(v);
+}
+FailureOrOwned<Cursor> BoundGenerate(rowcount_t count) {
+  View v((TupleSchema()));
+  v.set_row_count(count);
+  return Success(BoundScanView(v));
+}
+
 // ------------------------------------------------------------------ Table
 Table::Table(const TupleSchema& schema, BufferAllocator* allocator)
-    : block_(new Block(schema, allocator)), view_(schema) {}
+    : block_(new Block(schema, allocator)), view_(schema), arena_(allocator, 4096, 1 << 20) {}
 Table::~Table() {}
 bool Table::ReserveRowCapacity(rowcount_t needed) {
   if (needed <= block_->row_capacity()) return true;
@@ -2126,16 +2168,9 @@ rowid_t Table::AddRow() {
 rowcount_t Table::AppendView(const View& view) {
   const rowcount_t rows = view_.row_count(), n = view.row_count();
   if (!ReserveRowCapacity(rows + n)) return 0;
-  for (int c = 0; c < view.column_count(); ++c) {
-    const size_t w = view.column(c).type_info().size();
-    memcpy(static_cast<char*>(block_->mutable_data(c)) + rows * w, view.column(c).data().raw(), n * w);
-    if (bool* hn = block_->mutable_is_null(c)) {
-      if (view.column(c).is_null()) memcpy(hn + rows, view.column(c).is_null(), n);
-      else memset(hn + rows, 0, n);
-    }
-  }
-  view_.ResetFromSubRange(block_->view(), 0, rows + n);
-  return n;
+  const rowcount_t copied = ViewCopier(schema(), /* deep copy */ true).Copy(n, view, rows, block_.get());
+  view_.ResetFromSubRange(block_->view(), 0, rows + copied);
+  return copied;
 }
 FailureOrOwned<Cursor> Table::CreateCursor() const { return Success(static_cast<Cursor*>(new ViewCursor(view_))); }
 

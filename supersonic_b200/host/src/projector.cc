@@ -17,6 +17,12 @@ void BoundSingleSourceProjector::Project(const View& source, View* target) const
   }
   target->set_row_count(source.row_count());
 }
+// view_copier.h:95-97: copies the projected columns
+ViewCopier::ViewCopier(const BoundSingleSourceProjector* projector, bool deep_copy)
+    : schema_(projector->result_schema()), deep_copy_(deep_copy) {
+  for (int i = 0; i < schema_.attribute_count(); ++i) source_.push_back(projector->source_attribute_position(i));
+}
+
 bool BoundSingleSourceProjector::IsAttributeProjected(int source_position) const {
   for (size_t i = 0; i < positions_.size(); ++i) if (positions_[i] == source_position) return true;
   return false;

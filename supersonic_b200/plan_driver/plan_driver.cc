@@ -209,6 +209,8 @@ const Expression* BuildExpr(const Sx& s) {
   if (h == "null") { Arity(s, 1); return Null(ParseType(Atom(s.kids[1]))); }
   if (h == "sequence") { Arity(s, 0); return Sequence(); }
   if (h == "cast") { Arity(s, 2); return CastTo(ParseType(Atom(s.kids[1])), BuildExpr(s.kids[2])); }
+  if (h == "parse_string_nulling") { Arity(s, 2); return ParseStringNulling(ParseType(Atom(s.kids[1])), BuildExpr(s.kids[2])); }
+  if (h == "parse_string_quiet") { Arity(s, 2); return ParseStringQuiet(ParseType(Atom(s.kids[1])), BuildExpr(s.kids[2])); }
   if (h == "as") { Arity(s, 2); return Alias(Atom(s.kids[1]), BuildExpr(s.kids[2])); }
   if (h == "if") {
     Arity(s, 3);
@@ -378,6 +380,23 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
     const SingleSourceProjector* p = BuildProjector(s.kids[1]);
     AggregationSpecification* a = BuildAggs(s.kids[2]);
     return GroupAggregate(p, a, NULL, BuildOp(s.kids[3], in));
+  }
+  if (h == "group_opts") {
+    // (group_opts <memory quota | none> <estimated result rows | none> <best effort: 0 | 1> <allocator quota | none> proj aggs child)
+    Arity(s, 7);
+    GroupAggregateOptions* options = new GroupAggregateOptions();
+    if (Atom(s.kids[1]) != "none") options->set_memory_quota(static_cast<size_t>(strtoull(Atom(s.kids[1]).c_str(), NULL, 10)));
+    if (Atom(s.kids[2]) != "none") options->set_estimated_result_row_count(static_cast<size_t>(strtoull(Atom(s.kids[2]).c_str(), NULL, 10)));
+    const bool best_effort = Atom(s.kids[3]) == "1";
+    const SingleSourceProjector* p = BuildProjector(s.kids[5]);
+    AggregationSpecification* a = BuildAggs(s.kids[6]);
+    Operation* child = BuildOp(s.kids[7], in);
+    Operation* op = best_effort ? BestEffortGroupAggregate(p, a, options, child) : GroupAggregate(p, a, options, child);
+    if (Atom(s.kids[4]) != "none") {
+      // lives as long as the process: operations keep a bare pointer to their allocator
+      op->SetBufferAllocator(new MemoryLimit(static_cast<size_t>(strtoull(Atom(s.kids[4]).c_str(), NULL, 10)), HeapBufferAllocator::Get()), false);
+    }
+    return op;
   }
   if (h == "scalar_agg") {
     Arity(s, 2);

@@ -329,6 +329,18 @@ GOLDEN_STRINGS = [
     ("str_is_null_and_project", "(filter (not (is_null (col s))) (named s) (compute (compound (col s) (as n (plus (col v) (i32 1)))) (scan 0)))",
      [[ncol("s", S, ["q", N, "w"]), col("v", sp.INT32, [1, 2, 3])]], {"s": ["q", "w"]}, True),
     ("str_empty_table", "(group (named s) (aggs (COUNT \"\" n)) (scan 0))", [[col("s", S, [])]], {"s": [], "n": []}, True),
+    # expression/core/elementary_expressions.h:36-46 ParseStringQuiet / ParseStringNulling over literals (the form
+    # test/guide/join.cc:316-329 uses); parsers of base/infrastructure/types_infrastructure.cc:154-258: whitespace at
+    # either end accepted, " %Y/%m/%d " dates in days since 1970 (earlier dates refused), invalid input -> NULL
+    ("parse_string_constants",
+     "(compute (compound (as d (parse_string_nulling DATE (str \"1991/01/01\"))) (as bad (parse_string_nulling DATE (str \"Mort\")))"
+     " (as old (parse_string_nulling DATE (str \"1929/01/01\"))) (as i (parse_string_quiet INT32 (str \" 42 \")))"
+     " (as u (parse_string_nulling UINT32 (str \"-1\"))) (as f (parse_string_nulling DOUBLE (str \"2.5\")))"
+     " (as b (parse_string_nulling BOOL (str \"Yes\"))) (as t (parse_string_nulling DATETIME (str \"2001/02/03-04:05:06\")))"
+     " (as k (col k))) (scan 0))",
+     [[col("k", sp.INT32, [1, 2])]],
+     {"d": [7670, 7670], "bad": [N, N], "old": [N, N], "i": [42, 42], "u": [N, N], "f": [2.5, 2.5], "b": [True, True],
+      "t": [981173106000000, 981173106000000], "k": [1, 2]}, True),
 ]
 
 

@@ -32,12 +32,34 @@ class Message {
   std::ostringstream os_;
 };
 inline void InitGoogleTest(int*, char**) {}
+// Fixture base of TEST_F: a fresh object per test, SetUp() before and TearDown() after the body.
+class Test {
+ public:
+  virtual ~Test() {}
+ protected:
+  Test() {}
+  virtual void SetUp() {}
+  virtual void TearDown() {}
+  virtual void TestBody() = 0;
+ public:
+  void Run() { SetUp(); TestBody(); TearDown(); }
+};
 }  // namespace testing
 
 #define TEST(suite, name)                                                              \
   static void suite##_##name##_body();                                                 \
   static ::testing::Registrar suite##_##name##_reg(#suite, #name, &suite##_##name##_body); \
   static void suite##_##name##_body()
+
+#define TEST_F(fixture, name)                                                          \
+  class fixture##_##name##_Test : public fixture {                                     \
+   public:                                                                             \
+    fixture##_##name##_Test() {}                                                       \
+    virtual void TestBody();                                                           \
+    static void RunIt() { fixture##_##name##_Test t; t.Run(); }                        \
+  };                                                                                   \
+  static ::testing::Registrar fixture##_##name##_reg(#fixture, #name, &fixture##_##name##_Test::RunIt); \
+  void fixture##_##name##_Test::TestBody()
 
 #define SSB_GT_CHECK(cond, text) ::testing::Message(!(cond), __FILE__, __LINE__, text)
 #define EXPECT_TRUE(c) SSB_GT_CHECK((c), "expected true: " #c)

@@ -40,7 +40,7 @@ def test_q1_plan_compiles_to_an_sm100a_cubin(built):
     assert rc == 0, text[-4000:]
     assert size > 10000
     # the generated prelude: one X-macro line per input column, instruction and aggregate
-    assert "enum { T = 128, R = 2, G = 6" in text and "N_IN = 7" in text and "NK = 2, A = 6" in text
+    assert "enum { T = 192, R = 1, G = 6" in text and "N_IN = 7" in text and "NK = 2, A = 6" in text
     assert text.count("\n  X(") == 7 + 6 + text.split("#define SSB_JIT_PROGRAM(X)")[1].split("#define")[0].count("\n  X(")
     assert '#include "jit_rows.h"' in text
 

@@ -561,3 +561,43 @@ def test_bound_expression_factories_and_do_evaluate(ref, b200):
                  b200.run('(bound_bx_filter (equal (col s) (str "ab")) (named s a) (bound_scan 0))', t))
     fails = "(bx_evaluate (cpp_divide_signaling (col a) (minus (col a) (col a))) 0)"
     assert ref.run(fails, t).code == b200.run(fails, t).code == sp.ERROR_EVALUATION_ERROR
+
+
+# GroupAggregate's memory contract (aggregate_groups.cc:452-480; aggregate_groups_test.cc:538-573, 849-870): the result
+# block starts with estimated_result_row_count rows under a soft quota and fails with ERROR_MEMORY_EXCEEDED when it cannot
+# grow; BestEffortGroupAggregate never fails for lack of memory (it may emit a key in several rows).
+BUDGET_TABLE = [[sp.Column("col0", sp.INT32, [1, 3, 1, 3]), sp.Column("col1", sp.INT32, [3, -3, 4, -5])]]
+BUDGET_PLANS = [
+    "(group_opts 1 1 0 none (named col0) (aggs (SUM col1 sum)) (scan 0))",       # :551-573 quota for one row, two groups
+    "(group_opts none 2 0 none (named col0) (aggs (SUM col1 sum)) (scan 0))",    # :575-600 the block grows
+    "(group_opts 64 1 0 none (named col0) (aggs (SUM col1 sum)) (scan 0))",      # quota for seven rows
+    "(group_opts none none 0 0 (named) (aggs (SUM col0 sum)) (scan 0))",         # :538-549 MemoryLimit(0): bind fails
+    "(group_opts none none 0 16 (named col0) (aggs (SUM col1 sum)) (scan 0))",   # allocator too small for the first block
+    "(group_opts none none 0 4096 (named col0) (aggs (SUM col1 sum)) (scan 0))",
+]
+
+
+@pytest.mark.parametrize("plan", BUDGET_PLANS)
+def test_group_aggregate_memory_budget_matches_the_reference(ref, b200, plan):
+    a, b = ref.run(plan, BUDGET_TABLE), b200.run(plan, BUDGET_TABLE)
+    assert a.code == b.code, (plan, a.code, b.code, b.error)
+    if a.code == 0:
+        same_results(a, b, ordered=False)
+    else:
+        assert a.code == 102
+
+
+def test_best_effort_group_aggregate_never_runs_out_of_memory(ref, b200):
+    """With room for one result row the reference emits partial results (every input row on its own here); the GPU
+    cursor aggregates in HBM and emits every key once. Both are valid best-effort outputs: re-aggregated they agree."""
+    plan = "(group_opts 1 1 1 none (named col0) (aggs (SUM col1 sum)) (scan 0))"
+    a, b = ref.run(plan, BUDGET_TABLE), b200.run(plan, BUDGET_TABLE)
+    assert a.code == 0 and b.code == 0, (a.code, b.code, b.error)
+
+    def totals(r):
+        out = {}
+        for k, v in zip(r.columns[0], r.columns[1]):
+            out[int(k)] = out.get(int(k), 0) + int(v)
+        return out
+    assert totals(a) == totals(b) == {1: 7, 3: -8}
+    assert b.rows == 2

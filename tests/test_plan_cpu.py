@@ -129,3 +129,19 @@ def test_wide_plan_degrades_stage_by_stage(built):
     # more budget buys stages, never a different program
     big = capi.plan(nodes, types, [0] * 12, outs, tile=384, smem_budget=227 * 1024)
     assert big.stages > q.stages and big.n_insn == q.n_insn
+
+
+def test_group_aggregate_bind_time_memory_budget(ref, b200):
+    """aggregate_groups.cc:465-469: the aggregator's first block (estimated_result_row_count rows) comes out of the
+    operation's allocator at CreateCursor; an allocator that cannot hold it fails the bind with ERROR_MEMORY_EXCEEDED
+    (aggregate_groups_test.cc:538-549). Checked without a GPU: SSPLAN_BIND_ONLY stops after CreateCursor."""
+    table = [[sp.Column("col0", sp.INT32, [1, 3, 1, 3]), sp.Column("col1", sp.INT32, [3, -3, 4, -5])]]
+    for plan, want in [("(group_opts none none 0 0 (named) (aggs (SUM col0 sum)) (scan 0))", 102),
+                       ("(group_opts none none 0 0 (named col0) (aggs (SUM col1 sum)) (scan 0))", 102),
+                       ("(group_opts none none 0 16 (named col0) (aggs (SUM col1 sum)) (scan 0))", 102),
+                       ("(group_opts none none 0 4096 (named col0) (aggs (SUM col1 sum)) (scan 0))", 0),
+                       ("(group_opts 1 1 0 none (named col0) (aggs (SUM col1 sum)) (scan 0))", 0),
+                       ("(group_opts 1 1 1 none (named col0) (aggs (SUM col1 sum)) (scan 0))", 0)]:
+        a = ref.run(plan, table, flags=sp.SSPLAN_BIND_ONLY)
+        b = b200.run(plan, table, flags=sp.SSPLAN_BIND_ONLY)
+        assert a.code == b.code == want, (plan, a.code, b.code)

@@ -251,6 +251,9 @@ int ssb_group_update_program(ssb_group* g, ssb_program* prog, const ssb_column* 
  * expression/vector/vector_primitives.h, expression/templated/bound_expression_factory.h). This entry compiles the
  * kernel of one plan the same way and returns the generated source (or the compiler log) in `text`; `groups` =
  * CTA-local group entries (1..8), threads / rows_per_thread 0 = the defaults. */
+/* Process-wide counters of the run-time compiled kernels: distinct kernels compiled and loaded, the time that took
+ * (NVRTC + cudaLibraryLoadData, milliseconds), and how many times such a kernel was launched. */
+void ssb_jit_stats(int64_t* kernels_compiled, double* compile_ms, int64_t* launches);
 int ssb_jit_rows_compile(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs, const int32_t* input_types,
                          const int32_t* input_nullable, const int32_t* outputs, int32_t n_outputs, int32_t predicate,
                          int32_t n_keys, int32_t n_aggs, const ssb_agg_spec* aggs, int32_t groups, int32_t threads,

@@ -104,6 +104,7 @@ def load():
         "ssb_group_destroy": (None, [P]),
         "ssb_group_update": (C.c_int, [P, C.POINTER(Column), C.POINTER(Column), I64]),
         "ssb_group_update_program": (C.c_int, [P, P, C.POINTER(Column), I64]),
+        "ssb_jit_stats": (None, [C.POINTER(I64), C.POINTER(C.c_double), C.POINTER(I64)]),
         "ssb_jit_rows_compile": (C.c_int, [C.POINTER(ExprNode), C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(AggSpec),
                                            C.c_int32, C.c_int32, C.c_int32, C.c_char_p, I64, C.POINTER(I64)]),

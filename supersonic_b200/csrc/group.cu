@@ -1375,6 +1375,7 @@ static int feed_slice(ssb_group* g, const ssb_column* keys, const ssb_column* va
       JitRun run = jit->run;
       void* args[] = {&p, &run};
       cudaLaunchKernel(fn, dim3(static_cast<unsigned>(ctas)), dim3(static_cast<unsigned>(jit->shape.threads)), args, smem, ctx->stream);
+      jit_note_launch();
     } else if (fused != nullptr) {
       cudaFuncSetAttribute(group_update_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fused_smem));
       long long per_sm = static_cast<long long>((ctx->smem_per_sm - 8192) / (fused_smem + 8192));

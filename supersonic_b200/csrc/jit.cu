@@ -74,6 +74,8 @@ Nvrtc* nvrtc() {
 
 struct CacheEntry { JitKernel k; };
 std::mutex g_mu;
+long long g_compiled = 0, g_launches = 0;
+double g_compile_ms = 0;
 std::map<std::string, CacheEntry>* cache() {
   static std::map<std::string, CacheEntry>* c = new std::map<std::string, CacheEntry>();
   return c;
@@ -214,15 +216,28 @@ int jit_get_kernel(ssb_ctx* ctx, const std::string& source, const char* name, Ji
     fprintf(stderr, "[ssb200] jit: %s in %.0f ms, %d registers per thread%s%s\n", rc == 0 ? "compiled" : "FAILED", e.k.compile_ms, e.k.regs,
             log.size() > 1 ? "\n" : "", log.size() > 1 ? log.c_str() : "");
   }
+  if (rc == 0) { ++g_compiled; g_compile_ms += e.k.compile_ms; }
   (*cache())[source] = e;   // failures are cached too: the caller falls back to the interpreting kernels once, not per call
   *out = e.k;
   if (rc != 0) { ctx->last_error = "jit: " + log; return rc; }
   return 0;
 }
 
+void jit_note_launch() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  ++g_launches;
+}
+
 }  // namespace ssb
 
 extern "C" {
+
+void ssb_jit_stats(int64_t* kernels_compiled, double* compile_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lock(ssb::g_mu);
+  if (kernels_compiled) *kernels_compiled = ssb::g_compiled;
+  if (compile_ms) *compile_ms = ssb::g_compile_ms;
+  if (launches) *launches = ssb::g_launches;
+}
 
 // Test / tooling entry (no device needed): compiles the specialised aggregation kernel of a plan to an sm_100a cubin.
 int ssb_jit_rows_compile(const ssb_expr_node* nodes, int32_t n_nodes, int32_t n_inputs, const int32_t* input_types,

@@ -37,5 +37,8 @@ int jit_compile(const std::string& source, std::vector<char>* cubin, std::string
 // Compiled and loaded once per distinct source and process; later calls return the cached kernel.
 int jit_get_kernel(ssb_ctx* ctx, const std::string& source, const char* name, JitKernel* out);
 
+// Counts a launch of a compiled kernel (ssb_jit_stats).
+void jit_note_launch();
+
 }  // namespace ssb
 #endif  // SSB_CSRC_JIT_H_

@@ -124,7 +124,7 @@ enum JoinType { INNER = 0, LEFT_OUTER = 1, RIGHT_OUTER = 2, FULL_OUTER = 3 };
 enum KeyUniqueness { NOT_UNIQUE = 0, UNIQUE = 1 };
 // supersonic/cursor/proto/cursors.proto:13-62 (the ids this implementation reports)
 enum CursorId {
-  VIEW = 7, AGGREGATE_CLUSTERS = 8, COMPUTE = 15, FILTER = 16, GROUP_AGGREGATE = 20, HASH_JOIN = 21, MERGE_UNION_ALL = 24, PROJECT = 27,
+  FILE_INPUT = 3, VIEW = 7, AGGREGATE_CLUSTERS = 8, COMPUTE = 15, FILTER = 16, GROUP_AGGREGATE = 20, HASH_JOIN = 21, MERGE_UNION_ALL = 24, PROJECT = 27,
   SCALAR_AGGREGATE = 30, SORT = 32, UNKNOWN_ID = 99
 };
 

@@ -46,6 +46,9 @@
 #include "supersonic/supersonic.h"
 #include "supersonic/cursor/core/aggregator.h"
 #include "supersonic/cursor/core/merge_union_all.h"
+#include "supersonic/cursor/infrastructure/file_io.h"
+#include "supersonic/cursor/infrastructure/writer.h"
+#include "supersonic/utils/file.h"
 #include "supersonic/expression/core/arithmetic_bound_expressions.h"
 #include "supersonic/expression/core/comparison_bound_expressions.h"
 #include "supersonic/expression/core/elementary_bound_expressions.h"
@@ -566,6 +569,14 @@ Cursor* BuildCursor(const Sx& s, const Inputs& in, Keep* keep) {
     const BoundSingleSourceProjector* bp = Take(p->Bind(child->schema()));
     return Take(BoundFilter(tree.release(), bp, heap, child.release()));
   }
+  if (h == "bound_file_read") {
+    // (bound_file_read PATH N): FileInput over a file holding rows of table N's schema, as the source of a cursor tree
+    Arity(s, 2);
+    size_t n = static_cast<size_t>(atoi(Atom(s.kids[2]).c_str()));
+    if (n >= in.views.size()) throw ParseError{"bound_file_read: no such table"};
+    if (!File::Exists(Atom(s.kids[1]))) throw BindError{ERROR_GENERAL_IO_ERROR, "no such file: " + Atom(s.kids[1])};
+    return Take(FileInput(in.views[n].schema(), File::OpenOrDie(Atom(s.kids[1]), "r"), false, heap));
+  }
   if (h == "bound_scan") {
     Arity(s, 1);
     size_t n = static_cast<size_t>(atoi(Atom(s.kids[1]).c_str()));
@@ -863,7 +874,33 @@ int ssplan_run(const char* plan, int32_t ntables, const ssplan_table* tables,
     Sx sx = SxParser(plan).Parse();
     if (Head(sx) == "evaluate") return RunEvaluate(sx, in, flags, r);
     if (Head(sx) == "bx_evaluate") return RunBoundEvaluate(sx, in, flags, r);
-    if (Head(sx).compare(0, 6, "bound_") == 0) {
+    if (Head(sx) == "file_write" || Head(sx) == "file_read") {
+      // (file_write PATH <operation>): the operation's rows are written in the reference's block format
+      // (cursor/infrastructure/file_io.h: WriteCursor into FileOutput), then the file is scanned back (FileInput);
+      // (file_read PATH N): scans a file that holds rows of table N's schema.
+      Arity(sx, 2);
+      const std::string path = Atom(sx.kids[1]);
+      TupleSchema schema;
+      if (Head(sx) == "file_write") {
+        std::unique_ptr<Operation> source(BuildOp(sx.kids[2], in));
+        FailureOrOwned<Cursor> created = source->CreateCursor();
+        if (created.is_failure()) throw BindError{created.exception().return_code(), created.exception().message()};
+        schema = created->schema();
+        std::unique_ptr<Sink> sink(FileOutput(File::OpenOrDie(path, "w"), TAKE_OWNERSHIP));
+        FailureOrVoid written = WriteCursor(created.release(), sink.get());
+        FailureOrVoid finalized = sink->Finalize();   // closes the file
+        if (written.is_failure()) throw BindError{written.exception().return_code(), written.exception().message()};
+        if (finalized.is_failure()) throw BindError{finalized.exception().return_code(), finalized.exception().message()};
+      } else {
+        const size_t n = static_cast<size_t>(atoi(Atom(sx.kids[2]).c_str()));
+        if (n >= in.views.size()) throw ParseError{"file_read: no such table"};
+        schema = in.views[n].schema();
+      }
+      if (!File::Exists(path)) throw BindError{ERROR_GENERAL_IO_ERROR, "no such file: " + path};
+      FailureOrOwned<Cursor> scan = FileInput(schema, File::OpenOrDie(path, "r"), false, HeapBufferAllocator::Get());
+      if (scan.is_failure()) throw BindError{scan.exception().return_code(), scan.exception().message()};
+      cursor.reset(scan.release());
+    } else if (Head(sx).compare(0, 6, "bound_") == 0) {
       t0 = WallNow();
       cursor.reset(BuildCursor(sx, in, &keep));
       r->create_s = WallNow() - t0;

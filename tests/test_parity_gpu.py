@@ -601,3 +601,32 @@ def test_best_effort_group_aggregate_never_runs_out_of_memory(ref, b200):
         return out
     assert totals(a) == totals(b) == {1: 7, 3: -8}
     assert b.rows == 2
+
+
+def test_cursor_trees_over_a_file_scan_match_the_reference(ref, b200, tmp_path):
+    """rows arrive from outside the process in the reference's block format (file_io.cc:70-420). The file
+    is written by the REFERENCE's FileOutput; FileInput (a CPU cursor of <= 8192-row chunks) then feeds the GPU cursors
+    through Next(), and the results must equal the reference's over the same file."""
+    rng = np.random.default_rng(7)
+    rows = 30000
+    words = ["ab", "", "Supersonic", "B200", "columnar"]
+    table = [[sp.Column("k", sp.INT64, rng.integers(0, 50, rows)),
+              sp.Column("a", sp.INT64, rng.integers(-1000, 1000, rows), is_null=rng.random(rows) < 0.1),
+              sp.Column("x", sp.DOUBLE, rng.integers(0, 1 << 16, rows) / 4.0),
+              sp.Column("s", sp.STRING, [words[i] for i in rng.integers(0, len(words), rows)])]]
+    path = str(tmp_path / "rows.ssb")
+    assert ref.run("(file_write %s (scan 0))" % path, table).code == 0
+    src = "(bound_file_read %s 0)" % path
+    plans = [("(bound_filter (less (col a) (i64 10)) (named k x s) %s)" % src, True),
+             ("(bound_compute (compound (as e (plus (col a) (col k))) (col s)) %s)" % src, True),
+             ("(bound_group (named k) (aggs (SUM x sx) (COUNT a ca) (MIN a mn) (COUNT \"\" n)) %s)" % src, False),
+             ("(bound_group (named s) (aggs (SUM x sx) (MAX a mx)) %s)" % src, False),
+             ("(bound_sort (order (s ASC) (k DESC) (x ASC) (a ASC)) (all) %s)" % src, True)]
+    for plan, ordered in plans:
+        same_results(ref.run(plan, table), b200.run(plan, table), ordered=ordered)
+    # and back out: the GPU result written by the mirror's FileOutput is what the reference writes for its own result
+    fa, fb = str(tmp_path / "a.ssb"), str(tmp_path / "b.ssb")
+    plan = "(sort (order (k ASC) (x ASC) (a ASC) (s ASC)) (all) (filter (less (col a) (i64 10)) (all) (scan 0)))"
+    assert ref.run("(file_write %s %s)" % (fa, plan), table).code == 0
+    assert b200.run("(file_write %s %s)" % (fb, plan), table).code == 0
+    assert open(fa, "rb").read() == open(fb, "rb").read()

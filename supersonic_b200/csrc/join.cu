@@ -14,6 +14,7 @@
 // Rows with a NULL in any key column never match (hash_join.cc:67-76,616-617,755-756).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -41,7 +42,16 @@ struct JoinTable {
   unsigned long long* run_start;  // [capacity] offset into run_rows
   unsigned int* run_count;        // [capacity]
   long long* run_rows;            // build rows grouped by slot, insertion order
+  // Dense integer keys (UNIQUE, one integer key column whose values span at most 4 x rows, e.g. a surrogate primary
+  // key): no hashing and no slots, dense_rows[key - dense_min] = smallest build row with that key (kDenseEmpty = none).
+  // 4 bytes per key value instead of a 16-byte slot at load 0.25-0.5: the C4 table is 50 MB (L2 resident) instead of
+  // 537 MB, and a probe is one 4-byte load.
+  unsigned int* dense_rows;
+  unsigned int* dense_present;   // bit (key - dense_min): the key has a build row (range / 8 bytes: stays in L2)
+  long long dense_min;
+  unsigned long long dense_range;
 };
+enum : unsigned int { kDenseEmpty = 0xffffffffu };
 
 // The replicated form of the sharded join: the build side is hash-partitioned over the
 // ranks, every rank builds the table of its part, the tables are all-gathered, and a probe looks a
@@ -157,6 +167,55 @@ __global__ void __launch_bounds__(256) join_build_kernel(JoinTable t, JoinKeys b
   }
 }
 
+// Smallest and largest key of the build side (NULL keys skipped), as signed 64-bit values (the sign- / zero-extended
+// containers of jload): mm[0] = min, mm[1] = max, mm[2] = number of non-NULL keys.
+__global__ void __launch_bounds__(256) join_minmax_kernel(JoinKeys build, long long rows, long long* __restrict__ mm) {
+  long long lo = INT64_MAX, hi = INT64_MIN, cnt = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
+    if (key_has_null(build, row)) continue;
+    const long long k = static_cast<long long>(jload(build.data[0], build.phys[0], row));
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+    ++cnt;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    const long long ol = __shfl_xor_sync(0xffffffffu, lo, d), oh = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = ol < lo ? ol : lo;
+    hi = oh > hi ? oh : hi;
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&mm[2]), static_cast<unsigned long long>(cnt));
+  }
+}
+__global__ void __launch_bounds__(256) join_build_dense_kernel(JoinTable t, JoinKeys build, long long rows) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows; row += stride) {
+    if (key_has_null(build, row)) continue;
+    const long long k = static_cast<long long>(jload(build.data[0], build.phys[0], row));
+    // duplicates of a key keep the smallest row as the head, like the slot table
+    const unsigned long long idx = static_cast<unsigned long long>(k - t.dense_min);
+    atomicMin(&t.dense_rows[idx], static_cast<unsigned int>(row));
+    atomicOr(&t.dense_present[idx >> 5], 1u << (idx & 31));
+  }
+}
+// The materialising probe over a dense index reads its rhs result columns BY KEY: dst[key - min] = src[head row of the
+// key] (zero where the key has no row), so a probe row costs one random access per rhs column and a presence bit,
+// not an index access followed by a gather.
+__global__ void __launch_bounds__(256) join_dense_spread_kernel(JoinTable t, const void* __restrict__ src, int w, void* __restrict__ dst) {
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long idx = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < t.dense_range; idx += stride) {
+    const unsigned int r = t.dense_rows[idx];
+    const long long i = r == kDenseEmpty ? -1 : static_cast<long long>(r);
+    if (w == 8) static_cast<unsigned long long*>(dst)[idx] = i >= 0 ? static_cast<const unsigned long long*>(src)[i] : 0ull;
+    else if (w == 4) static_cast<uint32_t*>(dst)[idx] = i >= 0 ? static_cast<const uint32_t*>(src)[i] : 0u;
+    else static_cast<unsigned char*>(dst)[idx] = i >= 0 ? static_cast<const unsigned char*>(src)[i] : static_cast<unsigned char>(0);
+  }
+}
+
 // NOTE on atomicMin above: heads are positive once published, so min keeps the smallest row;
 // a concurrent reader may compare keys against either row of the same key - both are equal.
 
@@ -241,6 +300,7 @@ struct JoinEmit {
   const void* l_src[kEmitMax]; void* l_dst[kEmitMax]; int32_t l_w[kEmitMax];
   const void* r_src[kEmitMax]; void* r_dst[kEmitMax]; int32_t r_w[kEmitMax];
   unsigned char* matched;   // LEFT_OUTER: 1 = the row found a build row (else the rhs cells are zero), or nullptr
+  int32_t by_key;           // dense index: r_src are indexed by key - dense_min (join_dense_spread_kernel), not by build row
 };
 __device__ __forceinline__ void emit_cell(void* dst, unsigned long long o, const void* src, long long i, int w) {
   if (w == 8) static_cast<unsigned long long*>(dst)[o] = i >= 0 ? static_cast<const unsigned long long*>(src)[i] : 0ull;
@@ -248,7 +308,7 @@ __device__ __forceinline__ void emit_cell(void* dst, unsigned long long o, const
   else static_cast<unsigned char*>(dst)[o] = i >= 0 ? static_cast<const unsigned char*>(src)[i] : static_cast<unsigned char>(0);
 }
 
-template <bool PARTS, bool EMIT>
+template <bool PARTS, bool EMIT, bool DENSE>
 __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTable t, JoinKeys build, JoinKeys probe,
                                                                            long long rows, int left_outer,
                                                                            long long* __restrict__ lhs_out,
@@ -277,6 +337,24 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
     const unsigned long long* tab[kProbeRows];
     unsigned long long cap[kProbeRows];
     long long offset[kProbeRows];
+    if (DENSE) {
+      // dense integer keys: the key is the index; the four loads are in flight together
+      unsigned int dr[kProbeRows];
+#pragma unroll
+      for (int j = 0; j < kProbeRows; ++j) {
+        const long long row = r0 + j * kProbeThreads;
+        dr[j] = kDenseEmpty;
+        if (row < rows && !key_has_null(probe, row)) {
+          const unsigned long long idx = static_cast<unsigned long long>(static_cast<long long>(jload(probe.data[0], probe.phys[0], row)) - t.dense_min);
+          if (idx < t.dense_range) {
+            if (EMIT && emit.by_key) dr[j] = ((__ldg(&t.dense_present[idx >> 5]) >> (idx & 31)) & 1u) ? static_cast<unsigned int>(idx) : kDenseEmpty;
+            else dr[j] = __ldg(&t.dense_rows[idx]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kProbeRows; ++j) head[j] = dr[j] == kDenseEmpty ? -1 : static_cast<long long>(dr[j]);
+    } else {
     // hash and first table probe of all four rows before any of them is looked at
 #pragma unroll
     for (int j = 0; j < kProbeRows; ++j) {
@@ -314,6 +392,7 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
         e = __ldg(reinterpret_cast<const ulonglong2*>(tab[j]) + sl);
       }
     }
+    }   // !DENSE
     if (left_outer) {
 #pragma unroll
       for (int j = 0; j < kProbeRows; ++j) {
@@ -429,6 +508,8 @@ void ssb_join_destroy(ssb_join* j) {
   tmp_free(ctx, j->table.run_start);
   tmp_free(ctx, j->table.run_count);
   tmp_free(ctx, j->table.run_rows);
+  tmp_free(ctx, j->table.dense_rows);
+  tmp_free(ctx, j->table.dense_present);
   tmp_free(ctx, j->lhs_out);
   tmp_free(ctx, j->rhs_out);
   delete j;
@@ -470,6 +551,44 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
   if (cap >= (1ull << 32)) { delete j; return fail(ctx, SSB_ERROR_NOT_IMPLEMENTED, "hash join build side beyond 2^31 rows"); }
   j->table.capacity = cap;
   TimedRegion timed(ctx);
+  // dense integer keys (see JoinTable): decided from the key range; SSB200_JOIN_DENSE=0 keeps the slot table
+  {
+    static const bool dense_enabled = getenv("SSB200_JOIN_DENSE") == nullptr || atoi(getenv("SSB200_JOIN_DENSE")) != 0;
+    const int ph = j->build_keys.phys[0];
+    if (dense_enabled && uniqueness == SSB_KEYS_UNIQUE && !compact && n_keys == 1 && rows >= 4096 && rows < (1LL << 32) - 1 &&
+        (ph == T_I32 || ph == T_I64 || ph == T_U32)) {
+      long long* mm = nullptr;
+      cudaError_t e0 = tmp_malloc(ctx, &mm, 32);
+      if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "join key range"); }
+      const long long init[3] = {INT64_MAX, INT64_MIN, 0};
+      cudaMemcpyAsync(mm, init, 24, cudaMemcpyHostToDevice, ctx->stream);
+      join_minmax_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->build_keys, rows, mm);
+      ++ctx->launches;
+      long long host[3] = {0, 0, 0};
+      e0 = cudaMemcpyAsync(host, mm, 24, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(ctx->stream);
+      tmp_free(ctx, mm);
+      if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "join key range"); }
+      const unsigned long long span = static_cast<unsigned long long>(host[1]) - static_cast<unsigned long long>(host[0]);   // max - min, no overflow
+      if (host[2] > 0 && host[1] >= host[0] && span < static_cast<unsigned long long>(rows) * 4 && span < (1ull << 32) - 2) {
+        j->table.dense_min = host[0];
+        j->table.dense_range = span + 1;
+        e0 = tmp_malloc(ctx, &j->table.dense_rows, static_cast<size_t>(span + 1) * 4);
+        if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join index"); }
+        if (e0 == cudaSuccess) e0 = tmp_malloc(ctx, &j->table.dense_present, static_cast<size_t>(span / 32 + 2) * 4);
+        if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join index"); }
+        cudaMemsetAsync(j->table.dense_rows, 0xff, static_cast<size_t>(span + 1) * 4, ctx->stream);
+        cudaMemsetAsync(j->table.dense_present, 0, static_cast<size_t>(span / 32 + 2) * 4, ctx->stream);
+        join_build_dense_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, j->build_keys, rows);
+        ++ctx->launches;
+        e0 = cudaGetLastError();
+        if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(ctx->stream);
+        if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join build"); }
+        *out = j;
+        return 0;
+      }
+    }
+  }
   cudaError_t e = tmp_malloc(ctx, &j->table.slots, cap * 16);
   if (e != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e, "join table"); }
   cudaMemsetAsync(j->table.slots, 0, cap * 16, ctx->stream);
@@ -559,10 +678,13 @@ int ssb_join_probe(ssb_join* j, const ssb_column* keys, int64_t rows, int32_t jo
     JoinEmit no_emit;
     memset(&no_emit, 0, sizeof(no_emit));
     if (j->parts.n_parts > 0) {
-      join_probe_unique_kernel<true, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+      join_probe_unique_kernel<true, false, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+          j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts, no_emit);
+    } else if (j->table.dense_rows != nullptr) {
+      join_probe_unique_kernel<false, false, true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
           j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts, no_emit);
     } else {
-      join_probe_unique_kernel<false, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+      join_probe_unique_kernel<false, false, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
           j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, j->lhs_out, j->rhs_out, aux, j->parts, no_emit);
     }
     ++ctx->launches;
@@ -654,10 +776,39 @@ int ssb_join_probe_materialize(ssb_join* j, const ssb_column* keys, int64_t rows
   long long grid = static_cast<long long>(ctx->num_sms) * 4;
   if (grid > tiles) grid = tiles;
   if (j->parts.n_parts > 0) {
-    join_probe_unique_kernel<true, true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+    join_probe_unique_kernel<true, true, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
         j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, nullptr, nullptr, aux, j->parts, emit);
+  } else if (j->table.dense_rows != nullptr) {
+    // enough probe rows to pay for it: the rhs result columns are laid out by key first (one pass over the key range)
+    void* spread[kEmitMax];
+    for (int c = 0; c < kEmitMax; ++c) spread[c] = nullptr;
+    if (n_rhs > 0 && static_cast<unsigned long long>(rows) >= 2 * j->table.dense_range) {
+      for (int c = 0; c < n_rhs && e == cudaSuccess; ++c) e = tmp_malloc_bytes(ctx, &spread[c], static_cast<size_t>(j->table.dense_range) * emit.r_w[c] + 64);
+      if (e != cudaSuccess) {
+        for (int c = 0; c < n_rhs; ++c) tmp_free(ctx, spread[c]);
+        tmp_free(ctx, aux);
+        return cuda_fail(ctx, e, "join result columns by key");
+      }
+      for (int c = 0; c < n_rhs; ++c) {
+        join_dense_spread_kernel<<<grid_1d(ctx, static_cast<long long>(j->table.dense_range), 256), 256, 0, ctx->stream>>>(j->table, emit.r_src[c], emit.r_w[c], spread[c]);
+        ++ctx->launches;
+        emit.r_src[c] = spread[c];
+      }
+      emit.by_key = 1;
+    }
+    join_probe_unique_kernel<false, true, true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+        j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, nullptr, nullptr, aux, j->parts, emit);
+    ++ctx->launches;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_count, aux + 1, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    for (int c = 0; c < n_rhs; ++c) tmp_free(ctx, spread[c]);
+    tmp_free(ctx, aux);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "join probe");
+    *n_rows = *ctx->h_count;
+    return 0;
   } else {
-    join_probe_unique_kernel<false, true><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
+    join_probe_unique_kernel<false, true, false><<<static_cast<unsigned>(grid), kProbeThreads, 0, ctx->stream>>>(
         j->table, j->build_keys, probe, rows, join_type == SSB_JOIN_LEFT_OUTER ? 1 : 0, nullptr, nullptr, aux, j->parts, emit);
   }
   ++ctx->launches;
@@ -672,6 +823,10 @@ int ssb_join_probe_materialize(ssb_join* j, const ssb_column* keys, int64_t rows
 
 int ssb_join_table(const ssb_join* j, const void** d_slots, int64_t* capacity) {
   if (j->parts.n_parts > 0) return fail(j->ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "an attached index owns no table");
+  if (j->table.dense_rows != nullptr) {
+    *d_slots = nullptr; *capacity = 0;
+    return fail(j->ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "this index has no slot table (dense integer keys); build with SSB_KEYS_COMPACT_TABLE to export one");
+  }
   *d_slots = j->table.slots;
   *capacity = static_cast<int64_t>(j->table.capacity);
   return 0;

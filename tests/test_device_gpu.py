@@ -675,6 +675,51 @@ def test_probe_materialize_equals_probe_plus_gather(ctx, join_type, compact):
     ctx.lib.ssb_join_destroy(j)
 
 
+@pytest.mark.parametrize("build_dtype,probe_dtype", [(np.int64, np.int64), (np.int32, np.int64), (np.uint32, np.int32)])
+@pytest.mark.parametrize("lo,spread", [(0, 2), (-50_000, 3), (2**31 - 120_000, 1), (-2**40, 2), (0, 1000)])
+def test_join_dense_integer_keys_equal_host(ctx, lo, spread, build_dtype, probe_dtype):
+    """UNIQUE joins on one integer key column whose values span at most 4 x rows use a direct index
+    (dense_rows[key - min] = build row) instead of the slot table; spread 1000 keeps the slot table. Against numpy:
+    negative and large bases, build and probe keys of different integer types (compared by value), NULL keys on both
+    sides, probe keys below / above / inside the range without a build row, duplicate build keys (the smallest row is
+    the head, as in the slot table), INNER and LEFT_OUTER."""
+    nb, npr = 60_000, 250_003
+    narrow = np.dtype(build_dtype).itemsize == 4 or np.dtype(probe_dtype).itemsize == 4
+    unsigned = np.dtype(build_dtype).kind == "u" or np.dtype(probe_dtype).kind == "u"
+    if (narrow and (lo - 500 < -2**31 or lo + nb * spread + 500 >= 2**31)) or (unsigned and lo < 0):
+        pytest.skip("key range outside the 32-bit type")
+    rng = np.random.default_rng(abs(lo) % 1000 + spread)
+    pk = (rng.permutation(nb * spread)[:nb] + lo).astype(np.int64)
+    pk[1000:1200] = pk[:200]                                 # duplicates: rows 0..199 stay the heads
+    pk_null = rng.random(nb) < 0.02
+    fk = (rng.integers(-500, nb * spread + 500, npr) + lo).astype(np.int64)
+    fk_null = rng.random(npr) < 0.05
+    lim = np.iinfo(probe_dtype)
+    fk = np.clip(fk, lim.min, lim.max)
+    d_pk, d_pkn = _upload(ctx, pk.astype(build_dtype), pk_null)
+    d_fk, d_fkn = _upload(ctx, fk.astype(probe_dtype), fk_null)
+    tb = {np.int64: capi.INT64, np.int32: capi.INT32, np.uint32: capi.UINT32}
+    row_of = {}
+    for i in range(nb - 1, -1, -1):
+        if not pk_null[i]:
+            row_of[int(pk[i])] = i
+    hit = np.array([(-1 if fk_null[i] else row_of.get(int(fk[i]), -1)) for i in range(npr)])
+    j = C.c_void_p()
+    ctx.check(ctx.lib.ssb_join_build(ctx.h, 1, _cols([(d_pk, d_pkn, tb[build_dtype])]), nb, 1, C.byref(j)))
+    for join_type in (0, 1):
+        keep = np.arange(npr) if join_type == 1 else np.nonzero(hit >= 0)[0]
+        n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+        ctx.check(ctx.lib.ssb_join_probe(j, _cols([(d_fk, d_fkn, tb[probe_dtype])]), npr, join_type, C.byref(n), C.byref(pl), C.byref(pr)))
+        assert n.value == len(keep)
+        li, ri = np.empty(n.value, dtype=np.int64), np.empty(n.value, dtype=np.int64)
+        ctx.d2h(li, pl)
+        ctx.d2h(ri, pr)
+        assert np.array_equal(li, keep) and np.array_equal(ri, hit[keep])
+    ctx.lib.ssb_join_destroy(j)
+    for d in (d_pk, d_pkn, d_fk, d_fkn):
+        ctx.free(d)
+
+
 @pytest.mark.parametrize("with_count", [True, False])
 @pytest.mark.parametrize("lo", [0, -700_000, 2**62])
 def test_group_dense_keys_equal_host(ctx, lo, with_count, monkeypatch):

@@ -430,6 +430,7 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch, c
             assert n.value <= probe_rows
             ctx.sync()
             state["pairs"] = n.value
+            state["form"] = lib.ssb_shard_join_form(j)
             lib.ssb_shard_join_destroy(j)
     best, _ = _timed(ctx, world, dist, torch, once, repeats=2)
     pairs = state["pairs"]
@@ -448,9 +449,14 @@ def hash_join_aux(capi, ctx, rank, world, probe_rows, build_rows, dist, torch, c
             "value": world * probe_rows / best, "unit": "rows/s", "probe_rows_per_gpu": probe_rows,
             "build_rows_per_gpu": build_rows, "pairs": pairs, "seconds": best,
             "algorithmic_gbs_per_gpu": alg / best / 1e9, "check": "pairs == probe rows (every fk has one pk)",
-            "exchange": ("ssb_shard_join_* (C ABI, NCCL inside libssb200.so): build rows to the owner of their key's hash part "
-                         "(one grouped send/recv), one compact table per rank, all-gather of the tables + payload, local probe "
-                         "of the key's part; for the record, orchestrated from Python over torch.distributed: all-to-all form "
+            "exchange": ((("ssb_shard_join_* (C ABI, NCCL inside libssb200.so), dense integer keys: key + payload columns "
+                           "all-gathered as they are (one grouped exchange), every rank builds the direct index key - min -> row "
+                           "(one scatter, no hashing, no table travels), local probe reading the payload by key; ")
+                          if state.get("form") == 1 else
+                          ("ssb_shard_join_* (C ABI, NCCL inside libssb200.so): build rows to the owner of their key's hash part "
+                           "(one grouped send/recv), one compact table per rank, all-gather of the tables + payload, local probe "
+                           "of the key's part; ")) +
+                         "for the record, orchestrated from Python over torch.distributed: all-to-all form "
                          "%.4f s, broadcast form (whole table built on every rank) %.4f s, replicated form %.4f s"
                          % (state["all_to_all_seconds"], state["broadcast_seconds"], state["python_replicate_seconds"]))
             if world > 1 else "none"}

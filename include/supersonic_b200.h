@@ -409,6 +409,10 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
 int ssb_shard_join_probe(ssb_shard_join* j, const ssb_column* key, int64_t rows, int32_t join_type, int64_t* n_pairs,
                          const int64_t** d_lhs_rows, const int64_t** d_rhs_rows);
 int ssb_shard_join_payload(const ssb_shard_join* j, int32_t i, ssb_column* out, int64_t* rows);
+/* Which form the collective build chose (the same on every rank): 0 = hash-partitioned tables (build rows to the owner of
+ * their key's hash part, per-part compact tables all-gathered), 1 = dense integer keys (key and payload columns
+ * all-gathered as they are, every rank builds the direct index key - min -> row; no table travels). */
+int ssb_shard_join_form(const ssb_shard_join* j);
 /* ssb_join_probe_materialize on the sharded index: rhs columns are named by their payload index. */
 int ssb_shard_join_probe_materialize(ssb_shard_join* j, const ssb_column* keys, int64_t rows, int32_t join_type,
                                      int32_t n_lhs, const ssb_column* lhs_cols, int32_t n_rhs, const int32_t* rhs_payload,

@@ -127,6 +127,7 @@ def load():
         "ssb_shard_join_build": (C.c_int, [P, C.POINTER(Column), I32, C.POINTER(Column), I64, C.POINTER(P)]),
         "ssb_shard_join_probe": (C.c_int, [P, C.POINTER(Column), I64, I32, C.POINTER(I64), C.POINTER(P), C.POINTER(P)]),
         "ssb_shard_join_payload": (C.c_int, [P, I32, C.POINTER(Column), C.POINTER(I64)]),
+        "ssb_shard_join_form": (C.c_int, [P]),
         "ssb_shard_join_destroy": (None, [P]),
         "ssb_shard_join_probe_materialize": (C.c_int, [P, C.POINTER(Column), I64, I32, I32, C.POINTER(Column), I32, C.POINTER(I32),
                                                        C.POINTER(Column), P, C.POINTER(I64)]),

@@ -18,5 +18,10 @@ int comm_all_to_all_v(ssb_comm* c, int n_cols, const void* const* send, void* co
                       const int64_t* send_rows, const int64_t* recv_rows);
 int comm_all_gather_v(ssb_comm* c, int n_cols, const void* const* send, void* const* recv, const int32_t* width,
                       const int64_t* all_rows);
+// join.cu: smallest / largest value (as signed 64-bit containers) and number of non-NULL keys of an integer key
+// column: out = {min, max, count}; eligible = 0 when the column's type has no dense form. Synchronises.
+int join_key_range(ssb_ctx* ctx, const ssb_column* key, int64_t rows, long long out[3], int* eligible);
+// True when a UNIQUE index over `rows` keys spanning [lo, hi] is built as a direct index (JoinTable::dense_rows).
+bool join_dense_fits(long long lo, long long hi, long long count, long long rows);
 }  // namespace ssb
 #endif  // SSB_CSRC_COMM_H_

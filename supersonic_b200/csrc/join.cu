@@ -18,6 +18,7 @@
 
 #include <vector>
 
+#include "comm.h"
 #include "common.h"
 #include "device_utils.h"
 
@@ -483,6 +484,40 @@ __global__ void __launch_bounds__(256) part_id_kernel(JoinKeys keys, long long r
   }
 }
 
+static bool dense_enabled() {
+  static const bool on = getenv("SSB200_JOIN_DENSE") == nullptr || atoi(getenv("SSB200_JOIN_DENSE")) != 0;
+  return on;
+}
+
+bool join_dense_fits(long long lo, long long hi, long long count, long long rows) {
+  if (!dense_enabled() || count <= 0 || hi < lo || rows >= (1LL << 32) - 1) return false;
+  const unsigned long long span = static_cast<unsigned long long>(hi) - static_cast<unsigned long long>(lo);   // max - min, no overflow
+  return span < static_cast<unsigned long long>(rows) * 4 && span < (1ull << 32) - 2;
+}
+
+int join_key_range(ssb_ctx* ctx, const ssb_column* key, int64_t rows, long long out[3], int* eligible) {
+  out[0] = INT64_MAX; out[1] = INT64_MIN; out[2] = 0;
+  JoinKeys k;
+  memset(&k, 0, sizeof(k));
+  k.n_keys = 1;
+  k.phys[0] = phys_of(key->dtype);
+  k.data[0] = key->data;
+  k.nulls[0] = key->nulls;
+  *eligible = (k.phys[0] == T_I32 || k.phys[0] == T_I64 || k.phys[0] == T_U32) && dense_enabled() ? 1 : 0;
+  if (!*eligible || rows <= 0) return 0;
+  long long* mm = nullptr;
+  cudaError_t e = tmp_malloc(ctx, &mm, 32);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "join key range");
+  cudaMemcpyAsync(mm, out, 24, cudaMemcpyHostToDevice, ctx->stream);
+  join_minmax_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(k, rows, mm);
+  ++ctx->launches;
+  e = cudaMemcpyAsync(out, mm, 24, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  tmp_free(ctx, mm);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "join key range");
+  return 0;
+}
+
 }  // namespace ssb
 
 using namespace ssb;
@@ -552,41 +587,26 @@ int ssb_join_build(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, int64_t
   j->table.capacity = cap;
   TimedRegion timed(ctx);
   // dense integer keys (see JoinTable): decided from the key range; SSB200_JOIN_DENSE=0 keeps the slot table
-  {
-    static const bool dense_enabled = getenv("SSB200_JOIN_DENSE") == nullptr || atoi(getenv("SSB200_JOIN_DENSE")) != 0;
-    const int ph = j->build_keys.phys[0];
-    if (dense_enabled && uniqueness == SSB_KEYS_UNIQUE && !compact && n_keys == 1 && rows >= 4096 && rows < (1LL << 32) - 1 &&
-        (ph == T_I32 || ph == T_I64 || ph == T_U32)) {
-      long long* mm = nullptr;
-      cudaError_t e0 = tmp_malloc(ctx, &mm, 32);
-      if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "join key range"); }
-      const long long init[3] = {INT64_MAX, INT64_MIN, 0};
-      cudaMemcpyAsync(mm, init, 24, cudaMemcpyHostToDevice, ctx->stream);
-      join_minmax_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->build_keys, rows, mm);
+  if (uniqueness == SSB_KEYS_UNIQUE && !compact && n_keys == 1 && rows >= 4096) {
+    long long range[3] = {0, 0, 0};
+    int eligible = 0;
+    if (int rc0 = join_key_range(ctx, &keys[0], rows, range, &eligible)) { ssb_join_destroy(j); return rc0; }
+    if (eligible && join_dense_fits(range[0], range[1], range[2], rows)) {
+      const unsigned long long span = static_cast<unsigned long long>(range[1]) - static_cast<unsigned long long>(range[0]);
+      j->table.dense_min = range[0];
+      j->table.dense_range = span + 1;
+      cudaError_t e0 = tmp_malloc(ctx, &j->table.dense_rows, static_cast<size_t>(span + 1) * 4);
+      if (e0 == cudaSuccess) e0 = tmp_malloc(ctx, &j->table.dense_present, static_cast<size_t>(span / 32 + 2) * 4);
+      if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join index"); }
+      cudaMemsetAsync(j->table.dense_rows, 0xff, static_cast<size_t>(span + 1) * 4, ctx->stream);
+      cudaMemsetAsync(j->table.dense_present, 0, static_cast<size_t>(span / 32 + 2) * 4, ctx->stream);
+      join_build_dense_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, j->build_keys, rows);
       ++ctx->launches;
-      long long host[3] = {0, 0, 0};
-      e0 = cudaMemcpyAsync(host, mm, 24, cudaMemcpyDeviceToHost, ctx->stream);
+      e0 = cudaGetLastError();
       if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(ctx->stream);
-      tmp_free(ctx, mm);
-      if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "join key range"); }
-      const unsigned long long span = static_cast<unsigned long long>(host[1]) - static_cast<unsigned long long>(host[0]);   // max - min, no overflow
-      if (host[2] > 0 && host[1] >= host[0] && span < static_cast<unsigned long long>(rows) * 4 && span < (1ull << 32) - 2) {
-        j->table.dense_min = host[0];
-        j->table.dense_range = span + 1;
-        e0 = tmp_malloc(ctx, &j->table.dense_rows, static_cast<size_t>(span + 1) * 4);
-        if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join index"); }
-        if (e0 == cudaSuccess) e0 = tmp_malloc(ctx, &j->table.dense_present, static_cast<size_t>(span / 32 + 2) * 4);
-        if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join index"); }
-        cudaMemsetAsync(j->table.dense_rows, 0xff, static_cast<size_t>(span + 1) * 4, ctx->stream);
-        cudaMemsetAsync(j->table.dense_present, 0, static_cast<size_t>(span / 32 + 2) * 4, ctx->stream);
-        join_build_dense_kernel<<<grid_1d(ctx, rows, 256), 256, 0, ctx->stream>>>(j->table, j->build_keys, rows);
-        ++ctx->launches;
-        e0 = cudaGetLastError();
-        if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(ctx->stream);
-        if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join build"); }
-        *out = j;
-        return 0;
-      }
+      if (e0 != cudaSuccess) { ssb_join_destroy(j); return cuda_fail(ctx, e0, "dense join build"); }
+      *out = j;
+      return 0;
     }
   }
   cudaError_t e = tmp_malloc(ctx, &j->table.slots, cap * 16);
@@ -782,7 +802,7 @@ int ssb_join_probe_materialize(ssb_join* j, const ssb_column* keys, int64_t rows
     // enough probe rows to pay for it: the rhs result columns are laid out by key first (one pass over the key range)
     void* spread[kEmitMax];
     for (int c = 0; c < kEmitMax; ++c) spread[c] = nullptr;
-    if (n_rhs > 0 && static_cast<unsigned long long>(rows) >= 2 * j->table.dense_range) {
+    if (n_rhs > 0 && static_cast<unsigned long long>(rows) >= j->table.dense_range) {
       for (int c = 0; c < n_rhs && e == cudaSuccess; ++c) e = tmp_malloc_bytes(ctx, &spread[c], static_cast<size_t>(j->table.dense_range) * emit.r_w[c] + 64);
       if (e != cudaSuccess) {
         for (int c = 0; c < n_rhs; ++c) tmp_free(ctx, spread[c]);

@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <vector>
 
@@ -53,7 +54,8 @@ struct PhaseClock {
 struct ssb_shard_join {
   ssb_comm* comm;
   ssb_ctx* ctx;
-  ssb_join* attached;                 // index over the gathered tables
+  ssb_join* attached;                 // index over the gathered tables (or, dense keys: over the gathered key column)
+  void* keys;                         // dense keys: all ranks' key columns, end to end (global rhs row order)
   void* tables;                       // all ranks' slot arrays, end to end
   std::vector<void*> payload;         // all ranks' received payload columns, end to end (global rhs row order)
   std::vector<int32_t> payload_types;
@@ -67,6 +69,7 @@ void ssb_shard_join_destroy(ssb_shard_join* j) {
   if (j->attached) ssb_join_destroy(j->attached);
   cudaStreamSynchronize(j->ctx->stream);
   tmp_free(j->ctx, j->tables);
+  tmp_free(j->ctx, j->keys);
   for (size_t i = 0; i < j->payload.size(); ++i) tmp_free(j->ctx, j->payload[i]);
   delete j;
 }
@@ -91,6 +94,62 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
   width[0] = kw;
   for (int i = 0; i < n_payload; ++i) width[1 + i] = width_of(payload[i].dtype);
 
+  // ---- 0. dense integer keys (a surrogate primary key: values spanning at most 4 x the rows of ALL ranks, no NULL
+  // bitmap): nothing is partitioned and no table travels. The key and payload columns are all-gathered as they are
+  // (rank order = global insertion order) and every rank builds the direct index over the gathered keys
+  // (JoinTable::dense_rows: one scatter of 4-byte row numbers, no hashing) -- half the bytes of the partitioned form
+  // over NVLink (no tables) and a build that is one pass, so repeating it on every rank costs less than exchanging it.
+  PhaseClock clock(ctx, rank);
+  {   // collective: every rank takes part in the decision, whatever its own shard looks like
+    long long range[3] = {0, 0, 0};
+    int eligible = 0;
+    if (key->nulls == nullptr) {
+      if (int rc0 = join_key_range(ctx, key, rows, range, &eligible)) eligible = 0;   // a failed range pass: the general form
+    }
+    std::vector<int64_t> all4(4 * W, 0);
+    const int64_t mine4[4] = {range[0], range[1], range[2], eligible};
+    if (int rc0 = comm_all_gather_counts(comm, mine4, 4, all4.data())) return rc0;
+    long long lo = INT64_MAX, hi = INT64_MIN, count = 0;
+    bool all_eligible = true;
+    std::vector<int64_t> rows_of(W);
+    for (int r = 0; r < W; ++r) {
+      all_eligible = all_eligible && all4[4 * r + 3] != 0;
+      rows_of[r] = all4[4 * r + 2];
+      if (all4[4 * r + 2] > 0) { lo = std::min<long long>(lo, all4[4 * r]); hi = std::max<long long>(hi, all4[4 * r + 1]); }
+      count += all4[4 * r + 2];
+    }
+    clock.mark("key range");
+    if (all_eligible && count >= 4096 && join_dense_fits(lo, hi, count, count)) {   // the same decision on every rank
+      ssb_shard_join* dj = new ssb_shard_join;
+      dj->comm = comm; dj->ctx = ctx; dj->attached = nullptr; dj->tables = nullptr; dj->keys = nullptr; dj->total_rows = count;
+      int rc0 = 0;
+      cudaError_t e0 = tmp_malloc_bytes(ctx, &dj->keys, static_cast<size_t>(count) * kw + 64);
+      if (e0 != cudaSuccess) rc0 = cuda_fail(ctx, e0, "sharded join keys");
+      dj->payload.assign(n_payload, nullptr);
+      dj->payload_types.resize(n_payload);
+      std::vector<const void*> src(n_cols);
+      std::vector<void*> dst(n_cols);
+      src[0] = key->data; dst[0] = dj->keys;
+      for (int i = 0; i < n_payload && rc0 == 0; ++i) {
+        dj->payload_types[i] = payload[i].dtype;
+        e0 = tmp_malloc_bytes(ctx, &dj->payload[i], static_cast<size_t>(count) * width[1 + i] + 64);
+        if (e0 != cudaSuccess) rc0 = cuda_fail(ctx, e0, "sharded join payload");
+        src[1 + i] = payload[i].data; dst[1 + i] = dj->payload[i];
+      }
+      if (rc0 == 0) rc0 = comm_all_gather_v(comm, n_cols, src.data(), dst.data(), width.data(), rows_of.data());
+      clock.mark("all-gather keys + payload");
+      if (rc0 == 0) {
+        ssb_column k = *key;
+        k.data = dj->keys;
+        k.nulls = nullptr;
+        rc0 = ssb_join_build(ctx, 1, &k, count, SSB_KEYS_UNIQUE, &dj->attached);
+      }
+      clock.mark("dense index");
+      if (rc0 != 0) { ssb_shard_join_destroy(dj); return rc0; }
+      *out = dj;
+      return 0;
+    }
+  }
   // ---- 1. partition: parts 0..W-1 by key hash, part W = rows with a NULL key (they never match and stay behind)
   long long* d_perm = nullptr;
   cudaError_t e = tmp_malloc(ctx, &d_perm, static_cast<size_t>(rows) * 8 + 64);
@@ -106,7 +165,6 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
     for (int i = 0; i < n_cols; ++i) tmp_free(ctx, recv[i]);
     if (local) ssb_join_destroy(local);
   };
-  PhaseClock clock(ctx, rank);
   int rc = ssb_partition_rows(ctx, 1, key, rows, W, W, reinterpret_cast<int64_t*>(d_perm), part_rows.data());
   if (rc) { cleanup(); return rc; }
   clock.mark("partition");
@@ -165,6 +223,7 @@ int ssb_shard_join_build(ssb_comm* comm, const ssb_column* key, int32_t n_payloa
   j->ctx = ctx;
   j->attached = nullptr;
   j->tables = nullptr;
+  j->keys = nullptr;
   j->total_rows = total_rows;
   e = tmp_malloc_bytes(ctx, &j->tables, static_cast<size_t>(total_cap) * 16 + 64);
   if (e != cudaSuccess) rc = cuda_fail(ctx, e, "sharded join tables");
@@ -218,6 +277,8 @@ int ssb_shard_join_probe_materialize(ssb_shard_join* j, const ssb_column* keys, 
   clock.mark("probe + materialise");
   return rc;
 }
+
+int ssb_shard_join_form(const ssb_shard_join* j) { return j->keys != nullptr ? 1 : 0; }
 
 int ssb_shard_join_payload(const ssb_shard_join* j, int32_t i, ssb_column* out, int64_t* rows) {
   if (i < 0 || i >= static_cast<int32_t>(j->payload.size())) return fail(j->ctx, SSB_ERROR_INVALID_ARGUMENT_VALUE, "no such payload column");

@@ -536,9 +536,13 @@ int ssb_sort_permutation(ssb_ctx* ctx, int32_t n_keys, const ssb_column* keys, c
   if (n_keys == 0 || rows == 1) { SSB_CUDA(ctx, cudaGetLastError()); return 0; }
   unsigned long long *k0 = nullptr, *k1 = nullptr;
   long long* p1 = nullptr;
-  SSB_CUDA(ctx, tmp_malloc(ctx, &k0, static_cast<size_t>(rows) * 8));
-  SSB_CUDA(ctx, tmp_malloc(ctx, &k1, static_cast<size_t>(rows) * 8));
-  SSB_CUDA(ctx, tmp_malloc(ctx, &p1, static_cast<size_t>(rows) * 8));
+  cudaError_t e = tmp_malloc(ctx, &k0, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &k1, static_cast<size_t>(rows) * 8);
+  if (e == cudaSuccess) e = tmp_malloc(ctx, &p1, static_cast<size_t>(rows) * 8);
+  if (e != cudaSuccess) {   // out of memory: give back what was obtained
+    tmp_free(ctx, k0); tmp_free(ctx, k1); tmp_free(ctx, p1);
+    return cuda_fail(ctx, e, "sort scratch");
+  }
   long long* pa = perm;
   long long* pb = p1;
   int rc = 0;

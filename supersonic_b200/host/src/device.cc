@@ -29,6 +29,11 @@ FailureOr<Session*> Session::Get() {
   return Success(session);
 }
 
+void Session::SyncAll() {
+  ssb_ctx_sync(ctx_);
+  for (int i = 0; i < 2; ++i) if (lanes_[i] != NULL) ssb_ctx_sync(lanes_[i]);
+}
+
 FailureOr<ssb_ctx*> Session::lane(int i) {
   if (lanes_[i] == NULL) {
     ssb_ctx* c = NULL;
@@ -67,6 +72,10 @@ namespace {
 struct PoolState {
   std::mutex mu;
   std::multimap<size_t, void*> free_blocks[2];
+  // a block was released since the session's streams were last drained: work queued on the releasing cursor's stream
+  // may still touch it, so the next reuse waits for the streams first (Release did not order against them)
+  bool dirty[2];
+  PoolState() { dirty[0] = dirty[1] = false; }
 };
 PoolState* pool_state() {
   static PoolState* p = new PoolState;
@@ -85,6 +94,12 @@ FailureOr<void*> MemoryPool::Acquire(Kind kind, size_t bytes, size_t* granted) {
       void* p = it->second;
       *granted = it->first;
       ps->free_blocks[kind].erase(it);
+      const bool drain = ps->dirty[kind];
+      ps->dirty[kind] = false;
+      if (drain) {
+        FailureOr<Session*> session = Session::Get();
+        if (session.is_success()) session.get()->SyncAll();
+      }
       return Success(p);
     }
   }
@@ -113,6 +128,7 @@ void MemoryPool::Release(Kind kind, void* ptr, size_t granted) {
   PoolState* ps = pool_state();
   std::lock_guard<std::mutex> lock(ps->mu);
   ps->free_blocks[kind].insert(std::make_pair(granted, ptr));
+  ps->dirty[kind] = true;
 }
 
 FailureOrVoid DeviceBuffer::Allocate(size_t bytes) {

@@ -44,6 +44,8 @@ class Session {
   ssb_ctx* ctx() const { return ctx_; }
   // Additional contexts (own stream each) on the same device, for copy/compute overlap.
   FailureOr<ssb_ctx*> lane(int i);
+  // Waits for everything queued on the session's streams (the main context and the lanes that exist).
+  void SyncAll();
   int device() const { return device_; }
   Exception* Error(int code, const char* what) const;
   static Exception* ErrorOn(ssb_ctx* ctx, int code, const char* what);

@@ -276,6 +276,11 @@ Operation* GroupAggregate(const SingleSourceProjector* group_by, AggregationSpec
 // that contract allows, so the budget does not apply to it.
 Operation* BestEffortGroupAggregate(const SingleSourceProjector* group_by, AggregationSpecification* aggregation,
                                     GroupAggregateOptions* options, Operation* child);
+// aggregate.h:309-336: exact aggregation (DISTINCT included) of inputs larger than memory; the reference spills sorted
+// runs under temporary_directory_prefix, this implementation aggregates in HBM and ignores quota and directory.
+class HybridGroupDebugOptions;
+Operation* HybridGroupAggregate(const SingleSourceProjector* group_by_columns, const AggregationSpecification* aggregation_specification,
+                                size_t memory_quota, StringPiece temporary_directory_prefix, Operation* child);
 Operation* ScalarAggregate(AggregationSpecification* aggregation, Operation* child);  // aggregate.h:341
 // aggregate.h:277-307: aggregates an input that is CLUSTERED by the key columns (rows with equal keys are
 // consecutive; a key that comes back later is a new cluster), output in cluster order. On the GPU: cluster ids from
@@ -320,6 +325,10 @@ Cursor* BoundProject(const BoundSingleSourceProjector* projector, Cursor* child)
 FailureOrOwned<Cursor> BoundGroupAggregate(const BoundSingleSourceProjector* group_by, Aggregator* aggregator,
                                            BufferAllocator* allocator, BufferAllocator* original_allocator,
                                            bool best_effort, Cursor* child);                      // aggregate.h:254
+FailureOrOwned<Cursor> BoundHybridGroupAggregate(const SingleSourceProjector* group_by_columns,
+                                                 const AggregationSpecification& aggregation_specification,
+                                                 StringPiece temporary_directory_prefix, BufferAllocator* allocator, size_t memory_quota,
+                                                 const HybridGroupDebugOptions* debug_options, Cursor* child);
 Cursor* BoundScalarAggregate(Aggregator* aggregator, Cursor* child);                              // aggregate.h:345
 FailureOrOwned<Cursor> BoundAggregateClusters(const BoundSingleSourceProjector* group_by, Aggregator* aggregator,
                                               BufferAllocator* allocator, Cursor* child);          // aggregate.h:291

@@ -921,6 +921,7 @@ class ProjectOperation : public BasicOperation {
 struct BoundAggregation {
   ssb_agg_spec spec;
   int input_position;   // child column, -1 for COUNT(*)
+  bool distinct;        // COUNT / SUM over the distinct non-NULL values of the input per group
 };
 
 bool IsNumericType(DataType t) { return GetTypeInfo(t).is_numeric(); }
@@ -938,7 +939,12 @@ FailureOrVoid BindAggregations(const AggregationSpecification& spec, const Tuple
     BoundAggregation b;
     memset(&b.spec, 0, sizeof(b.spec));
     const Aggregation fn = e.aggregation_operator();
-    if (e.is_distinct()) THROW(new Exception(ERROR_NOT_IMPLEMENTED, "DISTINCT aggregations are not on the B200 hot path yet"));
+    // column_aggregator.cc:333-433 (DistinctAggregator): duplicates of the input value inside a group count once.
+    // MIN / MAX do not change under DISTINCT; COUNT and SUM take the two-phase form of GroupCursor::RunDistinct.
+    b.distinct = e.is_distinct() && (fn == COUNT || fn == SUM);
+    if (e.is_distinct() && (fn == FIRST || fn == LAST)) {
+      THROW(new Exception(ERROR_NOT_IMPLEMENTED, "DISTINCT FIRST / LAST aggregations are not on the B200 hot path"));
+    }
     if (fn == CONCAT) THROW(new Exception(ERROR_NOT_IMPLEMENTED, "CONCAT needs STRING columns (SURVEY 8f)"));
     b.spec.fn = fn;
     b.input_position = -1;
@@ -946,6 +952,7 @@ FailureOrVoid BindAggregations(const AggregationSpecification& spec, const Tuple
     bool in_nullable = false;
     if (e.input().empty()) {
       if (fn != COUNT) THROW(new Exception(ERROR_ATTRIBUTE_MISSING, "Only COUNT may have an empty input attribute name"));
+      b.distinct = false;
     } else {
       b.input_position = child.LookupAttributePosition(e.input());
       if (b.input_position < 0) {
@@ -1147,10 +1154,137 @@ class GroupCursor : public GpuCursor {
     return Success();
   }
 
+  // DISTINCT aggregates (COUNT / SUM over the distinct non-NULL input values of a group; the reference keeps a hash set
+  // per aggregate and group, column_aggregator.cc:333-433). Here in passes over the same hash-aggregation kernels:
+  //   pass 0         the non-distinct aggregates, grouped by the keys;
+  //   per input x    (a) the distinct (keys, x) combinations = a group-by on keys + x, (b) the DISTINCT aggregates over x
+  //                  grouped by the keys, fed with those combinations;
+  // every pass's result is merged into the final table as partial aggregates (ssb_group_merge; the aggregates a pass
+  // does not compute travel as NULL partials), which also lines the passes up by key, NULL keys included.
+  struct ScopedGroup {
+    ssb_group* g;
+    ScopedGroup() : g(NULL) {}
+    ~ScopedGroup() { if (g) ssb_group_destroy(g); }
+  };
+  FailureOrVoid MergePass(Session* s, const vector<int32_t>& key_types, const vector<int32_t>& key_nullable,
+                          const vector<ssb_column>& key_cols, const vector<size_t>& which, const vector<ssb_agg_spec>& pass_specs,
+                          const vector<ssb_column>& value_cols, int64 rows, const vector<ssb_agg_spec>& all_specs) {
+    int32_t dummy = 0;
+    ssb_column dummy_col;
+    memset(&dummy_col, 0, sizeof(dummy_col));
+    ScopedGroup pass;
+    SSB_CALL(s, ssb_group_create(s->ctx(), static_cast<int32_t>(keys_.size()), key_types.empty() ? &dummy : key_types.data(),
+                                 key_nullable.empty() ? &dummy : key_nullable.data(), static_cast<int32_t>(pass_specs.size()),
+                                 pass_specs.data(), 0, &pass.g), "group-by setup (DISTINCT pass)");
+    SSB_CALL(s, ssb_group_update(pass.g, key_cols.empty() ? &dummy_col : key_cols.data(),
+                                 value_cols.empty() ? &dummy_col : value_cols.data(), rows), "group-by (DISTINCT pass)");
+    int64_t n = 0;
+    vector<ssb_column> kout(keys_.size() ? keys_.size() : 1), aout(pass_specs.size() ? pass_specs.size() : 1);
+    SSB_CALL(s, ssb_group_finalize(pass.g, &n, kout.data(), aout.data()), "group-by finalize (DISTINCT pass)");
+    if (n == 0) return Success();
+    // partials of the aggregates this pass does not compute: NULL (COUNT: zero)
+    DeviceBuffer zeros, ones;
+    PROPAGATE_ON_FAILURE(zeros.Allocate(static_cast<size_t>(n) * 8 + 256));
+    PROPAGATE_ON_FAILURE(ones.Allocate(static_cast<size_t>(n / 32 + 2) * 4 + 256));
+    SSB_CALL(s, ssb_memset(s->ctx(), zeros.get(), 0, static_cast<size_t>(n) * 8 + 256), "memset");
+    SSB_CALL(s, ssb_memset(s->ctx(), ones.get(), 0xff, static_cast<size_t>(n / 32 + 2) * 4 + 256), "memset");
+    vector<ssb_column> full(all_specs.size());
+    for (size_t a = 0; a < all_specs.size(); ++a) {
+      full[a].data = zeros.get();
+      full[a].nulls = all_specs[a].fn == SSB_AGG_COUNT ? NULL : static_cast<uint32_t*>(ones.get());
+      full[a].dtype = all_specs[a].out_type;
+      full[a].reserved = 0;
+    }
+    for (size_t k = 0; k < which.size(); ++k) full[which[k]] = aout[k];
+    SSB_CALL(s, ssb_group_merge(group_, n, kout.data(), full.data()), "group-by merge (DISTINCT pass)");
+    SSB_CALL(s, ssb_ctx_sync(s->ctx()), "sync");   // the pass's table and the NULL partials go away with this scope
+    return Success();
+  }
+
+  FailureOrVoid RunDistinct(Session* s, DeviceTable* result) {
+    DeviceTable in;
+    std::unique_ptr<Block> keepalive;
+    PROPAGATE_ON_FAILURE(MaterializeOnDevice(child_.get(), &in, &keepalive));
+    vector<int32_t> key_types, key_nullable;
+    vector<ssb_column> key_cols;
+    for (size_t k = 0; k < keys_.size(); ++k) {
+      const Attribute& a = child_->schema().attribute(keys_[k]);
+      key_types.push_back(DeviceType(a.type()));
+      key_nullable.push_back(a.is_nullable() ? 1 : 0);
+      key_cols.push_back(in.columns[keys_[k]].col);
+    }
+    // the final table: every aggregate, fed with partials only
+    vector<ssb_agg_spec> all_specs;
+    for (size_t i = 0; i < aggs_.size(); ++i) {
+      ssb_agg_spec sp = aggs_[i].spec;
+      sp.input = aggs_[i].input_position >= 0 ? static_cast<int32_t>(i) : -1;
+      if (sp.fn != SSB_AGG_COUNT) sp.in_nullable = 1;   // the table receives NULL partials: it tracks which groups saw a value
+      all_specs.push_back(sp);
+    }
+    int32_t dummy = 0;
+    SSB_CALL(s, ssb_group_create(s->ctx(), static_cast<int32_t>(keys_.size()), key_types.empty() ? &dummy : key_types.data(),
+                                 key_nullable.empty() ? &dummy : key_nullable.data(), static_cast<int32_t>(all_specs.size()),
+                                 all_specs.data(), estimated_groups_ ? static_cast<int64>(estimated_groups_) : 0, &group_), "group-by setup");
+    // pass 0: the non-distinct aggregates (with none, a COUNT(*) nobody reads keeps groups alive whose DISTINCT inputs are all NULL)
+    {
+      vector<size_t> which;
+      vector<ssb_agg_spec> specs;
+      vector<ssb_column> values;
+      for (size_t i = 0; i < aggs_.size(); ++i) {
+        if (aggs_[i].distinct) continue;
+        ssb_agg_spec sp = aggs_[i].spec;
+        if (aggs_[i].input_position >= 0) { sp.input = static_cast<int32_t>(values.size()); values.push_back(in.columns[aggs_[i].input_position].col); }
+        which.push_back(i);
+        specs.push_back(sp);
+      }
+      if (!specs.empty()) PROPAGATE_ON_FAILURE(MergePass(s, key_types, key_nullable, key_cols, which, specs, values, in.rows, all_specs));
+    }
+    // one pair of passes per DISTINCT input column
+    std::set<int> inputs;
+    for (size_t i = 0; i < aggs_.size(); ++i) if (aggs_[i].distinct) inputs.insert(aggs_[i].input_position);
+    for (std::set<int>::const_iterator it = inputs.begin(); it != inputs.end(); ++it) {
+      const int px = *it;
+      const Attribute& xa = child_->schema().attribute(px);
+      // (a) the distinct (keys, x) combinations
+      vector<int32_t> kt2(key_types), kn2(key_nullable);
+      vector<ssb_column> kc2(key_cols);
+      kt2.push_back(DeviceType(xa.type()));
+      kn2.push_back(xa.is_nullable() ? 1 : 0);
+      kc2.push_back(in.columns[px].col);
+      if (kt2.size() > 8) THROW(new Exception(ERROR_NOT_IMPLEMENTED, "DISTINCT aggregation with eight group-by columns"));
+      ssb_agg_spec star;
+      memset(&star, 0, sizeof(star));
+      star.fn = SSB_AGG_COUNT; star.input = -1; star.in_type = SSB_INT64; star.out_type = SSB_UINT64;
+      ScopedGroup combos;
+      ssb_column dummy_col;
+      memset(&dummy_col, 0, sizeof(dummy_col));
+      SSB_CALL(s, ssb_group_create(s->ctx(), static_cast<int32_t>(kt2.size()), kt2.data(), kn2.data(), 1, &star, 0, &combos.g), "group-by setup (DISTINCT values)");
+      SSB_CALL(s, ssb_group_update(combos.g, kc2.data(), &dummy_col, in.rows), "group-by (DISTINCT values)");
+      int64_t n = 0;
+      vector<ssb_column> kout(kt2.size()), aout(1);
+      SSB_CALL(s, ssb_group_finalize(combos.g, &n, kout.data(), aout.data()), "group-by finalize (DISTINCT values)");
+      // (b) the DISTINCT aggregates of this input over the combinations
+      vector<size_t> which;
+      vector<ssb_agg_spec> specs;
+      for (size_t i = 0; i < aggs_.size(); ++i) {
+        if (!aggs_[i].distinct || aggs_[i].input_position != px) continue;
+        ssb_agg_spec sp = aggs_[i].spec;
+        sp.input = 0;
+        which.push_back(i);
+        specs.push_back(sp);
+      }
+      vector<ssb_column> kcols(kout.begin(), kout.begin() + static_cast<long>(keys_.size()));
+      vector<ssb_column> values(1, kout[keys_.size()]);
+      PROPAGATE_ON_FAILURE(MergePass(s, key_types, key_nullable, kcols, which, specs, values, n, all_specs));
+    }
+    return Finish(s, all_specs, result, &in);
+  }
+
   virtual FailureOrVoid Run(DeviceTable* result) {
     FailureOr<Session*> sr = Session::Get();
     PROPAGATE_ON_FAILURE(sr);
     Session* s = sr.get();
+    for (size_t i = 0; i < aggs_.size(); ++i) if (aggs_[i].distinct) return RunDistinct(s, result);
     if (fused_ && !aggs_.empty()) {
       FailureOr<bool> fused = RunFused(s, result);
       PROPAGATE_ON_FAILURE(fused);
@@ -1313,6 +1447,9 @@ class AggregateClustersOperation : public BasicOperation {
     }
     vector<BoundAggregation> aggs;
     PROPAGATE_ON_FAILURE(BindAggregations(*aggregation_, cs, &aggs, &result));
+    for (size_t i = 0; i < aggs.size(); ++i) {
+      if (aggs[i].distinct) THROW(new Exception(ERROR_NOT_IMPLEMENTED, "DISTINCT aggregations in AggregateClusters are not on the B200 hot path"));
+    }
     return Success(static_cast<Cursor*>(new ClustersCursor(result, buffer_allocator(), child_cursor.release(), keys, aggs)));
   }
  protected:
@@ -1435,6 +1572,7 @@ class GroupAggregateOperation : public BasicOperation {
         for (size_t i = 0; i < aggs.size(); ++i) {
           if (aggs[i].input_position >= 0) nontrivial = nontrivial || plan.outputs[aggs[i].input_position]->op != SSB_OP_INPUT;
         }
+        for (size_t i = 0; i < aggs.size(); ++i) nontrivial = nontrivial && !aggs[i].distinct;   // DISTINCT runs in passes over the materialised child
         if (nontrivial) cursor->FuseWith(plan);
       }
       delete describe_error;
@@ -1914,6 +2052,36 @@ FailureOrOwned<Cursor> BoundGroupAggregate(const BoundSingleSourceProjector* gro
   BufferAllocator* use = original_allocator ? original_allocator : HeapBufferAllocator::Get();
   return Success(static_cast<Cursor*>(new GroupCursor(result, use, child_cursor.release(), keys, agg->impl()->aggs,
                                                       static_cast<size_t>(agg->initial_row_capacity()), false)));
+}
+
+// aggregate.h:309-336: the reference's aggregation for inputs and DISTINCT sets larger than memory (it sorts and spills
+// to temporary files under `temporary_directory_prefix`). Here the groups are aggregated in HBM whatever the quota says
+// (host tables stream through in chunks), DISTINCT aggregates run as passes (GroupCursor::RunDistinct), nothing spills:
+// the result is the exact aggregation, every key once.
+Operation* HybridGroupAggregate(const SingleSourceProjector* group_by_columns, const AggregationSpecification* aggregation_specification,
+                                size_t, StringPiece, Operation* child) {
+  return new GroupAggregateOperation(group_by_columns, const_cast<AggregationSpecification*>(aggregation_specification), NULL, child,
+                                     /* no result budget */ true);
+}
+FailureOrOwned<Cursor> BoundHybridGroupAggregate(const SingleSourceProjector* group_by_columns,
+                                                 const AggregationSpecification& aggregation_specification, StringPiece,
+                                                 BufferAllocator* allocator, size_t, const HybridGroupDebugOptions* debug_options,
+                                                 Cursor* child) {
+  (void)debug_options;
+  std::unique_ptr<const SingleSourceProjector> group_by(group_by_columns);
+  std::unique_ptr<Cursor> child_cursor(child);
+  FailureOrOwned<const BoundSingleSourceProjector> proj = group_by->Bind(child_cursor->schema());
+  PROPAGATE_ON_FAILURE(proj);
+  TupleSchema result;
+  vector<int> keys;
+  for (int i = 0; i < proj->result_schema().attribute_count(); ++i) {
+    keys.push_back(proj->source_attribute_position(i));
+    result.add_attribute(proj->result_schema().attribute(i));
+  }
+  vector<BoundAggregation> aggs;
+  PROPAGATE_ON_FAILURE(BindAggregations(aggregation_specification, child_cursor->schema(), &aggs, &result));
+  return Success(static_cast<Cursor*>(new GroupCursor(result, allocator ? allocator : HeapBufferAllocator::Get(), child_cursor.release(),
+                                                      keys, aggs, 0, false)));
 }
 
 Cursor* BoundScalarAggregate(Aggregator* aggregator, Cursor* child) {

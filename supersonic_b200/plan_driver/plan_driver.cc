@@ -36,6 +36,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
 
 #include <deque>
@@ -400,6 +401,15 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
       op->SetBufferAllocator(new MemoryLimit(static_cast<size_t>(strtoull(Atom(s.kids[4]).c_str(), NULL, 10)), HeapBufferAllocator::Get()), false);
     }
     return op;
+  }
+  if (h == "hybrid_group") {
+    // (hybrid_group <memory quota> proj aggs child): aggregate.h:320
+    Arity(s, 4);
+    const size_t quota = static_cast<size_t>(strtoull(Atom(s.kids[1]).c_str(), NULL, 10));
+    const SingleSourceProjector* p = BuildProjector(s.kids[2]);
+    AggregationSpecification* a = BuildAggs(s.kids[3]);
+    mkdir("/tmp/ssplan_hybrid", 0700);   // the reference spills under this directory
+    return HybridGroupAggregate(p, a, quota, "/tmp/ssplan_hybrid", BuildOp(s.kids[4], in));
   }
   if (h == "scalar_agg") {
     Arity(s, 2);

@@ -263,6 +263,23 @@ GOLDEN_LATE = [
     ("bound_aggregate_clusters", "(bound_aggregate_clusters (named k) (aggs (MAX v mx) (LAST v l)) (scan 0))",
      [[col("k", sp.DOUBLE, [0.5, 0.5, -1.0, 0.5]), col("v", sp.INT64, [3, 9, 4, 1])]],
      {"k": [0.5, -1.0, 0.5], "mx": [9, 4, 1], "l": [9, 4, 1]}, True),
+    # cursor/core/column_aggregator.cc:333-433 (DistinctAggregator), aggregate_groups_test.cc DISTINCT cases: duplicates of
+    # the input inside a group count once, NULL inputs never count; MIN / MAX are unchanged by DISTINCT
+    ("group_distinct_count_with_plain_sum", "(group (named k) (aggs (distinct COUNT v c) (SUM v s)) (scan 0))",
+     [[col("k", sp.INT32, [1, 3, 1, 3, 1, 1]), ncol("v", sp.INT32, [3, -3, 3, -5, N, 4]), col("w", sp.DOUBLE, [1.5, 2.5, 1.5, 2.5, 1.5, 3.0])]],
+     {"k": [1, 3], "c": [2, 2], "s": [10, -8]}, False),
+    ("group_distinct_two_inputs", "(group (named k) (aggs (distinct SUM v s) (distinct COUNT w cw)) (scan 0))",
+     [[col("k", sp.INT32, [1, 3, 1, 3, 1, 1]), ncol("v", sp.INT32, [3, -3, 3, -5, N, 4]), col("w", sp.DOUBLE, [1.5, 2.5, 1.5, 2.5, 1.5, 3.0])]],
+     {"k": [1, 3], "s": [7, -8], "cw": [2, 1]}, False),
+    ("scalar_distinct", "(scalar_agg (aggs (distinct COUNT v c) (distinct SUM w sw) (COUNT \"\" n)) (scan 0))",
+     [[col("k", sp.INT32, [1, 3, 1, 3, 1, 1]), ncol("v", sp.INT32, [3, -3, 3, -5, N, 4]), col("w", sp.DOUBLE, [1.5, 2.5, 1.5, 2.5, 1.5, 3.0])]],
+     {"c": [4], "sw": [7.0], "n": [6]}, True),
+    ("group_distinct_min_max", "(group (named k) (aggs (distinct MIN v m) (distinct MAX w x)) (scan 0))",
+     [[col("k", sp.INT32, [1, 3, 1, 3, 1, 1]), ncol("v", sp.INT32, [3, -3, 3, -5, N, 4]), col("w", sp.DOUBLE, [1.5, 2.5, 1.5, 2.5, 1.5, 3.0])]],
+     {"k": [1, 3], "m": [3, -5], "x": [3.0, 2.5]}, False),
+    ("group_distinct_all_null_inputs", "(group (named k) (aggs (distinct COUNT v c) (distinct SUM v s)) (scan 0))",
+     [[ncol("k", sp.INT32, [1, N, 1, 2, N]), ncol("v", sp.INT64, [N, 5, N, 7, 5])]],
+     {"k": [1, N, 2], "c": [0, 1, 1], "s": [N, 5, 7]}, False),
 ]
 
 # STRING / BINARY columns: known-answer vectors of the reference's tests with their own STRING cells.

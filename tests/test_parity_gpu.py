@@ -633,3 +633,44 @@ def test_cursor_trees_over_a_file_scan_match_the_reference(ref, b200, tmp_path):
     assert ra.code == 0 and rb.code == 0, (ra.code, rb.code, rb.error)
     same_results(ra, rb)
     same_results(ref.run("(file_read %s 0)" % fa, table), ref.run("(file_read %s 0)" % fb, table))
+
+
+@pytest.mark.parametrize("groups", [7, 3000])
+def test_distinct_aggregates_match_the_reference(ref, b200, groups):
+    """COUNT / SUM DISTINCT (column_aggregator.cc:333-433) beside plain aggregates, over nullable inputs, NULL keys, two
+    key columns, DOUBLE and STRING inputs, under a Filter + Compute child, and as a ScalarAggregate: the passes of
+    GroupCursor::RunDistinct against the reference's per-group hash sets."""
+    rng = np.random.default_rng(groups)
+    rows = 40000
+    words = ["ab", "", "Supersonic", "B200", "columnar", "x"]
+    t = [[sp.Column("k", sp.INT64, rng.integers(0, groups, rows), is_null=rng.random(rows) < 0.03),
+          sp.Column("k2", sp.INT32, rng.integers(0, 3, rows)),
+          sp.Column("v", sp.INT64, rng.integers(-20, 20, rows), is_null=rng.random(rows) < 0.1),
+          sp.Column("w", sp.DOUBLE, rng.integers(0, 16, rows) / 4.0),
+          sp.Column("s", sp.STRING, [words[i] for i in rng.integers(0, len(words), rows)], is_null=rng.random(rows) < 0.05),
+          sp.Column("u", sp.INT32, rng.integers(0, 1000, rows))]]
+    plans = [
+        "(group (named k) (aggs (distinct COUNT v cv) (distinct SUM v sv) (SUM v s) (COUNT \"\" n) (MIN w mw)) (scan 0))",
+        "(group (named k k2) (aggs (distinct SUM w sw) (distinct COUNT v cv) (distinct COUNT s cs) (MAX u mu)) (scan 0))",
+        "(group (named k2) (aggs (distinct COUNT u cu) (distinct SUM u su)) (scan 0))",
+        "(scalar_agg (aggs (distinct COUNT v cv) (distinct SUM w sw) (distinct COUNT s cs) (COUNT \"\" n)) (scan 0))",
+        "(group (named k2) (aggs (distinct COUNT e ce) (SUM e se)) (compute (compound (col k2) (as e (plus (col v) (col u)))) "
+        "(filter (less (col u) (i32 500)) (all) (scan 0))))",
+        "(group (named k) (aggs (distinct COUNT v cv)) (scan 0))",
+    ]
+    for plan in plans:
+        same_results(ref.run(plan, t), b200.run(plan, t), ordered=False)
+
+
+@pytest.mark.parametrize("quota", [64, 1 << 30])
+def test_hybrid_group_aggregate_matches_the_reference(ref, b200, quota):
+    """aggregate.h:309-336 HybridGroupAggregate: exact aggregation, DISTINCT included, whatever the memory quota (the
+    reference spills sorted runs to temporary files; here the groups live in HBM)."""
+    rng = np.random.default_rng(quota % 1000)
+    rows = 20000
+    t = [[sp.Column("k", sp.INT64, rng.integers(0, 500, rows), is_null=rng.random(rows) < 0.03),
+          sp.Column("v", sp.INT64, rng.integers(-20, 20, rows), is_null=rng.random(rows) < 0.1),
+          sp.Column("w", sp.DOUBLE, rng.integers(0, 16, rows) / 4.0)]]
+    for plan in ["(hybrid_group %d (named k) (aggs (distinct COUNT v c) (SUM v s) (distinct SUM w sw) (COUNT \"\" n)) (scan 0))" % quota,
+                 "(hybrid_group %d (named k) (aggs (SUM v s) (MIN w m)) (scan 0))" % quota]:
+        same_results(ref.run(plan, t), b200.run(plan, t), ordered=False)

@@ -309,6 +309,20 @@ __device__ __forceinline__ void emit_cell(void* dst, unsigned long long o, const
   else static_cast<unsigned char*>(dst)[o] = i >= 0 ? static_cast<const unsigned char*>(src)[i] : static_cast<unsigned char>(0);
 }
 
+// A result cell read early (its load is in flight while the tile's ranks and prefix are computed) and written late.
+enum { kEmitEarly = 2 };   // columns per side whose cells are read early (registers: 2 sides x 2 columns x 4 rows x 8 bytes)
+__device__ __forceinline__ unsigned long long load_cell(const void* src, long long i, int w) {
+  if (i < 0) return 0ull;
+  if (w == 8) return static_cast<const unsigned long long*>(src)[i];
+  if (w == 4) return static_cast<const uint32_t*>(src)[i];
+  return static_cast<const unsigned char*>(src)[i];
+}
+__device__ __forceinline__ void store_cell(void* dst, unsigned long long o, unsigned long long v, int w) {
+  if (w == 8) static_cast<unsigned long long*>(dst)[o] = v;
+  else if (w == 4) static_cast<uint32_t*>(dst)[o] = static_cast<uint32_t>(v);
+  else static_cast<unsigned char*>(dst)[o] = static_cast<unsigned char>(v);
+}
+
 template <bool PARTS, bool EMIT, bool DENSE>
 __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTable t, JoinKeys build, JoinKeys probe,
                                                                            long long rows, int left_outer,
@@ -394,14 +408,34 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
       }
     }
     }   // !DENSE
+    // EMIT: the first cells of every pair are requested now -- lhs cells depend on the row only, rhs cells on the
+    // match -- so their (random, for the rhs) loads overlap the ranking and the look-back below instead of following them
+    unsigned long long lv_early[kEmitEarly][kProbeRows], rv_early[kEmitEarly][kProbeRows];
+    if (EMIT) {
+#pragma unroll
+      for (int c = 0; c < kEmitEarly; ++c) {
+#pragma unroll
+        for (int j = 0; j < kProbeRows; ++j) {
+          const long long row = r0 + j * kProbeThreads;
+          const bool wanted = row < rows && (left_outer || head[j] >= 0);
+          lv_early[c][j] = (c < emit.n_l && wanted) ? load_cell(emit.l_src[c], row, emit.l_w[c]) : 0ull;
+          rv_early[c][j] = (c < emit.n_r && wanted) ? load_cell(emit.r_src[c], head[j], emit.r_w[c]) : 0ull;
+        }
+      }
+    }
     if (left_outer) {
 #pragma unroll
       for (int j = 0; j < kProbeRows; ++j) {
         const long long row = r0 + j * kProbeThreads;
         if (row >= rows) continue;
         if (EMIT) {
-          for (int c = 0; c < emit.n_l; ++c) emit_cell(emit.l_dst[c], static_cast<unsigned long long>(row), emit.l_src[c], row, emit.l_w[c]);
-          for (int c = 0; c < emit.n_r; ++c) emit_cell(emit.r_dst[c], static_cast<unsigned long long>(row), emit.r_src[c], head[j], emit.r_w[c]);
+#pragma unroll
+          for (int c = 0; c < kEmitEarly; ++c) {
+            if (c < emit.n_l) store_cell(emit.l_dst[c], static_cast<unsigned long long>(row), lv_early[c][j], emit.l_w[c]);
+            if (c < emit.n_r) store_cell(emit.r_dst[c], static_cast<unsigned long long>(row), rv_early[c][j], emit.r_w[c]);
+          }
+          for (int c = kEmitEarly; c < emit.n_l; ++c) emit_cell(emit.l_dst[c], static_cast<unsigned long long>(row), emit.l_src[c], row, emit.l_w[c]);
+          for (int c = kEmitEarly; c < emit.n_r; ++c) emit_cell(emit.r_dst[c], static_cast<unsigned long long>(row), emit.r_src[c], head[j], emit.r_w[c]);
           if (emit.matched != nullptr) emit.matched[row] = head[j] >= 0 ? 1 : 0;
         } else {
           lhs_out[row] = row;
@@ -445,8 +479,13 @@ __global__ void __launch_bounds__(kProbeThreads) join_probe_unique_kernel(JoinTa
         const unsigned long long o = base + before[j] + pos[j];
         if (EMIT) {
           const long long row = r0 + j * kProbeThreads;
-          for (int c = 0; c < emit.n_l; ++c) emit_cell(emit.l_dst[c], o, emit.l_src[c], row, emit.l_w[c]);
-          for (int c = 0; c < emit.n_r; ++c) emit_cell(emit.r_dst[c], o, emit.r_src[c], head[j], emit.r_w[c]);
+#pragma unroll
+          for (int c = 0; c < kEmitEarly; ++c) {
+            if (c < emit.n_l) store_cell(emit.l_dst[c], o, lv_early[c][j], emit.l_w[c]);
+            if (c < emit.n_r) store_cell(emit.r_dst[c], o, rv_early[c][j], emit.r_w[c]);
+          }
+          for (int c = kEmitEarly; c < emit.n_l; ++c) emit_cell(emit.l_dst[c], o, emit.l_src[c], row, emit.l_w[c]);
+          for (int c = kEmitEarly; c < emit.n_r; ++c) emit_cell(emit.r_dst[c], o, emit.r_src[c], head[j], emit.r_w[c]);
         } else {
           lhs_out[o] = r0 + j * kProbeThreads;
           rhs_out[o] = head[j];

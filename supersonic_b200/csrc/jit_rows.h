@@ -152,7 +152,7 @@ __device__ __noinline__ void jit_overflow(const GroupParams& p, int a, long long
 }
 struct JitLocal {
   unsigned long long l_key[Spec::G][jit_max1(Spec::NK)];
-  unsigned long long l_fp[Spec::G];
+  unsigned int l_fp[Spec::G];   // 32-bit fingerprints: a hit is confirmed against l_key / l_knull
   unsigned int l_knull[Spec::G];
   unsigned int l_slot[Spec::G];
   unsigned int l_ready;
@@ -162,7 +162,7 @@ struct JitLocal {
 struct JitKey { unsigned long long v[jit_max1(Spec::NK)]; };   // by value: the key stays in registers at the call
 // Returns the slot in the high word ((slot + 1) << 8, 0 = defer the row) and the local entry + 1 in the low byte (0 = none).
 __device__ __noinline__ unsigned long long jit_claim(const GroupParams& p, JitLocal& L, const JitKey key, unsigned int knull,
-                                                     unsigned long long fp) {
+                                                     unsigned int fp) {
   constexpr int G = Spec::G, NK = Spec::NK;
   const unsigned long long* kv = key.v;
   const long long slot = p.packed ? find_slot_packed_kv(p, (knull & 1u) != 0, kv[0]) : find_slot_generic_kv(p, kv, knull);
@@ -227,7 +227,7 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
   if (tid == 0) L.l_ready = 0u;
   __syncthreads();
   unsigned int my_ready = 0;
-  unsigned long long my_fp[G];
+  unsigned int my_fp[G];
 #pragma unroll
   for (int e = 0; e < G; ++e) my_fp[e] = 0;
   uint32_t fail = 0;
@@ -279,7 +279,7 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
     if (ready_now != my_ready) {
       my_ready = ready_now;
 #pragma unroll
-      for (int e = 0; e < G; ++e) if ((my_ready >> e) & 1u) my_fp[e] = *reinterpret_cast<volatile unsigned long long*>(&L.l_fp[e]);
+      for (int e = 0; e < G; ++e) if ((my_ready >> e) & 1u) my_fp[e] = *reinterpret_cast<volatile unsigned int*>(&L.l_fp[e]);
     }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -293,12 +293,16 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
         kv[c] = 0;
         if ((s.on[c] >> j) & 1u) knull |= 1u << c; else kv[c] = s.ov[c][j];
       }
-      unsigned long long fp = 0x9E3779B97F4A7C15ull + knull;
+      // a cheap 32-bit fingerprint (the keys are compared in full after a hit): one multiply-add per key half
+      unsigned int fp = 0x9E3779B9u + knull;
 #pragma unroll
-      for (int c = 0; c < NK; ++c) fp = (fp ^ kv[c]) * 0xff51afd7ed558ccdULL + c;
+      for (int c = 0; c < NK; ++c) {
+        fp = (fp ^ static_cast<unsigned int>(kv[c])) * 0x85EBCA77u + static_cast<unsigned int>(kv[c] >> 32) * 0xC2B2AE3Du;
+      }
       int g = -1;
 #pragma unroll
-      for (int e = 0; e < G; ++e) if (((my_ready >> e) & 1u) && my_fp[e] == fp) g = e;
+      for (int e = 0; e < G; ++e) if (my_fp[e] == fp) g = e;
+      if (g >= 0 && !((my_ready >> g) & 1u)) g = -1;   // an entry this thread has not seen published yet
       if (g >= 0) {
         bool same = L.l_knull[g] == knull;
 #pragma unroll

@@ -14,8 +14,7 @@ def run(tag):
 os.environ["SSB200_GROUP_JIT"] = "0"
 run("interpreting sink")
 os.environ["SSB200_GROUP_JIT"] = "1"
-for t, r_, mc, pf in ((192, 1, "", 1), (192, 1, "", 2), (160, 1, "", 1), (160, 1, "", 2), (224, 1, "", 1), (256, 1, "", 2), (320, 1, "2", 1),
-                      (320, 1, "2", 2), (384, 1, "1", 2), (128, 1, "", 2), (192, 1, "", 0), (192, 2, "", 0)):
+for t, r_, mc, pf in ((192, 1, "", 1), (256, 1, "", 1), (224, 1, "", 1), (192, 1, "", 2)):
     os.environ["SSB200_JIT_THREADS"], os.environ["SSB200_JIT_ROWS"], os.environ["SSB200_JIT_PREFETCH"] = str(t), str(r_), str(pf)
     if mc:
         os.environ["SSB200_JIT_MIN_CTAS"] = mc

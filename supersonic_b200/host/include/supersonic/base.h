@@ -86,6 +86,9 @@ struct Voidify { void operator&(std::ostream&) {} };
 #define DCHECK_EQ(a, b) CHECK_EQ(a, b)
 #endif
 
+// utils/basictypes.h:14-17 (global, as in the reference): who closes a File handed to a sink
+enum Ownership { DO_NOT_TAKE_OWNERSHIP, TAKE_OWNERSHIP };
+
 namespace supersonic {
 
 using std::string;

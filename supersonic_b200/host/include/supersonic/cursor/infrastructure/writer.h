@@ -24,17 +24,21 @@ class Sink {
 class Writer {
  public:
   explicit Writer(Cursor* cursor) : cursor_(cursor), pending_(TupleSchema()), eos_(false), barrier_(false) {}
+
+  // state of the input after the last Write
+  bool is_eos() const { return eos_; }
+  bool is_waiting_on_barrier() const { return barrier_; }
+  const TupleSchema& schema() const { return cursor_->schema(); }
+  void Interrupt() { cursor_->Interrupt(); }
+
   // Writes at most max_row_count rows; fewer when the input ends, waits on a barrier or the sink takes fewer.
   FailureOr<rowcount_t> Write(Sink* sink, rowcount_t max_row_count);
   FailureOr<rowcount_t> WriteAll(Sink* sink) { return Write(sink, std::numeric_limits<rowcount_t>::max()); }
-  const TupleSchema& schema() const { return cursor_->schema(); }
-  bool is_eos() const { return eos_; }
-  bool is_waiting_on_barrier() const { return barrier_; }
-  void Interrupt() { cursor_->Interrupt(); }
+
  private:
+  bool has_pending() const { return pending_.column_count() == cursor_->schema().attribute_count() && pending_.row_count() > 0; }
   std::unique_ptr<Cursor> cursor_;
   View pending_;           // rows of the last Next() the sink has not taken yet
-  bool has_pending() const { return pending_.column_count() == cursor_->schema().attribute_count() && pending_.row_count() > 0; }
   bool eos_, barrier_;
 };
 

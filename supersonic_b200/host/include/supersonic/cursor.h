@@ -196,6 +196,13 @@ class TableRowWriter {
 Operation* Generate(rowcount_t count);
 FailureOrOwned<Cursor> BoundGenerate(rowcount_t count);
 
+// cursor/core/limit.h:27-30: rows [offset, offset + limit) of the child, in the child's order
+Operation* Limit(rowcount_t offset, rowcount_t limit, Operation* child);
+Cursor* BoundLimit(rowcount_t offset, rowcount_t limit, Cursor* child);
+// cursor/core/coalesce.h:30-34: the columns of the children side by side (equal row counts, distinct attribute names)
+Operation* Coalesce(const vector<Operation*>& children);
+FailureOrOwned<Cursor> BoundCoalesce(const vector<Cursor*>& children);
+
 // ---- row-wise operators ------------------------------------------------------------------
 Operation* Compute(const Expression* computation, Operation* child);                  // compute.h:32
 Operation* Filter(const Expression* predicate, const SingleSourceProjector* projector,

@@ -1879,7 +1879,140 @@ class MergeUnionAllOperation : public BasicOperation {
   std::unique_ptr<const SortOrder> order_;
 };
 
+// ------------------------------------------------------------------ Limit / Coalesce
+// cursor/core/limit.cc: skips `offset` rows of the child, then passes at most `limit` rows on. No computation: the views the
+// child hands out are sliced (a GPU child's result is already on the host when Next() returns it).
+class LimitCursor : public Cursor {
+ public:
+  LimitCursor(rowcount_t offset, rowcount_t limit, Cursor* child)
+      : child_(child), view_(child->schema()), to_skip_(offset), to_pass_(limit) {}
+  virtual const TupleSchema& schema() const { return child_->schema(); }
+  virtual ResultView Next(rowcount_t max_row_count) {
+    for (;;) {
+      if (to_pass_ == 0) return ResultView::EOS();
+      ResultView r = child_->Next(to_skip_ > 0 ? max_row_count : std::min(max_row_count, to_pass_));
+      if (!r.has_data()) return r;
+      rowcount_t n = r.view().row_count(), first = 0;
+      if (to_skip_ > 0) {
+        const rowcount_t skipped = std::min(to_skip_, n);
+        to_skip_ -= skipped;
+        first = skipped;
+        n -= skipped;
+        if (n == 0) continue;
+      }
+      n = std::min(n, to_pass_);
+      to_pass_ -= n;
+      view_.ResetFromSubRange(r.view(), first, n);
+      return ResultView::Success(&view_);
+    }
+  }
+  virtual void Interrupt() { child_->Interrupt(); }
+  virtual bool IsWaitingOnBarrierSupported() const { return child_->IsWaitingOnBarrierSupported(); }
+  virtual void ApplyToChildren(CursorTransformer* transformer) { child_.reset(transformer->Transform(child_.release())); }
+  virtual void AppendDebugDescription(string* target) const {
+    target->append("LimitCursor(");
+    child_->AppendDebugDescription(target);
+    target->append(")");
+  }
+ private:
+  std::unique_ptr<Cursor> child_;
+  View view_;
+  rowcount_t to_skip_, to_pass_;
+};
+
+class LimitOperation : public BasicOperation {
+ public:
+  LimitOperation(rowcount_t offset, rowcount_t limit, Operation* child) : BasicOperation(child), offset_(offset), limit_(limit) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    FailureOrOwned<Cursor> c = child()->CreateCursor();
+    PROPAGATE_ON_FAILURE(c);
+    return Success(static_cast<Cursor*>(new LimitCursor(offset_, limit_, c.release())));
+  }
+ protected:
+  virtual string DebugName() const { return "Limit"; }
+ private:
+  rowcount_t offset_, limit_;
+};
+
+// cursor/core/coalesce.cc: the columns of several inputs side by side (distinct attribute names); the stream ends when the
+// shortest input does. On the device the result references the inputs' columns: nothing is copied.
+class CoalesceCursor : public GpuCursor {
+ public:
+  CoalesceCursor(const TupleSchema& schema, BufferAllocator* allocator, vector<Cursor*>* inputs)
+      : GpuCursor(schema, allocator, "CoalesceCursor") {
+    for (size_t i = 0; i < inputs->size(); ++i) inputs_.push_back(std::unique_ptr<Cursor>((*inputs)[i]));
+    inputs->clear();
+  }
+  virtual void Interrupt() { GpuCursor::Interrupt(); for (size_t i = 0; i < inputs_.size(); ++i) inputs_[i]->Interrupt(); }
+  virtual void ApplyToChildren(CursorTransformer* transformer) {
+    for (size_t i = 0; i < inputs_.size(); ++i) inputs_[i].reset(transformer->Transform(inputs_[i].release()));
+  }
+ protected:
+  virtual FailureOrVoid Run(DeviceTable* result) {
+    parts_.resize(inputs_.size());
+    keep_.resize(inputs_.size());
+    result->schema = schema();
+    result->columns.clear();
+    result->rows = 0;
+    for (size_t i = 0; i < inputs_.size(); ++i) {
+      PROPAGATE_ON_FAILURE(MaterializeOnDevice(inputs_[i].get(), &parts_[i], &keep_[i]));
+      for (size_t c = 0; c < parts_[i].columns.size(); ++c) result->columns.push_back(parts_[i].columns[c]);
+      // coalesce.cc: the stream ends with its shortest input
+      result->rows = i == 0 ? parts_[i].rows : std::min(result->rows, parts_[i].rows);
+    }
+    return Success();
+  }
+ private:
+  vector<std::unique_ptr<Cursor> > inputs_;
+  vector<DeviceTable> parts_;                  // keep the inputs' columns alive
+  vector<std::unique_ptr<Block> > keep_;
+};
+
+FailureOr<TupleSchema> CoalescedSchema(const vector<Cursor*>& inputs) {
+  TupleSchema schema;
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    for (int c = 0; c < inputs[i]->schema().attribute_count(); ++c) {
+      if (!schema.add_attribute(inputs[i]->schema().attribute(c))) {
+        THROW(new Exception(ERROR_ATTRIBUTE_EXISTS, "Can't coalesce, ambiguous attribute name: " + inputs[i]->schema().attribute(c).name()));
+      }
+    }
+  }
+  return Success(schema);
+}
+
+class CoalesceOperation : public BasicOperation {
+ public:
+  explicit CoalesceOperation(const vector<Operation*>& children) : BasicOperation(children) {}
+  virtual FailureOrOwned<Cursor> CreateCursor() const {
+    vector<Cursor*> inputs;
+    struct Deleter { vector<Cursor*>* v; ~Deleter() { for (size_t i = 0; i < v->size(); ++i) delete (*v)[i]; } } deleter = {&inputs};
+    for (size_t i = 0; i < children_count(); ++i) {
+      FailureOrOwned<Cursor> c = child_at(i)->CreateCursor();
+      PROPAGATE_ON_FAILURE(c);
+      inputs.push_back(c.release());
+    }
+    FailureOr<TupleSchema> schema = CoalescedSchema(inputs);
+    PROPAGATE_ON_FAILURE(schema);
+    return Success(static_cast<Cursor*>(new CoalesceCursor(schema.get(), buffer_allocator(), &inputs)));
+  }
+ protected:
+  virtual string DebugName() const { return "Coalesce"; }
+};
+
 }  // namespace
+
+Operation* Limit(rowcount_t offset, rowcount_t limit, Operation* child) { return new LimitOperation(offset, limit, child); }
+Cursor* BoundLimit(rowcount_t offset, rowcount_t limit, Cursor* child) { return new LimitCursor(offset, limit, child); }
+Operation* Coalesce(const vector<Operation*>& children) { return new CoalesceOperation(children); }
+FailureOrOwned<Cursor> BoundCoalesce(const vector<Cursor*>& children) {
+  vector<Cursor*> inputs(children);
+  FailureOr<TupleSchema> schema = CoalescedSchema(inputs);
+  if (schema.is_failure()) {
+    for (size_t i = 0; i < inputs.size(); ++i) delete inputs[i];
+    return Failure(schema.release_exception());
+  }
+  return Success(static_cast<Cursor*>(new CoalesceCursor(schema.get(), HeapBufferAllocator::Get(), &inputs)));
+}
 
 Operation* MergeUnionAll(const SortOrder* sort_order, const vector<Operation*>& inputs) {
   std::unique_ptr<const SortOrder> order(sort_order);

@@ -402,6 +402,18 @@ Operation* BuildOp(const Sx& s, const Inputs& in) {
     }
     return op;
   }
+  if (h == "limit") {
+    // (limit OFFSET LIMIT child): limit.h:27
+    Arity(s, 3);
+    return Limit(static_cast<rowcount_t>(strtoull(Atom(s.kids[1]).c_str(), NULL, 10)),
+                 static_cast<rowcount_t>(strtoull(Atom(s.kids[2]).c_str(), NULL, 10)), BuildOp(s.kids[3], in));
+  }
+  if (h == "coalesce") {
+    // (coalesce child child ...): coalesce.h:30
+    std::vector<Operation*> children;
+    for (size_t i = 1; i < s.kids.size(); ++i) children.push_back(BuildOp(s.kids[i], in));
+    return Coalesce(children);
+  }
   if (h == "hybrid_group") {
     // (hybrid_group <memory quota> proj aggs child): aggregate.h:320
     Arity(s, 4);

@@ -280,6 +280,26 @@ GOLDEN_LATE = [
     ("group_distinct_all_null_inputs", "(group (named k) (aggs (distinct COUNT v c) (distinct SUM v s)) (scan 0))",
      [[ncol("k", sp.INT32, [1, N, 1, 2, N]), ncol("v", sp.INT64, [N, 5, N, 7, 5])]],
      {"k": [1, N, 2], "c": [0, 1, 1], "s": [N, 5, 7]}, False),
+    # cursor/core/limit.h:27 (limit_test.cc): rows [offset, offset + limit) in the child's order; coalesce.h:30
+    # (coalesce_test.cc): the children's columns side by side, the stream ends with its shortest input
+    ("limit_middle", "(limit 2 5 (scan 0))",
+     [[col("a", sp.INT32, list(range(10))), ncol("s", sp.STRING, ["x", N, "yy", "z", "", "q", N, "w", "e", "r"])]],
+     {"a": [2, 3, 4, 5, 6], "s": [b"yy", b"z", b"", b"q", N]}, True),
+    ("limit_past_the_end", "(limit 9 5 (scan 0))",
+     [[col("a", sp.INT32, list(range(10))), ncol("s", sp.STRING, ["x", N, "yy", "z", "", "q", N, "w", "e", "r"])]],
+     {"a": [9], "s": [b"r"]}, True),
+    ("limit_nothing", "(limit 20 5 (scan 0))",
+     [[col("a", sp.INT32, list(range(10))), ncol("s", sp.STRING, ["x", N, "yy", "z", "", "q", N, "w", "e", "r"])]],
+     {"a": [], "s": []}, True),
+    ("limit_over_sort", "(limit 1 3 (sort (order (a DESC)) (all) (scan 0)))",
+     [[col("a", sp.INT32, [5, 1, 9, 7, 3])]],
+     {"a": [7, 5, 3]}, True),
+    ("coalesce_two", "(limit 1 3 (coalesce (scan 0) (compute (as c (plus (col b) (i64 1))) (scan 1))))",
+     [[col("a", sp.INT32, list(range(10)))], [col("b", sp.INT64, [i * 10 for i in range(10)])]],
+     {"a": [1, 2, 3], "c": [11, 21, 31]}, True),
+    ("coalesce_shortest_input", "(coalesce (scan 0) (scan 1))",
+     [[col("b", sp.INT64, [i * 10 for i in range(10)])], [col("a", sp.INT64, [1, 2, 3])]],
+     {"b": [0, 10, 20], "a": [1, 2, 3]}, True),
 ]
 
 # STRING / BINARY columns: known-answer vectors of the reference's tests with their own STRING cells.

@@ -675,6 +675,82 @@ def test_probe_materialize_equals_probe_plus_gather(ctx, join_type, compact):
     ctx.lib.ssb_join_destroy(j)
 
 
+@pytest.mark.parametrize("n_parts", [2, 5])
+@pytest.mark.parametrize("join_type", [0, 1])
+def test_attached_table_parts_equal_host(ctx, join_type, n_parts):
+    """The replicated form of the sharded join on ONE GPU (what csrc/shard_join.cu does over NCCL): the build keys are
+    hash-partitioned (ssb_partition_rows), every part gets its own compact table, the tables are attached as one index
+    (ssb_join_attach_parts) and probed with the pairs-only and the materialising probe; NULL keys on both sides, keys
+    without a build row. rhs rows are reported in part order (row_offsets[part] + row inside the part)."""
+    rng = np.random.default_rng(n_parts * 10 + join_type)
+    nb, npr = 50_000, 200_003
+    pk = rng.permutation(nb * 50)[:nb].astype(np.int64) - 1_000_000          # sparse: the slot tables, not the dense index
+    pk_null = rng.random(nb) < 0.03
+    pay = rng.integers(-2**62, 2**62, nb)
+    fk = rng.integers(-1_000_100, nb * 50 - 999_900, npr)
+    fk_null = rng.random(npr) < 0.05
+    lv = rng.integers(0, 1000, npr)
+    d_pk, d_pkn = _upload(ctx, pk, pk_null)
+    d_pay, _ = _upload(ctx, pay)
+    d_fk, d_fkn = _upload(ctx, fk, fk_null)
+    d_lv, _ = _upload(ctx, lv)
+    lib = ctx.lib
+    # partition the build rows: parts 0 .. n_parts-1 by key hash, NULL keys set aside in part n_parts
+    d_perm = ctx.malloc(nb * 8 + 256)
+    counts = (C.c_int64 * (n_parts + 1))()
+    ctx.check(lib.ssb_partition_rows(ctx.h, 1, _cols([(d_pk, d_pkn, capi.INT64)]), nb, n_parts, n_parts, d_perm, counts))
+    perm = np.empty(nb, dtype=np.int64)
+    ctx.d2h(perm, d_perm)
+    sent = sum(counts[p] for p in range(n_parts))
+    assert counts[n_parts] == int(pk_null.sum()) and sent == nb - int(pk_null.sum())
+    d_pk_parts = ctx.malloc(nb * 8 + 256)
+    d_pay_parts = ctx.malloc(nb * 8 + 256)
+    ctx.check(lib.ssb_gather(ctx.h, _cols([(d_pk, None, capi.INT64)]), d_perm, sent, _cols([(d_pk_parts, None, capi.INT64)])))
+    ctx.check(lib.ssb_gather(ctx.h, _cols([(d_pay, None, capi.INT64)]), d_perm, sent, _cols([(d_pay_parts, None, capi.INT64)])))
+    joins, slots, caps, offs = [], (C.c_void_p * n_parts)(), (C.c_int64 * n_parts)(), (C.c_int64 * n_parts)()
+    at = 0
+    for p in range(n_parts):
+        j = C.c_void_p()
+        ctx.check(lib.ssb_join_build(ctx.h, 1, _cols([(d_pk_parts + at * 8, None, capi.INT64)]), counts[p], 1 | 0x100, C.byref(j)))
+        s_, c_ = C.c_void_p(), C.c_int64()
+        ctx.check(lib.ssb_join_table(j, C.byref(s_), C.byref(c_)))
+        joins.append(j)
+        slots[p], caps[p], offs[p] = s_.value, c_.value, at
+        at += counts[p]
+    idx = C.c_void_p()
+    ctx.check(lib.ssb_join_attach_parts(ctx.h, capi.INT64, n_parts, slots, caps, offs, C.byref(idx)))
+    # expected: build rows renumbered in part order
+    pos_in_parts = {int(pk[r]): i for i, r in enumerate(perm[:sent])}
+    hit = np.array([(-1 if fk_null[i] else pos_in_parts.get(int(fk[i]), -1)) for i in range(npr)])
+    keep = np.arange(npr) if join_type == 1 else np.nonzero(hit >= 0)[0]
+    n, pl, pr = C.c_int64(), C.c_void_p(), C.c_void_p()
+    ctx.check(lib.ssb_join_probe(idx, _cols([(d_fk, d_fkn, capi.INT64)]), npr, join_type, C.byref(n), C.byref(pl), C.byref(pr)))
+    assert n.value == len(keep)
+    li, ri = np.empty(n.value, dtype=np.int64), np.empty(n.value, dtype=np.int64)
+    ctx.d2h(li, pl)
+    ctx.d2h(ri, pr)
+    assert np.array_equal(li, keep) and np.array_equal(ri, hit[keep])
+    o_lv, o_pay = ctx.malloc(npr * 8 + 256), ctx.malloc(npr * 8 + 256)
+    d_match = ctx.malloc(npr + 256)
+    m = C.c_int64()
+    ctx.check(lib.ssb_join_probe_materialize(idx, _cols([(d_fk, d_fkn, capi.INT64)]), npr, join_type, 1, _cols([(d_lv, None, capi.INT64)]),
+                                             1, _cols([(d_pay_parts, None, capi.INT64)]),
+                                             _cols([(o_lv, None, capi.INT64), (o_pay, None, capi.INT64)]), d_match, C.byref(m)))
+    assert m.value == len(keep)
+    got_lv, got_pay = np.empty(m.value, dtype=np.int64), np.empty(m.value, dtype=np.int64)
+    ctx.d2h(got_lv, o_lv)
+    ctx.d2h(got_pay, o_pay)
+    h = hit[keep]
+    pay_parts = pay[perm[:sent]]
+    assert np.array_equal(got_lv, lv[keep])
+    assert np.array_equal(got_pay, np.where(h >= 0, pay_parts[np.maximum(h, 0)], 0))
+    lib.ssb_join_destroy(idx)
+    for j in joins:
+        lib.ssb_join_destroy(j)
+    for d in (d_pk, d_pkn, d_pay, d_fk, d_fkn, d_lv, d_perm, d_pk_parts, d_pay_parts, o_lv, o_pay, d_match):
+        ctx.free(d)
+
+
 @pytest.mark.parametrize("build_dtype,probe_dtype", [(np.int64, np.int64), (np.int32, np.int64), (np.uint32, np.int32)])
 @pytest.mark.parametrize("lo,spread", [(0, 2), (-50_000, 3), (2**31 - 120_000, 1), (-2**40, 2), (0, 1000)])
 def test_join_dense_integer_keys_equal_host(ctx, lo, spread, build_dtype, probe_dtype):

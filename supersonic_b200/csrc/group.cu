@@ -1809,6 +1809,8 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   const int jit_mode = jit_env == nullptr ? -1 : atoi(jit_env);   // -1: by size, 0: never, 1: always
   const char* jit_rows_env = getenv("SSB200_JIT_MIN_ROWS");
   const long long jit_min_rows = jit_rows_env != nullptr ? atoll(jit_rows_env) : (1LL << 26);
+  const char* jit_many_env = getenv("SSB200_JIT_MANY_GROUPS");
+  const long long jit_many_groups = jit_many_env != nullptr ? atoll(jit_many_env) : 4096;
   bool jit_ok = rows_feasible && !float_key && n_in <= kJitMaxIn;
   if (rows_feasible) {
     rp.n_insn = static_cast<int32_t>(prog.generic.size());
@@ -1852,11 +1854,16 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
     // (tests), 0 disables it; by default a call with at least SSB200_JIT_MIN_ROWS rows (64M) pays the compilation.
     JitLaunch jl;
     bool use_jit = false;
-    if (jit_mode != 0 && jit_ok && (jit_mode == 1 || rows >= jit_min_rows) &&
-        (g->n_keys == 0 || (g->rows_seen >= kProbeRowsFirst ? g->h_counters[0] <= kTinyGroups : jit_mode == 1))) {
+    // few groups: CTA-local accumulators for exactly the groups seen so far; many groups (>= SSB200_JIT_MANY_GROUPS,
+    // 4096): no local entries, every row goes to the global table (atomics on a few hot groups would serialise, so the
+    // range in between keeps the materialising form)
+    const bool groups_known = g->rows_seen >= kProbeRowsFirst;
+    const bool few_groups = g->n_keys == 0 || (groups_known ? g->h_counters[0] <= kTinyGroups : jit_mode == 1);
+    const bool many_groups = g->n_keys > 0 && groups_known && static_cast<long long>(g->h_counters[0]) >= jit_many_groups;
+    if (jit_mode != 0 && jit_ok && (jit_mode == 1 || rows >= jit_min_rows) && (few_groups || many_groups)) {
       memset(&jl, 0, sizeof(jl));
       jl.shape.n_keys = g->n_keys; jl.shape.n_aggs = A;
-      jl.shape.groups = g->n_keys == 0 ? 1 : (g->rows_seen >= kProbeRowsFirst ? static_cast<int>(g->h_counters[0] < 1 ? 1 : g->h_counters[0]) : kTinyGroups);
+      jl.shape.groups = g->n_keys == 0 ? 1 : many_groups ? 0 : (groups_known ? static_cast<int>(g->h_counters[0] < 1 ? 1 : g->h_counters[0]) : kTinyGroups);
       jit_rows_tune(&jl.shape);
       for (int a = 0; a < A; ++a) {
         jl.shape.fn[a] = g->aggs[a].fn;

@@ -121,7 +121,7 @@ std::string jit_rows_source(const Program& prog, const JitRowsShape& sh, std::st
   const int n_in = static_cast<int>(prog.input_types.size());
   const int n_out = static_cast<int>(prog.outputs.size());
   const int n_slot = n_in + prog.params.n_tmp;
-  if (n_in > kJitMaxIn || sh.n_aggs < 1 || sh.n_aggs > kLocalMaxAggs || sh.n_keys > kMaxKeys || sh.groups < 1 || sh.groups > kTinyGroups ||
+  if (n_in > kJitMaxIn || sh.n_aggs < 1 || sh.n_aggs > kLocalMaxAggs || sh.n_keys > kMaxKeys || sh.groups < 0 || sh.groups > kTinyGroups ||
       sh.rows_per_thread < 1 || sh.rows_per_thread > 8 || sh.threads % 32 != 0 || sh.threads < 32 || sh.threads > 1024) {
     if (err) *err = "plan outside the limits of the specialised aggregation kernel";
     return std::string();

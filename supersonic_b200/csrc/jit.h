@@ -20,7 +20,7 @@ struct JitKernel {
 struct JitRowsShape {
   int n_keys, n_aggs;
   int fn[16], in_phys[16], out_phys[16], out[16];   // out: program output feeding aggregate a, -1 = COUNT(*)
-  int groups;          // CTA-local group entries (1 .. kTinyGroups)
+  int groups;          // CTA-local group entries (1 .. kTinyGroups); 0 = many groups: every row goes to the global table
   int threads, rows_per_thread, min_ctas;
   int prefetch;        // the next step's inputs are loaded before this step's are evaluated
 };

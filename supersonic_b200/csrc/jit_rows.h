@@ -150,11 +150,11 @@ __device__ __noinline__ void jit_overflow(const GroupParams& p, int a, long long
   apply(ag, slot, v, 1ull);
   if (ag.seen != nullptr) ag.seen[slot] = 1u;
 }
-struct JitLocal {
-  unsigned long long l_key[Spec::G][jit_max1(Spec::NK)];
-  unsigned int l_fp[Spec::G];   // 32-bit fingerprints: a hit is confirmed against l_key / l_knull
-  unsigned int l_knull[Spec::G];
-  unsigned int l_slot[Spec::G];
+struct JitLocal {   // Spec::G == 0 (many groups: every row goes to the global table) keeps one unused entry
+  unsigned long long l_key[jit_max1(Spec::G)][jit_max1(Spec::NK)];
+  unsigned int l_fp[jit_max1(Spec::G)];   // 32-bit fingerprints: a hit is confirmed against l_key / l_knull
+  unsigned int l_knull[jit_max1(Spec::G)];
+  unsigned int l_slot[jit_max1(Spec::G)];
   unsigned int l_ready;
 };
 // The row's group is not among the CTA-local entries this thread knows: finds (or inserts) its slot in the global
@@ -213,6 +213,22 @@ __device__ __forceinline__ uint32_t jit_accumulate(const GroupParams& p, const J
   return 1u << AI;
 }
 
+// Spec::G == 0: one aggregate of one row straight into the global table (atomics), the function and type folded.
+template <int AI, int FN, int IN_PHYS, int OUT_PHYS, int OUT>
+__device__ __forceinline__ void jit_apply_direct(const GroupParams& p, const JitRow& s, int j, long long slot) {
+  unsigned long long v = 0;
+  if (OUT >= 0) {
+    if ((s.on[OUT < 0 ? 0 : OUT] >> j) & 1u) return;   // NULL input: no contribution
+    v = s.ov[OUT < 0 ? 0 : OUT][j];
+    if (FN != SSB_AGG_COUNT && IN_PHYS != OUT_PHYS) v = convert_value(v, IN_PHYS, OUT_PHYS);
+  }
+  AggDev ag = p.agg[AI];
+  ag.fn = FN;
+  ag.out_phys = OUT_PHYS;
+  apply(ag, slot, v, 1ull);
+  if (ag.seen != nullptr) ag.seen[slot] = 1u;
+}
+
 extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_rows(const __grid_constant__ GroupParams p,
                                                                                     const __grid_constant__ JitRun run) {
   constexpr int T = Spec::T, R = Spec::R, G = Spec::G, A = Spec::A, NK = Spec::NK;
@@ -227,9 +243,9 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
   if (tid == 0) L.l_ready = 0u;
   __syncthreads();
   unsigned int my_ready = 0;
-  unsigned int my_fp[G];
+  unsigned int my_fp[jit_max1(G)];
 #pragma unroll
-  for (int e = 0; e < G; ++e) my_fp[e] = 0;
+  for (int e = 0; e < jit_max1(G); ++e) my_fp[e] = 0;
   uint32_t fail = 0;
   const long long stride = static_cast<long long>(gridDim.x) * T * R;
   // Spec::PREFETCH = how many steps ahead the inputs are loaded (0: this step's loads are issued at the end of the
@@ -292,6 +308,18 @@ extern "C" __global__ void __launch_bounds__(Spec::T, Spec::MIN_CTAS) ssb_jit_ro
       for (int c = 0; c < NK; ++c) {
         kv[c] = 0;
         if ((s.on[c] >> j) & 1u) knull |= 1u << c; else kv[c] = s.ov[c][j];
+      }
+      if (G == 0) {   // many groups: no CTA-local entries, the row's slot in the global table takes the values
+        const long long direct = p.packed ? find_slot_packed_kv(p, (knull & 1u) != 0, kv[0]) : find_slot_generic_kv(p, kv, knull);
+        if (direct < 0) {
+          const unsigned long long d = atomicAdd(p.n_deferred, 1ull);
+          p.deferred[d] = rows_[j];
+          continue;
+        }
+#define SSB_JIT_X_DIRECT(AI, FN, IN_PHYS, OUT_PHYS, OUT, PAD) jit_apply_direct<AI, FN, IN_PHYS, OUT_PHYS, OUT>(p, s, j, direct);
+        SSB_JIT_AGGS(SSB_JIT_X_DIRECT)
+#undef SSB_JIT_X_DIRECT
+        continue;
       }
       // a cheap 32-bit fingerprint (the keys are compared in full after a hit): one multiply-add per key half
       unsigned int fp = 0x9E3779B9u + knull;

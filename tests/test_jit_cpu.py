@@ -80,3 +80,10 @@ def test_plans_outside_the_kernel_limits_are_refused(built):
     nodes, types, nullable, outputs, predicate, n_keys, aggs = _q1()
     rc, size, text = _compile(nodes, types, nullable, outputs, predicate, n_keys, aggs, groups=9)
     assert rc == 103 and size == 0 and "limits" in text
+
+
+def test_many_groups_form_compiles(built):
+    """groups = 0: no CTA-local entries, every row goes to the global table (csrc/jit_rows.h, Spec::G == 0)."""
+    rc, size, text = _compile(*_q1(), groups=0)
+    assert rc == 0 and size > 0, text[-4000:]
+    assert "G = 0" in text

@@ -1810,7 +1810,7 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
   const char* jit_rows_env = getenv("SSB200_JIT_MIN_ROWS");
   const long long jit_min_rows = jit_rows_env != nullptr ? atoll(jit_rows_env) : (1LL << 26);
   const char* jit_many_env = getenv("SSB200_JIT_MANY_GROUPS");
-  const long long jit_many_groups = jit_many_env != nullptr ? atoll(jit_many_env) : 4096;
+  const long long jit_many_groups = jit_many_env != nullptr ? atoll(jit_many_env) : 256;
   bool jit_ok = rows_feasible && !float_key && n_in <= kJitMaxIn;
   if (rows_feasible) {
     rp.n_insn = static_cast<int32_t>(prog.generic.size());
@@ -1855,8 +1855,9 @@ int ssb_group_update_program(ssb_group* g, ssb_program* sp, const ssb_column* in
     JitLaunch jl;
     bool use_jit = false;
     // few groups: CTA-local accumulators for exactly the groups seen so far; many groups (>= SSB200_JIT_MANY_GROUPS,
-    // 4096): no local entries, every row goes to the global table (atomics on a few hot groups would serialise, so the
-    // range in between keeps the materialising form)
+    // 256): no local entries, every row goes to the global table. Atomics on a few hot groups serialise -- measured per
+    // 200M rows against the materialising form (profiles/r2m_jit_many_groups.txt): 300 groups 5.9 vs 8.6 ms, 64 groups
+    // 12.4 vs 6.9 ms -- so the range in between keeps the materialising form
     const bool groups_known = g->rows_seen >= kProbeRowsFirst;
     const bool few_groups = g->n_keys == 0 || (groups_known ? g->h_counters[0] <= kTinyGroups : jit_mode == 1);
     const bool many_groups = g->n_keys > 0 && groups_known && static_cast<long long>(g->h_counters[0]) >= jit_many_groups;

@@ -105,6 +105,19 @@ def test_operation_schemas(ref, b200):
         "(group (named i32) (aggs (SUM d w2)) (scan 0))",
         "(group (named i32) (aggs (MAX b w2) (SUM u64 w3 INT32) (MIN i32 v INT64)) (scan 0))",
         "(scalar_agg (aggs (SUM f64 s) (COUNT \"\" c)) (scan 0))",
+        # round 2: DISTINCT aggregates, the spilling aggregation, Limit, Coalesce, ParseString over literals
+        "(group (named i32) (aggs (distinct COUNT ni64 c) (distinct SUM f64 s) (distinct MIN u32 m) (SUM i64 p)) (scan 0))",
+        "(group (named i32) (aggs (distinct SUM b s)) (scan 0))",
+        "(group (named i32) (aggs (distinct COUNT nope c)) (scan 0))",
+        "(scalar_agg (aggs (distinct COUNT i32 c) (distinct SUM ni32 s)) (scan 0))",
+        "(hybrid_group 1000 (named ni32 b) (aggs (distinct COUNT f64 c) (MAX u64 x)) (scan 0))",
+        "(limit 1 2 (scan 0))",
+        "(limit 0 0 (filter (col b) (named i32) (scan 0)))",
+        "(coalesce (project (named i32) (scan 0)) (project (rename (i32 again) (nf64 g)) (scan 0)))",
+        "(coalesce (project (named i32) (scan 0)) (project (named i32 f64) (scan 0)))",
+        "(compute (compound (as d (parse_string_nulling DATE (str \"2001/02/03\"))) (as x (parse_string_quiet UINT64 (str \"7\"))) "
+        "(as n (parse_string_nulling FLOAT (str \"x\"))) (col i32)) (scan 0))",
+        "(compute (parse_string_nulling INT32 (i32 5)) (scan 0))",
         "(hash_join INNER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (f64 rf)))) UNIQUE (scan 0) (scan 0))",
         "(hash_join LEFT_OUTER (named i64) (named i64) (multi (0 (named i32)) (1 (rename (f64 rf) (ni32 rn)))) NOT_UNIQUE (scan 0) (scan 0))",
         "(hash_join INNER (named i64) (named i32) (multi (0 (named i32)) (1 (rename (f64 rf)))) UNIQUE (scan 0) (scan 0))",

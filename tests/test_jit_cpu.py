@@ -87,3 +87,38 @@ def test_many_groups_form_compiles(built):
     rc, size, text = _compile(*_q1(), groups=0)
     assert rc == 0 and size > 0, text[-4000:]
     assert "G = 0" in text
+
+
+_T = {"i32": capi.INT32, "i64": capi.INT64, "u32": capi.UINT32, "u64": capi.UINT64, "f32": capi.FLOAT, "f64": capi.DOUBLE}
+
+
+@pytest.mark.parametrize("tname", sorted(_T))
+def test_every_operator_family_compiles_for_a_type(built, tname):
+    """One plan per operand type that strings together every operator family alu() folds (arithmetic incl. signaling /
+    nulling division and modulus, comparisons, three-valued logic, IF / NULLING_IF / IFNULL / IS_NULL, casts, and for the
+    integer types the bitwise operators and shifts), over nullable inputs, aggregated with SUM / MIN / MAX / COUNT: NVRTC
+    must accept the specialised source for every one of them (a plan that failed to compile would silently keep the
+    interpreting kernels on the GPU)."""
+    n = capi.node
+    t, B, I64, F64 = _T[tname], capi.BOOL, capi.INT64, capi.DOUBLE
+    integer = tname[0] in "iu"
+    nodes = [n(capi.OP_INPUT, t, [0]), n(capi.OP_INPUT, t, [1]), n(capi.OP_INPUT, I64, [2])]                 # 0 a, 1 b, 2 key
+    nodes += [n(capi.OP_ADD, t, [0, 1]), n(capi.OP_SUB, t, [3, 1]), n(capi.OP_MUL, t, [4, 0]),                # 3 4 5
+              n(capi.OP_DIV, t, [5, 1], flags=capi.NODE_ZERO_NULLS), n(capi.OP_MOD, I64 if not integer else t, [5, 1], flags=capi.NODE_ZERO_NULLS),   # 6 7
+              n(capi.OP_LT, B, [0, 1]), n(capi.OP_EQ, B, [0, 1]), n(capi.OP_GE, B, [3, 1]),                   # 8 9 10
+              n(capi.OP_AND, B, [8, 9]), n(capi.OP_OR, B, [11, 10]), n(capi.OP_NOT, B, [12]),                  # 11 12 13
+              n(capi.OP_IF, t, [13, 0, 1]), n(capi.OP_NULLING_IF, t, [8, 14, 6]), n(capi.OP_IF_NULL, t, [15, 0]),   # 14 15 16
+              n(capi.OP_IS_NULL, B, [6]), n(capi.OP_CAST, F64, [16]), n(capi.OP_CAST, I64, [18]),               # 17 18 19
+              n(capi.OP_NEGATE, I64 if tname in ("u32", "u64") else t, [0])]                                    # 20
+    outs = [2, 16, 18, 19, 20, 7]
+    if integer:
+        nodes += [n(40, t, [0, 1]), n(41, t, [21, 1]), n(42, t, [22, 0]), n(44, t, [23]), n(45, t, [24, 1]), n(46, t, [25, 1])]   # 21..26 bitwise, shifts
+        outs.append(26)
+    aggs = [(capi.AGG_SUM, 0, t, t, 1), (capi.AGG_MIN, 1, F64, F64, 1), (capi.AGG_MAX, 2, I64, I64, 1),
+            (capi.AGG_COUNT, 3, nodes[20].out_type, capi.UINT64, 1), (capi.AGG_SUM, 4, nodes[7].out_type, nodes[7].out_type, 1),
+            (capi.AGG_COUNT, -1, I64, capi.UINT64, 0)]
+    if integer:
+        aggs.append((capi.AGG_MAX, 5, t, t, 1))
+    for groups in (0, 3):
+        rc, size, text = _compile(nodes, [t, t, I64], [1, 1, 0], outs, 17, 1, aggs, groups=groups)
+        assert rc == 0 and size > 0, text[-6000:]

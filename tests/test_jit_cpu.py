@@ -3,6 +3,7 @@ plan-specialised source into an sm_100a cubin here (nvcc's runtime sibling needs
 generated code does not compile fails on the CPU suite, not on the GPU box. Values are checked on the GPU by
 tests/test_device_gpu.py::test_fused_* in their `jit` mode."""
 import ctypes as C
+import os
 
 import pytest
 
@@ -122,3 +123,27 @@ def test_every_operator_family_compiles_for_a_type(built, tname):
     for groups in (0, 3):
         rc, size, text = _compile(nodes, [t, t, I64], [1, 1, 0], outs, 17, 1, aggs, groups=groups)
         assert rc == 0 and size > 0, text[-6000:]
+
+
+def test_q1_kernel_resources_at_the_default_launch_shape(built, tmp_path, monkeypatch):
+    """The shape bench.py's Q1 leg runs (192 threads x 1 row, prefetch 1, 3 CTAs per SM): at most 84 registers per thread
+    (three CTAs of 192 threads must fit the register file) and no spills beyond the out-of-line cold paths' frames. Two rows
+    per thread with prefetch spilled and lost a factor of two (profiles/r2h_q1_jit.txt): this pins the compiled shape."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump on this box")
+    path = str(tmp_path / "q1.cubin")
+    monkeypatch.setenv("SSB200_JIT_DUMP", path)
+    for name in ("SSB200_JIT_THREADS", "SSB200_JIT_ROWS", "SSB200_JIT_PREFETCH", "SSB200_JIT_MIN_CTAS"):
+        monkeypatch.delenv(name, raising=False)
+    rc, size, text = _compile(*_q1(), groups=6)
+    assert rc == 0 and os.path.getsize(path) == size, text[-2000:]
+    assert "enum { T = 192, R = 1, G = 6, MIN_CTAS = 3, PREFETCH = 1" in text
+    usage = subprocess.run([cuobjdump, "-res-usage", path], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    m = re.search(r"Function ssb_jit_rows:\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", usage)
+    assert m, usage[-2000:]
+    regs, stack, shared, local = map(int, m.groups())
+    assert regs <= 84 and stack <= 64 and local == 0, usage[-1000:]

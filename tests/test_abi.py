@@ -65,3 +65,19 @@ def test_view_cursor_slices_like_the_reference(ref, b200, max_rows):
     a, b = ref.run("(scan 0)", [t], next_max_rows=max_rows), b200.run("(scan 0)", [t], next_max_rows=max_rows)
     same_results(a, b)
     assert a.next_calls == b.next_calls
+
+
+def test_library_sass_carries_the_blackwell_data_movement(built):
+    """The fused Compute / Filter kernel stages its column tiles with TMA bulk copies completed on mbarriers
+    (DESIGN.md 4.1): the sm_100a SASS of libssb200.so must contain UBLKCP and SYNCS, and -- none of the operators being a
+    dense contraction -- no tensor-core (UTC*MMA / HMMA) instruction."""
+    import shutil
+    import subprocess
+    from supersonic_b200 import capi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump on this box")
+    sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    assert "sm_100a" in sass or "SM100a" in sass.upper() or "EF_CUDA_SM100" in sass, sass[:500]
+    assert sass.count("UBLKCP") > 0 and sass.count("SYNCS") > 0
+    assert "UTCHMMA" not in sass and "UTCQMMA" not in sass and "HMMA" not in sass
